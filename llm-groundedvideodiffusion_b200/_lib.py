@@ -1,0 +1,90 @@
+"""ctypes binding of the C-ABI library (include/lvd_b200.h).  The library is mandatory: a missing or
+unloadable liblvd_b200.so raises -- there is no Python/torch fallback for any op behind it."""
+import ctypes
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "liblvd_b200.so")
+
+LVD_MAX_TAPS = 27
+
+
+class GemmDesc(ctypes.Structure):
+    _fields_ = [
+        ("a", ctypes.c_void_p),
+        ("a_dims", ctypes.c_int64 * 5),
+        ("a_strides", ctypes.c_int64 * 5),
+        ("a_box", ctypes.c_int32 * 5),
+        ("n_taps", ctypes.c_int32),
+        ("k_per_tap", ctypes.c_int32),
+        ("tap_off", (ctypes.c_int32 * 5) * LVD_MAX_TAPS),
+        ("b", ctypes.c_void_p),
+        ("b_mn_major", ctypes.c_int32),
+        ("block_n", ctypes.c_int32),
+        ("ldb", ctypes.c_int64),
+        ("n", ctypes.c_int32),
+        ("act", ctypes.c_int32),
+        ("out_dims", ctypes.c_int32 * 4),
+        ("rv_stride", ctypes.c_int32 * 4),
+        ("out_row_stride", ctypes.c_int64 * 4),
+        ("bias", ctypes.c_void_p),
+        ("rowvec", ctypes.c_void_p),
+        ("residual", ctypes.c_void_p),
+        ("out", ctypes.c_void_p),
+        ("ld_rowvec", ctypes.c_int64),
+        ("ld_res", ctypes.c_int64),
+        ("ld_out", ctypes.c_int64),
+        ("gamma", ctypes.c_float),
+        ("reserved", ctypes.c_int32),
+    ]
+
+
+_lib = None
+
+
+class LvdError(RuntimeError):
+    pass
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise LvdError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a). lvd_b200 has no fallback path."
+            )
+        _lib = ctypes.CDLL(LIB_PATH)
+        _lib.lvd_last_error.restype = ctypes.c_char_p
+        _lib.lvd_launch_count.restype = ctypes.c_int64
+        _declare(_lib)
+    return _lib
+
+
+def _declare(l):
+    vp, i32, i64, f32 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_float
+    l.lvd_gemm.argtypes = [ctypes.POINTER(GemmDesc), vp]
+    sigs = getattr(_declare, "extra", {})
+    for name, argtypes in sigs.items():
+        getattr(l, name).argtypes = argtypes
+    for name in EXPORTS:
+        fn = getattr(l, name)
+        if name not in ("lvd_last_error", "lvd_launch_count"):
+            fn.restype = ctypes.c_int
+
+
+# every symbol include/lvd_b200.h declares (checked by tests/test_abi.py without a GPU)
+EXPORTS = [
+    "lvd_last_error",
+    "lvd_version",
+    "lvd_launch_count",
+    "lvd_gemm",
+]
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = lib().lvd_last_error().decode("utf-8", "replace")
+        if rc == -1:
+            raise ValueError(f"lvd_b200 {what}: {msg}")
+        raise LvdError(f"lvd_b200 {what} failed (rc={rc}): {msg}")

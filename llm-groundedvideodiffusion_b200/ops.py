@@ -1,0 +1,203 @@
+"""Thin Python launch helpers over the C-ABI (one function per kernel family).
+
+Activations are 2-D fp16 CUDA tensors `[rows, C]` (channels-last; rows = ((b*F+f)*H + y)*W + x) that may be
+column slices of a wider buffer (stride(0) = ld >= C, stride(1) == 1).  torch is used for device memory and the
+current stream only; all arithmetic happens in liblvd_b200.so.
+"""
+import ctypes
+import functools
+
+import torch
+
+from . import _lib
+from ._lib import GemmDesc
+
+ACT_NONE, ACT_SILU, ACT_GEGLU = 0, 1, 2
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _check_act(t, name="tensor"):
+    if not (t.is_cuda and t.dtype == torch.float16 and t.dim() == 2 and t.stride(1) == 1):
+        raise ValueError(f"{name}: expected a 2-D fp16 CUDA tensor with unit column stride, got "
+                         f"{t.dtype} {tuple(t.shape)} strides {t.stride()} on {t.device}")
+    if t.stride(0) % 8 != 0 or t.data_ptr() % 16 != 0:
+        raise ValueError(f"{name}: row stride must be a multiple of 8 and base 16-byte aligned")
+
+
+def pick_block_n(n, act=ACT_NONE):
+    if act == ACT_GEGLU:
+        return 128
+    for bn in (256, 160, 128, 64):
+        if n % bn == 0:
+            return bn
+    raise ValueError(f"N={n} is not a multiple of 64")
+
+
+@functools.lru_cache(maxsize=None)
+def choose_box(dims, max_rows=128):
+    """Pick per-axis box extents (product <= 128) for output extents `dims` (fastest axis first) that maximise
+    the fraction of useful rows over all tiles."""
+    dims = tuple(int(d) for d in dims)
+    best = None
+
+    def rec(i, cur, rows):
+        nonlocal best
+        if i == len(dims):
+            tiles = 1
+            for d, b in zip(dims, cur):
+                tiles *= -(-d // b)
+            total = 1
+            for d in dims:
+                total *= d
+            eff = total / (tiles * 128.0)
+            key = (round(eff, 6), rows, cur[0])
+            if best is None or key > best[0]:
+                best = (key, tuple(cur))
+            return
+        d = dims[i]
+        for b in range(1, min(d, max_rows // rows, 256) + 1):
+            # only divisors, or the full extent, or power-of-two chunks: keeps the search small
+            if d % b == 0 or b == d or (b & (b - 1)) == 0:
+                rec(i + 1, cur + [b], rows * b)
+
+    rec(0, [], 1)
+    return best[1]
+
+
+def gemm_raw(*, a, a_dims, a_strides, a_box, taps, k_per_tap, w, n, out, out_dims, out_row_stride,
+             rv_stride=(0, 0, 0, 0), bias=None, act=ACT_NONE, rowvec=None, gamma=1.0, residual=None,
+             b_mn_major=False, block_n=None, ldb=None):
+    d = GemmDesc()
+    d.a = a.data_ptr()
+    for i in range(5):
+        d.a_dims[i] = int(a_dims[i])
+        d.a_strides[i] = int(a_strides[i])
+        d.a_box[i] = int(a_box[i])
+    d.n_taps = len(taps)
+    d.k_per_tap = int(k_per_tap)
+    for t, off in enumerate(taps):
+        for i in range(5):
+            d.tap_off[t][i] = int(off[i])
+    d.b = w.data_ptr()
+    d.b_mn_major = 1 if b_mn_major else 0
+    d.block_n = int(block_n or pick_block_n(n, act))
+    d.ldb = int(ldb if ldb is not None else w.stride(0))
+    d.n = int(n)
+    d.act = int(act)
+    for i in range(4):
+        d.out_dims[i] = int(out_dims[i])
+        d.rv_stride[i] = int(rv_stride[i])
+        d.out_row_stride[i] = int(out_row_stride[i])
+    d.bias = bias.data_ptr() if bias is not None else None
+    d.rowvec = rowvec.data_ptr() if rowvec is not None else None
+    d.residual = residual.data_ptr() if residual is not None else None
+    d.out = out.data_ptr()
+    d.ld_rowvec = rowvec.stride(0) if rowvec is not None else 0
+    d.ld_res = residual.stride(0) if residual is not None else 0
+    d.ld_out = out.stride(0)
+    d.gamma = float(gamma)
+    _lib.check(_lib.lib().lvd_gemm(ctypes.byref(d), _stream()), "gemm")
+    return out
+
+
+def _alloc_out(rows, n, like):
+    return torch.empty((rows, n), dtype=torch.float16, device=like.device)
+
+
+def linear(x, w, bias=None, *, act=ACT_NONE, residual=None, gamma=1.0, out=None, rowvec=None, rows_per_vec=0,
+           b_mn_major=False, n=None):
+    """out = epilogue(x @ w.T).  x [rows, K]; w [N, K] (or [K, N] when b_mn_major).  GEGLU expects the
+    value/gate-interleaved weight produced by `repack.geglu_interleave` and returns N/2 columns."""
+    _check_act(x, "x")
+    rows, k = x.shape
+    if n is None:
+        n = w.shape[1] if b_mn_major else w.shape[0]
+    n_out = n // 2 if act == ACT_GEGLU else n
+    if out is None:
+        out = _alloc_out(rows, n_out, x)
+    _check_act(out, "out")
+    ld = x.stride(0)
+    big = ld * max(rows, 1)
+    rv = (0, 0, 0, 0)
+    a_dims, a_strides, a_box = (k, rows, 1, 1, 1), (1, ld, big, big, big), (64, 128, 1, 1, 1)
+    out_dims, ors = (rows, 1, 1, 1), (1, 0, 0, 0)
+    if rowvec is not None:
+        # rows are grouped in blocks of rows_per_vec consecutive rows sharing one row-vector
+        assert rows_per_vec > 0 and rows % rows_per_vec == 0
+        bx = choose_box((rows_per_vec, rows // rows_per_vec))
+        a_dims = (k, rows_per_vec, rows // rows_per_vec, 1, 1)
+        a_strides = (1, ld, ld * rows_per_vec, big, big)
+        a_box = (64, bx[0], bx[1], 1, 1)
+        out_dims, ors, rv = (rows_per_vec, rows // rows_per_vec, 1, 1), (1, rows_per_vec, 0, 0), (0, 1, 0, 0)
+    return gemm_raw(a=x, a_dims=a_dims, a_strides=a_strides, a_box=a_box, taps=[(0, 0, 0, 0, 0)], k_per_tap=k, w=w,
+                    n=n, out=out, out_dims=out_dims, out_row_stride=ors, rv_stride=rv, bias=bias, act=act,
+                    rowvec=rowvec, gamma=gamma, residual=residual, b_mn_major=b_mn_major)
+
+
+TAPS_3X3 = [(0, dx, dy, 0, 0) for dy in (-1, 0, 1) for dx in (-1, 0, 1)]
+
+
+def conv2d_3x3(x, n_img, h, w_, wk, bias=None, *, rowvec=None, residual=None, out=None):
+    """3x3 / stride 1 / pad 1 convolution as 9 shifted TMA boxes.  x [n_img*h*w_, Cin]; wk [Cout, 9*Cin] with K
+    ordered (ky, kx, ci).  rowvec [n_img, Cout] is added per image (time-embedding projection)."""
+    _check_act(x, "x")
+    cin = x.shape[1]
+    cout = wk.shape[0]
+    assert wk.shape[1] == 9 * cin and x.shape[0] == n_img * h * w_
+    if out is None:
+        out = _alloc_out(x.shape[0], cout, x)
+    ld = x.stride(0)
+    bw, bh, bn = choose_box((w_, h, n_img))
+    return gemm_raw(a=x, a_dims=(cin, w_, h, n_img, 1), a_strides=(1, ld, ld * w_, ld * w_ * h, ld * w_ * h * n_img),
+                    a_box=(64, bw, bh, bn, 1), taps=TAPS_3X3, k_per_tap=cin, w=wk, n=cout, out=out,
+                    out_dims=(w_, h, n_img, 1), out_row_stride=(1, w_, w_ * h, 0), rv_stride=(0, 0, 1, 0), bias=bias,
+                    rowvec=rowvec, residual=residual)
+
+
+def conv2d_3x3_s2(x, n_img, h, w_, wk, bias=None, *, out=None):
+    """3x3 / stride 2 / pad 1 (diffusers Downsample2D).  The input is viewed as (2C, W/2, 2, H/2, N) so that the
+    column/row parity of each tap is a coordinate; no space-to-depth copy is made."""
+    _check_act(x, "x")
+    cin = x.shape[1]
+    cout = wk.shape[0]
+    assert h % 2 == 0 and w_ % 2 == 0 and x.stride(0) == cin, "stride-2 conv needs a dense even-sized input"
+    ho, wo = h // 2, w_ // 2
+    if out is None:
+        out = _alloc_out(n_img * ho * wo, cout, x)
+    taps = []
+    for ky in range(3):
+        pa, sy = ((1, -1), (0, 0), (1, 0))[ky]  # input row 2*oy + ky - 1 = 2*(oy+sy) + pa
+        for kx in range(3):
+            pb, sx = ((1, -1), (0, 0), (1, 0))[kx]
+            taps.append((pb * cin, sx, pa, sy, 0))
+    bw, bh, bn = choose_box((wo, ho, n_img))
+    return gemm_raw(a=x, a_dims=(2 * cin, wo, 2, ho, n_img),
+                    a_strides=(1, 2 * cin, w_ * cin, 2 * w_ * cin, h * w_ * cin), a_box=(64, bw, 1, bh, bn), taps=taps,
+                    k_per_tap=cin, w=wk, n=cout, out=out, out_dims=(wo, 1, ho, n_img),
+                    out_row_stride=(1, 0, wo, wo * ho), bias=bias)
+
+
+TAPS_T = [(0, 0, df, 0, 0) for df in (-1, 0, 1)]
+
+
+def conv_temporal(x, batch, frames, hw, wk, bias=None, *, residual=None, out=None):
+    """Conv3d (3,1,1) pad (1,0,0) over the frame axis.  x [(batch*frames)*hw, C]; wk [Cout, 3*Cin], K = (kt, ci)."""
+    _check_act(x, "x")
+    cin = x.shape[1]
+    cout = wk.shape[0]
+    assert x.shape[0] == batch * frames * hw
+    if out is None:
+        out = _alloc_out(x.shape[0], cout, x)
+    ld = x.stride(0)
+    bp, bf, bb = choose_box((hw, frames, batch))
+    return gemm_raw(a=x, a_dims=(cin, hw, frames, batch, 1),
+                    a_strides=(1, ld, ld * hw, ld * hw * frames, ld * hw * frames * batch), a_box=(64, bp, bf, bb, 1),
+                    taps=TAPS_T, k_per_tap=cin, w=wk, n=cout, out=out, out_dims=(hw, frames, batch, 1),
+                    out_row_stride=(1, hw, hw * frames, 0), bias=bias, residual=residual)

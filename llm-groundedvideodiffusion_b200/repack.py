@@ -1,0 +1,31 @@
+"""Weight repacking from the reference `state_dict` layouts to the layouts the kernels read.
+Pure data movement, done once at load time."""
+import torch
+
+
+def conv_weight_krsc(w):
+    """Conv2d weight (Cout, Cin, kh, kw) -> [Cout, kh*kw*Cin] with K ordered (ky, kx, ci)."""
+    co, ci, kh, kw = w.shape
+    return w.permute(0, 2, 3, 1).reshape(co, kh * kw * ci).contiguous()
+
+
+def tconv_weight(w):
+    """Conv3d weight (Cout, Cin, 3, 1, 1) -> [Cout, 3*Cin] with K ordered (kt, ci)."""
+    co, ci, kt = w.shape[:3]
+    return w.reshape(co, ci, kt).permute(0, 2, 1).reshape(co, kt * ci).contiguous()
+
+
+def geglu_interleave(w, b):
+    """GEGLU proj weight (8C, C) = [value rows | gate rows] -> rows regrouped per 64 so that every 128-row block is
+    [64 value rows | the matching 64 gate rows]; the GEMM epilogue then multiplies value * gelu(gate) in-tile
+    (models/attention.py:355-376)."""
+    n2, k = w.shape
+    n = n2 // 2
+    assert n % 64 == 0
+    wv, wg = w[:n].reshape(n // 64, 64, k), w[n:].reshape(n // 64, 64, k)
+    wi = torch.cat([wv, wg], dim=1).reshape(n2, k).contiguous()
+    bi = None
+    if b is not None:
+        bv, bg = b[:n].reshape(n // 64, 64), b[n:].reshape(n // 64, 64)
+        bi = torch.cat([bv, bg], dim=1).reshape(n2).contiguous()
+    return wi, bi
