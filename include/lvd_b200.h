@@ -74,6 +74,77 @@ typedef struct lvd_gemm_desc {
 
 int lvd_gemm(const lvd_gemm_desc* d, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Attention: softmax(Q K^T * scale) V, 64-wide heads, tcgen05 QK^T / PV tiles staged by TMA.
+ * Replaces F.scaled_dot_product_attention (models/attention_processor.py:406-408) and the materialising slow path
+ * baddbmm -> softmax -> bmm (models/attention_processor.py:222-258, :515-536, :553-586).
+ *
+ * mode 0 (spatial self / cross): Q rows [z][s_q] at q + column q_col0 + head*64 (row stride ld_q); K and V rows
+ *   [z / kv_z_div][s_k] of the same buffer `kv` at columns k_col0 / v_col0 (+ head*64).  kv_z_div = F lets all
+ *   frames of a video share one text K/V (the reference repeat_interleaves encoder_hidden_states instead,
+ *   unet_3d_condition.py:721-723).
+ * mode 1 (temporal): rows are ((z*frames + f)*hw + p); the sequence of pixel p is its `frames` rows
+ *   (transformer_temporal.py:142-156 permutes instead).  Q, K, V in one buffer.
+ * Output row order == Q row order; column o_col0 + head*64.
+ * Optional (s_k <= 128 only): p_full [nz, heads, s_q, s_k] fp16 = the reference's saved attention map
+ *   (attention_processor.py:553-586); p_tok [n_tok, nz, heads, s_q] = selected text-token columns only
+ *   (what utils/guidance.py:280-290 reads).
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct lvd_attn_desc {
+  const void* q;
+  const void* kv;
+  void* out;
+  void* p_full;
+  void* p_tok;
+  int64_t ld_q, ld_kv, ld_o;
+  int64_t q_width, kv_width; /* logical column counts of the q / kv buffers (TMA bounds) */
+  int64_t s_q, s_k;          /* mode 0 */
+  int64_t hw;                /* mode 1 */
+  int32_t frames;            /* mode 1 */
+  int32_t mode;
+  int32_t q_col0, k_col0, v_col0, o_col0;
+  int32_t heads, nz, kv_z_div;
+  int32_t n_tok;
+  int32_t tok_cols[16];
+  float scale;
+  int32_t reserved;
+} lvd_attn_desc;
+
+int lvd_attention(const lvd_attn_desc* d, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Normalisation (fp32 statistics, fp16 in/out, channels-last).
+ * lvd_groupnorm: x viewed [samples][rows_per_sample][channels]; statistics per (sample, group) over
+ *   rows_per_sample x channels/groups.  4-D GroupNorm of ResnetBlock2D / Transformer2DModel
+ *   (transformer_2d.py:155-160,311) -> sample = one frame; 5-D GroupNorm of diffusers TemporalConvLayer and
+ *   TransformerTemporalModel.norm (transformer_temporal.py:84-86,150) -> sample = one video (rows span frames).
+ *   silu != 0 fuses the following SiLU.  workspace: >= samples*1024*groups*8 bytes is always enough.
+ * lvd_layernorm: nn.LayerNorm over channels (models/attention.py:126,145,163).
+ * ---------------------------------------------------------------------------------------------------------- */
+int lvd_groupnorm(const void* x, int64_t ld_x, void* y, int64_t ld_y, int32_t samples, int64_t rows_per_sample,
+                  int32_t channels, int32_t groups, const void* gamma, const void* beta, float eps, int32_t silu,
+                  void* workspace, int64_t workspace_bytes, void* stream);
+int lvd_layernorm(const void* x, int64_t ld_x, void* y, int64_t ld_y, int64_t rows, int32_t channels,
+                  const void* gamma, const void* beta, float eps, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Thin ends of the UNet and small element-wise pieces.
+ * lvd_conv_in : sample (B, cin, F, H, W) NCFHW fp16 -> rows, 3x3 conv (unet_3d_condition.py:297,726-729);
+ *               weight in the reference's OIHW layout.
+ * lvd_conv_out: rows -> (B, cout, F, H, W) NCFHW (unet_3d_condition.py:424,847-854); weight [cout][ky][kx][cin].
+ * lvd_upsample2x: nearest 2x (diffusers Upsample2D's F.interpolate, unet_3d_blocks.py:610-613).
+ * lvd_timestep_embed: diffusers Timesteps(dim, flip_sin_to_cos=True, shift 0) (unet_3d_condition.py:304,712).
+ * ---------------------------------------------------------------------------------------------------------- */
+int lvd_conv_in(const void* sample, const void* weight, const void* bias, void* out, int64_t ld_out, int32_t batch,
+                int32_t cin, int32_t frames, int32_t height, int32_t width, int32_t cout, void* stream);
+int lvd_conv_out(const void* x, int64_t ld_x, const void* weight_krsc, const void* bias, void* out, int32_t batch,
+                 int32_t cin, int32_t frames, int32_t height, int32_t width, int32_t cout, void* stream);
+int lvd_upsample2x(const void* x, int64_t ld_x, void* y, int64_t ld_y, int32_t n_img, int32_t height, int32_t width,
+                   int32_t channels, void* stream);
+int lvd_timestep_embed(const void* timesteps_f32, void* out, int32_t batch, int32_t dim, void* stream);
+int lvd_silu(const void* x, void* y, int64_t n, void* stream);
+int lvd_copy_rows(const void* x, int64_t ld_x, void* y, int64_t ld_y, int64_t rows, int32_t channels, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

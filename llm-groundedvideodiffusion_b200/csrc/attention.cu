@@ -1,0 +1,393 @@
+// attention.cu -- softmax(Q K^T * scale) V on tcgen05 tensor cores with TMA-staged operands.
+//
+// One CTA = one (query tile of <=128 rows, head, batch index z).  Warp roles:
+//   warp 0     : TMA producer (Q once; K/V 128-row units through a 2-stage ring)
+//   warp 1     : MMA issuer   (S = Q K^T into TMEM cols [0,128); O_unit = P V into TMEM cols [128,192))
+//   warps 2..5 : softmax      (one query row per thread: tcgen05.ld S -> exp2 -> fp16 P into swizzled smem ->
+//                              accumulate / rescale O in registers -> fp16 store)
+// Three shapes of the reference run through it (models/attention_processor.py:344-430 fast path, :432-589 slow path):
+//   spatial self-attention  (S up to 2880+30, online softmax over several 128-column units)
+//   cross-attention         (77 text tokens: ONE unit -> exact softmax, fp16 probabilities feed P V exactly like
+//                            get_attention_scores()+bmm (:222-258,:536); optional emission of the probability map
+//                            or of selected token columns for the box-energy guidance)
+//   temporal self-attention (S = F frames; floor(128/F) pixels' sequences are packed in one tile with a
+//                            block-diagonal mask; rows are gathered straight from the channels-last activation)
+#include <atomic>
+
+#include "../../include/lvd_b200.h"
+#include "host_util.h"
+#include "ptx.cuh"
+
+namespace lvd {
+extern std::atomic<long long> g_launches;
+
+constexpr int kTile = 128 * 128;  // bytes of a 128-row x 64-half operand tile
+constexpr int kAttnThreads = 192;
+constexpr int kAttnSmem = kTile /*Q*/ + 4 * kTile /*K,V x2*/ + 2 * kTile /*P*/ + 128;
+
+struct AttnArgs {
+  CUtensorMap map_q;
+  CUtensorMap map_kv;
+  long long o_d1_stride, o_d2_stride, o_z_stride, ld_o;
+  long long p_rows;
+  __half* out;
+  __half* p_full;
+  __half* p_tok;
+  int q_col0, k_col0, v_col0, o_col0;
+  int qb1, qb2, q_dim1;
+  int q_bytes, kv_bytes;
+  int kv_same_tile, n_units, kv_total, diag_mod, kv_z_div, heads, nz;
+  int n_tok;
+  int tok_cols[16];
+  int last_cols16;
+  float scale_log2;
+  uint32_t idesc_qk_full, idesc_qk_last, idesc_pv;
+};
+
+__global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid_constant__ AttnArgs g) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t* sQ = smem;
+  uint8_t* sK = smem + kTile;      // 2 stages
+  uint8_t* sV = smem + 3 * kTile;  // 2 stages
+  uint8_t* sP = smem + 5 * kTile;  // 2 column blocks of 64
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 7 * kTile);
+  uint64_t* q_full = bars + 0;
+  uint64_t* kv_full = bars + 1;   // [2]
+  uint64_t* kv_empty = bars + 3;  // [2]
+  uint64_t* s_full = bars + 5;
+  uint64_t* p_full = bars + 6;
+  uint64_t* o_full = bars + 7;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int qt = blockIdx.x, h = blockIdx.y, z = blockIdx.z;
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+
+  if (g.q_bytes < kTile || g.kv_bytes < kTile) {
+    // partial boxes (temporal packing): rows the TMA never writes must hold finite values (0 * NaN = NaN in P V)
+    uint4 zero = make_uint4(0, 0, 0, 0);
+    for (int i = threadIdx.x; i < 5 * kTile / 16; i += kAttnThreads) reinterpret_cast<uint4*>(smem)[i] = zero;
+    fence_proxy_async_smem();
+  }
+  if (threadIdx.x == 0) {
+    mbar_init(q_full, 1);
+    mbar_init(&kv_full[0], 1);
+    mbar_init(&kv_full[1], 1);
+    mbar_init(&kv_empty[0], 1);
+    mbar_init(&kv_empty[1], 1);
+    mbar_init(s_full, 1);
+    mbar_init(p_full, 128);
+    mbar_init(o_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&g.map_q);
+    tma_prefetch_desc(&g.map_kv);
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_holder, 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+  const uint32_t tmem_s = tmem_base, tmem_o = tmem_base + 128;
+  const int zk = z / g.kv_z_div;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(q_full, static_cast<uint32_t>(g.q_bytes));
+      tma_load_4d(sQ, &g.map_q, q_full, g.q_col0 + h * 64, qt * g.qb1, 0, z);
+      for (int u = 0; u < g.n_units; ++u) {
+        const int st = u & 1;
+        mbar_wait(&kv_empty[st], ((u >> 1) & 1) ^ 1u);
+        mbar_arrive_expect_tx(&kv_full[st], static_cast<uint32_t>(2 * g.kv_bytes));
+        const int c1 = g.kv_same_tile ? qt * g.qb1 : u * 128;
+        tma_load_4d(sK + st * kTile, &g.map_kv, &kv_full[st], g.k_col0 + h * 64, c1, 0, zk);
+        tma_load_4d(sV + st * kTile, &g.map_kv, &kv_full[st], g.v_col0 + h * 64, c1, 0, zk);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      mbar_wait(q_full, 0);
+      const uint32_t q_addr = smem_u32(sQ);
+      const uint32_t p_addr = smem_u32(sP);
+      for (int u = 0; u < g.n_units; ++u) {
+        const int st = u & 1;
+        const bool last = (u == g.n_units - 1);
+        const int ncols = last ? g.last_cols16 : 128;
+        mbar_wait(&kv_full[st], (u >> 1) & 1);
+        tc_fence_after();
+        const uint32_t k_addr = smem_u32(sK + st * kTile);
+        const uint32_t v_addr = smem_u32(sV + st * kTile);
+        const uint32_t idesc_qk = last ? g.idesc_qk_last : g.idesc_qk_full;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_f16(tmem_s, make_smem_desc_sw128(q_addr + k * 32, 16, 1024),
+                   make_smem_desc_sw128(k_addr + k * 32, 16, 1024), idesc_qk, k != 0 ? 1u : 0u);
+        umma_commit(s_full);
+        mbar_wait(p_full, u & 1);
+        tc_fence_after();
+        const int ksteps = ncols / 16;
+        for (int ks = 0; ks < ksteps; ++ks) {
+          const uint64_t da = make_smem_desc_sw128(p_addr + (ks >> 2) * kTile + (ks & 3) * 32, 16, 1024);
+          const uint64_t db = make_smem_desc_sw128(v_addr + ks * 2048, 8192, 1024);  // V is MN-major: [kv][d]
+          umma_f16(tmem_o, da, db, g.idesc_pv, ks != 0 ? 1u : 0u);
+        }
+        umma_commit(o_full);
+        umma_commit(&kv_empty[st]);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const int j1 = r % g.qb1, j2 = r / g.qb1;
+    const int c1 = qt * g.qb1 + j1;
+    const bool row_valid = (j2 < g.qb2) && (c1 < g.q_dim1);
+    const int diag = g.diag_mod;
+    const int rmod = diag ? (r % diag) : 0;
+    const bool single = (g.n_units == 1);
+    const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+    const float sc = g.scale_log2;
+    float m_run = -INFINITY, l_run = 0.f;
+    float o[64];
+#pragma unroll
+    for (int i = 0; i < 64; ++i) o[i] = 0.f;
+    uint8_t* p_row = sP + r * 128;
+
+    for (int u = 0; u < g.n_units; ++u) {
+      const bool last = (u == g.n_units - 1);
+      const int ncols = last ? g.last_cols16 : 128;
+      const int nchunks = (ncols + 31) / 32;
+      int nvalid = g.kv_total - u * 128;
+      if (nvalid > 128) nvalid = 128;
+      mbar_wait(s_full, u & 1);
+      tc_fence_after();
+      // ---- pass 1: row maximum
+      float mx = -INFINITY;
+      for (int ch = 0; ch < nchunks; ++ch) {
+        uint32_t rr[32];
+        tmem_ld32(tmem_s + lane_off + ch * 32, rr);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int c = ch * 32 + i;
+          const bool ok = (c < nvalid) && (diag == 0 || (c % diag) == rmod);
+          const float s = ok ? __uint_as_float(rr[i]) * sc : -INFINITY;
+          mx = fmaxf(mx, s);
+        }
+      }
+      float m_new = fmaxf(m_run, mx);
+      if (!(m_new > -INFINITY)) m_new = 0.f;  // fully masked / garbage row: keep arithmetic finite
+      float inv = 1.f;
+      if (single) {
+        // ---- pass 2 (single-unit modes): exact denominator, so that the fp16 probabilities equal the reference's
+        float sum = 0.f;
+        for (int ch = 0; ch < nchunks; ++ch) {
+          uint32_t rr[32];
+          tmem_ld32(tmem_s + lane_off + ch * 32, rr);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int c = ch * 32 + i;
+            const bool ok = (c < nvalid) && (diag == 0 || (c % diag) == rmod);
+            sum += ok ? exp2f(__uint_as_float(rr[i]) * sc - m_new) : 0.f;
+          }
+        }
+        inv = 1.f / sum;
+      }
+      const float alpha = exp2f(m_run - m_new);
+      float psum = 0.f;
+      // ---- pass 3: probabilities -> fp16 -> swizzled smem (A operand of P V)
+      for (int ch = 0; ch < nchunks; ++ch) {
+        uint32_t rr[32];
+        tmem_ld32(tmem_s + lane_off + ch * 32, rr);
+        tmem_ld_wait();
+        float p[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int c = ch * 32 + i;
+          const bool ok = (c < nvalid) && (diag == 0 || (c % diag) == rmod);
+          const float e = ok ? exp2f(__uint_as_float(rr[i]) * sc - m_new) * inv : 0.f;
+          p[i] = e;
+          psum += e;
+        }
+        uint8_t* blk = p_row + (ch >> 1) * kTile;
+#pragma unroll
+        for (int s8 = 0; s8 < 4; ++s8) {
+          uint4 v;
+          __half2* hh = reinterpret_cast<__half2*>(&v);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) hh[i] = __floats2half2_rn(p[s8 * 8 + 2 * i], p[s8 * 8 + 2 * i + 1]);
+          const int chunk16 = ((ch & 1) * 4 + s8) ^ (r & 7);
+          *reinterpret_cast<uint4*>(blk + chunk16 * 16) = v;
+        }
+        if (single && row_valid) {
+          if (g.p_full) {
+            __half* dst = g.p_full + ((static_cast<long long>(z) * g.heads + h) * g.p_rows + c1) * g.kv_total;
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (ch * 32 + i < g.kv_total) dst[ch * 32 + i] = __float2half_rn(p[i]);
+          }
+          if (g.p_tok) {
+            for (int t = 0; t < g.n_tok; ++t) {
+              const int col = g.tok_cols[t] - ch * 32;
+              if (col >= 0 && col < 32) {
+                float pv = 0.f;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) pv = (i == col) ? p[i] : pv;
+                g.p_tok[((static_cast<long long>(t) * g.nz + z) * g.heads + h) * g.p_rows + c1] = __float2half_rn(pv);
+              }
+            }
+          }
+        }
+      }
+      l_run = l_run * alpha + psum;
+      m_run = m_new;
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(p_full);
+      // ---- O accumulation
+      mbar_wait(o_full, u & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int hlf = 0; hlf < 2; ++hlf) {
+        uint32_t rr[32];
+        tmem_ld32(tmem_o + lane_off + hlf * 32, rr);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[hlf * 32 + i] = o[hlf * 32 + i] * alpha + __uint_as_float(rr[i]);
+      }
+      tc_fence_before();
+    }
+    if (row_valid) {
+      const float fin = single ? 1.f : 1.f / l_run;
+      __half* dst = g.out + (static_cast<long long>(z) * g.o_z_stride + static_cast<long long>(j2) * g.o_d2_stride +
+                             static_cast<long long>(c1) * g.o_d1_stride) *
+                                g.ld_o +
+                    g.o_col0 + h * 64;
+#pragma unroll
+      for (int s8 = 0; s8 < 8; ++s8) {
+        uint4 v;
+        __half2* hh = reinterpret_cast<__half2*>(&v);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          hh[i] = __floats2half2_rn(o[s8 * 8 + 2 * i] * fin, o[s8 * 8 + 2 * i + 1] * fin);
+        *reinterpret_cast<uint4*>(dst + s8 * 8) = v;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+}  // namespace lvd
+
+using namespace lvd;
+
+extern "C" int lvd_attention(const lvd_attn_desc* d, void* stream) {
+  LVD_REQUIRE(d && d->q && d->kv && d->out, "lvd_attention: null pointer");
+  LVD_REQUIRE(d->heads >= 1 && d->nz >= 1 && d->kv_z_div >= 1, "lvd_attention: bad heads/nz");
+  LVD_REQUIRE(d->ld_q % 8 == 0 && d->ld_kv % 8 == 0 && d->ld_o % 8 == 0, "lvd_attention: ld must be multiples of 8");
+  LVD_REQUIRE(d->q_col0 % 8 == 0 && d->k_col0 % 8 == 0 && d->v_col0 % 8 == 0 && d->o_col0 % 8 == 0,
+              "lvd_attention: column offsets must be multiples of 8");
+  LVD_REQUIRE(d->n_tok >= 0 && d->n_tok <= 16, "lvd_attention: n_tok=%d", d->n_tok);
+  AttnArgs g;
+  memset(&g, 0, sizeof(g));
+  int rc;
+  const int64_t width_q = d->q_width, width_kv = d->kv_width;
+  if (d->mode == 0) {
+    // spatial / cross: Q [nz][s_q] rows, KV [nz/kv_z_div][s_k] rows
+    LVD_REQUIRE(d->s_q >= 1 && d->s_k >= 1, "lvd_attention: empty sequence");
+    int64_t qd[4] = {width_q, d->s_q, 1, d->nz};
+    int64_t qs[4] = {1, d->ld_q, d->ld_q * d->s_q, d->ld_q * d->s_q};
+    int qb[4] = {64, d->s_q < 128 ? (int)d->s_q : 128, 1, 1};
+    rc = encode_tmap_f16_sw128(&g.map_q, d->q, 4, qd, qs, qb);
+    if (rc) return rc;
+    const int64_t nzk = (d->nz + d->kv_z_div - 1) / d->kv_z_div;
+    int64_t kd[4] = {width_kv, d->s_k, 1, nzk};
+    int64_t ks[4] = {1, d->ld_kv, d->ld_kv * d->s_k, d->ld_kv * d->s_k};
+    int kb[4] = {64, d->s_k < 128 ? (int)d->s_k : 128, 1, 1};
+    rc = encode_tmap_f16_sw128(&g.map_kv, d->kv, 4, kd, ks, kb);
+    if (rc) return rc;
+    g.qb1 = qb[1];
+    g.qb2 = 1;
+    g.q_dim1 = static_cast<int>(d->s_q);
+    g.q_bytes = qb[1] * 128;
+    g.kv_bytes = kb[1] * 128;
+    g.kv_same_tile = 0;
+    g.n_units = static_cast<int>((d->s_k + 127) / 128);
+    g.kv_total = static_cast<int>(d->s_k);
+    g.diag_mod = 0;
+    g.o_d1_stride = 1;
+    g.o_d2_stride = 0;
+    g.o_z_stride = d->s_q;
+    g.p_rows = d->s_q;
+  } else {
+    // temporal: rows ((b*F + f)*hw + p); sequence = the F frames of pixel p; bp pixels per tile
+    const int F = d->frames;
+    LVD_REQUIRE(F >= 1 && F <= 128 && d->hw >= 1, "lvd_attention: frames=%d unsupported", F);
+    int bp = 128 / F;
+    if (bp > d->hw) bp = static_cast<int>(d->hw);
+    int64_t qd[4] = {width_q, d->hw, F, d->nz};
+    int64_t qs[4] = {1, d->ld_q, d->ld_q * d->hw, d->ld_q * d->hw * F};
+    int qb[4] = {64, bp, F, 1};
+    rc = encode_tmap_f16_sw128(&g.map_q, d->q, 4, qd, qs, qb);
+    if (rc) return rc;
+    int64_t kd[4] = {width_kv, d->hw, F, d->nz};
+    int64_t ks[4] = {1, d->ld_kv, d->ld_kv * d->hw, d->ld_kv * d->hw * F};
+    rc = encode_tmap_f16_sw128(&g.map_kv, d->kv, 4, kd, ks, qb);
+    if (rc) return rc;
+    g.qb1 = bp;
+    g.qb2 = F;
+    g.q_dim1 = static_cast<int>(d->hw);
+    g.q_bytes = bp * F * 128;
+    g.kv_bytes = bp * F * 128;
+    g.kv_same_tile = 1;
+    g.n_units = 1;
+    g.kv_total = bp * F;
+    g.diag_mod = bp;
+    g.o_d1_stride = 1;
+    g.o_d2_stride = d->hw;
+    g.o_z_stride = static_cast<long long>(F) * d->hw;
+    g.p_rows = d->hw;
+    LVD_REQUIRE(d->kv_z_div == 1, "lvd_attention: temporal mode has no kv broadcast");
+  }
+  LVD_REQUIRE((!d->p_full && !d->p_tok) || g.n_units == 1, "lvd_attention: probability output needs s_k <= 128");
+  const int last_valid = g.kv_total - (g.n_units - 1) * 128;
+  g.last_cols16 = (last_valid + 15) / 16 * 16;
+  g.q_col0 = d->q_col0;
+  g.k_col0 = d->k_col0;
+  g.v_col0 = d->v_col0;
+  g.o_col0 = d->o_col0;
+  g.kv_z_div = d->kv_z_div;
+  g.heads = d->heads;
+  g.nz = d->nz;
+  g.ld_o = d->ld_o;
+  g.out = static_cast<__half*>(d->out);
+  g.p_full = static_cast<__half*>(d->p_full);
+  g.p_tok = static_cast<__half*>(d->p_tok);
+  g.n_tok = d->n_tok;
+  for (int i = 0; i < d->n_tok; ++i) g.tok_cols[i] = d->tok_cols[i];
+  g.scale_log2 = d->scale * 1.4426950408889634f;
+  g.idesc_qk_full = make_idesc_f16(128, 128, 0, 0);
+  g.idesc_qk_last = make_idesc_f16(128, static_cast<uint32_t>(g.last_cols16), 0, 0);
+  g.idesc_pv = make_idesc_f16(128, 64, 0, 1);
+  static bool attr = false;
+  if (!attr) {
+    LVD_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
+    attr = true;
+  }
+  const int q_tiles = (g.q_dim1 + g.qb1 - 1) / g.qb1;
+  dim3 grid(q_tiles, d->heads, d->nz);
+  LVD_REQUIRE(d->heads <= 65535 && d->nz <= 65535, "lvd_attention: grid too large");
+  attention_kernel<<<grid, kAttnThreads, kAttnSmem, static_cast<cudaStream_t>(stream)>>>(g);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  LVD_CHECK_CUDA(cudaGetLastError());
+  return LVD_OK;
+}

@@ -1,0 +1,267 @@
+// eltwise.cu -- small HBM-bound kernels around the tensor-core path: conv_in / conv_out (4-channel ends of the
+// UNet, too thin for a tensor-core tile), nearest-2x upsample, timestep sinusoid, SiLU, latent/CFG/scheduler math.
+#include <atomic>
+
+#include "../../include/lvd_b200.h"
+#include "host_util.h"
+#include "ptx.cuh"
+
+namespace lvd {
+extern std::atomic<long long> g_launches;
+
+// ---------------------------------------------------------------------------------------------- conv_in
+// sample (B, Cin<=8, F, H, W) fp16 NCFHW -> rows [(b*F+f)*H*W + p, Cout] ; 3x3 pad 1 (unet_3d_condition.py:297,726-729)
+// One thread = one pixel x 8 output channels; weights [Cout][Cin][3][3] + bias staged in shared memory.
+__global__ void conv_in_kernel(const __half* __restrict__ x, const __half* __restrict__ w,
+                               const __half* __restrict__ bias, __half* __restrict__ out, long long ld_out, int B,
+                               int Cin, int F, int H, int W, int Cout) {
+  extern __shared__ __half s_w[];  // [Cout*Cin*9] + [Cout]
+  const int wn = Cout * Cin * 9;
+  for (int i = threadIdx.x; i < wn; i += blockDim.x) s_w[i] = w[i];
+  for (int i = threadIdx.x; i < Cout; i += blockDim.x) s_w[wn + i] = bias[i];
+  __syncthreads();
+  const int cvec = Cout / 8;
+  const long long total = static_cast<long long>(B) * F * H * W * cvec;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int cv = static_cast<int>(idx % cvec);
+    long long p = idx / cvec;
+    const int xx = static_cast<int>(p % W);
+    p /= W;
+    const int yy = static_cast<int>(p % H);
+    p /= H;
+    const int f = static_cast<int>(p % F);
+    const int b = static_cast<int>(p / F);
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    for (int ci = 0; ci < Cin; ++ci) {
+      const __half* xp = x + ((static_cast<long long>(b) * Cin + ci) * F + f) * H * W;
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        const int iy = yy + ky - 1;
+        if (iy < 0 || iy >= H) continue;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const int ix = xx + kx - 1;
+          if (ix < 0 || ix >= W) continue;
+          const float v = __half2float(xp[iy * W + ix]);
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            acc[i] += v * __half2float(s_w[((cv * 8 + i) * Cin + ci) * 9 + ky * 3 + kx]);
+        }
+      }
+    }
+    const long long row = ((static_cast<long long>(b) * F + f) * H + yy) * W + xx;
+    uint4 u;
+    __half2* h = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      h[i] = __floats2half2_rn(acc[2 * i] + __half2float(s_w[wn + cv * 8 + 2 * i]),
+                               acc[2 * i + 1] + __half2float(s_w[wn + cv * 8 + 2 * i + 1]));
+    *reinterpret_cast<uint4*>(out + row * ld_out + cv * 8) = u;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- conv_out
+// rows [(b*F+f)*H*W + p, Cin] -> (B, Cout<=8, F, H, W) NCFHW ; 3x3 pad 1 (unet_3d_condition.py:424,847-854).
+// One warp per output pixel: lanes split the input channels, shuffle-reduce the Cout sums.
+__global__ void conv_out_kernel(const __half* __restrict__ x, long long ld_x, const __half* __restrict__ wk,
+                                const __half* __restrict__ bias, __half* __restrict__ out, int B, int Cin, int F, int H,
+                                int W, int Cout) {
+  extern __shared__ __half s_wo[];  // [Cout][9][Cin]  (K ordered ky,kx,ci like every other conv here)
+  const int wn = Cout * 9 * Cin;
+  for (int i = threadIdx.x; i < wn; i += blockDim.x) s_wo[i] = wk[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const long long npix = static_cast<long long>(B) * F * H * W;
+  const long long warps_total = static_cast<long long>(gridDim.x) * (blockDim.x >> 5);
+  for (long long pix = blockIdx.x * static_cast<long long>(blockDim.x >> 5) + (threadIdx.x >> 5); pix < npix;
+       pix += warps_total) {
+    long long p = pix;
+    const int xx = static_cast<int>(p % W);
+    p /= W;
+    const int yy = static_cast<int>(p % H);
+    p /= H;  // p = b*F + f
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    for (int ky = 0; ky < 3; ++ky) {
+      const int iy = yy + ky - 1;
+      if (iy < 0 || iy >= H) continue;
+      for (int kx = 0; kx < 3; ++kx) {
+        const int ix = xx + kx - 1;
+        if (ix < 0 || ix >= W) continue;
+        const __half* xr = x + ((p * H + iy) * W + ix) * ld_x;
+        for (int c = lane * 2; c < Cin; c += 64) {
+          const float2 v = __half22float2(*reinterpret_cast<const __half2*>(xr + c));
+          for (int co = 0; co < Cout; ++co) {
+            const float2 ww =
+                __half22float2(*reinterpret_cast<const __half2*>(&s_wo[(co * 9 + ky * 3 + kx) * Cin + c]));
+            acc[co] += v.x * ww.x + v.y * ww.y;
+          }
+        }
+      }
+    }
+    for (int co = 0; co < Cout; ++co) {
+      float a = acc[co];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+      acc[co] = a;
+    }
+    if (lane < Cout) {
+      const int b = static_cast<int>(p / F), f = static_cast<int>(p % F);
+      float a = 0.f;
+      for (int co = 0; co < Cout; ++co)
+        if (co == lane) a = acc[co];
+      out[(((static_cast<long long>(b) * Cout + lane) * F + f) * H + yy) * W + xx] =
+          __float2half_rn(a + __half2float(bias[lane]));
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- upsample 2x nearest
+__global__ void upsample2x_kernel(const __half* __restrict__ x, long long ld_x, __half* __restrict__ y, long long ld_y,
+                                  int n_img, int H, int W, int C) {
+  const int cvec = C / 8;
+  const long long total = static_cast<long long>(n_img) * (2 * H) * (2 * W) * cvec;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int cv = static_cast<int>(idx % cvec);
+    long long p = idx / cvec;
+    const int ox = static_cast<int>(p % (2 * W));
+    p /= 2 * W;
+    const int oy = static_cast<int>(p % (2 * H));
+    const long long n = p / (2 * H);
+    const uint4 v = *reinterpret_cast<const uint4*>(x + ((n * H + (oy >> 1)) * W + (ox >> 1)) * ld_x + cv * 8);
+    *reinterpret_cast<uint4*>(y + ((n * 2 * H + oy) * 2 * W + ox) * ld_y + cv * 8) = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- timestep sinusoid
+// diffusers Timesteps(dim, flip_sin_to_cos=True, downscale_freq_shift=0) (unet_3d_condition.py:304,712-713):
+// out[b, i] = cos(t_b * f_i), out[b, half + i] = sin(t_b * f_i), f_i = exp(-ln(10000) * i / half); fp32 -> fp16.
+__global__ void timestep_embed_kernel(const float* __restrict__ t, __half* __restrict__ out, int B, int dim) {
+  const int half = dim / 2;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < B * half; idx += gridDim.x * blockDim.x) {
+    const int b = idx / half, i = idx % half;
+    const float freq = expf(-9.210340371976184f * static_cast<float>(i) / static_cast<float>(half));
+    const float a = t[b] * freq;
+    out[b * dim + i] = __float2half_rn(cosf(a));
+    out[b * dim + half + i] = __float2half_rn(sinf(a));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- y = silu(x) (fp16)
+__global__ void silu_kernel(const __half* __restrict__ x, __half* __restrict__ y, long long n) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float v = __half2float(x[i]);
+    y[i] = __float2half_rn(v / (1.0f + expf(-v)));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- strided row copy
+__global__ void copy_rows_kernel(const __half* __restrict__ x, long long ld_x, __half* __restrict__ y, long long ld_y,
+                                 long long rows, int C) {
+  const int cvec = C / 8;
+  const long long total = rows * cvec;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = idx / cvec;
+    const int cv = static_cast<int>(idx % cvec);
+    *reinterpret_cast<uint4*>(y + r * ld_y + cv * 8) = *reinterpret_cast<const uint4*>(x + r * ld_x + cv * 8);
+  }
+}
+
+static unsigned grid_for(long long total, int threads) {
+  long long b = (total + threads - 1) / threads;
+  const long long cap = 32LL * num_sms();
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return static_cast<unsigned>(b);
+}
+
+}  // namespace lvd
+
+using namespace lvd;
+
+extern "C" int lvd_conv_in(const void* sample, const void* weight, const void* bias, void* out, int64_t ld_out,
+                           int32_t batch, int32_t cin, int32_t frames, int32_t height, int32_t width, int32_t cout,
+                           void* stream) {
+  LVD_REQUIRE(sample && weight && bias && out, "lvd_conv_in: null pointer");
+  LVD_REQUIRE(cin >= 1 && cin <= 8 && cout % 8 == 0 && cout <= 1024 && ld_out % 8 == 0, "lvd_conv_in: bad channels");
+  const long long total = static_cast<long long>(batch) * frames * height * width * (cout / 8);
+  const size_t smem = (static_cast<size_t>(cout) * cin * 9 + cout) * sizeof(__half);
+  static bool attr = false;
+  if (!attr) {
+    LVD_CHECK_CUDA(cudaFuncSetAttribute(conv_in_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    attr = true;
+  }
+  conv_in_kernel<<<grid_for(total, 256), 256, smem, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __half*>(sample), static_cast<const __half*>(weight), static_cast<const __half*>(bias),
+      static_cast<__half*>(out), ld_out, batch, cin, frames, height, width, cout);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  LVD_CHECK_CUDA(cudaGetLastError());
+  return LVD_OK;
+}
+
+extern "C" int lvd_conv_out(const void* x, int64_t ld_x, const void* weight_krsc, const void* bias, void* out,
+                            int32_t batch, int32_t cin, int32_t frames, int32_t height, int32_t width, int32_t cout,
+                            void* stream) {
+  LVD_REQUIRE(x && weight_krsc && bias && out, "lvd_conv_out: null pointer");
+  LVD_REQUIRE(cout >= 1 && cout <= 8 && cin % 2 == 0 && ld_x % 8 == 0, "lvd_conv_out: bad channels");
+  const size_t smem = static_cast<size_t>(cout) * 9 * cin * sizeof(__half);
+  LVD_REQUIRE(smem <= 160 * 1024, "lvd_conv_out: weights do not fit shared memory");
+  static bool attr = false;
+  if (!attr) {
+    LVD_CHECK_CUDA(cudaFuncSetAttribute(conv_out_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    attr = true;
+  }
+  const long long npix = static_cast<long long>(batch) * frames * height * width;
+  conv_out_kernel<<<grid_for(npix * 32, 256), 256, smem, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __half*>(x), ld_x, static_cast<const __half*>(weight_krsc), static_cast<const __half*>(bias),
+      static_cast<__half*>(out), batch, cin, frames, height, width, cout);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  LVD_CHECK_CUDA(cudaGetLastError());
+  return LVD_OK;
+}
+
+extern "C" int lvd_upsample2x(const void* x, int64_t ld_x, void* y, int64_t ld_y, int32_t n_img, int32_t height,
+                              int32_t width, int32_t channels, void* stream) {
+  LVD_REQUIRE(x && y && channels % 8 == 0 && ld_x % 8 == 0 && ld_y % 8 == 0, "lvd_upsample2x: bad arguments");
+  const long long total = static_cast<long long>(n_img) * 4 * height * width * (channels / 8);
+  upsample2x_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __half*>(x), ld_x, static_cast<__half*>(y), ld_y, n_img, height, width, channels);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  LVD_CHECK_CUDA(cudaGetLastError());
+  return LVD_OK;
+}
+
+extern "C" int lvd_timestep_embed(const void* timesteps_f32, void* out, int32_t batch, int32_t dim, void* stream) {
+  LVD_REQUIRE(timesteps_f32 && out && dim % 2 == 0, "lvd_timestep_embed: bad arguments");
+  timestep_embed_kernel<<<grid_for(batch * (dim / 2), 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const float*>(timesteps_f32), static_cast<__half*>(out), batch, dim);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  LVD_CHECK_CUDA(cudaGetLastError());
+  return LVD_OK;
+}
+
+extern "C" int lvd_silu(const void* x, void* y, int64_t n, void* stream) {
+  LVD_REQUIRE(x && y, "lvd_silu: null pointer");
+  silu_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __half*>(x), static_cast<__half*>(y), n);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  LVD_CHECK_CUDA(cudaGetLastError());
+  return LVD_OK;
+}
+
+extern "C" int lvd_copy_rows(const void* x, int64_t ld_x, void* y, int64_t ld_y, int64_t rows, int32_t channels,
+                             void* stream) {
+  LVD_REQUIRE(x && y && channels % 8 == 0 && ld_x % 8 == 0 && ld_y % 8 == 0, "lvd_copy_rows: bad arguments");
+  copy_rows_kernel<<<grid_for(rows * (channels / 8), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __half*>(x), ld_x, static_cast<__half*>(y), ld_y, rows, channels);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  LVD_CHECK_CUDA(cudaGetLastError());
+  return LVD_OK;
+}

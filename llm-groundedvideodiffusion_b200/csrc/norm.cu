@@ -1,0 +1,258 @@
+// norm.cu -- GroupNorm (4-D per-frame and 5-D cross-frame statistics) and LayerNorm on channels-last fp16.
+// HBM/L2-bound: 16-byte vector loads, fp32 statistics, warp-shuffle / shared-memory reductions.
+#include <atomic>
+
+#include "../../include/lvd_b200.h"
+#include "host_util.h"
+#include "ptx.cuh"
+
+namespace lvd {
+extern std::atomic<long long> g_launches;
+
+__device__ __forceinline__ void ld8(const __half* p, float (&v)[8]) {
+  uint4 u = *reinterpret_cast<const uint4*>(p);
+  const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 f = __half22float2(h[i]);
+    v[2 * i] = f.x;
+    v[2 * i + 1] = f.y;
+  }
+}
+__device__ __forceinline__ void st8(__half* p, const float (&v)[8]) {
+  uint4 u;
+  __half2* h = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+
+// ------------------------------------------------------------------------------------------------ GroupNorm
+// x is viewed as [samples][rows_per_sample][C] (row stride ld).  4-D GroupNorm: sample = one frame image;
+// 5-D GroupNorm (TemporalConvLayer / TransformerTemporalModel): sample = one video, rows span all frames.
+// Pass 1 writes per-(sample, chunk, group) partial {sum, sumsq}; pass 2 folds the chunks (deterministic order),
+// normalises, applies the affine and optional SiLU.  Thread -> 8-channel vector mapping is fixed so the
+// per-channel accumulators / affine live in registers.
+__global__ void gn_stats_kernel(const __half* __restrict__ x, long long ld, long long rows_per_sample, int C, int G,
+                                int chunks, float* __restrict__ partial) {
+  extern __shared__ float s_acc[];  // [2*C]
+  const int vpr = C >> 3;
+  const int rpp = blockDim.x / vpr;  // rows per pass
+  const int v = threadIdx.x % vpr;
+  const int rsub = threadIdx.x / vpr;
+  const int chunk = blockIdx.x, s = blockIdx.y;
+  const long long rows_per_chunk = (rows_per_sample + chunks - 1) / chunks;
+  const long long r0 = chunk * rows_per_chunk;
+  long long r1 = r0 + rows_per_chunk;
+  if (r1 > rows_per_sample) r1 = rows_per_sample;
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) s_acc[i] = 0.f;
+  __syncthreads();
+  float sum[8], sq[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) sum[i] = sq[i] = 0.f;
+  if (rsub < rpp) {
+    const __half* base = x + (s * rows_per_sample) * ld + v * 8;
+    for (long long r = r0 + rsub; r < r1; r += rpp) {
+      float t[8];
+      ld8(base + r * ld, t);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        sum[i] += t[i];
+        sq[i] += t[i] * t[i];
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      atomicAdd(&s_acc[v * 8 + i], sum[i]);
+      atomicAdd(&s_acc[C + v * 8 + i], sq[i]);
+    }
+  }
+  __syncthreads();
+  const int cpg = C / G;
+  for (int g = threadIdx.x; g < G; g += blockDim.x) {
+    float a = 0.f, b = 0.f;
+    for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+      a += s_acc[c];
+      b += s_acc[C + c];
+    }
+    float* o = partial + ((static_cast<long long>(s) * chunks + chunk) * G + g) * 2;
+    o[0] = a;
+    o[1] = b;
+  }
+}
+
+__global__ void gn_apply_kernel(const __half* __restrict__ x, long long ld_x, __half* __restrict__ y, long long ld_y,
+                                long long rows_per_sample, int C, int G, int chunks_stats,
+                                const float* __restrict__ partial, const __half* __restrict__ gamma,
+                                const __half* __restrict__ beta, float eps, int silu, int chunks) {
+  __shared__ float s_mean[64], s_rstd[64];
+  const int vpr = C >> 3;
+  const int rpp = blockDim.x / vpr;
+  const int v = threadIdx.x % vpr;
+  const int rsub = threadIdx.x / vpr;
+  const int chunk = blockIdx.x, s = blockIdx.y;
+  const int cpg = C / G;
+  for (int g = threadIdx.x; g < G; g += blockDim.x) {
+    float a = 0.f, b = 0.f;
+    for (int k = 0; k < chunks_stats; ++k) {
+      const float* p = partial + ((static_cast<long long>(s) * chunks_stats + k) * G + g) * 2;
+      a += p[0];
+      b += p[1];
+    }
+    const float n = static_cast<float>(rows_per_sample) * cpg;
+    const float mean = a / n;
+    float var = b / n - mean * mean;
+    var = var > 0.f ? var : 0.f;
+    s_mean[g] = mean;
+    s_rstd[g] = rsqrtf(var + eps);
+  }
+  __syncthreads();
+  if (rsub >= rpp) return;
+  float ga[8], be[8], mu[8], rs[8];
+  {
+    float t[8];
+    ld8(gamma + v * 8, t);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) ga[i] = t[i];
+    ld8(beta + v * 8, t);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      be[i] = t[i];
+      const int g = (v * 8 + i) / cpg;
+      mu[i] = s_mean[g];
+      rs[i] = s_rstd[g];
+    }
+  }
+  const long long rows_per_chunk = (rows_per_sample + chunks - 1) / chunks;
+  const long long r0 = chunk * rows_per_chunk;
+  long long r1 = r0 + rows_per_chunk;
+  if (r1 > rows_per_sample) r1 = rows_per_sample;
+  const __half* xb = x + (s * rows_per_sample) * ld_x + v * 8;
+  __half* yb = y + (s * rows_per_sample) * ld_y + v * 8;
+  for (long long r = r0 + rsub; r < r1; r += rpp) {
+    float t[8];
+    ld8(xb + r * ld_x, t);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float o = round_h((t[i] - mu[i]) * rs[i] * ga[i] + be[i]);
+      if (silu) o = o / (1.0f + expf(-o));
+      t[i] = o;
+    }
+    st8(yb + r * ld_y, t);
+  }
+}
+
+static int gn_threads(int C) {
+  const int vpr = C / 8;
+  int rpp = 256 / vpr;
+  if (rpp < 1) rpp = 1;
+  return rpp * vpr;
+}
+
+// ------------------------------------------------------------------------------------------------ LayerNorm
+// One warp per row; the row stays in registers (C <= 2048), exact two-pass mean / variance in fp32.
+constexpr int kLnMaxVec = 8;  // 8 vectors of 8 halves per lane -> C <= 2048
+__global__ void layernorm_kernel(const __half* __restrict__ x, long long ld_x, __half* __restrict__ y, long long ld_y,
+                                 long long rows, int C, const __half* __restrict__ gamma,
+                                 const __half* __restrict__ beta, float eps) {
+  const int lane = threadIdx.x & 31;
+  const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int vpr = C >> 3;
+  float vals[kLnMaxVec][8];
+  float sum = 0.f;
+  const __half* xr = x + row * ld_x;
+#pragma unroll
+  for (int k = 0; k < kLnMaxVec; ++k) {
+    const int v = lane + k * 32;
+    if (v < vpr) {
+      ld8(xr + v * 8, vals[k]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) sum += vals[k][i];
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mean = sum / C;
+  float sq = 0.f;
+#pragma unroll
+  for (int k = 0; k < kLnMaxVec; ++k) {
+    const int v = lane + k * 32;
+    if (v < vpr) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float d = vals[k][i] - mean;
+        sq += d * d;
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  const float rstd = rsqrtf(sq / C + eps);
+  __half* yr = y + row * ld_y;
+#pragma unroll
+  for (int k = 0; k < kLnMaxVec; ++k) {
+    const int v = lane + k * 32;
+    if (v < vpr) {
+      float ga[8], be[8], o[8];
+      ld8(gamma + v * 8, ga);
+      ld8(beta + v * 8, be);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = (vals[k][i] - mean) * rstd * ga[i] + be[i];
+      st8(yr + v * 8, o);
+    }
+  }
+}
+
+}  // namespace lvd
+
+using namespace lvd;
+
+extern "C" int lvd_groupnorm(const void* x, int64_t ld_x, void* y, int64_t ld_y, int32_t samples,
+                             int64_t rows_per_sample, int32_t channels, int32_t groups, const void* gamma,
+                             const void* beta, float eps, int32_t silu, void* workspace, int64_t workspace_bytes,
+                             void* stream) {
+  LVD_REQUIRE(x && y && gamma && beta && workspace, "lvd_groupnorm: null pointer");
+  LVD_REQUIRE(channels % 8 == 0 && channels % groups == 0 && groups <= 64 && channels <= 4096,
+              "lvd_groupnorm: C=%d G=%d unsupported", channels, groups);
+  LVD_REQUIRE(ld_x % 8 == 0 && ld_y % 8 == 0, "lvd_groupnorm: ld must be a multiple of 8");
+  LVD_REQUIRE(samples >= 1 && rows_per_sample >= 1, "lvd_groupnorm: empty input");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // enough CTAs to fill 148 SMs a few times over, but at least ~64 rows per chunk
+  long long chunks = (4LL * num_sms() + samples - 1) / samples;
+  const long long max_chunks = (rows_per_sample + 63) / 64;
+  if (chunks > max_chunks) chunks = max_chunks;
+  if (chunks < 1) chunks = 1;
+  if (chunks > 1024) chunks = 1024;
+  const long long need = static_cast<long long>(samples) * chunks * groups * 2 * sizeof(float);
+  LVD_REQUIRE(workspace_bytes >= need, "lvd_groupnorm: workspace %lld < %lld bytes", (long long)workspace_bytes, need);
+  const int threads = gn_threads(channels);
+  LVD_REQUIRE(threads <= 1024, "lvd_groupnorm: C=%d too wide", channels);
+  dim3 grid(static_cast<unsigned>(chunks), static_cast<unsigned>(samples));
+  gn_stats_kernel<<<grid, threads, 2 * channels * sizeof(float), st>>>(
+      static_cast<const __half*>(x), ld_x, rows_per_sample, channels, groups, static_cast<int>(chunks),
+      static_cast<float*>(workspace));
+  gn_apply_kernel<<<grid, threads, 0, st>>>(static_cast<const __half*>(x), ld_x, static_cast<__half*>(y), ld_y,
+                                            rows_per_sample, channels, groups, static_cast<int>(chunks),
+                                            static_cast<const float*>(workspace), static_cast<const __half*>(gamma),
+                                            static_cast<const __half*>(beta), eps, silu, static_cast<int>(chunks));
+  g_launches.fetch_add(2, std::memory_order_relaxed);
+  LVD_CHECK_CUDA(cudaGetLastError());
+  return LVD_OK;
+}
+
+extern "C" int lvd_layernorm(const void* x, int64_t ld_x, void* y, int64_t ld_y, int64_t rows, int32_t channels,
+                             const void* gamma, const void* beta, float eps, void* stream) {
+  LVD_REQUIRE(x && y && gamma && beta, "lvd_layernorm: null pointer");
+  LVD_REQUIRE(channels % 8 == 0 && channels <= kLnMaxVec * 256, "lvd_layernorm: C=%d unsupported", channels);
+  LVD_REQUIRE(ld_x % 8 == 0 && ld_y % 8 == 0, "lvd_layernorm: ld must be a multiple of 8");
+  if (rows <= 0) return LVD_OK;
+  const int warps = 8;
+  const long long blocks = (rows + warps - 1) / warps;
+  layernorm_kernel<<<static_cast<unsigned>(blocks), warps * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __half*>(x), ld_x, static_cast<__half*>(y), ld_y, rows, channels,
+      static_cast<const __half*>(gamma), static_cast<const __half*>(beta), eps);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  LVD_CHECK_CUDA(cudaGetLastError());
+  return LVD_OK;
+}
