@@ -39,6 +39,37 @@ class GemmDesc(ctypes.Structure):
     ]
 
 
+class AttnDesc(ctypes.Structure):
+    _fields_ = [
+        ("q", ctypes.c_void_p),
+        ("kv", ctypes.c_void_p),
+        ("out", ctypes.c_void_p),
+        ("p_full", ctypes.c_void_p),
+        ("p_tok", ctypes.c_void_p),
+        ("ld_q", ctypes.c_int64),
+        ("ld_kv", ctypes.c_int64),
+        ("ld_o", ctypes.c_int64),
+        ("q_width", ctypes.c_int64),
+        ("kv_width", ctypes.c_int64),
+        ("s_q", ctypes.c_int64),
+        ("s_k", ctypes.c_int64),
+        ("hw", ctypes.c_int64),
+        ("frames", ctypes.c_int32),
+        ("mode", ctypes.c_int32),
+        ("q_col0", ctypes.c_int32),
+        ("k_col0", ctypes.c_int32),
+        ("v_col0", ctypes.c_int32),
+        ("o_col0", ctypes.c_int32),
+        ("heads", ctypes.c_int32),
+        ("nz", ctypes.c_int32),
+        ("kv_z_div", ctypes.c_int32),
+        ("n_tok", ctypes.c_int32),
+        ("tok_cols", ctypes.c_int32 * 16),
+        ("scale", ctypes.c_float),
+        ("reserved", ctypes.c_int32),
+    ]
+
+
 _lib = None
 
 
@@ -64,9 +95,15 @@ def lib():
 def _declare(l):
     vp, i32, i64, f32 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_float
     l.lvd_gemm.argtypes = [ctypes.POINTER(GemmDesc), vp]
-    sigs = getattr(_declare, "extra", {})
-    for name, argtypes in sigs.items():
-        getattr(l, name).argtypes = argtypes
+    l.lvd_attention.argtypes = [ctypes.POINTER(AttnDesc), vp]
+    l.lvd_groupnorm.argtypes = [vp, i64, vp, i64, i32, i64, i32, i32, vp, vp, f32, i32, vp, i64, vp]
+    l.lvd_layernorm.argtypes = [vp, i64, vp, i64, i64, i32, vp, vp, f32, vp]
+    l.lvd_conv_in.argtypes = [vp, vp, vp, vp, i64, i32, i32, i32, i32, i32, i32, vp]
+    l.lvd_conv_out.argtypes = [vp, i64, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]
+    l.lvd_upsample2x.argtypes = [vp, i64, vp, i64, i32, i32, i32, i32, vp]
+    l.lvd_timestep_embed.argtypes = [vp, vp, i32, i32, vp]
+    l.lvd_silu.argtypes = [vp, vp, i64, vp]
+    l.lvd_copy_rows.argtypes = [vp, i64, vp, i64, i64, i32, vp]
     for name in EXPORTS:
         fn = getattr(l, name)
         if name not in ("lvd_last_error", "lvd_launch_count"):
@@ -79,6 +116,15 @@ EXPORTS = [
     "lvd_version",
     "lvd_launch_count",
     "lvd_gemm",
+    "lvd_attention",
+    "lvd_groupnorm",
+    "lvd_layernorm",
+    "lvd_conv_in",
+    "lvd_conv_out",
+    "lvd_upsample2x",
+    "lvd_timestep_embed",
+    "lvd_silu",
+    "lvd_copy_rows",
 ]
 
 

@@ -201,3 +201,123 @@ def conv_temporal(x, batch, frames, hw, wk, bias=None, *, residual=None, out=Non
                     a_strides=(1, ld, ld * hw, ld * hw * frames, ld * hw * frames * batch), a_box=(64, bp, bf, bb, 1),
                     taps=TAPS_T, k_per_tap=cin, w=wk, n=cout, out=out, out_dims=(hw, frames, batch, 1),
                     out_row_stride=(1, hw, hw * frames, 0), bias=bias, residual=residual)
+
+
+# ----------------------------------------------------------------------------------------------- normalisation
+_gn_ws = {}
+
+
+def _gn_workspace(dev, samples, groups):
+    need = samples * 1024 * groups * 8
+    ws = _gn_ws.get(dev)
+    if ws is None or ws.numel() < need:
+        ws = torch.empty(max(need, 1 << 22), dtype=torch.uint8, device=dev)
+        _gn_ws[dev] = ws
+    return ws
+
+
+def groupnorm(x, samples, gamma, beta, eps, *, groups=32, silu=False, out=None):
+    """GroupNorm (+ optional SiLU) with statistics per (sample, group); x [samples*rows_per_sample, C]."""
+    _check_act(x, "x")
+    rows, c = x.shape
+    assert rows % samples == 0
+    if out is None:
+        out = _alloc_out(rows, c, x)
+    ws = _gn_workspace(x.device, samples, groups)
+    _lib.check(_lib.lib().lvd_groupnorm(x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), samples,
+                                        rows // samples, c, groups, gamma.data_ptr(), beta.data_ptr(), float(eps),
+                                        1 if silu else 0, ws.data_ptr(), ws.numel(), _stream()), "groupnorm")
+    return out
+
+
+def layernorm(x, gamma, beta, eps=1e-5, out=None):
+    _check_act(x, "x")
+    rows, c = x.shape
+    if out is None:
+        out = _alloc_out(rows, c, x)
+    _lib.check(_lib.lib().lvd_layernorm(x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), rows, c,
+                                        gamma.data_ptr(), beta.data_ptr(), float(eps), _stream()), "layernorm")
+    return out
+
+
+# ----------------------------------------------------------------------------------------------- attention
+def attention(q, kv, *, heads, nz, s_q=0, s_k=0, q_col0=0, k_col0=0, v_col0=0, kv_z_div=1, temporal=False, frames=0,
+              hw=0, scale=0.125, out=None, o_col0=0, p_full=None, p_tok=None, tok_cols=()):
+    """softmax(Q K^T * scale) V with 64-wide heads.  q / kv are 2-D row buffers; q/k/v live at column offsets."""
+    _check_act(q, "q")
+    _check_act(kv, "kv")
+    d = _lib.AttnDesc()
+    rows = q.shape[0]
+    if out is None:
+        out = _alloc_out(rows, heads * 64, q)
+    d.q, d.kv, d.out = q.data_ptr(), kv.data_ptr(), out.data_ptr()
+    d.p_full = p_full.data_ptr() if p_full is not None else None
+    d.p_tok = p_tok.data_ptr() if p_tok is not None else None
+    d.ld_q, d.ld_kv, d.ld_o = q.stride(0), kv.stride(0), out.stride(0)
+    d.q_width, d.kv_width = q.shape[1], kv.shape[1]
+    d.s_q, d.s_k, d.hw, d.frames = int(s_q), int(s_k), int(hw), int(frames)
+    d.mode = 1 if temporal else 0
+    d.q_col0, d.k_col0, d.v_col0, d.o_col0 = int(q_col0), int(k_col0), int(v_col0), int(o_col0)
+    d.heads, d.nz, d.kv_z_div = int(heads), int(nz), int(kv_z_div)
+    d.n_tok = len(tok_cols)
+    for i, t in enumerate(tok_cols):
+        d.tok_cols[i] = int(t)
+    d.scale = float(scale)
+    _lib.check(_lib.lib().lvd_attention(ctypes.byref(d), _stream()), "attention")
+    return out
+
+
+# ----------------------------------------------------------------------------------------------- thin ends / eltwise
+def conv_in(sample, weight, bias, out=None):
+    """sample (B, Cin, F, H, W) fp16 contiguous -> rows [B*F*H*W, Cout]; weight OIHW."""
+    b, cin, f, h, w_ = sample.shape
+    assert sample.is_contiguous() and sample.dtype == torch.float16
+    cout = weight.shape[0]
+    if out is None:
+        out = torch.empty((b * f * h * w_, cout), dtype=torch.float16, device=sample.device)
+    _lib.check(_lib.lib().lvd_conv_in(sample.data_ptr(), weight.data_ptr(), bias.data_ptr(), out.data_ptr(),
+                                      out.stride(0), b, cin, f, h, w_, cout, _stream()), "conv_in")
+    return out
+
+
+def conv_out(x, wk, bias, batch, frames, h, w_):
+    """rows [B*F*H*W, Cin] -> (B, Cout, F, H, W); wk [Cout, 9*Cin] (K = ky,kx,ci)."""
+    _check_act(x, "x")
+    cin = x.shape[1]
+    cout = wk.shape[0]
+    out = torch.empty((batch, cout, frames, h, w_), dtype=torch.float16, device=x.device)
+    _lib.check(_lib.lib().lvd_conv_out(x.data_ptr(), x.stride(0), wk.data_ptr(), bias.data_ptr(), out.data_ptr(),
+                                       batch, cin, frames, h, w_, cout, _stream()), "conv_out")
+    return out
+
+
+def upsample2x(x, n_img, h, w_, out=None):
+    _check_act(x, "x")
+    c = x.shape[1]
+    if out is None:
+        out = _alloc_out(n_img * 4 * h * w_, c, x)
+    _lib.check(_lib.lib().lvd_upsample2x(x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), n_img, h, w_, c,
+                                         _stream()), "upsample2x")
+    return out
+
+
+def timestep_embed(t_f32, dim):
+    out = torch.empty((t_f32.numel(), dim), dtype=torch.float16, device=t_f32.device)
+    _lib.check(_lib.lib().lvd_timestep_embed(t_f32.data_ptr(), out.data_ptr(), t_f32.numel(), dim, _stream()),
+               "timestep_embed")
+    return out
+
+
+def silu(x):
+    assert x.is_contiguous() and x.dtype == torch.float16
+    y = torch.empty_like(x)
+    _lib.check(_lib.lib().lvd_silu(x.data_ptr(), y.data_ptr(), x.numel(), _stream()), "silu")
+    return y
+
+
+def copy_rows(x, out):
+    _check_act(x, "x")
+    _check_act(out, "out")
+    _lib.check(_lib.lib().lvd_copy_rows(x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), x.shape[0],
+                                        x.shape[1], _stream()), "copy_rows")
+    return out

@@ -1,0 +1,79 @@
+"""GPU parity of the tcgen05 attention kernel against a plain PyTorch fp32 reference of the same op.
+Outputs are fp16 and P is fp16 inside the kernel (as in the reference's fp16 bmm): tolerance 3e-3 of max|ref|."""
+import pytest
+import torch
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 3e-3
+
+
+def _rand(shape, dev, scale=1.0, seed=0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).to(dev).half()
+
+
+def _ref_attn(q, k, v, heads, scale=0.125):
+    # q [z, sq, heads*64], k/v [z, sk, heads*64]
+    z, sq, _ = q.shape
+    sk = k.shape[1]
+    qh = q.float().view(z, sq, heads, 64).transpose(1, 2)
+    kh = k.float().view(z, sk, heads, 64).transpose(1, 2)
+    vh = v.float().view(z, sk, heads, 64).transpose(1, 2)
+    p = torch.softmax(qh @ kh.transpose(-1, -2) * scale, dim=-1)
+    o = p @ vh
+    return o.transpose(1, 2).reshape(z, sq, heads * 64), p
+
+
+@pytest.mark.parametrize("z,s,heads", [(2, 128, 1), (3, 45, 2), (2, 180, 2), (2, 720, 2), (1, 2880, 5), (2, 210, 3),
+                                       (2, 1024, 1), (4, 16, 2)])
+def test_self_attention(cuda, z, s, heads):
+    from lvd_b200 import ops
+    c = heads * 64
+    qkv = _rand((z * s, 3 * c), cuda, seed=1)
+    out = ops.attention(qkv, qkv, heads=heads, nz=z, s_q=s, s_k=s, q_col0=0, k_col0=c, v_col0=2 * c)
+    q, k, v = (qkv[:, i * c:(i + 1) * c].reshape(z, s, c) for i in range(3))
+    ref, _ = _ref_attn(q, k, v, heads)
+    assert rel_err(out, ref.reshape(z * s, c)) < TOL
+
+
+@pytest.mark.parametrize("b,frames,s,heads,sk", [(1, 4, 180, 2, 77), (2, 3, 45, 4, 77), (1, 2, 720, 3, 77),
+                                                 (1, 2, 300, 1, 107)])
+def test_cross_attention_with_maps(cuda, b, frames, s, heads, sk):
+    from lvd_b200 import ops
+    c = heads * 64
+    z = b * frames
+    q = _rand((z * s, c), cuda, seed=2)
+    kv = _rand((b * sk, 2 * c), cuda, seed=3)
+    toks = (2, 5, 40, sk - 1)
+    p_full = torch.zeros((z, heads, s, sk), dtype=torch.float16, device=cuda)
+    p_tok = torch.zeros((len(toks), z, heads, s), dtype=torch.float16, device=cuda)
+    out = ops.attention(q, kv, heads=heads, nz=z, s_q=s, s_k=sk, k_col0=0, v_col0=c, kv_z_div=frames,
+                        p_full=p_full, p_tok=p_tok, tok_cols=toks)
+    k = kv[:, :c].reshape(b, sk, c).repeat_interleave(frames, 0)
+    v = kv[:, c:].reshape(b, sk, c).repeat_interleave(frames, 0)
+    ref, p = _ref_attn(q.reshape(z, s, c), k, v, heads)
+    assert rel_err(out, ref.reshape(z * s, c)) < TOL
+    assert rel_err(p_full, p) < TOL
+    for i, t in enumerate(toks):
+        assert rel_err(p_tok[i], p[..., t]) < TOL
+
+
+@pytest.mark.parametrize("b,frames,hw,heads", [(1, 24, 45, 2), (2, 24, 180, 1), (2, 16, 64, 2), (1, 8, 16, 1),
+                                               (1, 24, 2880, 1), (1, 24, 7, 1)])
+def test_temporal_attention(cuda, b, frames, hw, heads):
+    from lvd_b200 import ops
+    c = heads * 64
+    rows = b * frames * hw
+    qkv = _rand((rows, 3 * c), cuda, seed=4)
+    out = ops.attention(qkv, qkv, heads=heads, nz=b, temporal=True, frames=frames, hw=hw, q_col0=0, k_col0=c,
+                        v_col0=2 * c)
+
+    def seq(t):  # rows ((b*F+f)*hw+p) -> [b*hw, F, c]
+        return t.reshape(b, frames, hw, c).permute(0, 2, 1, 3).reshape(b * hw, frames, c)
+
+    q, k, v = (seq(qkv[:, i * c:(i + 1) * c]) for i in range(3))
+    ref, _ = _ref_attn(q, k, v, heads)
+    ref = ref.reshape(b, hw, frames, c).permute(0, 2, 1, 3).reshape(rows, c)
+    assert rel_err(out, ref) < TOL

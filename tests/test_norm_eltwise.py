@@ -1,0 +1,90 @@
+"""GPU parity of the normalisation / thin-end kernels against PyTorch fp32 references."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 2e-3
+
+
+def _rand(shape, dev, scale=1.0, seed=0, shift=0.0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale + shift).to(dev).half()
+
+
+@pytest.mark.parametrize("samples,rows,c,silu", [(4, 45, 1280, True), (48, 180, 320, False), (2, 24 * 45, 640, True),
+                                                 (3, 2880, 960, True), (2, 300, 1920, False), (1, 17, 2560, True),
+                                                 (2, 64, 512, False)])
+def test_groupnorm(cuda, samples, rows, c, silu):
+    from lvd_b200 import ops
+    x = _rand((samples * rows, c), cuda, seed=1, shift=0.7)
+    ga = _rand((c,), cuda, seed=2, shift=1.0)
+    be = _rand((c,), cuda, seed=3)
+    out = ops.groupnorm(x, samples, ga, be, 1e-5, silu=silu)
+    xr = x.float().reshape(samples, rows, c).permute(0, 2, 1)
+    ref = F.group_norm(xr, 32, ga.float(), be.float(), 1e-5)
+    if silu:
+        ref = F.silu(ref.half().float())
+    ref = ref.permute(0, 2, 1).reshape(samples * rows, c)
+    assert rel_err(out, ref) < TOL
+
+
+def test_groupnorm_strided_concat_slice(cuda):
+    from lvd_b200 import ops
+    samples, rows, c1, c2 = 3, 90, 640, 320
+    buf = _rand((samples * rows, c1 + c2), cuda, seed=4)
+    ga = _rand((c1 + c2,), cuda, seed=5, shift=1.0)
+    be = _rand((c1 + c2,), cuda, seed=6)
+    out = ops.groupnorm(buf, samples, ga, be, 1e-6)
+    ref = F.group_norm(buf.float().reshape(samples, rows, -1).permute(0, 2, 1), 32, ga.float(), be.float(), 1e-6)
+    assert rel_err(out, ref.permute(0, 2, 1).reshape(samples * rows, -1)) < TOL
+
+
+@pytest.mark.parametrize("rows,c", [(1000, 320), (77, 1280), (4321, 640), (50, 512), (9, 1024)])
+def test_layernorm(cuda, rows, c):
+    from lvd_b200 import ops
+    x = _rand((rows, c), cuda, seed=7, shift=0.3)
+    ga = _rand((c,), cuda, seed=8, shift=1.0)
+    be = _rand((c,), cuda, seed=9)
+    out = ops.layernorm(x, ga, be)
+    ref = F.layer_norm(x.float(), (c,), ga.float(), be.float(), 1e-5)
+    assert rel_err(out, ref) < TOL
+
+
+def test_conv_in_out(cuda):
+    from lvd_b200 import ops, repack
+    b, f, h, w = 2, 3, 10, 18
+    x = _rand((b, 4, f, h, w), cuda, seed=10)
+    wi = _rand((320, 4, 3, 3), cuda, 1 / 6, seed=11)
+    bi = _rand((320,), cuda, seed=12)
+    rows = ops.conv_in(x, wi, bi)
+    x4 = x.permute(0, 2, 1, 3, 4).reshape(b * f, 4, h, w).float()
+    ref = F.conv2d(x4, wi.float(), bi.float(), padding=1).permute(0, 2, 3, 1).reshape(b * f * h * w, 320)
+    assert rel_err(rows, ref) < TOL
+    wo = _rand((4, 320, 3, 3), cuda, (9 * 320) ** -0.5, seed=13)
+    bo = _rand((4,), cuda, seed=14)
+    y = ops.conv_out(rows, repack.conv_weight_krsc(wo), bo, b, f, h, w)
+    r4 = rows.float().reshape(b * f, h, w, 320).permute(0, 3, 1, 2)
+    ref2 = F.conv2d(r4, wo.float(), bo.float(), padding=1).reshape(b, f, 4, h, w).permute(0, 2, 1, 3, 4)
+    assert y.shape == (b, 4, f, h, w)
+    assert rel_err(y, ref2) < TOL
+
+
+def test_upsample_timestep_silu(cuda):
+    from lvd_b200 import ops
+    n, h, w, c = 3, 5, 9, 64
+    x = _rand((n * h * w, c), cuda, seed=15)
+    y = ops.upsample2x(x, n, h, w)
+    ref = F.interpolate(x.float().reshape(n, h, w, c).permute(0, 3, 1, 2), scale_factor=2.0, mode="nearest")
+    assert torch.equal(y.float(), ref.permute(0, 2, 3, 1).reshape(-1, c))
+    t = torch.tensor([951.0, 20.0, 1.0], device=cuda)
+    e = ops.timestep_embed(t, 320)
+    import math
+    freq = torch.exp(-math.log(10000.0) * torch.arange(160, device=cuda, dtype=torch.float32) / 160)
+    a = t[:, None] * freq[None]
+    ref = torch.cat([a.cos(), a.sin()], -1)
+    assert (e.float() - ref).abs().max().item() < 2e-3
+    v = _rand((1000,), cuda, seed=16, scale=3.0)
+    assert rel_err(ops.silu(v), F.silu(v.float())) < TOL
