@@ -145,6 +145,19 @@ int lvd_timestep_embed(const void* timesteps_f32, void* out, int32_t batch, int3
 int lvd_silu(const void* x, void* y, int64_t n, void* stream);
 int lvd_copy_rows(const void* x, int64_t ld_x, void* y, int64_t ld_y, int64_t rows, int32_t channels, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Per-step latent arithmetic (fp16 tensors of n elements, evaluated with the reference's fp16 op order).
+ * lvd_cfg_dpm_step: classifier-free-guidance combine (controllable_pipeline_text_to_video_synth.py:926-930) fused
+ *   with diffusers 0.27.2 DPMSolverMultistepScheduler.step (dpmsolver++, midpoint, epsilon prediction; used at
+ *   :941-943).  eps_cond == NULL skips the CFG combine.  Host passes the scalar coefficients:
+ *     x0 = (x - sigma_t*eps)/alpha_t ;  x_out = c_x*x - c_d0*x0 - c_d1*D1 ,  D1 = inv_r0*(x0 - x0_prev) (order 2)
+ * lvd_axpy_h: latents - scale*grad (models/pipelines.py:124-132).
+ * ---------------------------------------------------------------------------------------------------------- */
+int lvd_cfg_dpm_step(const void* eps_uncond, const void* eps_cond, const void* x, const void* x0_prev, void* x_out,
+                     void* x0_out, int64_t n, float guidance_scale, float sigma_t, float alpha_t, float c_x,
+                     float c_d0, float c_d1, float inv_r0, int32_t order, void* stream);
+int lvd_axpy_h(const void* x, const void* g, void* out, int64_t n, float scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -104,6 +104,8 @@ def _declare(l):
     l.lvd_timestep_embed.argtypes = [vp, vp, i32, i32, vp]
     l.lvd_silu.argtypes = [vp, vp, i64, vp]
     l.lvd_copy_rows.argtypes = [vp, i64, vp, i64, i64, i32, vp]
+    l.lvd_cfg_dpm_step.argtypes = [vp, vp, vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, f32, f32, i32, vp]
+    l.lvd_axpy_h.argtypes = [vp, vp, vp, i64, f32, vp]
     for name in EXPORTS:
         fn = getattr(l, name)
         if name not in ("lvd_last_error", "lvd_launch_count"):
@@ -125,6 +127,8 @@ EXPORTS = [
     "lvd_timestep_embed",
     "lvd_silu",
     "lvd_copy_rows",
+    "lvd_cfg_dpm_step",
+    "lvd_axpy_h",
 ]
 
 

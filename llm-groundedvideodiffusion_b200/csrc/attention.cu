@@ -60,7 +60,9 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid
   uint64_t* o_full = bars + 7;
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 8);
 
-  const int qt = blockIdx.x, h = blockIdx.y, z = blockIdx.z;
+  // heads vary fastest across concurrently scheduled CTAs so that neighbouring CTAs read neighbouring 128-byte
+  // pieces of the same activation rows (DRAM page locality; matters most for the temporal row gather)
+  const int h = blockIdx.x, qt = blockIdx.y, z = blockIdx.z;
   if ((smem_u32(smem) & 1023u) != 0) __trap();
 
   if (g.q_bytes < kTile || g.kv_bytes < kTile) {
@@ -384,8 +386,8 @@ extern "C" int lvd_attention(const lvd_attn_desc* d, void* stream) {
     attr = true;
   }
   const int q_tiles = (g.q_dim1 + g.qb1 - 1) / g.qb1;
-  dim3 grid(q_tiles, d->heads, d->nz);
-  LVD_REQUIRE(d->heads <= 65535 && d->nz <= 65535, "lvd_attention: grid too large");
+  dim3 grid(d->heads, q_tiles, d->nz);
+  LVD_REQUIRE(q_tiles <= 65535 && d->nz <= 65535, "lvd_attention: grid too large");
   attention_kernel<<<grid, kAttnThreads, kAttnSmem, static_cast<cudaStream_t>(stream)>>>(g);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   LVD_CHECK_CUDA(cudaGetLastError());

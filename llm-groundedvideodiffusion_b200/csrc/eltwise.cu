@@ -265,3 +265,69 @@ extern "C" int lvd_copy_rows(const void* x, int64_t ld_x, void* y, int64_t ld_y,
   LVD_CHECK_CUDA(cudaGetLastError());
   return LVD_OK;
 }
+
+// ---------------------------------------------------------------------------------------------- CFG + DPM-Solver++ step
+// Fuses, per latent element (controllable_pipeline_text_to_video_synth.py:926-950 + diffusers 0.27.2
+// DPMSolverMultistepScheduler.step):
+//   eps  = eps_u + gs * (eps_c - eps_u)                        (fp16 ops, as the reference evaluates them)
+//   x0   = (x - sigma_t * eps) / alpha_t                       (fp16: convert_model_output, epsilon prediction)
+//   x'   = c_x * float(x) - half(c_d0 * x0) - half(c_d1 * D1),  D1 = half(inv_r0 * half(x0 - x0_prev))   (2nd order)
+// x0 is written to x0_out (the scheduler's model_outputs ring).  order == 1 drops the D1 term.
+namespace lvd {
+__device__ __forceinline__ float hmul(float a, float b) { return round_h(a * b); }
+__global__ void cfg_dpm_step_kernel(const __half* __restrict__ eps_u, const __half* __restrict__ eps_c,
+                                    const __half* __restrict__ x, const __half* __restrict__ x0_prev,
+                                    __half* __restrict__ x_out, __half* __restrict__ x0_out, long long n, float gs,
+                                    float sigma_t, float alpha_t, float c_x, float c_d0, float c_d1, float inv_r0,
+                                    int order, int use_cfg) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float u = __half2float(eps_u[i]);
+    float e = u;
+    if (use_cfg) {
+      const float c = __half2float(eps_c[i]);
+      e = round_h(u + hmul(gs, round_h(c - u)));
+    }
+    const float xs = __half2float(x[i]);
+    const float x0 = round_h(round_h(xs - hmul(sigma_t, e)) / alpha_t);
+    float xn = c_x * xs - hmul(c_d0, x0);
+    if (order == 2) {
+      const float d1 = hmul(inv_r0, round_h(x0 - __half2float(x0_prev[i])));
+      xn -= hmul(c_d1, d1);
+    }
+    x_out[i] = __float2half_rn(xn);
+    x0_out[i] = __float2half_rn(x0);
+  }
+}
+// x <- x - scale * grad   (models/pipelines.py:124-132), fp16 ops
+__global__ void axpy_h_kernel(const __half* __restrict__ x, const __half* __restrict__ gvec, __half* __restrict__ out,
+                              long long n, float scale) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    out[i] = __float2half_rn(__half2float(x[i]) - hmul(scale, __half2float(gvec[i])));
+}
+}  // namespace lvd
+
+extern "C" int lvd_cfg_dpm_step(const void* eps_uncond, const void* eps_cond, const void* x, const void* x0_prev,
+                                void* x_out, void* x0_out, int64_t n, float guidance_scale, float sigma_t,
+                                float alpha_t, float c_x, float c_d0, float c_d1, float inv_r0, int32_t order,
+                                void* stream) {
+  LVD_REQUIRE(eps_uncond && x && x_out && x0_out, "lvd_cfg_dpm_step: null pointer");
+  LVD_REQUIRE(order == 1 || (order == 2 && x0_prev), "lvd_cfg_dpm_step: order %d", order);
+  cfg_dpm_step_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __half*>(eps_uncond), static_cast<const __half*>(eps_cond), static_cast<const __half*>(x),
+      static_cast<const __half*>(x0_prev), static_cast<__half*>(x_out), static_cast<__half*>(x0_out), n,
+      guidance_scale, sigma_t, alpha_t, c_x, c_d0, c_d1, inv_r0, order, eps_cond != nullptr);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  LVD_CHECK_CUDA(cudaGetLastError());
+  return LVD_OK;
+}
+
+extern "C" int lvd_axpy_h(const void* x, const void* g, void* out, int64_t n, float scale, void* stream) {
+  LVD_REQUIRE(x && g && out, "lvd_axpy_h: null pointer");
+  axpy_h_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __half*>(x), static_cast<const __half*>(g), static_cast<__half*>(out), n, scale);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  LVD_CHECK_CUDA(cudaGetLastError());
+  return LVD_OK;
+}

@@ -2,7 +2,8 @@
 //
 //   warp 0      : TMA producer   (one elected lane; cp.async.bulk.tensor into a multi-stage smem ring)
 //   warp 1      : MMA issuer     (one elected lane; tcgen05.mma, fp32 accumulators double-buffered in TMEM)
-//   warps 2..5  : epilogue       (tcgen05.ld -> bias / SiLU / GEGLU / time-embedding / gate / residual -> fp16 store)
+//   warps 2..9  : epilogue       (tcgen05.ld -> bias / SiLU / GEGLU / time-embedding / gate / residual -> fp16 store;
+//                 two warps per TMEM lane quarter, interleaved over 32-column chunks)
 //
 // A tiles are rank-5 TMA boxes of the channels-last activation; a convolution tap is a coordinate offset and the
 // zero padding is TMA out-of-bounds fill, so Linear, Conv2d (3x3, 1x1, stride 2) and Conv3d (3,1,1) all run here.
@@ -17,7 +18,7 @@ namespace lvd {
 std::atomic<long long> g_launches{0};
 
 constexpr int kAStageBytes = 128 * 128;  // 128 rows x 64 halves
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;  // 2 control warps + 8 epilogue warps
 constexpr int kSmemLimit = 232448;  // 227 KB
 
 struct GemmArgs {
@@ -118,8 +119,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     }
     mbar_init(&tfull[0], 1);
     mbar_init(&tfull[1], 1);
-    mbar_init(&tempty[0], 128);
-    mbar_init(&tempty[1], 128);
+    mbar_init(&tempty[0], 256);
+    mbar_init(&tempty[1], 256);
     fence_barrier_init();
   }
   if (warp == 0 && lane == 0) {
@@ -203,6 +204,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     }
   } else {
     const int q = warp & 3;  // this warp may only touch TMEM lanes [32q, 32q+32)
+    const int chalf = (warp - 2) >> 2;  // which of the two warps sharing this lane quarter
     const int r = q * 32 + lane;
     int j[4];
     {
@@ -234,7 +236,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       tc_fence_after();
       const uint32_t taddr = tmem_base + static_cast<uint32_t>(acc) * 256u + (static_cast<uint32_t>(q * 32) << 16);
       if (g.act != 2) {
-        for (int ch = 0; ch < g.block_n / 32; ++ch) {
+        for (int ch = chalf; ch < g.block_n / 32; ch += 2) {
           uint32_t rr[32];
           tmem_ld32(taddr + ch * 32, rr);
           tmem_ld_wait();
@@ -264,7 +266,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         }
       } else {
         // GEGLU: block_n == 128; TMEM columns [0,64) = value, [64,128) = gate of output columns nt*64 + [0,64)
-        for (int ch = 0; ch < 2; ++ch) {
+        for (int ch = chalf; ch < 2; ch += 2) {
           uint32_t rv[32], rg[32];
           tmem_ld32(taddr + ch * 32, rv);
           tmem_ld32(taddr + 64 + ch * 32, rg);

@@ -42,11 +42,19 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t addr, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded spin: a protocol bug traps (surfacing as a launch failure) instead of hanging the GPU box.
+// Bounded wait: a protocol bug traps after ~2 s of wall clock (surfacing as a launch failure) instead of hanging
+// the GPU box.  try_wait itself may suspend the thread for an implementation-defined time, so count time, not spins.
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
-  for (uint32_t spins = 0; !mbar_try_wait(addr, parity); ++spins) {
-    if (spins > (1u << 24)) __trap();
+  if (mbar_try_wait(addr, parity)) return;
+  const uint64_t t0 = globaltimer_ns();
+  while (!mbar_try_wait(addr, parity)) {
+    if (globaltimer_ns() - t0 > 2000000000ull) __trap();
   }
 }
 
@@ -165,6 +173,18 @@ __host__ __device__ __forceinline__ uint32_t make_idesc_f16(uint32_t M, uint32_t
 // ---------------------------------------------------------------- misc math helpers
 __device__ __forceinline__ float round_h(float v) { return __half2float(__float2half_rn(v)); }
 __device__ __forceinline__ float silu_f(float v) { return v / (1.0f + __expf(-v)); }
-__device__ __forceinline__ float gelu_erf_f(float v) { return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f)); }
+// erf-GELU (F.gelu default, models/attention.py:365-376).  erf by Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7, far
+// below fp16 resolution): one ex2 + one rcp + 6 FMA instead of the ~40-instruction erff -- the GEGLU epilogue is
+// otherwise bound by this function, not by the tensor pipe.
+__device__ __forceinline__ float gelu_erf_f(float v) {
+  const float x = fabsf(v) * 0.70710678118654752440f;
+  const float t = __frcp_rn(fmaf(0.3275911f, x, 1.0f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float e = 1.0f - p * t * __expf(-x * x);  // erf(|v|/sqrt2)
+  return 0.5f * v * (1.0f + copysignf(e, v));
+}
 
 }  // namespace lvd

@@ -217,8 +217,12 @@ class UNetEngine:
         n_img = b * frames
         ehs = encoder_hidden_states.to(device=dev, dtype=torch.float16).contiguous()
         ctx = ehs.reshape(b * ehs.shape[1], ehs.shape[2])
-        t = torch.as_tensor(timestep, device=dev).reshape(-1).to(torch.float32)
-        t = t.expand(b).repeat_interleave(frames).contiguous()
+        if torch.is_tensor(timestep) and timestep.is_cuda and timestep.dtype == torch.float32 and \
+                timestep.numel() == n_img:
+            t = timestep  # pre-expanded device tensor (CUDA-graph replay: the value is read at run time)
+        else:
+            t = torch.as_tensor(timestep, device=dev).reshape(-1).to(torch.float32)
+            t = t.expand(b).repeat_interleave(frames).contiguous()
         temb = ops.timestep_embed(t, boc[0])
         temb = ops.linear(temb, w["time1"].w, w["time1"].b, act=ops.ACT_SILU)  # silu fused: only silu(temb@W1) is used
         temb = ops.linear(temb, w["time2"].w, w["time2"].b)

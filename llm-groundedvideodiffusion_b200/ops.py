@@ -14,6 +14,29 @@ from ._lib import GemmDesc
 
 ACT_NONE, ACT_SILU, ACT_GEGLU = 0, 1, 2
 
+# Optional per-launch instrumentation (bench.py's roofline pass): when PROF is a list, every launch appends
+# (kernel family, algorithmic flops, algorithmic bytes, start event, end event) recorded on the launching stream.
+PROF = None
+
+
+class _Timed:
+    def __init__(self, family, flops=0.0, nbytes=0.0):
+        self.rec = None
+        if PROF is not None:
+            self.rec = [family, float(flops), float(nbytes), torch.cuda.Event(enable_timing=True),
+                        torch.cuda.Event(enable_timing=True)]
+
+    def __enter__(self):
+        if self.rec is not None:
+            self.rec[3].record()
+        return self
+
+    def __exit__(self, *a):
+        if self.rec is not None:
+            self.rec[4].record()
+            PROF.append(self.rec)
+        return False
+
 
 def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
@@ -103,6 +126,16 @@ def gemm_raw(*, a, a_dims, a_strides, a_box, taps, k_per_tap, w, n, out, out_dim
     d.ld_res = residual.stride(0) if residual is not None else 0
     d.ld_out = out.stride(0)
     d.gamma = float(gamma)
+    if PROF is not None:
+        m = 1
+        for v in out_dims:
+            m *= int(v)
+        kt = len(taps) * int(k_per_tap)
+        n_out = n // 2 if act == ACT_GEGLU else n
+        nbytes = 2.0 * (m * int(k_per_tap) + n * kt + m * n_out * (2 if residual is not None else 1))
+        with _Timed("gemm_tc_kernel", 2.0 * m * n * kt, nbytes):
+            _lib.check(_lib.lib().lvd_gemm(ctypes.byref(d), _stream()), "gemm")
+        return out
     _lib.check(_lib.lib().lvd_gemm(ctypes.byref(d), _stream()), "gemm")
     return out
 
@@ -224,9 +257,10 @@ def groupnorm(x, samples, gamma, beta, eps, *, groups=32, silu=False, out=None):
     if out is None:
         out = _alloc_out(rows, c, x)
     ws = _gn_workspace(x.device, samples, groups)
-    _lib.check(_lib.lib().lvd_groupnorm(x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), samples,
-                                        rows // samples, c, groups, gamma.data_ptr(), beta.data_ptr(), float(eps),
-                                        1 if silu else 0, ws.data_ptr(), ws.numel(), _stream()), "groupnorm")
+    with _Timed("groupnorm", 0.0, 2.0 * rows * c * 2):
+        _lib.check(_lib.lib().lvd_groupnorm(x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), samples,
+                                            rows // samples, c, groups, gamma.data_ptr(), beta.data_ptr(), float(eps),
+                                            1 if silu else 0, ws.data_ptr(), ws.numel(), _stream()), "groupnorm")
     return out
 
 
@@ -235,8 +269,9 @@ def layernorm(x, gamma, beta, eps=1e-5, out=None):
     rows, c = x.shape
     if out is None:
         out = _alloc_out(rows, c, x)
-    _lib.check(_lib.lib().lvd_layernorm(x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), rows, c,
-                                        gamma.data_ptr(), beta.data_ptr(), float(eps), _stream()), "layernorm")
+    with _Timed("layernorm", 0.0, 2.0 * rows * c * 2):
+        _lib.check(_lib.lib().lvd_layernorm(x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), rows, c,
+                                            gamma.data_ptr(), beta.data_ptr(), float(eps), _stream()), "layernorm")
     return out
 
 
@@ -263,7 +298,12 @@ def attention(q, kv, *, heads, nz, s_q=0, s_k=0, q_col0=0, k_col0=0, v_col0=0, k
     for i, t in enumerate(tok_cols):
         d.tok_cols[i] = int(t)
     d.scale = float(scale)
-    _lib.check(_lib.lib().lvd_attention(ctypes.byref(d), _stream()), "attention")
+    if temporal:
+        fl, fam = 4.0 * nz * hw * heads * frames * frames * 64, "attention_temporal"
+    else:
+        fl, fam = 4.0 * nz * heads * s_q * s_k * 64, ("attention_self" if kv is q else "attention_cross")
+    with _Timed(fam, fl, 2.0 * (q.shape[0] * heads * 64 * 2 + kv.shape[0] * heads * 128)):
+        _lib.check(_lib.lib().lvd_attention(ctypes.byref(d), _stream()), "attention")
     return out
 
 
