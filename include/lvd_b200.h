@@ -158,6 +158,32 @@ int lvd_cfg_dpm_step(const void* eps_uncond, const void* eps_cond, const void* x
                      float c_d0, float c_d1, float inv_r0, int32_t order, void* stream);
 int lvd_axpy_h(const void* x, const void* g, void* out, int64_t n, float scale, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Box energy of the LVD backward guidance on one saved cross-attention map, and dE/dP.
+ * Replaces utils/guidance.py:160-526 (add_ca_loss_per_attn_map_to_loss; default top-k "max-based" loss + optional
+ * centre-of-mass position/velocity terms) and the normalisation of compute_ca_lossv3 (:529-574).
+ *   slot  = one (object, text token) pair; boxes[slot][frame] = (x0,y0,x1,y1) integer rectangle at this map's
+ *           resolution (host applies utils/utils.py:82-103 scale_proportion -- Python banker's rounding);
+ *   slot_weight[slot] = 1 / len(object_positions[object])  (guidance.py:524)
+ *   out_scale = loss_scale / (n_objects * n_keys)           (guidance.py:569-572, models/pipelines.py:101-112)
+ * layout 0: p = token-column maps [n_slots][frames][heads][H*W] (what lvd_attention's p_tok emits);
+ * layout 1: p = the reference's saved map [frames][heads][H*W][n_text], slot_col[slot] = text token index.
+ * *loss is atomically incremented (zero it first).  dp (same layout as p, may be NULL) receives
+ * grad_scale * dE/dP for the slot's column (fp16; grad_scale guards against underflow).
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct lvd_energy_desc {
+  const void* p;
+  const int32_t* slot_col;
+  const int32_t* boxes;
+  const float* slot_weight;
+  float* loss;
+  void* dp;
+  int32_t layout, n_text, n_slots, frames, heads, H, W;
+  float fg_top_p, bg_top_p, fg_weight, bg_weight, com_loss_scale, out_scale, grad_scale;
+} lvd_energy_desc;
+
+int lvd_box_energy(const lvd_energy_desc* d, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -70,6 +70,31 @@ class AttnDesc(ctypes.Structure):
     ]
 
 
+class EnergyDesc(ctypes.Structure):
+    _fields_ = [
+        ("p", ctypes.c_void_p),
+        ("slot_col", ctypes.c_void_p),
+        ("boxes", ctypes.c_void_p),
+        ("slot_weight", ctypes.c_void_p),
+        ("loss", ctypes.c_void_p),
+        ("dp", ctypes.c_void_p),
+        ("layout", ctypes.c_int32),
+        ("n_text", ctypes.c_int32),
+        ("n_slots", ctypes.c_int32),
+        ("frames", ctypes.c_int32),
+        ("heads", ctypes.c_int32),
+        ("H", ctypes.c_int32),
+        ("W", ctypes.c_int32),
+        ("fg_top_p", ctypes.c_float),
+        ("bg_top_p", ctypes.c_float),
+        ("fg_weight", ctypes.c_float),
+        ("bg_weight", ctypes.c_float),
+        ("com_loss_scale", ctypes.c_float),
+        ("out_scale", ctypes.c_float),
+        ("grad_scale", ctypes.c_float),
+    ]
+
+
 _lib = None
 
 
@@ -106,6 +131,7 @@ def _declare(l):
     l.lvd_copy_rows.argtypes = [vp, i64, vp, i64, i64, i32, vp]
     l.lvd_cfg_dpm_step.argtypes = [vp, vp, vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, f32, f32, i32, vp]
     l.lvd_axpy_h.argtypes = [vp, vp, vp, i64, f32, vp]
+    l.lvd_box_energy.argtypes = [ctypes.POINTER(EnergyDesc), vp]
     for name in EXPORTS:
         fn = getattr(l, name)
         if name not in ("lvd_last_error", "lvd_launch_count"):
@@ -129,6 +155,7 @@ EXPORTS = [
     "lvd_copy_rows",
     "lvd_cfg_dpm_step",
     "lvd_axpy_h",
+    "lvd_box_energy",
 ]
 
 

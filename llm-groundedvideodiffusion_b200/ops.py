@@ -361,3 +361,31 @@ def copy_rows(x, out):
     _lib.check(_lib.lib().lvd_copy_rows(x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), x.shape[0],
                                         x.shape[1], _stream()), "copy_rows")
     return out
+
+
+# ----------------------------------------------------------------------------------------------- box energy
+def box_energy(p, loss, boxes, slot_weight, *, frames, heads, H, W, slot_col=None, n_text=0, fg_top_p=0.2,
+               bg_top_p=0.2, fg_weight=1.0, bg_weight=1.0, com_loss_scale=0.0, out_scale=1.0, dp=None,
+               grad_scale=1.0):
+    """Accumulate the box energy of one attention map into `loss` (0-d fp32 CUDA tensor) and optionally write
+    grad_scale * dE/dP into `dp`.  slot_col given -> `p` is the full map [F, heads, hw, n_text]; otherwise `p` holds
+    token columns [n_slots, F, heads, hw]."""
+    d = _lib.EnergyDesc()
+    assert p.is_cuda and p.dtype == torch.float16 and p.is_contiguous()
+    assert boxes.dtype == torch.int32 and boxes.is_contiguous() and slot_weight.dtype == torch.float32
+    d.p = p.data_ptr()
+    d.slot_col = slot_col.data_ptr() if slot_col is not None else None
+    d.boxes = boxes.data_ptr()
+    d.slot_weight = slot_weight.data_ptr()
+    d.loss = loss.data_ptr()
+    d.dp = dp.data_ptr() if dp is not None else None
+    d.layout = 1 if slot_col is not None else 0
+    d.n_text = int(n_text)
+    d.n_slots = int(boxes.shape[0])
+    d.frames, d.heads, d.H, d.W = int(frames), int(heads), int(H), int(W)
+    d.fg_top_p, d.bg_top_p = float(fg_top_p), float(bg_top_p)
+    d.fg_weight, d.bg_weight = float(fg_weight), float(bg_weight)
+    d.com_loss_scale, d.out_scale, d.grad_scale = float(com_loss_scale), float(out_scale), float(grad_scale)
+    with _Timed("box_energy", 0.0, 2.0 * p.numel()):
+        _lib.check(_lib.lib().lvd_box_energy(ctypes.byref(d), _stream()), "box_energy")
+    return loss
