@@ -184,6 +184,18 @@ typedef struct lvd_energy_desc {
 
 int lvd_box_energy(const lvd_energy_desc* d, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * GLIGEN helpers.
+ * lvd_copy_rows_seq: dst[(r/n)*dst_seq + dst_off + r%n] = src[(r/n)*src_seq + src_off + r%n]; builds / splits the
+ *   [visual ; grounding-token] sequence of GatedSelfAttentionDense.forward (models/attention.py:50-57).
+ * lvd_gligen_prep: FourierEmbedder + masked null blending + concat of PositionNet.forward
+ *   (models/unet_3d_condition.py:47-64,119-150); out [n_obj, dim + 64] feeds position_net.linears via lvd_gemm.
+ * ---------------------------------------------------------------------------------------------------------- */
+int lvd_copy_rows_seq(const void* x, int64_t ld_x, void* y, int64_t ld_y, int64_t rows, int32_t channels, int32_t n,
+                      int32_t src_seq, int32_t src_off, int32_t dst_seq, int32_t dst_off, void* stream);
+int lvd_gligen_prep(const void* boxes, const void* masks, const void* positive_embeddings, const void* null_positive,
+                    const void* null_position, void* out, int64_t n_obj, int32_t dim, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

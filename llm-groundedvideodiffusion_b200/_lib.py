@@ -132,6 +132,8 @@ def _declare(l):
     l.lvd_cfg_dpm_step.argtypes = [vp, vp, vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, f32, f32, i32, vp]
     l.lvd_axpy_h.argtypes = [vp, vp, vp, i64, f32, vp]
     l.lvd_box_energy.argtypes = [ctypes.POINTER(EnergyDesc), vp]
+    l.lvd_copy_rows_seq.argtypes = [vp, i64, vp, i64, i64, i32, i32, i32, i32, i32, i32, vp]
+    l.lvd_gligen_prep.argtypes = [vp, vp, vp, vp, vp, vp, i64, i32, vp]
     for name in EXPORTS:
         fn = getattr(l, name)
         if name not in ("lvd_last_error", "lvd_launch_count"):
@@ -156,6 +158,8 @@ EXPORTS = [
     "lvd_cfg_dpm_step",
     "lvd_axpy_h",
     "lvd_box_energy",
+    "lvd_copy_rows_seq",
+    "lvd_gligen_prep",
 ]
 
 

@@ -331,3 +331,75 @@ extern "C" int lvd_axpy_h(const void* x, const void* g, void* out, int64_t n, fl
   LVD_CHECK_CUDA(cudaGetLastError());
   return LVD_OK;
 }
+
+// ---------------------------------------------------------------------------------------------- sequence-strided row copy
+// dst[(r / n)*dst_seq + dst_off + r % n] = src[(r / n)*src_seq + src_off + r % n]   for r in [0, groups*n)
+// (builds / splits the [visual tokens ; grounding tokens] sequences of GatedSelfAttentionDense, models/attention.py:50-57)
+namespace lvd {
+__global__ void copy_rows_seq_kernel(const __half* __restrict__ x, long long ld_x, __half* __restrict__ y,
+                                     long long ld_y, long long rows, int C, int n, int src_seq, int src_off,
+                                     int dst_seq, int dst_off) {
+  const int cvec = C / 8;
+  const long long total = rows * cvec;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = idx / cvec;
+    const int cv = static_cast<int>(idx % cvec);
+    const long long grp = r / n, j = r % n;
+    *reinterpret_cast<uint4*>(y + (grp * dst_seq + dst_off + j) * ld_y + cv * 8) =
+        *reinterpret_cast<const uint4*>(x + (grp * src_seq + src_off + j) * ld_x + cv * 8);
+  }
+}
+
+// GLIGEN PositionNet input (models/unet_3d_condition.py:47-64,119-150): Fourier embedding of the xyxy box
+// (8 frequencies 100^(j/8), layout j*8 + {sin,cos}*4 + coord), masked blend with the learned null features, and
+// concatenation [positive_embedding (D) | position embedding (64)].  fp32 math on fp16 inputs.
+__global__ void gligen_prep_kernel(const __half* __restrict__ boxes, const __half* __restrict__ masks,
+                                   const __half* __restrict__ pos, const __half* __restrict__ null_pos,
+                                   const __half* __restrict__ null_xyxy, __half* __restrict__ out, long long n_obj,
+                                   int D) {
+  const int width = D + 64;
+  const long long total = n_obj * width;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long o = idx / width;
+    const int c = static_cast<int>(idx % width);
+    const float m = __half2float(masks[o]);
+    float v;
+    if (c < D) {
+      v = __half2float(pos[o * D + c]) * m + (1.f - m) * __half2float(null_pos[c]);
+    } else {
+      const int e = c - D, j = e >> 3, s = (e >> 2) & 1, k = e & 3;
+      const float freq = powf(100.f, static_cast<float>(j) / 8.f);
+      const float a = freq * __half2float(boxes[o * 4 + k]);
+      v = (s == 0 ? sinf(a) : cosf(a)) * m + (1.f - m) * __half2float(null_xyxy[e]);
+    }
+    out[idx] = __float2half_rn(v);
+  }
+}
+}  // namespace lvd
+
+extern "C" int lvd_copy_rows_seq(const void* x, int64_t ld_x, void* y, int64_t ld_y, int64_t rows, int32_t channels,
+                                 int32_t n, int32_t src_seq, int32_t src_off, int32_t dst_seq, int32_t dst_off,
+                                 void* stream) {
+  LVD_REQUIRE(x && y && channels % 8 == 0 && ld_x % 8 == 0 && ld_y % 8 == 0 && n >= 1, "lvd_copy_rows_seq: bad arguments");
+  copy_rows_seq_kernel<<<grid_for(rows * (channels / 8), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __half*>(x), ld_x, static_cast<__half*>(y), ld_y, rows, channels, n, src_seq, src_off, dst_seq,
+      dst_off);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  LVD_CHECK_CUDA(cudaGetLastError());
+  return LVD_OK;
+}
+
+extern "C" int lvd_gligen_prep(const void* boxes, const void* masks, const void* positive_embeddings,
+                               const void* null_positive, const void* null_position, void* out, int64_t n_obj,
+                               int32_t dim, void* stream) {
+  LVD_REQUIRE(boxes && masks && positive_embeddings && null_positive && null_position && out, "lvd_gligen_prep: null");
+  gligen_prep_kernel<<<grid_for(n_obj * (dim + 64), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __half*>(boxes), static_cast<const __half*>(masks),
+      static_cast<const __half*>(positive_embeddings), static_cast<const __half*>(null_positive),
+      static_cast<const __half*>(null_position), static_cast<__half*>(out), n_obj, dim);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  LVD_CHECK_CUDA(cudaGetLastError());
+  return LVD_OK;
+}

@@ -64,6 +64,16 @@ class UNetEngine:
             wi, bi = repack.geglu_interleave(g(p + ".ff.net.0.proj.weight"), g(p + ".ff.net.0.proj.bias"))
             d["ff1"] = LayerWeights(w=wi, b=bi)
             d["ff2"] = lin(p + ".ff.net.2")
+            f = p + ".fuser"
+            if (f + ".linear.weight") in sd:  # GatedSelfAttentionDense (models/attention.py:26-60)
+                fwi, fbi = repack.geglu_interleave(g(f + ".ff.net.0.proj.weight"), g(f + ".ff.net.0.proj.bias"))
+                d["fuser"] = LayerWeights(
+                    linear=lin(f + ".linear"), norm1=norm(f + ".norm1"), norm2=norm(f + ".norm2"),
+                    qkv=torch.cat([g(f + ".attn.to_q.weight"), g(f + ".attn.to_k.weight"),
+                                   g(f + ".attn.to_v.weight")], 0).contiguous(),
+                    out=lin(f + ".attn.to_out.0"), ff1=LayerWeights(w=fwi, b=fbi), ff2=lin(f + ".ff.net.2"),
+                    g_attn=float(torch.tanh(sd[f + ".alpha_attn"].float())),
+                    g_dense=float(torch.tanh(sd[f + ".alpha_dense"].float())))
             return d
 
         def transformer(p, cross):
@@ -135,6 +145,11 @@ class UNetEngine:
             if i < nb - 1:
                 blk["up"] = conv3(f"{p}.upsamplers.0.conv")
             w["up"].append(blk)
+        if "position_net.linears.0.weight" in sd:
+            w["position_net"] = LayerWeights(l0=lin("position_net.linears.0"), l2=lin("position_net.linears.2"),
+                                             l4=lin("position_net.linears.4"),
+                                             null_pos=g("position_net.null_positive_feature"),
+                                             null_xyxy=g("position_net.null_position_feature"))
         w["norm_out"] = norm("conv_norm_out")
         w["conv_out"] = LayerWeights(w=repack.conv_weight_krsc(g("conv_out.weight")), b=g("conv_out.bias"))
         # all 22 time_emb_proj Linear layers fused into one GEMM per forward (ResnetBlock2D)
@@ -164,7 +179,36 @@ class UNetEngine:
             t = ops.conv_temporal(t, batch, frames, hw, L.w, L.b, residual=x if i == 3 else None)
         return t
 
-    def _block(self, B, t, *, heads, spatial, n_img, hw, batch, frames, ctx_kv=None, key=None, capture=None):
+    def _fuser(self, Fz, x, objs, *, heads, n_img, hw):
+        """GatedSelfAttentionDense.forward (models/attention.py:44-60): x += tanh(a_attn) * SA(LN([x; W objs]))[:hw];
+        x += tanh(a_dense) * FF(LN(x))."""
+        c = x.shape[1]
+        n_obj = objs.shape[0] // n_img
+        seq = hw + n_obj
+        lo = ops.linear(objs, Fz.linear.w, Fz.linear.b)
+        cat = torch.empty((n_img * seq, c), dtype=torch.float16, device=self.dev)
+        ops.copy_rows_seq(x, cat, hw, src_seq=hw, src_off=0, dst_seq=seq, dst_off=0, groups=n_img)
+        ops.copy_rows_seq(lo, cat, n_obj, src_seq=n_obj, src_off=0, dst_seq=seq, dst_off=hw, groups=n_img)
+        n1 = ops.layernorm(cat, Fz.norm1.w, Fz.norm1.b)
+        qkv = ops.linear(n1, Fz.qkv)
+        a = ops.attention(qkv, qkv, heads=heads, nz=n_img, s_q=seq, s_k=seq, k_col0=c, v_col0=2 * c)
+        av = torch.empty((n_img * hw, c), dtype=torch.float16, device=self.dev)
+        ops.copy_rows_seq(a, av, hw, src_seq=seq, src_off=0, dst_seq=hw, dst_off=0, groups=n_img)
+        x = ops.linear(av, Fz.out.w, Fz.out.b, gamma=Fz.g_attn, residual=x)
+        n2 = ops.layernorm(x, Fz.norm2.w, Fz.norm2.b)
+        gg = ops.linear(n2, Fz.ff1.w, Fz.ff1.b, act=ops.ACT_GEGLU)
+        return ops.linear(gg, Fz.ff2.w, Fz.ff2.b, gamma=Fz.g_dense, residual=x)
+
+    def _position_net(self, gligen):
+        """PositionNet.forward, text-only features (models/unet_3d_condition.py:119-150)."""
+        P = self.w["position_net"]
+        h = ops.gligen_prep(gligen["boxes"], gligen["masks"], gligen["positive_embeddings"], P.null_pos, P.null_xyxy)
+        h = ops.linear(h, P.l0.w, P.l0.b, act=ops.ACT_SILU)
+        h = ops.linear(h, P.l2.w, P.l2.b, act=ops.ACT_SILU)
+        return ops.linear(h, P.l4.w, P.l4.b)
+
+    def _block(self, B, t, *, heads, spatial, n_img, hw, batch, frames, ctx_kv=None, key=None, capture=None,
+               objs=None):
         c = t.shape[1]
         n1 = ops.layernorm(t, B.norm1.w, B.norm1.b)
         qkv = ops.linear(n1, B.qkv1)
@@ -174,6 +218,8 @@ class UNetEngine:
             a = ops.attention(qkv, qkv, heads=heads, nz=batch, temporal=True, frames=frames, hw=hw, k_col0=c,
                               v_col0=2 * c)
         t = ops.linear(a, B.out1.w, B.out1.b, residual=t)
+        if spatial and objs is not None and "fuser" in B and self.fuser_enabled:
+            t = self._fuser(B.fuser, t, objs, heads=heads, n_img=n_img, hw=hw)
         n2 = ops.layernorm(t, B.norm2.w, B.norm2.b)
         if spatial:
             q = ops.linear(n2, B.q2)
@@ -193,17 +239,17 @@ class UNetEngine:
         return ops.linear(gg, B.ff2.w, B.ff2.b, residual=t)
 
     def _transformer(self, T, x, *, spatial, n_img, hw, batch, frames, ctx_kv=None, key=None, capture=None,
-                     out=None):
+                     out=None, objs=None):
         samples = n_img if spatial else batch
         t = ops.groupnorm(x, samples, T.norm.w, T.norm.b, 1e-6, silu=False)
         t = ops.linear(t, T.proj_in.w, T.proj_in.b)
         heads = t.shape[1] // self.cfg["attention_head_dim"]
         t = self._block(T.block, t, heads=heads, spatial=spatial, n_img=n_img, hw=hw, batch=batch, frames=frames,
-                        ctx_kv=ctx_kv, key=key, capture=capture)
+                        ctx_kv=ctx_kv, key=key, capture=capture, objs=objs)
         return ops.linear(t, T.proj_out.w, T.proj_out.b, residual=x, out=out)
 
     # ------------------------------------------------------------------------------------------------ forward
-    def forward(self, sample, timestep, encoder_hidden_states, *, capture=None, stop_after_key=None):
+    def forward(self, sample, timestep, encoder_hidden_states, *, capture=None, stop_after_key=None, gligen=None):
         """sample (B, 4, F, h, w) fp16 cuda; timestep scalar / 0-d / (B,) ; encoder_hidden_states (B, 77, D) fp16.
         `capture(key, n_img, heads, hw) -> dict(p_full=..., p_tok=..., tok_cols=...)` is consulted for every
         cross-attention key (kind, stage, layer, 0)."""
@@ -231,6 +277,11 @@ class UNetEngine:
         x = ops.conv_in(sample, w["conv_in"].w, w["conv_in"].b)
         hw = h * w_
         x = self._transformer(w["transformer_in"], x, spatial=False, n_img=n_img, hw=hw, batch=b, frames=frames)
+        objs = None
+        if gligen is not None:
+            if "position_net" not in w:
+                raise ValueError("`gligen` inputs given but the model has no GLIGEN weights (attention_type='default')")
+            objs = self._position_net(gligen)  # unet_3d_condition.py:739-748
 
         class _Stop(Exception):
             pass
@@ -242,7 +293,7 @@ class UNetEngine:
             if "attn" in L:
                 key = (kind, stage, j, 0)
                 x = self._transformer(L.attn, x, spatial=True, n_img=n_img, hw=hw, batch=b, frames=frames, ctx_kv=ctx,
-                                      key=key, capture=capture)
+                                      key=key, capture=capture, objs=objs)
                 if stop_after_key is not None and key == tuple(stop_after_key):
                     raise _Stop()
                 x = self._transformer(L.tattn, x, spatial=False, n_img=n_img, hw=hw, batch=b, frames=frames)
@@ -264,7 +315,7 @@ class UNetEngine:
             x = self._resnet(M.res0, x, n_img, h, w_, temb_all)
             x = self._tconv(M.tconv0, x, b, frames, hw)
             x = self._transformer(M.attn, x, spatial=True, n_img=n_img, hw=hw, batch=b, frames=frames, ctx_kv=ctx,
-                                  key=("mid", 0, 0, 0), capture=capture)
+                                  key=("mid", 0, 0, 0), capture=capture, objs=objs)
             x = self._transformer(M.tattn, x, spatial=False, n_img=n_img, hw=hw, batch=b, frames=frames)
             x = self._resnet(M.res1, x, n_img, h, w_, temb_all)
             x = self._tconv(M.tconv1, x, b, frames, hw)

@@ -389,3 +389,27 @@ def box_energy(p, loss, boxes, slot_weight, *, frames, heads, H, W, slot_col=Non
     with _Timed("box_energy", 0.0, 2.0 * p.numel()):
         _lib.check(_lib.lib().lvd_box_energy(ctypes.byref(d), _stream()), "box_energy")
     return loss
+
+
+# ----------------------------------------------------------------------------------------------- GLIGEN helpers
+def copy_rows_seq(x, out, n, *, src_seq, src_off, dst_seq, dst_off, groups):
+    _check_act(x, "x")
+    _check_act(out, "out")
+    _lib.check(_lib.lib().lvd_copy_rows_seq(x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), groups * n,
+                                            x.shape[1], n, src_seq, src_off, dst_seq, dst_off, _stream()),
+               "copy_rows_seq")
+    return out
+
+
+def gligen_prep(boxes, masks, positive_embeddings, null_positive, null_position):
+    """boxes (N, n_obj, 4), masks (N, n_obj), positive_embeddings (N, n_obj, D) -> [N*n_obj, D+64] fp16."""
+    n, no, d = positive_embeddings.shape
+    dev = null_positive.device
+    b = boxes.to(device=dev, dtype=torch.float16).contiguous()
+    m = masks.to(device=dev, dtype=torch.float16).contiguous()
+    pe = positive_embeddings.to(device=dev, dtype=torch.float16).contiguous()
+    out = torch.empty((n * no, d + 64), dtype=torch.float16, device=dev)
+    _lib.check(_lib.lib().lvd_gligen_prep(b.data_ptr(), m.data_ptr(), pe.data_ptr(), null_positive.data_ptr(),
+                                          null_position.data_ptr(), out.data_ptr(), n * no, d, _stream()),
+               "gligen_prep")
+    return out

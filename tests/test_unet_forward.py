@@ -59,3 +59,76 @@ def test_unet_forward_tiny(cuda, b, f, h, w):
     for k in keys:
         d = (maps[k].float() - saved32[k]).abs().max().item()
         assert d < 2e-3, (k, d)
+
+
+def test_unet_forward_tiny_gligen(cuda):
+    """GLIGEN path: PositionNet + 16 GatedSelfAttentionDense fusers (configs 3/4 of BASELINE.json)."""
+    from lvd_b200.engine import UNetEngine
+    from oracle import unet3d_ref as R
+    from oracle import weights
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    cfg = weights.make_cfg("tiny", gated=True)
+    sd16 = {k: v.half() for k, v in weights.random_state_dict(cfg, seed=2).items()}
+    sd32 = {k: v.float().to(cuda) for k, v in sd16.items()}
+    b, f, h, w = 2, 4, 16, 16
+    x, ehs = _inputs(cfg, b, f, h, w, cuda, seed=3)
+    g = torch.Generator().manual_seed(9)
+    boxes = torch.rand((b * f, 30, 4), generator=g).half().to(cuda)
+    masks = (torch.rand((b * f, 30), generator=g) > 0.6).half().to(cuda)
+    pe = torch.randn((b * f, 30, cfg["cross_attention_dim"]), generator=g).half().to(cuda)
+    gl = dict(boxes=boxes, masks=masks, positive_embeddings=pe)
+    with torch.no_grad():
+        y32 = R.unet_forward(sd32, cfg, x.half().float(), 300, ehs.half().float(),
+                             gligen={k: v.float() for k, v in gl.items()})
+        y_off = R.unet_forward(sd32, cfg, x.half().float(), 300, ehs.half().float())
+    eng = UNetEngine(cfg, sd16, device=cuda)
+    y = eng.forward(x.half(), 300, ehs.half(), gligen=gl)
+    e = rel_err(y, y32)
+    print(f"\n[unet tiny gligen] engine-vs-fp32 {e:.3e}; fuser effect {rel_err(y_off, y32):.3e}")
+    assert e <= 3e-3
+    assert rel_err(y_off, y32) > 10 * e  # the fusers actually change the output
+    eng.fuser_enabled = False
+    assert rel_err(eng.forward(x.half(), 300, ehs.half(), gligen=gl), y_off) <= 3e-3
+
+
+def test_unet_mirror_api_and_golden(cuda):
+    """The reference-shaped class (UNet3DConditionModel.forward + save_attn_to_dict) against the golden vectors that
+    the reference's own modules produced (oracle/make_golden.py)."""
+    import os
+    import numpy as np
+    from lvd_b200.models.unet_3d_condition import UNet3DConditionModel, UNet3DConditionOutput
+    from oracle import weights
+    from oracle.make_golden import CASES
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    for name, (gated, B, F, h, w, seed) in CASES.items():
+        g = np.load(os.path.join(gold, name + ".npz"))
+        cfg = weights.make_cfg("tiny", gated=gated)
+        m = UNet3DConditionModel(sample_size=16, block_out_channels=cfg["block_out_channels"],
+                                 cross_attention_dim=cfg["cross_attention_dim"],
+                                 attention_type="gated" if gated else "default")
+        m.load_state_dict(weights.random_state_dict(cfg, seed=seed))
+        m.to(torch.float16).to("cuda")
+        saved = {}
+        keys = [("down", 1, 0, 0), ("down", 2, 0, 0), ("down", 2, 1, 0), ("up", 1, 0, 0), ("up", 1, 1, 0),
+                ("up", 2, 2, 0)]
+        kw = {"save_attn_to_dict": saved, "save_keys": keys}
+        if gated:
+            kw["gligen"] = dict(boxes=torch.from_numpy(g["gligen_boxes"]), masks=torch.from_numpy(g["gligen_masks"]),
+                                positive_embeddings=torch.from_numpy(g["gligen_pe"]))
+        out = m(torch.from_numpy(g["sample"]).half().cuda(), int(g["timestep"]),
+                encoder_hidden_states=torch.from_numpy(g["ehs"]).half().cuda(), cross_attention_kwargs=kw)
+        assert isinstance(out, UNet3DConditionOutput)
+        ref = torch.from_numpy(g["unet_out"]).cuda()
+        e = rel_err(out.sample, ref)
+        print(f"\n[golden {name}] engine fp16 vs reference fp32: {e:.3e}")
+        assert e <= 4e-3
+        for k in keys:
+            assert saved[k].shape == (B * F, cfg["block_out_channels"][k[1]] // 64, (h >> k[1]) * (w >> k[1]), 77)
+            cols = saved[k][..., [1, 2, 4, 6, 7]].float()
+            assert (cols - torch.from_numpy(g["attn_" + "_".join(map(str, k))]).float().cuda()).abs().max() < 3e-3
+    with pytest.raises(TypeError):
+        m(torch.zeros(1, 4, 2, 8, 8).half().cuda(), 1, encoder_hidden_states=torch.zeros(1, 77, 128).half().cuda())
+    with pytest.raises(NotImplementedError):
+        m(torch.zeros(1, 4, 2, 8, 8).half().cuda(), 1, encoder_hidden_states=torch.zeros(1, 77, 128).half().cuda(),
+          cross_attention_kwargs={}, attention_mask=torch.ones(1, 1))
