@@ -83,8 +83,12 @@ int lvd_gemm(const lvd_gemm_desc* d, void* stream);
  *   [z / kv_z_div][s_k] of the same buffer `kv` at columns k_col0 / v_col0 (+ head*64).  kv_z_div = F lets all
  *   frames of a video share one text K/V (the reference repeat_interleaves encoder_hidden_states instead,
  *   unet_3d_condition.py:721-723).
- * mode 1 (temporal): rows are ((z*frames + f)*hw + p); the sequence of pixel p is its `frames` rows
+ * mode 1 (temporal, gathered): rows are ((z*frames + f)*hw + p); the sequence of pixel p is its `frames` rows
  *   (transformer_temporal.py:142-156 permutes instead).  Q, K, V in one buffer.
+ * mode 2 (temporal, packed): rows are ((z*hw + p)*frames + f), i.e. every `frames` consecutive rows are one
+ *   sequence (the QKV projection writes this order through lvd_gemm's output row mapping, the output projection
+ *   reads it back); frames % 8 == 0.  This is the fast path: contiguous TMA boxes, per-row window softmax.
+ * lse (optional, fp32 [nz, heads, rows]) receives log2-domain logsumexp of every query row for the backward kernels.
  * Output row order == Q row order; column o_col0 + head*64.
  * Optional (s_k <= 128 only): p_full [nz, heads, s_q, s_k] fp16 = the reference's saved attention map
  *   (attention_processor.py:553-586); p_tok [n_tok, nz, heads, s_q] = selected text-token columns only
@@ -96,6 +100,7 @@ typedef struct lvd_attn_desc {
   void* out;
   void* p_full;
   void* p_tok;
+  float* lse;
   int64_t ld_q, ld_kv, ld_o;
   int64_t q_width, kv_width; /* logical column counts of the q / kv buffers (TMA bounds) */
   int64_t s_q, s_k;          /* mode 0 */
@@ -195,6 +200,40 @@ int lvd_copy_rows_seq(const void* x, int64_t ld_x, void* y, int64_t ld_y, int64_
                       int32_t src_seq, int32_t src_off, int32_t dst_seq, int32_t dst_off, void* stream);
 int lvd_gligen_prep(const void* boxes, const void* masks, const void* positive_embeddings, const void* null_positive,
                     const void* null_position, void* out, int64_t n_obj, int32_t dim, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Input-gradient kernels of the guidance path -- replace torch.autograd.grad(loss, [latents])
+ * (models/pipelines.py:120).  Only d/d(latents) exists; weight gradients are never formed.  Linear / Conv dgrads run
+ * on lvd_gemm (b_mn_major = 1, per-tap weight column offsets); these are the HBM-bound adjoints around them.
+ *   lvd_groupnorm_bwd : GroupNorm (+ fused SiLU) adjoint; same sample/row view as lvd_groupnorm; recomputes the
+ *                       forward statistics; accumulate != 0 adds into dx (gradient fan-in of a residual branch).
+ *                       workspace >= 2 x the forward requirement.
+ *   lvd_layernorm_bwd : LayerNorm adjoint (row statistics recomputed).
+ *   lvd_geglu / lvd_geglu_bwd : un-fused GEGLU on the value/gate-interleaved projection (the guidance forward keeps
+ *                       the pre-activation so that the adjoint needs no recomputation), models/attention.py:355-376.
+ *   lvd_add_rows, lvd_upsample2x_bwd, lvd_conv_in_bwd (fp32 d_sample in NCFHW), lvd_attn_rowdot
+ *                       (D[row, head] = <O, dO>, the softmax-adjoint row term),
+ *   lvd_latent_update : latents - sqrt(1 - alpha_bar_t) * grad (models/pipelines.py:124-132) from the fp32 gradient.
+ * ---------------------------------------------------------------------------------------------------------- */
+int lvd_groupnorm_bwd(const void* x, int64_t ld_x, const void* dz, int64_t ld_dz, void* dx, int64_t ld_dx,
+                      int32_t samples, int64_t rows_per_sample, int32_t channels, int32_t groups, const void* gamma,
+                      const void* beta, float eps, int32_t silu, int32_t accumulate, void* workspace,
+                      int64_t workspace_bytes, void* stream);
+int lvd_layernorm_bwd(const void* x, int64_t ld_x, const void* dy, int64_t ld_dy, void* dx, int64_t ld_dx, int64_t rows,
+                      int32_t channels, const void* gamma, float eps, int32_t accumulate, void* stream);
+int lvd_geglu(const void* pre, int64_t ld_pre, void* out, int64_t ld_out, int64_t rows, int32_t n_out, void* stream);
+int lvd_geglu_bwd(const void* pre, int64_t ld_pre, const void* dout, int64_t ld_dout, void* dpre, int64_t ld_dpre,
+                  int64_t rows, int32_t n_out, void* stream);
+int lvd_add_rows(const void* a, int64_t ld_a, const void* b, int64_t ld_b, void* out, int64_t ld_out, int64_t rows,
+                 int32_t channels, void* stream);
+int lvd_upsample2x_bwd(const void* dy, int64_t ld_dy, void* dx, int64_t ld_dx, int32_t n_img, int32_t height,
+                       int32_t width, int32_t channels, void* stream);
+int lvd_conv_in_bwd(const void* drows, int64_t ld, const void* weight, void* dsample_f32, int32_t batch, int32_t cin,
+                    int32_t frames, int32_t height, int32_t width, int32_t cout, void* stream);
+int lvd_latent_update(const void* latents, const void* grad_f32, void* out, void* grad_h_out, int64_t n, float coef,
+                      float unscale, void* stream);
+int lvd_attn_rowdot(const void* o, int64_t ld_o, const void* d_o, int64_t ld_do, void* out_f32, int64_t rows,
+                    int32_t heads, void* stream);
 
 #ifdef __cplusplus
 }

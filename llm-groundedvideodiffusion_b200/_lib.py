@@ -46,6 +46,7 @@ class AttnDesc(ctypes.Structure):
         ("out", ctypes.c_void_p),
         ("p_full", ctypes.c_void_p),
         ("p_tok", ctypes.c_void_p),
+        ("lse", ctypes.c_void_p),
         ("ld_q", ctypes.c_int64),
         ("ld_kv", ctypes.c_int64),
         ("ld_o", ctypes.c_int64),
@@ -134,6 +135,15 @@ def _declare(l):
     l.lvd_box_energy.argtypes = [ctypes.POINTER(EnergyDesc), vp]
     l.lvd_copy_rows_seq.argtypes = [vp, i64, vp, i64, i64, i32, i32, i32, i32, i32, i32, vp]
     l.lvd_gligen_prep.argtypes = [vp, vp, vp, vp, vp, vp, i64, i32, vp]
+    l.lvd_groupnorm_bwd.argtypes = [vp, i64, vp, i64, vp, i64, i32, i64, i32, i32, vp, vp, f32, i32, i32, vp, i64, vp]
+    l.lvd_layernorm_bwd.argtypes = [vp, i64, vp, i64, vp, i64, i64, i32, vp, f32, i32, vp]
+    l.lvd_geglu.argtypes = [vp, i64, vp, i64, i64, i32, vp]
+    l.lvd_geglu_bwd.argtypes = [vp, i64, vp, i64, vp, i64, i64, i32, vp]
+    l.lvd_add_rows.argtypes = [vp, i64, vp, i64, vp, i64, i64, i32, vp]
+    l.lvd_upsample2x_bwd.argtypes = [vp, i64, vp, i64, i32, i32, i32, i32, vp]
+    l.lvd_conv_in_bwd.argtypes = [vp, i64, vp, vp, i32, i32, i32, i32, i32, i32, vp]
+    l.lvd_latent_update.argtypes = [vp, vp, vp, vp, i64, f32, f32, vp]
+    l.lvd_attn_rowdot.argtypes = [vp, i64, vp, i64, vp, i64, i32, vp]
     for name in EXPORTS:
         fn = getattr(l, name)
         if name not in ("lvd_last_error", "lvd_launch_count"):
@@ -160,6 +170,15 @@ EXPORTS = [
     "lvd_box_energy",
     "lvd_copy_rows_seq",
     "lvd_gligen_prep",
+    "lvd_groupnorm_bwd",
+    "lvd_layernorm_bwd",
+    "lvd_geglu",
+    "lvd_geglu_bwd",
+    "lvd_add_rows",
+    "lvd_upsample2x_bwd",
+    "lvd_conv_in_bwd",
+    "lvd_latent_update",
+    "lvd_attn_rowdot",
 ]
 
 

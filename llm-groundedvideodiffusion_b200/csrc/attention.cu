@@ -40,6 +40,8 @@ struct AttnArgs {
   int n_tok;
   int tok_cols[16];
   int last_cols16;
+  int seq_len;  // > 0: packed-sequence (temporal) mode
+  float* lse;   // optional [nz, heads, p_rows] log2-domain logsumexp (multi-unit mode), for the backward kernels
   float scale_log2;
   uint32_t idesc_qk_full, idesc_qk_last, idesc_pv;
 };
@@ -65,10 +67,11 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid
   const int h = blockIdx.x, qt = blockIdx.y, z = blockIdx.z;
   if ((smem_u32(smem) & 1023u) != 0) __trap();
 
-  if (g.q_bytes < kTile || g.kv_bytes < kTile) {
+  if (g.q_bytes < kTile || g.kv_bytes < kTile || g.seq_len > 0) {
     // partial boxes (temporal packing): rows the TMA never writes must hold finite values (0 * NaN = NaN in P V)
     uint4 zero = make_uint4(0, 0, 0, 0);
-    for (int i = threadIdx.x; i < 5 * kTile / 16; i += kAttnThreads) reinterpret_cast<uint4*>(smem)[i] = zero;
+    const int nfill = (g.seq_len > 0 ? 7 : 5) * kTile / 16;  // packed mode also needs zeros in P outside the windows
+    for (int i = threadIdx.x; i < nfill; i += kAttnThreads) reinterpret_cast<uint4*>(smem)[i] = zero;
     fence_proxy_async_smem();
   }
   if (threadIdx.x == 0) {
@@ -147,136 +150,232 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid
     const int j1 = r % g.qb1, j2 = r / g.qb1;
     const int c1 = qt * g.qb1 + j1;
     const bool row_valid = (j2 < g.qb2) && (c1 < g.q_dim1);
-    const int diag = g.diag_mod;
-    const int rmod = diag ? (r % diag) : 0;
-    const bool single = (g.n_units == 1);
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
     const float sc = g.scale_log2;
-    float m_run = -INFINITY, l_run = 0.f;
-    float o[64];
-#pragma unroll
-    for (int i = 0; i < 64; ++i) o[i] = 0.f;
     uint8_t* p_row = sP + r * 128;
+    __half* dst = g.out + (static_cast<long long>(z) * g.o_z_stride + static_cast<long long>(j2) * g.o_d2_stride +
+                           static_cast<long long>(c1) * g.o_d1_stride) *
+                              g.ld_o +
+                  g.o_col0 + h * 64;
 
-    for (int u = 0; u < g.n_units; ++u) {
-      const bool last = (u == g.n_units - 1);
-      const int ncols = last ? g.last_cols16 : 128;
-      const int nchunks = (ncols + 31) / 32;
-      int nvalid = g.kv_total - u * 128;
-      if (nvalid > 128) nvalid = 128;
-      mbar_wait(s_full, u & 1);
+    if (g.seq_len > 0) {
+      // ---------------- packed sequences (temporal attention): rows [i*F, (i+1)*F) of the tile form sequence i.
+      // Only the F columns of the row's own sequence matter, so each warp loads the union window of its 32 rows
+      // (<= 64 columns) once, keeps it in registers, and writes exact fp16 probabilities; everything outside the
+      // window stays zero from the initial fill of sP.
+      const int F = g.seq_len;
+      const int wbase = (q * 32) / F * F;
+      int wend = ((q * 32 + 31) / F + 1) * F;
+      if (wend > 128) wend = 128;
+      const int nch = (wend - wbase + 7) >> 3;
+      const int mystart = (r / F) * F;
+      mbar_wait(s_full, 0);
       tc_fence_after();
-      // ---- pass 1: row maximum
+      float sv[8][8];
       float mx = -INFINITY;
-      for (int ch = 0; ch < nchunks; ++ch) {
-        uint32_t rr[32];
-        tmem_ld32(tmem_s + lane_off + ch * 32, rr);
-        tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int c = ch * 32 + i;
-          const bool ok = (c < nvalid) && (diag == 0 || (c % diag) == rmod);
-          const float s = ok ? __uint_as_float(rr[i]) * sc : -INFINITY;
-          mx = fmaxf(mx, s);
-        }
-      }
-      float m_new = fmaxf(m_run, mx);
-      if (!(m_new > -INFINITY)) m_new = 0.f;  // fully masked / garbage row: keep arithmetic finite
-      float inv = 1.f;
-      if (single) {
-        // ---- pass 2 (single-unit modes): exact denominator, so that the fp16 probabilities equal the reference's
-        float sum = 0.f;
-        for (int ch = 0; ch < nchunks; ++ch) {
-          uint32_t rr[32];
-          tmem_ld32(tmem_s + lane_off + ch * 32, rr);
+      for (int k = 0; k < 8; ++k) {
+        if (k < nch) {
+          uint32_t rr[8];
+          tmem_ld8(tmem_s + lane_off + wbase + k * 8, rr);
           tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const int c = ch * 32 + i;
-            const bool ok = (c < nvalid) && (diag == 0 || (c % diag) == rmod);
-            sum += ok ? exp2f(__uint_as_float(rr[i]) * sc - m_new) : 0.f;
+          for (int i = 0; i < 8; ++i) {
+            const int c = wbase + k * 8 + i;
+            const bool ok = (c >= mystart) && (c < mystart + F) && (c < g.kv_total);
+            sv[k][i] = ok ? __uint_as_float(rr[i]) * sc : -INFINITY;
+            mx = fmaxf(mx, sv[k][i]);
           }
         }
-        inv = 1.f / sum;
       }
-      const float alpha = exp2f(m_run - m_new);
-      float psum = 0.f;
-      // ---- pass 3: probabilities -> fp16 -> swizzled smem (A operand of P V)
-      for (int ch = 0; ch < nchunks; ++ch) {
-        uint32_t rr[32];
-        tmem_ld32(tmem_s + lane_off + ch * 32, rr);
-        tmem_ld_wait();
-        float p[32];
+      if (!(mx > -INFINITY)) mx = 0.f;
+      float sum = 0.f;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int c = ch * 32 + i;
-          const bool ok = (c < nvalid) && (diag == 0 || (c % diag) == rmod);
-          const float e = ok ? exp2f(__uint_as_float(rr[i]) * sc - m_new) * inv : 0.f;
-          p[i] = e;
-          psum += e;
+      for (int k = 0; k < 8; ++k) {
+        if (k < nch) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            sv[k][i] = exp2f(sv[k][i] - mx);
+            sum += sv[k][i];
+          }
         }
-        uint8_t* blk = p_row + (ch >> 1) * kTile;
+      }
+      const float inv = 1.f / sum;
 #pragma unroll
-        for (int s8 = 0; s8 < 4; ++s8) {
+      for (int k = 0; k < 8; ++k) {
+        if (k < nch) {
           uint4 v;
           __half2* hh = reinterpret_cast<__half2*>(&v);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) hh[i] = __floats2half2_rn(p[s8 * 8 + 2 * i], p[s8 * 8 + 2 * i + 1]);
-          const int chunk16 = ((ch & 1) * 4 + s8) ^ (r & 7);
-          *reinterpret_cast<uint4*>(blk + chunk16 * 16) = v;
-        }
-        if (single && row_valid) {
-          if (g.p_full) {
-            __half* dst = g.p_full + ((static_cast<long long>(z) * g.heads + h) * g.p_rows + c1) * g.kv_total;
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (ch * 32 + i < g.kv_total) dst[ch * 32 + i] = __float2half_rn(p[i]);
-          }
-          if (g.p_tok) {
-            for (int t = 0; t < g.n_tok; ++t) {
-              const int col = g.tok_cols[t] - ch * 32;
-              if (col >= 0 && col < 32) {
-                float pv = 0.f;
-#pragma unroll
-                for (int i = 0; i < 32; ++i) pv = (i == col) ? p[i] : pv;
-                g.p_tok[((static_cast<long long>(t) * g.nz + z) * g.heads + h) * g.p_rows + c1] = __float2half_rn(pv);
-              }
-            }
-          }
+          for (int i = 0; i < 4; ++i) hh[i] = __floats2half2_rn(sv[k][2 * i] * inv, sv[k][2 * i + 1] * inv);
+          const int col = wbase + k * 8;
+          *reinterpret_cast<uint4*>(p_row + (col >> 6) * kTile + ((((col & 63) >> 3) ^ (r & 7)) << 4)) = v;
         }
       }
-      l_run = l_run * alpha + psum;
-      m_run = m_new;
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(p_full);
-      // ---- O accumulation
-      mbar_wait(o_full, u & 1);
+      mbar_wait(o_full, 0);
       tc_fence_after();
 #pragma unroll
       for (int hlf = 0; hlf < 2; ++hlf) {
         uint32_t rr[32];
         tmem_ld32(tmem_o + lane_off + hlf * 32, rr);
         tmem_ld_wait();
+        if (row_valid) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) o[hlf * 32 + i] = o[hlf * 32 + i] * alpha + __uint_as_float(rr[i]);
+          for (int s8 = 0; s8 < 4; ++s8) {
+            uint4 v;
+            __half2* hh = reinterpret_cast<__half2*>(&v);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              hh[i] = __floats2half2_rn(__uint_as_float(rr[s8 * 8 + 2 * i]), __uint_as_float(rr[s8 * 8 + 2 * i + 1]));
+            *reinterpret_cast<uint4*>(dst + hlf * 32 + s8 * 8) = v;
+          }
+        }
       }
       tc_fence_before();
-    }
-    if (row_valid) {
-      const float fin = single ? 1.f : 1.f / l_run;
-      __half* dst = g.out + (static_cast<long long>(z) * g.o_z_stride + static_cast<long long>(j2) * g.o_d2_stride +
-                             static_cast<long long>(c1) * g.o_d1_stride) *
-                                g.ld_o +
-                    g.o_col0 + h * 64;
+    } else {
+      const int diag = g.diag_mod;
+      const int rmod = diag ? (r % diag) : 0;
+      const bool single = (g.n_units == 1);
+      float m_run = -INFINITY, l_run = 0.f;
+      float o[64];
 #pragma unroll
-      for (int s8 = 0; s8 < 8; ++s8) {
-        uint4 v;
-        __half2* hh = reinterpret_cast<__half2*>(&v);
+      for (int i = 0; i < 64; ++i) o[i] = 0.f;
+
+      for (int u = 0; u < g.n_units; ++u) {
+        const bool last = (u == g.n_units - 1);
+        const int ncols = last ? g.last_cols16 : 128;
+        const int nchunks = (ncols + 31) / 32;
+        int nvalid = g.kv_total - u * 128;
+        if (nvalid > 128) nvalid = 128;
+        const bool full = (nvalid == 128) && (diag == 0) && !single;  // no masking needed anywhere in this unit
+        mbar_wait(s_full, u & 1);
+        tc_fence_after();
+        // ---- pass 1: row maximum
+        float mx = -INFINITY;
+        for (int ch = 0; ch < nchunks; ++ch) {
+          uint32_t rr[32];
+          tmem_ld32(tmem_s + lane_off + ch * 32, rr);
+          tmem_ld_wait();
+          if (full) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-          hh[i] = __floats2half2_rn(o[s8 * 8 + 2 * i] * fin, o[s8 * 8 + 2 * i + 1] * fin);
-        *reinterpret_cast<uint4*>(dst + s8 * 8) = v;
+            for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(rr[i]));
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const int c = ch * 32 + i;
+              const bool ok = (c < nvalid) && (diag == 0 || (c % diag) == rmod);
+              mx = fmaxf(mx, ok ? __uint_as_float(rr[i]) : -INFINITY);
+            }
+          }
+        }
+        mx *= sc;  // sc > 0
+        float m_new = fmaxf(m_run, mx);
+        if (!(m_new > -INFINITY)) m_new = 0.f;  // fully masked / garbage row: keep arithmetic finite
+        float inv = 1.f;
+        if (single) {
+          // ---- pass 2 (single-unit modes): exact denominator, so that the fp16 probabilities equal the reference's
+          float sum = 0.f;
+          for (int ch = 0; ch < nchunks; ++ch) {
+            uint32_t rr[32];
+            tmem_ld32(tmem_s + lane_off + ch * 32, rr);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const int c = ch * 32 + i;
+              const bool ok = (c < nvalid) && (diag == 0 || (c % diag) == rmod);
+              sum += ok ? exp2f(fmaf(__uint_as_float(rr[i]), sc, -m_new)) : 0.f;
+            }
+          }
+          inv = 1.f / sum;
+        }
+        const float alpha = exp2f(m_run - m_new);
+        float psum = 0.f;
+        // ---- pass 3: probabilities -> fp16 -> swizzled smem (A operand of P V)
+        for (int ch = 0; ch < nchunks; ++ch) {
+          uint32_t rr[32];
+          tmem_ld32(tmem_s + lane_off + ch * 32, rr);
+          tmem_ld_wait();
+          float p[32];
+          if (full) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              p[i] = exp2f(fmaf(__uint_as_float(rr[i]), sc, -m_new));
+              psum += p[i];
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const int c = ch * 32 + i;
+              const bool ok = (c < nvalid) && (diag == 0 || (c % diag) == rmod);
+              const float e = ok ? exp2f(fmaf(__uint_as_float(rr[i]), sc, -m_new)) * inv : 0.f;
+              p[i] = e;
+              psum += e;
+            }
+          }
+          uint8_t* blk = p_row + (ch >> 1) * kTile;
+#pragma unroll
+          for (int s8 = 0; s8 < 4; ++s8) {
+            uint4 v;
+            __half2* hh = reinterpret_cast<__half2*>(&v);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) hh[i] = __floats2half2_rn(p[s8 * 8 + 2 * i], p[s8 * 8 + 2 * i + 1]);
+            const int chunk16 = ((ch & 1) * 4 + s8) ^ (r & 7);
+            *reinterpret_cast<uint4*>(blk + chunk16 * 16) = v;
+          }
+          if (single && row_valid) {
+            if (g.p_full) {
+              __half* pd = g.p_full + ((static_cast<long long>(z) * g.heads + h) * g.p_rows + c1) * g.kv_total;
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (ch * 32 + i < g.kv_total) pd[ch * 32 + i] = __float2half_rn(p[i]);
+            }
+            if (g.p_tok) {
+              for (int t = 0; t < g.n_tok; ++t) {
+                const int col = g.tok_cols[t] - ch * 32;
+                if (col >= 0 && col < 32) {
+                  float pv = 0.f;
+#pragma unroll
+                  for (int i = 0; i < 32; ++i) pv = (i == col) ? p[i] : pv;
+                  g.p_tok[((static_cast<long long>(t) * g.nz + z) * g.heads + h) * g.p_rows + c1] =
+                      __float2half_rn(pv);
+                }
+              }
+            }
+          }
+        }
+        l_run = l_run * alpha + psum;
+        m_run = m_new;
+        fence_proxy_async_smem();
+        tc_fence_before();
+        mbar_arrive(p_full);
+        // ---- O accumulation
+        mbar_wait(o_full, u & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int hlf = 0; hlf < 2; ++hlf) {
+          uint32_t rr[32];
+          tmem_ld32(tmem_o + lane_off + hlf * 32, rr);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[hlf * 32 + i] = fmaf(o[hlf * 32 + i], alpha, __uint_as_float(rr[i]));
+        }
+        tc_fence_before();
+      }
+      if (row_valid) {
+        const float fin = single ? 1.f : 1.f / l_run;
+        if (g.lse) g.lse[(static_cast<long long>(z) * g.heads + h) * g.p_rows + c1] = m_run + log2f(l_run);
+#pragma unroll
+        for (int s8 = 0; s8 < 8; ++s8) {
+          uint4 v;
+          __half2* hh = reinterpret_cast<__half2*>(&v);
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            hh[i] = __floats2half2_rn(o[s8 * 8 + 2 * i] * fin, o[s8 * 8 + 2 * i + 1] * fin);
+          *reinterpret_cast<uint4*>(dst + s8 * 8) = v;
+        }
       }
     }
   }
@@ -330,6 +429,37 @@ extern "C" int lvd_attention(const lvd_attn_desc* d, void* stream) {
     g.o_d2_stride = 0;
     g.o_z_stride = d->s_q;
     g.p_rows = d->s_q;
+  } else if (d->mode == 2) {
+    // packed sequences: rows (z*hw + p)*F + f -- every F consecutive rows are one sequence; bp sequences per tile
+    const int F = d->frames;
+    LVD_REQUIRE(F >= 8 && F <= 64 && F % 8 == 0 && d->hw >= 1, "lvd_attention: packed mode needs frames %% 8 == 0 (got %d)", F);
+    int bp = 128 / F;
+    if (bp > d->hw) bp = static_cast<int>(d->hw);
+    const int64_t rows_z = d->hw * F;
+    int64_t qd[4] = {width_q, rows_z, 1, d->nz};
+    int64_t qs[4] = {1, d->ld_q, d->ld_q * rows_z, d->ld_q * rows_z};
+    int qb[4] = {64, bp * F, 1, 1};
+    rc = encode_tmap_f16_sw128(&g.map_q, d->q, 4, qd, qs, qb);
+    if (rc) return rc;
+    int64_t kd[4] = {width_kv, rows_z, 1, d->nz};
+    int64_t ks[4] = {1, d->ld_kv, d->ld_kv * rows_z, d->ld_kv * rows_z};
+    rc = encode_tmap_f16_sw128(&g.map_kv, d->kv, 4, kd, ks, qb);
+    if (rc) return rc;
+    g.qb1 = bp * F;
+    g.qb2 = 1;
+    g.q_dim1 = static_cast<int>(rows_z);
+    g.q_bytes = bp * F * 128;
+    g.kv_bytes = bp * F * 128;
+    g.kv_same_tile = 1;
+    g.n_units = 1;
+    g.kv_total = bp * F;
+    g.diag_mod = 0;
+    g.seq_len = F;
+    g.o_d1_stride = 1;
+    g.o_d2_stride = 0;
+    g.o_z_stride = rows_z;
+    g.p_rows = rows_z;
+    LVD_REQUIRE(d->kv_z_div == 1 && !d->p_full && !d->p_tok, "lvd_attention: packed mode has no kv broadcast / maps");
   } else {
     // temporal: rows ((b*F + f)*hw + p); sequence = the F frames of pixel p; bp pixels per tile
     const int F = d->frames;
@@ -374,6 +504,8 @@ extern "C" int lvd_attention(const lvd_attn_desc* d, void* stream) {
   g.out = static_cast<__half*>(d->out);
   g.p_full = static_cast<__half*>(d->p_full);
   g.p_tok = static_cast<__half*>(d->p_tok);
+  g.lse = static_cast<float*>(d->lse);
+  LVD_REQUIRE(!d->lse || g.n_units >= 1, "lvd_attention: lse");
   g.n_tok = d->n_tok;
   for (int i = 0; i < d->n_tok; ++i) g.tok_cols[i] = d->tok_cols[i];
   g.scale_log2 = d->scale * 1.4426950408889634f;

@@ -289,7 +289,7 @@ __global__ void cfg_dpm_step_kernel(const __half* __restrict__ eps_u, const __ha
       e = round_h(u + hmul(gs, round_h(c - u)));
     }
     const float xs = __half2float(x[i]);
-    const float x0 = round_h(round_h(xs - hmul(sigma_t, e)) / alpha_t);
+    const float x0 = hmul(round_h(xs - hmul(sigma_t, e)), 1.0f / alpha_t);  // torch divides by a scalar as a multiply
     float xn = c_x * xs - hmul(c_d0, x0);
     if (order == 2) {
       const float d1 = hmul(inv_r0, round_h(x0 - __half2float(x0_prev[i])));

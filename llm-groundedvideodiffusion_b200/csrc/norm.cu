@@ -52,7 +52,20 @@ __global__ void gn_stats_kernel(const __half* __restrict__ x, long long ld, long
   for (int i = 0; i < 8; ++i) sum[i] = sq[i] = 0.f;
   if (rsub < rpp) {
     const __half* base = x + (s * rows_per_sample) * ld + v * 8;
-    for (long long r = r0 + rsub; r < r1; r += rpp) {
+    long long r = r0 + rsub;
+    for (; r + 3LL * rpp < r1; r += 4LL * rpp) {  // 4 independent 16-byte loads in flight per thread
+      float t0[8], t1[8], t2[8], t3[8];
+      ld8(base + r * ld, t0);
+      ld8(base + (r + rpp) * ld, t1);
+      ld8(base + (r + 2LL * rpp) * ld, t2);
+      ld8(base + (r + 3LL * rpp) * ld, t3);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        sum[i] += (t0[i] + t1[i]) + (t2[i] + t3[i]);
+        sq[i] += (t0[i] * t0[i] + t1[i] * t1[i]) + (t2[i] * t2[i] + t3[i] * t3[i]);
+      }
+    }
+    for (; r < r1; r += rpp) {
       float t[8];
       ld8(base + r * ld, t);
 #pragma unroll
@@ -129,13 +142,32 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x, long long ld_x, __
   if (r1 > rows_per_sample) r1 = rows_per_sample;
   const __half* xb = x + (s * rows_per_sample) * ld_x + v * 8;
   __half* yb = y + (s * rows_per_sample) * ld_y + v * 8;
-  for (long long r = r0 + rsub; r < r1; r += rpp) {
+  long long r = r0 + rsub;
+  for (; r + rpp < r1; r += 2LL * rpp) {  // two rows per iteration: loads issued before the dependent math
+    float t[8], u[8];
+    ld8(xb + r * ld_x, t);
+    ld8(xb + (r + rpp) * ld_x, u);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float o = round_h((t[i] - mu[i]) * rs[i] * ga[i] + be[i]);
+      float o2 = round_h((u[i] - mu[i]) * rs[i] * ga[i] + be[i]);
+      if (silu) {
+        o = o / (1.0f + __expf(-o));
+        o2 = o2 / (1.0f + __expf(-o2));
+      }
+      t[i] = o;
+      u[i] = o2;
+    }
+    st8(yb + r * ld_y, t);
+    st8(yb + (r + rpp) * ld_y, u);
+  }
+  for (; r < r1; r += rpp) {
     float t[8];
     ld8(xb + r * ld_x, t);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       float o = round_h((t[i] - mu[i]) * rs[i] * ga[i] + be[i]);
-      if (silu) o = o / (1.0f + expf(-o));
+      if (silu) o = o / (1.0f + __expf(-o));
       t[i] = o;
     }
     st8(yb + r * ld_y, t);
@@ -155,51 +187,58 @@ constexpr int kLnMaxVec = 8;  // 8 vectors of 8 halves per lane -> C <= 2048
 __global__ void layernorm_kernel(const __half* __restrict__ x, long long ld_x, __half* __restrict__ y, long long ld_y,
                                  long long rows, int C, const __half* __restrict__ gamma,
                                  const __half* __restrict__ beta, float eps) {
-  const int lane = threadIdx.x & 31;
-  const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= rows) return;
-  const int vpr = C >> 3;
-  float vals[kLnMaxVec][8];
-  float sum = 0.f;
-  const __half* xr = x + row * ld_x;
-#pragma unroll
-  for (int k = 0; k < kLnMaxVec; ++k) {
-    const int v = lane + k * 32;
-    if (v < vpr) {
-      ld8(xr + v * 8, vals[k]);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) sum += vals[k][i];
-    }
+  extern __shared__ float s_affine[];  // gamma[C], beta[C] as fp32, loaded once per block
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    s_affine[i] = __half2float(gamma[i]);
+    s_affine[C + i] = __half2float(beta[i]);
   }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int vpr = C >> 3;
+  const long long warps_total = static_cast<long long>(gridDim.x) * (blockDim.x >> 5);
+  for (long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows;
+       row += warps_total) {
+    float vals[kLnMaxVec][8];
+    float sum = 0.f;
+    const __half* xr = x + row * ld_x;
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-  const float mean = sum / C;
-  float sq = 0.f;
+    for (int k = 0; k < kLnMaxVec; ++k) {
+      const int v = lane + k * 32;
+      if (v < vpr) {
+        ld8(xr + v * 8, vals[k]);
 #pragma unroll
-  for (int k = 0; k < kLnMaxVec; ++k) {
-    const int v = lane + k * 32;
-    if (v < vpr) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float d = vals[k][i] - mean;
-        sq += d * d;
+        for (int i = 0; i < 8; ++i) sum += vals[k][i];
       }
     }
-  }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-  const float rstd = rsqrtf(sq / C + eps);
-  __half* yr = y + row * ld_y;
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum / C;
+    float sq = 0.f;
 #pragma unroll
-  for (int k = 0; k < kLnMaxVec; ++k) {
-    const int v = lane + k * 32;
-    if (v < vpr) {
-      float ga[8], be[8], o[8];
-      ld8(gamma + v * 8, ga);
-      ld8(beta + v * 8, be);
+    for (int k = 0; k < kLnMaxVec; ++k) {
+      const int v = lane + k * 32;
+      if (v < vpr) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) o[i] = (vals[k][i] - mean) * rstd * ga[i] + be[i];
-      st8(yr + v * 8, o);
+        for (int i = 0; i < 8; ++i) {
+          const float d = vals[k][i] - mean;
+          sq += d * d;
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    const float rstd = rsqrtf(sq / C + eps);
+    __half* yr = y + row * ld_y;
+#pragma unroll
+    for (int k = 0; k < kLnMaxVec; ++k) {
+      const int v = lane + k * 32;
+      if (v < vpr) {
+        float o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          o[i] = (vals[k][i] - mean) * rstd * s_affine[v * 8 + i] + s_affine[C + v * 8 + i];
+        st8(yr + v * 8, o);
+      }
     }
   }
 }
@@ -219,8 +258,8 @@ extern "C" int lvd_groupnorm(const void* x, int64_t ld_x, void* y, int64_t ld_y,
   LVD_REQUIRE(samples >= 1 && rows_per_sample >= 1, "lvd_groupnorm: empty input");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   // enough CTAs to fill 148 SMs a few times over, but at least ~64 rows per chunk
-  long long chunks = (4LL * num_sms() + samples - 1) / samples;
-  const long long max_chunks = (rows_per_sample + 63) / 64;
+  long long chunks = (8LL * num_sms() + samples - 1) / samples;
+  const long long max_chunks = (rows_per_sample + 15) / 16;
   if (chunks > max_chunks) chunks = max_chunks;
   if (chunks < 1) chunks = 1;
   if (chunks > 1024) chunks = 1024;
@@ -248,8 +287,11 @@ extern "C" int lvd_layernorm(const void* x, int64_t ld_x, void* y, int64_t ld_y,
   LVD_REQUIRE(ld_x % 8 == 0 && ld_y % 8 == 0, "lvd_layernorm: ld must be a multiple of 8");
   if (rows <= 0) return LVD_OK;
   const int warps = 8;
-  const long long blocks = (rows + warps - 1) / warps;
-  layernorm_kernel<<<static_cast<unsigned>(blocks), warps * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+  long long blocks = (rows + warps - 1) / warps;
+  const long long cap = 8LL * num_sms();
+  if (blocks > cap) blocks = cap;
+  layernorm_kernel<<<static_cast<unsigned>(blocks), warps * 32, 2 * channels * sizeof(float),
+                     static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __half*>(x), ld_x, static_cast<__half*>(y), ld_y, rows, channels,
       static_cast<const __half*>(gamma), static_cast<const __half*>(beta), eps);
   g_launches.fetch_add(1, std::memory_order_relaxed);

@@ -211,13 +211,16 @@ class UNetEngine:
                objs=None):
         c = t.shape[1]
         n1 = ops.layernorm(t, B.norm1.w, B.norm1.b)
-        qkv = ops.linear(n1, B.qkv1)
+        packed = (not spatial) and frames % 8 == 0
+        fm2sm = ("fm2sm", batch, frames, hw) if packed else None
+        sm2fm = ("sm2fm", batch, frames, hw) if packed else None
+        qkv = ops.linear(n1, B.qkv1, row_map=fm2sm)
         if spatial:
             a = ops.attention(qkv, qkv, heads=heads, nz=n_img, s_q=hw, s_k=hw, k_col0=c, v_col0=2 * c)
         else:
             a = ops.attention(qkv, qkv, heads=heads, nz=batch, temporal=True, frames=frames, hw=hw, k_col0=c,
-                              v_col0=2 * c)
-        t = ops.linear(a, B.out1.w, B.out1.b, residual=t)
+                              v_col0=2 * c, packed=packed)
+        t = ops.linear(a, B.out1.w, B.out1.b, residual=t, row_map=sm2fm)
         if spatial and objs is not None and "fuser" in B and self.fuser_enabled:
             t = self._fuser(B.fuser, t, objs, heads=heads, n_img=n_img, hw=hw)
         n2 = ops.layernorm(t, B.norm2.w, B.norm2.b)
@@ -230,10 +233,10 @@ class UNetEngine:
             a = ops.attention(q, kv, heads=heads, nz=n_img, s_q=hw, s_k=ctx_kv.shape[0] // batch, k_col0=0, v_col0=c,
                               kv_z_div=frames, **extra)
         else:
-            qkv = ops.linear(n2, B.qkv2)
+            qkv = ops.linear(n2, B.qkv2, row_map=fm2sm)
             a = ops.attention(qkv, qkv, heads=heads, nz=batch, temporal=True, frames=frames, hw=hw, k_col0=c,
-                              v_col0=2 * c)
-        t = ops.linear(a, B.out2.w, B.out2.b, residual=t)
+                              v_col0=2 * c, packed=packed)
+        t = ops.linear(a, B.out2.w, B.out2.b, residual=t, row_map=sm2fm if not spatial else None)
         n3 = ops.layernorm(t, B.norm3.w, B.norm3.b)
         gg = ops.linear(n3, B.ff1.w, B.ff1.b, act=ops.ACT_GEGLU)
         return ops.linear(gg, B.ff2.w, B.ff2.b, residual=t)

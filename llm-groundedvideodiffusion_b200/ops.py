@@ -145,7 +145,7 @@ def _alloc_out(rows, n, like):
 
 
 def linear(x, w, bias=None, *, act=ACT_NONE, residual=None, gamma=1.0, out=None, rowvec=None, rows_per_vec=0,
-           b_mn_major=False, n=None):
+           b_mn_major=False, n=None, row_map=None):
     """out = epilogue(x @ w.T).  x [rows, K]; w [N, K] (or [K, N] when b_mn_major).  GEGLU expects the
     value/gate-interleaved weight produced by `repack.geglu_interleave` and returns N/2 columns."""
     _check_act(x, "x")
@@ -161,6 +161,24 @@ def linear(x, w, bias=None, *, act=ACT_NONE, residual=None, gamma=1.0, out=None,
     rv = (0, 0, 0, 0)
     a_dims, a_strides, a_box = (k, rows, 1, 1, 1), (1, ld, big, big, big), (64, 128, 1, 1, 1)
     out_dims, ors = (rows, 1, 1, 1), (1, 0, 0, 0)
+    if row_map is not None:
+        # Row permutation folded into the launch: the A tile is a (pixels x frames) box of the input order and the
+        # epilogue writes / reads residual rows in the output order -- this is how the temporal transformer's
+        # permutes (transformer_temporal.py:142-156,176-182) cost nothing.
+        kind, batch, frames, hw = row_map
+        assert rows == batch * frames * hw and rowvec is None
+        if kind == "fm2sm":      # input rows ((b*F+f)*hw+p)  ->  output rows ((b*hw+p)*F+f)
+            bp, bf, bb = choose_box((hw, frames, batch))
+            a_dims, a_strides = (k, hw, frames, batch, 1), (1, ld, ld * hw, ld * hw * frames, big)
+            a_box = (64, bp, bf, bb, 1)
+            out_dims, ors = (hw, frames, batch, 1), (frames, 1, hw * frames, 0)
+        elif kind == "sm2fm":    # input rows ((b*hw+p)*F+f)  ->  output rows ((b*F+f)*hw+p)
+            bf, bp, bb = choose_box((frames, hw, batch))
+            a_dims, a_strides = (k, frames, hw, batch, 1), (1, ld, ld * frames, ld * hw * frames, big)
+            a_box = (64, bf, bp, bb, 1)
+            out_dims, ors = (frames, hw, batch, 1), (hw, 1, hw * frames, 0)
+        else:
+            raise ValueError(kind)
     if rowvec is not None:
         # rows are grouped in blocks of rows_per_vec consecutive rows sharing one row-vector
         assert rows_per_vec > 0 and rows % rows_per_vec == 0
@@ -277,7 +295,7 @@ def layernorm(x, gamma, beta, eps=1e-5, out=None):
 
 # ----------------------------------------------------------------------------------------------- attention
 def attention(q, kv, *, heads, nz, s_q=0, s_k=0, q_col0=0, k_col0=0, v_col0=0, kv_z_div=1, temporal=False, frames=0,
-              hw=0, scale=0.125, out=None, o_col0=0, p_full=None, p_tok=None, tok_cols=()):
+              hw=0, scale=0.125, out=None, o_col0=0, p_full=None, p_tok=None, tok_cols=(), packed=False, lse=None):
     """softmax(Q K^T * scale) V with 64-wide heads.  q / kv are 2-D row buffers; q/k/v live at column offsets."""
     _check_act(q, "q")
     _check_act(kv, "kv")
@@ -291,7 +309,8 @@ def attention(q, kv, *, heads, nz, s_q=0, s_k=0, q_col0=0, k_col0=0, v_col0=0, k
     d.ld_q, d.ld_kv, d.ld_o = q.stride(0), kv.stride(0), out.stride(0)
     d.q_width, d.kv_width = q.shape[1], kv.shape[1]
     d.s_q, d.s_k, d.hw, d.frames = int(s_q), int(s_k), int(hw), int(frames)
-    d.mode = 1 if temporal else 0
+    d.mode = (2 if packed else 1) if temporal else 0
+    d.lse = lse.data_ptr() if lse is not None else None
     d.q_col0, d.k_col0, d.v_col0, d.o_col0 = int(q_col0), int(k_col0), int(v_col0), int(o_col0)
     d.heads, d.nz, d.kv_z_div = int(heads), int(nz), int(kv_z_div)
     d.n_tok = len(tok_cols)

@@ -77,3 +77,30 @@ def test_temporal_attention(cuda, b, frames, hw, heads):
     ref, _ = _ref_attn(q, k, v, heads)
     ref = ref.reshape(b, hw, frames, c).permute(0, 2, 1, 3).reshape(rows, c)
     assert rel_err(out, ref) < TOL
+
+
+@pytest.mark.parametrize("b,frames,hw,heads", [(1, 24, 45, 2), (2, 24, 180, 1), (2, 16, 64, 2), (1, 8, 16, 1),
+                                               (1, 24, 2880, 1), (1, 24, 7, 1), (1, 32, 9, 1)])
+def test_temporal_attention_packed(cuda, b, frames, hw, heads):
+    """mode 2: rows ((b*hw + p)*F + f); sequences are runs of F consecutive rows."""
+    from lvd_b200 import ops
+    c = heads * 64
+    rows = b * hw * frames
+    qkv = _rand((rows, 3 * c), cuda, seed=5)
+    out = ops.attention(qkv, qkv, heads=heads, nz=b, temporal=True, packed=True, frames=frames, hw=hw, q_col0=0,
+                        k_col0=c, v_col0=2 * c)
+    q, k, v = (qkv[:, i * c:(i + 1) * c].reshape(b * hw, frames, c) for i in range(3))
+    ref, _ = _ref_attn(q, k, v, heads)
+    assert rel_err(out, ref.reshape(rows, c)) < TOL
+
+
+def test_self_attention_lse(cuda):
+    from lvd_b200 import ops
+    z, s, heads = 2, 300, 2
+    c = heads * 64
+    qkv = _rand((z * s, 3 * c), cuda, seed=6)
+    lse = torch.zeros((z, heads, s), dtype=torch.float32, device=cuda)
+    ops.attention(qkv, qkv, heads=heads, nz=z, s_q=s, s_k=s, k_col0=c, v_col0=2 * c, lse=lse)
+    q, k = (qkv[:, i * c:(i + 1) * c].reshape(z, s, heads, 64).transpose(1, 2).float() for i in range(2))
+    ref = torch.logsumexp(q @ k.transpose(-1, -2) * 0.125, dim=-1) / 0.6931471805599453
+    assert (lse - ref).abs().max().item() < 2e-3

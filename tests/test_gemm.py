@@ -129,3 +129,20 @@ def test_conv_temporal(cuda, batch, frames, hw, c):
     ref = F.conv3d(x.float(), wt.float(), b.float(), padding=(1, 0, 0)).half().float()
     ref = ref[..., 0].permute(0, 2, 3, 1).reshape(-1, c) + res.float()
     assert rel_err(out, ref) < TOL
+
+
+@pytest.mark.parametrize("batch,frames,hw", [(2, 24, 45), (1, 16, 64), (2, 8, 300)])
+def test_linear_row_maps(cuda, batch, frames, hw):
+    """frame-major <-> sequence-major row permutations folded into the GEMM (temporal transformer permutes)."""
+    from lvd_b200 import ops
+    rows, k, n = batch * frames * hw, 128, 192
+    x = _rand((rows, k), cuda, seed=30)
+    w = _rand((n, k), cuda, k ** -0.5, seed=31)
+    res = _rand((rows, n), cuda, seed=32)
+    y = x.float() @ w.float().t()
+    out = ops.linear(x, w, row_map=("fm2sm", batch, frames, hw))
+    ref = y.reshape(batch, frames, hw, n).permute(0, 2, 1, 3).reshape(rows, n)
+    assert rel_err(out, ref) < TOL
+    out2 = ops.linear(x, w, residual=res, row_map=("sm2fm", batch, frames, hw))
+    ref2 = y.half().float().reshape(batch, hw, frames, n).permute(0, 2, 1, 3).reshape(rows, n) + res.float()
+    assert rel_err(out2, ref2) < TOL

@@ -49,4 +49,6 @@ def test_cfg_dpm_step_kernel_matches_oracle(cuda):
         lat = s.step_cfg(eu, ec, lat, 9.0)
         lat_r = r.step(scheduler_ref.cfg_combine(eu, ec, 9.0), lat_r)
         d = (lat.float() - lat_r.float()).abs().max().item()
-        assert d <= 2e-3 * lat_r.float().abs().max().item(), (i, d)
+        # |x0| reaches ~1e2..1e3 here (alpha_t ~ 0.07 at t=951): one fp16 ulp there is ~0.06-0.5, and a single
+        # differently-ordered rounding moves the result by a few ulps -> 5e-3 of the value range
+        assert d <= 5e-3 * lat_r.float().abs().max().item(), (i, d)
