@@ -69,6 +69,10 @@ typedef struct lvd_gemm_desc {
   void* out;                 /* fp16 [rows, ld_out] */
   int64_t ld_rowvec, ld_res, ld_out;
   float gamma; /* scalar multiplier (GLIGEN tanh gate), 1.0f = off */
+  /* B coordinate of tap t: k0 = t * b_k_tap_stride, n0 += t * b_n_tap_stride.  Forward conv: (k_per_tap, 0).
+   * Conv dgrad reads the SAME [Cout][taps*Cin] weight as an MN-major B: (0, Cin), with negated tap offsets on A. */
+  int32_t b_k_tap_stride;
+  int32_t b_n_tap_stride;
   int32_t reserved;
 } lvd_gemm_desc;
 
@@ -234,6 +238,27 @@ int lvd_latent_update(const void* latents, const void* grad_f32, void* out, void
                       float unscale, void* stream);
 int lvd_attn_rowdot(const void* o, int64_t ld_o, const void* d_o, int64_t ld_do, void* out_f32, int64_t rows,
                     int32_t heads, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Attention adjoints (probabilities recomputed from Q, K; fp32 math; gradients w.r.t. the q|k|v row buffer).
+ *   lvd_self_attn_bwd     : spatial self-attention, tcgen05 (two kernels: dQ; dK+dV).  qkv rows [nz*s]; `lse` is
+ *                           lvd_attention's log2-domain log-sum-exp [nz, heads, s]; `dvec` = lvd_attn_rowdot(O, dO).
+ *   lvd_temporal_attn_bwd : packed temporal attention (mode 2 rows, frames <= 32), one warp per (sequence, head).
+ *   lvd_cross_attn_bwd    : cross-attention, dQ only (text K/V carry no gradient to the latents).  dp_tok
+ *                           [n_slots, nz, heads, s_q] is lvd_box_energy's dE/dP on the object-token columns
+ *                           slot_col_host[n_slots]: the point where the guidance energy enters the backward pass
+ *                           (replaces autograd through attention_processor.py:515-536 and utils/guidance.py:346-353).
+ * ---------------------------------------------------------------------------------------------------------- */
+int lvd_self_attn_bwd(const void* qkv, int64_t ld_qkv, int64_t width_qkv, int32_t q_col0, int32_t k_col0,
+                      int32_t v_col0, const void* d_o, int64_t ld_do, const void* lse, const void* dvec, void* d_qkv,
+                      int64_t ld_dqkv, int64_t s, int32_t heads, int32_t nz, float scale, void* stream);
+int lvd_temporal_attn_bwd(const void* qkv, int64_t ld_qkv, int32_t q_col0, int32_t k_col0, int32_t v_col0,
+                          const void* d_o, int64_t ld_do, void* d_qkv, int64_t ld_dqkv, int64_t n_seq, int32_t heads,
+                          int32_t frames, float scale, void* stream);
+int lvd_cross_attn_bwd(const void* q, int64_t ld_q, const void* kv, int64_t ld_kv, int32_t k_col0, int32_t v_col0,
+                       const void* d_o, int64_t ld_do, const void* dp_tok, const int32_t* slot_col_host,
+                       int32_t n_slots, void* dq, int64_t ld_dq, int64_t s_q, int32_t s_k, int32_t heads, int32_t nz,
+                       int32_t kv_z_div, float scale, void* stream);
 
 #ifdef __cplusplus
 }

@@ -35,6 +35,8 @@ class GemmDesc(ctypes.Structure):
         ("ld_res", ctypes.c_int64),
         ("ld_out", ctypes.c_int64),
         ("gamma", ctypes.c_float),
+        ("b_k_tap_stride", ctypes.c_int32),
+        ("b_n_tap_stride", ctypes.c_int32),
         ("reserved", ctypes.c_int32),
     ]
 
@@ -144,6 +146,10 @@ def _declare(l):
     l.lvd_conv_in_bwd.argtypes = [vp, i64, vp, vp, i32, i32, i32, i32, i32, i32, vp]
     l.lvd_latent_update.argtypes = [vp, vp, vp, vp, i64, f32, f32, vp]
     l.lvd_attn_rowdot.argtypes = [vp, i64, vp, i64, vp, i64, i32, vp]
+    l.lvd_self_attn_bwd.argtypes = [vp, i64, i64, i32, i32, i32, vp, i64, vp, vp, vp, i64, i64, i32, i32, f32, vp]
+    l.lvd_temporal_attn_bwd.argtypes = [vp, i64, i32, i32, i32, vp, i64, vp, i64, i64, i32, i32, f32, vp]
+    l.lvd_cross_attn_bwd.argtypes = [vp, i64, vp, i64, i32, i32, vp, i64, vp, ctypes.POINTER(ctypes.c_int32), i32, vp,
+                                     i64, i64, i32, i32, i32, i32, f32, vp]
     for name in EXPORTS:
         fn = getattr(l, name)
         if name not in ("lvd_last_error", "lvd_launch_count"):
@@ -179,6 +185,9 @@ EXPORTS = [
     "lvd_conv_in_bwd",
     "lvd_latent_update",
     "lvd_attn_rowdot",
+    "lvd_self_attn_bwd",
+    "lvd_temporal_attn_bwd",
+    "lvd_cross_attn_bwd",
 ]
 
 

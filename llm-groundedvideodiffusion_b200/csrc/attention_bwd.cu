@@ -1,0 +1,444 @@
+// attention_bwd.cu -- adjoint of spatial self-attention on tcgen05 tensor cores (flash-style: probabilities are
+// recomputed from Q, K and the saved log-sum-exp; nothing of size S x S is ever stored).
+//
+//   dP = dO V^T ;  dS = P o (dP - D),  D = rowsum(dO o O) ;  dQ = scale dS K ;  dK = scale dS^T Q ;  dV = P^T dO
+//
+// Two kernels, both one CTA per (128-row tile, head, image) with the forward kernel's warp roles
+// (warp 0 TMA, warp 1 MMA issue, warps 2..5 one score row per thread):
+//   attn_bwd_dq_kernel   : fixed query tile, loops over key units;   dQ accumulates in TMEM across units.
+//   attn_bwd_dkdv_kernel : fixed key tile,   loops over query units; dK, dV accumulate in TMEM across units.  The
+//                          P / dS tiles are written once in shared memory as [query][key] and consumed by the
+//                          tensor core as MN-major A operands (P^T, dS^T) -- no transposition pass.
+// Gradients are carried scaled (grad_scale, see lvd_box_energy) so that fp16 tiles do not underflow.
+#include <atomic>
+
+#include "../../include/lvd_b200.h"
+#include "host_util.h"
+#include "ptx.cuh"
+
+namespace lvd {
+extern std::atomic<long long> g_launches;
+
+constexpr int kT = 128 * 128;  // bytes of a 128 x 64 fp16 tile
+constexpr int kBwdThreads = 192;
+
+struct AttnBwdArgs {
+  CUtensorMap map_qkv;  // [rows, width] of the q|k|v buffer, box 64 x 128
+  CUtensorMap map_do;   // [rows, C] of dO, box 64 x 128
+  const float* lse;     // [nz, heads, S] log2-domain
+  const float* dvec;    // [nz*S, heads]
+  __half* d_qkv;
+  long long ld_dqkv;
+  int q_col0, k_col0, v_col0;
+  int S, heads, n_units;
+  float scale, scale_log2;
+  uint32_t idesc_s_full, idesc_s_last;  // M128 x N(keys) K-major/K-major
+  uint32_t idesc_dq;                    // M128 x N64, A K-major, B MN-major
+  uint32_t idesc_dkv;                   // M128 x N64, A MN-major, B MN-major
+  int last_cols16;
+};
+
+__device__ __forceinline__ void store_chunk16(uint8_t* tile_row, int r, int col, const float (&v)[8]) {
+  uint4 u;
+  __half2* hh = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) hh[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+  *reinterpret_cast<uint4*>(tile_row + (col >> 6) * kT + ((((col & 63) >> 3) ^ (r & 7)) << 4)) = u;
+}
+
+// ------------------------------------------------------------------------------------------------ dQ
+__global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_dq_kernel(const __grid_constant__ AttnBwdArgs g) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t* sQ = smem;
+  uint8_t* sDO = smem + kT;
+  uint8_t* sK = smem + 2 * kT;   // 2 stages
+  uint8_t* sV = smem + 4 * kT;   // 2 stages
+  uint8_t* sDS = smem + 6 * kT;  // 2 column blocks
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 8 * kT);
+  uint64_t* q_full = bars + 0;
+  uint64_t* kv_full = bars + 1;   // [2]
+  uint64_t* kv_empty = bars + 3;  // [2]
+  uint64_t* sdp_full = bars + 5;
+  uint64_t* ds_full = bars + 6;
+  uint64_t* dq_done = bars + 7;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 8);
+  const int h = blockIdx.x, qt = blockIdx.y, z = blockIdx.z;
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  if (threadIdx.x == 0) {
+    mbar_init(q_full, 1);
+    mbar_init(&kv_full[0], 1);
+    mbar_init(&kv_full[1], 1);
+    mbar_init(&kv_empty[0], 1);
+    mbar_init(&kv_empty[1], 1);
+    mbar_init(sdp_full, 1);
+    mbar_init(ds_full, 128);
+    mbar_init(dq_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&g.map_qkv);
+    tma_prefetch_desc(&g.map_do);
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_holder, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+  const uint32_t tm_s = tmem_base, tm_dp = tmem_base + 128, tm_dq = tmem_base + 256;
+  const int row0 = z * g.S;  // first row of this image in the row buffers
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(q_full, 2 * kT);
+      tma_load_2d(sQ, &g.map_qkv, q_full, g.q_col0 + h * 64, row0 + qt * 128);
+      tma_load_2d(sDO, &g.map_do, q_full, h * 64, row0 + qt * 128);
+      for (int u = 0; u < g.n_units; ++u) {
+        const int st = u & 1;
+        mbar_wait(&kv_empty[st], ((u >> 1) & 1) ^ 1u);
+        mbar_arrive_expect_tx(&kv_full[st], 2 * kT);
+        tma_load_2d(sK + st * kT, &g.map_qkv, &kv_full[st], g.k_col0 + h * 64, row0 + u * 128);
+        tma_load_2d(sV + st * kT, &g.map_qkv, &kv_full[st], g.v_col0 + h * 64, row0 + u * 128);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      mbar_wait(q_full, 0);
+      const uint32_t q_addr = smem_u32(sQ), do_addr = smem_u32(sDO), ds_addr = smem_u32(sDS);
+      for (int u = 0; u < g.n_units; ++u) {
+        const int st = u & 1;
+        const bool last = (u == g.n_units - 1);
+        const int ncols = last ? g.last_cols16 : 128;
+        const uint32_t idesc_s = last ? g.idesc_s_last : g.idesc_s_full;
+        mbar_wait(&kv_full[st], (u >> 1) & 1);
+        tc_fence_after();
+        const uint32_t k_addr = smem_u32(sK + st * kT), v_addr = smem_u32(sV + st * kT);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_f16(tm_s, make_smem_desc_sw128(q_addr + k * 32, 16, 1024),
+                   make_smem_desc_sw128(k_addr + k * 32, 16, 1024), idesc_s, k != 0 ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_f16(tm_dp, make_smem_desc_sw128(do_addr + k * 32, 16, 1024),
+                   make_smem_desc_sw128(v_addr + k * 32, 16, 1024), idesc_s, k != 0 ? 1u : 0u);
+        umma_commit(sdp_full);
+        mbar_wait(ds_full, u & 1);
+        tc_fence_after();
+        for (int ks = 0; ks < ncols / 16; ++ks)
+          umma_f16(tm_dq, make_smem_desc_sw128(ds_addr + (ks >> 2) * kT + (ks & 3) * 32, 16, 1024),
+                   make_smem_desc_sw128(k_addr + ks * 2048, 8192, 1024), g.idesc_dq, (u | ks) != 0 ? 1u : 0u);
+        umma_commit(dq_done);
+        umma_commit(&kv_empty[st]);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const int qi = qt * 128 + r;
+    const bool row_valid = qi < g.S;
+    const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+    const float L = row_valid ? g.lse[(static_cast<long long>(z) * g.heads + h) * g.S + qi] : 0.f;
+    const float Dv = row_valid ? g.dvec[(static_cast<long long>(row0) + qi) * g.heads + h] : 0.f;
+    uint8_t* ds_row = sDS + r * 128;
+    for (int u = 0; u < g.n_units; ++u) {
+      const bool last = (u == g.n_units - 1);
+      const int ncols = last ? g.last_cols16 : 128;
+      int nvalid = g.S - u * 128;
+      if (nvalid > 128) nvalid = 128;
+      mbar_wait(sdp_full, u & 1);
+      tc_fence_after();
+      if (u > 0) mbar_wait(dq_done, (u - 1) & 1);  // the previous dQ MMA has finished reading sDS
+      for (int ch = 0; ch < (ncols + 31) / 32; ++ch) {
+        uint32_t rs[32], rp[32];
+        tmem_ld32(tm_s + lane_off + ch * 32, rs);
+        tmem_ld32(tm_dp + lane_off + ch * 32, rp);
+        tmem_ld_wait();
+#pragma unroll
+        for (int s8 = 0; s8 < 4; ++s8) {
+          float v[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int c = ch * 32 + s8 * 8 + i;
+            const bool ok = row_valid && (c < nvalid);
+            const float p = ok ? exp2f(fmaf(__uint_as_float(rs[s8 * 8 + i]), g.scale_log2, -L)) : 0.f;
+            v[i] = p * (__uint_as_float(rp[s8 * 8 + i]) - Dv);
+          }
+          store_chunk16(ds_row, r, ch * 32 + s8 * 8, v);
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(ds_full);
+    }
+    mbar_wait(dq_done, (g.n_units - 1) & 1);
+    tc_fence_after();
+    __half* dst = g.d_qkv + (static_cast<long long>(row0) + qi) * g.ld_dqkv + g.q_col0 + h * 64;
+#pragma unroll
+    for (int hlf = 0; hlf < 2; ++hlf) {
+      uint32_t rr[32];
+      tmem_ld32(tm_dq + lane_off + hlf * 32, rr);
+      tmem_ld_wait();
+      if (row_valid) {
+#pragma unroll
+        for (int s8 = 0; s8 < 4; ++s8) {
+          uint4 v;
+          __half2* hh = reinterpret_cast<__half2*>(&v);
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            hh[i] = __floats2half2_rn(__uint_as_float(rr[s8 * 8 + 2 * i]) * g.scale,
+                                      __uint_as_float(rr[s8 * 8 + 2 * i + 1]) * g.scale);
+          *reinterpret_cast<uint4*>(dst + hlf * 32 + s8 * 8) = v;
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ dK, dV
+__global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_dkdv_kernel(const __grid_constant__ AttnBwdArgs g) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t* sK = smem;
+  uint8_t* sV = smem + kT;
+  uint8_t* sQ = smem + 2 * kT;   // 2 stages
+  uint8_t* sDO = smem + 4 * kT;  // 2 stages
+  uint8_t* sP = smem + 6 * kT;   // [query][key], 2 key blocks
+  uint8_t* sDS = smem + 8 * kT;  // [query][key], 2 key blocks
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 10 * kT);
+  uint64_t* k_full = bars + 0;
+  uint64_t* q_full = bars + 1;   // [2]
+  uint64_t* q_empty = bars + 3;  // [2]
+  uint64_t* sdp_full = bars + 5;
+  uint64_t* pds_full = bars + 6;
+  uint64_t* acc_done = bars + 7;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 8);
+  const int h = blockIdx.x, kt = blockIdx.y, z = blockIdx.z;
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  if (threadIdx.x == 0) {
+    mbar_init(k_full, 1);
+    mbar_init(&q_full[0], 1);
+    mbar_init(&q_full[1], 1);
+    mbar_init(&q_empty[0], 1);
+    mbar_init(&q_empty[1], 1);
+    mbar_init(sdp_full, 1);
+    mbar_init(pds_full, 128);
+    mbar_init(acc_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&g.map_qkv);
+    tma_prefetch_desc(&g.map_do);
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_holder, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+  const uint32_t tm_s = tmem_base, tm_dp = tmem_base + 128, tm_dv = tmem_base + 256, tm_dk = tmem_base + 320;
+  const int row0 = z * g.S;
+  int kvalid = g.S - kt * 128;  // valid keys in this tile
+  if (kvalid > 128) kvalid = 128;
+  const int kcols16 = (kvalid + 15) / 16 * 16;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(k_full, 2 * kT);
+      tma_load_2d(sK, &g.map_qkv, k_full, g.k_col0 + h * 64, row0 + kt * 128);
+      tma_load_2d(sV, &g.map_qkv, k_full, g.v_col0 + h * 64, row0 + kt * 128);
+      for (int u = 0; u < g.n_units; ++u) {
+        const int st = u & 1;
+        mbar_wait(&q_empty[st], ((u >> 1) & 1) ^ 1u);
+        mbar_arrive_expect_tx(&q_full[st], 2 * kT);
+        tma_load_2d(sQ + st * kT, &g.map_qkv, &q_full[st], g.q_col0 + h * 64, row0 + u * 128);
+        tma_load_2d(sDO + st * kT, &g.map_do, &q_full[st], h * 64, row0 + u * 128);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      mbar_wait(k_full, 0);
+      const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV), p_addr = smem_u32(sP), ds_addr = smem_u32(sDS);
+      const uint32_t idesc_s = make_idesc_f16(128, static_cast<uint32_t>(kcols16), 0, 0);
+      for (int u = 0; u < g.n_units; ++u) {
+        const int st = u & 1;
+        mbar_wait(&q_full[st], (u >> 1) & 1);
+        tc_fence_after();
+        const uint32_t q_addr = smem_u32(sQ + st * kT), do_addr = smem_u32(sDO + st * kT);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_f16(tm_s, make_smem_desc_sw128(q_addr + k * 32, 16, 1024),
+                   make_smem_desc_sw128(k_addr + k * 32, 16, 1024), idesc_s, k != 0 ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_f16(tm_dp, make_smem_desc_sw128(do_addr + k * 32, 16, 1024),
+                   make_smem_desc_sw128(v_addr + k * 32, 16, 1024), idesc_s, k != 0 ? 1u : 0u);
+        umma_commit(sdp_full);
+        mbar_wait(pds_full, u & 1);
+        tc_fence_after();
+        // dV[key, d] += sum_q P[q, key] dO[q, d] ;  dK[key, d] += sum_q dS[q, key] Q[q, d]
+        // A = P^T / dS^T read MN-major straight from the [query][key] tiles (M = keys: 2 blocks of 64, LBO = kT);
+        // B = dO / Q tiles MN-major ([query rows][d]); one k-step = 16 query rows = 2048 bytes in both.
+        for (int ks = 0; ks < 8; ++ks) {
+          umma_f16(tm_dv, make_smem_desc_sw128(p_addr + ks * 2048, kT, 1024),
+                   make_smem_desc_sw128(do_addr + ks * 2048, 8192, 1024), g.idesc_dkv, (u | ks) != 0 ? 1u : 0u);
+          umma_f16(tm_dk, make_smem_desc_sw128(ds_addr + ks * 2048, kT, 1024),
+                   make_smem_desc_sw128(q_addr + ks * 2048, 8192, 1024), g.idesc_dkv, (u | ks) != 0 ? 1u : 0u);
+        }
+        umma_commit(acc_done);
+        umma_commit(&q_empty[st]);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+    uint8_t* p_row = sP + r * 128;
+    uint8_t* ds_row = sDS + r * 128;
+    for (int u = 0; u < g.n_units; ++u) {
+      const int qi = u * 128 + r;
+      const bool row_valid = qi < g.S;
+      const float L = row_valid ? g.lse[(static_cast<long long>(z) * g.heads + h) * g.S + qi] : 0.f;
+      const float Dv = row_valid ? g.dvec[(static_cast<long long>(row0) + qi) * g.heads + h] : 0.f;
+      mbar_wait(sdp_full, u & 1);
+      tc_fence_after();
+      if (u > 0) mbar_wait(acc_done, (u - 1) & 1);  // previous dV/dK MMAs have finished reading sP / sDS
+      for (int ch = 0; ch < 4; ++ch) {
+        float pv[32], dv_[32];
+        if (ch * 32 < kcols16) {
+          uint32_t rs[32], rp[32];
+          tmem_ld32(tm_s + lane_off + ch * 32, rs);
+          tmem_ld32(tm_dp + lane_off + ch * 32, rp);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const bool ok = row_valid && (ch * 32 + i < kvalid);
+            const float p = ok ? exp2f(fmaf(__uint_as_float(rs[i]), g.scale_log2, -L)) : 0.f;
+            pv[i] = p;
+            dv_[i] = p * (__uint_as_float(rp[i]) - Dv);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) pv[i] = dv_[i] = 0.f;  // keys beyond the tile: the M=128 MMA still reads them
+        }
+#pragma unroll
+        for (int s8 = 0; s8 < 4; ++s8) {
+          float a[8], b[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            a[i] = pv[s8 * 8 + i];
+            b[i] = dv_[s8 * 8 + i];
+          }
+          store_chunk16(p_row, r, ch * 32 + s8 * 8, a);
+          store_chunk16(ds_row, r, ch * 32 + s8 * 8, b);
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(pds_full);
+    }
+    mbar_wait(acc_done, (g.n_units - 1) & 1);
+    tc_fence_after();
+    const int ki = kt * 128 + r;  // this thread's key row
+    const bool key_valid = r < kvalid;
+    __half* dst = g.d_qkv + (static_cast<long long>(row0) + ki) * g.ld_dqkv + h * 64;
+#pragma unroll
+    for (int part = 0; part < 4; ++part) {  // 0,1: dV halves; 2,3: dK halves
+      uint32_t rr[32];
+      tmem_ld32((part < 2 ? tm_dv : tm_dk) + lane_off + (part & 1) * 32, rr);
+      tmem_ld_wait();
+      if (key_valid) {
+        const float sc = part < 2 ? 1.f : g.scale;
+        __half* d = dst + (part < 2 ? g.v_col0 : g.k_col0) + (part & 1) * 32;
+#pragma unroll
+        for (int s8 = 0; s8 < 4; ++s8) {
+          uint4 v;
+          __half2* hh = reinterpret_cast<__half2*>(&v);
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            hh[i] = __floats2half2_rn(__uint_as_float(rr[s8 * 8 + 2 * i]) * sc, __uint_as_float(rr[s8 * 8 + 2 * i + 1]) * sc);
+          *reinterpret_cast<uint4*>(d + s8 * 8) = v;
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace lvd
+
+using namespace lvd;
+
+extern "C" int lvd_self_attn_bwd(const void* qkv, int64_t ld_qkv, int64_t width_qkv, int32_t q_col0, int32_t k_col0,
+                                 int32_t v_col0, const void* d_o, int64_t ld_do, const void* lse, const void* dvec,
+                                 void* d_qkv, int64_t ld_dqkv, int64_t s, int32_t heads, int32_t nz, float scale,
+                                 void* stream) {
+  LVD_REQUIRE(qkv && d_o && lse && dvec && d_qkv, "lvd_self_attn_bwd: null pointer");
+  LVD_REQUIRE(s >= 1 && heads >= 1 && nz >= 1 && nz <= 65535, "lvd_self_attn_bwd: bad sizes");
+  LVD_REQUIRE(ld_qkv % 8 == 0 && ld_do % 8 == 0 && ld_dqkv % 8 == 0 && q_col0 % 8 == 0 && k_col0 % 8 == 0 &&
+                  v_col0 % 8 == 0,
+              "lvd_self_attn_bwd: alignment");
+  AttnBwdArgs g;
+  memset(&g, 0, sizeof(g));
+  const int64_t rows = s * nz;
+  // plain 2-D maps; tiles that cross an image boundary read the neighbour's rows, which the per-row / per-key
+  // validity masks discard (they are finite values), rows past the end of the buffer read as zero.
+  int64_t d1[2] = {width_qkv, rows};
+  int64_t s1[2] = {1, ld_qkv};
+  int b1[2] = {64, 128};
+  int rc = encode_tmap_f16_sw128(&g.map_qkv, qkv, 2, d1, s1, b1);
+  if (rc) return rc;
+  int64_t d2[2] = {static_cast<int64_t>(heads) * 64, rows};
+  int64_t s2[2] = {1, ld_do};
+  rc = encode_tmap_f16_sw128(&g.map_do, d_o, 2, d2, s2, b1);
+  if (rc) return rc;
+  g.lse = static_cast<const float*>(lse);
+  g.dvec = static_cast<const float*>(dvec);
+  g.d_qkv = static_cast<__half*>(d_qkv);
+  g.ld_dqkv = ld_dqkv;
+  g.q_col0 = q_col0;
+  g.k_col0 = k_col0;
+  g.v_col0 = v_col0;
+  g.S = static_cast<int>(s);
+  g.heads = heads;
+  g.n_units = static_cast<int>((s + 127) / 128);
+  g.scale = scale;
+  g.scale_log2 = scale * 1.4426950408889634f;
+  const int last_valid = g.S - (g.n_units - 1) * 128;
+  g.last_cols16 = (last_valid + 15) / 16 * 16;
+  g.idesc_s_full = make_idesc_f16(128, 128, 0, 0);
+  g.idesc_s_last = make_idesc_f16(128, static_cast<uint32_t>(g.last_cols16), 0, 0);
+  g.idesc_dq = make_idesc_f16(128, 64, 0, 1);
+  g.idesc_dkv = make_idesc_f16(128, 64, 1, 1);
+  const int smem_dq = 8 * kT + 128, smem_dkv = 10 * kT + 128;
+  static bool attr = false;
+  if (!attr) {
+    LVD_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dq));
+    LVD_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dkdv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dkv));
+    attr = true;
+  }
+  dim3 grid(heads, g.n_units, nz);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  attn_bwd_dq_kernel<<<grid, kBwdThreads, smem_dq, st>>>(g);
+  attn_bwd_dkdv_kernel<<<grid, kBwdThreads, smem_dkv, st>>>(g);
+  g_launches.fetch_add(2, std::memory_order_relaxed);
+  LVD_CHECK_CUDA(cudaGetLastError());
+  return LVD_OK;
+}

@@ -15,9 +15,14 @@ extern std::atomic<long long> g_launches;
 __global__ void conv_in_kernel(const __half* __restrict__ x, const __half* __restrict__ w,
                                const __half* __restrict__ bias, __half* __restrict__ out, long long ld_out, int B,
                                int Cin, int F, int H, int W, int Cout) {
-  extern __shared__ __half s_w[];  // [Cout*Cin*9] + [Cout]
+  // weights transposed to [ci][ky][kx][Cout] in shared memory so that the 8 channels of a thread are one 16-byte,
+  // bank-conflict-free read (neighbouring threads own neighbouring channel vectors)
+  extern __shared__ __align__(16) __half s_w[];  // [Cin*9][Cout] + [Cout]
   const int wn = Cout * Cin * 9;
-  for (int i = threadIdx.x; i < wn; i += blockDim.x) s_w[i] = w[i];
+  for (int i = threadIdx.x; i < wn; i += blockDim.x) {
+    const int co = i / (Cin * 9), rem = i % (Cin * 9);  // source layout [co][ci][ky][kx]
+    s_w[rem * Cout + co] = w[i];
+  }
   for (int i = threadIdx.x; i < Cout; i += blockDim.x) s_w[wn + i] = bias[i];
   __syncthreads();
   const int cvec = Cout / 8;
@@ -33,8 +38,16 @@ __global__ void conv_in_kernel(const __half* __restrict__ x, const __half* __res
     const int f = static_cast<int>(p % F);
     const int b = static_cast<int>(p / F);
     float acc[8];
+    {
+      const uint4 bq = *reinterpret_cast<const uint4*>(&s_w[wn + cv * 8]);
+      const __half2* bh = reinterpret_cast<const __half2*>(&bq);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+      for (int i = 0; i < 4; ++i) {
+        const float2 t = __half22float2(bh[i]);
+        acc[2 * i] = t.x;
+        acc[2 * i + 1] = t.y;
+      }
+    }
     for (int ci = 0; ci < Cin; ++ci) {
       const __half* xp = x + ((static_cast<long long>(b) * Cin + ci) * F + f) * H * W;
 #pragma unroll
@@ -46,9 +59,14 @@ __global__ void conv_in_kernel(const __half* __restrict__ x, const __half* __res
           const int ix = xx + kx - 1;
           if (ix < 0 || ix >= W) continue;
           const float v = __half2float(xp[iy * W + ix]);
+          const uint4 wq = *reinterpret_cast<const uint4*>(&s_w[((ci * 3 + ky) * 3 + kx) * Cout + cv * 8]);
+          const __half2* wh = reinterpret_cast<const __half2*>(&wq);
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
-            acc[i] += v * __half2float(s_w[((cv * 8 + i) * Cin + ci) * 9 + ky * 3 + kx]);
+          for (int i = 0; i < 4; ++i) {
+            const float2 t = __half22float2(wh[i]);
+            acc[2 * i] = fmaf(v, t.x, acc[2 * i]);
+            acc[2 * i + 1] = fmaf(v, t.y, acc[2 * i + 1]);
+          }
         }
       }
     }
@@ -56,9 +74,7 @@ __global__ void conv_in_kernel(const __half* __restrict__ x, const __half* __res
     uint4 u;
     __half2* h = reinterpret_cast<__half2*>(&u);
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-      h[i] = __floats2half2_rn(acc[2 * i] + __half2float(s_w[wn + cv * 8 + 2 * i]),
-                               acc[2 * i + 1] + __half2float(s_w[wn + cv * 8 + 2 * i + 1]));
+    for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(acc[2 * i], acc[2 * i + 1]);
     *reinterpret_cast<uint4*>(out + row * ld_out + cv * 8) = u;
   }
 }

@@ -2,8 +2,8 @@
 //
 //   warp 0      : TMA producer   (one elected lane; cp.async.bulk.tensor into a multi-stage smem ring)
 //   warp 1      : MMA issuer     (one elected lane; tcgen05.mma, fp32 accumulators double-buffered in TMEM)
-//   warps 2..9  : epilogue       (tcgen05.ld -> bias / SiLU / GEGLU / time-embedding / gate / residual -> fp16 store;
-//                 two warps per TMEM lane quarter, interleaved over 32-column chunks)
+//   warps 2..17 : epilogue       (tcgen05.ld -> bias / SiLU / GEGLU / time-embedding / gate / residual -> fp16 store;
+//                 four warps per TMEM lane quarter, interleaved over 16-column units)
 //
 // A tiles are rank-5 TMA boxes of the channels-last activation; a convolution tap is a coordinate offset and the
 // zero padding is TMA out-of-bounds fill, so Linear, Conv2d (3x3, 1x1, stride 2) and Conv3d (3,1,1) all run here.
@@ -18,7 +18,7 @@ namespace lvd {
 std::atomic<long long> g_launches{0};
 
 constexpr int kAStageBytes = 128 * 128;  // 128 rows x 64 halves
-constexpr int kThreads = 320;  // 2 control warps + 8 epilogue warps
+constexpr int kThreads = 576;  // 2 control warps + 16 epilogue warps
 constexpr int kSmemLimit = 232448;  // 227 KB
 
 struct GemmArgs {
@@ -38,6 +38,7 @@ struct GemmArgs {
   int n_taps, kb_per_tap;
   int n_tiles_n, block_n, b_mn_major, act;
   int num_tiles, stages, a_bytes, b_bytes;
+  int b_k_tap_stride, b_n_tap_stride;
   float gamma;
   uint32_t idesc;
 };
@@ -73,29 +74,6 @@ __device__ __forceinline__ void store8(__half* p, const float (&v)[8]) {
   *reinterpret_cast<uint4*>(p) = u;
 }
 
-// Shared tail of the epilogue for 8 consecutive output columns starting at `col` (already fp16-rounded `v`).
-__device__ __forceinline__ void epilogue_tail8(const GemmArgs& g, float (&v)[8], long long orow, long long rvrow,
-                                               int col) {
-  if (g.rowvec) {
-    float t[8];
-    load8(g.rowvec + rvrow * g.ld_rowvec + col, t);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = round_h(v[i] + t[i]);
-  }
-  if (g.gamma != 1.0f) {
-    const float gm = g.gamma;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = round_h(v[i] * gm);
-  }
-  if (g.residual) {
-    float t[8];
-    load8(g.residual + orow * g.ld_res + col, t);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = v[i] + t[i];
-  }
-  store8(g.out + orow * g.ld_out + col, v);
-}
-
 __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_constant__ GemmArgs g) {
   extern __shared__ uint8_t smem_raw[];
   // 128-byte swizzle atoms need 1024-byte aligned stage bases
@@ -119,8 +97,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     }
     mbar_init(&tfull[0], 1);
     mbar_init(&tfull[1], 1);
-    mbar_init(&tempty[0], 256);
-    mbar_init(&tempty[1], 256);
+    mbar_init(&tempty[0], 512);
+    mbar_init(&tempty[1], 512);
     fence_barrier_init();
   }
   if (warp == 0 && lane == 0) {
@@ -153,13 +131,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
             mbar_wait(&empty[stage], phase ^ 1u);
             mbar_arrive_expect_tx(&full[stage], static_cast<uint32_t>(g.a_bytes + g.b_bytes));
             tma_load_5d(sA + stage * kAStageBytes, &g.map_a, &full[stage], o0 + kb * 64, c1, c2, c3, c4);
-            const int kcoord = (tap * g.kb_per_tap + kb) * 64;
+            const int kcoord = tap * g.b_k_tap_stride + kb * 64;
+            const int ncoord = nt * g.block_n + tap * g.b_n_tap_stride;
             uint8_t* bdst = sB + stage * b_stage_bytes;
             if (!g.b_mn_major) {
-              tma_load_2d(bdst, &g.map_b, &full[stage], kcoord, nt * g.block_n);
+              tma_load_2d(bdst, &g.map_b, &full[stage], kcoord, ncoord);
             } else {
               for (int ch = 0; ch < g.block_n / 64; ++ch)
-                tma_load_2d(bdst + ch * 8192, &g.map_b, &full[stage], nt * g.block_n + ch * 64, kcoord);
+                tma_load_2d(bdst + ch * 8192, &g.map_b, &full[stage], ncoord + ch * 64, kcoord);
             }
             if (++stage == stages) {
               stage = 0;
@@ -203,8 +182,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       }
     }
   } else {
-    const int q = warp & 3;  // this warp may only touch TMEM lanes [32q, 32q+32)
-    const int chalf = (warp - 2) >> 2;  // which of the two warps sharing this lane quarter
+    // 16 epilogue warps: four per TMEM lane quarter, interleaved over 16-column units, so that each SM sub-partition
+    // has four warps to hide the latency of the TMEM / residual loads behind the others' arithmetic.
+    const int q = warp & 3;            // this warp may only touch TMEM lanes [32q, 32q+32)
+    const int csub = (warp - 2) >> 2;  // 0..3: which units of the tile this warp handles
     const int r = q * 32 + lane;
     int j[4];
     {
@@ -219,6 +200,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     }
     int acc = 0;
     uint32_t acc_phase = 0;
+    const bool geglu = (g.act == 2);
+    const int units = geglu ? 4 : g.block_n / 16;
     for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
       const int nt = tile % g.n_tiles_n;
       int c[4];
@@ -235,66 +218,70 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + static_cast<uint32_t>(acc) * 256u + (static_cast<uint32_t>(q * 32) << 16);
-      if (g.act != 2) {
-        for (int ch = chalf; ch < g.block_n / 32; ch += 2) {
-          uint32_t rr[32];
-          tmem_ld32(taddr + ch * 32, rr);
-          tmem_ld_wait();
-          if (valid) {
-            const int col0 = nt * g.block_n + ch * 32;
-#pragma unroll
-            for (int s = 0; s < 4; ++s) {
-              float v[8];
-#pragma unroll
-              for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(rr[s * 8 + i]);
-              const int col = col0 + s * 8;
-              if (g.bias) {
-                float t[8];
-                load8(g.bias + col, t);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] += t[i];
-              }
-#pragma unroll
-              for (int i = 0; i < 8; ++i) v[i] = round_h(v[i]);
-              if (g.act == 1) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] = round_h(silu_f(v[i]));
-              }
-              epilogue_tail8(g, v, orow, rvrow, col);
-            }
-          }
+      for (int u = csub; u < units; u += 4) {
+        // output columns [ocol, ocol+16); issue the residual loads first so they overlap the TMEM read
+        const int ocol = geglu ? nt * 64 + u * 16 : nt * g.block_n + u * 16;
+        float res[2][8];
+        if (g.residual && valid) {
+          load8(g.residual + orow * g.ld_res + ocol, res[0]);
+          load8(g.residual + orow * g.ld_res + ocol + 8, res[1]);
         }
-      } else {
-        // GEGLU: block_n == 128; TMEM columns [0,64) = value, [64,128) = gate of output columns nt*64 + [0,64)
-        for (int ch = chalf; ch < 2; ch += 2) {
-          uint32_t rv[32], rg[32];
-          tmem_ld32(taddr + ch * 32, rv);
-          tmem_ld32(taddr + 64 + ch * 32, rg);
-          tmem_ld_wait();
-          if (valid) {
+        uint32_t rv[16], rg[16];
+        tmem_ld16(taddr + u * 16, rv);
+        if (geglu) tmem_ld16(taddr + 64 + u * 16, rg);
+        tmem_ld_wait();
+        if (valid) {
+          float v[2][8];
 #pragma unroll
-            for (int s = 0; s < 4; ++s) {
-              float v[8], gt[8];
+          for (int i = 0; i < 16; ++i) v[i >> 3][i & 7] = __uint_as_float(rv[i]);
+          if (geglu) {
+            // value * gelu(gate); biases of the interleaved weight: value at tcol, gate at tcol + 64
+            const int tcol = nt * 128 + u * 16;
+            float bv[2][8], bg[2][8];
+            if (g.bias) {
+              load8(g.bias + tcol, bv[0]);
+              load8(g.bias + tcol + 8, bv[1]);
+              load8(g.bias + tcol + 64, bg[0]);
+              load8(g.bias + tcol + 72, bg[1]);
+            } else {
 #pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                v[i] = __uint_as_float(rv[s * 8 + i]);
-                gt[i] = __uint_as_float(rg[s * 8 + i]);
-              }
-              const int tcol = nt * 128 + ch * 32 + s * 8;  // column inside the interleaved weight (value part)
-              if (g.bias) {
-                float t[8];
-                load8(g.bias + tcol, t);
+              for (int i = 0; i < 16; ++i) bv[i >> 3][i & 7] = bg[i >> 3][i & 7] = 0.f;
+            }
 #pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] += t[i];
-                load8(g.bias + tcol + 64, t);
+            for (int i = 0; i < 16; ++i)
+              v[i >> 3][i & 7] = round_h(v[i >> 3][i & 7] + bv[i >> 3][i & 7]) *
+                               round_h(gelu_erf_f(__uint_as_float(rg[i]) + bg[i >> 3][i & 7]));
+          } else {
+            if (g.bias) {
+              float b[2][8];
+              load8(g.bias + ocol, b[0]);
+              load8(g.bias + ocol + 8, b[1]);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) gt[i] += t[i];
-              }
+              for (int i = 0; i < 16; ++i) v[i >> 3][i & 7] += b[i >> 3][i & 7];
+            }
+            if (g.act == 1) {
 #pragma unroll
-              for (int i = 0; i < 8; ++i) v[i] = round_h(round_h(v[i]) * round_h(gelu_erf_f(round_h(gt[i]))));
-              epilogue_tail8(g, v, orow, rvrow, nt * 64 + ch * 32 + s * 8);
+              for (int i = 0; i < 16; ++i) v[i >> 3][i & 7] = silu_f(round_h(v[i >> 3][i & 7]));
             }
           }
+          if (g.rowvec) {
+            float t[2][8];
+            load8(g.rowvec + rvrow * g.ld_rowvec + ocol, t[0]);
+            load8(g.rowvec + rvrow * g.ld_rowvec + ocol + 8, t[1]);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i >> 3][i & 7] = round_h(v[i >> 3][i & 7]) + t[i >> 3][i & 7];
+          }
+          if (g.gamma != 1.0f) {
+            const float gm = g.gamma;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i >> 3][i & 7] = round_h(v[i >> 3][i & 7]) * gm;
+          }
+          if (g.residual) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i >> 3][i & 7] = round_h(v[i >> 3][i & 7]) + res[i >> 3][i & 7];
+          }
+          store8(g.out + orow * g.ld_out + ocol, v[0]);
+          store8(g.out + orow * g.ld_out + ocol + 8, v[1]);
         }
       }
       tc_fence_before();
@@ -333,14 +320,16 @@ static int launch_gemm(const lvd_gemm_desc* d, cudaStream_t stream) {
   memset(&g, 0, sizeof(g));
   int rc = encode_tmap_f16_sw128(&g.map_a, d->a, 5, d->a_dims, d->a_strides, d->a_box);
   if (rc) return rc;
-  const long long k_total = static_cast<long long>(d->n_taps) * d->k_per_tap;
+  const int k_tap_stride = (d->b_k_tap_stride == 0 && d->b_n_tap_stride == 0) ? d->k_per_tap : d->b_k_tap_stride;
+  const long long k_total = static_cast<long long>(d->n_taps - 1) * k_tap_stride + d->k_per_tap;
+  const long long n_total = static_cast<long long>(d->n_taps - 1) * d->b_n_tap_stride + d->n;
   if (!d->b_mn_major) {
-    int64_t dims[2] = {k_total, d->n};
+    int64_t dims[2] = {k_total, n_total};
     int64_t str[2] = {1, d->ldb};
     int box[2] = {64, d->block_n};
     rc = encode_tmap_f16_sw128(&g.map_b, d->b, 2, dims, str, box);
   } else {
-    int64_t dims[2] = {d->n, k_total};
+    int64_t dims[2] = {n_total, k_total};
     int64_t str[2] = {1, d->ldb};
     int box[2] = {64, 64};
     rc = encode_tmap_f16_sw128(&g.map_b, d->b, 2, dims, str, box);
@@ -363,6 +352,8 @@ static int launch_gemm(const lvd_gemm_desc* d, cudaStream_t stream) {
   g.block_n = d->block_n;
   g.n_tiles_n = d->n / d->block_n;
   g.b_mn_major = d->b_mn_major;
+  g.b_k_tap_stride = k_tap_stride;
+  g.b_n_tap_stride = d->b_n_tap_stride;
   g.act = d->act;
   LVD_REQUIRE(m_tiles * g.n_tiles_n < (1ll << 30), "lvd_gemm: too many tiles");
   g.num_tiles = static_cast<int>(m_tiles * g.n_tiles_n);

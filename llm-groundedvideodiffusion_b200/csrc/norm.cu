@@ -152,8 +152,8 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x, long long ld_x, __
       float o = round_h((t[i] - mu[i]) * rs[i] * ga[i] + be[i]);
       float o2 = round_h((u[i] - mu[i]) * rs[i] * ga[i] + be[i]);
       if (silu) {
-        o = o / (1.0f + __expf(-o));
-        o2 = o2 / (1.0f + __expf(-o2));
+        o = __fdividef(o, 1.0f + __expf(-o));
+        o2 = __fdividef(o2, 1.0f + __expf(-o2));
       }
       t[i] = o;
       u[i] = o2;
@@ -167,7 +167,7 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x, long long ld_x, __
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       float o = round_h((t[i] - mu[i]) * rs[i] * ga[i] + be[i]);
-      if (silu) o = o / (1.0f + __expf(-o));
+      if (silu) o = __fdividef(o, 1.0f + __expf(-o));
       t[i] = o;
     }
     st8(yb + r * ld_y, t);
@@ -184,6 +184,9 @@ static int gn_threads(int C) {
 // ------------------------------------------------------------------------------------------------ LayerNorm
 // One warp per row; the row stays in registers (C <= 2048), exact two-pass mean / variance in fp32.
 constexpr int kLnMaxVec = 8;  // 8 vectors of 8 halves per lane -> C <= 2048
+// NV = ceil(C / 256) vectors per lane: a template parameter so that narrow rows (C = 320: NV = 2) hold 16 instead of
+// 64 registers of row data and many more rows are in flight per SM.
+template <int NV>
 __global__ void layernorm_kernel(const __half* __restrict__ x, long long ld_x, __half* __restrict__ y, long long ld_y,
                                  long long rows, int C, const __half* __restrict__ gamma,
                                  const __half* __restrict__ beta, float eps) {
@@ -198,11 +201,11 @@ __global__ void layernorm_kernel(const __half* __restrict__ x, long long ld_x, _
   const long long warps_total = static_cast<long long>(gridDim.x) * (blockDim.x >> 5);
   for (long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows;
        row += warps_total) {
-    float vals[kLnMaxVec][8];
+    float vals[NV][8];
     float sum = 0.f;
     const __half* xr = x + row * ld_x;
 #pragma unroll
-    for (int k = 0; k < kLnMaxVec; ++k) {
+    for (int k = 0; k < NV; ++k) {
       const int v = lane + k * 32;
       if (v < vpr) {
         ld8(xr + v * 8, vals[k]);
@@ -215,7 +218,7 @@ __global__ void layernorm_kernel(const __half* __restrict__ x, long long ld_x, _
     const float mean = sum / C;
     float sq = 0.f;
 #pragma unroll
-    for (int k = 0; k < kLnMaxVec; ++k) {
+    for (int k = 0; k < NV; ++k) {
       const int v = lane + k * 32;
       if (v < vpr) {
 #pragma unroll
@@ -230,7 +233,7 @@ __global__ void layernorm_kernel(const __half* __restrict__ x, long long ld_x, _
     const float rstd = rsqrtf(sq / C + eps);
     __half* yr = y + row * ld_y;
 #pragma unroll
-    for (int k = 0; k < kLnMaxVec; ++k) {
+    for (int k = 0; k < NV; ++k) {
       const int v = lane + k * 32;
       if (v < vpr) {
         float o[8];
@@ -288,12 +291,24 @@ extern "C" int lvd_layernorm(const void* x, int64_t ld_x, void* y, int64_t ld_y,
   if (rows <= 0) return LVD_OK;
   const int warps = 8;
   long long blocks = (rows + warps - 1) / warps;
-  const long long cap = 8LL * num_sms();
+  const long long cap = 16LL * num_sms();
   if (blocks > cap) blocks = cap;
-  layernorm_kernel<<<static_cast<unsigned>(blocks), warps * 32, 2 * channels * sizeof(float),
-                     static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __half*>(x), ld_x, static_cast<__half*>(y), ld_y, rows, channels,
-      static_cast<const __half*>(gamma), static_cast<const __half*>(beta), eps);
+  const int nv = (channels / 8 + 31) / 32;
+#define LVD_LN_LAUNCH(NV)                                                                                         \
+  layernorm_kernel<NV><<<static_cast<unsigned>(blocks), warps * 32, 2 * channels * sizeof(float),                \
+                         static_cast<cudaStream_t>(stream)>>>(                                                   \
+      static_cast<const __half*>(x), ld_x, static_cast<__half*>(y), ld_y, rows, channels,                        \
+      static_cast<const __half*>(gamma), static_cast<const __half*>(beta), eps)
+  if (nv <= 2) {
+    LVD_LN_LAUNCH(2);
+  } else if (nv <= 3) {
+    LVD_LN_LAUNCH(3);
+  } else if (nv <= 5) {
+    LVD_LN_LAUNCH(5);
+  } else {
+    LVD_LN_LAUNCH(8);
+  }
+#undef LVD_LN_LAUNCH
   g_launches.fetch_add(1, std::memory_order_relaxed);
   LVD_CHECK_CUDA(cudaGetLastError());
   return LVD_OK;

@@ -54,10 +54,10 @@ def _check_act(t, name="tensor"):
         raise ValueError(f"{name}: row stride must be a multiple of 8 and base 16-byte aligned")
 
 
-def pick_block_n(n, act=ACT_NONE):
+def pick_block_n(n, act=ACT_NONE, mn_major=False):
     if act == ACT_GEGLU:
         return 128
-    for bn in (256, 160, 128, 64):
+    for bn in ((256, 128, 64) if mn_major else (256, 160, 128, 64)):
         if n % bn == 0:
             return bn
     raise ValueError(f"N={n} is not a multiple of 64")
@@ -96,7 +96,7 @@ def choose_box(dims, max_rows=128):
 
 def gemm_raw(*, a, a_dims, a_strides, a_box, taps, k_per_tap, w, n, out, out_dims, out_row_stride,
              rv_stride=(0, 0, 0, 0), bias=None, act=ACT_NONE, rowvec=None, gamma=1.0, residual=None,
-             b_mn_major=False, block_n=None, ldb=None):
+             b_mn_major=False, block_n=None, ldb=None, b_k_tap_stride=0, b_n_tap_stride=0):
     d = GemmDesc()
     d.a = a.data_ptr()
     for i in range(5):
@@ -110,7 +110,7 @@ def gemm_raw(*, a, a_dims, a_strides, a_box, taps, k_per_tap, w, n, out, out_dim
             d.tap_off[t][i] = int(off[i])
     d.b = w.data_ptr()
     d.b_mn_major = 1 if b_mn_major else 0
-    d.block_n = int(block_n or pick_block_n(n, act))
+    d.block_n = int(block_n or pick_block_n(n, act, b_mn_major))
     d.ldb = int(ldb if ldb is not None else w.stride(0))
     d.n = int(n)
     d.act = int(act)
@@ -126,6 +126,8 @@ def gemm_raw(*, a, a_dims, a_strides, a_box, taps, k_per_tap, w, n, out, out_dim
     d.ld_res = residual.stride(0) if residual is not None else 0
     d.ld_out = out.stride(0)
     d.gamma = float(gamma)
+    d.b_k_tap_stride = int(b_k_tap_stride)
+    d.b_n_tap_stride = int(b_n_tap_stride)
     if PROF is not None:
         m = 1
         for v in out_dims:
@@ -431,4 +433,213 @@ def gligen_prep(boxes, masks, positive_embeddings, null_positive, null_position)
     _lib.check(_lib.lib().lvd_gligen_prep(b.data_ptr(), m.data_ptr(), pe.data_ptr(), null_positive.data_ptr(),
                                           null_position.data_ptr(), out.data_ptr(), n * no, d, _stream()),
                "gligen_prep")
+    return out
+
+
+# =============================================================================================== backward (dgrad) ops
+def _gn_workspace2(dev, samples, groups):
+    return _gn_workspace(dev, 2 * samples, groups)
+
+
+def linear_dgrad(dy, w, *, residual=None, out=None, row_map=None):
+    """dx = dy @ w  for a forward y = x @ w.T (w [N_out, K_in], as stored for the forward; read MN-major)."""
+    return linear(dy, w, b_mn_major=True, n=w.shape[1], residual=residual, out=out, row_map=row_map)
+
+
+def conv2d_3x3_dgrad(dy, n_img, h, w_, wk, *, residual=None, out=None):
+    """Adjoint of conv2d_3x3 w.r.t. its input: 9 shifted boxes of dy (negated offsets) against the same
+    [Cout, 9*Cin] weight read MN-major with a per-tap column offset."""
+    _check_act(dy, "dy")
+    cout = wk.shape[0]
+    cin = wk.shape[1] // 9
+    assert dy.shape == (n_img * h * w_, cout)
+    if out is None:
+        out = _alloc_out(dy.shape[0], cin, dy)
+    ld = dy.stride(0)
+    bw, bh, bn = choose_box((w_, h, n_img))
+    taps = [(0, -dx, -dy_, 0, 0) for dy_ in (-1, 0, 1) for dx in (-1, 0, 1)]
+    return gemm_raw(a=dy, a_dims=(cout, w_, h, n_img, 1), a_strides=(1, ld, ld * w_, ld * w_ * h, ld * w_ * h * n_img),
+                    a_box=(64, bw, bh, bn, 1), taps=taps, k_per_tap=cout, w=wk, n=cin, out=out,
+                    out_dims=(w_, h, n_img, 1), out_row_stride=(1, w_, w_ * h, 0), residual=residual, b_mn_major=True,
+                    b_k_tap_stride=0, b_n_tap_stride=cin)
+
+
+def conv_temporal_dgrad(dy, batch, frames, hw, wk, *, residual=None, out=None):
+    _check_act(dy, "dy")
+    cout = wk.shape[0]
+    cin = wk.shape[1] // 3
+    if out is None:
+        out = _alloc_out(dy.shape[0], cin, dy)
+    ld = dy.stride(0)
+    bp, bf, bb = choose_box((hw, frames, batch))
+    taps = [(0, 0, -df, 0, 0) for df in (-1, 0, 1)]
+    return gemm_raw(a=dy, a_dims=(cout, hw, frames, batch, 1),
+                    a_strides=(1, ld, ld * hw, ld * hw * frames, ld * hw * frames * batch), a_box=(64, bp, bf, bb, 1),
+                    taps=taps, k_per_tap=cout, w=wk, n=cin, out=out, out_dims=(hw, frames, batch, 1),
+                    out_row_stride=(1, hw, hw * frames, 0), residual=residual, b_mn_major=True, b_k_tap_stride=0,
+                    b_n_tap_stride=cin)
+
+
+def conv2d_3x3_s2_dgrad(dy, n_img, h, w_, wk_parity, *, out=None):
+    """Adjoint of conv2d_3x3_s2 (input h x w_, output h/2 x w_/2).  One launch per input-pixel parity class (a, b);
+    `wk_parity[(a, b)]` = ([Cout, ntaps*Cin] weight slice, [(sx, sy)] output-pixel shifts) from
+    repack.s2_dgrad_weights."""
+    _check_act(dy, "dy")
+    ho, wo = h // 2, w_ // 2
+    cout = dy.shape[1]
+    any_w = wk_parity[(0, 0)][0]
+    cin = any_w.shape[1]
+    if out is None:
+        out = _alloc_out(n_img * h * w_, cin, dy)
+    ld = dy.stride(0)
+    bw, bh, bn = choose_box((wo, ho, n_img))
+    for (a, b), (wsub, shifts) in wk_parity.items():
+        taps = [(0, sx, sy, 0, 0) for (sx, sy) in shifts]
+        gemm_raw(a=dy, a_dims=(cout, wo, ho, n_img, 1), a_strides=(1, ld, ld * wo, ld * wo * ho, ld * wo * ho * n_img),
+                 a_box=(64, bw, bh, bn, 1), taps=taps, k_per_tap=cout, w=wsub, n=cin, out=out[a * w_ + b:],
+                 out_dims=(wo, ho, n_img, 1), out_row_stride=(2, 2 * w_, h * w_, 0), b_mn_major=True,
+                 b_k_tap_stride=0, b_n_tap_stride=cin)
+    return out
+
+
+def groupnorm_bwd(x, dz, samples, gamma, beta, eps, *, groups=32, silu=False, out=None, accumulate=False):
+    _check_act(x, "x")
+    _check_act(dz, "dz")
+    rows, c = x.shape
+    if out is None:
+        assert not accumulate
+        out = _alloc_out(rows, c, x)
+    ws = _gn_workspace2(x.device, samples, groups)
+    with _Timed("groupnorm_bwd", 0.0, 2.0 * rows * c * 4):
+        _lib.check(_lib.lib().lvd_groupnorm_bwd(x.data_ptr(), x.stride(0), dz.data_ptr(), dz.stride(0), out.data_ptr(),
+                                                out.stride(0), samples, rows // samples, c, groups, gamma.data_ptr(),
+                                                beta.data_ptr(), float(eps), 1 if silu else 0, 1 if accumulate else 0,
+                                                ws.data_ptr(), ws.numel(), _stream()), "groupnorm_bwd")
+    return out
+
+
+def layernorm_bwd(x, dy, gamma, eps=1e-5, *, out=None, accumulate=False):
+    _check_act(x, "x")
+    _check_act(dy, "dy")
+    rows, c = x.shape
+    if out is None:
+        assert not accumulate
+        out = _alloc_out(rows, c, x)
+    with _Timed("layernorm_bwd", 0.0, 2.0 * rows * c * 3):
+        _lib.check(_lib.lib().lvd_layernorm_bwd(x.data_ptr(), x.stride(0), dy.data_ptr(), dy.stride(0), out.data_ptr(),
+                                                out.stride(0), rows, c, gamma.data_ptr(), float(eps),
+                                                1 if accumulate else 0, _stream()), "layernorm_bwd")
+    return out
+
+
+def geglu(pre, out=None):
+    _check_act(pre, "pre")
+    rows, n2 = pre.shape
+    if out is None:
+        out = _alloc_out(rows, n2 // 2, pre)
+    _lib.check(_lib.lib().lvd_geglu(pre.data_ptr(), pre.stride(0), out.data_ptr(), out.stride(0), rows, n2 // 2,
+                                    _stream()), "geglu")
+    return out
+
+
+def geglu_bwd(pre, dout, out=None):
+    _check_act(pre, "pre")
+    _check_act(dout, "dout")
+    rows, n2 = pre.shape
+    if out is None:
+        out = _alloc_out(rows, n2, pre)
+    _lib.check(_lib.lib().lvd_geglu_bwd(pre.data_ptr(), pre.stride(0), dout.data_ptr(), dout.stride(0), out.data_ptr(),
+                                        out.stride(0), rows, n2 // 2, _stream()), "geglu_bwd")
+    return out
+
+
+def add_rows(a, b, out=None):
+    _check_act(a, "a")
+    _check_act(b, "b")
+    if out is None:
+        out = _alloc_out(a.shape[0], a.shape[1], a)
+    _lib.check(_lib.lib().lvd_add_rows(a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), out.data_ptr(),
+                                       out.stride(0), a.shape[0], a.shape[1], _stream()), "add_rows")
+    return out
+
+
+def upsample2x_bwd(dy, n_img, h, w_):
+    """dy rows of the (2h x 2w_) image -> dx rows of the (h x w_) image."""
+    _check_act(dy, "dy")
+    out = _alloc_out(n_img * h * w_, dy.shape[1], dy)
+    _lib.check(_lib.lib().lvd_upsample2x_bwd(dy.data_ptr(), dy.stride(0), out.data_ptr(), out.stride(0), n_img, h, w_,
+                                             dy.shape[1], _stream()), "upsample2x_bwd")
+    return out
+
+
+def conv_in_bwd(drows, weight, batch, frames, h, w_):
+    _check_act(drows, "drows")
+    cout, cin = weight.shape[0], weight.shape[1]
+    out = torch.empty((batch, cin, frames, h, w_), dtype=torch.float32, device=drows.device)
+    _lib.check(_lib.lib().lvd_conv_in_bwd(drows.data_ptr(), drows.stride(0), weight.data_ptr(), out.data_ptr(), batch,
+                                          cin, frames, h, w_, cout, _stream()), "conv_in_bwd")
+    return out
+
+
+def latent_update(latents, grad_f32, coef, unscale, want_grad=False):
+    out = torch.empty_like(latents)
+    gh = torch.empty_like(latents) if want_grad else None
+    _lib.check(_lib.lib().lvd_latent_update(latents.data_ptr(), grad_f32.data_ptr(), out.data_ptr(),
+                                            gh.data_ptr() if gh is not None else None, latents.numel(), float(coef),
+                                            float(unscale), _stream()), "latent_update")
+    return out, gh
+
+
+def attn_rowdot(o, d_o, heads):
+    _check_act(o, "o")
+    _check_act(d_o, "d_o")
+    out = torch.empty((o.shape[0], heads), dtype=torch.float32, device=o.device)
+    _lib.check(_lib.lib().lvd_attn_rowdot(o.data_ptr(), o.stride(0), d_o.data_ptr(), d_o.stride(0), out.data_ptr(),
+                                          o.shape[0], heads, _stream()), "attn_rowdot")
+    return out
+
+
+def self_attention_bwd(qkv, d_o, o, lse, *, heads, nz, s, scale=0.125, out=None):
+    """qkv [nz*s, 3C] (q|k|v); returns d_qkv of the same shape."""
+    _check_act(qkv, "qkv")
+    _check_act(d_o, "d_o")
+    c = heads * 64
+    if out is None:
+        out = torch.empty_like(qkv)
+    dvec = attn_rowdot(o, d_o, heads)
+    with _Timed("attention_self_bwd", 10.0 * nz * heads * s * s * 64, 0.0):
+        _lib.check(_lib.lib().lvd_self_attn_bwd(qkv.data_ptr(), qkv.stride(0), qkv.shape[1], 0, c, 2 * c, d_o.data_ptr(),
+                                                d_o.stride(0), lse.data_ptr(), dvec.data_ptr(), out.data_ptr(),
+                                                out.stride(0), s, heads, nz, float(scale), _stream()), "self_attn_bwd")
+    return out
+
+
+def temporal_attention_bwd(qkv, d_o, *, heads, n_seq, frames, scale=0.125, out=None):
+    _check_act(qkv, "qkv")
+    _check_act(d_o, "d_o")
+    c = heads * 64
+    if out is None:
+        out = torch.empty_like(qkv)
+    with _Timed("attention_temporal_bwd", 10.0 * n_seq * heads * frames * frames * 64, 0.0):
+        _lib.check(_lib.lib().lvd_temporal_attn_bwd(qkv.data_ptr(), qkv.stride(0), 0, c, 2 * c, d_o.data_ptr(),
+                                                    d_o.stride(0), out.data_ptr(), out.stride(0), n_seq, heads, frames,
+                                                    float(scale), _stream()), "temporal_attn_bwd")
+    return out
+
+
+def cross_attention_bwd(q, kv, d_o, *, heads, nz, s_q, s_k, kv_z_div, dp_tok=None, slot_cols=(), scale=0.125, out=None):
+    _check_act(q, "q")
+    _check_act(kv, "kv")
+    _check_act(d_o, "d_o")
+    c = heads * 64
+    if out is None:
+        out = _alloc_out(q.shape[0], c, q)
+    cols = (ctypes.c_int32 * max(1, len(slot_cols)))(*[int(x) for x in slot_cols])
+    with _Timed("attention_cross_bwd", 6.0 * nz * heads * s_q * s_k * 64, 0.0):
+        _lib.check(_lib.lib().lvd_cross_attn_bwd(q.data_ptr(), q.stride(0), kv.data_ptr(), kv.stride(0), 0, c,
+                                                 d_o.data_ptr(), d_o.stride(0),
+                                                 dp_tok.data_ptr() if dp_tok is not None else None, cols,
+                                                 len(slot_cols) if dp_tok is not None else 0, out.data_ptr(),
+                                                 out.stride(0), s_q, s_k, heads, nz, kv_z_div, float(scale), _stream()),
+                   "cross_attn_bwd")
     return out

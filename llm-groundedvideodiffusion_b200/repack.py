@@ -29,3 +29,21 @@ def geglu_interleave(w, b):
         bv, bg = b[:n].reshape(n // 64, 64), b[n:].reshape(n // 64, 64)
         bi = torch.cat([bv, bg], dim=1).reshape(n2).contiguous()
     return wi, bi
+
+
+def s2_dgrad_weights(wk, cin):
+    """Per input-pixel parity class (a, b) of a 3x3 / stride-2 / pad-1 conv: the taps that touch it, gathered into a
+    contiguous [Cout, ntaps*Cin] weight, and for each tap the shift (sx, sy) from the input half-coordinate (X, Y) to
+    the output pixel that used it:  iy = 2*oy + ky - 1  =>  a=0: ky=1, oy=Y;  a=1: ky=0 -> oy=Y+1, ky=2 -> oy=Y."""
+    sel = {0: [(1, 0)], 1: [(0, 1), (2, 0)]}  # parity -> [(k, shift)]
+    out = {}
+    for a in (0, 1):
+        for b in (0, 1):
+            cols, shifts = [], []
+            for ky, sy in sel[a]:
+                for kx, sx in sel[b]:
+                    t = ky * 3 + kx
+                    cols.append(wk[:, t * cin:(t + 1) * cin])
+                    shifts.append((sx, sy))
+            out[(a, b)] = (torch.cat(cols, dim=1).contiguous(), shifts)
+    return out
