@@ -1,0 +1,346 @@
+"""Guidance pass of the denoiser: forward of the UNet prefix that the box energy depends on, the fused energy, and a
+hand-built backward (input gradients only) down to d(energy)/d(latents).
+
+This replaces, for one iteration of the reference's while-loop (models/pipelines.py:65-137):
+    unet(latents, t, cond_embeddings, save_attn_to_dict=..., save_keys=guidance_attn_keys)      # with autograd graph
+    loss = compute_ca_lossv3(saved_attn, bboxes, object_positions, guidance_attn_keys, **kw) * loss_scale
+    grad_cond = torch.autograd.grad(loss, [latents])[0]
+No autograd tape exists here: every forward module below returns a context of the few activations its adjoint needs,
+and `backward` walks the modules in reverse calling the dgrad kernels (lvd_gemm with MN-major weights, GroupNorm /
+LayerNorm / GEGLU adjoints, tcgen05 self-attention dQ/dKdV, temporal and cross attention adjoints).  The forward stops
+right after the last guided cross-attention (the reference computes the rest of the UNet and throws it away,
+models/pipelines.py:99), the attention maps are never materialised (only the object-token columns are emitted), and
+the GLIGEN fusers are bypassed exactly as in the reference (no "gligen" key on this path, models/pipelines.py:66-72).
+Gradients are carried multiplied by GRAD_SCALE in fp16 and un-scaled in the final fp32 latent update.
+"""
+import torch
+
+from . import ops, repack
+from .utils.guidance import build_slots
+from .utils.utils import get_hw_from_attn_dim
+
+GRAD_SCALE = 1024.0
+
+# execution order of the cross-attention keys
+KEY_ORDER = ([("down", i, j, 0) for i in range(3) for j in range(2)] + [("mid", 0, 0, 0)] +
+             [("up", i, j, 0) for i in range(1, 4) for j in range(3)])
+
+
+class Ctx(dict):
+    __getattr__ = dict.__getitem__
+
+
+class GuidanceGraph:
+    def __init__(self, engine):
+        self.e = engine
+        self.w = engine.w
+        self.cfg = engine.cfg
+        self.dev = engine.dev
+        self._s2 = {}
+
+    # ------------------------------------------------------------------------------------------ module pairs
+    def _resnet_fwd(self, L, x, n_img, h, w_, temb_all):
+        eps = self.cfg["norm_eps"]
+        t1 = ops.groupnorm(x, n_img, L.norm1.w, L.norm1.b, eps, silu=True)
+        lo, hi = L.temb
+        t2 = ops.conv2d_3x3(t1, n_img, h, w_, L.conv1.w, L.conv1.b, rowvec=temb_all[:, lo:hi])
+        t3 = ops.groupnorm(t2, n_img, L.norm2.w, L.norm2.b, eps, silu=True)
+        sc = ops.linear(x, L.shortcut.w, L.shortcut.b) if "shortcut" in L else x
+        out = ops.conv2d_3x3(t3, n_img, h, w_, L.conv2.w, L.conv2.b, residual=sc)
+        return out, Ctx(x=x, t2=t2, n_img=n_img, h=h, w=w_)
+
+    def _resnet_bwd(self, L, c, dout):
+        eps = self.cfg["norm_eps"]
+        d3 = ops.conv2d_3x3_dgrad(dout, c.n_img, c.h, c.w, L.conv2.w)
+        d2 = ops.groupnorm_bwd(c.t2, d3, c.n_img, L.norm2.w, L.norm2.b, eps, silu=True)
+        d1 = ops.conv2d_3x3_dgrad(d2, c.n_img, c.h, c.w, L.conv1.w)
+        if "shortcut" in L:
+            dx = ops.linear_dgrad(dout, L.shortcut.w)
+            return ops.groupnorm_bwd(c.x, d1, c.n_img, L.norm1.w, L.norm1.b, eps, silu=True, out=dx, accumulate=True)
+        dx = ops.groupnorm_bwd(c.x, d1, c.n_img, L.norm1.w, L.norm1.b, eps, silu=True)
+        return ops.add_rows(dx, dout)
+
+    def _tconv_fwd(self, layers, x, batch, frames, hw):
+        t = x
+        ins = []
+        for i, L in enumerate(layers):
+            ins.append(t)
+            g = ops.groupnorm(t, batch, L.norm.w, L.norm.b, 1e-5, silu=True)
+            t = ops.conv_temporal(g, batch, frames, hw, L.w, L.b, residual=x if i == 3 else None)
+        return t, Ctx(ins=ins, batch=batch, frames=frames, hw=hw)
+
+    def _tconv_bwd(self, layers, c, dout):
+        d = dout
+        for i in (3, 2, 1, 0):
+            L = layers[i]
+            d = ops.conv_temporal_dgrad(d, c.batch, c.frames, c.hw, L.w)
+            d = ops.groupnorm_bwd(c.ins[i], d, c.batch, L.norm.w, L.norm.b, 1e-5, silu=True)
+        return ops.add_rows(d, dout)
+
+    def _block_fwd(self, B, t, *, heads, spatial, n_img, hw, batch, frames, ctx_kv, tok_cols, want_tok):
+        c = t.shape[1]
+        ctx = Ctx(t0=t, heads=heads, spatial=spatial, n_img=n_img, hw=hw, batch=batch, frames=frames)
+        n1 = ops.layernorm(t, B.norm1.w, B.norm1.b)
+        fm2sm = None if spatial else ("fm2sm", batch, frames, hw)
+        sm2fm = None if spatial else ("sm2fm", batch, frames, hw)
+        qkv = ops.linear(n1, B.qkv1, row_map=fm2sm)
+        if spatial:
+            lse = torch.empty((n_img, heads, hw), dtype=torch.float32, device=self.dev)
+            a = ops.attention(qkv, qkv, heads=heads, nz=n_img, s_q=hw, s_k=hw, k_col0=c, v_col0=2 * c, lse=lse)
+            ctx.update(lse1=lse, a1=a)
+        else:
+            a = ops.attention(qkv, qkv, heads=heads, nz=batch, temporal=True, packed=True, frames=frames, hw=hw,
+                              k_col0=c, v_col0=2 * c)
+        ctx["qkv1"] = qkv
+        t1 = ops.linear(a, B.out1.w, B.out1.b, residual=t, row_map=sm2fm)
+        ctx["t1"] = t1
+        n2 = ops.layernorm(t1, B.norm2.w, B.norm2.b)
+        if spatial:
+            q = ops.linear(n2, B.q2)
+            kv = ops.linear(ctx_kv, B.kv2)
+            p_tok = None
+            if want_tok:
+                p_tok = torch.empty((len(tok_cols), n_img, heads, hw), dtype=torch.float16, device=self.dev)
+            a2 = ops.attention(q, kv, heads=heads, nz=n_img, s_q=hw, s_k=ctx_kv.shape[0] // batch, k_col0=0, v_col0=c,
+                               kv_z_div=frames, p_tok=p_tok, tok_cols=tok_cols if want_tok else ())
+            ctx.update(q2=q, kv2=kv, p_tok=p_tok, s_k=ctx_kv.shape[0] // batch)
+        else:
+            qkv2 = ops.linear(n2, B.qkv2, row_map=fm2sm)
+            a2 = ops.attention(qkv2, qkv2, heads=heads, nz=batch, temporal=True, packed=True, frames=frames, hw=hw,
+                               k_col0=c, v_col0=2 * c)
+            ctx["qkv2"] = qkv2
+        t2 = ops.linear(a2, B.out2.w, B.out2.b, residual=t1, row_map=sm2fm)
+        ctx["t2"] = t2
+        n3 = ops.layernorm(t2, B.norm3.w, B.norm3.b)
+        pre = ops.linear(n3, B.ff1.w, B.ff1.b)  # un-fused GEGLU: the adjoint needs the pre-activation
+        gg = ops.geglu(pre)
+        ctx["pre"] = pre
+        t3 = ops.linear(gg, B.ff2.w, B.ff2.b, residual=t2)
+        return t3, ctx
+
+    def _block_bwd(self, B, c, d3, dp_tok=None, tok_cols=()):
+        """d3: gradient w.r.t. the block output, or None when only the cross-attention energy seeds it."""
+        sp = c.spatial
+        fm2sm = None if sp else ("fm2sm", c.batch, c.frames, c.hw)
+        sm2fm = None if sp else ("sm2fm", c.batch, c.frames, c.hw)
+        ch = c.t0.shape[1]
+        if d3 is not None:
+            d_gg = ops.linear_dgrad(d3, B.ff2.w)
+            d_pre = ops.geglu_bwd(c.pre, d_gg)
+            d_n3 = ops.linear_dgrad(d_pre, B.ff1.w)
+            d_t2 = ops.layernorm_bwd(c.t2, d_n3, B.norm3.w, out=d3, accumulate=True)
+            d_a2 = ops.linear_dgrad(d_t2, B.out2.w, row_map=fm2sm)
+        else:
+            d_t2 = None
+            d_a2 = torch.zeros((c.t0.shape[0], ch), dtype=torch.float16, device=self.dev)
+        if sp:
+            d_q = ops.cross_attention_bwd(c.q2, c.kv2, d_a2, heads=c.heads, nz=c.n_img, s_q=c.hw, s_k=c.s_k,
+                                          kv_z_div=c.frames, dp_tok=dp_tok, slot_cols=tok_cols)
+            d_n2 = ops.linear_dgrad(d_q, B.q2)
+        else:
+            d_qkv2 = ops.temporal_attention_bwd(c.qkv2, d_a2, heads=c.heads, n_seq=c.batch * c.hw, frames=c.frames)
+            d_n2 = ops.linear_dgrad(d_qkv2, B.qkv2, row_map=sm2fm)
+        if d_t2 is not None:
+            d_t1 = ops.layernorm_bwd(c.t1, d_n2, B.norm2.w, out=d_t2, accumulate=True)
+        else:
+            d_t1 = ops.layernorm_bwd(c.t1, d_n2, B.norm2.w)
+        d_a = ops.linear_dgrad(d_t1, B.out1.w, row_map=fm2sm)
+        if sp:
+            d_qkv = ops.self_attention_bwd(c.qkv1, d_a, c.a1, c.lse1, heads=c.heads, nz=c.n_img, s=c.hw)
+        else:
+            d_qkv = ops.temporal_attention_bwd(c.qkv1, d_a, heads=c.heads, n_seq=c.batch * c.hw, frames=c.frames)
+        d_n1 = ops.linear_dgrad(d_qkv, B.qkv1, row_map=sm2fm)
+        return ops.layernorm_bwd(c.t0, d_n1, B.norm1.w, out=d_t1, accumulate=True)
+
+    def _transformer_fwd(self, T, x, *, spatial, n_img, hw, batch, frames, ctx_kv=None, tok_cols=(), want_tok=False,
+                         last=False):
+        samples = n_img if spatial else batch
+        g = ops.groupnorm(x, samples, T.norm.w, T.norm.b, 1e-6, silu=False)
+        t0 = ops.linear(g, T.proj_in.w, T.proj_in.b)
+        heads = t0.shape[1] // self.cfg["attention_head_dim"]
+        t1, bctx = self._block_fwd(T.block, t0, heads=heads, spatial=spatial, n_img=n_img, hw=hw, batch=batch,
+                                   frames=frames, ctx_kv=ctx_kv, tok_cols=tok_cols, want_tok=want_tok)
+        out = None if last else ops.linear(t1, T.proj_out.w, T.proj_out.b, residual=x)
+        return out, Ctx(x=x, block=bctx, samples=samples)
+
+    def _transformer_bwd(self, T, c, dout, dp_tok=None, tok_cols=()):
+        if dout is not None:
+            d_t1 = ops.linear_dgrad(dout, T.proj_out.w)
+        else:
+            d_t1 = None
+        d_t0 = self._block_bwd(T.block, c.block, d_t1, dp_tok=dp_tok, tok_cols=tok_cols)
+        d_g = ops.linear_dgrad(d_t0, T.proj_in.w)
+        if dout is not None:
+            return ops.groupnorm_bwd(c.x, d_g, c.samples, T.norm.w, T.norm.b, 1e-6, silu=False, out=dout,
+                                     accumulate=True)
+        return ops.groupnorm_bwd(c.x, d_g, c.samples, T.norm.w, T.norm.b, 1e-6, silu=False)
+
+    def _s2_weights(self, blk):
+        key = id(blk)
+        if key not in self._s2:
+            self._s2[key] = repack.s2_dgrad_weights(blk.down.w, blk.down.w.shape[1] // 9)
+        return self._s2[key]
+
+    # ------------------------------------------------------------------------------------------ the pass
+    def run(self, latents, timestep, cond_embeddings, bboxes, object_positions, guidance_attn_keys, *, loss_scale=1.0,
+            base_attn_dim=(40, 72), fg_top_p=0.2, bg_top_p=0.2, fg_weight=1.0, bg_weight=1.0, com_loss_scale=0.0):
+        """latents (1, 4, F, h, w) fp16; cond_embeddings (1, 77, D).  Returns (loss [0-d fp32 cuda, scaled by
+        loss_scale], grad (1, 4, F, h, w) fp32 = GRAD_SCALE * d loss / d latents)."""
+        cfg, w, dev = self.cfg, self.w, self.dev
+        boc = list(cfg["block_out_channels"])
+        nb = len(boc)
+        keys = [tuple(k) for k in guidance_attn_keys]
+        assert len(keys) > 0 and all(k in KEY_ORDER for k in keys)
+        last_key = max(keys, key=KEY_ORDER.index)
+        latents = latents.to(device=dev, dtype=torch.float16).contiguous()
+        b, cin, frames, h, w_ = latents.shape
+        assert b == 1, "the guidance pass runs the conditional branch only (models/pipelines.py:78-83)"
+        n_img = frames
+        ehs = cond_embeddings.to(device=dev, dtype=torch.float16).contiguous()
+        ctx_kv = ehs.reshape(ehs.shape[1], ehs.shape[2])
+        n_obj = len(bboxes)
+        loss = torch.zeros((), dtype=torch.float32, device=dev)
+        tok_cols = tuple(int(t) for obj in object_positions for t in obj)
+        if n_obj == 0 or len(tok_cols) == 0:
+            return loss, torch.zeros(latents.shape, dtype=torch.float32, device=dev)
+        assert len(tok_cols) <= 16, "at most 16 (object, token) pairs per guidance call"
+        t = torch.as_tensor(timestep, device=dev).reshape(-1).to(torch.float32).expand(1).repeat_interleave(frames)
+        t = t.contiguous()
+        temb = ops.timestep_embed(t, boc[0])
+        temb = ops.linear(temb, w["time1"].w, w["time1"].b, act=ops.ACT_SILU)
+        temb = ops.linear(temb, w["time2"].w, w["time2"].b)
+        temb_all = ops.linear(ops.silu(temb), w["temb_all"].w, w["temb_all"].b)
+
+        tape = []  # (kind, weights, ctx, extra)
+        x = ops.conv_in(latents, w["conv_in"].w, w["conv_in"].b)
+        hw = h * w_
+        x, c = self._transformer_fwd(w["transformer_in"], x, spatial=False, n_img=n_img, hw=hw, batch=1,
+                                     frames=frames)
+        tape.append(("tattn", w["transformer_in"], c, None))
+        done = False
+
+        def layer(L, x, kind, stage, j, h, w_):
+            nonlocal done
+            hw = h * w_
+            x, c = self._resnet_fwd(L.resnet, x, n_img, h, w_, temb_all)
+            tape.append(("resnet", L.resnet, c, None))
+            x, c = self._tconv_fwd(L.tconv, x, 1, frames, hw)
+            tape.append(("tconv", L.tconv, c, None))
+            if "attn" in L:
+                key = (kind, stage, j, 0)
+                is_last = key == last_key
+                x, c = self._transformer_fwd(L.attn, x, spatial=True, n_img=n_img, hw=hw, batch=1, frames=frames,
+                                             ctx_kv=ctx_kv, tok_cols=tok_cols, want_tok=key in keys, last=is_last)
+                tape.append(("attn", L.attn, c, key if key in keys else None))
+                if is_last:
+                    done = True
+                    return x
+                x, c = self._transformer_fwd(L.tattn, x, spatial=False, n_img=n_img, hw=hw, batch=1, frames=frames)
+                tape.append(("tattn", L.tattn, c, None))
+            return x
+
+        skips = [x]
+        for i in range(nb):
+            blk = w["down"][i]
+            for j, L in enumerate(blk.layers):
+                x = layer(L, x, "down", i, j, h, w_)
+                if done:
+                    break
+                skips.append(x)
+                tape.append(("skip_out", None, None, len(skips) - 1))
+            if done:
+                break
+            if "down" in blk:
+                x = ops.conv2d_3x3_s2(x, n_img, h, w_, blk.down.w, blk.down.b)
+                tape.append(("down", blk, Ctx(n_img=n_img, h=h, w=w_), None))
+                h, w_ = h // 2, w_ // 2
+                skips.append(x)
+                tape.append(("skip_out", None, None, len(skips) - 1))
+        if not done:
+            M = w["mid"]
+            hw = h * w_
+            x, c = self._resnet_fwd(M.res0, x, n_img, h, w_, temb_all)
+            tape.append(("resnet", M.res0, c, None))
+            x, c = self._tconv_fwd(M.tconv0, x, 1, frames, hw)
+            tape.append(("tconv", M.tconv0, c, None))
+            key = ("mid", 0, 0, 0)
+            x, c = self._transformer_fwd(M.attn, x, spatial=True, n_img=n_img, hw=hw, batch=1, frames=frames,
+                                         ctx_kv=ctx_kv, tok_cols=tok_cols, want_tok=key in keys, last=key == last_key)
+            tape.append(("attn", M.attn, c, key if key in keys else None))
+            done = key == last_key
+        if not done:
+            M = w["mid"]
+            x, c = self._transformer_fwd(M.tattn, x, spatial=False, n_img=n_img, hw=hw, batch=1, frames=frames)
+            tape.append(("tattn", M.tattn, c, None))
+            x, c = self._resnet_fwd(M.res1, x, n_img, h, w_, temb_all)
+            tape.append(("resnet", M.res1, c, None))
+            x, c = self._tconv_fwd(M.tconv1, x, 1, frames, hw)
+            tape.append(("tconv", M.tconv1, c, None))
+            for i in range(nb):
+                blk = w["up"][i]
+                for j, L in enumerate(blk.layers):
+                    skip = skips.pop()
+                    c1, c2 = x.shape[1], skip.shape[1]
+                    cat = torch.empty((x.shape[0], c1 + c2), dtype=torch.float16, device=dev)
+                    ops.copy_rows(x, cat[:, :c1])
+                    ops.copy_rows(skip, cat[:, c1:])
+                    tape.append(("cat", None, Ctx(c1=c1, c2=c2), len(skips)))
+                    x = layer(L, cat, "up", i, j, h, w_)
+                    if done:
+                        break
+                if done:
+                    break
+                if "up" in blk:
+                    x = ops.upsample2x(x, n_img, h, w_)
+                    tape.append(("up", blk, Ctx(n_img=n_img, h=h, w=w_), None))
+                    h, w_ = 2 * h, 2 * w_
+                    x = ops.conv2d_3x3(x, n_img, h, w_, blk.up.w, blk.up.b)
+        assert done
+
+        # ---------------- energy on the emitted token columns (one launch per guided key), dE/dP seeds
+        seeds = {}
+        out_scale = float(loss_scale) / (n_obj * len(keys))
+        for kind, wts, c, key in tape:
+            if kind == "attn" and key is not None:
+                bc = c.block
+                H, W = get_hw_from_attn_dim(attn_dim=bc.hw, base_attn_dim=base_attn_dim)
+                _, boxes, wts_slot = build_slots(bboxes, object_positions, frames, H, W, dev)
+                dp = torch.empty_like(bc.p_tok)
+                ops.box_energy(bc.p_tok, loss, boxes, wts_slot, frames=frames, heads=bc.heads, H=H, W=W,
+                               fg_top_p=fg_top_p, bg_top_p=bg_top_p, fg_weight=fg_weight, bg_weight=bg_weight,
+                               com_loss_scale=com_loss_scale, out_scale=out_scale, dp=dp, grad_scale=GRAD_SCALE)
+                seeds[key] = dp
+
+        # ---------------- backward
+        gskip = {}
+        d = None
+        for kind, wts, c, extra in reversed(tape):
+            if kind == "attn":
+                d = self._transformer_bwd(wts, c, d, dp_tok=seeds.get(extra), tok_cols=tok_cols if extra else ())
+            elif kind == "tattn":
+                d = self._transformer_bwd(wts, c, d)
+            elif kind == "resnet":
+                d = self._resnet_bwd(wts, c, d)
+            elif kind == "tconv":
+                d = self._tconv_bwd(wts, c, d)
+            elif kind == "cat":
+                dx = torch.empty((d.shape[0], c.c1), dtype=torch.float16, device=dev)
+                ds = torch.empty((d.shape[0], c.c2), dtype=torch.float16, device=dev)
+                ops.copy_rows(d[:, :c.c1], dx)
+                ops.copy_rows(d[:, c.c1:], ds)
+                gskip[extra] = ds
+                d = dx
+            elif kind == "up":
+                d = ops.conv2d_3x3_dgrad(d, c.n_img, 2 * c.h, 2 * c.w, wts.up.w)
+                d = ops.upsample2x_bwd(d, c.n_img, c.h, c.w)
+            elif kind == "down":
+                d = ops.conv2d_3x3_s2_dgrad(d, c.n_img, c.h, c.w, self._s2_weights(wts))
+            elif kind == "skip_out":
+                g = gskip.pop(extra, None)
+                if g is not None:
+                    d = g if d is None else ops.add_rows(d, g)
+        g0 = gskip.pop(0, None)
+        if g0 is not None:
+            d = ops.add_rows(d, g0)
+        grad = ops.conv_in_bwd(d, w["conv_in"].w, 1, frames, latents.shape[3], latents.shape[4])
+        return loss, grad
