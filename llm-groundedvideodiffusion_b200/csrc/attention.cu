@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid
         if (k < nch) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            sv[k][i] = exp2f(sv[k][i] - mx);
+            sv[k][i] = fast_exp2(sv[k][i] - mx);
             sum += sv[k][i];
           }
         }
@@ -239,7 +239,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid
       const int diag = g.diag_mod;
       const int rmod = diag ? (r % diag) : 0;
       const bool single = (g.n_units == 1);
-      float m_run = -INFINITY, l_run = 0.f;
+      float m_run = -INFINITY, l_run = 0.f, l_single = 1.f;
       float o[64];
 #pragma unroll
       for (int i = 0; i < 64; ++i) o[i] = 0.f;
@@ -286,12 +286,13 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid
             for (int i = 0; i < 32; ++i) {
               const int c = ch * 32 + i;
               const bool ok = (c < nvalid) && (diag == 0 || (c % diag) == rmod);
-              sum += ok ? exp2f(fmaf(__uint_as_float(rr[i]), sc, -m_new)) : 0.f;
+              sum += ok ? fast_exp2(fmaf(__uint_as_float(rr[i]), sc, -m_new)) : 0.f;
             }
           }
           inv = 1.f / sum;
+          l_single = sum;
         }
-        const float alpha = exp2f(m_run - m_new);
+        const float alpha = fast_exp2(m_run - m_new);
         float psum = 0.f;
         // ---- pass 3: probabilities -> fp16 -> swizzled smem (A operand of P V)
         for (int ch = 0; ch < nchunks; ++ch) {
@@ -302,7 +303,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid
           if (full) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
-              p[i] = exp2f(fmaf(__uint_as_float(rr[i]), sc, -m_new));
+              p[i] = fast_exp2(fmaf(__uint_as_float(rr[i]), sc, -m_new));
               psum += p[i];
             }
           } else {
@@ -310,7 +311,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid
             for (int i = 0; i < 32; ++i) {
               const int c = ch * 32 + i;
               const bool ok = (c < nvalid) && (diag == 0 || (c % diag) == rmod);
-              const float e = ok ? exp2f(fmaf(__uint_as_float(rr[i]), sc, -m_new)) * inv : 0.f;
+              const float e = ok ? fast_exp2(fmaf(__uint_as_float(rr[i]), sc, -m_new)) * inv : 0.f;
               p[i] = e;
               psum += e;
             }
@@ -366,7 +367,8 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid
       }
       if (row_valid) {
         const float fin = single ? 1.f : 1.f / l_run;
-        if (g.lse) g.lse[(static_cast<long long>(z) * g.heads + h) * g.p_rows + c1] = m_run + log2f(l_run);
+        if (g.lse)
+          g.lse[(static_cast<long long>(z) * g.heads + h) * g.p_rows + c1] = m_run + log2f(single ? l_single : l_run);
 #pragma unroll
         for (int s8 = 0; s8 < 8; ++s8) {
           uint4 v;

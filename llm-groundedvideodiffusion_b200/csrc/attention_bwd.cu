@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_dq_kernel(const __gri
           for (int i = 0; i < 8; ++i) {
             const int c = ch * 32 + s8 * 8 + i;
             const bool ok = row_valid && (c < nvalid);
-            const float p = ok ? exp2f(fmaf(__uint_as_float(rs[s8 * 8 + i]), g.scale_log2, -L)) : 0.f;
+            const float p = ok ? fast_exp2(fmaf(__uint_as_float(rs[s8 * 8 + i]), g.scale_log2, -L)) : 0.f;
             v[i] = p * (__uint_as_float(rp[s8 * 8 + i]) - Dv);
           }
           store_chunk16(ds_row, r, ch * 32 + s8 * 8, v);
@@ -324,7 +324,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_dkdv_kernel(const __g
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             const bool ok = row_valid && (ch * 32 + i < kvalid);
-            const float p = ok ? exp2f(fmaf(__uint_as_float(rs[i]), g.scale_log2, -L)) : 0.f;
+            const float p = ok ? fast_exp2(fmaf(__uint_as_float(rs[i]), g.scale_log2, -L)) : 0.f;
             pv[i] = p;
             dv_[i] = p * (__uint_as_float(rp[i]) - Dv);
           }

@@ -62,7 +62,7 @@ __device__ __forceinline__ float silu_grad(float y) {
 
 __global__ void gn_bwd_stats_kernel(const __half* __restrict__ x, long long ld_x, const __half* __restrict__ dz,
                                     long long ld_dz, long long rows_per_sample, int C, int G, int chunks,
-                                    const float* __restrict__ fwd_partial, const __half* __restrict__ gamma,
+                                    const float* __restrict__ stats, const __half* __restrict__ gamma,
                                     const __half* __restrict__ beta, float eps, int silu,
                                     float* __restrict__ bwd_partial) {
   extern __shared__ float s_acc[];  // [2*C] then [2*G] mean/rstd
@@ -73,9 +73,11 @@ __global__ void gn_bwd_stats_kernel(const __half* __restrict__ x, long long ld_x
   const int v = threadIdx.x % vpr, rsub = threadIdx.x / vpr;
   const int chunk = blockIdx.x, s = blockIdx.y;
   const int cpg = C / G;
-  const float n = static_cast<float>(rows_per_sample) * cpg;
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) s_acc[i] = 0.f;
-  for (int g = threadIdx.x; g < G; g += blockDim.x) gn_finalize_fwd(fwd_partial, s, chunks, G, g, n, eps, s_mean[g], s_rstd[g]);
+  for (int g = threadIdx.x; g < G; g += blockDim.x) {
+    s_mean[g] = stats[(static_cast<long long>(s) * G + g) * 2];
+    s_rstd[g] = stats[(static_cast<long long>(s) * G + g) * 2 + 1];
+  }
   __syncthreads();
   const long long rows_per_chunk = (rows_per_sample + chunks - 1) / chunks;
   const long long r0 = chunk * rows_per_chunk;
@@ -130,7 +132,7 @@ __global__ void gn_bwd_stats_kernel(const __half* __restrict__ x, long long ld_x
 __global__ void gn_bwd_apply_kernel(const __half* __restrict__ x, long long ld_x, const __half* __restrict__ dz,
                                     long long ld_dz, __half* __restrict__ dx, long long ld_dx,
                                     long long rows_per_sample, int C, int G, int chunks,
-                                    const float* __restrict__ fwd_partial, const float* __restrict__ bwd_partial,
+                                    const float* __restrict__ stats, const float* __restrict__ bstats,
                                     const __half* __restrict__ gamma, const __half* __restrict__ beta, float eps,
                                     int silu, int accumulate) {
   __shared__ float s_mean[64], s_rstd[64], s_m1[64], s_m2[64];
@@ -139,17 +141,11 @@ __global__ void gn_bwd_apply_kernel(const __half* __restrict__ x, long long ld_x
   const int v = threadIdx.x % vpr, rsub = threadIdx.x / vpr;
   const int chunk = blockIdx.x, s = blockIdx.y;
   const int cpg = C / G;
-  const float n = static_cast<float>(rows_per_sample) * cpg;
   for (int g = threadIdx.x; g < G; g += blockDim.x) {
-    gn_finalize_fwd(fwd_partial, s, chunks, G, g, n, eps, s_mean[g], s_rstd[g]);
-    float a = 0.f, b = 0.f;
-    for (int k = 0; k < chunks; ++k) {
-      const float* p = bwd_partial + ((static_cast<long long>(s) * chunks + k) * G + g) * 2;
-      a += p[0];
-      b += p[1];
-    }
-    s_m1[g] = a / n;
-    s_m2[g] = b / n;
+    s_mean[g] = stats[(static_cast<long long>(s) * G + g) * 2];
+    s_rstd[g] = stats[(static_cast<long long>(s) * G + g) * 2 + 1];
+    s_m1[g] = bstats[(static_cast<long long>(s) * G + g) * 2];
+    s_m2[g] = bstats[(static_cast<long long>(s) * G + g) * 2 + 1];
   }
   __syncthreads();
   if (rsub >= rpp) return;
@@ -192,6 +188,8 @@ __global__ void gn_bwd_apply_kernel(const __half* __restrict__ x, long long ld_x
 // forward statistics kernel lives in norm.cu
 __global__ void gn_stats_kernel(const __half* __restrict__ x, long long ld, long long rows_per_sample, int C, int G,
                                 int chunks, float* __restrict__ partial);
+__global__ void gn_finalize_kernel(const float* __restrict__ partial, int chunks, int G, float n, float eps,
+                                   float* __restrict__ stats, int raw_means);
 
 // ------------------------------------------------------------------------------------------------ LayerNorm backward
 constexpr int kLnbMaxVec = 8;
@@ -467,24 +465,31 @@ extern "C" int lvd_groupnorm_bwd(const void* x, int64_t ld_x, const void* dz, in
   if (chunks < 1) chunks = 1;
   if (chunks > 1024) chunks = 1024;
   const long long one = static_cast<long long>(samples) * chunks * groups * 2 * sizeof(float);
-  LVD_REQUIRE(workspace_bytes >= 2 * one, "lvd_groupnorm_bwd: workspace too small");
+  const long long small = static_cast<long long>(samples) * groups * 2 * sizeof(float);
+  LVD_REQUIRE(workspace_bytes >= 2 * one + 2 * small, "lvd_groupnorm_bwd: workspace too small");
   float* fwd = static_cast<float*>(workspace);
   float* bwd = fwd + one / sizeof(float);
+  float* stats = bwd + one / sizeof(float);
+  float* bstats = stats + small / sizeof(float);
   const int vpr = channels / 8;
   int rpp = 256 / vpr;
   if (rpp < 1) rpp = 1;
   const int threads = rpp * vpr;
   LVD_REQUIRE(threads <= 1024, "lvd_groupnorm_bwd: C too wide");
   dim3 grid(static_cast<unsigned>(chunks), static_cast<unsigned>(samples));
+  const float n = static_cast<float>(rows_per_sample) * (channels / groups);
+  const int fin_threads = 256 / groups * groups;
   gn_stats_kernel<<<grid, threads, 2 * channels * sizeof(float), ST(stream)>>>(HC(x), ld_x, rows_per_sample, channels,
                                                                                groups, static_cast<int>(chunks), fwd);
+  gn_finalize_kernel<<<samples, fin_threads, 0, ST(stream)>>>(fwd, static_cast<int>(chunks), groups, n, eps, stats, 0);
   gn_bwd_stats_kernel<<<grid, threads, (2 * channels + 2 * groups) * sizeof(float), ST(stream)>>>(
-      HC(x), ld_x, HC(dz), ld_dz, rows_per_sample, channels, groups, static_cast<int>(chunks), fwd, HC(gamma), HC(beta),
-      eps, silu, bwd);
+      HC(x), ld_x, HC(dz), ld_dz, rows_per_sample, channels, groups, static_cast<int>(chunks), stats, HC(gamma),
+      HC(beta), eps, silu, bwd);
+  gn_finalize_kernel<<<samples, fin_threads, 0, ST(stream)>>>(bwd, static_cast<int>(chunks), groups, n, eps, bstats, 1);
   gn_bwd_apply_kernel<<<grid, threads, 0, ST(stream)>>>(HC(x), ld_x, HC(dz), ld_dz, HM(dx), ld_dx, rows_per_sample,
-                                                        channels, groups, static_cast<int>(chunks), fwd, bwd, HC(gamma),
-                                                        HC(beta), eps, silu, accumulate);
-  g_launches.fetch_add(3, std::memory_order_relaxed);
+                                                        channels, groups, static_cast<int>(chunks), stats, bstats,
+                                                        HC(gamma), HC(beta), eps, silu, accumulate);
+  g_launches.fetch_add(5, std::memory_order_relaxed);
   LVD_CHECK_CUDA(cudaGetLastError());
   return LVD_OK;
 }

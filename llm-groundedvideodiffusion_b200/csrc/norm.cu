@@ -94,10 +94,43 @@ __global__ void gn_stats_kernel(const __half* __restrict__ x, long long ld, long
   }
 }
 
+// Folds the per-chunk partial sums of one sample into {mean, rstd} per group (deterministic order).  A separate
+// tiny launch: with 5-D GroupNorm (2 samples x ~600 chunks) doing this in every apply CTA serialised ~600 dependent
+// loads in front of the streaming loop.
+__global__ void gn_finalize_kernel(const float* __restrict__ partial, int chunks, int G, float n, float eps,
+                                   float* __restrict__ stats, int raw_means) {
+  __shared__ float s_a[256], s_b[256];
+  const int s = blockIdx.x;
+  const int g = threadIdx.x % G, part = threadIdx.x / G, nparts = blockDim.x / G;
+  float a = 0.f, b = 0.f;
+  if (part < nparts)
+    for (int k = part; k < chunks; k += nparts) {
+      const float* p = partial + ((static_cast<long long>(s) * chunks + k) * G + g) * 2;
+      a += p[0];
+      b += p[1];
+    }
+  s_a[threadIdx.x] = a;
+  s_b[threadIdx.x] = b;
+  __syncthreads();
+  if (threadIdx.x < G) {
+    a = 0.f;
+    b = 0.f;
+    for (int q = 0; q < nparts; ++q) {
+      a += s_a[q * G + threadIdx.x];
+      b += s_b[q * G + threadIdx.x];
+    }
+    const float mean = a / n;
+    float var = b / n - mean * mean;
+    var = var > 0.f ? var : 0.f;
+    stats[(static_cast<long long>(s) * G + threadIdx.x) * 2] = mean;
+    stats[(static_cast<long long>(s) * G + threadIdx.x) * 2 + 1] = raw_means ? b / n : rsqrtf(var + eps);
+  }
+}
+
 __global__ void gn_apply_kernel(const __half* __restrict__ x, long long ld_x, __half* __restrict__ y, long long ld_y,
-                                long long rows_per_sample, int C, int G, int chunks_stats,
-                                const float* __restrict__ partial, const __half* __restrict__ gamma,
-                                const __half* __restrict__ beta, float eps, int silu, int chunks) {
+                                long long rows_per_sample, int C, int G, const float* __restrict__ stats,
+                                const __half* __restrict__ gamma, const __half* __restrict__ beta, int silu,
+                                int chunks) {
   __shared__ float s_mean[64], s_rstd[64];
   const int vpr = C >> 3;
   const int rpp = blockDim.x / vpr;
@@ -106,18 +139,8 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x, long long ld_x, __
   const int chunk = blockIdx.x, s = blockIdx.y;
   const int cpg = C / G;
   for (int g = threadIdx.x; g < G; g += blockDim.x) {
-    float a = 0.f, b = 0.f;
-    for (int k = 0; k < chunks_stats; ++k) {
-      const float* p = partial + ((static_cast<long long>(s) * chunks_stats + k) * G + g) * 2;
-      a += p[0];
-      b += p[1];
-    }
-    const float n = static_cast<float>(rows_per_sample) * cpg;
-    const float mean = a / n;
-    float var = b / n - mean * mean;
-    var = var > 0.f ? var : 0.f;
-    s_mean[g] = mean;
-    s_rstd[g] = rsqrtf(var + eps);
+    s_mean[g] = stats[(static_cast<long long>(s) * G + g) * 2];
+    s_rstd[g] = stats[(static_cast<long long>(s) * G + g) * 2 + 1];
   }
   __syncthreads();
   if (rsub >= rpp) return;
@@ -267,18 +290,24 @@ extern "C" int lvd_groupnorm(const void* x, int64_t ld_x, void* y, int64_t ld_y,
   if (chunks < 1) chunks = 1;
   if (chunks > 1024) chunks = 1024;
   const long long need = static_cast<long long>(samples) * chunks * groups * 2 * sizeof(float);
-  LVD_REQUIRE(workspace_bytes >= need, "lvd_groupnorm: workspace %lld < %lld bytes", (long long)workspace_bytes, need);
+  LVD_REQUIRE(workspace_bytes >= need + static_cast<long long>(samples) * groups * 2 * sizeof(float),
+              "lvd_groupnorm: workspace %lld < %lld bytes", (long long)workspace_bytes, need);
   const int threads = gn_threads(channels);
   LVD_REQUIRE(threads <= 1024, "lvd_groupnorm: C=%d too wide", channels);
   dim3 grid(static_cast<unsigned>(chunks), static_cast<unsigned>(samples));
   gn_stats_kernel<<<grid, threads, 2 * channels * sizeof(float), st>>>(
       static_cast<const __half*>(x), ld_x, rows_per_sample, channels, groups, static_cast<int>(chunks),
       static_cast<float*>(workspace));
+  float* stats = static_cast<float*>(workspace) + need / sizeof(float);
+  gn_finalize_kernel<<<samples, 256 / groups * groups, 0, st>>>(static_cast<const float*>(workspace),
+                                                               static_cast<int>(chunks), groups,
+                                                               static_cast<float>(rows_per_sample) * (channels / groups),
+                                                               eps, stats, 0);
   gn_apply_kernel<<<grid, threads, 0, st>>>(static_cast<const __half*>(x), ld_x, static_cast<__half*>(y), ld_y,
-                                            rows_per_sample, channels, groups, static_cast<int>(chunks),
-                                            static_cast<const float*>(workspace), static_cast<const __half*>(gamma),
-                                            static_cast<const __half*>(beta), eps, silu, static_cast<int>(chunks));
-  g_launches.fetch_add(2, std::memory_order_relaxed);
+                                            rows_per_sample, channels, groups, stats,
+                                            static_cast<const __half*>(gamma), static_cast<const __half*>(beta), silu,
+                                            static_cast<int>(chunks));
+  g_launches.fetch_add(3, std::memory_order_relaxed);
   LVD_CHECK_CUDA(cudaGetLastError());
   return LVD_OK;
 }

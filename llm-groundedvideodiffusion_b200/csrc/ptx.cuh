@@ -177,6 +177,12 @@ __host__ __device__ __forceinline__ uint32_t make_idesc_f16(uint32_t M, uint32_t
 }
 
 // ---------------------------------------------------------------- misc math helpers
+// single-MUFU 2^x (rel. error 2^-22); exp2f() without fast-math adds range handling the softmax does not need
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ float round_h(float v) { return __half2float(__float2half_rn(v)); }
 __device__ __forceinline__ float silu_f(float v) { return v / (1.0f + __expf(-v)); }
 // erf-GELU (F.gelu default, models/attention.py:365-376).  erf by Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7, far

@@ -261,7 +261,7 @@ _gn_ws = {}
 
 
 def _gn_workspace(dev, samples, groups):
-    need = samples * 1024 * groups * 8
+    need = samples * 1040 * groups * 8
     ws = _gn_ws.get(dev)
     if ws is None or ws.numel() < need:
         ws = torch.empty(max(need, 1 << 22), dtype=torch.uint8, device=dev)

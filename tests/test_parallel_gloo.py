@@ -1,0 +1,57 @@
+"""CPU test of the N>1 host path: world_size-2 gloo processes exercise the work-table broadcast, the contiguous
+sharding, the ordered gather and the max-over-ranks timing reduction that bench.py uses under NCCL."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from lvd_b200 import parallel
+    n_items = 7
+    table = torch.stack([torch.arange(n_items), torch.zeros(n_items, dtype=torch.int64),
+                         torch.tensor([parallel.seed_for(i, 0, 3) for i in range(n_items)])], 1) \
+        if rank == 0 else torch.empty(0, dtype=torch.int64)
+    table = parallel.broadcast_work_table(table, "cpu")
+    lo, hi = parallel.shard_items(n_items, rank, world)
+    local = (table[lo:hi, 2:3].float() * 2.0)  # "result" of each item
+    out = parallel.gather_results(local, n_items)
+    mx = parallel.max_over_ranks(10.0 + rank, "cpu")
+    if rank == 0:
+        ret["gathered"] = out.flatten().tolist()
+    ret[f"max{rank}"] = mx
+    ret[f"win{rank}"] = (lo, hi)
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_sharding_and_gather():
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+    assert ret["win0"] == (0, 4) and ret["win1"] == (4, 7)
+    assert ret["gathered"] == [2.0 * (i + 3) for i in range(7)]
+    assert ret["max0"] == 11.0 and ret["max1"] == 11.0
+
+
+def test_shard_items_covers_everything():
+    from lvd_b200 import parallel
+    for n in (0, 1, 7, 32, 500):
+        for w in (1, 2, 4, 8):
+            wins = [parallel.shard_items(n, r, w) for r in range(w)]
+            assert wins[0][0] == 0 and wins[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(wins, wins[1:]))
+            assert max(h - l for l, h in wins) - min(h - l for l, h in wins) <= 1
