@@ -36,12 +36,31 @@ UNIT = "frames/s"
 FRAMES, LAT_H, LAT_W = 24, 40, 72
 GUIDANCE_SCALE = 9.0
 CFG_FWD_TFLOP = 42.79  # algorithmic work of one CFG forward at this shape
+GUID_ITER_TFLOP = 32.59  # minimal guidance iteration: forward prefix 15.92 + dgrad 16.67
+# lvd_zeroscope runs guidance on the first 10 of 50 steps (max_index_step=10, generation/lvd.py:92-104): the timed
+# steps follow the same 1:4 pattern -- step i is guided (one guidance iteration, README.md:68 max_iter=1) iff i % 5 == 0
+GUIDED_EVERY = 5
+GUIDANCE_KEYS = [("down", 1, 0, 0), ("down", 2, 0, 0), ("down", 2, 1, 0), ("up", 1, 0, 0), ("up", 1, 1, 0),
+                 ("up", 2, 2, 0)]  # generation/lvd.py:66-73
+GUIDANCE_HP = dict(fg_top_p=0.25, bg_top_p=0.25, fg_weight=1.0, bg_weight=2.0)  # README.md:68
+GUIDANCE_LOSS_SCALE = 2.5
+
+
+def bear_layout(frames):
+    """The in-repo demo layout "A bear walks from the left to the right" (cache/cache_demo_v0.1_gpt-4-1106-preview.json):
+    one object sweeping x from 0 to 0.83 at y 0.5..0.695, interpolated to `frames` boxes; prompt token 2."""
+    boxes = []
+    for f in range(frames):
+        x0 = 0.83 * f / max(frames - 1, 1) * 0.8
+        boxes.append((x0, 0.5, x0 + 0.17, 0.695))
+    return [boxes], [[2]]
 
 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=6)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--unguided", action="store_true", help="time the unguided CFG step only")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="lvd_b200", choices=["lvd_b200", "reference"])
     ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying a CUDA graph")
@@ -101,11 +120,12 @@ class ClockSampler(threading.Thread):
 
 
 # ---------------------------------------------------------------------------------------------- CPU reference arm
-def cpu_reference_step(sample_frames, steps, warmup):
+def cpu_reference_step(sample_frames, steps, warmup, guided_every=GUIDED_EVERY):
     """The reference algorithm (oracle/ restatement, fp32, all host threads) on a bounded sample of the workload:
-    the CFG denoising step on `sample_frames` of the 24 frames, full-size UNet.  Returns (frames/s, seconds, cores)."""
+    the same step pattern (guided iff i % 5 == 0) on `sample_frames` of the 24 frames, full-size UNet.
+    Returns (frames/s, mean seconds/step, cores, seconds of a guided step, seconds of an unguided step)."""
     import torch
-    from oracle import scheduler_ref
+    from oracle import guidance_ref, scheduler_ref
     from oracle import unet3d_ref as R
     from oracle import weights
 
@@ -118,34 +138,54 @@ def cpu_reference_step(sample_frames, steps, warmup):
     ehs = torch.randn((2, 77, 1024), generator=g)
     sched = scheduler_ref.DPMSolverRef()
     sched.set_timesteps(50)
-    times = []
-    with torch.no_grad():
-        for it in range(warmup + steps):
-            t0 = time.perf_counter()
+    bboxes, positions = bear_layout(sample_frames)
+    t_g, t_u = [], []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        tt = int(sched.timesteps[min(it, 49)])
+        guided = guided_every and (it % guided_every == 0)
+        if guided:
+            lat, _, _, _ = guidance_ref.guidance_step(sd, cfg, lat, tt, ehs[1:], bboxes, positions,
+                                                      sched.alphas_cumprod[tt], guidance_attn_keys=GUIDANCE_KEYS,
+                                                      loss_scale=GUIDANCE_LOSS_SCALE, base_attn_dim=(LAT_H, LAT_W),
+                                                      **GUIDANCE_HP)
+        with torch.no_grad():
             x = torch.cat([lat, lat], 0)
-            eps = R.unet_forward(sd, cfg, x, int(sched.timesteps[min(it, 49)]), ehs)
+            eps = R.unet_forward(sd, cfg, x, tt, ehs)
             e = scheduler_ref.cfg_combine(eps[:1], eps[1:], GUIDANCE_SCALE)
             lat = sched.step(e, lat)
-            dt = time.perf_counter() - t0
-            if it >= warmup:
-                times.append(dt)
-    sec = sum(times) / len(times)
-    return sample_frames / sec, sec, cores
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            (t_g if guided else t_u).append(dt)
+    sec_g = sum(t_g) / len(t_g) if t_g else None
+    sec_u = sum(t_u) / len(t_u) if t_u else None
+    sec = (sum(t_g) + sum(t_u)) / (len(t_g) + len(t_u))
+    return sample_frames / sec, sec, cores, sec_g, sec_u
+
+
+def _workload(unguided):
+    if unguided:
+        return "lvd_zeroscope 1 prompt/GPU, 24 frames 576x320 (72x40 latent), unguided CFG denoising step"
+    return ("lvd_zeroscope 1 prompt/GPU, 24 frames 576x320 (72x40 latent), 50-step schedule pattern: step i runs one "
+            "backward-guidance iteration (6 guided cross-attention keys, demo 'bear' layout) iff i % 5 == 0 "
+            "(= 10 guided of 50), then the CFG UNet forward (B=2) + CFG combine + DPM-Solver++ update")
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    fps, sec, cores = cpu_reference_step(args.cpu_sample_frames, max(1, args.steps), max(0, min(args.warmup, 1)))
-    sample = (f"CFG denoising step (B=2 UNet forward + CFG + DPM-Solver++) on {args.cpu_sample_frames} of 24 frames, "
-              f"72x40 latent, full 1.41B-param UNet, fp32, oracle port of the reference")
+    ge = 0 if args.unguided else GUIDED_EVERY
+    fps, sec, cores, sec_g, sec_u = cpu_reference_step(args.cpu_sample_frames, max(1, args.steps),
+                                                       max(0, min(args.warmup, 1)), ge)
+    sample = (f"same step pattern on {args.cpu_sample_frames} of 24 frames (72x40 latent, full 1.41B-param UNet), fp32, "
+              f"oracle port of the reference incl. autograd guidance; guided step {sec_g and round(sec_g, 1)} s, "
+              f"unguided step {sec_u and round(sec_u, 1)} s")
     line = {
         "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "lvd_zeroscope 1 prompt, 24 frames 576x320 (72x40 latent), unguided CFG denoising step",
-                   "sample": sample},
+        "config": {"workload": _workload(args.unguided), "sample": sample},
         "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -162,6 +202,7 @@ def run_gpu(args):
     ge.build()
     from lvd_b200 import _lib, ops, synthetic
     from lvd_b200.engine import UNetEngine
+    from lvd_b200.guidance_engine import GRAD_SCALE, GuidanceGraph
     from lvd_b200.scheduler import DPMSolverMultistepScheduler
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -199,13 +240,31 @@ def run_gpu(args):
     def forward_eager():
         state["out"] = eng.forward(static_x, static_t, static_ehs)
 
-    def denoise_step(i):
-        """One unguided denoising step on device-resident inputs; returns nothing (latents updated in place)."""
+    graph = GuidanceGraph(eng)
+    bboxes, positions = bear_layout(FRAMES)
+    guided_every = 0 if args.unguided else GUIDED_EVERY
+    cond = static_ehs[1:2]
+    loss_host = torch.zeros((), dtype=torch.float32).pin_memory()
+
+    def guidance_iteration(i):
+        """One iteration of latent_backward_guidance's loop (models/pipelines.py:65-137) on the native pass."""
         nonlocal latents
+        tt = int(sched.timesteps[i % 50])
+        loss, grad = graph.run(latents, tt, cond, bboxes, positions, GUIDANCE_KEYS, loss_scale=GUIDANCE_LOSS_SCALE,
+                               base_attn_dim=(LAT_H, LAT_W), **GUIDANCE_HP)
+        scale = (1.0 - float(sched.alphas_cumprod[tt])) ** 0.5
+        latents, _ = ops.latent_update(latents, grad, scale, 1.0 / GRAD_SCALE)
+        loss_host.copy_(loss, non_blocking=True)  # the 4-byte D2H the reference's while-condition needs
+
+    def denoise_step(i):
+        """One denoising-loop iteration on device-resident inputs (latents updated in place)."""
+        nonlocal latents
+        if guided_every and i % guided_every == 0:
+            guidance_iteration(i)
         static_x[0].copy_(latents[0])
         static_x[1].copy_(latents[0])
         static_t.fill_(float(sched.timesteps[i % 50]))
-        if state["graph"] is not None:
+        if state["graph"] is not None and ops.PROF is None:
             state["graph"].replay()
         else:
             forward_eager()
@@ -275,6 +334,20 @@ def run_gpu(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, ms_e2e = float(t[0]), float(t[1])
 
+    # ---------------- separate timings of the two step kinds (device events, resident inputs)
+    def time_steps(idx):
+        torch.cuda.synchronize()
+        a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in idx:
+            denoise_step(i)
+        b_.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b_) / len(idx)
+
+    ms_unguided = time_steps([1, 2, 3])
+    ms_guided = time_steps([0, 5]) if guided_every else None
+
     # ---------------- instrumented step: per-kernel-family durations (CUDA events around every launch)
     ops.PROF = []
     l0 = _lib.lib().lvd_launch_count()
@@ -282,16 +355,26 @@ def run_gpu(args):
     forward_eager()
     torch.cuda.synchronize()
     launches_per_forward = _lib.lib().lvd_launch_count() - l0
+    n_fwd_records = len(ops.PROF)
+    launches_per_guidance = 0
+    if guided_every:
+        l1 = _lib.lib().lvd_launch_count()
+        guidance_iteration(0)
+        torch.cuda.synchronize()
+        launches_per_guidance = _lib.lib().lvd_launch_count() - l1
     fam = {}
-    for name, fl, nb, s, e in ops.PROF:
-        d = fam.setdefault(name, {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "launches": 0})
+    fam_guid = {}
+    for k_, (name, fl, nb, s, e) in enumerate(ops.PROF):
+        d = (fam if k_ < n_fwd_records else fam_guid).setdefault(name, {"ms": 0.0, "flops": 0.0, "bytes": 0.0,
+                                                                        "launches": 0})
         d["ms"] += s.elapsed_time(e)
         d["flops"] += fl
         d["bytes"] += nb
         d["launches"] += 1
     ops.PROF = None
     if use_graph:
-        launches = (launches_per_forward + 1) * args.steps
+        n_guided = sum(1 for i in range(args.steps) if guided_every and i % guided_every == 0)
+        launches = (launches_per_forward + 1) * args.steps + (launches_per_guidance + 1) * n_guided
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -299,14 +382,22 @@ def run_gpu(args):
         pass
     peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
     peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1.4 PFLOP/s sustained"
-    gm = fam.get("gemm_tc_kernel", {"ms": 1.0, "flops": 0.0, "launches": 1})
+    gm = dict(fam.get("gemm_tc_kernel", {"ms": 1.0, "flops": 0.0, "launches": 1}))
+    gg = fam_guid.get("gemm_tc_kernel")
+    if gg:  # one guided step = CFG forward + one guidance iteration: the dominant kernel's launches of both
+        share = 1.0 / GUIDED_EVERY
+        gm = {"ms": gm["ms"] + share * gg["ms"], "flops": gm["flops"] + share * gg["flops"],
+              "launches": gm["launches"] + share * gg["launches"]}
     achieved = gm["flops"] / (gm["ms"] * 1e-3) / 1e12
     roofline = {"bound": "tensor", "kernel": "gemm_tc_kernel", "achieved": achieved, "peak": peak_tf,
                 "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": None, "peak_source": peak_src,
                 "launches_per_step": gm["launches"], "ms_per_step": gm["ms"],
-                "share_of_instrumented_step": gm["ms"] / max(1e-9, sum(v["ms"] for v in fam.values()))}
+                "share_of_instrumented_step": gm["ms"] / max(1e-9, sum(v["ms"] for v in fam.values()) + (
+                    sum(v["ms"] for v in fam_guid.values()) / GUIDED_EVERY if fam_guid else 0.0)),
+                "note": "FLOPs and CUDA-event time summed over all gemm_tc_kernel launches of one CFG forward plus "
+                        "1/5 of one guidance iteration (the timed step mix), instrumented pass after the timed region"}
     if args.profile_json and rank == 0:
-        json.dump(fam, open(args.profile_json, "w"), indent=1)
+        json.dump({"cfg_forward": fam, "guidance_iteration": fam_guid}, open(args.profile_json, "w"), indent=1)
 
     if rank == 0:
         ms_step = ms / args.steps
@@ -316,26 +407,41 @@ def run_gpu(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f16", "data": "synthetic",
-            "config": {"workload": "lvd_zeroscope 1 prompt/GPU, 24 frames 576x320 (72x40 latent), unguided CFG "
-                                   "denoising step (B=2 UNet forward + CFG combine + DPM-Solver++ update)",
+            "config": {"workload": _workload(args.unguided),
                        "weights": "seeded random init of the Zeroscope UNet3D config (1411.2 M params), fp16",
                        "parallelism": f"replicas x{world} (independent prompts, no data-path collective)",
                        "l2": "inputs larger than L2 (2.8 GB weights + >20 GB activations per step vs 126 MB)",
-                       "cuda_graph": bool(use_graph), "algorithmic_tflop_per_step": CFG_FWD_TFLOP},
+                       "cuda_graph": "CFG forward replayed from a CUDA graph; guidance pass eager" if use_graph else False,
+                       "algorithmic_tflop_per_step": CFG_FWD_TFLOP + (GUID_ITER_TFLOP / GUIDED_EVERY if guided_every
+                                                                      else 0.0),
+                       "guidance": None if not guided_every else {
+                           "keys": GUIDANCE_KEYS, "layout": "demo bear, 1 object, token 2", "iterations_per_guided_step": 1,
+                           "loss_scale": GUIDANCE_LOSS_SCALE, **GUIDANCE_HP}},
+            "unguided_step": {"ms": ms_unguided, "frames_per_s": world * FRAMES / (ms_unguided * 1e-3)},
+            "guided_step": None if ms_guided is None else {"ms": ms_guided,
+                                                           "frames_per_s": world * FRAMES / (ms_guided * 1e-3)},
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": lat_host.numel() * 2 + ehs_host.numel() * 2,
                     "d2h_bytes_per_step": out_host.numel() * 2},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": roofline,
-            "step_tflops": CFG_FWD_TFLOP / (ms_step * 1e-3),
+            "step_tflops": (CFG_FWD_TFLOP + (GUID_ITER_TFLOP / GUIDED_EVERY if guided_every else 0.0)) / (ms_step * 1e-3),
             "kernel_families_ms": {k: round(v["ms"], 3) for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])},
+            "guidance_families_ms": {k: round(v["ms"], 3) for k, v in sorted(fam_guid.items(),
+                                                                            key=lambda kv: -kv[1]["ms"])},
         }
         if world == 1 and not args.no_cpu_baseline:
-            fps, sec, cores = cpu_reference_step(args.cpu_sample_frames, 1, 0)
+            # one guided + one unguided step on the CPU, combined with the schedule weights 1:4
+            _, _, cores, sec_g, sec_u = cpu_reference_step(args.cpu_sample_frames, 2, 0, 0 if args.unguided else 2)
+            if args.unguided:
+                sec = sec_u
+            else:
+                sec = (sec_g + (GUIDED_EVERY - 1) * sec_u) / GUIDED_EVERY
             line["cpu_baseline"] = {
-                "value": fps, "unit": UNIT, "cores": cores, "kind": "port",
-                "sample": f"same CFG denoising step on {args.cpu_sample_frames} of 24 frames (72x40 latent, full "
-                          f"UNet), fp32, oracle port of the reference, {sec:.1f} s"}
+                "value": args.cpu_sample_frames / sec, "unit": UNIT, "cores": cores, "kind": "port",
+                "sample": f"same step mix on {args.cpu_sample_frames} of 24 frames (72x40 latent, full UNet), fp32, "
+                          f"oracle port of the reference (autograd guidance): guided step "
+                          f"{sec_g and round(sec_g, 1)} s, unguided {sec_u and round(sec_u, 1)} s, weighted 1:4"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
