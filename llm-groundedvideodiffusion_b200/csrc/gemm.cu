@@ -20,10 +20,13 @@ std::atomic<long long> g_launches{0};
 constexpr int kAStageBytes = 128 * 128;  // 128 rows x 64 halves
 constexpr int kThreads = 576;  // 2 control warps + 16 epilogue warps
 constexpr int kSmemLimit = 232448;  // 227 KB
+constexpr int kSlabBytes = 128 * 64;  // epilogue staging slab: 128 rows x 32 halves
 
 struct GemmArgs {
   CUtensorMap map_a;
   CUtensorMap map_b;
+  CUtensorMap map_out;  // 32-column slabs of the output (64-byte swizzle), rows mapped like the A box
+  CUtensorMap map_res;  // same geometry over the residual
   long long out_row_stride[4];
   long long ld_rowvec, ld_res, ld_out;
   const __half* bias;
@@ -39,6 +42,7 @@ struct GemmArgs {
   int n_tiles_n, block_n, b_mn_major, act;
   int num_tiles, stages, a_bytes, b_bytes;
   int b_k_tap_stride, b_n_tap_stride;
+  int slab_bytes;  // rows of the box * 64
   float gamma;
   uint32_t idesc;
 };
@@ -84,11 +88,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   const uint32_t b_stage_bytes = static_cast<uint32_t>(g.block_n) * 128u;
   uint8_t* sA = smem;
   uint8_t* sB = smem + stages * kAStageBytes;
-  uint64_t* full = reinterpret_cast<uint64_t*>(sB + stages * b_stage_bytes);
+  uint8_t* sOut = sB + stages * b_stage_bytes;  // 2 output slabs [128 rows][32 cols] fp16, one per epilogue group
+  uint8_t* sRes = sOut + 2 * kSlabBytes;        // 2 residual slabs
+  uint64_t* full = reinterpret_cast<uint64_t*>(sRes + 2 * kSlabBytes);
   uint64_t* empty = full + stages;
   uint64_t* tfull = empty + stages;
   uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* res_full = tempty + 2;  // [2]
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(res_full + 2);
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < stages; ++i) {
@@ -99,11 +106,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     mbar_init(&tfull[1], 1);
     mbar_init(&tempty[0], 512);
     mbar_init(&tempty[1], 512);
+    mbar_init(&res_full[0], 1);
+    mbar_init(&res_full[1], 1);
     fence_barrier_init();
   }
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&g.map_a);
     tma_prefetch_desc(&g.map_b);
+    tma_prefetch_desc(&g.map_out);
   }
   if (warp == 1) {
     tmem_alloc(tmem_holder, 512);
@@ -182,10 +192,18 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       }
     }
   } else {
-    // 16 epilogue warps: four per TMEM lane quarter, interleaved over 16-column units, so that each SM sub-partition
-    // has four warps to hide the latency of the TMEM / residual loads behind the others' arithmetic.
+    // 16 epilogue warps in two groups of 8 (256 threads).  The tile's output is emitted as 32-column slabs: group 0
+    // takes the even slabs, group 1 the odd ones.  Per slab: [leader] wait until the group's staging buffer has been
+    // drained by the previous TMA store and kick the residual slab's TMA load -> named barrier -> every thread reads
+    // its 16 accumulator columns from TMEM, applies the epilogue and writes two 16-byte chunks of its row into the
+    // swizzled staging slab -> named barrier -> [leader] one TMA store of the slab.  Global traffic is therefore
+    // full-line bulk copies issued by the TMA engine (row mapping and edge clipping come from the tensor map), not
+    // 32 scattered 16-byte accesses per warp instruction.
     const int q = warp & 3;            // this warp may only touch TMEM lanes [32q, 32q+32)
-    const int csub = (warp - 2) >> 2;  // 0..3: which units of the tile this warp handles
+    const int wi = warp - 2;           // 0..15
+    const int grp = wi >> 3;           // 0 / 1
+    const int usub = (wi >> 2) & 1;    // which 16-column half of the slab
+    const bool leader = (wi & 7) == 0 && lane == 0;
     const int r = q * 32 + lane;
     int j[4];
     {
@@ -198,90 +216,109 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       t /= g.box[2];
       j[3] = t;  // >= box[3] when the box has fewer than 128 rows
     }
+    uint8_t* my_out = sOut + grp * kSlabBytes;
+    uint8_t* my_res = sRes + grp * kSlabBytes;
+    // 64-byte swizzle: physical = logical ^ (((logical >> 7) & 3) << 4), logical = r*64 + chunk*16
+    const uint32_t sw = static_cast<uint32_t>((r >> 1) & 3);
+    const uint32_t off0 = static_cast<uint32_t>(r * 64) + (((static_cast<uint32_t>(usub * 2)) ^ sw) << 4);
+    const uint32_t off1 = static_cast<uint32_t>(r * 64) + (((static_cast<uint32_t>(usub * 2 + 1)) ^ sw) << 4);
     int acc = 0;
-    uint32_t acc_phase = 0;
+    uint32_t acc_phase = 0, res_phase = 0;
     const bool geglu = (g.act == 2);
-    const int units = geglu ? 4 : g.block_n / 16;
+    const int nslabs = geglu ? 2 : g.block_n / 32;
+    const int bar_id = 1 + grp;
     for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
       const int nt = tile % g.n_tiles_n;
       int c[4];
       tile_coords(g, tile / g.n_tiles_n, c);
       bool valid = j[3] < g.box[3];
-      long long orow = 0, rvrow = 0;
+      long long rvrow = 0;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int x = c[i] + j[i];
         valid = valid && (x < g.out_dims[i]);
-        orow += static_cast<long long>(x) * g.out_row_stride[i];
         rvrow += static_cast<long long>(x) * g.rv_stride[i];
       }
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + static_cast<uint32_t>(acc) * 256u + (static_cast<uint32_t>(q * 32) << 16);
-      for (int u = csub; u < units; u += 4) {
-        // output columns [ocol, ocol+16); issue the residual loads first so they overlap the TMEM read
-        const int ocol = geglu ? nt * 64 + u * 16 : nt * g.block_n + u * 16;
-        float res[2][8];
-        if (g.residual && valid) {
-          load8(g.residual + orow * g.ld_res + ocol, res[0]);
-          load8(g.residual + orow * g.ld_res + ocol + 8, res[1]);
-        }
-        uint32_t rv[16], rg[16];
-        tmem_ld16(taddr + u * 16, rv);
-        if (geglu) tmem_ld16(taddr + 64 + u * 16, rg);
-        tmem_ld_wait();
-        if (valid) {
-          float v[2][8];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i >> 3][i & 7] = __uint_as_float(rv[i]);
-          if (geglu) {
-            // value * gelu(gate); biases of the interleaved weight: value at tcol, gate at tcol + 64
-            const int tcol = nt * 128 + u * 16;
-            float bv[2][8], bg[2][8];
-            if (g.bias) {
-              load8(g.bias + tcol, bv[0]);
-              load8(g.bias + tcol + 8, bv[1]);
-              load8(g.bias + tcol + 64, bg[0]);
-              load8(g.bias + tcol + 72, bg[1]);
-            } else {
-#pragma unroll
-              for (int i = 0; i < 16; ++i) bv[i >> 3][i & 7] = bg[i >> 3][i & 7] = 0.f;
-            }
-#pragma unroll
-            for (int i = 0; i < 16; ++i)
-              v[i >> 3][i & 7] = round_h(v[i >> 3][i & 7] + bv[i >> 3][i & 7]) *
-                               round_h(gelu_erf_f(__uint_as_float(rg[i]) + bg[i >> 3][i & 7]));
-          } else {
-            if (g.bias) {
-              float b[2][8];
-              load8(g.bias + ocol, b[0]);
-              load8(g.bias + ocol + 8, b[1]);
-#pragma unroll
-              for (int i = 0; i < 16; ++i) v[i >> 3][i & 7] += b[i >> 3][i & 7];
-            }
-            if (g.act == 1) {
-#pragma unroll
-              for (int i = 0; i < 16; ++i) v[i >> 3][i & 7] = silu_f(round_h(v[i >> 3][i & 7]));
-            }
-          }
-          if (g.rowvec) {
-            float t[2][8];
-            load8(g.rowvec + rvrow * g.ld_rowvec + ocol, t[0]);
-            load8(g.rowvec + rvrow * g.ld_rowvec + ocol + 8, t[1]);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i >> 3][i & 7] = round_h(v[i >> 3][i & 7]) + t[i >> 3][i & 7];
-          }
-          if (g.gamma != 1.0f) {
-            const float gm = g.gamma;
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i >> 3][i & 7] = round_h(v[i >> 3][i & 7]) * gm;
-          }
+      for (int sl = grp; sl < nslabs; sl += 2) {
+        const int gcol = (geglu ? nt * 64 : nt * g.block_n) + sl * 32;  // first global output column of the slab
+        if (leader) {
+          bulk_wait_read_all();
           if (g.residual) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i >> 3][i & 7] = round_h(v[i >> 3][i & 7]) + res[i >> 3][i & 7];
+            mbar_arrive_expect_tx(&res_full[grp], static_cast<uint32_t>(g.slab_bytes));
+            tma_load_5d(my_res, &g.map_res, &res_full[grp], gcol, c[0], c[1], c[2], c[3]);
           }
-          store8(g.out + orow * g.ld_out + ocol, v[0]);
-          store8(g.out + orow * g.ld_out + ocol + 8, v[1]);
+        }
+        named_bar_sync(bar_id, 256);
+        const int ucol = sl * 32 + usub * 16;  // tile-relative column of this thread's 16-column unit
+        const int ocol = gcol + usub * 16;
+        uint32_t rv[16], rg[16];
+        tmem_ld16(taddr + ucol, rv);
+        if (geglu) tmem_ld16(taddr + 64 + ucol, rg);
+        tmem_ld_wait();
+        float v[2][8];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i >> 3][i & 7] = __uint_as_float(rv[i]);
+        if (geglu) {
+          // value * gelu(gate); biases of the interleaved weight: value at tcol, gate at tcol + 64
+          const int tcol = nt * 128 + ucol;
+          float bv[2][8], bg[2][8];
+          if (g.bias) {
+            load8(g.bias + tcol, bv[0]);
+            load8(g.bias + tcol + 8, bv[1]);
+            load8(g.bias + tcol + 64, bg[0]);
+            load8(g.bias + tcol + 72, bg[1]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) bv[i >> 3][i & 7] = bg[i >> 3][i & 7] = 0.f;
+          }
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            v[i >> 3][i & 7] = round_h(v[i >> 3][i & 7] + bv[i >> 3][i & 7]) *
+                               round_h(gelu_erf_f(__uint_as_float(rg[i]) + bg[i >> 3][i & 7]));
+        } else {
+          if (g.bias) {
+            float b[2][8];
+            load8(g.bias + ocol, b[0]);
+            load8(g.bias + ocol + 8, b[1]);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i >> 3][i & 7] += b[i >> 3][i & 7];
+          }
+          if (g.act == 1) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i >> 3][i & 7] = silu_f(round_h(v[i >> 3][i & 7]));
+          }
+        }
+        if (g.rowvec && valid) {
+          float t[2][8];
+          load8(g.rowvec + rvrow * g.ld_rowvec + ocol, t[0]);
+          load8(g.rowvec + rvrow * g.ld_rowvec + ocol + 8, t[1]);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i >> 3][i & 7] = round_h(v[i >> 3][i & 7]) + t[i >> 3][i & 7];
+        }
+        if (g.gamma != 1.0f) {
+          const float gm = g.gamma;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i >> 3][i & 7] = round_h(v[i >> 3][i & 7]) * gm;
+        }
+        if (g.residual) {
+          mbar_wait(&res_full[grp], res_phase);
+          res_phase ^= 1u;
+          float t[2][8];
+          load8(reinterpret_cast<const __half*>(my_res + off0), t[0]);
+          load8(reinterpret_cast<const __half*>(my_res + off1), t[1]);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i >> 3][i & 7] = round_h(v[i >> 3][i & 7]) + t[i >> 3][i & 7];
+        }
+        store8(reinterpret_cast<__half*>(my_out + off0), v[0]);
+        store8(reinterpret_cast<__half*>(my_out + off1), v[1]);
+        fence_proxy_async_smem();
+        named_bar_sync(bar_id, 256);
+        if (leader) {
+          tma_store_5d(&g.map_out, my_out, gcol, c[0], c[1], c[2], c[3]);
+          bulk_commit_group();
         }
       }
       tc_fence_before();
@@ -289,6 +326,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
     }
+    if (leader) bulk_wait_all();  // the staging slabs must outlive the last store's reads
   }
   tc_fence_before();
   __syncthreads();
@@ -359,8 +397,30 @@ static int launch_gemm(const lvd_gemm_desc* d, cudaStream_t stream) {
   g.num_tiles = static_cast<int>(m_tiles * g.n_tiles_n);
   g.a_bytes = static_cast<int>(rows) * 128;
   g.b_bytes = d->block_n * 128;
+  g.slab_bytes = static_cast<int>(rows) * 64;
+  {
+    // output / residual as rank-5 tensors whose axes 1..4 are the tile axes: stride_i = out_row_stride[i] * ld
+    const int n_out = d->act == 2 ? d->n / 2 : d->n;
+    int64_t od[5] = {n_out, d->out_dims[0], d->out_dims[1], d->out_dims[2], d->out_dims[3]};
+    int ob[5] = {32, d->a_box[1], d->a_box[2], d->a_box[3], d->a_box[4]};
+    int64_t os[5], rs[5];
+    os[0] = rs[0] = 1;
+    for (int i = 0; i < 4; ++i) {
+      LVD_REQUIRE(d->out_row_stride[i] > 0 || d->out_dims[i] == 1, "lvd_gemm: out_row_stride[%d] == 0 on an axis of extent %d",
+                  i, d->out_dims[i]);
+      const int64_t st = d->out_row_stride[i] > 0 ? d->out_row_stride[i] : 1;
+      os[i + 1] = st * d->ld_out;
+      rs[i + 1] = st * d->ld_res;
+    }
+    rc = encode_tmap_f16_sw64(&g.map_out, d->out, 5, od, os, ob);
+    if (rc) return rc;
+    if (d->residual) {
+      rc = encode_tmap_f16_sw64(&g.map_res, d->residual, 5, od, rs, ob);
+      if (rc) return rc;
+    }
+  }
   const int stage_bytes = kAStageBytes + g.b_bytes;
-  int stages = (kSmemLimit - 1024 - 256) / stage_bytes;
+  int stages = (kSmemLimit - 1024 - 256 - 4 * kSlabBytes) / stage_bytes;
   if (stages > 8) stages = 8;
   g.stages = stages;
   g.bias = static_cast<const __half*>(d->bias);
@@ -373,7 +433,7 @@ static int launch_gemm(const lvd_gemm_desc* d, cudaStream_t stream) {
   g.gamma = d->gamma;
   g.idesc = make_idesc_f16(128, static_cast<uint32_t>(d->block_n), 0, d->b_mn_major ? 1u : 0u);
 
-  const int smem_bytes = 1024 + stages * stage_bytes + 256;
+  const int smem_bytes = 1024 + stages * stage_bytes + 4 * kSlabBytes + 256;
   static bool attr_set = false;
   if (!attr_set) {
     LVD_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));

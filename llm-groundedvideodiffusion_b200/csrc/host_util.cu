@@ -42,14 +42,26 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
+static int encode_tmap_impl(CUtensorMap* out, const void* base, int rank, const int64_t* dims, const int64_t* strides,
+                            const int* box, int box0, CUtensorMapSwizzle swz);
+
 int encode_tmap_f16_sw128(CUtensorMap* out, const void* base, int rank, const int64_t* dims, const int64_t* strides,
                           const int* box) {
+  return encode_tmap_impl(out, base, rank, dims, strides, box, 64, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+int encode_tmap_f16_sw64(CUtensorMap* out, const void* base, int rank, const int64_t* dims, const int64_t* strides,
+                         const int* box) {
+  return encode_tmap_impl(out, base, rank, dims, strides, box, 32, CU_TENSOR_MAP_SWIZZLE_64B);
+}
+
+static int encode_tmap_impl(CUtensorMap* out, const void* base, int rank, const int64_t* dims, const int64_t* strides,
+                            const int* box, int box0, CUtensorMapSwizzle swz) {
   EncodeTiledFn enc = get_encode();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
     return LVD_ERR_CUDA;
   }
-  if (rank < 2 || rank > 5 || strides[0] != 1 || box[0] != 64) {
+  if (rank < 2 || rank > 5 || strides[0] != 1 || box[0] != box0) {
     set_error("encode_tmap: bad rank/stride0/box0 (%d, %lld, %d)", rank, (long long)strides[0], box[0]);
     return LVD_ERR_INVALID;
   }
@@ -76,7 +88,7 @@ int encode_tmap_f16_sw128(CUtensorMap* out, const void* base, int rank, const in
     return LVD_ERR_INVALID;
   }
   CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d dims %lld,%lld,.. box %d,%d,..)", (int)r, rank,

@@ -31,6 +31,9 @@ int cuda_fail(cudaError_t e, const char* what);
 // (strides[0] must be 1); box[0] must be 64 (=128 bytes). Out-of-bounds elements read as zero.
 int encode_tmap_f16_sw128(CUtensorMap* out, const void* base, int rank, const int64_t* dims, const int64_t* strides,
                           const int* box);
+// Same with 64-byte swizzle and box[0] == 32 (64-byte rows): the output / residual slabs of the GEMM epilogue.
+int encode_tmap_f16_sw64(CUtensorMap* out, const void* base, int rank, const int64_t* dims, const int64_t* strides,
+                         const int* box);
 
 int num_sms();
 

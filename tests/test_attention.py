@@ -104,3 +104,43 @@ def test_self_attention_lse(cuda):
     q, k = (qkv[:, i * c:(i + 1) * c].reshape(z, s, heads, 64).transpose(1, 2).float() for i in range(2))
     ref = torch.logsumexp(q @ k.transpose(-1, -2) * 0.125, dim=-1) / 0.6931471805599453
     assert (lse - ref).abs().max().item() < 2e-3
+
+
+def test_attn_processor_mirror_matches_reference_semantics(cuda):
+    """AttnProcessor.__call__ boundary: fused path, materialising path with save_attn_to_dict / return probs."""
+    from lvd_b200.models.attention_processor import Attention
+    torch.manual_seed(0)
+    b, s, c, heads, ctx = 4, 90, 128, 2, 128
+    sd = {"to_q.weight": torch.randn(c, c) * c ** -0.5, "to_k.weight": torch.randn(c, ctx) * ctx ** -0.5,
+          "to_v.weight": torch.randn(c, ctx) * ctx ** -0.5, "to_out.0.weight": torch.randn(c, c) * c ** -0.5,
+          "to_out.0.bias": torch.randn(c) * 0.1}
+    attn = Attention(query_dim=c, cross_attention_dim=ctx, heads=heads, dim_head=64).load_state_dict(sd)
+    x = _rand((b, s, c), cuda, seed=7)
+    e = _rand((b, 77, ctx), cuda, seed=8)
+    w = {k: v.half().float().to(cuda) for k, v in sd.items()}
+
+    def ref(xq, ctxt):
+        q = xq.float() @ w["to_q.weight"].t()
+        k = ctxt.float() @ w["to_k.weight"].t()
+        v = ctxt.float() @ w["to_v.weight"].t()
+        o, p = _ref_attn(q, k, v, heads)
+        return o @ w["to_out.0.weight"].t() + w["to_out.0.bias"], p
+
+    saved = {}
+    out = attn(x, encoder_hidden_states=e, attn_key=["down", 1, 0, 0], save_attn_to_dict=saved,
+               save_keys=[("down", 1, 0, 0)])
+    o_ref, p_ref = ref(x, e)
+    assert rel_err(out, o_ref) < 4e-3
+    assert saved[("down", 1, 0, 0)].shape == (b, heads, s, 77)
+    assert rel_err(saved[("down", 1, 0, 0)], p_ref) < 4e-3
+    out2 = attn(x, encoder_hidden_states=e, attn_key=["down", 1, 1, 0], save_attn_to_dict={}, save_keys=[])
+    assert rel_err(out2, o_ref) < 4e-3                     # unsaved key -> fused path, same numbers
+    out3, p3 = attn(x, encoder_hidden_states=e, return_attntion_probs=True, return_token_ca_only=5,
+                    return_cond_ca_only=True)
+    assert p3.shape == (b // 2, heads, s, 1) and rel_err(p3[..., 0], p_ref[b // 2:, ..., 5]) < 4e-3
+    self_attn = Attention(query_dim=c, heads=heads, dim_head=64).load_state_dict(
+        {**sd, "to_k.weight": sd["to_q.weight"] * 0.5, "to_v.weight": sd["to_out.0.weight"]})
+    ws = {**w, "to_k.weight": w["to_q.weight"] * 0.5, "to_v.weight": w["to_out.0.weight"]}
+    q = x.float() @ ws["to_q.weight"].t()
+    o, _ = _ref_attn(q, x.float() @ ws["to_k.weight"].t(), x.float() @ ws["to_v.weight"].t(), heads)
+    assert rel_err(self_attn(x), o @ ws["to_out.0.weight"].t() + ws["to_out.0.bias"]) < 4e-3
