@@ -120,6 +120,31 @@ class ClockSampler(threading.Thread):
 
 
 # ---------------------------------------------------------------------------------------------- CPU reference arm
+def pick_cpu_threads():
+    """All the host threads the reference can USE: PyTorch's CPU kernels stop scaling (and regress) well before 128
+    threads on the small per-layer problems of the bounded sample, so probe a conv + matmul at a few thread counts
+    (<2 s) and keep the fastest; the count used is reported as `cores`."""
+    import torch
+    n = os.cpu_count() or 1
+    cands = sorted({c for c in (8, 16, 32, 64, n) if c <= n})
+    x = torch.randn(2, 320, 40, 72)
+    w = torch.randn(320, 320, 3, 3)
+    a = torch.randn(5760, 320)
+    b = torch.randn(320, 1280)
+    best, best_t = cands[0], float("inf")
+    for c in cands:
+        torch.set_num_threads(c)
+        torch.nn.functional.conv2d(x, w, padding=1)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            torch.nn.functional.conv2d(x, w, padding=1)
+            a @ b
+        dt = time.perf_counter() - t0
+        if dt < best_t:
+            best, best_t = c, dt
+    return best
+
+
 def cpu_reference_step(sample_frames, steps, warmup, guided_every=GUIDED_EVERY):
     """The reference algorithm (oracle/ restatement, fp32, all host threads) on a bounded sample of the workload:
     the same step pattern (guided iff i % 5 == 0) on `sample_frames` of the 24 frames, full-size UNet.
@@ -129,7 +154,7 @@ def cpu_reference_step(sample_frames, steps, warmup, guided_every=GUIDED_EVERY):
     from oracle import unet3d_ref as R
     from oracle import weights
 
-    cores = os.cpu_count() or 1
+    cores = pick_cpu_threads()
     torch.set_num_threads(cores)
     cfg = weights.make_cfg("zeroscope")
     sd = weights.random_state_dict(cfg, seed=0)

@@ -132,6 +132,7 @@ int lvd_attention(const lvd_attn_desc* d, void* stream);
  * ---------------------------------------------------------------------------------------------------------- */
 int lvd_groupnorm(const void* x, int64_t ld_x, void* y, int64_t ld_y, int32_t samples, int64_t rows_per_sample,
                   int32_t channels, int32_t groups, const void* gamma, const void* beta, float eps, int32_t silu,
+                  void* stats_out /* optional fp32 [samples, groups, 2] = {mean, rstd}, kept for lvd_groupnorm_bwd */,
                   void* workspace, int64_t workspace_bytes, void* stream);
 int lvd_layernorm(const void* x, int64_t ld_x, void* y, int64_t ld_y, int64_t rows, int32_t channels,
                   const void* gamma, const void* beta, float eps, void* stream);
@@ -221,8 +222,9 @@ int lvd_gligen_prep(const void* boxes, const void* masks, const void* positive_e
  * ---------------------------------------------------------------------------------------------------------- */
 int lvd_groupnorm_bwd(const void* x, int64_t ld_x, const void* dz, int64_t ld_dz, void* dx, int64_t ld_dx,
                       int32_t samples, int64_t rows_per_sample, int32_t channels, int32_t groups, const void* gamma,
-                      const void* beta, float eps, int32_t silu, int32_t accumulate, void* workspace,
-                      int64_t workspace_bytes, void* stream);
+                      const void* beta, float eps, int32_t silu, int32_t accumulate,
+                      const void* fwd_stats /* optional: stats_out of the forward launch (skips the recomputation) */,
+                      void* workspace, int64_t workspace_bytes, void* stream);
 int lvd_layernorm_bwd(const void* x, int64_t ld_x, const void* dy, int64_t ld_dy, void* dx, int64_t ld_dx, int64_t rows,
                       int32_t channels, const void* gamma, float eps, int32_t accumulate, void* stream);
 int lvd_geglu(const void* pre, int64_t ld_pre, void* out, int64_t ld_out, int64_t rows, int32_t n_out, void* stream);
@@ -252,11 +254,14 @@ int lvd_attn_rowdot(const void* o, int64_t ld_o, const void* d_o, int64_t ld_do,
 int lvd_self_attn_bwd(const void* qkv, int64_t ld_qkv, int64_t width_qkv, int32_t q_col0, int32_t k_col0,
                       int32_t v_col0, const void* d_o, int64_t ld_do, const void* lse, const void* dvec, void* d_qkv,
                       int64_t ld_dqkv, int64_t s, int32_t heads, int32_t nz, float scale, void* stream);
-int lvd_temporal_attn_bwd(const void* qkv, int64_t ld_qkv, int32_t q_col0, int32_t k_col0, int32_t v_col0,
-                          const void* d_o, int64_t ld_do, void* d_qkv, int64_t ld_dqkv, int64_t n_seq, int32_t heads,
-                          int32_t frames, float scale, void* stream);
-int lvd_cross_attn_bwd(const void* q, int64_t ld_q, const void* kv, int64_t ld_kv, int32_t k_col0, int32_t v_col0,
-                       const void* d_o, int64_t ld_do, const void* dp_tok, const int32_t* slot_col_host,
+/* width_* = logical column count of the buffer (TMA bounds); > 0 selects the tcgen05 single-unit kernel
+ * (attn_bwd_small_kernel: probabilities recomputed exactly in-kernel), 0 the scalar fallback for odd frame counts. */
+int lvd_temporal_attn_bwd(const void* qkv, int64_t ld_qkv, int64_t width_qkv, int32_t q_col0, int32_t k_col0,
+                          int32_t v_col0, const void* d_o, int64_t ld_do, void* d_qkv, int64_t ld_dqkv, int64_t n_seq,
+                          int32_t heads, int32_t frames, float scale, void* stream);
+int lvd_cross_attn_bwd(const void* q, int64_t ld_q, int64_t width_q, const void* kv, int64_t ld_kv, int64_t width_kv,
+                       int32_t k_col0, int32_t v_col0, const void* d_o, int64_t ld_do, const void* dp_tok,
+                       const int32_t* slot_col_host,
                        int32_t n_slots, void* dq, int64_t ld_dq, int64_t s_q, int32_t s_k, int32_t heads, int32_t nz,
                        int32_t kv_z_div, float scale, void* stream);
 

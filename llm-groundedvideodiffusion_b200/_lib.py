@@ -124,7 +124,7 @@ def _declare(l):
     vp, i32, i64, f32 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_float
     l.lvd_gemm.argtypes = [ctypes.POINTER(GemmDesc), vp]
     l.lvd_attention.argtypes = [ctypes.POINTER(AttnDesc), vp]
-    l.lvd_groupnorm.argtypes = [vp, i64, vp, i64, i32, i64, i32, i32, vp, vp, f32, i32, vp, i64, vp]
+    l.lvd_groupnorm.argtypes = [vp, i64, vp, i64, i32, i64, i32, i32, vp, vp, f32, i32, vp, vp, i64, vp]
     l.lvd_layernorm.argtypes = [vp, i64, vp, i64, i64, i32, vp, vp, f32, vp]
     l.lvd_conv_in.argtypes = [vp, vp, vp, vp, i64, i32, i32, i32, i32, i32, i32, vp]
     l.lvd_conv_out.argtypes = [vp, i64, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]
@@ -137,7 +137,8 @@ def _declare(l):
     l.lvd_box_energy.argtypes = [ctypes.POINTER(EnergyDesc), vp]
     l.lvd_copy_rows_seq.argtypes = [vp, i64, vp, i64, i64, i32, i32, i32, i32, i32, i32, vp]
     l.lvd_gligen_prep.argtypes = [vp, vp, vp, vp, vp, vp, i64, i32, vp]
-    l.lvd_groupnorm_bwd.argtypes = [vp, i64, vp, i64, vp, i64, i32, i64, i32, i32, vp, vp, f32, i32, i32, vp, i64, vp]
+    l.lvd_groupnorm_bwd.argtypes = [vp, i64, vp, i64, vp, i64, i32, i64, i32, i32, vp, vp, f32, i32, i32, vp, vp, i64,
+                                    vp]
     l.lvd_layernorm_bwd.argtypes = [vp, i64, vp, i64, vp, i64, i64, i32, vp, f32, i32, vp]
     l.lvd_geglu.argtypes = [vp, i64, vp, i64, i64, i32, vp]
     l.lvd_geglu_bwd.argtypes = [vp, i64, vp, i64, vp, i64, i64, i32, vp]
@@ -147,9 +148,9 @@ def _declare(l):
     l.lvd_latent_update.argtypes = [vp, vp, vp, vp, i64, f32, f32, vp]
     l.lvd_attn_rowdot.argtypes = [vp, i64, vp, i64, vp, i64, i32, vp]
     l.lvd_self_attn_bwd.argtypes = [vp, i64, i64, i32, i32, i32, vp, i64, vp, vp, vp, i64, i64, i32, i32, f32, vp]
-    l.lvd_temporal_attn_bwd.argtypes = [vp, i64, i32, i32, i32, vp, i64, vp, i64, i64, i32, i32, f32, vp]
-    l.lvd_cross_attn_bwd.argtypes = [vp, i64, vp, i64, i32, i32, vp, i64, vp, ctypes.POINTER(ctypes.c_int32), i32, vp,
-                                     i64, i64, i32, i32, i32, i32, f32, vp]
+    l.lvd_temporal_attn_bwd.argtypes = [vp, i64, i64, i32, i32, i32, vp, i64, vp, i64, i64, i32, i32, f32, vp]
+    l.lvd_cross_attn_bwd.argtypes = [vp, i64, i64, vp, i64, i64, i32, i32, vp, i64, vp, ctypes.POINTER(ctypes.c_int32),
+                                     i32, vp, i64, i64, i32, i32, i32, i32, f32, vp]
     for name in EXPORTS:
         fn = getattr(l, name)
         if name not in ("lvd_last_error", "lvd_launch_count"):

@@ -382,6 +382,237 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_dkdv_kernel(const __g
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------ single-unit adjoint
+// All keys of a query tile fit one 128-column unit, so the probabilities are recomputed exactly in-kernel (row max,
+// row sum) and D = sum_j P dP needs no forward output.  Two users:
+//   mode 1, temporal packed attention: the tile's 128 rows are bp sequences of F consecutive rows; query tile ==
+//           key tile; block-diagonal window mask; emits dQ, dK, dV.
+//   mode 0, cross-attention: keys/values are the text tokens of batch z / kv_z_div; emits dQ only and injects the
+//           box-energy gradient dE/dP on the object-token columns.
+struct AttnBwdSmallArgs {
+  CUtensorMap map_q;   // query-side buffer (q | and for mode 1 also k | v), box 64 x 128
+  CUtensorMap map_kv;  // key/value buffer
+  CUtensorMap map_do;
+  const __half* dp_tok;
+  __half* d_q;
+  long long ld_dq;
+  long long total_q_rows;  // mode 1: all packed rows; mode 0: s_q
+  int mode, q_col0, k_col0, v_col0, dq_col0, dk_col0, dv_col0;
+  int tile_rows;  // row stride between tiles (mode 1: bp*F, mode 0: 128)
+  int seq_len, s_q, s_k, heads, nz, kv_z_div, n_slots;
+  int slot_col[16];
+  int ncols16;
+  float scale, scale_log2;
+  uint32_t idesc_s, idesc_dq, idesc_dkv;
+};
+
+__global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_small_kernel(const __grid_constant__ AttnBwdSmallArgs g) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t* sQ = smem;
+  uint8_t* sDO = smem + kT;
+  uint8_t* sK = smem + 2 * kT;
+  uint8_t* sV = smem + 3 * kT;
+  uint8_t* sP = smem + 4 * kT;   // [query][key], 2 key blocks
+  uint8_t* sDS = smem + 6 * kT;  // [query][key], 2 key blocks
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 8 * kT);
+  uint64_t* in_full = bars + 0;
+  uint64_t* sdp_full = bars + 1;
+  uint64_t* pds_full = bars + 2;
+  uint64_t* acc_done = bars + 3;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 4);
+  const int h = blockIdx.x, qt = blockIdx.y, z = blockIdx.z;
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  {
+    uint4 zero = make_uint4(0, 0, 0, 0);  // P / dS must be zero outside the columns the threads write
+    for (int i = threadIdx.x; i < 4 * kT / 16; i += kBwdThreads) reinterpret_cast<uint4*>(sP)[i] = zero;
+    fence_proxy_async_smem();
+  }
+  if (threadIdx.x == 0) {
+    mbar_init(in_full, 1);
+    mbar_init(sdp_full, 1);
+    mbar_init(pds_full, 128);
+    mbar_init(acc_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_holder, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+  const uint32_t tm_s = tmem_base, tm_dp = tmem_base + 128, tm_dq = tmem_base + 256, tm_dk = tmem_base + 320,
+                 tm_dv = tmem_base + 384;
+  const bool temporal = g.mode == 1;
+  const long long q_row0 = temporal ? static_cast<long long>(qt) * g.tile_rows
+                                    : static_cast<long long>(z) * g.s_q + static_cast<long long>(qt) * 128;
+  const long long kv_row0 = temporal ? q_row0 : static_cast<long long>(z / g.kv_z_div) * g.s_k;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(in_full, 4 * kT);
+      tma_load_2d(sQ, &g.map_q, in_full, g.q_col0 + h * 64, static_cast<int>(q_row0));
+      tma_load_2d(sDO, &g.map_do, in_full, h * 64, static_cast<int>(q_row0));
+      tma_load_2d(sK, &g.map_kv, in_full, g.k_col0 + h * 64, static_cast<int>(kv_row0));
+      tma_load_2d(sV, &g.map_kv, in_full, g.v_col0 + h * 64, static_cast<int>(kv_row0));
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      mbar_wait(in_full, 0);
+      tc_fence_after();
+      const uint32_t q_addr = smem_u32(sQ), do_addr = smem_u32(sDO), k_addr = smem_u32(sK), v_addr = smem_u32(sV);
+      const uint32_t p_addr = smem_u32(sP), ds_addr = smem_u32(sDS);
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        umma_f16(tm_s, make_smem_desc_sw128(q_addr + k * 32, 16, 1024), make_smem_desc_sw128(k_addr + k * 32, 16, 1024),
+                 g.idesc_s, k != 0 ? 1u : 0u);
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        umma_f16(tm_dp, make_smem_desc_sw128(do_addr + k * 32, 16, 1024),
+                 make_smem_desc_sw128(v_addr + k * 32, 16, 1024), g.idesc_s, k != 0 ? 1u : 0u);
+      umma_commit(sdp_full);
+      mbar_wait(pds_full, 0);
+      tc_fence_after();
+      for (int ks = 0; ks < g.ncols16 / 16; ++ks)  // dQ = dS K        (K tile as MN-major B)
+        umma_f16(tm_dq, make_smem_desc_sw128(ds_addr + (ks >> 2) * kT + (ks & 3) * 32, 16, 1024),
+                 make_smem_desc_sw128(k_addr + ks * 2048, 8192, 1024), g.idesc_dq, ks != 0 ? 1u : 0u);
+      if (temporal) {
+        for (int ks = 0; ks < 8; ++ks) {  // dV = P^T dO, dK = dS^T Q   (P / dS tiles as MN-major A)
+          umma_f16(tm_dv, make_smem_desc_sw128(p_addr + ks * 2048, kT, 1024),
+                   make_smem_desc_sw128(do_addr + ks * 2048, 8192, 1024), g.idesc_dkv, ks != 0 ? 1u : 0u);
+          umma_f16(tm_dk, make_smem_desc_sw128(ds_addr + ks * 2048, kT, 1024),
+                   make_smem_desc_sw128(q_addr + ks * 2048, 8192, 1024), g.idesc_dkv, ks != 0 ? 1u : 0u);
+        }
+      }
+      umma_commit(acc_done);
+    }
+  } else {
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+    const long long qrow = q_row0 + r;  // global query row (mode 1: also this thread's key row)
+    const int qi = qt * 128 + r;        // mode 0: query index inside image z
+    const bool row_valid = temporal ? (r < g.tile_rows && qrow < g.total_q_rows) : (qi < g.s_q);
+    // columns this warp has to look at, in chunks of 8
+    int cbeg = 0, cend = g.ncols16, mystart = 0, myend = g.s_k;
+    if (temporal) {
+      const int F = g.seq_len;
+      cbeg = (q * 32) / F * F;
+      cend = ((q * 32 + 31) / F + 1) * F;
+      if (cend > 128) cend = 128;
+      mystart = (r / F) * F;
+      myend = mystart + F;
+      if (myend > g.tile_rows) myend = g.tile_rows;
+    }
+    const int nch = (cend - cbeg + 7) >> 3;
+    mbar_wait(sdp_full, 0);
+    tc_fence_after();
+    // energy gradient on this row's object-token columns (mode 0)
+    float tokg[16];
+#pragma unroll
+    for (int t = 0; t < 16; ++t)
+      tokg[t] = (t < g.n_slots && row_valid)
+                    ? __half2float(g.dp_tok[((static_cast<long long>(t) * g.nz + z) * g.heads + h) * g.s_q + qi])
+                    : 0.f;
+    float mx = -INFINITY;
+    for (int k = 0; k < nch; ++k) {
+      uint32_t rs[8];
+      tmem_ld8(tm_s + lane_off + cbeg + k * 8, rs);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int c = cbeg + k * 8 + i;
+        if (c >= mystart && c < myend) mx = fmaxf(mx, __uint_as_float(rs[i]));
+      }
+    }
+    mx *= g.scale_log2;
+    if (!(mx > -INFINITY)) mx = 0.f;
+    float l = 0.f, td = 0.f;
+    for (int k = 0; k < nch; ++k) {
+      uint32_t rs[8], rp[8];
+      tmem_ld8(tm_s + lane_off + cbeg + k * 8, rs);
+      tmem_ld8(tm_dp + lane_off + cbeg + k * 8, rp);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int c = cbeg + k * 8 + i;
+        if (c >= mystart && c < myend) {
+          const float e = fast_exp2(fmaf(__uint_as_float(rs[i]), g.scale_log2, -mx));
+          float dp = __uint_as_float(rp[i]);
+          for (int t = 0; t < g.n_slots; ++t)
+            if (g.slot_col[t] == c) dp += tokg[t];
+          l += e;
+          td += e * dp;
+        }
+      }
+    }
+    const float inv = row_valid ? 1.f / l : 0.f;
+    const float Dv = td * inv;
+    uint8_t* p_row = sP + r * 128;
+    uint8_t* ds_row = sDS + r * 128;
+    for (int k = 0; k < nch; ++k) {
+      uint32_t rs[8], rp[8];
+      tmem_ld8(tm_s + lane_off + cbeg + k * 8, rs);
+      tmem_ld8(tm_dp + lane_off + cbeg + k * 8, rp);
+      tmem_ld_wait();
+      float pv[8], dsv[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int c = cbeg + k * 8 + i;
+        float p = 0.f, ds = 0.f;
+        if (c >= mystart && c < myend) {
+          p = round_h(fast_exp2(fmaf(__uint_as_float(rs[i]), g.scale_log2, -mx)) * inv);
+          float dp = __uint_as_float(rp[i]);
+          for (int t = 0; t < g.n_slots; ++t)
+            if (g.slot_col[t] == c) dp += tokg[t];
+          ds = p * (dp - Dv);
+        }
+        pv[i] = p;
+        dsv[i] = ds;
+      }
+      if (temporal) store_chunk16(p_row, r, cbeg + k * 8, pv);
+      store_chunk16(ds_row, r, cbeg + k * 8, dsv);
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    mbar_arrive(pds_full);
+    mbar_wait(acc_done, 0);
+    tc_fence_after();
+    __half* dst = g.d_q + qrow * g.ld_dq + h * 64;
+    const int nparts = temporal ? 6 : 2;
+#pragma unroll 1
+    for (int part = 0; part < nparts; ++part) {  // 0,1: dQ halves; 2,3: dK halves; 4,5: dV halves
+      uint32_t rr[32];
+      const uint32_t base = part < 2 ? tm_dq : (part < 4 ? tm_dk : tm_dv);
+      tmem_ld32(base + lane_off + (part & 1) * 32, rr);
+      tmem_ld_wait();
+      if (row_valid) {
+        const float sc = part < 4 ? g.scale : 1.f;
+        __half* d = dst + (part < 2 ? g.dq_col0 : (part < 4 ? g.dk_col0 : g.dv_col0)) + (part & 1) * 32;
+#pragma unroll
+        for (int s8 = 0; s8 < 4; ++s8) {
+          uint4 v;
+          __half2* hh = reinterpret_cast<__half2*>(&v);
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            hh[i] = __floats2half2_rn(__uint_as_float(rr[s8 * 8 + 2 * i]) * sc, __uint_as_float(rr[s8 * 8 + 2 * i + 1]) * sc);
+          *reinterpret_cast<uint4*>(d + s8 * 8) = v;
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 }  // namespace lvd
 
 using namespace lvd;
@@ -442,3 +673,74 @@ extern "C" int lvd_self_attn_bwd(const void* qkv, int64_t ld_qkv, int64_t width_
   LVD_CHECK_CUDA(cudaGetLastError());
   return LVD_OK;
 }
+
+// tensor-core single-unit adjoints; declared in attention_bwd_small.cu's entry points
+namespace lvd {
+int launch_attn_bwd_small(int mode, const void* q, long long ld_q, long long q_width, long long q_rows, const void* kv,
+                          long long ld_kv, long long kv_width, long long kv_rows, const void* d_o, long long ld_do,
+                          long long do_width, const void* dp_tok, const int* slot_col, int n_slots, void* d_q,
+                          long long ld_dq, int q_col0, int k_col0, int v_col0, int dq_col0, int dk_col0, int dv_col0,
+                          int frames, long long s_q, int s_k, int heads, int nz, int kv_z_div, float scale,
+                          cudaStream_t st) {
+  AttnBwdSmallArgs g;
+  memset(&g, 0, sizeof(g));
+  int b[2] = {64, 128};
+  int64_t d1[2] = {q_width, q_rows}, s1[2] = {1, ld_q};
+  int rc = encode_tmap_f16_sw128(&g.map_q, q, 2, d1, s1, b);
+  if (rc) return rc;
+  int64_t d2[2] = {kv_width, kv_rows}, s2[2] = {1, ld_kv};
+  rc = encode_tmap_f16_sw128(&g.map_kv, kv, 2, d2, s2, b);
+  if (rc) return rc;
+  int64_t d3[2] = {do_width, q_rows}, s3[2] = {1, ld_do};
+  rc = encode_tmap_f16_sw128(&g.map_do, d_o, 2, d3, s3, b);
+  if (rc) return rc;
+  g.dp_tok = static_cast<const __half*>(dp_tok);
+  g.d_q = static_cast<__half*>(d_q);
+  g.ld_dq = ld_dq;
+  g.mode = mode;
+  g.q_col0 = q_col0;
+  g.k_col0 = k_col0;
+  g.v_col0 = v_col0;
+  g.dq_col0 = dq_col0;
+  g.dk_col0 = dk_col0;
+  g.dv_col0 = dv_col0;
+  g.heads = heads;
+  g.nz = nz;
+  g.kv_z_div = kv_z_div;
+  g.n_slots = n_slots;
+  for (int i = 0; i < n_slots; ++i) g.slot_col[i] = slot_col[i];
+  g.scale = scale;
+  g.scale_log2 = scale * 1.4426950408889634f;
+  dim3 grid;
+  if (mode == 1) {
+    const int bp = 128 / frames;
+    g.tile_rows = bp * frames;
+    g.seq_len = frames;
+    g.total_q_rows = q_rows;
+    g.s_q = 0;
+    g.s_k = g.tile_rows;
+    g.ncols16 = (g.tile_rows + 15) / 16 * 16;
+    grid = dim3(heads, static_cast<unsigned>((q_rows + g.tile_rows - 1) / g.tile_rows), 1);
+  } else {
+    g.tile_rows = 128;
+    g.s_q = static_cast<int>(s_q);
+    g.s_k = s_k;
+    g.total_q_rows = s_q;
+    g.ncols16 = (s_k + 15) / 16 * 16;
+    grid = dim3(heads, static_cast<unsigned>((s_q + 127) / 128), nz);
+  }
+  g.idesc_s = make_idesc_f16(128, static_cast<uint32_t>(g.ncols16), 0, 0);
+  g.idesc_dq = make_idesc_f16(128, 64, 0, 1);
+  g.idesc_dkv = make_idesc_f16(128, 64, 1, 1);
+  const int smem_b = 8 * kT + 128;
+  static bool attr = false;
+  if (!attr) {
+    LVD_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_b));
+    attr = true;
+  }
+  attn_bwd_small_kernel<<<grid, kBwdThreads, smem_b, st>>>(g);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  LVD_CHECK_CUDA(cudaGetLastError());
+  return LVD_OK;
+}
+}  // namespace lvd

@@ -269,14 +269,28 @@ __global__ void __launch_bounds__(kCbWarps * 32) cross_attn_bwd_kernel(const Cro
   }
 }
 
+int launch_attn_bwd_small(int mode, const void* q, long long ld_q, long long q_width, long long q_rows, const void* kv,
+                          long long ld_kv, long long kv_width, long long kv_rows, const void* d_o, long long ld_do,
+                          long long do_width, const void* dp_tok, const int* slot_col, int n_slots, void* d_q,
+                          long long ld_dq, int q_col0, int k_col0, int v_col0, int dq_col0, int dk_col0, int dv_col0,
+                          int frames, long long s_q, int s_k, int heads, int nz, int kv_z_div, float scale,
+                          cudaStream_t st);
+
 }  // namespace lvd
 
 using namespace lvd;
 
-extern "C" int lvd_temporal_attn_bwd(const void* qkv, int64_t ld_qkv, int32_t q_col0, int32_t k_col0, int32_t v_col0,
-                                     const void* d_o, int64_t ld_do, void* d_qkv, int64_t ld_dqkv, int64_t n_seq,
-                                     int32_t heads, int32_t frames, float scale, void* stream) {
+extern "C" int lvd_temporal_attn_bwd(const void* qkv, int64_t ld_qkv, int64_t width_qkv, int32_t q_col0, int32_t k_col0,
+                                     int32_t v_col0, const void* d_o, int64_t ld_do, void* d_qkv, int64_t ld_dqkv,
+                                     int64_t n_seq, int32_t heads, int32_t frames, float scale, void* stream) {
   LVD_REQUIRE(qkv && d_o && d_qkv, "lvd_temporal_attn_bwd: null pointer");
+  if (frames % 8 == 0 && frames >= 8 && frames <= 64 && width_qkv > 0) {
+    // tensor-core path: packed tiles of floor(128/frames) sequences (attn_bwd_small_kernel, mode 1)
+    return launch_attn_bwd_small(1, qkv, ld_qkv, width_qkv, n_seq * frames, qkv, ld_qkv, width_qkv, n_seq * frames, d_o,
+                                 ld_do, static_cast<long long>(heads) * 64, nullptr, nullptr, 0, d_qkv, ld_dqkv, q_col0,
+                                 k_col0, v_col0, q_col0, k_col0, v_col0, frames, 0, 0, heads, 1, 1, scale,
+                                 static_cast<cudaStream_t>(stream));
+  }
   LVD_REQUIRE(frames >= 1 && frames <= 32, "lvd_temporal_attn_bwd: frames=%d unsupported (<= 32)", frames);
   LVD_REQUIRE(ld_qkv % 8 == 0 && ld_do % 8 == 0 && ld_dqkv % 8 == 0 && q_col0 % 8 == 0 && k_col0 % 8 == 0 &&
                   v_col0 % 8 == 0,
@@ -297,13 +311,22 @@ extern "C" int lvd_temporal_attn_bwd(const void* qkv, int64_t ld_qkv, int32_t q_
   return LVD_OK;
 }
 
-extern "C" int lvd_cross_attn_bwd(const void* q, int64_t ld_q, const void* kv, int64_t ld_kv, int32_t k_col0,
-                                  int32_t v_col0, const void* d_o, int64_t ld_do, const void* dp_tok,
+extern "C" int lvd_cross_attn_bwd(const void* q, int64_t ld_q, int64_t width_q, const void* kv, int64_t ld_kv,
+                                  int64_t width_kv, int32_t k_col0, int32_t v_col0, const void* d_o, int64_t ld_do,
+                                  const void* dp_tok,
                                   const int32_t* slot_col_host, int32_t n_slots, void* dq, int64_t ld_dq, int64_t s_q,
                                   int32_t s_k, int32_t heads, int32_t nz, int32_t kv_z_div, float scale, void* stream) {
   LVD_REQUIRE(q && kv && d_o && dq, "lvd_cross_attn_bwd: null pointer");
   LVD_REQUIRE(s_k >= 1 && s_k <= 128 && n_slots >= 0 && n_slots <= 16 && (n_slots == 0 || (dp_tok && slot_col_host)),
               "lvd_cross_attn_bwd: s_k=%d n_slots=%d unsupported", s_k, n_slots);
+  if (width_q > 0 && width_kv > 0) {
+    // tensor-core path (attn_bwd_small_kernel, mode 0)
+    return launch_attn_bwd_small(0, q, ld_q, width_q, static_cast<long long>(nz) * s_q, kv, ld_kv, width_kv,
+                                 static_cast<long long>((nz + kv_z_div - 1) / kv_z_div) * s_k, d_o, ld_do,
+                                 static_cast<long long>(heads) * 64, dp_tok, slot_col_host, n_slots, dq, ld_dq, 0, k_col0,
+                                 v_col0, 0, 0, 0, 0, s_q, s_k, heads, nz, kv_z_div, scale,
+                                 static_cast<cudaStream_t>(stream));
+  }
   CrossBwdArgs g;
   g.q = static_cast<const __half*>(q);
   g.kv = static_cast<const __half*>(kv);

@@ -56,8 +56,8 @@ __device__ __forceinline__ void gn_finalize_fwd(const float* fwd_partial, int s,
   rstd = rsqrtf(var + eps);
 }
 __device__ __forceinline__ float silu_grad(float y) {
-  const float s = 1.f / (1.f + expf(-y));
-  return s * (1.f + y * (1.f - s));
+  const float s = __fdividef(1.f, 1.f + __expf(-y));
+  return s * fmaf(y, 1.f - s, 1.f);
 }
 
 __global__ void gn_bwd_stats_kernel(const __half* __restrict__ x, long long ld_x, const __half* __restrict__ dz,
@@ -96,7 +96,28 @@ __global__ void gn_bwd_stats_kernel(const __half* __restrict__ x, long long ld_x
     }
     const __half* xb = x + (s * rows_per_sample) * ld_x + v * 8;
     const __half* db = dz + (s * rows_per_sample) * ld_dz + v * 8;
-    for (long long r = r0 + rsub; r < r1; r += rpp) {
+    long long r = r0 + rsub;
+    for (; r + rpp < r1; r += 2LL * rpp) {
+      float t[8], d[8], t2[8], d2[8];
+      ld8b(xb + r * ld_x, t);
+      ld8b(db + r * ld_dz, d);
+      ld8b(xb + (r + rpp) * ld_x, t2);
+      ld8b(db + (r + rpp) * ld_dz, d2);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float xh = (t[i] - mu[i]) * rs[i], xh2 = (t2[i] - mu[i]) * rs[i];
+        float gg = d[i], gg2 = d2[i];
+        if (silu) {
+          gg *= silu_grad(xh * ga[i] + be[i]);
+          gg2 *= silu_grad(xh2 * ga[i] + be[i]);
+        }
+        gg *= ga[i];
+        gg2 *= ga[i];
+        a1[i] += gg + gg2;
+        a2[i] += gg * xh + gg2 * xh2;
+      }
+    }
+    for (; r < r1; r += rpp) {
       float t[8], d[8];
       ld8b(xb + r * ld_x, t);
       ld8b(db + r * ld_dz, d);
@@ -193,17 +214,19 @@ __global__ void gn_finalize_kernel(const float* __restrict__ partial, int chunks
 
 // ------------------------------------------------------------------------------------------------ LayerNorm backward
 constexpr int kLnbMaxVec = 8;
+template <int NV>
 __global__ void layernorm_bwd_kernel(const __half* __restrict__ x, long long ld_x, const __half* __restrict__ dy,
                                      long long ld_dy, __half* __restrict__ dx, long long ld_dx, long long rows, int C,
                                      const __half* __restrict__ gamma, float eps, int accumulate) {
   const int lane = threadIdx.x & 31;
-  const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= rows) return;
   const int vpr = C >> 3;
-  float xv[kLnbMaxVec][8], gv[kLnbMaxVec][8];
+  const long long warps_total = static_cast<long long>(gridDim.x) * (blockDim.x >> 5);
+  for (long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows;
+       row += warps_total) {
+  float xv[NV][8], gv[NV][8];
   float sum = 0.f;
 #pragma unroll
-  for (int k = 0; k < kLnbMaxVec; ++k) {
+  for (int k = 0; k < NV; ++k) {
     const int v = lane + k * 32;
     if (v < vpr) {
       ld8b(x + row * ld_x + v * 8, xv[k]);
@@ -216,7 +239,7 @@ __global__ void layernorm_bwd_kernel(const __half* __restrict__ x, long long ld_
   const float mean = sum / C;
   float sq = 0.f;
 #pragma unroll
-  for (int k = 0; k < kLnbMaxVec; ++k) {
+  for (int k = 0; k < NV; ++k) {
     const int v = lane + k * 32;
     if (v < vpr) {
 #pragma unroll
@@ -231,7 +254,7 @@ __global__ void layernorm_bwd_kernel(const __half* __restrict__ x, long long ld_
   const float rstd = rsqrtf(sq / C + eps);
   float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-  for (int k = 0; k < kLnbMaxVec; ++k) {
+  for (int k = 0; k < NV; ++k) {
     const int v = lane + k * 32;
     if (v < vpr) {
       float d[8], ga[8];
@@ -256,7 +279,7 @@ __global__ void layernorm_bwd_kernel(const __half* __restrict__ x, long long ld_
   s1 /= C;
   s2 /= C;
 #pragma unroll
-  for (int k = 0; k < kLnbMaxVec; ++k) {
+  for (int k = 0; k < NV; ++k) {
     const int v = lane + k * 32;
     if (v < vpr) {
       float o[8];
@@ -268,6 +291,7 @@ __global__ void layernorm_bwd_kernel(const __half* __restrict__ x, long long ld_
       }
       st8b(dx + row * ld_dx + v * 8, o);
     }
+  }
   }
 }
 
@@ -454,13 +478,13 @@ using namespace lvd;
 extern "C" int lvd_groupnorm_bwd(const void* x, int64_t ld_x, const void* dz, int64_t ld_dz, void* dx, int64_t ld_dx,
                                  int32_t samples, int64_t rows_per_sample, int32_t channels, int32_t groups,
                                  const void* gamma, const void* beta, float eps, int32_t silu, int32_t accumulate,
-                                 void* workspace, int64_t workspace_bytes, void* stream) {
+                                 const void* fwd_stats, void* workspace, int64_t workspace_bytes, void* stream) {
   LVD_REQUIRE(x && dz && dx && gamma && beta && workspace, "lvd_groupnorm_bwd: null pointer");
   LVD_REQUIRE(channels % 8 == 0 && channels % groups == 0 && groups <= 64 && channels <= 4096,
               "lvd_groupnorm_bwd: C=%d G=%d unsupported", channels, groups);
   LVD_REQUIRE(ld_x % 8 == 0 && ld_dz % 8 == 0 && ld_dx % 8 == 0, "lvd_groupnorm_bwd: ld must be a multiple of 8");
-  long long chunks = (4LL * num_sms() + samples - 1) / samples;
-  const long long max_chunks = (rows_per_sample + 63) / 64;
+  long long chunks = (8LL * num_sms() + samples - 1) / samples;
+  const long long max_chunks = (rows_per_sample + 15) / 16;
   if (chunks > max_chunks) chunks = max_chunks;
   if (chunks < 1) chunks = 1;
   if (chunks > 1024) chunks = 1024;
@@ -479,9 +503,13 @@ extern "C" int lvd_groupnorm_bwd(const void* x, int64_t ld_x, const void* dz, in
   dim3 grid(static_cast<unsigned>(chunks), static_cast<unsigned>(samples));
   const float n = static_cast<float>(rows_per_sample) * (channels / groups);
   const int fin_threads = 256 / groups * groups;
-  gn_stats_kernel<<<grid, threads, 2 * channels * sizeof(float), ST(stream)>>>(HC(x), ld_x, rows_per_sample, channels,
-                                                                               groups, static_cast<int>(chunks), fwd);
-  gn_finalize_kernel<<<samples, fin_threads, 0, ST(stream)>>>(fwd, static_cast<int>(chunks), groups, n, eps, stats, 0);
+  if (fwd_stats) {
+    stats = const_cast<float*>(static_cast<const float*>(fwd_stats));  // {mean, rstd} kept from the forward launch
+  } else {
+    gn_stats_kernel<<<grid, threads, 2 * channels * sizeof(float), ST(stream)>>>(
+        HC(x), ld_x, rows_per_sample, channels, groups, static_cast<int>(chunks), fwd);
+    gn_finalize_kernel<<<samples, fin_threads, 0, ST(stream)>>>(fwd, static_cast<int>(chunks), groups, n, eps, stats, 0);
+  }
   gn_bwd_stats_kernel<<<grid, threads, (2 * channels + 2 * groups) * sizeof(float), ST(stream)>>>(
       HC(x), ld_x, HC(dz), ld_dz, rows_per_sample, channels, groups, static_cast<int>(chunks), stats, HC(gamma),
       HC(beta), eps, silu, bwd);
@@ -501,9 +529,24 @@ extern "C" int lvd_layernorm_bwd(const void* x, int64_t ld_x, const void* dy, in
   LVD_REQUIRE(channels % 8 == 0 && channels <= kLnbMaxVec * 256, "lvd_layernorm_bwd: C=%d unsupported", channels);
   LVD_REQUIRE(ld_x % 8 == 0 && ld_dy % 8 == 0 && ld_dx % 8 == 0, "lvd_layernorm_bwd: ld must be a multiple of 8");
   if (rows <= 0) return LVD_OK;
-  const int warps = 4;
-  layernorm_bwd_kernel<<<static_cast<unsigned>((rows + warps - 1) / warps), warps * 32, 0, ST(stream)>>>(
-      HC(x), ld_x, HC(dy), ld_dy, HM(dx), ld_dx, rows, channels, HC(gamma), eps, accumulate);
+  const int warps = 8;
+  long long blocks = (rows + warps - 1) / warps;
+  const long long cap = 16LL * num_sms();
+  if (blocks > cap) blocks = cap;
+  const int nv = (channels / 8 + 31) / 32;
+#define LVD_LNB_LAUNCH(NV)                                                                          \
+  layernorm_bwd_kernel<NV><<<static_cast<unsigned>(blocks), warps * 32, 0, ST(stream)>>>(           \
+      HC(x), ld_x, HC(dy), ld_dy, HM(dx), ld_dx, rows, channels, HC(gamma), eps, accumulate)
+  if (nv <= 2) {
+    LVD_LNB_LAUNCH(2);
+  } else if (nv <= 3) {
+    LVD_LNB_LAUNCH(3);
+  } else if (nv <= 5) {
+    LVD_LNB_LAUNCH(5);
+  } else {
+    LVD_LNB_LAUNCH(8);
+  }
+#undef LVD_LNB_LAUNCH
   g_launches.fetch_add(1, std::memory_order_relaxed);
   LVD_CHECK_CUDA(cudaGetLastError());
   return LVD_OK;

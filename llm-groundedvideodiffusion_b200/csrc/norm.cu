@@ -275,8 +275,8 @@ using namespace lvd;
 
 extern "C" int lvd_groupnorm(const void* x, int64_t ld_x, void* y, int64_t ld_y, int32_t samples,
                              int64_t rows_per_sample, int32_t channels, int32_t groups, const void* gamma,
-                             const void* beta, float eps, int32_t silu, void* workspace, int64_t workspace_bytes,
-                             void* stream) {
+                             const void* beta, float eps, int32_t silu, void* stats_out, void* workspace,
+                             int64_t workspace_bytes, void* stream) {
   LVD_REQUIRE(x && y && gamma && beta && workspace, "lvd_groupnorm: null pointer");
   LVD_REQUIRE(channels % 8 == 0 && channels % groups == 0 && groups <= 64 && channels <= 4096,
               "lvd_groupnorm: C=%d G=%d unsupported", channels, groups);
@@ -298,7 +298,7 @@ extern "C" int lvd_groupnorm(const void* x, int64_t ld_x, void* y, int64_t ld_y,
   gn_stats_kernel<<<grid, threads, 2 * channels * sizeof(float), st>>>(
       static_cast<const __half*>(x), ld_x, rows_per_sample, channels, groups, static_cast<int>(chunks),
       static_cast<float*>(workspace));
-  float* stats = static_cast<float*>(workspace) + need / sizeof(float);
+  float* stats = stats_out ? static_cast<float*>(stats_out) : static_cast<float*>(workspace) + need / sizeof(float);
   gn_finalize_kernel<<<samples, 256 / groups * groups, 0, st>>>(static_cast<const float*>(workspace),
                                                                static_cast<int>(chunks), groups,
                                                                static_cast<float>(rows_per_sample) * (channels / groups),

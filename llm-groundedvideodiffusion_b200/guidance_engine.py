@@ -41,40 +41,43 @@ class GuidanceGraph:
     # ------------------------------------------------------------------------------------------ module pairs
     def _resnet_fwd(self, L, x, n_img, h, w_, temb_all):
         eps = self.cfg["norm_eps"]
-        t1 = ops.groupnorm(x, n_img, L.norm1.w, L.norm1.b, eps, silu=True)
+        s1, s2 = ops.gn_stats_buffer(n_img, self.dev), ops.gn_stats_buffer(n_img, self.dev)
+        t1 = ops.groupnorm(x, n_img, L.norm1.w, L.norm1.b, eps, silu=True, stats_out=s1)
         lo, hi = L.temb
         t2 = ops.conv2d_3x3(t1, n_img, h, w_, L.conv1.w, L.conv1.b, rowvec=temb_all[:, lo:hi])
-        t3 = ops.groupnorm(t2, n_img, L.norm2.w, L.norm2.b, eps, silu=True)
+        t3 = ops.groupnorm(t2, n_img, L.norm2.w, L.norm2.b, eps, silu=True, stats_out=s2)
         sc = ops.linear(x, L.shortcut.w, L.shortcut.b) if "shortcut" in L else x
         out = ops.conv2d_3x3(t3, n_img, h, w_, L.conv2.w, L.conv2.b, residual=sc)
-        return out, Ctx(x=x, t2=t2, n_img=n_img, h=h, w=w_)
+        return out, Ctx(x=x, t2=t2, n_img=n_img, h=h, w=w_, s1=s1, s2=s2)
 
     def _resnet_bwd(self, L, c, dout):
         eps = self.cfg["norm_eps"]
         d3 = ops.conv2d_3x3_dgrad(dout, c.n_img, c.h, c.w, L.conv2.w)
-        d2 = ops.groupnorm_bwd(c.t2, d3, c.n_img, L.norm2.w, L.norm2.b, eps, silu=True)
+        d2 = ops.groupnorm_bwd(c.t2, d3, c.n_img, L.norm2.w, L.norm2.b, eps, silu=True, stats=c.s2)
         d1 = ops.conv2d_3x3_dgrad(d2, c.n_img, c.h, c.w, L.conv1.w)
         if "shortcut" in L:
             dx = ops.linear_dgrad(dout, L.shortcut.w)
-            return ops.groupnorm_bwd(c.x, d1, c.n_img, L.norm1.w, L.norm1.b, eps, silu=True, out=dx, accumulate=True)
-        dx = ops.groupnorm_bwd(c.x, d1, c.n_img, L.norm1.w, L.norm1.b, eps, silu=True)
+            return ops.groupnorm_bwd(c.x, d1, c.n_img, L.norm1.w, L.norm1.b, eps, silu=True, out=dx, accumulate=True,
+                                     stats=c.s1)
+        dx = ops.groupnorm_bwd(c.x, d1, c.n_img, L.norm1.w, L.norm1.b, eps, silu=True, stats=c.s1)
         return ops.add_rows(dx, dout)
 
     def _tconv_fwd(self, layers, x, batch, frames, hw):
         t = x
-        ins = []
+        ins, sts = [], []
         for i, L in enumerate(layers):
             ins.append(t)
-            g = ops.groupnorm(t, batch, L.norm.w, L.norm.b, 1e-5, silu=True)
+            sts.append(ops.gn_stats_buffer(batch, self.dev))
+            g = ops.groupnorm(t, batch, L.norm.w, L.norm.b, 1e-5, silu=True, stats_out=sts[-1])
             t = ops.conv_temporal(g, batch, frames, hw, L.w, L.b, residual=x if i == 3 else None)
-        return t, Ctx(ins=ins, batch=batch, frames=frames, hw=hw)
+        return t, Ctx(ins=ins, sts=sts, batch=batch, frames=frames, hw=hw)
 
     def _tconv_bwd(self, layers, c, dout):
         d = dout
         for i in (3, 2, 1, 0):
             L = layers[i]
             d = ops.conv_temporal_dgrad(d, c.batch, c.frames, c.hw, L.w)
-            d = ops.groupnorm_bwd(c.ins[i], d, c.batch, L.norm.w, L.norm.b, 1e-5, silu=True)
+            d = ops.groupnorm_bwd(c.ins[i], d, c.batch, L.norm.w, L.norm.b, 1e-5, silu=True, stats=c.sts[i])
         return ops.add_rows(d, dout)
 
     def _block_fwd(self, B, t, *, heads, spatial, n_img, hw, batch, frames, ctx_kv, tok_cols, want_tok):
@@ -155,13 +158,14 @@ class GuidanceGraph:
     def _transformer_fwd(self, T, x, *, spatial, n_img, hw, batch, frames, ctx_kv=None, tok_cols=(), want_tok=False,
                          last=False):
         samples = n_img if spatial else batch
-        g = ops.groupnorm(x, samples, T.norm.w, T.norm.b, 1e-6, silu=False)
+        st = ops.gn_stats_buffer(samples, self.dev)
+        g = ops.groupnorm(x, samples, T.norm.w, T.norm.b, 1e-6, silu=False, stats_out=st)
         t0 = ops.linear(g, T.proj_in.w, T.proj_in.b)
         heads = t0.shape[1] // self.cfg["attention_head_dim"]
         t1, bctx = self._block_fwd(T.block, t0, heads=heads, spatial=spatial, n_img=n_img, hw=hw, batch=batch,
                                    frames=frames, ctx_kv=ctx_kv, tok_cols=tok_cols, want_tok=want_tok)
         out = None if last else ops.linear(t1, T.proj_out.w, T.proj_out.b, residual=x)
-        return out, Ctx(x=x, block=bctx, samples=samples)
+        return out, Ctx(x=x, block=bctx, samples=samples, st=st)
 
     def _transformer_bwd(self, T, c, dout, dp_tok=None, tok_cols=()):
         if dout is not None:
@@ -172,8 +176,8 @@ class GuidanceGraph:
         d_g = ops.linear_dgrad(d_t0, T.proj_in.w)
         if dout is not None:
             return ops.groupnorm_bwd(c.x, d_g, c.samples, T.norm.w, T.norm.b, 1e-6, silu=False, out=dout,
-                                     accumulate=True)
-        return ops.groupnorm_bwd(c.x, d_g, c.samples, T.norm.w, T.norm.b, 1e-6, silu=False)
+                                     accumulate=True, stats=c.st)
+        return ops.groupnorm_bwd(c.x, d_g, c.samples, T.norm.w, T.norm.b, 1e-6, silu=False, stats=c.st)
 
     def _s2_weights(self, blk):
         key = id(blk)

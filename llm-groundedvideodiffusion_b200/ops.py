@@ -269,7 +269,7 @@ def _gn_workspace(dev, samples, groups):
     return ws
 
 
-def groupnorm(x, samples, gamma, beta, eps, *, groups=32, silu=False, out=None):
+def groupnorm(x, samples, gamma, beta, eps, *, groups=32, silu=False, out=None, stats_out=None):
     """GroupNorm (+ optional SiLU) with statistics per (sample, group); x [samples*rows_per_sample, C]."""
     _check_act(x, "x")
     rows, c = x.shape
@@ -280,7 +280,8 @@ def groupnorm(x, samples, gamma, beta, eps, *, groups=32, silu=False, out=None):
     with _Timed("groupnorm", 0.0, 2.0 * rows * c * 2):
         _lib.check(_lib.lib().lvd_groupnorm(x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), samples,
                                             rows // samples, c, groups, gamma.data_ptr(), beta.data_ptr(), float(eps),
-                                            1 if silu else 0, ws.data_ptr(), ws.numel(), _stream()), "groupnorm")
+                                            1 if silu else 0, stats_out.data_ptr() if stats_out is not None else None,
+                                            ws.data_ptr(), ws.numel(), _stream()), "groupnorm")
     return out
 
 
@@ -502,7 +503,11 @@ def conv2d_3x3_s2_dgrad(dy, n_img, h, w_, wk_parity, *, out=None):
     return out
 
 
-def groupnorm_bwd(x, dz, samples, gamma, beta, eps, *, groups=32, silu=False, out=None, accumulate=False):
+def gn_stats_buffer(samples, dev, groups=32):
+    return torch.empty((samples, groups, 2), dtype=torch.float32, device=dev)
+
+
+def groupnorm_bwd(x, dz, samples, gamma, beta, eps, *, groups=32, silu=False, out=None, accumulate=False, stats=None):
     _check_act(x, "x")
     _check_act(dz, "dz")
     rows, c = x.shape
@@ -514,7 +519,8 @@ def groupnorm_bwd(x, dz, samples, gamma, beta, eps, *, groups=32, silu=False, ou
         _lib.check(_lib.lib().lvd_groupnorm_bwd(x.data_ptr(), x.stride(0), dz.data_ptr(), dz.stride(0), out.data_ptr(),
                                                 out.stride(0), samples, rows // samples, c, groups, gamma.data_ptr(),
                                                 beta.data_ptr(), float(eps), 1 if silu else 0, 1 if accumulate else 0,
-                                                ws.data_ptr(), ws.numel(), _stream()), "groupnorm_bwd")
+                                                stats.data_ptr() if stats is not None else None, ws.data_ptr(),
+                                                ws.numel(), _stream()), "groupnorm_bwd")
     return out
 
 
@@ -614,20 +620,22 @@ def self_attention_bwd(qkv, d_o, o, lse, *, heads, nz, s, scale=0.125, out=None)
     return out
 
 
-def temporal_attention_bwd(qkv, d_o, *, heads, n_seq, frames, scale=0.125, out=None):
+def temporal_attention_bwd(qkv, d_o, *, heads, n_seq, frames, scale=0.125, out=None, tensor_core=True):
     _check_act(qkv, "qkv")
     _check_act(d_o, "d_o")
     c = heads * 64
     if out is None:
         out = torch.empty_like(qkv)
     with _Timed("attention_temporal_bwd", 10.0 * n_seq * heads * frames * frames * 64, 0.0):
-        _lib.check(_lib.lib().lvd_temporal_attn_bwd(qkv.data_ptr(), qkv.stride(0), 0, c, 2 * c, d_o.data_ptr(),
+        _lib.check(_lib.lib().lvd_temporal_attn_bwd(qkv.data_ptr(), qkv.stride(0), qkv.shape[1] if tensor_core else 0, 0, c,
+                                                    2 * c, d_o.data_ptr(),
                                                     d_o.stride(0), out.data_ptr(), out.stride(0), n_seq, heads, frames,
                                                     float(scale), _stream()), "temporal_attn_bwd")
     return out
 
 
-def cross_attention_bwd(q, kv, d_o, *, heads, nz, s_q, s_k, kv_z_div, dp_tok=None, slot_cols=(), scale=0.125, out=None):
+def cross_attention_bwd(q, kv, d_o, *, heads, nz, s_q, s_k, kv_z_div, dp_tok=None, slot_cols=(), scale=0.125, out=None,
+                        tensor_core=True):
     _check_act(q, "q")
     _check_act(kv, "kv")
     _check_act(d_o, "d_o")
@@ -636,7 +644,8 @@ def cross_attention_bwd(q, kv, d_o, *, heads, nz, s_q, s_k, kv_z_div, dp_tok=Non
         out = _alloc_out(q.shape[0], c, q)
     cols = (ctypes.c_int32 * max(1, len(slot_cols)))(*[int(x) for x in slot_cols])
     with _Timed("attention_cross_bwd", 6.0 * nz * heads * s_q * s_k * 64, 0.0):
-        _lib.check(_lib.lib().lvd_cross_attn_bwd(q.data_ptr(), q.stride(0), kv.data_ptr(), kv.stride(0), 0, c,
+        _lib.check(_lib.lib().lvd_cross_attn_bwd(q.data_ptr(), q.stride(0), q.shape[1] if tensor_core else 0, kv.data_ptr(),
+                                                 kv.stride(0), kv.shape[1] if tensor_core else 0, 0, c,
                                                  d_o.data_ptr(), d_o.stride(0),
                                                  dp_tok.data_ptr() if dp_tok is not None else None, cols,
                                                  len(slot_cols) if dp_tok is not None else 0, out.data_ptr(),

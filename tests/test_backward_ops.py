@@ -155,8 +155,9 @@ def _attn(q, k, v, heads):
     return (p @ vh).transpose(1, 2).reshape(z, sq, c), p
 
 
-@pytest.mark.parametrize("n_seq,frames,heads", [(20, 24, 2), (7, 16, 1), (5, 8, 3), (3, 32, 1)])
-def test_temporal_attention_bwd(cuda, n_seq, frames, heads):
+@pytest.mark.parametrize("tc", [True, False])
+@pytest.mark.parametrize("n_seq,frames,heads", [(20, 24, 2), (7, 16, 1), (5, 8, 3), (3, 32, 1), (2880, 24, 1)])
+def test_temporal_attention_bwd(cuda, n_seq, frames, heads, tc):
     from lvd_b200 import ops
     c = heads * 64
     qkv = _rand((n_seq * frames, 3 * c), cuda, seed=31)
@@ -167,12 +168,13 @@ def test_temporal_attention_bwd(cuda, n_seq, frames, heads):
         return _attn(q, k, v, heads)[0].reshape(n_seq * frames, c)
 
     ref = _grad(fn, qkv, d_o)
-    out = ops.temporal_attention_bwd(qkv, d_o, heads=heads, n_seq=n_seq, frames=frames)
+    out = ops.temporal_attention_bwd(qkv, d_o, heads=heads, n_seq=n_seq, frames=frames, tensor_core=tc)
     assert rel_err(out, ref) < TOL
 
 
+@pytest.mark.parametrize("tc", [True, False])
 @pytest.mark.parametrize("b,frames,s,heads", [(1, 3, 180, 2), (2, 2, 45, 4), (1, 2, 720, 1)])
-def test_cross_attention_bwd_with_energy_seed(cuda, b, frames, s, heads):
+def test_cross_attention_bwd_with_energy_seed(cuda, b, frames, s, heads, tc):
     from lvd_b200 import ops
     c = heads * 64
     z = b * frames
@@ -190,7 +192,7 @@ def test_cross_attention_bwd_with_energy_seed(cuda, b, frames, s, heads):
         seed = seed + (p[..., col] * dp_tok[i].float()).sum()
     (ref,) = torch.autograd.grad(seed, [qr])
     out = ops.cross_attention_bwd(q, kv, d_o, heads=heads, nz=z, s_q=s, s_k=77, kv_z_div=frames, dp_tok=dp_tok,
-                                  slot_cols=cols)
+                                  slot_cols=cols, tensor_core=tc)
     assert rel_err(out, ref) < TOL
 
 
