@@ -88,14 +88,13 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   const uint32_t b_stage_bytes = static_cast<uint32_t>(g.block_n) * 128u;
   uint8_t* sA = smem;
   uint8_t* sB = smem + stages * kAStageBytes;
-  uint8_t* sOut = sB + stages * b_stage_bytes;  // 2 output slabs [128 rows][32 cols] fp16, one per epilogue group
-  uint8_t* sRes = sOut + 2 * kSlabBytes;        // 2 residual slabs
-  uint64_t* full = reinterpret_cast<uint64_t*>(sRes + 2 * kSlabBytes);
+  uint8_t* sOut = sB + stages * b_stage_bytes;  // output slabs [128 rows][32 cols] fp16: 2 per epilogue group
+  uint64_t* full = reinterpret_cast<uint64_t*>(sOut + 4 * kSlabBytes);
   uint64_t* empty = full + stages;
   uint64_t* tfull = empty + stages;
   uint64_t* tempty = tfull + 2;
-  uint64_t* res_full = tempty + 2;  // [2]
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(res_full + 2);
+  uint64_t* res_full = tempty + 2;  // [group][buffer]
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(res_full + 4);
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < stages; ++i) {
@@ -106,8 +105,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     mbar_init(&tfull[1], 1);
     mbar_init(&tempty[0], 512);
     mbar_init(&tempty[1], 512);
-    mbar_init(&res_full[0], 1);
-    mbar_init(&res_full[1], 1);
+    for (int i = 0; i < 4; ++i) mbar_init(&res_full[i], 1);
     fence_barrier_init();
   }
   if (warp == 0 && lane == 0) {
@@ -216,17 +214,27 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       t /= g.box[2];
       j[3] = t;  // >= box[3] when the box has fewer than 128 rows
     }
-    uint8_t* my_out = sOut + grp * kSlabBytes;
-    uint8_t* my_res = sRes + grp * kSlabBytes;
+    uint8_t* my_out = sOut + grp * 2 * kSlabBytes;  // two buffers, alternated per slab
+    uint64_t* my_res_full = res_full + grp * 2;
     // 64-byte swizzle: physical = logical ^ (((logical >> 7) & 3) << 4), logical = r*64 + chunk*16
     const uint32_t sw = static_cast<uint32_t>((r >> 1) & 3);
     const uint32_t off0 = static_cast<uint32_t>(r * 64) + (((static_cast<uint32_t>(usub * 2)) ^ sw) << 4);
     const uint32_t off1 = static_cast<uint32_t>(r * 64) + (((static_cast<uint32_t>(usub * 2 + 1)) ^ sw) << 4);
     int acc = 0;
-    uint32_t acc_phase = 0, res_phase = 0;
+    uint32_t acc_phase = 0;
     const bool geglu = (g.act == 2);
     const int nslabs = geglu ? 2 : g.block_n / 32;
     const int bar_id = 1 + grp;
+    uint32_t seq = 0;  // slabs processed by this group so far: buffer = seq & 1, residual parity = (seq >> 1) & 1
+    auto issue_res = [&](int tile_, int sl_, uint32_t seq_) {  // leader only: TMA-load the residual slab (tile_, sl_)
+      int cc[4];
+      tile_coords(g, tile_ / g.n_tiles_n, cc);
+      const int gc = (geglu ? (tile_ % g.n_tiles_n) * 64 : (tile_ % g.n_tiles_n) * g.block_n) + sl_ * 32;
+      mbar_arrive_expect_tx(&my_res_full[seq_ & 1], static_cast<uint32_t>(g.slab_bytes));
+      // the residual lands in the slab's own output buffer: threads add to it in place
+      tma_load_5d(my_out + (seq_ & 1) * kSlabBytes, &g.map_res, &my_res_full[seq_ & 1], gc, cc[0], cc[1], cc[2], cc[3]);
+    };
+    if (leader && g.residual && blockIdx.x < g.num_tiles && grp < nslabs) issue_res(blockIdx.x, grp, 0);
     for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
       const int nt = tile % g.n_tiles_n;
       int c[4];
@@ -242,16 +250,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + static_cast<uint32_t>(acc) * 256u + (static_cast<uint32_t>(q * 32) << 16);
-      for (int sl = grp; sl < nslabs; sl += 2) {
+      for (int sl = grp; sl < nslabs; sl += 2, ++seq) {
         const int gcol = (geglu ? nt * 64 : nt * g.block_n) + sl * 32;  // first global output column of the slab
-        if (leader) {
-          bulk_wait_read_all();
-          if (g.residual) {
-            mbar_arrive_expect_tx(&res_full[grp], static_cast<uint32_t>(g.slab_bytes));
-            tma_load_5d(my_res, &g.map_res, &res_full[grp], gcol, c[0], c[1], c[2], c[3]);
-          }
-        }
-        named_bar_sync(bar_id, 256);
+        uint8_t* obuf = my_out + (seq & 1) * kSlabBytes;
         const int ucol = sl * 32 + usub * 16;  // tile-relative column of this thread's 16-column unit
         const int ocol = gcol + usub * 16;
         uint32_t rv[16], rg[16];
@@ -276,8 +277,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
           }
 #pragma unroll
           for (int i = 0; i < 16; ++i)
-            v[i >> 3][i & 7] = round_h(v[i >> 3][i & 7] + bv[i >> 3][i & 7]) *
-                               round_h(gelu_erf_f(__uint_as_float(rg[i]) + bg[i >> 3][i & 7]));
+            v[i >> 3][i & 7] = (v[i >> 3][i & 7] + bv[i >> 3][i & 7]) *
+                               gelu_erf_f(__uint_as_float(rg[i]) + bg[i >> 3][i & 7]);
         } else {
           if (g.bias) {
             float b[2][8];
@@ -304,21 +305,29 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
           for (int i = 0; i < 16; ++i) v[i >> 3][i & 7] = round_h(v[i >> 3][i & 7]) * gm;
         }
         if (g.residual) {
-          mbar_wait(&res_full[grp], res_phase);
-          res_phase ^= 1u;
+          mbar_wait(&my_res_full[seq & 1], (seq >> 1) & 1u);
           float t[2][8];
-          load8(reinterpret_cast<const __half*>(my_res + off0), t[0]);
-          load8(reinterpret_cast<const __half*>(my_res + off1), t[1]);
+          load8(reinterpret_cast<const __half*>(obuf + off0), t[0]);
+          load8(reinterpret_cast<const __half*>(obuf + off1), t[1]);
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i >> 3][i & 7] = round_h(v[i >> 3][i & 7]) + t[i >> 3][i & 7];
         }
-        store8(reinterpret_cast<__half*>(my_out + off0), v[0]);
-        store8(reinterpret_cast<__half*>(my_out + off1), v[1]);
+        store8(reinterpret_cast<__half*>(obuf + off0), v[0]);
+        store8(reinterpret_cast<__half*>(obuf + off1), v[1]);
         fence_proxy_async_smem();
+        // the other output buffer must have been drained (store seq-1) before anyone writes it in the next slab
+        if (leader) bulk_wait_read_all();
         named_bar_sync(bar_id, 256);
         if (leader) {
-          tma_store_5d(&g.map_out, my_out, gcol, c[0], c[1], c[2], c[3]);
+          tma_store_5d(&g.map_out, obuf, gcol, c[0], c[1], c[2], c[3]);
           bulk_commit_group();
+          if (g.residual) {  // prefetch the residual of this group's next slab (same tile, or the next tile's first)
+            if (sl + 2 < nslabs) {
+              issue_res(tile, sl + 2, seq + 1);
+            } else if (tile + static_cast<int>(gridDim.x) < g.num_tiles) {
+              issue_res(tile + static_cast<int>(gridDim.x), grp, seq + 1);
+            }
+          }
         }
       }
       tc_fence_before();
@@ -420,7 +429,8 @@ static int launch_gemm(const lvd_gemm_desc* d, cudaStream_t stream) {
     }
   }
   const int stage_bytes = kAStageBytes + g.b_bytes;
-  int stages = (kSmemLimit - 1024 - 256 - 4 * kSlabBytes) / stage_bytes;
+  const int n_slabs_smem = 4;
+  int stages = (kSmemLimit - 1024 - 256 - n_slabs_smem * kSlabBytes) / stage_bytes;
   if (stages > 8) stages = 8;
   g.stages = stages;
   g.bias = static_cast<const __half*>(d->bias);
@@ -433,7 +443,7 @@ static int launch_gemm(const lvd_gemm_desc* d, cudaStream_t stream) {
   g.gamma = d->gamma;
   g.idesc = make_idesc_f16(128, static_cast<uint32_t>(d->block_n), 0, d->b_mn_major ? 1u : 0u);
 
-  const int smem_bytes = 1024 + stages * stage_bytes + 4 * kSlabBytes + 256;
+  const int smem_bytes = 1024 + stages * stage_bytes + n_slabs_smem * kSlabBytes + 256;
   static bool attr_set = false;
   if (!attr_set) {
     LVD_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
