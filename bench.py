@@ -412,10 +412,18 @@ def run_gpu(args):
     if gg:  # one guided step = CFG forward + one guidance iteration: the dominant kernel's launches of both
         share = 1.0 / GUIDED_EVERY
         gm = {"ms": gm["ms"] + share * gg["ms"], "flops": gm["flops"] + share * gg["flops"],
-              "launches": gm["launches"] + share * gg["launches"]}
+              "launches": gm["launches"] + share * gg["launches"], "bytes": gm.get("bytes", 0.0) + share * gg["bytes"]}
     achieved = gm["flops"] / (gm["ms"] * 1e-3) / 1e12
+    traffic, traffic_src = None, None
+    try:  # DRAM bytes per gemm_tc_kernel launch from the committed ncu capture (profiles/, measured, not live)
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_gemm_traffic.json")))
+        traffic, traffic_src = tj["traffic_bytes_per_launch"], "profiles/r1_gemm_traffic.json (ncu dram__bytes_*.sum)"
+    except Exception:
+        pass
     roofline = {"bound": "tensor", "kernel": "gemm_tc_kernel", "achieved": achieved, "peak": peak_tf,
-                "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": None, "peak_source": peak_src,
+                "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": traffic, "traffic_unit": "bytes/launch",
+                "traffic_source": traffic_src, "algorithmic_bytes_per_launch": gm.get("bytes", 0.0) / max(1, gm["launches"]),
+                "peak_source": peak_src,
                 "launches_per_step": gm["launches"], "ms_per_step": gm["ms"],
                 "share_of_instrumented_step": gm["ms"] / max(1e-9, sum(v["ms"] for v in fam.values()) + (
                     sum(v["ms"] for v in fam_guid.values()) / GUIDED_EVERY if fam_guid else 0.0)),

@@ -113,15 +113,6 @@ def gemm_raw(*, a, a_dims, a_strides, a_box, taps, k_per_tap, w, n, out, out_dim
     d.b_mn_major = 1 if b_mn_major else 0
     if block_n is None:
         block_n = pick_block_n(n, act, b_mn_major)
-        if act != ACT_GEGLU:
-            # under-filled grids (deep levels: M = 2160 / 8640 rows): trade tile width for tile count until every
-            # SM has work
-            m_tiles = 1
-            for i in range(4):
-                m_tiles *= -(-int(out_dims[i]) // int(a_box[i + 1]))
-            while block_n > 64 and m_tiles * (n // block_n) < _NUM_SMS and n % (block_n // 2) == 0 \
-                    and (block_n // 2) % 32 == 0:
-                block_n //= 2
     d.block_n = int(block_n)
     d.ldb = int(ldb if ldb is not None else w.stride(0))
     d.n = int(n)
