@@ -389,9 +389,15 @@ def run_gpu(args):
         launches_per_guidance = _lib.lib().lvd_launch_count() - l1
     fam = {}
     fam_guid = {}
-    for k_, (name, fl, nb, s, e) in enumerate(ops.PROF):
+    shapes = ({}, {})
+    for k_, (name, fl, nb, s, e, tag) in enumerate(ops.PROF):
         d = (fam if k_ < n_fwd_records else fam_guid).setdefault(name, {"ms": 0.0, "flops": 0.0, "bytes": 0.0,
                                                                         "launches": 0})
+        if tag is not None:
+            sd = shapes[0 if k_ < n_fwd_records else 1].setdefault(tag, {"ms": 0.0, "flops": 0.0, "launches": 0})
+            sd["ms"] += s.elapsed_time(e)
+            sd["flops"] += fl
+            sd["launches"] += 1
         d["ms"] += s.elapsed_time(e)
         d["flops"] += fl
         d["bytes"] += nb
@@ -430,7 +436,8 @@ def run_gpu(args):
                 "note": "FLOPs and CUDA-event time summed over all gemm_tc_kernel launches of one CFG forward plus "
                         "1/5 of one guidance iteration (the timed step mix), instrumented pass after the timed region"}
     if args.profile_json and rank == 0:
-        json.dump({"cfg_forward": fam, "guidance_iteration": fam_guid}, open(args.profile_json, "w"), indent=1)
+        json.dump({"cfg_forward": fam, "guidance_iteration": fam_guid, "gemm_shapes_cfg_forward": shapes[0],
+                   "gemm_shapes_guidance_iteration": shapes[1]}, open(args.profile_json, "w"), indent=1)
 
     if rank == 0:
         ms_step = ms / args.steps

@@ -29,6 +29,9 @@ const char* lvd_last_error(void);
 int lvd_version(void);
 /* number of kernels this library has launched since load (bench.py's gpu_launches claim) */
 int64_t lvd_launch_count(void);
+/* tuning aid: with LVD_GEMM_DEBUG=64 in the environment CTA 0 of every lvd_gemm launch records a timeline
+ * (event << 48 | %globaltimer ns); this copies out and resets it.  Returns the number of events, < 0 on error. */
+int lvd_debug_trace_read(unsigned long long* host_buf, int max_events);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Tensor-core contraction with a fused epilogue (tcgen05.mma + TMA, fp16 in, fp32 accumulate in TMEM).
@@ -55,9 +58,9 @@ typedef struct lvd_gemm_desc {
   /* B operand (weights), fp16 */
   const void* b;
   int32_t b_mn_major; /* 0: B = [n][K_total], K contiguous.  1: B = [K_total][n], n contiguous (dgrad) */
-  int32_t block_n;    /* 64 | 128 | 160 | 256; n % block_n == 0 (GEGLU: 128) */
+  int32_t block_n;    /* 64 | 128 | 160 | 256; n % block_n == 0 (GEGLU: 128 | 256) */
   int64_t ldb;        /* elements */
-  int32_t n;          /* GEMM N (for GEGLU: 2x the output width, value/gate interleaved per 64) */
+  int32_t n;          /* GEMM N (for GEGLU: 2x the output width; every block_n columns = [block_n/2 value | block_n/2 gate]) */
   int32_t act;        /* 0 none, 1 SiLU, 2 GEGLU */
   /* output geometry: tile axis i (=A dims 1..4) covers out_dims[i] positions in steps of a_box[i+1] */
   int32_t out_dims[4];
@@ -73,7 +76,9 @@ typedef struct lvd_gemm_desc {
    * Conv dgrad reads the SAME [Cout][taps*Cin] weight as an MN-major B: (0, Cin), with negated tap offsets on A. */
   int32_t b_k_tap_stride;
   int32_t b_n_tap_stride;
-  int32_t reserved;
+  /* 0: automatic; 1: one CTA per 128-row tile; 2: CTA pairs (2-CTA clusters, tcgen05 cta_group::2, 256-row tiles --
+   * each SM stages half of every B tile; needs >= 2 row tiles, MN-major B: block_n % 128 == 0) */
+  int32_t cta_pair;
 } lvd_gemm_desc;
 
 int lvd_gemm(const lvd_gemm_desc* d, void* stream);

@@ -37,7 +37,7 @@ class GemmDesc(ctypes.Structure):
         ("gamma", ctypes.c_float),
         ("b_k_tap_stride", ctypes.c_int32),
         ("b_n_tap_stride", ctypes.c_int32),
-        ("reserved", ctypes.c_int32),
+        ("cta_pair", ctypes.c_int32),
     ]
 
 
@@ -161,6 +161,7 @@ def _declare(l):
 EXPORTS = [
     "lvd_last_error",
     "lvd_version",
+    "lvd_debug_trace_read",
     "lvd_launch_count",
     "lvd_gemm",
     "lvd_attention",

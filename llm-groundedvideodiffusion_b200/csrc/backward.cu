@@ -296,7 +296,8 @@ __global__ void layernorm_bwd_kernel(const __half* __restrict__ x, long long ld_
 }
 
 // ------------------------------------------------------------------------------------------------ GEGLU (un-fused) fwd/bwd
-// pre [rows, 2N] in the interleaved layout of repack.geglu_interleave: every 128-column block = [64 value | 64 gate].
+// pre [rows, 2N] in the interleaved layout of repack.geglu_interleave: every 256-column block = [128 value | 128 gate].
+constexpr int kGegluHalf = 128;
 __global__ void geglu_fwd_kernel(const __half* __restrict__ pre, long long ld_pre, __half* __restrict__ out,
                                  long long ld_out, long long rows, int n_out) {
   const int vec = n_out / 8;
@@ -305,10 +306,10 @@ __global__ void geglu_fwd_kernel(const __half* __restrict__ pre, long long ld_pr
        idx += static_cast<long long>(gridDim.x) * blockDim.x) {
     const long long r = idx / vec;
     const int c = static_cast<int>(idx % vec) * 8;  // output column
-    const int pc = (c / 64) * 128 + (c % 64);
+    const int pc = (c / kGegluHalf) * (2 * kGegluHalf) + (c % kGegluHalf);
     float a[8], g[8];
     ld8b(pre + r * ld_pre + pc, a);
-    ld8b(pre + r * ld_pre + pc + 64, g);
+    ld8b(pre + r * ld_pre + pc + kGegluHalf, g);
 #pragma unroll
     for (int i = 0; i < 8; ++i) a[i] = round_h(a[i] * round_h(gelu_erf_f(g[i])));
     st8b(out + r * ld_out + c, a);
@@ -323,10 +324,10 @@ __global__ void geglu_bwd_kernel(const __half* __restrict__ pre, long long ld_pr
        idx += static_cast<long long>(gridDim.x) * blockDim.x) {
     const long long r = idx / vec;
     const int c = static_cast<int>(idx % vec) * 8;
-    const int pc = (c / 64) * 128 + (c % 64);
+    const int pc = (c / kGegluHalf) * (2 * kGegluHalf) + (c % kGegluHalf);
     float a[8], g[8], d[8], da[8], dg[8];
     ld8b(pre + r * ld_pre + pc, a);
-    ld8b(pre + r * ld_pre + pc + 64, g);
+    ld8b(pre + r * ld_pre + pc + kGegluHalf, g);
     ld8b(dout + r * ld_dout + c, d);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -337,7 +338,7 @@ __global__ void geglu_bwd_kernel(const __half* __restrict__ pre, long long ld_pr
       dg[i] = d[i] * a[i] * (cdf + x * pdf);
     }
     st8b(dpre + r * ld_dpre + pc, da);
-    st8b(dpre + r * ld_dpre + pc + 64, dg);
+    st8b(dpre + r * ld_dpre + pc + kGegluHalf, dg);
   }
 }
 
@@ -554,7 +555,7 @@ extern "C" int lvd_layernorm_bwd(const void* x, int64_t ld_x, const void* dy, in
 
 extern "C" int lvd_geglu(const void* pre, int64_t ld_pre, void* out, int64_t ld_out, int64_t rows, int32_t n_out,
                          void* stream) {
-  LVD_REQUIRE(pre && out && n_out % 64 == 0 && ld_pre % 8 == 0 && ld_out % 8 == 0, "lvd_geglu: bad arguments");
+  LVD_REQUIRE(pre && out && n_out % kGegluHalf == 0 && ld_pre % 8 == 0 && ld_out % 8 == 0, "lvd_geglu: bad arguments");
   geglu_fwd_kernel<<<bgrid(rows * (n_out / 8), 256), 256, 0, ST(stream)>>>(HC(pre), ld_pre, HM(out), ld_out, rows,
                                                                           n_out);
   g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -563,7 +564,7 @@ extern "C" int lvd_geglu(const void* pre, int64_t ld_pre, void* out, int64_t ld_
 }
 extern "C" int lvd_geglu_bwd(const void* pre, int64_t ld_pre, const void* dout, int64_t ld_dout, void* dpre,
                              int64_t ld_dpre, int64_t rows, int32_t n_out, void* stream) {
-  LVD_REQUIRE(pre && dout && dpre && n_out % 64 == 0, "lvd_geglu_bwd: bad arguments");
+  LVD_REQUIRE(pre && dout && dpre && n_out % kGegluHalf == 0, "lvd_geglu_bwd: bad arguments");
   LVD_REQUIRE(ld_pre % 8 == 0 && ld_dout % 8 == 0 && ld_dpre % 8 == 0, "lvd_geglu_bwd: ld must be a multiple of 8");
   geglu_bwd_kernel<<<bgrid(rows * (n_out / 8), 256), 256, 0, ST(stream)>>>(HC(pre), ld_pre, HC(dout), ld_dout,
                                                                           HM(dpre), ld_dpre, rows, n_out);

@@ -2,12 +2,13 @@
 //
 //   warp 0      : TMA producer   (one elected lane; cp.async.bulk.tensor into a multi-stage smem ring)
 //   warp 1      : MMA issuer     (one elected lane; tcgen05.mma, fp32 accumulators double-buffered in TMEM)
-//   warps 2..17 : epilogue       (tcgen05.ld -> bias / SiLU / GEGLU / time-embedding / gate / residual -> fp16 store;
-//                 four warps per TMEM lane quarter, interleaved over 16-column units)
+//   warps 2..17 : epilogue       (four groups of four warps -- one warp per TMEM lane quarter; a group turns one
+//                 128-row x 32-column slab of the accumulator into fp16 in shared memory and TMA-stores it)
 //
 // A tiles are rank-5 TMA boxes of the channels-last activation; a convolution tap is a coordinate offset and the
 // zero padding is TMA out-of-bounds fill, so Linear, Conv2d (3x3, 1x1, stride 2) and Conv3d (3,1,1) all run here.
 #include <atomic>
+#include <cstdlib>
 
 #include "../../include/lvd_b200.h"
 #include "host_util.h"
@@ -18,21 +19,24 @@ namespace lvd {
 std::atomic<long long> g_launches{0};
 
 constexpr int kAStageBytes = 128 * 128;  // 128 rows x 64 halves
-constexpr int kThreads = 576;  // 2 control warps + 16 epilogue warps
-constexpr int kSmemLimit = 232448;  // 227 KB
-constexpr int kSlabBytes = 128 * 64;  // epilogue staging slab: 128 rows x 32 halves
+constexpr int kThreads = 576;            // 2 control warps + 16 epilogue warps
+constexpr int kSmemLimit = 232448;       // 227 KB
+constexpr int kSlabBytes = 128 * 64;     // epilogue staging slab: 128 rows x 32 halves
+constexpr int kSlabBufs = 8;             // 4 epilogue groups x 2 buffers
+constexpr int kBarrierBytes = 512;       // mbarriers (8+8 ring, 4+4 accumulator, 8 residual) + the TMEM address
+
+// epilogue specialisations (template parameter): the common cases carry no feature branches in the slab loop
+enum { kEpiGeneric = 0, kEpiBias = 1, kEpiResidual = 2, kEpiGeglu = 3 };
 
 struct GemmArgs {
   CUtensorMap map_a;
   CUtensorMap map_b;
   CUtensorMap map_out;  // 32-column slabs of the output (64-byte swizzle), rows mapped like the A box
   CUtensorMap map_res;  // same geometry over the residual
-  long long out_row_stride[4];
-  long long ld_rowvec, ld_res, ld_out;
+  long long ld_rowvec;
   const __half* bias;
   const __half* rowvec;
   const __half* residual;
-  __half* out;
   int box[4];
   int ntile[4];
   int out_dims[4];
@@ -43,25 +47,60 @@ struct GemmArgs {
   int num_tiles, stages, a_bytes, b_bytes;
   int b_k_tap_stride, b_n_tap_stride;
   int slab_bytes;  // rows of the box * 64
+  int n_acc;       // accumulator stages in TMEM (512 columns / block_n, 2..4), block_n columns apart
+  // persistent tile walk: tile += tile_step; its n-tile / row-tile digits advance by precomputed mixed-radix steps
+  int tile_step, step_nt;
+  int step_lo[4], step_hi[4];
+  int debug;  // tools/perf_gemm_sweep.py: bit 0 = skip the TMA loads, bit 1 = skip the MMAs (results are garbage)
   float gamma;
   uint32_t idesc;
 };
 
-__device__ __forceinline__ void tile_coords(const GemmArgs& g, int mt, int (&c)[4]) {
-  int t0 = mt % g.ntile[0];
-  int r = mt / g.ntile[0];
-  int t1 = r % g.ntile[1];
-  r /= g.ntile[1];
-  int t2 = r % g.ntile[2];
-  int t3 = r / g.ntile[2];
-  c[0] = t0 * g.box[0];
-  c[1] = t1 * g.box[1];
-  c[2] = t2 * g.box[2];
-  c[3] = t3 * g.box[3];
+// Timeline tracing for tools/trace_gemm.py (LVD_GEMM_DEBUG bit 6): CTA 0 appends (event << 48 | globaltimer ns).
+__device__ unsigned long long g_trace[8192];
+__device__ unsigned int g_trace_n;
+__device__ __forceinline__ void trace_event(const GemmArgs& g, unsigned ev) {
+  if ((g.debug & 64) && blockIdx.x == 0) {
+    const unsigned i = atomicAdd(&g_trace_n, 1u);
+    if (i < 8192) g_trace[i] = (static_cast<unsigned long long>(ev) << 48) | (globaltimer_ns() & 0xFFFFFFFFFFFFull);
+  }
 }
 
-__device__ __forceinline__ void load8(const __half* p, float (&v)[8]) {
-  uint4 u = *reinterpret_cast<const uint4*>(p);
+// (n-tile, row-tile digits) of the current tile.  Integer division by run-time extents costs ~100 dependent
+// instructions each; doing six of them per tile in the single producer thread was ~0.8 us per tile (measured).
+struct TileIter {
+  int tile, nt, t0, t1, t2, t3;
+};
+template <int kCtas>
+__device__ __forceinline__ void tile_init(const GemmArgs& g, TileIter& it, int tile, int cta_rank) {
+  it.tile = tile;
+  it.nt = tile % g.n_tiles_n;
+  int r = (tile / g.n_tiles_n) * kCtas + cta_rank;
+  it.t0 = r % g.ntile[0];
+  r /= g.ntile[0];
+  it.t1 = r % g.ntile[1];
+  r /= g.ntile[1];
+  it.t2 = r % g.ntile[2];
+  it.t3 = r / g.ntile[2];
+}
+__device__ __forceinline__ void tile_advance(const GemmArgs& g, TileIter& it) {
+  it.tile += g.tile_step;
+  it.nt += g.step_nt;
+  const bool carry = it.nt >= g.n_tiles_n;
+  if (carry) it.nt -= g.n_tiles_n;
+  it.t0 += carry ? g.step_hi[0] : g.step_lo[0];
+  int c = it.t0 >= g.ntile[0] ? 1 : 0;
+  it.t0 -= c ? g.ntile[0] : 0;
+  it.t1 += (carry ? g.step_hi[1] : g.step_lo[1]) + c;
+  c = it.t1 >= g.ntile[1] ? 1 : 0;
+  it.t1 -= c ? g.ntile[1] : 0;
+  it.t2 += (carry ? g.step_hi[2] : g.step_lo[2]) + c;
+  c = it.t2 >= g.ntile[2] ? 1 : 0;
+  it.t2 -= c ? g.ntile[2] : 0;
+  it.t3 += (carry ? g.step_hi[3] : g.step_lo[3]) + c;  // past ntile[3]: out of bounds for every TMA box
+}
+
+__device__ __forceinline__ void unpack8(const uint4& u, float (&v)[8]) {
   const __half2* h = reinterpret_cast<const __half2*>(&u);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -70,14 +109,18 @@ __device__ __forceinline__ void load8(const __half* p, float (&v)[8]) {
     v[2 * i + 1] = f.y;
   }
 }
-__device__ __forceinline__ void store8(__half* p, const float (&v)[8]) {
+__device__ __forceinline__ uint4 pack8(const float* v) {
   uint4 u;
   __half2* h = reinterpret_cast<__half2*>(&u);
 #pragma unroll
   for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
-  *reinterpret_cast<uint4*>(p) = u;
+  return u;
 }
 
+// kCtas == 2: the CTA pair of a 2-CTA cluster works on one 256-row tile (tcgen05 cta_group::2).  Each CTA stages its
+// own 128-row A tile and HALF of the B tile, the leader's MMA warp issues M=256 instructions that read both CTAs'
+// shared memory, and each CTA's TMEM receives (and its epilogue warps drain) its own 128 accumulator rows.
+template <int kCtas, int kEpi>
 __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_constant__ GemmArgs g) {
   extern __shared__ uint8_t smem_raw[];
   // 128-byte swizzle atoms need 1024-byte aligned stage bases
@@ -85,27 +128,29 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int stages = g.stages;
-  const uint32_t b_stage_bytes = static_cast<uint32_t>(g.block_n) * 128u;
+  const uint32_t cta_rank = kCtas == 2 ? cluster_ctarank() : 0u;
+  const int b_rows = g.block_n / kCtas;  // B rows (N) staged by this CTA
+  const uint32_t b_stage_bytes = static_cast<uint32_t>(b_rows) * 128u;
   uint8_t* sA = smem;
   uint8_t* sB = smem + stages * kAStageBytes;
   uint8_t* sOut = sB + stages * b_stage_bytes;  // output slabs [128 rows][32 cols] fp16: 2 per epilogue group
-  uint64_t* full = reinterpret_cast<uint64_t*>(sOut + 4 * kSlabBytes);
+  uint64_t* full = reinterpret_cast<uint64_t*>(sOut + kSlabBufs * kSlabBytes);
   uint64_t* empty = full + stages;
   uint64_t* tfull = empty + stages;
-  uint64_t* tempty = tfull + 2;
-  uint64_t* res_full = tempty + 2;  // [group][buffer]
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(res_full + 4);
+  uint64_t* tempty = tfull + 4;
+  uint64_t* res_full = tempty + 4;  // [group][buffer]
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(res_full + kSlabBufs);
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < stages; ++i) {
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], 1);
     }
-    mbar_init(&tfull[0], 1);
-    mbar_init(&tfull[1], 1);
-    mbar_init(&tempty[0], 512);
-    mbar_init(&tempty[1], 512);
-    for (int i = 0; i < 4; ++i) mbar_init(&res_full[i], 1);
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 16 * kCtas);  // one arrival per epilogue warp of every CTA of the pair
+    }
+    for (int i = 0; i < kSlabBufs; ++i) mbar_init(&res_full[i], 1);
     fence_barrier_init();
   }
   if (warp == 0 && lane == 0) {
@@ -114,97 +159,159 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     tma_prefetch_desc(&g.map_out);
   }
   if (warp == 1) {
-    tmem_alloc(tmem_holder, 512);
-    tmem_relinquish();
+    if (kCtas == 2) {
+      tmem_alloc_pair(tmem_holder, 512);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(tmem_holder, 512);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (kCtas == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
-  const int kblocks = g.n_taps * g.kb_per_tap;
+  const int tile0 = static_cast<int>(blockIdx.x) / kCtas;  // first (pair-)tile of this CTA
+  const int num_tiles = g.num_tiles;
 
   if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
-        const int nt = tile % g.n_tiles_n;
-        int c[4];
-        tile_coords(g, tile / g.n_tiles_n, c);
-        for (int tap = 0; tap < g.n_taps; ++tap) {
-          const int o0 = g.tap_off[tap][0];
-          const int c1 = c[0] + g.tap_off[tap][1], c2 = c[1] + g.tap_off[tap][2];
-          const int c3 = c[2] + g.tap_off[tap][3], c4 = c[3] + g.tap_off[tap][4];
-          for (int kb = 0; kb < g.kb_per_tap; ++kb) {
-            mbar_wait(&empty[stage], phase ^ 1u);
-            mbar_arrive_expect_tx(&full[stage], static_cast<uint32_t>(g.a_bytes + g.b_bytes));
-            tma_load_5d(sA + stage * kAStageBytes, &g.map_a, &full[stage], o0 + kb * 64, c1, c2, c3, c4);
-            const int kcoord = tap * g.b_k_tap_stride + kb * 64;
-            const int ncoord = nt * g.block_n + tap * g.b_n_tap_stride;
+    // ---- TMA producer: the whole warp walks the loop, one elected lane issues
+    int stage = 0;
+    uint32_t phase = 0;
+    const int n_taps = g.n_taps, kb_per_tap = g.kb_per_tap, block_n = g.block_n;
+    const int k_tap_stride = g.b_k_tap_stride, n_tap_stride = g.b_n_tap_stride;
+    const bool mn_major = g.b_mn_major != 0;
+    const uint32_t tx_bytes = static_cast<uint32_t>(kCtas) * static_cast<uint32_t>(g.a_bytes + g.b_bytes);
+    const bool skip_loads = (g.debug & 1) != 0;
+    TileIter it;
+    tile_init<kCtas>(g, it, tile0, static_cast<int>(cta_rank));
+    for (; it.tile < num_tiles; tile_advance(g, it)) {
+      if (lane == 0) trace_event(g, 1);  // producer: tile start
+      const int c0 = it.t0 * g.box[0], c1_ = it.t1 * g.box[1], c2_ = it.t2 * g.box[2], c3_ = it.t3 * g.box[3];
+      const int ncoord0 = it.nt * block_n + static_cast<int>(cta_rank) * b_rows;
+      for (int tap = 0; tap < n_taps; ++tap) {
+        const int o0 = g.tap_off[tap][0];
+        const int c1 = c0 + g.tap_off[tap][1], c2 = c1_ + g.tap_off[tap][2];
+        const int c3 = c2_ + g.tap_off[tap][3], c4 = c3_ + g.tap_off[tap][4];
+        const int ncoord = ncoord0 + tap * n_tap_stride;
+        for (int kb = 0; kb < kb_per_tap; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1u);
+          if (elect_one_sync()) {
+            const int kcoord = tap * k_tap_stride + kb * 64;
+            uint8_t* adst = sA + stage * kAStageBytes;
             uint8_t* bdst = sB + stage * b_stage_bytes;
-            if (!g.b_mn_major) {
-              tma_load_2d(bdst, &g.map_b, &full[stage], kcoord, ncoord);
+            if (skip_loads) {
+              if (cta_rank == 0) mbar_arrive(&full[stage]);
+            } else if (kCtas == 2) {
+              // both CTAs' bytes are counted on the leader's barrier (the leader's MMA warp is the only waiter)
+              if (cta_rank == 0) mbar_arrive_expect_tx(&full[stage], tx_bytes);
+              const uint32_t fbar = mapa_shared(smem_u32(&full[stage]), 0);
+              tma_load_5d_pair(adst, &g.map_a, fbar, o0 + kb * 64, c1, c2, c3, c4);
+              if (!mn_major) {
+                tma_load_2d_pair(bdst, &g.map_b, fbar, kcoord, ncoord);
+              } else {
+                for (int ch = 0; ch < b_rows / 64; ++ch)
+                  tma_load_2d_pair(bdst + ch * 8192, &g.map_b, fbar, ncoord + ch * 64, kcoord);
+              }
             } else {
-              for (int ch = 0; ch < g.block_n / 64; ++ch)
-                tma_load_2d(bdst + ch * 8192, &g.map_b, &full[stage], ncoord + ch * 64, kcoord);
-            }
-            if (++stage == stages) {
-              stage = 0;
-              phase ^= 1u;
+              mbar_arrive_expect_tx(&full[stage], tx_bytes);
+              tma_load_5d(adst, &g.map_a, &full[stage], o0 + kb * 64, c1, c2, c3, c4);
+              if (!mn_major) {
+                tma_load_2d(bdst, &g.map_b, &full[stage], kcoord, ncoord);
+              } else {
+                for (int ch = 0; ch < b_rows / 64; ++ch)
+                  tma_load_2d(bdst + ch * 8192, &g.map_b, &full[stage], ncoord + ch * 64, kcoord);
+              }
             }
           }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
-        mbar_wait(&tempty[acc], acc_phase ^ 1u);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc) * 256u;
-        for (int kb = 0; kb < kblocks; ++kb) {
-          mbar_wait(&full[stage], phase);
-          tc_fence_after();
-          const uint32_t a_addr = smem_u32(sA + stage * kAStageBytes);
-          const uint32_t b_addr = smem_u32(sB + stage * b_stage_bytes);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint64_t da = make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
-            const uint64_t db = g.b_mn_major ? make_smem_desc_sw128(b_addr + k * 2048, 8192, 1024)
-                                             : make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
-            umma_f16(d_tmem, da, db, g.idesc, (kb | k) != 0 ? 1u : 0u);
-          }
-          umma_commit(&empty[stage]);
+          __syncwarp();
           if (++stage == stages) {
             stage = 0;
             phase ^= 1u;
           }
         }
-        umma_commit(&tfull[acc]);
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+  } else if (warp == 1) {
+    // ---- MMA issuer (leader CTA of a pair only).  Shared-memory descriptors: the upper word is constant, the lower
+    // word is (address >> 4) | (LBO >> 4) << 16, so stage / k-step changes are plain adds on the lower word.
+    if (cta_rank == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      const bool mn_major = g.b_mn_major != 0;
+      const uint32_t idesc = g.idesc;
+      const uint32_t desc_hi = (1024u >> 4) | (1u << 14) | (2u << 29);  // SBO = 1024 B, version 1, SWIZZLE_128B
+      const uint32_t a_lo0 = ((smem_u32(sA) & 0x3FFFFu) >> 4) | (1u << 16);  // LBO (unused) = 16 B
+      const uint32_t b_lo0 = ((smem_u32(sB) & 0x3FFFFu) >> 4) | ((mn_major ? (8192u >> 4) : 1u) << 16);
+      const uint32_t b_kstep = mn_major ? (2048u >> 4) : (32u >> 4);  // 16 k: 16 rows of 128 B / 32 B along the row
+      const uint32_t b_stage16 = b_stage_bytes >> 4;
+      const bool skip_mma = (g.debug & 2) != 0;
+      const int kblocks = g.n_taps * g.kb_per_tap;
+      for (int tile = tile0; tile < num_tiles; tile += g.tile_step) {
+        if (lane == 0) trace_event(g, 2);  // MMA: waiting for the accumulator
+        mbar_wait(&tempty[acc], acc_phase ^ 1u);
+        tc_fence_after();
+        if (lane == 0) trace_event(g, 3);  // MMA: accumulator free, first k-block wait
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * g.block_n);
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          if (elect_one_sync()) {
+            const uint32_t a_lo = a_lo0 + static_cast<uint32_t>(stage) * (kAStageBytes >> 4);
+            const uint32_t b_lo = b_lo0 + static_cast<uint32_t>(stage) * b_stage16;
+            if (!skip_mma) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const uint64_t da = (static_cast<uint64_t>(desc_hi) << 32) | (a_lo + 2u * k);
+                const uint64_t db = (static_cast<uint64_t>(desc_hi) << 32) | (b_lo + b_kstep * k);
+                if (kCtas == 2)
+                  umma_f16_pair(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+                else
+                  umma_f16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+              }
+            }
+            if (kCtas == 2) umma_commit_pair(&empty[stage], 3); else umma_commit(&empty[stage]);
+          }
+          __syncwarp();
+          if (++stage == stages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        if (elect_one_sync()) {
+          if (kCtas == 2) umma_commit_pair(&tfull[acc], 3); else umma_commit(&tfull[acc]);
+        }
+        __syncwarp();
+        if (lane == 0) trace_event(g, 4);  // MMA: all k-blocks issued
+        if (++acc == g.n_acc) {
+          acc = 0;
+          acc_phase ^= 1u;
+        }
       }
     }
   } else {
-    // 16 epilogue warps in two groups of 8 (256 threads).  The tile's output is emitted as 32-column slabs: group 0
-    // takes the even slabs, group 1 the odd ones.  Per slab: [leader] wait until the group's staging buffer has been
-    // drained by the previous TMA store and kick the residual slab's TMA load -> named barrier -> every thread reads
-    // its 16 accumulator columns from TMEM, applies the epilogue and writes two 16-byte chunks of its row into the
-    // swizzled staging slab -> named barrier -> [leader] one TMA store of the slab.  Global traffic is therefore
-    // full-line bulk copies issued by the TMA engine (row mapping and edge clipping come from the tensor map), not
-    // 32 scattered 16-byte accesses per warp instruction.
-    const int q = warp & 3;            // this warp may only touch TMEM lanes [32q, 32q+32)
-    const int wi = warp - 2;           // 0..15
-    const int grp = wi >> 3;           // 0 / 1
-    const int usub = (wi >> 2) & 1;    // which 16-column half of the slab
-    const bool leader = (wi & 7) == 0 && lane == 0;
+    // ---- epilogue: 16 warps = 4 groups x 4 warps (one per TMEM lane quarter).  The tile's output is emitted as
+    // 32-column slabs, dealt round-robin to the groups ACROSS tiles (slab number tile_seq*nslabs + sl goes to group
+    // number mod 4), so 5-slab tiles (block_n = 160) still load the groups evenly.  Per slab a thread reads its row's
+    // 32 accumulator columns from TMEM, applies the epilogue and writes four 16-byte chunks into the group's staging
+    // slab (64-byte swizzle); one elected lane then issues ONE TMA store for the slab -- global traffic is full-line
+    // bulk copies with the row mapping and edge clipping done by the tensor map.  The residual is TMA-prefetched INTO
+    // the staging slab one slab ahead and added in place.  Two staging buffers per group: the store of slab s-1 drains
+    // while slab s is computed.
+    const int q = warp & 3;        // this warp may only touch TMEM lanes [32q, 32q+32)
+    const int grp = (warp - 2) >> 2;
+    const bool leader_warp = ((warp - 2) & 3) == 0;  // one elected lane of this warp issues the group's TMA traffic
     const int r = q * 32 + lane;
+    const bool geglu = kEpi == kEpiGeglu || (kEpi == kEpiGeneric && g.act == 2);
+    const bool has_res = kEpi == kEpiResidual || (kEpi == kEpiGeneric && g.residual != nullptr);
+    const bool has_rowvec = kEpi == kEpiGeneric && g.rowvec != nullptr;
+    const bool has_gamma = kEpi == kEpiGeneric && g.gamma != 1.0f;
+    const bool has_silu = kEpi == kEpiGeneric && g.act == 1;
+    const __half* const bias = g.bias;
     int j[4];
-    {
+    if (has_rowvec) {
       int t = r;
       j[0] = t % g.box[0];
       t /= g.box[0];
@@ -216,132 +323,200 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     }
     uint8_t* my_out = sOut + grp * 2 * kSlabBytes;  // two buffers, alternated per slab
     uint64_t* my_res_full = res_full + grp * 2;
-    // 64-byte swizzle: physical = logical ^ (((logical >> 7) & 3) << 4), logical = r*64 + chunk*16
+    // 64-byte swizzle: 16-byte chunk c of row r lives at r*64 + ((c ^ ((r >> 1) & 3)) << 4)
+    const uint32_t row_off = static_cast<uint32_t>(r * 64);
     const uint32_t sw = static_cast<uint32_t>((r >> 1) & 3);
-    const uint32_t off0 = static_cast<uint32_t>(r * 64) + (((static_cast<uint32_t>(usub * 2)) ^ sw) << 4);
-    const uint32_t off1 = static_cast<uint32_t>(r * 64) + (((static_cast<uint32_t>(usub * 2 + 1)) ^ sw) << 4);
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    const bool geglu = (g.act == 2);
-    const int nslabs = geglu ? 2 : g.block_n / 32;
+    const int block_n = g.block_n;
+    const int n_half = block_n >> 1;                  // GEGLU: tile = [n_half value columns | n_half gate columns]
+    const int out_cols = geglu ? n_half : block_n;    // output columns one tile produces
+    const int nslabs = out_cols / 32;
     const int bar_id = 1 + grp;
-    uint32_t seq = 0;  // slabs processed by this group so far: buffer = seq & 1, residual parity = (seq >> 1) & 1
-    auto issue_res = [&](int tile_, int sl_, uint32_t seq_) {  // leader only: TMA-load the residual slab (tile_, sl_)
-      int cc[4];
-      tile_coords(g, tile_ / g.n_tiles_n, cc);
-      const int gc = (geglu ? (tile_ % g.n_tiles_n) * 64 : (tile_ % g.n_tiles_n) * g.block_n) + sl_ * 32;
+    // the accumulator-drained signal goes to the leader CTA's barrier (the only MMA issuer of the pair)
+    const uint32_t tempty_addr0 = kCtas == 2 ? mapa_shared(smem_u32(&tempty[0]), 0) : smem_u32(&tempty[0]);
+    uint32_t seq = 0;   // slabs processed by this group: buffer = seq & 1, residual barrier parity = (seq >> 1) & 1
+    int acc = 0;        // accumulator stage of the current tile and its barrier parity
+    uint32_t acc_phase = 0;
+    const int n_acc = g.n_acc;
+    int first = grp;    // this group's first slab of the current tile
+    bool res_issued = false;  // the residual of the group's next slab is already on its way
+    TileIter it;
+    tile_init<kCtas>(g, it, tile0, static_cast<int>(cta_rank));
+    auto issue_res = [&](const TileIter& ti, int sl_, uint32_t seq_) {  // elected lane: TMA-load a residual slab
       mbar_arrive_expect_tx(&my_res_full[seq_ & 1], static_cast<uint32_t>(g.slab_bytes));
       // the residual lands in the slab's own output buffer: threads add to it in place
-      tma_load_5d(my_out + (seq_ & 1) * kSlabBytes, &g.map_res, &my_res_full[seq_ & 1], gc, cc[0], cc[1], cc[2], cc[3]);
+      tma_load_5d(my_out + (seq_ & 1) * kSlabBytes, &g.map_res, &my_res_full[seq_ & 1], ti.nt * out_cols + sl_ * 32,
+                  ti.t0 * g.box[0], ti.t1 * g.box[1], ti.t2 * g.box[2], ti.t3 * g.box[3]);
     };
-    if (leader && g.residual && blockIdx.x < g.num_tiles && grp < nslabs) issue_res(blockIdx.x, grp, 0);
-    for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
-      const int nt = tile % g.n_tiles_n;
-      int c[4];
-      tile_coords(g, tile / g.n_tiles_n, c);
-      bool valid = j[3] < g.box[3];
-      long long rvrow = 0;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int x = c[i] + j[i];
-        valid = valid && (x < g.out_dims[i]);
-        rvrow += static_cast<long long>(x) * g.rv_stride[i];
+    // The accumulator goes back to the MMA warp as soon as this warp has pulled its last columns of the tile out of
+    // TMEM -- before the slab is staged, fenced and stored (measured: releasing after the store made the MMA warp wait
+    // for the accumulator ~2/3 of the time on 5-k-block tiles).
+    auto release_acc = [&]() {
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (kCtas == 2) mbar_arrive_cluster(tempty_addr0 + 8u * acc); else mbar_arrive(&tempty[acc]);
       }
+    };
+    for (; it.tile < num_tiles; tile_advance(g, it), first = (first - nslabs) & 3) {
+      bool valid = false;
+      long long rvrow = 0;
+      if (has_rowvec) {
+        const int x0 = it.t0 * g.box[0] + j[0], x1 = it.t1 * g.box[1] + j[1];
+        const int x2 = it.t2 * g.box[2] + j[2], x3 = it.t3 * g.box[3] + j[3];
+        valid = j[3] < g.box[3] && x0 < g.out_dims[0] && x1 < g.out_dims[1] && x2 < g.out_dims[2] &&
+                x3 < g.out_dims[3];
+        rvrow = static_cast<long long>(x0) * g.rv_stride[0] + static_cast<long long>(x1) * g.rv_stride[1] +
+                static_cast<long long>(x2) * g.rv_stride[2] + static_cast<long long>(x3) * g.rv_stride[3];
+      }
+      if (leader_warp && lane == 0) trace_event(g, 16 + grp * 16 + 0);  // epilogue group: waiting for the tile
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + static_cast<uint32_t>(acc) * 256u + (static_cast<uint32_t>(q * 32) << 16);
-      for (int sl = grp; sl < nslabs; sl += 2, ++seq) {
-        const int gcol = (geglu ? nt * 64 : nt * g.block_n) + sl * 32;  // first global output column of the slab
+      if (leader_warp && lane == 0) trace_event(g, 16 + grp * 16 + 1);  // tile's accumulator complete
+      const uint32_t taddr = tmem_base + static_cast<uint32_t>(acc * block_n) + (static_cast<uint32_t>(q * 32) << 16);
+      if (first >= nslabs) release_acc();  // no slab of this tile falls to this group
+      for (int sl = first; sl < nslabs; sl += 4, ++seq) {
+        const int gcol = it.nt * out_cols + sl * 32;  // first global output column of the slab
         uint8_t* obuf = my_out + (seq & 1) * kSlabBytes;
-        const int ucol = sl * 32 + usub * 16;  // tile-relative column of this thread's 16-column unit
-        const int ocol = gcol + usub * 16;
-        uint32_t rv[16], rg[16];
-        tmem_ld16(taddr + ucol, rv);
-        if (geglu) tmem_ld16(taddr + 64 + ucol, rg);
-        tmem_ld_wait();
-        float v[2][8];
+        if (has_res && !res_issued && leader_warp) {  // no prefetch happened (first slab, or a slab-less tile between)
+          if (elect_one_sync()) issue_res(it, sl, seq);
+          __syncwarp();
+        }
+        res_issued = false;
+        uint4 packed[4];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i >> 3][i & 7] = __uint_as_float(rv[i]);
-        if (geglu) {
-          // value * gelu(gate); biases of the interleaved weight: value at tcol, gate at tcol + 64
-          const int tcol = nt * 128 + ucol;
-          float bv[2][8], bg[2][8];
-          if (g.bias) {
-            load8(g.bias + tcol, bv[0]);
-            load8(g.bias + tcol + 8, bv[1]);
-            load8(g.bias + tcol + 64, bg[0]);
-            load8(g.bias + tcol + 72, bg[1]);
+        for (int h = 0; h < 2; ++h) {  // two 16-column halves: bounds the live registers
+          const int ucol = sl * 32 + h * 16;  // tile-relative accumulator column
+          const int ocol = gcol + h * 16;     // global output column
+          uint32_t rv[16];
+          float v[16];
+          tmem_ld16(taddr + ucol, rv);
+          if (geglu) {
+            uint32_t rg[16];
+            tmem_ld16(taddr + n_half + ucol, rg);
+            // value * gelu(gate); biases of the interleaved weight: value at tcol, gate at tcol + n_half
+            const int tcol = it.nt * block_n + ucol;
+            float bv[16], bg[16];
+            if (bias) {
+              unpack8(*reinterpret_cast<const uint4*>(bias + tcol), *reinterpret_cast<float(*)[8]>(&bv[0]));
+              unpack8(*reinterpret_cast<const uint4*>(bias + tcol + 8), *reinterpret_cast<float(*)[8]>(&bv[8]));
+              unpack8(*reinterpret_cast<const uint4*>(bias + tcol + n_half), *reinterpret_cast<float(*)[8]>(&bg[0]));
+              unpack8(*reinterpret_cast<const uint4*>(bias + tcol + n_half + 8),
+                      *reinterpret_cast<float(*)[8]>(&bg[8]));
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) bv[i] = bg[i] = 0.f;
+            }
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              v[i] = (__uint_as_float(rv[i]) + bv[i]) * gelu_erf_f(__uint_as_float(rg[i]) + bg[i]);
           } else {
+            if (bias) {
+              float b[16];
+              unpack8(*reinterpret_cast<const uint4*>(bias + ocol), *reinterpret_cast<float(*)[8]>(&b[0]));
+              unpack8(*reinterpret_cast<const uint4*>(bias + ocol + 8), *reinterpret_cast<float(*)[8]>(&b[8]));
+              tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 16; ++i) bv[i >> 3][i & 7] = bg[i >> 3][i & 7] = 0.f;
+              for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(rv[i]) + b[i];
+            } else {
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(rv[i]);
+            }
+            if (has_silu) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = silu_f(round_h(v[i]));
+            }
           }
+          if (has_rowvec && valid) {
+            float t[16];
+            unpack8(*reinterpret_cast<const uint4*>(g.rowvec + rvrow * g.ld_rowvec + ocol),
+                    *reinterpret_cast<float(*)[8]>(&t[0]));
+            unpack8(*reinterpret_cast<const uint4*>(g.rowvec + rvrow * g.ld_rowvec + ocol + 8),
+                    *reinterpret_cast<float(*)[8]>(&t[8]));
 #pragma unroll
-          for (int i = 0; i < 16; ++i)
-            v[i >> 3][i & 7] = (v[i >> 3][i & 7] + bv[i >> 3][i & 7]) *
-                               gelu_erf_f(__uint_as_float(rg[i]) + bg[i >> 3][i & 7]);
-        } else {
-          if (g.bias) {
-            float b[2][8];
-            load8(g.bias + ocol, b[0]);
-            load8(g.bias + ocol + 8, b[1]);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i >> 3][i & 7] += b[i >> 3][i & 7];
+            for (int i = 0; i < 16; ++i) v[i] = round_h(v[i]) + t[i];
           }
-          if (g.act == 1) {
+          if (has_gamma) {
+            const float gm = g.gamma;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i >> 3][i & 7] = silu_f(round_h(v[i >> 3][i & 7]));
+            for (int i = 0; i < 16; ++i) v[i] = round_h(v[i]) * gm;
           }
-        }
-        if (g.rowvec && valid) {
-          float t[2][8];
-          load8(g.rowvec + rvrow * g.ld_rowvec + ocol, t[0]);
-          load8(g.rowvec + rvrow * g.ld_rowvec + ocol + 8, t[1]);
+          if (has_res) {
+            if (h == 0) mbar_wait(&my_res_full[seq & 1], (seq >> 1) & 1u);
+            float t[16];
+            unpack8(*reinterpret_cast<const uint4*>(obuf + row_off + (((2u * h) ^ sw) << 4)),
+                    *reinterpret_cast<float(*)[8]>(&t[0]));
+            unpack8(*reinterpret_cast<const uint4*>(obuf + row_off + (((2u * h + 1u) ^ sw) << 4)),
+                    *reinterpret_cast<float(*)[8]>(&t[8]));
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i >> 3][i & 7] = round_h(v[i >> 3][i & 7]) + t[i >> 3][i & 7];
+            for (int i = 0; i < 16; ++i) v[i] = round_h(v[i]) + t[i];
+          }
+          packed[2 * h] = pack8(&v[0]);
+          packed[2 * h + 1] = pack8(&v[8]);
         }
-        if (g.gamma != 1.0f) {
-          const float gm = g.gamma;
+        if (sl + 4 >= nslabs) release_acc();  // this warp's last TMEM reads of the tile have completed
+        if (leader_warp && lane == 0) trace_event(g, 16 + grp * 16 + 2);  // slab math done
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i >> 3][i & 7] = round_h(v[i >> 3][i & 7]) * gm;
-        }
-        if (g.residual) {
-          mbar_wait(&my_res_full[seq & 1], (seq >> 1) & 1u);
-          float t[2][8];
-          load8(reinterpret_cast<const __half*>(obuf + off0), t[0]);
-          load8(reinterpret_cast<const __half*>(obuf + off1), t[1]);
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i >> 3][i & 7] = round_h(v[i >> 3][i & 7]) + t[i >> 3][i & 7];
-        }
-        store8(reinterpret_cast<__half*>(obuf + off0), v[0]);
-        store8(reinterpret_cast<__half*>(obuf + off1), v[1]);
+        for (int cidx = 0; cidx < 4; ++cidx)
+          *reinterpret_cast<uint4*>(obuf + row_off + ((static_cast<uint32_t>(cidx) ^ sw) << 4)) = packed[cidx];
         fence_proxy_async_smem();
-        // the other output buffer must have been drained (store seq-1) before anyone writes it in the next slab
-        if (leader) bulk_wait_read_all();
-        named_bar_sync(bar_id, 256);
-        if (leader) {
-          tma_store_5d(&g.map_out, obuf, gcol, c[0], c[1], c[2], c[3]);
-          bulk_commit_group();
-          if (g.residual) {  // prefetch the residual of this group's next slab (same tile, or the next tile's first)
-            if (sl + 2 < nslabs) {
-              issue_res(tile, sl + 2, seq + 1);
-            } else if (tile + static_cast<int>(gridDim.x) < g.num_tiles) {
-              issue_res(tile + static_cast<int>(gridDim.x), grp, seq + 1);
+        // the group's other buffer must have been drained (store seq-1) before anyone writes it in the next slab
+        if (leader_warp) {
+          if (elect_one_sync()) bulk_wait_read_all();
+          __syncwarp();
+        }
+        if (leader_warp && lane == 0) trace_event(g, 16 + grp * 16 + 3);  // fence + previous store drained
+        named_bar_sync(bar_id, 128);
+        if (leader_warp && lane == 0) trace_event(g, 16 + grp * 16 + 4);  // group barrier passed
+        if (leader_warp) {
+          if (elect_one_sync()) {  // elect.sync is deterministic: the same lane owns the bulk async-groups throughout
+            tma_store_5d(&g.map_out, obuf, gcol, it.t0 * g.box[0], it.t1 * g.box[1], it.t2 * g.box[2],
+                         it.t3 * g.box[3]);
+            bulk_commit_group();
+          }
+          __syncwarp();
+        }
+        if (has_res) {  // prefetch the residual of this group's next slab: same tile, or the next tile's first slab
+          if (sl + 4 < nslabs) {
+            if (leader_warp) {
+              if (elect_one_sync()) issue_res(it, sl + 4, seq + 1);
+              __syncwarp();
+            }
+            res_issued = true;
+          } else {
+            const int nf = (first - nslabs) & 3;
+            if (nf < nslabs && it.tile + g.tile_step < num_tiles) {
+              if (leader_warp) {
+                if (elect_one_sync()) {
+                  TileIter nx = it;
+                  tile_advance(g, nx);
+                  issue_res(nx, nf, seq + 1);
+                }
+                __syncwarp();
+              }
+              res_issued = true;
             }
           }
         }
       }
-      tc_fence_before();
-      mbar_arrive(&tempty[acc]);
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1u;
+      if (leader_warp && lane == 0) trace_event(g, 16 + grp * 16 + 5);  // tile done
+      if (++acc == n_acc) {
+        acc = 0;
+        acc_phase ^= 1u;
+      }
     }
-    if (leader) bulk_wait_all();  // the staging slabs must outlive the last store's reads
+    if (leader_warp) {  // the staging slabs must outlive the last store's reads
+      if (elect_one_sync()) bulk_wait_all();
+      __syncwarp();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  // the peer's shared memory / TMEM / barriers must stay alive until the pair's last MMA and commit have landed
+  if (kCtas == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    if (kCtas == 2) tmem_dealloc_pair(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -354,9 +529,10 @@ static int launch_gemm(const lvd_gemm_desc* d, cudaStream_t stream) {
               d->k_per_tap);
   LVD_REQUIRE(d->n_taps >= 1 && d->n_taps <= LVD_MAX_TAPS, "lvd_gemm: n_taps=%d", d->n_taps);
   LVD_REQUIRE(d->act >= 0 && d->act <= 2, "lvd_gemm: act=%d", d->act);
-  LVD_REQUIRE(d->act != 2 || d->block_n == 128, "lvd_gemm: GEGLU needs block_n == 128");
+  LVD_REQUIRE(d->act != 2 || d->block_n == 128 || d->block_n == 256, "lvd_gemm: GEGLU needs block_n 128 or 256");
   LVD_REQUIRE(!d->b_mn_major || d->block_n % 64 == 0, "lvd_gemm: MN-major B needs block_n %% 64 == 0");
   LVD_REQUIRE(d->a_box[0] == 64, "lvd_gemm: a_box[0] must be 64");
+  LVD_REQUIRE(d->cta_pair >= 0 && d->cta_pair <= 2, "lvd_gemm: cta_pair=%d", d->cta_pair);
   long long rows = 1;
   for (int i = 1; i < 5; ++i) rows *= d->a_box[i];
   LVD_REQUIRE(rows >= 1 && rows <= 128, "lvd_gemm: tile has %lld rows (max 128)", rows);
@@ -365,23 +541,6 @@ static int launch_gemm(const lvd_gemm_desc* d, cudaStream_t stream) {
 
   GemmArgs g;
   memset(&g, 0, sizeof(g));
-  int rc = encode_tmap_f16_sw128(&g.map_a, d->a, 5, d->a_dims, d->a_strides, d->a_box);
-  if (rc) return rc;
-  const int k_tap_stride = (d->b_k_tap_stride == 0 && d->b_n_tap_stride == 0) ? d->k_per_tap : d->b_k_tap_stride;
-  const long long k_total = static_cast<long long>(d->n_taps - 1) * k_tap_stride + d->k_per_tap;
-  const long long n_total = static_cast<long long>(d->n_taps - 1) * d->b_n_tap_stride + d->n;
-  if (!d->b_mn_major) {
-    int64_t dims[2] = {k_total, n_total};
-    int64_t str[2] = {1, d->ldb};
-    int box[2] = {64, d->block_n};
-    rc = encode_tmap_f16_sw128(&g.map_b, d->b, 2, dims, str, box);
-  } else {
-    int64_t dims[2] = {n_total, k_total};
-    int64_t str[2] = {1, d->ldb};
-    int box[2] = {64, 64};
-    rc = encode_tmap_f16_sw128(&g.map_b, d->b, 2, dims, str, box);
-  }
-  if (rc) return rc;
   long long m_tiles = 1;
   for (int i = 0; i < 4; ++i) {
     g.box[i] = d->a_box[i + 1];
@@ -390,8 +549,35 @@ static int launch_gemm(const lvd_gemm_desc* d, cudaStream_t stream) {
     g.ntile[i] = (d->out_dims[i] + g.box[i] - 1) / g.box[i];
     m_tiles *= g.ntile[i];
     g.rv_stride[i] = d->rv_stride[i];
-    g.out_row_stride[i] = d->out_row_stride[i];
   }
+  // CTA pairs (2-CTA clusters, cta_group::2 MMA with M = 256): each SM stages only half of every B tile.  Measured on
+  // the Zeroscope shapes (tools/perf_gemm_shapes.py): +4..15% from K = 640 up, but -5..15% on the 5-k-block GEMMs
+  // (K = 320), which are bound by the output write and lose from coupling two CTAs' epilogues.  MN-major B is staged
+  // in 64-column chunks, so its half tile must be a multiple of 64.
+  const long long k_contract = static_cast<long long>(d->n_taps) * d->k_per_tap;
+  const bool pair_ok = m_tiles >= 2 && (!d->b_mn_major || d->block_n % 128 == 0);
+  LVD_REQUIRE(d->cta_pair != 2 || pair_ok, "lvd_gemm: cta_pair=2 needs >= 2 row tiles (MN-major B: block_n %% 128 == 0)");
+  const bool pair = d->cta_pair == 2 || (d->cta_pair == 0 && pair_ok && k_contract >= 640);
+  const int ctas = pair ? 2 : 1;
+  const int b_rows = d->block_n / ctas;
+
+  int rc = encode_tmap_f16_sw128(&g.map_a, d->a, 5, d->a_dims, d->a_strides, d->a_box);
+  if (rc) return rc;
+  const int k_tap_stride = (d->b_k_tap_stride == 0 && d->b_n_tap_stride == 0) ? d->k_per_tap : d->b_k_tap_stride;
+  const long long k_total = static_cast<long long>(d->n_taps - 1) * k_tap_stride + d->k_per_tap;
+  const long long n_total = static_cast<long long>(d->n_taps - 1) * d->b_n_tap_stride + d->n;
+  if (!d->b_mn_major) {
+    int64_t dims[2] = {k_total, n_total};
+    int64_t str[2] = {1, d->ldb};
+    int box[2] = {64, b_rows};
+    rc = encode_tmap_f16_sw128(&g.map_b, d->b, 2, dims, str, box);
+  } else {
+    int64_t dims[2] = {n_total, k_total};
+    int64_t str[2] = {1, d->ldb};
+    int box[2] = {64, 64};
+    rc = encode_tmap_f16_sw128(&g.map_b, d->b, 2, dims, str, box);
+  }
+  if (rc) return rc;
   for (int t = 0; t < d->n_taps; ++t)
     for (int i = 0; i < 5; ++i) g.tap_off[t][i] = d->tap_off[t][i];
   g.n_taps = d->n_taps;
@@ -402,11 +588,27 @@ static int launch_gemm(const lvd_gemm_desc* d, cudaStream_t stream) {
   g.b_k_tap_stride = k_tap_stride;
   g.b_n_tap_stride = d->b_n_tap_stride;
   g.act = d->act;
-  LVD_REQUIRE(m_tiles * g.n_tiles_n < (1ll << 30), "lvd_gemm: too many tiles");
-  g.num_tiles = static_cast<int>(m_tiles * g.n_tiles_n);
+  const long long row_tiles = pair ? (m_tiles + 1) / 2 : m_tiles;  // an odd tail tile is paired with an all-OOB tile
+  LVD_REQUIRE(row_tiles * g.n_tiles_n < (1ll << 30), "lvd_gemm: too many tiles");
+  g.num_tiles = static_cast<int>(row_tiles * g.n_tiles_n);
   g.a_bytes = static_cast<int>(rows) * 128;
-  g.b_bytes = d->block_n * 128;
+  g.b_bytes = b_rows * 128;
   g.slab_bytes = static_cast<int>(rows) * 64;
+  g.n_acc = 512 / d->block_n > 4 ? 4 : 512 / d->block_n;
+  // grid and the mixed-radix step of the persistent tile walk
+  const int max_units = pair ? num_sms() / 2 : num_sms();
+  const int units = g.num_tiles < max_units ? g.num_tiles : max_units;  // CTAs, or CTA pairs
+  g.tile_step = units;
+  g.step_nt = units % g.n_tiles_n;
+  for (int hi = 0; hi < 2; ++hi) {
+    long long delta = static_cast<long long>(ctas) * (units / g.n_tiles_n + hi);
+    int* e = hi ? g.step_hi : g.step_lo;
+    for (int i = 0; i < 3; ++i) {
+      e[i] = static_cast<int>(delta % g.ntile[i]);
+      delta /= g.ntile[i];
+    }
+    e[3] = static_cast<int>(delta);
+  }
   {
     // output / residual as rank-5 tensors whose axes 1..4 are the tile axes: stride_i = out_row_stride[i] * ld
     const int n_out = d->act == 2 ? d->n / 2 : d->n;
@@ -429,28 +631,55 @@ static int launch_gemm(const lvd_gemm_desc* d, cudaStream_t stream) {
     }
   }
   const int stage_bytes = kAStageBytes + g.b_bytes;
-  const int n_slabs_smem = 4;
-  int stages = (kSmemLimit - 1024 - 256 - n_slabs_smem * kSlabBytes) / stage_bytes;
+  const int n_slabs_smem = kSlabBufs;
+  int stages = (kSmemLimit - 1024 - kBarrierBytes - n_slabs_smem * kSlabBytes) / stage_bytes;
   if (stages > 8) stages = 8;
+  {  // tuning aid (tools/perf_gemm_sweep.py): cap the ring depth
+    static const char* env = getenv("LVD_GEMM_STAGES");
+    if (env && atoi(env) >= 2 && atoi(env) < stages) stages = atoi(env);
+  }
   g.stages = stages;
+  {
+    static const char* env = getenv("LVD_GEMM_DEBUG");
+    g.debug = env ? atoi(env) : 0;
+  }
   g.bias = static_cast<const __half*>(d->bias);
   g.rowvec = static_cast<const __half*>(d->rowvec);
   g.residual = static_cast<const __half*>(d->residual);
-  g.out = static_cast<__half*>(d->out);
   g.ld_rowvec = d->ld_rowvec;
-  g.ld_res = d->ld_res;
-  g.ld_out = d->ld_out;
   g.gamma = d->gamma;
-  g.idesc = make_idesc_f16(128, static_cast<uint32_t>(d->block_n), 0, d->b_mn_major ? 1u : 0u);
+  g.idesc = make_idesc_f16(128u * ctas, static_cast<uint32_t>(d->block_n), 0, d->b_mn_major ? 1u : 0u);
 
-  const int smem_bytes = 1024 + stages * stage_bytes + n_slabs_smem * kSlabBytes + 256;
+  const int smem_bytes = 1024 + stages * stage_bytes + n_slabs_smem * kSlabBytes + kBarrierBytes;
+  const bool plain = d->rowvec == nullptr && d->gamma == 1.0f;
+  int epi = kEpiGeneric;
+  if (plain && d->act == 2 && !d->residual) epi = kEpiGeglu;
+  if (plain && d->act == 0) epi = d->residual ? kEpiResidual : kEpiBias;
+  typedef void (*KernelFn)(const GemmArgs);
+  static const KernelFn kernels[2][4] = {
+      {gemm_tc_kernel<1, 0>, gemm_tc_kernel<1, 1>, gemm_tc_kernel<1, 2>, gemm_tc_kernel<1, 3>},
+      {gemm_tc_kernel<2, 0>, gemm_tc_kernel<2, 1>, gemm_tc_kernel<2, 2>, gemm_tc_kernel<2, 3>}};
   static bool attr_set = false;
   if (!attr_set) {
-    LVD_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+    for (int i = 0; i < 2; ++i)
+      for (int j = 0; j < 4; ++j)
+        LVD_CHECK_CUDA(cudaFuncSetAttribute(kernels[i][j], cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
     attr_set = true;
   }
-  int grid = g.num_tiles < num_sms() ? g.num_tiles : num_sms();
-  gemm_tc_kernel<<<grid, kThreads, smem_bytes, stream>>>(g);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(static_cast<unsigned>(ctas * units));
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = static_cast<unsigned>(ctas);
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  LVD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kernels[ctas - 1][epi], g));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   LVD_CHECK_CUDA(cudaGetLastError());
   return LVD_OK;
@@ -460,6 +689,17 @@ static int launch_gemm(const lvd_gemm_desc* d, cudaStream_t stream) {
 
 extern "C" int lvd_gemm(const lvd_gemm_desc* d, void* stream) {
   return lvd::launch_gemm(d, static_cast<cudaStream_t>(stream));
+}
+// tools/trace_gemm.py: copy out (and reset) the timeline CTA 0 recorded under LVD_GEMM_DEBUG=64
+extern "C" int lvd_debug_trace_read(unsigned long long* host_buf, int max_events) {
+  unsigned int n = 0;
+  if (cudaMemcpyFromSymbol(&n, lvd::g_trace_n, sizeof(n)) != cudaSuccess) return -1;
+  if (n > 8192u) n = 8192u;
+  if (static_cast<int>(n) > max_events) n = static_cast<unsigned>(max_events);
+  if (n && cudaMemcpyFromSymbol(host_buf, lvd::g_trace, n * sizeof(unsigned long long)) != cudaSuccess) return -1;
+  unsigned int zero = 0;
+  cudaMemcpyToSymbol(lvd::g_trace_n, &zero, sizeof(zero));
+  return static_cast<int>(n);
 }
 extern "C" int lvd_version(void) { return 1; }
 extern "C" int64_t lvd_launch_count(void) { return lvd::g_launches.load(); }

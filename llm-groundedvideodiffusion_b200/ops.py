@@ -18,14 +18,17 @@ _NUM_SMS = 148  # B200
 # Optional per-launch instrumentation (bench.py's roofline pass): when PROF is a list, every launch appends
 # (kernel family, algorithmic flops, algorithmic bytes, start event, end event) recorded on the launching stream.
 PROF = None
+FORCE_BLOCK_N = None  # tools/perf_gemm_sweep.py only: override the tile width of every lvd_gemm launch
+FORCE_CTA_PAIR = 0    # 0 auto / 1 single-CTA tiles / 2 CTA pairs (tests and tools/perf_gemm_sweep.py)
+GEGLU_HALF = 128      # value/gate interleave granularity of GEGLU projections (repack.geglu_interleave)
 
 
 class _Timed:
-    def __init__(self, family, flops=0.0, nbytes=0.0):
+    def __init__(self, family, flops=0.0, nbytes=0.0, tag=None):
         self.rec = None
         if PROF is not None:
             self.rec = [family, float(flops), float(nbytes), torch.cuda.Event(enable_timing=True),
-                        torch.cuda.Event(enable_timing=True)]
+                        torch.cuda.Event(enable_timing=True), tag]
 
     def __enter__(self):
         if self.rec is not None:
@@ -57,7 +60,7 @@ def _check_act(t, name="tensor"):
 
 def pick_block_n(n, act=ACT_NONE, mn_major=False):
     if act == ACT_GEGLU:
-        return 128
+        return 2 * GEGLU_HALF
     for bn in ((256, 128, 64) if mn_major else (256, 160, 128, 64)):
         if n % bn == 0:
             return bn
@@ -112,7 +115,7 @@ def gemm_raw(*, a, a_dims, a_strides, a_box, taps, k_per_tap, w, n, out, out_dim
     d.b = w.data_ptr()
     d.b_mn_major = 1 if b_mn_major else 0
     if block_n is None:
-        block_n = pick_block_n(n, act, b_mn_major)
+        block_n = FORCE_BLOCK_N or pick_block_n(n, act, b_mn_major)
     d.block_n = int(block_n)
     d.ldb = int(ldb if ldb is not None else w.stride(0))
     d.n = int(n)
@@ -131,6 +134,7 @@ def gemm_raw(*, a, a_dims, a_strides, a_box, taps, k_per_tap, w, n, out, out_dim
     d.gamma = float(gamma)
     d.b_k_tap_stride = int(b_k_tap_stride)
     d.b_n_tap_stride = int(b_n_tap_stride)
+    d.cta_pair = int(FORCE_CTA_PAIR)
     if PROF is not None:
         m = 1
         for v in out_dims:
@@ -138,7 +142,9 @@ def gemm_raw(*, a, a_dims, a_strides, a_box, taps, k_per_tap, w, n, out, out_dim
         kt = len(taps) * int(k_per_tap)
         n_out = n // 2 if act == ACT_GEGLU else n
         nbytes = 2.0 * (m * int(k_per_tap) + n * kt + m * n_out * (2 if residual is not None else 1))
-        with _Timed("gemm_tc_kernel", 2.0 * m * n * kt, nbytes):
+        tag = "m%d n%d k%d taps%d act%d res%d mn%d bn%d" % (m, n, int(k_per_tap), len(taps), act,
+                                                           residual is not None, bool(b_mn_major), block_n)
+        with _Timed("gemm_tc_kernel", 2.0 * m * n * kt, nbytes, tag):
             _lib.check(_lib.lib().lvd_gemm(ctypes.byref(d), _stream()), "gemm")
         return out
     _lib.check(_lib.lib().lvd_gemm(ctypes.byref(d), _stream()), "gemm")

@@ -15,18 +15,18 @@ def tconv_weight(w):
     return w.reshape(co, ci, kt).permute(0, 2, 1).reshape(co, kt * ci).contiguous()
 
 
-def geglu_interleave(w, b):
-    """GEGLU proj weight (8C, C) = [value rows | gate rows] -> rows regrouped per 64 so that every 128-row block is
-    [64 value rows | the matching 64 gate rows]; the GEMM epilogue then multiplies value * gelu(gate) in-tile
-    (models/attention.py:355-376)."""
+def geglu_interleave(w, b, half=128):
+    """GEGLU proj weight (8C, C) = [value rows | gate rows] -> rows regrouped per `half` so that every 2*half-row
+    block is [half value rows | the matching half gate rows]; the GEMM epilogue (block_n = 2*half) then multiplies
+    value * gelu(gate) in-tile (models/attention.py:355-376)."""
     n2, k = w.shape
     n = n2 // 2
-    assert n % 64 == 0
-    wv, wg = w[:n].reshape(n // 64, 64, k), w[n:].reshape(n // 64, 64, k)
+    assert n % half == 0
+    wv, wg = w[:n].reshape(n // half, half, k), w[n:].reshape(n // half, half, k)
     wi = torch.cat([wv, wg], dim=1).reshape(n2, k).contiguous()
     bi = None
     if b is not None:
-        bv, bg = b[:n].reshape(n // 64, 64), b[n:].reshape(n // 64, 64)
+        bv, bg = b[:n].reshape(n // half, half), b[n:].reshape(n // half, half)
         bi = torch.cat([bv, bg], dim=1).reshape(n2).contiguous()
     return wi, bi
 

@@ -107,8 +107,9 @@ def test_geglu_fwd_bwd(cuda):
     rows, c = 200, 128
     pre_ref = _rand((rows, 8 * c), cuda, seed=22)                    # reference order: [value | gate]
     n = 4 * c
-    wv = pre_ref[:, :n].reshape(rows, n // 64, 64)
-    wg = pre_ref[:, n:].reshape(rows, n // 64, 64)
+    hf = ops.GEGLU_HALF
+    wv = pre_ref[:, :n].reshape(rows, n // hf, hf)
+    wg = pre_ref[:, n:].reshape(rows, n // hf, hf)
     pre = torch.cat([wv, wg], dim=2).reshape(rows, 2 * n).contiguous()  # interleaved like repack.geglu_interleave
     dout = _rand((rows, n), cuda, seed=23)
     out = ops.geglu(pre)
@@ -116,8 +117,8 @@ def test_geglu_fwd_bwd(cuda):
     assert rel_err(out, ref) < TOL
     g = _grad(lambda t: t[:, :n] * F.gelu(t[:, n:]), pre_ref, dout)
     dpre = ops.geglu_bwd(pre, dout)
-    gv = dpre.reshape(rows, n // 64, 128)[:, :, :64].reshape(rows, n)
-    gg = dpre.reshape(rows, n // 64, 128)[:, :, 64:].reshape(rows, n)
+    gv = dpre.reshape(rows, n // hf, 2 * hf)[:, :, :hf].reshape(rows, n)
+    gg = dpre.reshape(rows, n // hf, 2 * hf)[:, :, hf:].reshape(rows, n)
     assert rel_err(gv, g[:, :n]) < TOL and rel_err(gg, g[:, n:]) < TOL
 
 

@@ -10,6 +10,16 @@ pytestmark = pytest.mark.gpu
 TOL = 2e-3
 
 
+@pytest.fixture(autouse=True, params=["auto", "single_cta"])
+def cta_mode(request):
+    """Every case runs through both instantiations of the kernel: CTA pairs (cta_group::2, picked automatically when a
+    problem has >= 2 row tiles) and one CTA per tile."""
+    from lvd_b200 import ops
+    ops.FORCE_CTA_PAIR = 1 if request.param == "single_cta" else 0
+    yield
+    ops.FORCE_CTA_PAIR = 0
+
+
 def _rand(shape, dev, scale=1.0, seed=0):
     g = torch.Generator(device="cpu").manual_seed(seed)
     return (torch.randn(shape, generator=g) * scale).to(dev).half()
