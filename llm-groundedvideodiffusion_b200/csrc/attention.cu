@@ -100,49 +100,66 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid
   const uint32_t tmem_s = tmem_base, tmem_o = tmem_base + 128;
   const int zk = z / g.kv_z_div;
 
+  // producer and MMA warps: every lane walks the loop, one elected lane issues -- under `if (lane == 0)` each
+  // UTMALDG / UTCHMMA is wrapped in an ELECT / R2UR.BROADCAST retry loop (~45 ns per tcgen05.mma; see ptx.cuh)
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one_sync()) {
       mbar_arrive_expect_tx(q_full, static_cast<uint32_t>(g.q_bytes));
       tma_load_4d(sQ, &g.map_q, q_full, g.q_col0 + h * 64, qt * g.qb1, 0, z);
-      for (int u = 0; u < g.n_units; ++u) {
-        const int st = u & 1;
-        mbar_wait(&kv_empty[st], ((u >> 1) & 1) ^ 1u);
+    }
+    __syncwarp();
+    const int n_units = g.n_units;
+    for (int u = 0; u < n_units; ++u) {
+      const int st = u & 1;
+      mbar_wait(&kv_empty[st], ((u >> 1) & 1) ^ 1u);
+      if (elect_one_sync()) {
         mbar_arrive_expect_tx(&kv_full[st], static_cast<uint32_t>(2 * g.kv_bytes));
         const int c1 = g.kv_same_tile ? qt * g.qb1 : u * 128;
         tma_load_4d(sK + st * kTile, &g.map_kv, &kv_full[st], g.k_col0 + h * 64, c1, 0, zk);
         tma_load_4d(sV + st * kTile, &g.map_kv, &kv_full[st], g.v_col0 + h * 64, c1, 0, zk);
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      mbar_wait(q_full, 0);
-      const uint32_t q_addr = smem_u32(sQ);
-      const uint32_t p_addr = smem_u32(sP);
-      for (int u = 0; u < g.n_units; ++u) {
-        const int st = u & 1;
-        const bool last = (u == g.n_units - 1);
-        const int ncols = last ? g.last_cols16 : 128;
-        mbar_wait(&kv_full[st], (u >> 1) & 1);
-        tc_fence_after();
-        const uint32_t k_addr = smem_u32(sK + st * kTile);
-        const uint32_t v_addr = smem_u32(sV + st * kTile);
-        const uint32_t idesc_qk = last ? g.idesc_qk_last : g.idesc_qk_full;
+    mbar_wait(q_full, 0);
+    // descriptors: constant upper word (SBO 1024 B, version 1, 128-byte swizzle), lower word = address >> 4 | LBO >> 4 << 16
+    const uint32_t desc_hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+    const uint32_t q_lo = ((smem_u32(sQ) & 0x3FFFFu) >> 4) | (1u << 16);
+    const uint32_t p_lo = ((smem_u32(sP) & 0x3FFFFu) >> 4) | (1u << 16);
+    const uint32_t k_lo0 = ((smem_u32(sK) & 0x3FFFFu) >> 4) | (1u << 16);
+    const uint32_t v_lo0 = ((smem_u32(sV) & 0x3FFFFu) >> 4) | ((8192u >> 4) << 16);  // V is MN-major: [kv][d]
+    const int n_units = g.n_units;
+    const uint32_t idesc_pv = g.idesc_pv;
+    for (int u = 0; u < n_units; ++u) {
+      const int st = u & 1;
+      const bool last = (u == n_units - 1);
+      const int ksteps = (last ? g.last_cols16 : 128) / 16;
+      const uint32_t idesc_qk = last ? g.idesc_qk_last : g.idesc_qk_full;
+      mbar_wait(&kv_full[st], (u >> 1) & 1);
+      tc_fence_after();
+      if (elect_one_sync()) {
+        const uint32_t k_lo = k_lo0 + static_cast<uint32_t>(st) * (kTile >> 4);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          umma_f16(tmem_s, make_smem_desc_sw128(q_addr + k * 32, 16, 1024),
-                   make_smem_desc_sw128(k_addr + k * 32, 16, 1024), idesc_qk, k != 0 ? 1u : 0u);
+          umma_f16(tmem_s, (static_cast<uint64_t>(desc_hi) << 32) | (q_lo + 2u * k),
+                   (static_cast<uint64_t>(desc_hi) << 32) | (k_lo + 2u * k), idesc_qk, k != 0 ? 1u : 0u);
         umma_commit(s_full);
-        mbar_wait(p_full, u & 1);
-        tc_fence_after();
-        const int ksteps = ncols / 16;
+      }
+      __syncwarp();
+      mbar_wait(p_full, u & 1);
+      tc_fence_after();
+      if (elect_one_sync()) {
+        const uint32_t v_lo = v_lo0 + static_cast<uint32_t>(st) * (kTile >> 4);
         for (int ks = 0; ks < ksteps; ++ks) {
-          const uint64_t da = make_smem_desc_sw128(p_addr + (ks >> 2) * kTile + (ks & 3) * 32, 16, 1024);
-          const uint64_t db = make_smem_desc_sw128(v_addr + ks * 2048, 8192, 1024);  // V is MN-major: [kv][d]
-          umma_f16(tmem_o, da, db, g.idesc_pv, ks != 0 ? 1u : 0u);
+          const uint64_t da = (static_cast<uint64_t>(desc_hi) << 32) |
+                              (p_lo + static_cast<uint32_t>((ks >> 2) * (kTile >> 4) + (ks & 3) * 2));
+          const uint64_t db = (static_cast<uint64_t>(desc_hi) << 32) | (v_lo + static_cast<uint32_t>(ks) * (2048u >> 4));
+          umma_f16(tmem_o, da, db, idesc_pv, ks != 0 ? 1u : 0u);
         }
         umma_commit(o_full);
         umma_commit(&kv_empty[st]);
       }
+      __syncwarp();
     }
   } else {
     const int q = warp & 3;

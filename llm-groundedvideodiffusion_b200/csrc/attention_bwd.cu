@@ -91,31 +91,39 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_dq_kernel(const __gri
   const uint32_t tm_s = tmem_base, tm_dp = tmem_base + 128, tm_dq = tmem_base + 256;
   const int row0 = z * g.S;  // first row of this image in the row buffers
 
+  // producer / MMA warps: all lanes walk the loops, one elected lane issues (no ELECT/R2UR retry loops, see ptx.cuh)
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one_sync()) {
       mbar_arrive_expect_tx(q_full, 2 * kT);
       tma_load_2d(sQ, &g.map_qkv, q_full, g.q_col0 + h * 64, row0 + qt * 128);
       tma_load_2d(sDO, &g.map_do, q_full, h * 64, row0 + qt * 128);
-      for (int u = 0; u < g.n_units; ++u) {
-        const int st = u & 1;
-        mbar_wait(&kv_empty[st], ((u >> 1) & 1) ^ 1u);
+    }
+    __syncwarp();
+    const int n_units = g.n_units;
+    for (int u = 0; u < n_units; ++u) {
+      const int st = u & 1;
+      mbar_wait(&kv_empty[st], ((u >> 1) & 1) ^ 1u);
+      if (elect_one_sync()) {
         mbar_arrive_expect_tx(&kv_full[st], 2 * kT);
         tma_load_2d(sK + st * kT, &g.map_qkv, &kv_full[st], g.k_col0 + h * 64, row0 + u * 128);
         tma_load_2d(sV + st * kT, &g.map_qkv, &kv_full[st], g.v_col0 + h * 64, row0 + u * 128);
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      mbar_wait(q_full, 0);
-      const uint32_t q_addr = smem_u32(sQ), do_addr = smem_u32(sDO), ds_addr = smem_u32(sDS);
-      for (int u = 0; u < g.n_units; ++u) {
-        const int st = u & 1;
-        const bool last = (u == g.n_units - 1);
-        const int ncols = last ? g.last_cols16 : 128;
-        const uint32_t idesc_s = last ? g.idesc_s_last : g.idesc_s_full;
-        mbar_wait(&kv_full[st], (u >> 1) & 1);
-        tc_fence_after();
-        const uint32_t k_addr = smem_u32(sK + st * kT), v_addr = smem_u32(sV + st * kT);
+    mbar_wait(q_full, 0);
+    const uint32_t q_addr = smem_u32(sQ), do_addr = smem_u32(sDO), ds_addr = smem_u32(sDS);
+    const int n_units = g.n_units;
+    const uint32_t idesc_dq = g.idesc_dq;
+    for (int u = 0; u < n_units; ++u) {
+      const int st = u & 1;
+      const bool last = (u == n_units - 1);
+      const int ncols = last ? g.last_cols16 : 128;
+      const uint32_t idesc_s = last ? g.idesc_s_last : g.idesc_s_full;
+      mbar_wait(&kv_full[st], (u >> 1) & 1);
+      tc_fence_after();
+      const uint32_t k_addr = smem_u32(sK + st * kT), v_addr = smem_u32(sV + st * kT);
+      if (elect_one_sync()) {
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           umma_f16(tm_s, make_smem_desc_sw128(q_addr + k * 32, 16, 1024),
@@ -125,14 +133,18 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_dq_kernel(const __gri
           umma_f16(tm_dp, make_smem_desc_sw128(do_addr + k * 32, 16, 1024),
                    make_smem_desc_sw128(v_addr + k * 32, 16, 1024), idesc_s, k != 0 ? 1u : 0u);
         umma_commit(sdp_full);
-        mbar_wait(ds_full, u & 1);
-        tc_fence_after();
+      }
+      __syncwarp();
+      mbar_wait(ds_full, u & 1);
+      tc_fence_after();
+      if (elect_one_sync()) {
         for (int ks = 0; ks < ncols / 16; ++ks)
           umma_f16(tm_dq, make_smem_desc_sw128(ds_addr + (ks >> 2) * kT + (ks & 3) * 32, 16, 1024),
-                   make_smem_desc_sw128(k_addr + ks * 2048, 8192, 1024), g.idesc_dq, (u | ks) != 0 ? 1u : 0u);
+                   make_smem_desc_sw128(k_addr + ks * 2048, 8192, 1024), idesc_dq, (u | ks) != 0 ? 1u : 0u);
         umma_commit(dq_done);
         umma_commit(&kv_empty[st]);
       }
+      __syncwarp();
     }
   } else {
     const int q = warp & 3;
@@ -254,28 +266,35 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_dkdv_kernel(const __g
   const int kcols16 = (kvalid + 15) / 16 * 16;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one_sync()) {
       mbar_arrive_expect_tx(k_full, 2 * kT);
       tma_load_2d(sK, &g.map_qkv, k_full, g.k_col0 + h * 64, row0 + kt * 128);
       tma_load_2d(sV, &g.map_qkv, k_full, g.v_col0 + h * 64, row0 + kt * 128);
-      for (int u = 0; u < g.n_units; ++u) {
-        const int st = u & 1;
-        mbar_wait(&q_empty[st], ((u >> 1) & 1) ^ 1u);
+    }
+    __syncwarp();
+    const int n_units = g.n_units;
+    for (int u = 0; u < n_units; ++u) {
+      const int st = u & 1;
+      mbar_wait(&q_empty[st], ((u >> 1) & 1) ^ 1u);
+      if (elect_one_sync()) {
         mbar_arrive_expect_tx(&q_full[st], 2 * kT);
         tma_load_2d(sQ + st * kT, &g.map_qkv, &q_full[st], g.q_col0 + h * 64, row0 + u * 128);
         tma_load_2d(sDO + st * kT, &g.map_do, &q_full[st], h * 64, row0 + u * 128);
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      mbar_wait(k_full, 0);
-      const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV), p_addr = smem_u32(sP), ds_addr = smem_u32(sDS);
-      const uint32_t idesc_s = make_idesc_f16(128, static_cast<uint32_t>(kcols16), 0, 0);
-      for (int u = 0; u < g.n_units; ++u) {
-        const int st = u & 1;
-        mbar_wait(&q_full[st], (u >> 1) & 1);
-        tc_fence_after();
-        const uint32_t q_addr = smem_u32(sQ + st * kT), do_addr = smem_u32(sDO + st * kT);
+    mbar_wait(k_full, 0);
+    const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV), p_addr = smem_u32(sP), ds_addr = smem_u32(sDS);
+    const uint32_t idesc_s = make_idesc_f16(128, static_cast<uint32_t>(kcols16), 0, 0);
+    const uint32_t idesc_dkv = g.idesc_dkv;
+    const int n_units = g.n_units;
+    for (int u = 0; u < n_units; ++u) {
+      const int st = u & 1;
+      mbar_wait(&q_full[st], (u >> 1) & 1);
+      tc_fence_after();
+      const uint32_t q_addr = smem_u32(sQ + st * kT), do_addr = smem_u32(sDO + st * kT);
+      if (elect_one_sync()) {
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           umma_f16(tm_s, make_smem_desc_sw128(q_addr + k * 32, 16, 1024),
@@ -285,20 +304,25 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_dkdv_kernel(const __g
           umma_f16(tm_dp, make_smem_desc_sw128(do_addr + k * 32, 16, 1024),
                    make_smem_desc_sw128(v_addr + k * 32, 16, 1024), idesc_s, k != 0 ? 1u : 0u);
         umma_commit(sdp_full);
-        mbar_wait(pds_full, u & 1);
-        tc_fence_after();
+      }
+      __syncwarp();
+      mbar_wait(pds_full, u & 1);
+      tc_fence_after();
         // dV[key, d] += sum_q P[q, key] dO[q, d] ;  dK[key, d] += sum_q dS[q, key] Q[q, d]
         // A = P^T / dS^T read MN-major straight from the [query][key] tiles (M = keys: 2 blocks of 64, LBO = kT);
         // B = dO / Q tiles MN-major ([query rows][d]); one k-step = 16 query rows = 2048 bytes in both.
+      if (elect_one_sync()) {
+#pragma unroll
         for (int ks = 0; ks < 8; ++ks) {
           umma_f16(tm_dv, make_smem_desc_sw128(p_addr + ks * 2048, kT, 1024),
-                   make_smem_desc_sw128(do_addr + ks * 2048, 8192, 1024), g.idesc_dkv, (u | ks) != 0 ? 1u : 0u);
+                   make_smem_desc_sw128(do_addr + ks * 2048, 8192, 1024), idesc_dkv, (u | ks) != 0 ? 1u : 0u);
           umma_f16(tm_dk, make_smem_desc_sw128(ds_addr + ks * 2048, kT, 1024),
-                   make_smem_desc_sw128(q_addr + ks * 2048, 8192, 1024), g.idesc_dkv, (u | ks) != 0 ? 1u : 0u);
+                   make_smem_desc_sw128(q_addr + ks * 2048, 8192, 1024), idesc_dkv, (u | ks) != 0 ? 1u : 0u);
         }
         umma_commit(acc_done);
         umma_commit(&q_empty[st]);
       }
+      __syncwarp();
     }
   } else {
     const int q = warp & 3;
@@ -452,17 +476,18 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_small_kernel(const __
   const long long kv_row0 = temporal ? q_row0 : static_cast<long long>(z / g.kv_z_div) * g.s_k;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one_sync()) {
       mbar_arrive_expect_tx(in_full, 4 * kT);
       tma_load_2d(sQ, &g.map_q, in_full, g.q_col0 + h * 64, static_cast<int>(q_row0));
       tma_load_2d(sDO, &g.map_do, in_full, h * 64, static_cast<int>(q_row0));
       tma_load_2d(sK, &g.map_kv, in_full, g.k_col0 + h * 64, static_cast<int>(kv_row0));
       tma_load_2d(sV, &g.map_kv, in_full, g.v_col0 + h * 64, static_cast<int>(kv_row0));
     }
+    __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
-      mbar_wait(in_full, 0);
-      tc_fence_after();
+    mbar_wait(in_full, 0);
+    tc_fence_after();
+    if (elect_one_sync()) {
       const uint32_t q_addr = smem_u32(sQ), do_addr = smem_u32(sDO), k_addr = smem_u32(sK), v_addr = smem_u32(sV);
       const uint32_t p_addr = smem_u32(sP), ds_addr = smem_u32(sDS);
 #pragma unroll
@@ -474,8 +499,13 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_small_kernel(const __
         umma_f16(tm_dp, make_smem_desc_sw128(do_addr + k * 32, 16, 1024),
                  make_smem_desc_sw128(v_addr + k * 32, 16, 1024), g.idesc_s, k != 0 ? 1u : 0u);
       umma_commit(sdp_full);
-      mbar_wait(pds_full, 0);
-      tc_fence_after();
+    }
+    __syncwarp();
+    mbar_wait(pds_full, 0);
+    tc_fence_after();
+    if (elect_one_sync()) {
+      const uint32_t q_addr = smem_u32(sQ), do_addr = smem_u32(sDO), k_addr = smem_u32(sK);
+      const uint32_t p_addr = smem_u32(sP), ds_addr = smem_u32(sDS);
       for (int ks = 0; ks < g.ncols16 / 16; ++ks)  // dQ = dS K        (K tile as MN-major B)
         umma_f16(tm_dq, make_smem_desc_sw128(ds_addr + (ks >> 2) * kT + (ks & 3) * 32, 16, 1024),
                  make_smem_desc_sw128(k_addr + ks * 2048, 8192, 1024), g.idesc_dq, ks != 0 ? 1u : 0u);
@@ -489,6 +519,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_small_kernel(const __
       }
       umma_commit(acc_done);
     }
+    __syncwarp();
   } else {
     const int q = warp & 3;
     const int r = q * 32 + lane;

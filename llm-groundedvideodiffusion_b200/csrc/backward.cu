@@ -65,15 +65,14 @@ __global__ void gn_bwd_stats_kernel(const __half* __restrict__ x, long long ld_x
                                     const float* __restrict__ stats, const __half* __restrict__ gamma,
                                     const __half* __restrict__ beta, float eps, int silu,
                                     float* __restrict__ bwd_partial) {
-  extern __shared__ float s_acc[];  // [2*C] then [2*G] mean/rstd
-  float* s_mean = s_acc + 2 * C;
-  float* s_rstd = s_mean + G;
+  extern __shared__ float s_part[];  // [rows per pass][2*C] partial sums (folded in a fixed order), then [2*G] mean/rstd
   const int vpr = C >> 3;
   const int rpp = blockDim.x / vpr;
+  float* s_mean = s_part + static_cast<long long>(rpp) * 2 * C;
+  float* s_rstd = s_mean + G;
   const int v = threadIdx.x % vpr, rsub = threadIdx.x / vpr;
   const int chunk = blockIdx.x, s = blockIdx.y;
   const int cpg = C / G;
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) s_acc[i] = 0.f;
   for (int g = threadIdx.x; g < G; g += blockDim.x) {
     s_mean[g] = stats[(static_cast<long long>(s) * G + g) * 2];
     s_rstd[g] = stats[(static_cast<long long>(s) * G + g) * 2 + 1];
@@ -131,18 +130,22 @@ __global__ void gn_bwd_stats_kernel(const __half* __restrict__ x, long long ld_x
         a2[i] += gg * xh;
       }
     }
+    float* mine = s_part + static_cast<long long>(rsub) * 2 * C + v * 8;  // no atomics: run-to-run reproducible
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      atomicAdd(&s_acc[v * 8 + i], a1[i]);
-      atomicAdd(&s_acc[C + v * 8 + i], a2[i]);
+      mine[i] = a1[i];
+      mine[C + i] = a2[i];
     }
   }
   __syncthreads();
   for (int g = threadIdx.x; g < G; g += blockDim.x) {
     float a = 0.f, b = 0.f;
-    for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
-      a += s_acc[c];
-      b += s_acc[C + c];
+    for (int rs = 0; rs < rpp; ++rs) {
+      const float* row = s_part + static_cast<long long>(rs) * 2 * C;
+      for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+        a += row[c];
+        b += row[C + c];
+      }
     }
     float* o = bwd_partial + ((static_cast<long long>(s) * chunks + chunk) * G + g) * 2;
     o[0] = a;
@@ -507,11 +510,14 @@ extern "C" int lvd_groupnorm_bwd(const void* x, int64_t ld_x, const void* dz, in
   if (fwd_stats) {
     stats = const_cast<float*>(static_cast<const float*>(fwd_stats));  // {mean, rstd} kept from the forward launch
   } else {
-    gn_stats_kernel<<<grid, threads, 2 * channels * sizeof(float), ST(stream)>>>(
+    gn_stats_kernel<<<grid, threads, static_cast<size_t>(threads / (channels / 8)) * 2 * channels * sizeof(float),
+                      ST(stream)>>>(
         HC(x), ld_x, rows_per_sample, channels, groups, static_cast<int>(chunks), fwd);
     gn_finalize_kernel<<<samples, fin_threads, 0, ST(stream)>>>(fwd, static_cast<int>(chunks), groups, n, eps, stats, 0);
   }
-  gn_bwd_stats_kernel<<<grid, threads, (2 * channels + 2 * groups) * sizeof(float), ST(stream)>>>(
+  gn_bwd_stats_kernel<<<grid, threads,
+                        (static_cast<size_t>(threads / (channels / 8)) * 2 * channels + 2 * groups) * sizeof(float),
+                        ST(stream)>>>(
       HC(x), ld_x, HC(dz), ld_dz, rows_per_sample, channels, groups, static_cast<int>(chunks), stats, HC(gamma),
       HC(beta), eps, silu, bwd);
   gn_finalize_kernel<<<samples, fin_threads, 0, ST(stream)>>>(bwd, static_cast<int>(chunks), groups, n, eps, bstats, 1);

@@ -35,7 +35,7 @@ __device__ __forceinline__ void st8(__half* p, const float (&v)[8]) {
 // per-channel accumulators / affine live in registers.
 __global__ void gn_stats_kernel(const __half* __restrict__ x, long long ld, long long rows_per_sample, int C, int G,
                                 int chunks, float* __restrict__ partial) {
-  extern __shared__ float s_acc[];  // [2*C]
+  extern __shared__ float s_part[];  // [rows per pass][2*C]: per-thread partial sums, folded in a FIXED order below
   const int vpr = C >> 3;
   const int rpp = blockDim.x / vpr;  // rows per pass
   const int v = threadIdx.x % vpr;
@@ -45,8 +45,6 @@ __global__ void gn_stats_kernel(const __half* __restrict__ x, long long ld, long
   const long long r0 = chunk * rows_per_chunk;
   long long r1 = r0 + rows_per_chunk;
   if (r1 > rows_per_sample) r1 = rows_per_sample;
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) s_acc[i] = 0.f;
-  __syncthreads();
   float sum[8], sq[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) sum[i] = sq[i] = 0.f;
@@ -74,19 +72,24 @@ __global__ void gn_stats_kernel(const __half* __restrict__ x, long long ld, long
         sq[i] += t[i] * t[i];
       }
     }
+    // no atomics: the summation order (and therefore every output bit) is the same on every run
+    float* mine = s_part + static_cast<long long>(rsub) * 2 * C + v * 8;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      atomicAdd(&s_acc[v * 8 + i], sum[i]);
-      atomicAdd(&s_acc[C + v * 8 + i], sq[i]);
+      mine[i] = sum[i];
+      mine[C + i] = sq[i];
     }
   }
   __syncthreads();
   const int cpg = C / G;
   for (int g = threadIdx.x; g < G; g += blockDim.x) {
     float a = 0.f, b = 0.f;
-    for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
-      a += s_acc[c];
-      b += s_acc[C + c];
+    for (int rs = 0; rs < rpp; ++rs) {
+      const float* row = s_part + static_cast<long long>(rs) * 2 * C;
+      for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+        a += row[c];
+        b += row[C + c];
+      }
     }
     float* o = partial + ((static_cast<long long>(s) * chunks + chunk) * G + g) * 2;
     o[0] = a;
@@ -295,7 +298,7 @@ extern "C" int lvd_groupnorm(const void* x, int64_t ld_x, void* y, int64_t ld_y,
   const int threads = gn_threads(channels);
   LVD_REQUIRE(threads <= 1024, "lvd_groupnorm: C=%d too wide", channels);
   dim3 grid(static_cast<unsigned>(chunks), static_cast<unsigned>(samples));
-  gn_stats_kernel<<<grid, threads, 2 * channels * sizeof(float), st>>>(
+  gn_stats_kernel<<<grid, threads, static_cast<size_t>(threads / (channels / 8)) * 2 * channels * sizeof(float), st>>>(
       static_cast<const __half*>(x), ld_x, rows_per_sample, channels, groups, static_cast<int>(chunks),
       static_cast<float*>(workspace));
   float* stats = stats_out ? static_cast<float*>(stats_out) : static_cast<float*>(workspace) + need / sizeof(float);
