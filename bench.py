@@ -394,9 +394,11 @@ def run_gpu(args):
         d = (fam if k_ < n_fwd_records else fam_guid).setdefault(name, {"ms": 0.0, "flops": 0.0, "bytes": 0.0,
                                                                         "launches": 0})
         if tag is not None:
-            sd = shapes[0 if k_ < n_fwd_records else 1].setdefault(tag, {"ms": 0.0, "flops": 0.0, "launches": 0})
+            sd = shapes[0 if k_ < n_fwd_records else 1].setdefault(tag, {"ms": 0.0, "flops": 0.0, "bytes": 0.0,
+                                                                                  "launches": 0})
             sd["ms"] += s.elapsed_time(e)
             sd["flops"] += fl
+            sd["bytes"] += nb
             sd["launches"] += 1
         d["ms"] += s.elapsed_time(e)
         d["flops"] += fl

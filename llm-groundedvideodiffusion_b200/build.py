@@ -45,7 +45,8 @@ def build(force=False, verbose=False):
     for s in srcs:
         o = os.path.join(objdir, os.path.basename(s)[:-3] + ".o")
         objs.append(o)
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
+        extra = os.environ.get("LVD_EXTRA_NVCC_FLAGS", "").split()  # tuning builds only (e.g. -DLVD_GEMM_PHASE_PROF)
+        cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
         procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     ok = True
     for s, p in procs:

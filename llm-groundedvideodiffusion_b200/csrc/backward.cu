@@ -211,7 +211,7 @@ __global__ void gn_bwd_apply_kernel(const __half* __restrict__ x, long long ld_x
 
 // forward statistics kernel lives in norm.cu
 __global__ void gn_stats_kernel(const __half* __restrict__ x, long long ld, long long rows_per_sample, int C, int G,
-                                int chunks, float* __restrict__ partial);
+                                int chunks, float* __restrict__ partial, float n, float eps, float* __restrict__ stats);
 __global__ void gn_finalize_kernel(const float* __restrict__ partial, int chunks, int G, float n, float eps,
                                    float* __restrict__ stats, int raw_means);
 
@@ -510,10 +510,10 @@ extern "C" int lvd_groupnorm_bwd(const void* x, int64_t ld_x, const void* dz, in
   if (fwd_stats) {
     stats = const_cast<float*>(static_cast<const float*>(fwd_stats));  // {mean, rstd} kept from the forward launch
   } else {
-    gn_stats_kernel<<<grid, threads, static_cast<size_t>(threads / (channels / 8)) * 2 * channels * sizeof(float),
+    LVD_REQUIRE(samples <= 8192, "lvd_groupnorm_bwd: too many samples");
+    gn_stats_kernel<<<grid, threads, (static_cast<size_t>(threads / (channels / 8)) + 1) * 2 * channels * sizeof(float),
                       ST(stream)>>>(
-        HC(x), ld_x, rows_per_sample, channels, groups, static_cast<int>(chunks), fwd);
-    gn_finalize_kernel<<<samples, fin_threads, 0, ST(stream)>>>(fwd, static_cast<int>(chunks), groups, n, eps, stats, 0);
+        HC(x), ld_x, rows_per_sample, channels, groups, static_cast<int>(chunks), fwd, n, eps, stats);
   }
   gn_bwd_stats_kernel<<<grid, threads,
                         (static_cast<size_t>(threads / (channels / 8)) * 2 * channels + 2 * groups) * sizeof(float),

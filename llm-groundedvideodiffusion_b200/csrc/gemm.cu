@@ -51,7 +51,8 @@ struct GemmArgs {
   // persistent tile walk: tile += tile_step; its n-tile / row-tile digits advance by precomputed mixed-radix steps
   int tile_step, step_nt;
   int step_lo[4], step_hi[4];
-  int debug;  // tools/perf_gemm_sweep.py: bit 0 = skip the TMA loads, bit 1 = skip the MMAs (results are garbage)
+  int debug;  // tools/perf_gemm_sweep.py: bit 0 = skip the TMA loads, bit 1 = skip the MMAs, bit 2 = skip the output
+              // stores, bit 3 = skip the residual loads (results are garbage)
   float gamma;
   uint32_t idesc;
 };
@@ -65,6 +66,19 @@ __device__ __forceinline__ void trace_event(const GemmArgs& g, unsigned ev) {
     if (i < 8192) g_trace[i] = (static_cast<unsigned long long>(ev) << 48) | (globaltimer_ns() & 0xFFFFFFFFFFFFull);
   }
 }
+
+// Per-warp phase profile of the epilogue (build with LVD_EXTRA_NVCC_FLAGS=-DLVD_GEMM_PHASE_PROF; tools/phase_gemm.py):
+// clock64 deltas accumulated in registers, dumped into g_trace[warp * 16 + phase] by CTA 0 at kernel end.
+#ifdef LVD_GEMM_PHASE_PROF
+#define LVD_PH(i)                 \
+  do {                            \
+    const long long t_ = clock64(); \
+    ph[i] += t_ - ph_last;        \
+    ph_last = t_;                 \
+  } while (0)
+#else
+#define LVD_PH(i)
+#endif
 
 // (n-tile, row-tile digits) of the current tile.  Integer division by run-time extents costs ~100 dependent
 // instructions each; doing six of them per tile in the single producer thread was ~0.8 us per tile (measured).
@@ -341,7 +355,15 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     bool res_issued = false;  // the residual of the group's next slab is already on its way
     TileIter it;
     tile_init<kCtas>(g, it, tile0, static_cast<int>(cta_rank));
+#ifdef LVD_GEMM_PHASE_PROF
+    long long ph[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    long long ph_last = clock64();
+#endif
     auto issue_res = [&](const TileIter& ti, int sl_, uint32_t seq_) {  // elected lane: TMA-load a residual slab
+      if (g.debug & 8) {  // tuning aid: no residual traffic
+        mbar_arrive(&my_res_full[seq_ & 1]);
+        return;
+      }
       mbar_arrive_expect_tx(&my_res_full[seq_ & 1], static_cast<uint32_t>(g.slab_bytes));
       // the residual lands in the slab's own output buffer: threads add to it in place
       tma_load_5d(my_out + (seq_ & 1) * kSlabBytes, &g.map_res, &my_res_full[seq_ & 1], ti.nt * out_cols + sl_ * 32,
@@ -369,8 +391,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                 static_cast<long long>(x2) * g.rv_stride[2] + static_cast<long long>(x3) * g.rv_stride[3];
       }
       if (leader_warp && lane == 0) trace_event(g, 16 + grp * 16 + 0);  // epilogue group: waiting for the tile
+      LVD_PH(7);
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
+      LVD_PH(0);
       if (leader_warp && lane == 0) trace_event(g, 16 + grp * 16 + 1);  // tile's accumulator complete
       const uint32_t taddr = tmem_base + static_cast<uint32_t>(acc * block_n) + (static_cast<uint32_t>(q * 32) << 16);
       if (first >= nslabs) release_acc();  // no slab of this tile falls to this group
@@ -382,6 +406,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
           __syncwarp();
         }
         res_issued = false;
+        LVD_PH(1);
         uint4 packed[4];
 #pragma unroll
         for (int h = 0; h < 2; ++h) {  // two 16-column halves: bounds the live registers
@@ -455,24 +480,29 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
           packed[2 * h] = pack8(&v[0]);
           packed[2 * h + 1] = pack8(&v[8]);
         }
+        LVD_PH(2);
         if (sl + 4 >= nslabs) release_acc();  // this warp's last TMEM reads of the tile have completed
         if (leader_warp && lane == 0) trace_event(g, 16 + grp * 16 + 2);  // slab math done
 #pragma unroll
         for (int cidx = 0; cidx < 4; ++cidx)
           *reinterpret_cast<uint4*>(obuf + row_off + ((static_cast<uint32_t>(cidx) ^ sw) << 4)) = packed[cidx];
         fence_proxy_async_smem();
+        LVD_PH(3);
         // the group's other buffer must have been drained (store seq-1) before anyone writes it in the next slab
         if (leader_warp) {
           if (elect_one_sync()) bulk_wait_read_all();
           __syncwarp();
         }
         if (leader_warp && lane == 0) trace_event(g, 16 + grp * 16 + 3);  // fence + previous store drained
+        LVD_PH(4);
         named_bar_sync(bar_id, 128);
+        LVD_PH(5);
         if (leader_warp && lane == 0) trace_event(g, 16 + grp * 16 + 4);  // group barrier passed
         if (leader_warp) {
           if (elect_one_sync()) {  // elect.sync is deterministic: the same lane owns the bulk async-groups throughout
-            tma_store_5d(&g.map_out, obuf, gcol, it.t0 * g.box[0], it.t1 * g.box[1], it.t2 * g.box[2],
-                         it.t3 * g.box[3]);
+            if (!(g.debug & 4))  // tuning aid: bit 2 drops the output stores
+              tma_store_5d(&g.map_out, obuf, gcol, it.t0 * g.box[0], it.t1 * g.box[1], it.t2 * g.box[2],
+                           it.t3 * g.box[3]);
             bulk_commit_group();
           }
           __syncwarp();
@@ -501,6 +531,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         }
       }
       if (leader_warp && lane == 0) trace_event(g, 16 + grp * 16 + 5);  // tile done
+      LVD_PH(6);
       if (++acc == n_acc) {
         acc = 0;
         acc_phase ^= 1u;
@@ -510,6 +541,12 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       if (elect_one_sync()) bulk_wait_all();
       __syncwarp();
     }
+#ifdef LVD_GEMM_PHASE_PROF
+    LVD_PH(8);
+    if (blockIdx.x == 0 && lane == 0)
+      for (int i = 0; i < 10; ++i) g_trace[warp * 16 + i] = static_cast<unsigned long long>(ph[i]);
+    if (blockIdx.x == 0 && threadIdx.x == 64) g_trace_n = 18 * 16;
+#endif
   }
   tc_fence_before();
   // the peer's shared memory / TMEM / barriers must stay alive until the pair's last MMA and commit have landed

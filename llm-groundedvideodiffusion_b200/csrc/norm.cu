@@ -1,6 +1,7 @@
 // norm.cu -- GroupNorm (4-D per-frame and 5-D cross-frame statistics) and LayerNorm on channels-last fp16.
 // HBM/L2-bound: 16-byte vector loads, fp32 statistics, warp-shuffle / shared-memory reductions.
 #include <atomic>
+#include <cstdlib>
 
 #include "../../include/lvd_b200.h"
 #include "host_util.h"
@@ -19,6 +20,15 @@ __device__ __forceinline__ void ld8(const __half* p, float (&v)[8]) {
     v[2 * i + 1] = f.y;
   }
 }
+__device__ __forceinline__ void unpack8v(const uint4& u, float (&v)[8]) {
+  const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = __half22float2(h[i]);
+    v[2 * i] = f.x;
+    v[2 * i + 1] = f.y;
+  }
+}
 __device__ __forceinline__ void st8(__half* p, const float (&v)[8]) {
   uint4 u;
   __half2* h = reinterpret_cast<__half2*>(&u);
@@ -33,9 +43,15 @@ __device__ __forceinline__ void st8(__half* p, const float (&v)[8]) {
 // Pass 1 writes per-(sample, chunk, group) partial {sum, sumsq}; pass 2 folds the chunks (deterministic order),
 // normalises, applies the affine and optional SiLU.  Thread -> 8-channel vector mapping is fixed so the
 // per-channel accumulators / affine live in registers.
+// Per-sample arrival tickets of gn_stats_kernel (zero at module load, reset by the last CTA of each sample): the
+// library serialises GroupNorm launches on one stream per handle (include/lvd_b200.h, threading), so one set suffices.
+constexpr int kGnMaxSamples = 8192;
+__device__ unsigned int g_gn_tickets[kGnMaxSamples];
+
 __global__ void gn_stats_kernel(const __half* __restrict__ x, long long ld, long long rows_per_sample, int C, int G,
-                                int chunks, float* __restrict__ partial) {
-  extern __shared__ float s_part[];  // [rows per pass][2*C]: per-thread partial sums, folded in a FIXED order below
+                                int chunks, float* __restrict__ partial, float n, float eps, float* __restrict__ stats) {
+  extern __shared__ float s_part[];  // [rows per pass][2*C] per-thread partial sums, then [2*C] column sums
+  __shared__ int s_last;
   const int vpr = C >> 3;
   const int rpp = blockDim.x / vpr;  // rows per pass
   const int v = threadIdx.x % vpr;
@@ -51,28 +67,26 @@ __global__ void gn_stats_kernel(const __half* __restrict__ x, long long ld, long
   if (rsub < rpp) {
     const __half* base = x + (s * rows_per_sample) * ld + v * 8;
     long long r = r0 + rsub;
-    for (; r + 3LL * rpp < r1; r += 4LL * rpp) {  // 4 independent 16-byte loads in flight per thread
-      float t0[8], t1[8], t2[8], t3[8];
-      ld8(base + r * ld, t0);
-      ld8(base + (r + rpp) * ld, t1);
-      ld8(base + (r + 2LL * rpp) * ld, t2);
-      ld8(base + (r + 3LL * rpp) * ld, t3);
+    for (; r < r1; r += 8LL * rpp) {  // 8 independent 16-byte loads in flight per thread (predicated at the chunk end)
+      uint4 u[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        sum[i] += (t0[i] + t1[i]) + (t2[i] + t3[i]);
-        sq[i] += (t0[i] * t0[i] + t1[i] * t1[i]) + (t2[i] * t2[i] + t3[i] * t3[i]);
+      for (int k = 0; k < 8; ++k) {
+        const long long rk = r + static_cast<long long>(k) * rpp;
+        u[k] = rk < r1 ? *reinterpret_cast<const uint4*>(base + rk * ld) : make_uint4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int k = 0; k < 8; k += 2) {
+        float t0[8], t1[8];
+        unpack8v(u[k], t0);
+        unpack8v(u[k + 1], t1);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          sum[i] += t0[i] + t1[i];
+          sq[i] += t0[i] * t0[i] + t1[i] * t1[i];
+        }
       }
     }
-    for (; r < r1; r += rpp) {
-      float t[8];
-      ld8(base + r * ld, t);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        sum[i] += t[i];
-        sq[i] += t[i] * t[i];
-      }
-    }
-    // no atomics: the summation order (and therefore every output bit) is the same on every run
+    // no floating-point atomics anywhere: the summation order (and therefore every output bit) is the same on every run
     float* mine = s_part + static_cast<long long>(rsub) * 2 * C + v * 8;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -81,25 +95,61 @@ __global__ void gn_stats_kernel(const __half* __restrict__ x, long long ld, long
     }
   }
   __syncthreads();
-  const int cpg = C / G;
-  for (int g = threadIdx.x; g < G; g += blockDim.x) {
-    float a = 0.f, b = 0.f;
-    for (int rs = 0; rs < rpp; ++rs) {
-      const float* row = s_part + static_cast<long long>(rs) * 2 * C;
-      for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
-        a += row[c];
-        b += row[C + c];
-      }
-    }
-    float* o = partial + ((static_cast<long long>(s) * chunks + chunk) * G + g) * 2;
-    o[0] = a;
-    o[1] = b;
+  // fold rows-per-pass -> one value per column (all threads), then columns -> groups
+  float* s_col = s_part + static_cast<long long>(rpp) * 2 * C;
+  for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) {
+    float a = 0.f;
+    for (int rs = 0; rs < rpp; ++rs) a += s_part[static_cast<long long>(rs) * 2 * C + c];
+    s_col[c] = a;
   }
+  __syncthreads();
+  const int cpg = C / G;
+  for (int t = threadIdx.x; t < 2 * G; t += blockDim.x) {
+    const int g = t >> 1, which = t & 1;
+    const float* col = s_col + which * C + g * cpg;
+    float a = 0.f;
+    for (int c = 0; c < cpg; ++c) a += col[c];
+    partial[((static_cast<long long>(s) * chunks + chunk) * G + g) * 2 + which] = a;
+  }
+  // the last CTA of the sample to arrive folds the chunk partials into {mean, rstd} (fixed order: deterministic)
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(&g_gn_tickets[s], 1u) == static_cast<unsigned>(chunks - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  float* s_a = s_part;  // [blockDim.x] x 2
+  float* s_b = s_part + blockDim.x;
+  const int nparts = blockDim.x / G;
+  {
+    const int g = threadIdx.x % G, part = threadIdx.x / G;
+    float a = 0.f, b = 0.f;
+    if (part < nparts)
+      for (int k = part; k < chunks; k += nparts) {
+        const float* p = partial + ((static_cast<long long>(s) * chunks + k) * G + g) * 2;
+        a += __ldcg(p);
+        b += __ldcg(p + 1);
+      }
+    s_a[threadIdx.x] = a;
+    s_b[threadIdx.x] = b;
+  }
+  __syncthreads();
+  if (threadIdx.x < G) {
+    float a = 0.f, b = 0.f;
+    for (int q = 0; q < nparts; ++q) {
+      a += s_a[q * G + threadIdx.x];
+      b += s_b[q * G + threadIdx.x];
+    }
+    const float mean = a / n;
+    float var = b / n - mean * mean;
+    var = var > 0.f ? var : 0.f;
+    stats[(static_cast<long long>(s) * G + threadIdx.x) * 2] = mean;
+    stats[(static_cast<long long>(s) * G + threadIdx.x) * 2 + 1] = rsqrtf(var + eps);
+  }
+  if (threadIdx.x == 0) g_gn_tickets[s] = 0u;  // ready for the next launch on this stream
 }
 
-// Folds the per-chunk partial sums of one sample into {mean, rstd} per group (deterministic order).  A separate
-// tiny launch: with 5-D GroupNorm (2 samples x ~600 chunks) doing this in every apply CTA serialised ~600 dependent
-// loads in front of the streaming loop.
+// Folds per-chunk partial sums of one sample into per-group means (used by the backward pass, backward.cu).
 __global__ void gn_finalize_kernel(const float* __restrict__ partial, int chunks, int G, float n, float eps,
                                    float* __restrict__ stats, int raw_means) {
   __shared__ float s_a[256], s_b[256];
@@ -147,19 +197,17 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x, long long ld_x, __
   }
   __syncthreads();
   if (rsub >= rpp) return;
-  float ga[8], be[8], mu[8], rs[8];
+  // y = x * sc + sh with sc = rstd * gamma, sh = beta - mean * rstd * gamma
+  float sc[8], sh[8];
   {
-    float t[8];
-    ld8(gamma + v * 8, t);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) ga[i] = t[i];
-    ld8(beta + v * 8, t);
+    float ga[8], be[8];
+    ld8(gamma + v * 8, ga);
+    ld8(beta + v * 8, be);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      be[i] = t[i];
       const int g = (v * 8 + i) / cpg;
-      mu[i] = s_mean[g];
-      rs[i] = s_rstd[g];
+      sc[i] = s_rstd[g] * ga[i];
+      sh[i] = be[i] - s_mean[g] * sc[i];
     }
   }
   const long long rows_per_chunk = (rows_per_sample + chunks - 1) / chunks;
@@ -169,34 +217,251 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x, long long ld_x, __
   const __half* xb = x + (s * rows_per_sample) * ld_x + v * 8;
   __half* yb = y + (s * rows_per_sample) * ld_y + v * 8;
   long long r = r0 + rsub;
-  for (; r + rpp < r1; r += 2LL * rpp) {  // two rows per iteration: loads issued before the dependent math
-    float t[8], u[8];
-    ld8(xb + r * ld_x, t);
-    ld8(xb + (r + rpp) * ld_x, u);
+  for (; r < r1; r += 8LL * rpp) {  // eight rows per iteration (predicated at the chunk end): loads before the math
+    uint4 u[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float o = round_h((t[i] - mu[i]) * rs[i] * ga[i] + be[i]);
-      float o2 = round_h((u[i] - mu[i]) * rs[i] * ga[i] + be[i]);
-      if (silu) {
-        o = __fdividef(o, 1.0f + __expf(-o));
-        o2 = __fdividef(o2, 1.0f + __expf(-o2));
+    for (int k = 0; k < 8; ++k) {
+      const long long rk = r + static_cast<long long>(k) * rpp;
+      if (rk < r1) u[k] = *reinterpret_cast<const uint4*>(xb + rk * ld_x);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const long long rk = r + static_cast<long long>(k) * rpp;
+      if (rk < r1) {
+        float t[8];
+        unpack8v(u[k], t);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float o = round_h(fmaf(t[i], sc[i], sh[i]));
+          if (silu) o = __fdividef(o, 1.0f + __expf(-o));
+          t[i] = o;
+        }
+        st8(yb + rk * ld_y, t);
       }
-      t[i] = o;
-      u[i] = o2;
     }
-    st8(yb + r * ld_y, t);
-    st8(yb + (r + rpp) * ld_y, u);
   }
-  for (; r < r1; r += rpp) {
-    float t[8];
-    ld8(xb + r * ld_x, t);
+}
+
+// ---- streaming GroupNorm passes.  Two persistent CTAs per SM; each streams its row range through a ring of kGnStages
+// shared-memory stages filled by 1-D bulk copies (cp.async.bulk, one per row, or one per stage when rows are dense):
+// the bytes in flight (~75 KB per CTA) no longer depend on registers or occupancy, which is what held the
+// register-staged kernels at half of the HBM rate.  Pass 1 = statistics (+ ticketed finalize), pass 2 = normalise.
+constexpr int kGnStages = 5;
+
+struct GnStream {
+  uint64_t* full;      // [kGnStages]
+  uint4* ring;         // [kGnStages][T][vpr]
+  const __half* src;   // first row of this CTA's range
+  long long ld;
+  int n, T, vpr, nit;
+  bool dense;
+  __device__ __forceinline__ void issue(int it) const {  // whole warp 0
+    const int stage = it % kGnStages;
+    const int rows = n - it * T < T ? n - it * T : T;
+    const uint32_t row_bytes = static_cast<uint32_t>(vpr) * 16u;
+    const int lane = threadIdx.x & 31;
+    if (lane == 0) mbar_arrive_expect_tx(&full[stage], static_cast<uint32_t>(rows) * row_bytes);
+    __syncwarp();
+    uint4* dst = ring + static_cast<long long>(stage) * T * vpr;
+    const __half* from = src + static_cast<long long>(it) * T * ld;
+    if (dense) {
+      if (lane == 0) bulk_load_1d(dst, from, static_cast<uint32_t>(rows) * row_bytes, &full[stage]);
+    } else {
+      for (int r = lane; r < rows; r += 32) bulk_load_1d(dst + static_cast<long long>(r) * vpr, from + r * ld, row_bytes, &full[stage]);
+    }
+  }
+};
+
+__global__ void __launch_bounds__(320, 2) gn_stream_stats_kernel(const __half* __restrict__ x, long long ld,
+                                                                  long long rows_per_sample, int C, int G, int chunks,
+                                                                  int T, float* __restrict__ partial, float n,
+                                                                  float eps, float* __restrict__ stats) {
+  extern __shared__ uint4 s_dyn[];
+  __shared__ uint64_t s_full[kGnStages];
+  __shared__ int s_last;
+  const int vpr = C >> 3;
+  const int rpp = blockDim.x / vpr;
+  const int v = threadIdx.x % vpr;
+  const int rsub = threadIdx.x / vpr;
+  const int chunk = blockIdx.x, s = blockIdx.y;
+  const long long rows_per_chunk = (rows_per_sample + chunks - 1) / chunks;
+  const long long r0 = chunk * rows_per_chunk;
+  long long r1 = r0 + rows_per_chunk;
+  if (r1 > rows_per_sample) r1 = rows_per_sample;
+  GnStream st;
+  st.full = s_full;
+  st.ring = s_dyn;
+  st.src = x + (s * rows_per_sample + r0) * ld;
+  st.ld = ld;
+  st.n = r1 > r0 ? static_cast<int>(r1 - r0) : 0;
+  st.T = T;
+  st.vpr = vpr;
+  st.nit = (st.n + T - 1) / T;
+  st.dense = ld == C;
+  float* s_part = reinterpret_cast<float*>(s_dyn + static_cast<long long>(kGnStages) * T * vpr);
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kGnStages; ++i) mbar_init(&s_full[i], 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  if (threadIdx.x < 32)
+    for (int it = 0; it < kGnStages && it < st.nit; ++it) st.issue(it);
+  float sum[8], sq[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) sum[i] = sq[i] = 0.f;
+  for (int it = 0; it < st.nit; ++it) {
+    const int stage = it % kGnStages;
+    mbar_wait(&s_full[stage], static_cast<uint32_t>(it / kGnStages) & 1u);
+    const int rows = st.n - it * T < T ? st.n - it * T : T;
+    const uint4* buf = s_dyn + static_cast<long long>(stage) * T * vpr;
+    if (rsub < rpp) {
+      for (int r = rsub; r < rows; r += rpp) {
+        float t[8];
+        unpack8v(buf[static_cast<long long>(r) * vpr + v], t);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          sum[i] += t[i];
+          sq[i] += t[i] * t[i];
+        }
+      }
+    }
+    __syncthreads();  // everyone is done with the stage before it is refilled
+    if (threadIdx.x < 32 && it + kGnStages < st.nit) st.issue(it + kGnStages);
+  }
+  if (rsub < rpp) {
+    float* mine = s_part + static_cast<long long>(rsub) * 2 * C + v * 8;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      float o = round_h((t[i] - mu[i]) * rs[i] * ga[i] + be[i]);
-      if (silu) o = __fdividef(o, 1.0f + __expf(-o));
-      t[i] = o;
+      mine[i] = sum[i];
+      mine[C + i] = sq[i];
     }
-    st8(yb + r * ld_y, t);
+  }
+  __syncthreads();
+  float* s_col = s_part + static_cast<long long>(rpp) * 2 * C;
+  for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) {
+    float a = 0.f;
+    for (int rs = 0; rs < rpp; ++rs) a += s_part[static_cast<long long>(rs) * 2 * C + c];
+    s_col[c] = a;
+  }
+  __syncthreads();
+  const int cpg = C / G;
+  for (int t = threadIdx.x; t < 2 * G; t += blockDim.x) {
+    const int g = t >> 1, which = t & 1;
+    const float* col = s_col + which * C + g * cpg;
+    float a = 0.f;
+    for (int c = 0; c < cpg; ++c) a += col[c];
+    partial[((static_cast<long long>(s) * chunks + chunk) * G + g) * 2 + which] = a;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(&g_gn_tickets[s], 1u) == static_cast<unsigned>(chunks - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  float* s_a = s_part;
+  float* s_b = s_part + blockDim.x;
+  const int nparts = blockDim.x / G;
+  {
+    const int g = threadIdx.x % G, part = threadIdx.x / G;
+    float a = 0.f, b = 0.f;
+    if (part < nparts)
+      for (int k = part; k < chunks; k += nparts) {
+        const float* p = partial + ((static_cast<long long>(s) * chunks + k) * G + g) * 2;
+        a += __ldcg(p);
+        b += __ldcg(p + 1);
+      }
+    s_a[threadIdx.x] = a;
+    s_b[threadIdx.x] = b;
+  }
+  __syncthreads();
+  if (threadIdx.x < G) {
+    float a = 0.f, b = 0.f;
+    for (int q = 0; q < nparts; ++q) {
+      a += s_a[q * G + threadIdx.x];
+      b += s_b[q * G + threadIdx.x];
+    }
+    const float mean = a / n;
+    float var = b / n - mean * mean;
+    var = var > 0.f ? var : 0.f;
+    stats[(static_cast<long long>(s) * G + threadIdx.x) * 2] = mean;
+    stats[(static_cast<long long>(s) * G + threadIdx.x) * 2 + 1] = rsqrtf(var + eps);
+  }
+  if (threadIdx.x == 0) g_gn_tickets[s] = 0u;
+}
+
+__global__ void __launch_bounds__(320, 2) gn_stream_apply_kernel(const __half* __restrict__ x, long long ld_x,
+                                                                  __half* __restrict__ y, long long ld_y,
+                                                                  long long rows_per_sample, int C, int G, int chunks,
+                                                                  int T, const float* __restrict__ stats,
+                                                                  const __half* __restrict__ gamma,
+                                                                  const __half* __restrict__ beta, int silu) {
+  extern __shared__ uint4 s_dyn[];
+  __shared__ uint64_t s_full[kGnStages];
+  __shared__ float s_mean[64], s_rstd[64];
+  const int vpr = C >> 3;
+  const int rpp = blockDim.x / vpr;
+  const int v = threadIdx.x % vpr;
+  const int rsub = threadIdx.x / vpr;
+  const int chunk = blockIdx.x, s = blockIdx.y;
+  const long long rows_per_chunk = (rows_per_sample + chunks - 1) / chunks;
+  const long long r0 = chunk * rows_per_chunk;
+  long long r1 = r0 + rows_per_chunk;
+  if (r1 > rows_per_sample) r1 = rows_per_sample;
+  GnStream st;
+  st.full = s_full;
+  st.ring = s_dyn;
+  st.src = x + (s * rows_per_sample + r0) * ld_x;
+  st.ld = ld_x;
+  st.n = r1 > r0 ? static_cast<int>(r1 - r0) : 0;
+  st.T = T;
+  st.vpr = vpr;
+  st.nit = (st.n + T - 1) / T;
+  st.dense = ld_x == C;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kGnStages; ++i) mbar_init(&s_full[i], 1);
+    fence_barrier_init();
+  }
+  for (int g = threadIdx.x; g < G; g += blockDim.x) {
+    s_mean[g] = stats[(static_cast<long long>(s) * G + g) * 2];
+    s_rstd[g] = stats[(static_cast<long long>(s) * G + g) * 2 + 1];
+  }
+  __syncthreads();
+  if (threadIdx.x < 32)
+    for (int it = 0; it < kGnStages && it < st.nit; ++it) st.issue(it);
+  const int cpg = C / G;
+  float sc[8], sh[8];
+  if (rsub < rpp) {
+    float ga[8], be[8];
+    ld8(gamma + v * 8, ga);
+    ld8(beta + v * 8, be);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int g = (v * 8 + i) / cpg;
+      sc[i] = s_rstd[g] * ga[i];
+      sh[i] = be[i] - s_mean[g] * sc[i];
+    }
+  }
+  __half* yb = y + (s * rows_per_sample + r0) * ld_y + v * 8;
+  for (int it = 0; it < st.nit; ++it) {
+    const int stage = it % kGnStages;
+    mbar_wait(&s_full[stage], static_cast<uint32_t>(it / kGnStages) & 1u);
+    const int rows = st.n - it * T < T ? st.n - it * T : T;
+    const uint4* buf = s_dyn + static_cast<long long>(stage) * T * vpr;
+    if (rsub < rpp) {
+      for (int r = rsub; r < rows; r += rpp) {
+        float t[8];
+        unpack8v(buf[static_cast<long long>(r) * vpr + v], t);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float o = round_h(fmaf(t[i], sc[i], sh[i]));
+          if (silu) o = __fdividef(o, 1.0f + __expf(-o));
+          t[i] = o;
+        }
+        st8(yb + (static_cast<long long>(it) * T + r) * ld_y, t);
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x < 32 && it + kGnStages < st.nit) st.issue(it + kGnStages);
   }
 }
 
@@ -208,65 +473,123 @@ static int gn_threads(int C) {
 }
 
 // ------------------------------------------------------------------------------------------------ LayerNorm
-// One warp per row; the row stays in registers (C <= 2048), exact two-pass mean / variance in fp32.
-constexpr int kLnMaxVec = 8;  // 8 vectors of 8 halves per lane -> C <= 2048
-// NV = ceil(C / 256) vectors per lane: a template parameter so that narrow rows (C = 320: NV = 2) hold 16 instead of
-// 64 registers of row data and many more rows are in flight per SM.
-template <int NV>
-__global__ void layernorm_kernel(const __half* __restrict__ x, long long ld_x, __half* __restrict__ y, long long ld_y,
-                                 long long rows, int C, const __half* __restrict__ gamma,
-                                 const __half* __restrict__ beta, float eps) {
-  extern __shared__ float s_affine[];  // gamma[C], beta[C] as fp32, loaded once per block
+// L lanes per row (8 / 16 / 32, so that a row is NV <= 8 16-byte vectors per lane: C = 320 -> 8 lanes x 5, 640 -> 16 x 5,
+// 1280 -> 32 x 5), 32 / L rows side by side in a warp and R such row sets in flight.  Rows are held PACKED (fp16) in
+// registers, so a warp keeps (32 / L) * R rows -- 7.7 KB at C = 320 -- of loads outstanding before the first dependent
+// shuffle: with one row per warp in flight the kernel sat at 1/3 of the HBM rate.  Exact two-pass mean / variance, fp32.
+__device__ __forceinline__ void unpack8u(const uint4& u, float (&v)[8]) {
+  const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = __half22float2(h[i]);
+    v[2 * i] = f.x;
+    v[2 * i + 1] = f.y;
+  }
+}
+// Makes the compiler forget what it knows about a packed vector: the fp32 conversions are redone in every pass instead of
+// all converted values being kept live (which doubled the register count and halved the rows in flight).
+__device__ __forceinline__ void opaque(uint4& u) { asm volatile("" : "+r"(u.x), "+r"(u.y), "+r"(u.z), "+r"(u.w)); }
+constexpr int kLnMaxVec = 8;
+template <int NV, int L, int R>
+__global__ void __launch_bounds__(256, 2) layernorm_kernel(const __half* __restrict__ x, long long ld_x,
+                                                        __half* __restrict__ y, long long ld_y, long long rows, int C,
+                                                        const __half* __restrict__ gamma,
+                                                        const __half* __restrict__ beta, float eps) {
+  extern __shared__ uint4 s_affine_v[];  // gamma[C], beta[C] (fp16), loaded once per block
+  __half* s_affine = reinterpret_cast<__half*>(s_affine_v);
   for (int i = threadIdx.x; i < C; i += blockDim.x) {
-    s_affine[i] = __half2float(gamma[i]);
-    s_affine[C + i] = __half2float(beta[i]);
+    s_affine[i] = gamma[i];
+    s_affine[C + i] = beta[i];
   }
   __syncthreads();
+  constexpr int kRowsPerSet = 32 / L;
   const int lane = threadIdx.x & 31;
+  const int j = lane % L;       // lane within the row
+  const int sub = lane / L;     // row within the set
   const int vpr = C >> 3;
+  const float inv_c = 1.0f / static_cast<float>(C);
   const long long warps_total = static_cast<long long>(gridDim.x) * (blockDim.x >> 5);
-  for (long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows;
-       row += warps_total) {
-    float vals[NV][8];
-    float sum = 0.f;
-    const __half* xr = x + row * ld_x;
+  const long long rows_per_iter = static_cast<long long>(kRowsPerSet) * R;
+  for (long long row0 = (static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5)) * rows_per_iter;
+       row0 < rows; row0 += warps_total * rows_per_iter) {
+    uint4 vals[R][NV];
 #pragma unroll
-    for (int k = 0; k < NV; ++k) {
-      const int v = lane + k * 32;
-      if (v < vpr) {
-        ld8(xr + v * 8, vals[k]);
+    for (int r = 0; r < R; ++r) {
+      const long long row = row0 + r * kRowsPerSet + sub;
+      const __half* xr = x + row * ld_x;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) sum += vals[k][i];
+      for (int k = 0; k < NV; ++k) {
+        const int v = j + k * L;
+        vals[r][k] = (row < rows && v < vpr) ? *reinterpret_cast<const uint4*>(xr + v * 8) : make_uint4(0, 0, 0, 0);
       }
     }
+    float mean[R], rstd[R];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    const float mean = sum / C;
-    float sq = 0.f;
+    for (int r = 0; r < R; ++r) {
+      float a = 0.f;
 #pragma unroll
-    for (int k = 0; k < NV; ++k) {
-      const int v = lane + k * 32;
-      if (v < vpr) {
+      for (int k = 0; k < NV; ++k) {
+        float f[8];
+        unpack8u(vals[r][k], f);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float d = vals[k][i] - mean;
-          sq += d * d;
+        for (int i = 0; i < 8; ++i) a += f[i];
+      }
+      mean[r] = a;
+    }
+#pragma unroll
+    for (int o = L / 2; o > 0; o >>= 1)
+#pragma unroll
+      for (int r = 0; r < R; ++r) mean[r] += __shfl_xor_sync(0xffffffffu, mean[r], o);
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int k = 0; k < NV; ++k) opaque(vals[r][k]);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      mean[r] *= inv_c;
+      float q = 0.f;
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        if (j + k * L < vpr) {
+          float f[8];
+          unpack8u(vals[r][k], f);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float d = f[i] - mean[r];
+            q += d * d;
+          }
         }
       }
+      rstd[r] = q;
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-    const float rstd = rsqrtf(sq / C + eps);
-    __half* yr = y + row * ld_y;
+    for (int o = L / 2; o > 0; o >>= 1)
+#pragma unroll
+      for (int r = 0; r < R; ++r) rstd[r] += __shfl_xor_sync(0xffffffffu, rstd[r], o);
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int k = 0; k < NV; ++k) opaque(vals[r][k]);
+#pragma unroll
+    for (int r = 0; r < R; ++r) rstd[r] = rsqrtf(rstd[r] * inv_c + eps);
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
-      const int v = lane + k * 32;
+      const int v = j + k * L;
       if (v < vpr) {
-        float o[8];
+        float ga[8], be[8];
+        unpack8u(s_affine_v[v], ga);
+        unpack8u(s_affine_v[vpr + v], be);
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
-          o[i] = (vals[k][i] - mean) * rstd * s_affine[v * 8 + i] + s_affine[C + v * 8 + i];
-        st8(yr + v * 8, o);
+        for (int r = 0; r < R; ++r) {
+          const long long row = row0 + r * kRowsPerSet + sub;
+          if (row < rows) {
+            float f[8], o[8];
+            unpack8u(vals[r][k], f);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o[i] = (f[i] - mean[r]) * rstd[r] * ga[i] + be[i];
+            st8(y + row * ld_y + v * 8, o);
+          }
+        }
       }
     }
   }
@@ -297,20 +620,48 @@ extern "C" int lvd_groupnorm(const void* x, int64_t ld_x, void* y, int64_t ld_y,
               "lvd_groupnorm: workspace %lld < %lld bytes", (long long)workspace_bytes, need);
   const int threads = gn_threads(channels);
   LVD_REQUIRE(threads <= 1024, "lvd_groupnorm: C=%d too wide", channels);
-  dim3 grid(static_cast<unsigned>(chunks), static_cast<unsigned>(samples));
-  gn_stats_kernel<<<grid, threads, static_cast<size_t>(threads / (channels / 8)) * 2 * channels * sizeof(float), st>>>(
-      static_cast<const __half*>(x), ld_x, rows_per_sample, channels, groups, static_cast<int>(chunks),
-      static_cast<float*>(workspace));
+  LVD_REQUIRE(samples <= kGnMaxSamples, "lvd_groupnorm: more than %d samples", kGnMaxSamples);
   float* stats = stats_out ? static_cast<float*>(stats_out) : static_cast<float*>(workspace) + need / sizeof(float);
-  gn_finalize_kernel<<<samples, 256 / groups * groups, 0, st>>>(static_cast<const float*>(workspace),
-                                                               static_cast<int>(chunks), groups,
-                                                               static_cast<float>(rows_per_sample) * (channels / groups),
-                                                               eps, stats, 0);
-  gn_apply_kernel<<<grid, threads, 0, st>>>(static_cast<const __half*>(x), ld_x, static_cast<__half*>(y), ld_y,
-                                            rows_per_sample, channels, groups, stats,
-                                            static_cast<const __half*>(gamma), static_cast<const __half*>(beta), silu,
-                                            static_cast<int>(chunks));
-  g_launches.fetch_add(3, std::memory_order_relaxed);
+  {
+    // streaming passes: ~2 persistent CTAs per SM, each with a ring of kGnStages stages of ~15 KB
+    const long long row_bytes = 2LL * channels;
+    const int rpp_ = threads / (channels / 8);
+    int T = static_cast<int>((15 * 1024) / row_bytes) / rpp_ * rpp_;
+    if (T < rpp_) T = rpp_;
+    long long schunks = (2LL * num_sms()) / samples;  // one wave: never more CTAs than are co-resident (2 per SM)
+    const long long most = (rows_per_sample + T - 1) / T;
+    if (schunks > most) schunks = most;
+    if (schunks > chunks) schunks = chunks;  // the workspace was sized for `chunks`
+    if (schunks < 1) schunks = 1;
+    const size_t ring_bytes = static_cast<size_t>(kGnStages) * T * row_bytes;
+    const size_t scratch = (static_cast<size_t>(rpp_) + 1) * 2 * channels * sizeof(float);
+    static bool attr2 = false;
+    if (!attr2) {
+      LVD_CHECK_CUDA(cudaFuncSetAttribute(gn_stream_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
+      LVD_CHECK_CUDA(cudaFuncSetAttribute(gn_stream_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
+      attr2 = true;
+    }
+    if (threads <= 320 && ring_bytes + scratch <= 225 * 1024) {
+    dim3 sgrid(static_cast<unsigned>(schunks), static_cast<unsigned>(samples));
+    gn_stream_stats_kernel<<<sgrid, threads, ring_bytes + scratch, st>>>(
+        static_cast<const __half*>(x), ld_x, rows_per_sample, channels, groups, static_cast<int>(schunks), T,
+        static_cast<float*>(workspace), static_cast<float>(rows_per_sample) * (channels / groups), eps, stats);
+    gn_stream_apply_kernel<<<sgrid, threads, ring_bytes, st>>>(
+        static_cast<const __half*>(x), ld_x, static_cast<__half*>(y), ld_y, rows_per_sample, channels, groups,
+        static_cast<int>(schunks), T, stats, static_cast<const __half*>(gamma), static_cast<const __half*>(beta), silu);
+    } else {  // very wide rows: register-staged passes
+      dim3 grid(static_cast<unsigned>(chunks), static_cast<unsigned>(samples));
+      const size_t smem_stats = (static_cast<size_t>(rpp_) + 1) * 2 * channels * sizeof(float);
+      gn_stats_kernel<<<grid, threads, smem_stats, st>>>(
+          static_cast<const __half*>(x), ld_x, rows_per_sample, channels, groups, static_cast<int>(chunks),
+          static_cast<float*>(workspace), static_cast<float>(rows_per_sample) * (channels / groups), eps, stats);
+      gn_apply_kernel<<<grid, threads, 0, st>>>(static_cast<const __half*>(x), ld_x, static_cast<__half*>(y), ld_y,
+                                                rows_per_sample, channels, groups, stats,
+                                                static_cast<const __half*>(gamma), static_cast<const __half*>(beta),
+                                                silu, static_cast<int>(chunks));
+    }
+  }
+  g_launches.fetch_add(2, std::memory_order_relaxed);
   LVD_CHECK_CUDA(cudaGetLastError());
   return LVD_OK;
 }
@@ -322,24 +673,37 @@ extern "C" int lvd_layernorm(const void* x, int64_t ld_x, void* y, int64_t ld_y,
   LVD_REQUIRE(ld_x % 8 == 0 && ld_y % 8 == 0, "lvd_layernorm: ld must be a multiple of 8");
   if (rows <= 0) return LVD_OK;
   const int warps = 8;
-  long long blocks = (rows + warps - 1) / warps;
+  const int vpr = channels / 8;
+  const int lanes = vpr <= 8 * kLnMaxVec ? 8 : (vpr <= 16 * kLnMaxVec ? 16 : 32);  // lanes per row
+  const int nv = (vpr + lanes - 1) / lanes;
+  // R row sets in flight per warp; small problems (fewer than ~2 warps per scheduler slot) take R = 1 to fill the SMs
+  int rsets = nv <= 2 ? 4 : (nv <= 5 ? 3 : 2);
+  if (rows / ((32 / lanes) * rsets) < 16LL * num_sms()) rsets = 1;
+  const int rows_per_warp = (32 / lanes) * rsets;
+  long long blocks = (rows + warps * rows_per_warp - 1) / (warps * rows_per_warp);
   const long long cap = 16LL * num_sms();
   if (blocks > cap) blocks = cap;
-  const int nv = (channels / 8 + 31) / 32;
-#define LVD_LN_LAUNCH(NV)                                                                                         \
-  layernorm_kernel<NV><<<static_cast<unsigned>(blocks), warps * 32, 2 * channels * sizeof(float),                \
-                         static_cast<cudaStream_t>(stream)>>>(                                                   \
+#define LVD_LN_LAUNCH(NV, L, R)                                                                                   \
+  layernorm_kernel<NV, L, R><<<static_cast<unsigned>(blocks), warps * 32, 2 * channels * sizeof(__half),         \
+                               static_cast<cudaStream_t>(stream)>>>(                                             \
       static_cast<const __half*>(x), ld_x, static_cast<__half*>(y), ld_y, rows, channels,                        \
       static_cast<const __half*>(gamma), static_cast<const __half*>(beta), eps)
-  if (nv <= 2) {
-    LVD_LN_LAUNCH(2);
-  } else if (nv <= 3) {
-    LVD_LN_LAUNCH(3);
-  } else if (nv <= 5) {
-    LVD_LN_LAUNCH(5);
-  } else {
-    LVD_LN_LAUNCH(8);
+#define LVD_LN_LANES(L)                                          \
+  if (nv <= 2) {                                                 \
+    if (rsets == 1) LVD_LN_LAUNCH(2, L, 1); else LVD_LN_LAUNCH(2, L, 4); \
+  } else if (nv <= 5) {                                          \
+    if (rsets == 1) LVD_LN_LAUNCH(5, L, 1); else LVD_LN_LAUNCH(5, L, 3); \
+  } else {                                                       \
+    if (rsets == 1) LVD_LN_LAUNCH(8, L, 1); else LVD_LN_LAUNCH(8, L, 2); \
   }
+  if (lanes == 8) {
+    LVD_LN_LANES(8)
+  } else if (lanes == 16) {
+    LVD_LN_LANES(16)
+  } else {
+    LVD_LN_LANES(32)
+  }
+#undef LVD_LN_LANES
 #undef LVD_LN_LAUNCH
   g_launches.fetch_add(1, std::memory_order_relaxed);
   LVD_CHECK_CUDA(cudaGetLastError());

@@ -286,7 +286,7 @@ def groupnorm(x, samples, gamma, beta, eps, *, groups=32, silu=False, out=None, 
     if out is None:
         out = _alloc_out(rows, c, x)
     ws = _gn_workspace(x.device, samples, groups)
-    with _Timed("groupnorm", 0.0, 2.0 * rows * c * 2):
+    with _Timed("groupnorm", 0.0, 2.0 * rows * c * 2, "gn s%d r%d c%d" % (samples, rows // samples, c)):
         _lib.check(_lib.lib().lvd_groupnorm(x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), samples,
                                             rows // samples, c, groups, gamma.data_ptr(), beta.data_ptr(), float(eps),
                                             1 if silu else 0, stats_out.data_ptr() if stats_out is not None else None,
@@ -299,7 +299,7 @@ def layernorm(x, gamma, beta, eps=1e-5, out=None):
     rows, c = x.shape
     if out is None:
         out = _alloc_out(rows, c, x)
-    with _Timed("layernorm", 0.0, 2.0 * rows * c * 2):
+    with _Timed("layernorm", 0.0, 2.0 * rows * c * 2, "ln r%d c%d" % (rows, c)):
         _lib.check(_lib.lib().lvd_layernorm(x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), rows, c,
                                             gamma.data_ptr(), beta.data_ptr(), float(eps), _stream()), "layernorm")
     return out
@@ -333,7 +333,8 @@ def attention(q, kv, *, heads, nz, s_q=0, s_k=0, q_col0=0, k_col0=0, v_col0=0, k
         fl, fam = 4.0 * nz * hw * heads * frames * frames * 64, "attention_temporal"
     else:
         fl, fam = 4.0 * nz * heads * s_q * s_k * 64, ("attention_self" if kv is q else "attention_cross")
-    with _Timed(fam, fl, 2.0 * (q.shape[0] * heads * 64 * 2 + kv.shape[0] * heads * 128)):
+    with _Timed(fam, fl, 2.0 * (q.shape[0] * heads * 64 * 2 + kv.shape[0] * heads * 128),
+                "%s nz%d h%d sq%d sk%d f%d" % (fam, nz, heads, s_q, s_k, frames)):
         _lib.check(_lib.lib().lvd_attention(ctypes.byref(d), _stream()), "attention")
     return out
 
@@ -524,7 +525,7 @@ def groupnorm_bwd(x, dz, samples, gamma, beta, eps, *, groups=32, silu=False, ou
         assert not accumulate
         out = _alloc_out(rows, c, x)
     ws = _gn_workspace2(x.device, samples, groups)
-    with _Timed("groupnorm_bwd", 0.0, 2.0 * rows * c * 4):
+    with _Timed("groupnorm_bwd", 0.0, 2.0 * rows * c * 4, "gnb s%d r%d c%d" % (samples, rows // samples, c)):
         _lib.check(_lib.lib().lvd_groupnorm_bwd(x.data_ptr(), x.stride(0), dz.data_ptr(), dz.stride(0), out.data_ptr(),
                                                 out.stride(0), samples, rows // samples, c, groups, gamma.data_ptr(),
                                                 beta.data_ptr(), float(eps), 1 if silu else 0, 1 if accumulate else 0,
@@ -540,7 +541,7 @@ def layernorm_bwd(x, dy, gamma, eps=1e-5, *, out=None, accumulate=False):
     if out is None:
         assert not accumulate
         out = _alloc_out(rows, c, x)
-    with _Timed("layernorm_bwd", 0.0, 2.0 * rows * c * 3):
+    with _Timed("layernorm_bwd", 0.0, 2.0 * rows * c * 3, "lnb r%d c%d" % (rows, c)):
         _lib.check(_lib.lib().lvd_layernorm_bwd(x.data_ptr(), x.stride(0), dy.data_ptr(), dy.stride(0), out.data_ptr(),
                                                 out.stride(0), rows, c, gamma.data_ptr(), float(eps),
                                                 1 if accumulate else 0, _stream()), "layernorm_bwd")
