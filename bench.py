@@ -63,6 +63,8 @@ def parse():
     ap.add_argument("--unguided", action="store_true", help="time the unguided CFG step only")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="lvd_b200", choices=["lvd_b200", "reference"])
+    ap.add_argument("--workload", default="lvd_zeroscope", choices=list(WORKLOADS),
+                    help="BASELINE.json config: lvd_zeroscope is the headline (config 2)")
     ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-frames", type=int, default=2)
@@ -188,12 +190,32 @@ def cpu_reference_step(sample_frames, steps, warmup, guided_every=GUIDED_EVERY):
     return sample_frames / sec, sec, cores, sec_g, sec_u
 
 
-def _workload(unguided):
-    if unguided:
-        return "lvd_zeroscope 1 prompt/GPU, 24 frames 576x320 (72x40 latent), unguided CFG denoising step"
-    return ("lvd_zeroscope 1 prompt/GPU, 24 frames 576x320 (72x40 latent), 50-step schedule pattern: step i runs one "
-            "backward-guidance iteration (6 guided cross-attention keys, demo 'bear' layout) iff i % 5 == 0 "
-            "(= 10 guided of 50), then the CFG UNet forward (B=2) + CFG combine + DPM-Solver++ update")
+# BASELINE.json configs 2-4: algorithmic TFLOP per CFG forward / guidance iteration from section 8(d)
+WORKLOADS = {
+    "lvd_zeroscope": dict(model="Zeroscope", frames=24, h=40, w=72, gated=False, guided=True, cfg_tflop=42.79,
+                          cfg_tflop_fusers=None, guid_tflop=32.59),
+    "lvd_gligen_zeroscope": dict(model="Zeroscope + GLIGEN", frames=24, h=40, w=72, gated=True, guided=False,
+                                 cfg_tflop=42.79, cfg_tflop_fusers=52.885, guid_tflop=0.0),
+    "lvd_gligen_zeroscope_guided": dict(model="Zeroscope + GLIGEN", frames=24, h=40, w=72, gated=True, guided=True,
+                                        cfg_tflop=42.79, cfg_tflop_fusers=52.885, guid_tflop=32.59),
+    "lvd_plus_modelscope256": dict(model="ModelScope-256 + GLIGEN", frames=16, h=32, w=32, gated=True, guided=True,
+                                   cfg_tflop=9.77, cfg_tflop_fusers=11.803, guid_tflop=7.48),
+}
+
+
+def _workload(name="lvd_zeroscope", unguided=False):
+    wl = WORKLOADS[name]
+    shape = f"{wl['frames']} frames {wl['w'] * 8}x{wl['h'] * 8} ({wl['w']}x{wl['h']} latent)"
+    parts = [f"{name} 1 prompt/GPU, {shape}, 50-step schedule pattern:"]
+    if wl["guided"] and not unguided:
+        parts.append("step i runs one backward-guidance iteration (6 guided cross-attention keys, demo 'bear' layout) "
+                     "iff i % 5 == 0 (= 10 guided of 50);")
+    if wl["gated"]:
+        parts.append("GLIGEN fusers enabled iff i % 5 < 2 (= 20 of 50, beta 0.4);")
+    parts.append("then the CFG UNet forward (B=2) + CFG combine + DPM-Solver++ update")
+    if unguided and not wl["gated"]:
+        return f"{name} 1 prompt/GPU, {shape}, unguided CFG denoising step"
+    return " ".join(parts)
 
 
 def run_reference(args):
@@ -210,7 +232,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": _workload(args.unguided), "sample": sample},
+        "config": {"workload": _workload("lvd_zeroscope", args.unguided), "sample": sample},
         "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -219,6 +241,24 @@ def run_reference(args):
 
 
 # ---------------------------------------------------------------------------------------------- GPU arm
+def gligen_inputs(frames, bboxes, dev, gen):
+    """30-slot padded grounding inputs as the pipeline builds them (controllable_pipeline...py:738-814): CFG batch of 2,
+    the unconditional half masked out.  Phrase embeddings are synthetic (the text encoder is outside the hot path)."""
+    import torch
+    n_obj = len(bboxes)
+    boxes = torch.zeros((2, frames, 30, 4))
+    emb = torch.zeros((2, frames, 30, 1024))
+    masks = torch.zeros((2, frames, 30))
+    phrase = torch.randn((n_obj, 1024), generator=gen)
+    for o in range(n_obj):
+        for f in range(frames):
+            boxes[:, f, o] = torch.tensor(bboxes[o][f])
+        emb[:, :, o] = phrase[o]
+        masks[1, :, o] = 1
+    return {"boxes": boxes.flatten(0, 1).half().to(dev), "positive_embeddings": emb.flatten(0, 1).half().to(dev),
+            "masks": masks.flatten(0, 1).half().to(dev)}
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
@@ -226,10 +266,13 @@ def run_gpu(args):
     import __graft_entry__ as ge
     ge.build()
     from lvd_b200 import _lib, ops, synthetic
-    from lvd_b200.engine import UNetEngine
-    from lvd_b200.guidance_engine import GRAD_SCALE, GuidanceGraph
+    from lvd_b200.models import pipelines
+    from lvd_b200.models.pipelines import latent_backward_guidance
+    from lvd_b200.models.unet_3d_condition import UNet3DConditionModel
     from lvd_b200.scheduler import DPMSolverMultistepScheduler
 
+    wl = WORKLOADS[args.workload]
+    frames, lat_h, lat_w = wl["frames"], wl["h"], wl["w"]
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -240,82 +283,63 @@ def run_gpu(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    cfg = synthetic.make_cfg("zeroscope")
-    sd = synthetic.random_state_dict(cfg, seed=0, dtype=torch.float16)
-    eng = UNetEngine(cfg, sd, device=dev)
-    del sd
+    # the reference's own model class (mirror) with seeded random weights of the Zeroscope / ModelScope architecture
+    unet = UNet3DConditionModel(sample_size=32, attention_type="gated" if wl["gated"] else "default")
+    unet.to(dev)
+    unet.load_state_dict(synthetic.random_state_dict(unet._cfg, seed=0, dtype=torch.float16))
+    eng = unet._engine
 
     # one independent work item (prompt) per rank: NCCL only carries the seed scatter and the timing reduction
     seeds = torch.arange(world, dtype=torch.int64, device=dev) + 1234
     if world > 1:
         dist.broadcast(seeds, src=0)
     g = torch.Generator().manual_seed(int(seeds[rank].item()))
-    lat_host = torch.randn((1, 4, FRAMES, LAT_H, LAT_W), generator=g).half().pin_memory()
+    lat_host = torch.randn((1, 4, frames, lat_h, lat_w), generator=g).half().pin_memory()
     ehs_host = torch.randn((2, 77, 1024), generator=g).half().pin_memory()
+    out_host = torch.empty((1, 4, frames, lat_h, lat_w), dtype=torch.float16).pin_memory()
 
     sched = DPMSolverMultistepScheduler()
     sched.set_timesteps(50)
-    n_img = 2 * FRAMES
-    static_x = torch.empty((2, 4, FRAMES, LAT_H, LAT_W), dtype=torch.float16, device=dev)
-    static_t = torch.empty((n_img,), dtype=torch.float32, device=dev)
-    static_ehs = ehs_host.to(dev)
+    prompt_embeds = ehs_host.to(dev)
     latents = lat_host.to(dev)
-    state = {"out": None, "graph": None}
+    bboxes, positions = bear_layout(frames)
+    guided_every = GUIDED_EVERY if (wl["guided"] and not args.unguided) else 0
+    gl_in = gligen_inputs(frames, bboxes, dev, g) if wl["gated"] else None
+    guidance_kw = dict(bboxes=bboxes, object_positions=positions, guidance_attn_keys=GUIDANCE_KEYS,
+                       loss_scale=GUIDANCE_LOSS_SCALE, loss_threshold=0.0, max_iter=1, max_index_step=10,
+                       base_attn_dim=(lat_h, lat_w), **GUIDANCE_HP)
+    import warnings
+    warnings.filterwarnings("ignore", message="Using guidance scaled")
 
-    def forward_eager():
-        state["out"] = eng.forward(static_x, static_t, static_ehs)
+    def fusers_on(i):  # GLIGEN scheduled sampling beta = 0.4 (README.md:83): fusers enabled on 2 of every 5 steps
+        return wl["gated"] and (i % 5) < 2
 
-    graph = GuidanceGraph(eng)
-    bboxes, positions = bear_layout(FRAMES)
-    guided_every = 0 if args.unguided else GUIDED_EVERY
-    cond = static_ehs[1:2]
-    loss_host = torch.zeros((), dtype=torch.float32).pin_memory()
-
-    def guidance_iteration(i):
-        """One iteration of latent_backward_guidance's loop (models/pipelines.py:65-137) on the native pass."""
-        nonlocal latents
-        tt = int(sched.timesteps[i % 50])
-        loss, grad = graph.run(latents, tt, cond, bboxes, positions, GUIDANCE_KEYS, loss_scale=GUIDANCE_LOSS_SCALE,
-                               base_attn_dim=(LAT_H, LAT_W), **GUIDANCE_HP)
-        scale = (1.0 - float(sched.alphas_cumprod[tt])) ** 0.5
-        latents, _ = ops.latent_update(latents, grad, scale, 1.0 / GRAD_SCALE)
-        loss_host.copy_(loss, non_blocking=True)  # the 4-byte D2H the reference's while-condition needs
+    def set_fusers(on):
+        for m in unet.modules():
+            if type(m).__name__ == "GatedSelfAttentionDense":
+                m.enabled = on
 
     def denoise_step(i):
-        """One denoising-loop iteration on device-resident inputs (latents updated in place)."""
+        """One iteration of the reference's loop body (controllable_pipeline...py:836-958) through the public mirrors:
+        latent_backward_guidance -> UNet3DConditionModel.forward (CFG batch) -> fused CFG combine + DPM-Solver++ step."""
         nonlocal latents
+        t = sched.timesteps[i % 50]
+        if wl["gated"]:
+            set_fusers(fusers_on(i))
         if guided_every and i % guided_every == 0:
-            guidance_iteration(i)
-        static_x[0].copy_(latents[0])
-        static_x[1].copy_(latents[0])
-        static_t.fill_(float(sched.timesteps[i % 50]))
-        if state["graph"] is not None and ops.PROF is None:
-            state["graph"].replay()
-        else:
-            forward_eager()
-        eps = state["out"]
+            latents, _ = latent_backward_guidance(sched, unet, prompt_embeds[1:2], index=0, t=t, latents=latents,
+                                                  loss=torch.tensor(10000.0), **guidance_kw)
+        kw = {"gligen": gl_in} if wl["gated"] else {}
+        eps = unet(torch.cat([latents] * 2), t, encoder_hidden_states=prompt_embeds, cross_attention_kwargs=kw,
+                   return_dict=False)[0]
         if sched._step_index >= 49:
             sched._reset()
         latents = sched.step_cfg(eps[0:1], eps[1:2], latents, GUIDANCE_SCALE)
 
-    # warm-up (also sets kernel attributes before any graph capture)
-    for i in range(max(3, args.warmup)):
+    unet.use_cuda_graph = not args.no_graph
+    for i in range(max(3, args.warmup) + 5):  # warm-up: every (fuser on/off) variant is seen, captured and replayed once
         denoise_step(i)
     torch.cuda.synchronize()
-    use_graph = not args.no_graph
-    if use_graph:
-        try:
-            gr = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(gr):
-                forward_eager()
-            state["graph"] = gr
-            denoise_step(0)
-            torch.cuda.synchronize()
-        except Exception as e:  # graph capture is an optimisation of launch overhead, not a different code path
-            sys.stderr.write(f"[bench] CUDA graph capture failed ({e}); running eagerly\n")
-            state["graph"] = None
-            use_graph = False
-            torch.cuda.synchronize()
 
     def barrier():
         if world > 1:
@@ -326,7 +350,6 @@ def run_gpu(args):
     sampler = ClockSampler(local)
     sampler.start()
     time.sleep(0.3)
-    launches0 = _lib.lib().lvd_launch_count()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -335,16 +358,13 @@ def run_gpu(args):
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
-    launches = _lib.lib().lvd_launch_count() - launches0
-    # a CUDA graph replays the captured launches without re-entering the library: count them from one eager step
-    # ---------------- timed region 2: end to end with host buffers
-    out_host = torch.empty((1, 4, FRAMES, LAT_H, LAT_W), dtype=torch.float16).pin_memory()
+    # ---------------- timed region 2: end to end with host buffers (same public calls; H2D in, D2H out, every step)
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
     for i in range(args.steps):
-        latents.copy_(lat_host, non_blocking=True)
-        static_ehs.copy_(ehs_host, non_blocking=True)
+        latents = lat_host.to(dev, non_blocking=True)
+        prompt_embeds = ehs_host.to(dev, non_blocking=True)
         denoise_step(i)
         out_host.copy_(latents, non_blocking=True)
         torch.cuda.current_stream().synchronize()
@@ -359,7 +379,7 @@ def run_gpu(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, ms_e2e = float(t[0]), float(t[1])
 
-    # ---------------- separate timings of the two step kinds (device events, resident inputs)
+    # ---------------- separate timings of the step kinds (device events, resident inputs)
     def time_steps(idx):
         torch.cuda.synchronize()
         a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -370,32 +390,45 @@ def run_gpu(args):
         torch.cuda.synchronize()
         return a.elapsed_time(b_) / len(idx)
 
-    ms_unguided = time_steps([1, 2, 3])
-    ms_guided = time_steps([0, 5]) if guided_every else None
+    ms_unguided = time_steps([2, 3, 4])          # fusers off, no guidance
+    ms_fused = time_steps([1, 6]) if wl["gated"] else None   # fusers on, no guidance
+    ms_guided = time_steps([0, 5]) if guided_every else None  # guidance (+ fusers when gated)
 
-    # ---------------- instrumented step: per-kernel-family durations (CUDA events around every launch)
+    # ---------------- instrumented passes: per-kernel-family durations (CUDA events around every launch), eager
+    lib = _lib.lib()
+    set_fusers(False)
+    x2 = torch.cat([latents] * 2)
     ops.PROF = []
-    l0 = _lib.lib().lvd_launch_count()
-    static_t.fill_(float(sched.timesteps[0]))
-    forward_eager()
+    l0 = lib.lvd_launch_count()
+    eng.forward(x2, float(sched.timesteps[0]), prompt_embeds)
     torch.cuda.synchronize()
-    launches_per_forward = _lib.lib().lvd_launch_count() - l0
+    launches_per_forward = lib.lvd_launch_count() - l0
     n_fwd_records = len(ops.PROF)
     launches_per_guidance = 0
     if guided_every:
-        l1 = _lib.lib().lvd_launch_count()
-        guidance_iteration(0)
+        l1 = lib.lvd_launch_count()
+        latent_backward_guidance(sched, unet, prompt_embeds[1:2], index=0, t=sched.timesteps[0], latents=latents,
+                                 loss=torch.tensor(10000.0), **guidance_kw)
         torch.cuda.synchronize()
-        launches_per_guidance = _lib.lib().lvd_launch_count() - l1
+        launches_per_guidance = lib.lvd_launch_count() - l1
+    prof = ops.PROF
+    ops.PROF = None
+    launches_per_fused_forward = launches_per_forward
+    if wl["gated"]:
+        set_fusers(True)
+        l2 = lib.lvd_launch_count()
+        eng.forward(x2, float(sched.timesteps[0]), prompt_embeds, gligen=gl_in)
+        torch.cuda.synchronize()
+        launches_per_fused_forward = lib.lvd_launch_count() - l2
     fam = {}
     fam_guid = {}
     shapes = ({}, {})
-    for k_, (name, fl, nb, s, e, tag) in enumerate(ops.PROF):
+    for k_, (name, fl, nb, s, e, tag) in enumerate(prof):
         d = (fam if k_ < n_fwd_records else fam_guid).setdefault(name, {"ms": 0.0, "flops": 0.0, "bytes": 0.0,
                                                                         "launches": 0})
         if tag is not None:
             sd = shapes[0 if k_ < n_fwd_records else 1].setdefault(tag, {"ms": 0.0, "flops": 0.0, "bytes": 0.0,
-                                                                                  "launches": 0})
+                                                                         "launches": 0})
             sd["ms"] += s.elapsed_time(e)
             sd["flops"] += fl
             sd["bytes"] += nb
@@ -404,10 +437,12 @@ def run_gpu(args):
         d["flops"] += fl
         d["bytes"] += nb
         d["launches"] += 1
-    ops.PROF = None
-    if use_graph:
-        n_guided = sum(1 for i in range(args.steps) if guided_every and i % guided_every == 0)
-        launches = (launches_per_forward + 1) * args.steps + (launches_per_guidance + 1) * n_guided
+    # kernels of this library launched inside timed region 1 (graph replays re-run the captured launches)
+    launches = 0
+    for i in range(args.steps):
+        launches += (launches_per_fused_forward if fusers_on(i) else launches_per_forward) + 1
+        if guided_every and i % guided_every == 0:
+            launches += launches_per_guidance
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -417,7 +452,7 @@ def run_gpu(args):
     peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1.4 PFLOP/s sustained"
     gm = dict(fam.get("gemm_tc_kernel", {"ms": 1.0, "flops": 0.0, "launches": 1}))
     gg = fam_guid.get("gemm_tc_kernel")
-    if gg:  # one guided step = CFG forward + one guidance iteration: the dominant kernel's launches of both
+    if gg:  # the timed step mix = CFG forward + 1/5 guidance iteration: the dominant kernel's launches of both
         share = 1.0 / GUIDED_EVERY
         gm = {"ms": gm["ms"] + share * gg["ms"], "flops": gm["flops"] + share * gg["flops"],
               "launches": gm["launches"] + share * gg["launches"], "bytes": gm.get("bytes", 0.0) + share * gg["bytes"]}
@@ -425,7 +460,9 @@ def run_gpu(args):
     traffic, traffic_src = None, None
     try:  # DRAM bytes per gemm_tc_kernel launch from the committed ncu capture (profiles/, measured, not live)
         tj = json.load(open(os.path.join(ROOT, "profiles", "r1_gemm_traffic.json")))
-        traffic, traffic_src = tj["traffic_bytes_per_launch"], "profiles/r1_gemm_traffic.json (ncu dram__bytes_*.sum)"
+        if args.workload == "lvd_zeroscope":
+            traffic = tj["traffic_bytes_per_launch"]
+            traffic_src = "profiles/r1_gemm_traffic.json (ncu dram__bytes_*.sum)"
     except Exception:
         pass
     roofline = {"bound": "tensor", "kernel": "gemm_tc_kernel", "achieved": achieved, "peak": peak_tf,
@@ -435,50 +472,55 @@ def run_gpu(args):
                 "launches_per_step": gm["launches"], "ms_per_step": gm["ms"],
                 "share_of_instrumented_step": gm["ms"] / max(1e-9, sum(v["ms"] for v in fam.values()) + (
                     sum(v["ms"] for v in fam_guid.values()) / GUIDED_EVERY if fam_guid else 0.0)),
-                "note": "FLOPs and CUDA-event time summed over all gemm_tc_kernel launches of one CFG forward plus "
-                        "1/5 of one guidance iteration (the timed step mix), instrumented pass after the timed region"}
+                "note": "FLOPs and CUDA-event time summed over all gemm_tc_kernel launches of one CFG forward (fusers "
+                        "off) plus 1/5 of one guidance iteration when the workload is guided; instrumented eager pass "
+                        "after the timed region"}
     if args.profile_json and rank == 0:
         json.dump({"cfg_forward": fam, "guidance_iteration": fam_guid, "gemm_shapes_cfg_forward": shapes[0],
                    "gemm_shapes_guidance_iteration": shapes[1]}, open(args.profile_json, "w"), indent=1)
 
     if rank == 0:
         ms_step = ms / args.steps
-        value = world * FRAMES / (ms_step * 1e-3)
-        e2e_val = world * FRAMES / (ms_e2e / args.steps * 1e-3)
+        value = world * frames / (ms_step * 1e-3)
+        e2e_val = world * frames / (ms_e2e / args.steps * 1e-3)
+        n_fused = sum(1 for i in range(5) if fusers_on(i)) / 5.0
+        tflop_step = (wl["cfg_tflop"] * (1 - n_fused) + (wl["cfg_tflop_fusers"] or 0.0) * n_fused +
+                      (wl["guid_tflop"] / GUIDED_EVERY if guided_every else 0.0))
+        fps = lambda m: None if m is None else {"ms": m, "frames_per_s": world * frames / (m * 1e-3)}  # noqa: E731
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "warmup": max(3, args.warmup) + 5, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f16", "data": "synthetic",
-            "config": {"workload": _workload(args.unguided),
-                       "weights": "seeded random init of the Zeroscope UNet3D config (1411.2 M params), fp16",
+            "config": {"workload": _workload(args.workload, args.unguided),
+                       "weights": f"seeded random init of the {wl['model']} UNet3D config "
+                                  f"({'1623.8' if wl['gated'] else '1411.2'} M params), fp16",
                        "parallelism": f"replicas x{world} (independent prompts, no data-path collective)",
                        "l2": "inputs larger than L2 (2.8 GB weights + >20 GB activations per step vs 126 MB)",
-                       "cuda_graph": "CFG forward replayed from a CUDA graph; guidance pass eager" if use_graph else False,
-                       "algorithmic_tflop_per_step": CFG_FWD_TFLOP + (GUID_ITER_TFLOP / GUIDED_EVERY if guided_every
-                                                                      else 0.0),
+                       "api": "lvd_b200.models: latent_backward_guidance + UNet3DConditionModel.forward + "
+                              "DPMSolverMultistepScheduler.step_cfg (the reference pipeline's loop body)",
+                       "cuda_graph": "UNet3DConditionModel.forward replays a CUDA graph per input shape; guidance pass "
+                                     "eager" if unet.use_cuda_graph else False,
+                       "algorithmic_tflop_per_step": tflop_step,
                        "guidance": None if not guided_every else {
                            "keys": GUIDANCE_KEYS, "layout": "demo bear, 1 object, token 2", "iterations_per_guided_step": 1,
-                           "loss_scale": GUIDANCE_LOSS_SCALE, **GUIDANCE_HP}},
-            "unguided_step": {"ms": ms_unguided, "frames_per_s": world * FRAMES / (ms_unguided * 1e-3)},
-            "guided_step": None if ms_guided is None else {"ms": ms_guided,
-                                                           "frames_per_s": world * FRAMES / (ms_guided * 1e-3)},
+                           "loss_scale": GUIDANCE_LOSS_SCALE, **GUIDANCE_HP},
+                       "gligen": None if not wl["gated"] else "30-slot grounding tokens, fusers enabled on 2 of 5 steps "
+                                                              "(scheduled sampling beta 0.4)"},
+            "unguided_step": fps(ms_unguided), "fuser_step": fps(ms_fused), "guided_step": fps(ms_guided),
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": lat_host.numel() * 2 + ehs_host.numel() * 2,
-                    "d2h_bytes_per_step": out_host.numel() * 2},
+                    "d2h_bytes_per_step": out_host.numel() * 2 + (4 if guided_every else 0)},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": roofline,
-            "step_tflops": (CFG_FWD_TFLOP + (GUID_ITER_TFLOP / GUIDED_EVERY if guided_every else 0.0)) / (ms_step * 1e-3),
+            "step_tflops": tflop_step / (ms_step * 1e-3),
             "kernel_families_ms": {k: round(v["ms"], 3) for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])},
             "guidance_families_ms": {k: round(v["ms"], 3) for k, v in sorted(fam_guid.items(),
                                                                             key=lambda kv: -kv[1]["ms"])},
         }
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and args.workload == "lvd_zeroscope":
             # one guided + one unguided step on the CPU, combined with the schedule weights 1:4
-            _, _, cores, sec_g, sec_u = cpu_reference_step(args.cpu_sample_frames, 2, 0, 0 if args.unguided else 2)
-            if args.unguided:
-                sec = sec_u
-            else:
-                sec = (sec_g + (GUIDED_EVERY - 1) * sec_u) / GUIDED_EVERY
+            _, _, cores, sec_g, sec_u = cpu_reference_step(args.cpu_sample_frames, 2, 0, 2 if guided_every else 0)
+            sec = (sec_g + (GUIDED_EVERY - 1) * sec_u) / GUIDED_EVERY if guided_every else sec_u
             line["cpu_baseline"] = {
                 "value": args.cpu_sample_frames / sec, "unit": UNIT, "cores": cores, "kind": "port",
                 "sample": f"same step mix on {args.cpu_sample_frames} of 24 frames (72x40 latent, full UNet), fp32, "

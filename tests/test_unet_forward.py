@@ -133,3 +133,43 @@ def test_unet_mirror_api_and_golden(cuda):
     with pytest.raises(NotImplementedError):
         m(torch.zeros(1, 4, 2, 8, 8).half().cuda(), 1, encoder_hidden_states=torch.zeros(1, 77, 128).half().cuda(),
           cross_attention_kwargs={}, attention_mask=torch.ones(1, 1))
+
+
+def test_unet_mirror_graph_replay_is_bit_identical_to_eager(cuda):
+    """UNet3DConditionModel.forward replays a CUDA graph from the second call of a shape on (launch sequencing only):
+    eager call, capture call and replays must agree bit for bit, also with GLIGEN fusers toggled between calls."""
+    from lvd_b200.models.unet_3d_condition import UNet3DConditionModel
+    from oracle import weights
+    cfg = weights.make_cfg("tiny", gated=True)
+    sd = {k: v.half() for k, v in weights.random_state_dict(cfg, seed=5).items()}
+    unet = UNet3DConditionModel(sample_size=16, block_out_channels=cfg["block_out_channels"],
+                                cross_attention_dim=cfg["cross_attention_dim"], attention_type="gated")
+    unet.to(cuda)
+    unet.load_state_dict(sd)
+    g = torch.Generator().manual_seed(6)
+    b, f, h, w = 2, 8, 16, 16
+    xs = [torch.randn((b, 4, f, h, w), generator=g).half().to(cuda) for _ in range(3)]
+    ehs = torch.randn((b, 77, cfg["cross_attention_dim"]), generator=g).half().to(cuda)
+    gl = dict(boxes=torch.rand((b * f, 30, 4), generator=g).half().to(cuda),
+              positive_embeddings=torch.randn((b * f, 30, cfg["cross_attention_dim"]), generator=g).half().to(cuda),
+              masks=(torch.rand((b * f, 30), generator=g) > 0.5).half().to(cuda))
+
+    def fusers(on):
+        for m in unet.modules():
+            if type(m).__name__ == "GatedSelfAttentionDense":
+                m.enabled = on
+
+    ref = {}
+    unet.use_cuda_graph = False
+    for on in (True, False):
+        fusers(on)
+        for i, x in enumerate(xs):
+            ref[(on, i)] = unet(x, 300 + i, ehs, cross_attention_kwargs={"gligen": gl}, return_dict=False)[0].clone()
+    unet.use_cuda_graph = True
+    for rep in range(3):  # eager first sighting, capture, replay
+        for on in (True, False):
+            fusers(on)
+            for i, x in enumerate(xs):
+                y = unet(x, 300 + i, ehs, cross_attention_kwargs={"gligen": gl}, return_dict=False)[0]
+                assert torch.equal(y, ref[(on, i)]), (rep, on, i)
+    assert not torch.equal(ref[(True, 0)], ref[(False, 0)])
