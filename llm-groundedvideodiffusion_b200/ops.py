@@ -452,8 +452,33 @@ def _gn_workspace2(dev, samples, groups):
     return _gn_workspace(dev, 2 * samples, groups)
 
 
+# The adjoint GEMMs contract over the forward's output channels.  Reading the forward weight MN-major needs no copy but
+# restricts the tile width to multiples of 64 (N = 320 -> 64-wide tiles at ~450 TFLOP/s); with 180 GB of HBM a K-major
+# transposed copy per weight (made once, on first use: +2.8 GB for the whole guidance prefix) lets the adjoints run the
+# same 160/256-wide tiles and CTA pairs as the forward.  DGRAD_TRANSPOSED = False restores the zero-copy path.
+DGRAD_TRANSPOSED = True
+
+
+def _dgrad_weight(w, taps):
+    """forward weight [Cout, taps*Cin] (K ordered (tap, ci)) -> [Cin, taps*Cout] (K ordered (tap, co)); the copy is
+    cached on the weight tensor object itself, so it lives exactly as long as the weight."""
+    cache = getattr(w, "_lvd_dgrad", None)
+    if cache is None:
+        cache = {}
+        w._lvd_dgrad = cache
+    t = cache.get(taps)
+    if t is None:
+        cout = w.shape[0]
+        cin = w.shape[1] // taps
+        t = w.reshape(cout, taps, cin).permute(2, 1, 0).reshape(cin, taps * cout).contiguous()
+        cache[taps] = t
+    return t
+
+
 def linear_dgrad(dy, w, *, residual=None, out=None, row_map=None):
-    """dx = dy @ w  for a forward y = x @ w.T (w [N_out, K_in], as stored for the forward; read MN-major)."""
+    """dx = dy @ w  for a forward y = x @ w.T (w [N_out, K_in], as stored for the forward)."""
+    if DGRAD_TRANSPOSED:
+        return linear(dy, _dgrad_weight(w, 1), residual=residual, out=out, row_map=row_map)
     return linear(dy, w, b_mn_major=True, n=w.shape[1], residual=residual, out=out, row_map=row_map)
 
 
@@ -469,6 +494,11 @@ def conv2d_3x3_dgrad(dy, n_img, h, w_, wk, *, residual=None, out=None):
     ld = dy.stride(0)
     bw, bh, bn = choose_box((w_, h, n_img))
     taps = [(0, -dx, -dy_, 0, 0) for dy_ in (-1, 0, 1) for dx in (-1, 0, 1)]
+    if DGRAD_TRANSPOSED:
+        return gemm_raw(a=dy, a_dims=(cout, w_, h, n_img, 1),
+                        a_strides=(1, ld, ld * w_, ld * w_ * h, ld * w_ * h * n_img), a_box=(64, bw, bh, bn, 1),
+                        taps=taps, k_per_tap=cout, w=_dgrad_weight(wk, 9), n=cin, out=out, out_dims=(w_, h, n_img, 1),
+                        out_row_stride=(1, w_, w_ * h, 0), residual=residual)
     return gemm_raw(a=dy, a_dims=(cout, w_, h, n_img, 1), a_strides=(1, ld, ld * w_, ld * w_ * h, ld * w_ * h * n_img),
                     a_box=(64, bw, bh, bn, 1), taps=taps, k_per_tap=cout, w=wk, n=cin, out=out,
                     out_dims=(w_, h, n_img, 1), out_row_stride=(1, w_, w_ * h, 0), residual=residual, b_mn_major=True,
@@ -484,6 +514,11 @@ def conv_temporal_dgrad(dy, batch, frames, hw, wk, *, residual=None, out=None):
     ld = dy.stride(0)
     bp, bf, bb = choose_box((hw, frames, batch))
     taps = [(0, 0, -df, 0, 0) for df in (-1, 0, 1)]
+    if DGRAD_TRANSPOSED:
+        return gemm_raw(a=dy, a_dims=(cout, hw, frames, batch, 1),
+                        a_strides=(1, ld, ld * hw, ld * hw * frames, ld * hw * frames * batch),
+                        a_box=(64, bp, bf, bb, 1), taps=taps, k_per_tap=cout, w=_dgrad_weight(wk, 3), n=cin, out=out,
+                        out_dims=(hw, frames, batch, 1), out_row_stride=(1, hw, hw * frames, 0), residual=residual)
     return gemm_raw(a=dy, a_dims=(cout, hw, frames, batch, 1),
                     a_strides=(1, ld, ld * hw, ld * hw * frames, ld * hw * frames * batch), a_box=(64, bp, bf, bb, 1),
                     taps=taps, k_per_tap=cout, w=wk, n=cin, out=out, out_dims=(hw, frames, batch, 1),
@@ -506,6 +541,12 @@ def conv2d_3x3_s2_dgrad(dy, n_img, h, w_, wk_parity, *, out=None):
     bw, bh, bn = choose_box((wo, ho, n_img))
     for (a, b), (wsub, shifts) in wk_parity.items():
         taps = [(0, sx, sy, 0, 0) for (sx, sy) in shifts]
+        if DGRAD_TRANSPOSED:
+            gemm_raw(a=dy, a_dims=(cout, wo, ho, n_img, 1),
+                     a_strides=(1, ld, ld * wo, ld * wo * ho, ld * wo * ho * n_img), a_box=(64, bw, bh, bn, 1),
+                     taps=taps, k_per_tap=cout, w=_dgrad_weight(wsub, len(shifts)), n=cin, out=out[a * w_ + b:],
+                     out_dims=(wo, ho, n_img, 1), out_row_stride=(2, 2 * w_, h * w_, 0))
+            continue
         gemm_raw(a=dy, a_dims=(cout, wo, ho, n_img, 1), a_strides=(1, ld, ld * wo, ld * wo * ho, ld * wo * ho * n_img),
                  a_box=(64, bw, bh, bn, 1), taps=taps, k_per_tap=cout, w=wsub, n=cin, out=out[a * w_ + b:],
                  out_dims=(wo, ho, n_img, 1), out_row_stride=(2, 2 * w_, h * w_, 0), b_mn_major=True,
