@@ -13,6 +13,7 @@
 //   temporal self-attention (S = F frames; floor(128/F) pixels' sequences are packed in one tile with a
 //                            block-diagonal mask; rows are gathered straight from the channels-last activation)
 #include <atomic>
+#include <cstdlib>
 
 #include "../../include/lvd_b200.h"
 #include "host_util.h"
@@ -406,6 +407,9 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid
   }
 }
 
+int launch_temporal_attn_mma(const lvd_attn_desc* d, cudaStream_t stream);  // attention_temporal.cu
+int launch_cross_attn_mma(const lvd_attn_desc* d, cudaStream_t stream);     // attention_temporal.cu
+
 }  // namespace lvd
 
 using namespace lvd;
@@ -424,6 +428,15 @@ extern "C" int lvd_attention(const lvd_attn_desc* d, void* stream) {
   if (d->mode == 0) {
     // spatial / cross: Q [nz][s_q] rows, KV [nz/kv_z_div][s_k] rows
     LVD_REQUIRE(d->s_q >= 1 && d->s_k >= 1, "lvd_attention: empty sequence");
+    if (d->s_k <= 128 && !d->p_full && !d->p_tok && !d->lse) {
+      // <= 128 keys (the 77 text tokens; the 45-pixel mid block) and no map requested: warp-level kernel
+      // (attention_temporal.cu)
+      static const bool force_tile = getenv("LVD_CROSS_TILE") != nullptr;  // A/B switch for tools/
+      if (!force_tile) {
+        const int r = launch_cross_attn_mma(d, static_cast<cudaStream_t>(stream));
+        if (r != 1) return r;
+      }
+    }
     int64_t qd[4] = {width_q, d->s_q, 1, d->nz};
     int64_t qs[4] = {1, d->ld_q, d->ld_q * d->s_q, d->ld_q * d->s_q};
     int qb[4] = {64, d->s_q < 128 ? (int)d->s_q : 128, 1, 1};
@@ -451,7 +464,15 @@ extern "C" int lvd_attention(const lvd_attn_desc* d, void* stream) {
   } else if (d->mode == 2) {
     // packed sequences: rows (z*hw + p)*F + f -- every F consecutive rows are one sequence; bp sequences per tile
     const int F = d->frames;
-    LVD_REQUIRE(F >= 8 && F <= 64 && F % 8 == 0 && d->hw >= 1, "lvd_attention: packed mode needs frames %% 8 == 0 (got %d)", F);
+    LVD_REQUIRE(F >= 8 && F <= 32 && F % 8 == 0 && d->hw >= 1,
+                "lvd_attention: packed mode covers frames in {8, 16, 24, 32} (got %d); use mode 1", F);
+    {  // F <= 32: one warp per (sequence, head) on mma.sync (attention_temporal.cu); the tile kernel covers the rest
+      static const bool force_tile = getenv("LVD_TEMPORAL_TILE") != nullptr;  // A/B switch for tools/
+      if (!force_tile) {
+        const int r = launch_temporal_attn_mma(d, static_cast<cudaStream_t>(stream));
+        if (r != 1) return r;
+      }
+    }
     int bp = 128 / F;
     if (bp > d->hw) bp = static_cast<int>(d->hw);
     const int64_t rows_z = d->hw * F;

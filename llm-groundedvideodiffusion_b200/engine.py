@@ -211,7 +211,7 @@ class UNetEngine:
                objs=None):
         c = t.shape[1]
         n1 = ops.layernorm(t, B.norm1.w, B.norm1.b)
-        packed = (not spatial) and frames % 8 == 0
+        packed = (not spatial) and frames % 8 == 0 and frames <= 32
         fm2sm = ("fm2sm", batch, frames, hw) if packed else None
         sm2fm = ("sm2fm", batch, frames, hw) if packed else None
         qkv = ops.linear(n1, B.qkv1, row_map=fm2sm)

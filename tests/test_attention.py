@@ -60,6 +60,24 @@ def test_cross_attention_with_maps(cuda, b, frames, s, heads, sk):
         assert rel_err(p_tok[i], p[..., t]) < TOL
 
 
+@pytest.mark.parametrize("b,frames,s,heads,sk", [(1, 4, 180, 2, 77), (2, 3, 45, 4, 77), (1, 2, 2880, 5, 77),
+                                                 (1, 2, 301, 1, 107), (2, 2, 37, 2, 30), (1, 3, 50, 1, 128),
+                                                 (1, 1, 16, 1, 1)])
+def test_cross_attention_without_maps(cuda, b, frames, s, heads, sk):
+    """No probability output requested: the warp-level mma.sync kernel (attention_temporal.cu) -- ragged query counts,
+    key counts on both sides of every template boundary (32 / 80 / 128 keys), a single key."""
+    from lvd_b200 import ops
+    c = heads * 64
+    z = b * frames
+    q = _rand((z * s, c), cuda, seed=12)
+    kv = _rand((b * sk, 2 * c), cuda, seed=13)
+    out = ops.attention(q, kv, heads=heads, nz=z, s_q=s, s_k=sk, k_col0=0, v_col0=c, kv_z_div=frames)
+    k = kv[:, :c].reshape(b, sk, c).repeat_interleave(frames, 0)
+    v = kv[:, c:].reshape(b, sk, c).repeat_interleave(frames, 0)
+    ref, _ = _ref_attn(q.reshape(z, s, c), k, v, heads)
+    assert rel_err(out, ref.reshape(z * s, c)) < TOL
+
+
 @pytest.mark.parametrize("b,frames,hw,heads", [(1, 24, 45, 2), (2, 24, 180, 1), (2, 16, 64, 2), (1, 8, 16, 1),
                                                (1, 24, 2880, 1), (1, 24, 7, 1)])
 def test_temporal_attention(cuda, b, frames, hw, heads):
@@ -80,7 +98,8 @@ def test_temporal_attention(cuda, b, frames, hw, heads):
 
 
 @pytest.mark.parametrize("b,frames,hw,heads", [(1, 24, 45, 2), (2, 24, 180, 1), (2, 16, 64, 2), (1, 8, 16, 1),
-                                               (1, 24, 2880, 1), (1, 24, 7, 1), (1, 32, 9, 1)])
+                                               (1, 24, 2880, 1), (1, 24, 7, 1), (1, 32, 9, 1), (2, 32, 33, 3),
+                                               (3, 8, 5, 5)])
 def test_temporal_attention_packed(cuda, b, frames, hw, heads):
     """mode 2: rows ((b*hw + p)*F + f); sequences are runs of F consecutive rows."""
     from lvd_b200 import ops

@@ -1,0 +1,3 @@
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_attention.py tests/test_backward_ops.py tests/test_unet_forward.py tests/test_guidance.py -m gpu -q --no-header -p no:cacheprovider -x 2>&1 | tail -4
+WHICH=self,temporal timeout 100 python tools/perf_attn.py 2>&1 | tail -12
