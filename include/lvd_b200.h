@@ -147,6 +147,8 @@ int lvd_layernorm(const void* x, int64_t ld_x, void* y, int64_t ld_y, int64_t ro
  * lvd_conv_in : sample (B, cin, F, H, W) NCFHW fp16 -> rows, 3x3 conv (unet_3d_condition.py:297,726-729);
  *               weight in the reference's OIHW layout.
  * lvd_conv_out: rows -> (B, cout, F, H, W) NCFHW (unet_3d_condition.py:424,847-854); weight [cout][ky][kx][cin].
+ * lvd_rows_to_ncfhw: columns [0, cout) of a [B*F*hw, ld] row matrix -> (B, cout, F, H, W); the layout change of
+ *               conv_out when the conv itself runs on lvd_gemm with cout zero-padded to one 64-wide tile.
  * lvd_upsample2x: nearest 2x (diffusers Upsample2D's F.interpolate, unet_3d_blocks.py:610-613).
  * lvd_timestep_embed: diffusers Timesteps(dim, flip_sin_to_cos=True, shift 0) (unet_3d_condition.py:304,712).
  * ---------------------------------------------------------------------------------------------------------- */
@@ -154,6 +156,8 @@ int lvd_conv_in(const void* sample, const void* weight, const void* bias, void* 
                 int32_t cin, int32_t frames, int32_t height, int32_t width, int32_t cout, void* stream);
 int lvd_conv_out(const void* x, int64_t ld_x, const void* weight_krsc, const void* bias, void* out, int32_t batch,
                  int32_t cin, int32_t frames, int32_t height, int32_t width, int32_t cout, void* stream);
+int lvd_rows_to_ncfhw(const void* rows, int64_t ld, void* out, int32_t batch, int32_t cout, int32_t frames, int64_t hw,
+                      void* stream);
 int lvd_upsample2x(const void* x, int64_t ld_x, void* y, int64_t ld_y, int32_t n_img, int32_t height, int32_t width,
                    int32_t channels, void* stream);
 int lvd_timestep_embed(const void* timesteps_f32, void* out, int32_t batch, int32_t dim, void* stream);

@@ -132,6 +132,7 @@ def _declare(l):
     l.lvd_timestep_embed.argtypes = [vp, vp, i32, i32, vp]
     l.lvd_silu.argtypes = [vp, vp, i64, vp]
     l.lvd_copy_rows.argtypes = [vp, i64, vp, i64, i64, i32, vp]
+    l.lvd_rows_to_ncfhw.argtypes = [vp, i64, vp, i32, i32, i32, i64, vp]
     l.lvd_cfg_dpm_step.argtypes = [vp, vp, vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, f32, f32, i32, vp]
     l.lvd_axpy_h.argtypes = [vp, vp, vp, i64, f32, vp]
     l.lvd_box_energy.argtypes = [ctypes.POINTER(EnergyDesc), vp]
@@ -173,6 +174,7 @@ EXPORTS = [
     "lvd_timestep_embed",
     "lvd_silu",
     "lvd_copy_rows",
+    "lvd_rows_to_ncfhw",
     "lvd_cfg_dpm_step",
     "lvd_axpy_h",
     "lvd_box_energy",

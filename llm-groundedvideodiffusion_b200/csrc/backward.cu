@@ -8,6 +8,7 @@
 #include "../../include/lvd_b200.h"
 #include "host_util.h"
 #include "ptx.cuh"
+#include "norm_stream.cuh"
 
 namespace lvd {
 extern std::atomic<long long> g_launches;
@@ -22,6 +23,16 @@ __device__ __forceinline__ void ld8b(const __half* p, float (&v)[8]) {
     v[2 * i + 1] = f.y;
   }
 }
+__device__ __forceinline__ void unpack8b(const uint4& u, float (&v)[8]) {
+  const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = __half22float2(h[i]);
+    v[2 * i] = f.x;
+    v[2 * i + 1] = f.y;
+  }
+}
+__device__ __forceinline__ void opaque_b(uint4& u) { asm volatile("" : "+r"(u.x), "+r"(u.y), "+r"(u.z), "+r"(u.w)); }
 __device__ __forceinline__ void st8b(__half* p, const float (&v)[8]) {
   uint4 u;
   __half2* h = reinterpret_cast<__half2*>(&u);
@@ -209,6 +220,232 @@ __global__ void gn_bwd_apply_kernel(const __half* __restrict__ x, long long ld_x
   }
 }
 
+// ---- streaming versions (same ring as the forward passes, norm_stream.cuh): x and dz travel through the ring in lock
+// step; pass A's last CTA per sample (ticket) folds the chunk partials into {mean g, mean g*xhat}.
+__device__ unsigned int g_gnb_tickets[8192];
+
+__global__ void __launch_bounds__(320, 2) gn_stream_bwd_stats_kernel(
+    const __half* __restrict__ x, long long ld_x, const __half* __restrict__ dz, long long ld_dz,
+    long long rows_per_sample, int C, int G, int chunks, int T, const float* __restrict__ stats,
+    const __half* __restrict__ gamma, const __half* __restrict__ beta, int silu, float* __restrict__ bwd_partial,
+    float n, float* __restrict__ bstats) {
+  extern __shared__ uint4 s_dyn[];
+  __shared__ uint64_t s_full[kGnStages];
+  __shared__ int s_last;
+  __shared__ float s_mean[64], s_rstd[64];
+  const int vpr = C >> 3;
+  const int rpp = blockDim.x / vpr;
+  const int v = threadIdx.x % vpr, rsub = threadIdx.x / vpr;
+  const int chunk = blockIdx.x, s = blockIdx.y;
+  const int cpg = C / G;
+  const long long rows_per_chunk = (rows_per_sample + chunks - 1) / chunks;
+  const long long r0 = chunk * rows_per_chunk;
+  long long r1 = r0 + rows_per_chunk;
+  if (r1 > rows_per_sample) r1 = rows_per_sample;
+  GnStream st;
+  st.full = s_full;
+  st.ring = s_dyn;
+  st.src = x + (s * rows_per_sample + r0) * ld_x;
+  st.ld = ld_x;
+  st.src2 = dz + (s * rows_per_sample + r0) * ld_dz;
+  st.ld2 = ld_dz;
+  st.n = r1 > r0 ? static_cast<int>(r1 - r0) : 0;
+  st.T = T;
+  st.vpr = vpr;
+  st.nit = (st.n + T - 1) / T;
+  st.dense = ld_x == C;
+  float* s_part = reinterpret_cast<float*>(s_dyn + static_cast<long long>(kGnStages) * 2 * T * vpr);
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kGnStages; ++i) mbar_init(&s_full[i], 1);
+    fence_barrier_init();
+  }
+  for (int g = threadIdx.x; g < G; g += blockDim.x) {
+    s_mean[g] = stats[(static_cast<long long>(s) * G + g) * 2];
+    s_rstd[g] = stats[(static_cast<long long>(s) * G + g) * 2 + 1];
+  }
+  __syncthreads();
+  if (threadIdx.x < 32)
+    for (int it = 0; it < kGnStages && it < st.nit; ++it) st.issue(it);
+  float ga[8], be[8], mu[8], rs[8], a1[8], a2[8];
+  if (rsub < rpp) {
+    ld8b(gamma + v * 8, ga);
+    ld8b(beta + v * 8, be);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int g = rsub < rpp ? (v * 8 + i) / cpg : 0;
+    mu[i] = s_mean[g];
+    rs[i] = s_rstd[g];
+    a1[i] = a2[i] = 0.f;
+  }
+  for (int it = 0; it < st.nit; ++it) {
+    const int stage = it % kGnStages;
+    mbar_wait(&s_full[stage], static_cast<uint32_t>(it / kGnStages) & 1u);
+    const int rows = st.n - it * T < T ? st.n - it * T : T;
+    const uint4* bx = s_dyn + static_cast<long long>(stage) * 2 * T * vpr;
+    const uint4* bd = bx + static_cast<long long>(T) * vpr;
+    if (rsub < rpp) {
+      for (int r = rsub; r < rows; r += rpp) {
+        float t[8], d[8];
+        unpack8b(bx[static_cast<long long>(r) * vpr + v], t);
+        unpack8b(bd[static_cast<long long>(r) * vpr + v], d);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float xh = (t[i] - mu[i]) * rs[i];
+          float gg = d[i];
+          if (silu) gg *= silu_grad(xh * ga[i] + be[i]);
+          gg *= ga[i];
+          a1[i] += gg;
+          a2[i] += gg * xh;
+        }
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x < 32 && it + kGnStages < st.nit) st.issue(it + kGnStages);
+  }
+  if (rsub < rpp) {
+    float* mine = s_part + static_cast<long long>(rsub) * 2 * C + v * 8;  // no atomics: run-to-run reproducible
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      mine[i] = a1[i];
+      mine[C + i] = a2[i];
+    }
+  }
+  __syncthreads();
+  float* s_col = s_part + static_cast<long long>(rpp) * 2 * C;
+  for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) {
+    float a = 0.f;
+    for (int q = 0; q < rpp; ++q) a += s_part[static_cast<long long>(q) * 2 * C + c];
+    s_col[c] = a;
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < 2 * G; t += blockDim.x) {
+    const int g = t >> 1, which = t & 1;
+    const float* col = s_col + which * C + g * cpg;
+    float a = 0.f;
+    for (int c = 0; c < cpg; ++c) a += col[c];
+    bwd_partial[((static_cast<long long>(s) * chunks + chunk) * G + g) * 2 + which] = a;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(&g_gnb_tickets[s], 1u) == static_cast<unsigned>(chunks - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  float* s_a = s_part;
+  float* s_b = s_part + blockDim.x;
+  const int nparts = blockDim.x / G;
+  {
+    const int g = threadIdx.x % G, part = threadIdx.x / G;
+    float a = 0.f, b = 0.f;
+    if (part < nparts)
+      for (int k = part; k < chunks; k += nparts) {
+        const float* p = bwd_partial + ((static_cast<long long>(s) * chunks + k) * G + g) * 2;
+        a += __ldcg(p);
+        b += __ldcg(p + 1);
+      }
+    s_a[threadIdx.x] = a;
+    s_b[threadIdx.x] = b;
+  }
+  __syncthreads();
+  if (threadIdx.x < G) {
+    float a = 0.f, b = 0.f;
+    for (int q = 0; q < nparts; ++q) {
+      a += s_a[q * G + threadIdx.x];
+      b += s_b[q * G + threadIdx.x];
+    }
+    bstats[(static_cast<long long>(s) * G + threadIdx.x) * 2] = a / n;
+    bstats[(static_cast<long long>(s) * G + threadIdx.x) * 2 + 1] = b / n;
+  }
+  if (threadIdx.x == 0) g_gnb_tickets[s] = 0u;
+}
+
+__global__ void __launch_bounds__(320, 2) gn_stream_bwd_apply_kernel(
+    const __half* __restrict__ x, long long ld_x, const __half* __restrict__ dz, long long ld_dz,
+    __half* __restrict__ dx, long long ld_dx, long long rows_per_sample, int C, int G, int chunks, int T,
+    const float* __restrict__ stats, const float* __restrict__ bstats, const __half* __restrict__ gamma,
+    const __half* __restrict__ beta, int silu, int accumulate) {
+  extern __shared__ uint4 s_dyn[];
+  __shared__ uint64_t s_full[kGnStages];
+  __shared__ float s_mean[64], s_rstd[64], s_m1[64], s_m2[64];
+  const int vpr = C >> 3;
+  const int rpp = blockDim.x / vpr;
+  const int v = threadIdx.x % vpr, rsub = threadIdx.x / vpr;
+  const int chunk = blockIdx.x, s = blockIdx.y;
+  const int cpg = C / G;
+  const long long rows_per_chunk = (rows_per_sample + chunks - 1) / chunks;
+  const long long r0 = chunk * rows_per_chunk;
+  long long r1 = r0 + rows_per_chunk;
+  if (r1 > rows_per_sample) r1 = rows_per_sample;
+  GnStream st;
+  st.full = s_full;
+  st.ring = s_dyn;
+  st.src = x + (s * rows_per_sample + r0) * ld_x;
+  st.ld = ld_x;
+  st.src2 = dz + (s * rows_per_sample + r0) * ld_dz;
+  st.ld2 = ld_dz;
+  st.n = r1 > r0 ? static_cast<int>(r1 - r0) : 0;
+  st.T = T;
+  st.vpr = vpr;
+  st.nit = (st.n + T - 1) / T;
+  st.dense = ld_x == C;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kGnStages; ++i) mbar_init(&s_full[i], 1);
+    fence_barrier_init();
+  }
+  for (int g = threadIdx.x; g < G; g += blockDim.x) {
+    s_mean[g] = stats[(static_cast<long long>(s) * G + g) * 2];
+    s_rstd[g] = stats[(static_cast<long long>(s) * G + g) * 2 + 1];
+    s_m1[g] = bstats[(static_cast<long long>(s) * G + g) * 2];
+    s_m2[g] = bstats[(static_cast<long long>(s) * G + g) * 2 + 1];
+  }
+  __syncthreads();
+  if (threadIdx.x < 32)
+    for (int it = 0; it < kGnStages && it < st.nit; ++it) st.issue(it);
+  float ga[8], be[8], mu[8], rs[8], m1[8], m2[8];
+  if (rsub < rpp) {
+    ld8b(gamma + v * 8, ga);
+    ld8b(beta + v * 8, be);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int g = rsub < rpp ? (v * 8 + i) / cpg : 0;
+    mu[i] = s_mean[g];
+    rs[i] = s_rstd[g];
+    m1[i] = s_m1[g];
+    m2[i] = s_m2[g];
+  }
+  __half* ob = dx + (s * rows_per_sample + r0) * ld_dx + v * 8;
+  for (int it = 0; it < st.nit; ++it) {
+    const int stage = it % kGnStages;
+    mbar_wait(&s_full[stage], static_cast<uint32_t>(it / kGnStages) & 1u);
+    const int rows = st.n - it * T < T ? st.n - it * T : T;
+    const uint4* bx = s_dyn + static_cast<long long>(stage) * 2 * T * vpr;
+    const uint4* bd = bx + static_cast<long long>(T) * vpr;
+    if (rsub < rpp) {
+      for (int r = rsub; r < rows; r += rpp) {
+        float t[8], d[8], o[8];
+        __half* op = ob + (static_cast<long long>(it) * T + r) * ld_dx;
+        if (accumulate) ld8b(op, o);
+        unpack8b(bx[static_cast<long long>(r) * vpr + v], t);
+        unpack8b(bd[static_cast<long long>(r) * vpr + v], d);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float xh = (t[i] - mu[i]) * rs[i];
+          float gg = d[i];
+          if (silu) gg *= silu_grad(xh * ga[i] + be[i]);
+          gg *= ga[i];
+          const float res = rs[i] * (gg - m1[i] - xh * m2[i]);
+          o[i] = accumulate ? o[i] + res : res;
+        }
+        st8b(op, o);
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x < 32 && it + kGnStages < st.nit) st.issue(it + kGnStages);
+  }
+}
+
 // forward statistics kernel lives in norm.cu
 __global__ void gn_stats_kernel(const __half* __restrict__ x, long long ld, long long rows_per_sample, int C, int G,
                                 int chunks, float* __restrict__ partial, float n, float eps, float* __restrict__ stats);
@@ -216,85 +453,157 @@ __global__ void gn_finalize_kernel(const float* __restrict__ partial, int chunks
                                    float* __restrict__ stats, int raw_means);
 
 // ------------------------------------------------------------------------------------------------ LayerNorm backward
+// dx = rstd * (g - mean(g) - xhat * mean(g * xhat)), g = dy * gamma.  Same thread layout as the forward kernel
+// (norm.cu): L lanes per row, 32 / L rows side by side in a warp, R row sets in flight, x and dy held packed (fp16) in
+// registers so that every load of the rows in flight is issued before the first dependent shuffle.
 constexpr int kLnbMaxVec = 8;
-template <int NV>
-__global__ void layernorm_bwd_kernel(const __half* __restrict__ x, long long ld_x, const __half* __restrict__ dy,
-                                     long long ld_dy, __half* __restrict__ dx, long long ld_dx, long long rows, int C,
-                                     const __half* __restrict__ gamma, float eps, int accumulate) {
+
+template <int NV, int L, int R>
+__global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(const __half* __restrict__ x, long long ld_x,
+                                                               const __half* __restrict__ dy, long long ld_dy,
+                                                               __half* __restrict__ dx, long long ld_dx,
+                                                               long long rows, int C, const __half* __restrict__ gamma,
+                                                               float eps, int accumulate) {
+  extern __shared__ uint4 s_gamma_v[];  // gamma[C] (fp16), loaded once per block
+  {
+    __half* sg = reinterpret_cast<__half*>(s_gamma_v);
+    for (int i = threadIdx.x; i < C; i += blockDim.x) sg[i] = gamma[i];
+  }
+  __syncthreads();
+  constexpr int kRowsPerSet = 32 / L;
   const int lane = threadIdx.x & 31;
+  const int j = lane % L, sub = lane / L;
   const int vpr = C >> 3;
+  const float inv_c = 1.0f / static_cast<float>(C);
   const long long warps_total = static_cast<long long>(gridDim.x) * (blockDim.x >> 5);
-  for (long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows;
-       row += warps_total) {
-  float xv[NV][8], gv[NV][8];
-  float sum = 0.f;
+  const long long rows_per_iter = static_cast<long long>(kRowsPerSet) * R;
+  for (long long row0 = (static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5)) * rows_per_iter;
+       row0 < rows; row0 += warps_total * rows_per_iter) {
+    uint4 xv[R][NV], dv[R][NV];
 #pragma unroll
-  for (int k = 0; k < NV; ++k) {
-    const int v = lane + k * 32;
-    if (v < vpr) {
-      ld8b(x + row * ld_x + v * 8, xv[k]);
+    for (int r = 0; r < R; ++r) {
+      const long long row = row0 + r * kRowsPerSet + sub;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) sum += xv[k][i];
-    }
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-  const float mean = sum / C;
-  float sq = 0.f;
-#pragma unroll
-  for (int k = 0; k < NV; ++k) {
-    const int v = lane + k * 32;
-    if (v < vpr) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float d = xv[k][i] - mean;
-        sq += d * d;
+      for (int k = 0; k < NV; ++k) {
+        const int v = j + k * L;
+        const bool ok = row < rows && v < vpr;
+        xv[r][k] = ok ? *reinterpret_cast<const uint4*>(x + row * ld_x + v * 8) : make_uint4(0, 0, 0, 0);
+        dv[r][k] = ok ? *reinterpret_cast<const uint4*>(dy + row * ld_dy + v * 8) : make_uint4(0, 0, 0, 0);
       }
     }
-  }
+    float mean[R], rstd[R], s1[R], s2[R];
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-  const float rstd = rsqrtf(sq / C + eps);
-  float s1 = 0.f, s2 = 0.f;
+    for (int r = 0; r < R; ++r) {
+      float a = 0.f;
 #pragma unroll
-  for (int k = 0; k < NV; ++k) {
-    const int v = lane + k * 32;
-    if (v < vpr) {
-      float d[8], ga[8];
-      ld8b(dy + row * ld_dy + v * 8, d);
-      ld8b(gamma + v * 8, ga);
+      for (int k = 0; k < NV; ++k) {
+        float f[8];
+        unpack8b(xv[r][k], f);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float xh = (xv[k][i] - mean) * rstd;
-        const float g = d[i] * ga[i];
-        gv[k][i] = g;
-        xv[k][i] = xh;
-        s1 += g;
-        s2 += g * xh;
+        for (int i = 0; i < 8; ++i) a += f[i];
+      }
+      mean[r] = a;
+    }
+#pragma unroll
+    for (int o = L / 2; o > 0; o >>= 1)
+#pragma unroll
+      for (int r = 0; r < R; ++r) mean[r] += __shfl_xor_sync(0xffffffffu, mean[r], o);
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int k = 0; k < NV; ++k) opaque_b(xv[r][k]);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      mean[r] *= inv_c;
+      float q = 0.f;
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        if (j + k * L < vpr) {
+          float f[8];
+          unpack8b(xv[r][k], f);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float d = f[i] - mean[r];
+            q += d * d;
+          }
+        }
+      }
+      rstd[r] = q;
+    }
+#pragma unroll
+    for (int o = L / 2; o > 0; o >>= 1)
+#pragma unroll
+      for (int r = 0; r < R; ++r) rstd[r] += __shfl_xor_sync(0xffffffffu, rstd[r], o);
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int k = 0; k < NV; ++k) opaque_b(xv[r][k]);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      rstd[r] = rsqrtf(rstd[r] * inv_c + eps);
+      s1[r] = 0.f;
+      s2[r] = 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int v = j + k * L;
+      if (v < vpr) {
+        float ga[8];
+        unpack8b(s_gamma_v[v], ga);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          float f[8], d[8];
+          unpack8b(xv[r][k], f);
+          unpack8b(dv[r][k], d);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float g = d[i] * ga[i];
+            s1[r] += g;
+            s2[r] += g * ((f[i] - mean[r]) * rstd[r]);
+          }
+        }
       }
     }
-  }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-  }
-  s1 /= C;
-  s2 /= C;
+    for (int o = L / 2; o > 0; o >>= 1)
 #pragma unroll
-  for (int k = 0; k < NV; ++k) {
-    const int v = lane + k * 32;
-    if (v < vpr) {
-      float o[8];
-      if (accumulate) ld8b(dx + row * ld_dx + v * 8, o);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float res = rstd * (gv[k][i] - s1 - xv[k][i] * s2);
-        o[i] = accumulate ? o[i] + res : res;
+      for (int r = 0; r < R; ++r) {
+        s1[r] += __shfl_xor_sync(0xffffffffu, s1[r], o);
+        s2[r] += __shfl_xor_sync(0xffffffffu, s2[r], o);
       }
-      st8b(dx + row * ld_dx + v * 8, o);
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        opaque_b(xv[r][k]);
+        opaque_b(dv[r][k]);
+      }
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int v = j + k * L;
+      if (v < vpr) {
+        float ga[8];
+        unpack8b(s_gamma_v[v], ga);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const long long row = row0 + r * kRowsPerSet + sub;
+          if (row < rows) {
+            float f[8], d[8], o[8];
+            unpack8b(xv[r][k], f);
+            unpack8b(dv[r][k], d);
+            if (accumulate) ld8b(dx + row * ld_dx + v * 8, o);
+            const float m1 = s1[r] * inv_c, m2 = s2[r] * inv_c;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float xh = (f[i] - mean[r]) * rstd[r];
+              const float res = rstd[r] * (d[i] * ga[i] - m1 - xh * m2);
+              o[i] = accumulate ? o[i] + res : res;
+            }
+            st8b(dx + row * ld_dx + v * 8, o);
+          }
+        }
+      }
     }
-  }
   }
 }
 
@@ -515,15 +824,45 @@ extern "C" int lvd_groupnorm_bwd(const void* x, int64_t ld_x, const void* dz, in
                       ST(stream)>>>(
         HC(x), ld_x, rows_per_sample, channels, groups, static_cast<int>(chunks), fwd, n, eps, stats);
   }
-  gn_bwd_stats_kernel<<<grid, threads,
-                        (static_cast<size_t>(threads / (channels / 8)) * 2 * channels + 2 * groups) * sizeof(float),
-                        ST(stream)>>>(
-      HC(x), ld_x, HC(dz), ld_dz, rows_per_sample, channels, groups, static_cast<int>(chunks), stats, HC(gamma),
-      HC(beta), eps, silu, bwd);
-  gn_finalize_kernel<<<samples, fin_threads, 0, ST(stream)>>>(bwd, static_cast<int>(chunks), groups, n, eps, bstats, 1);
-  gn_bwd_apply_kernel<<<grid, threads, 0, ST(stream)>>>(HC(x), ld_x, HC(dz), ld_dz, HM(dx), ld_dx, rows_per_sample,
-                                                        channels, groups, static_cast<int>(chunks), stats, bstats,
-                                                        HC(gamma), HC(beta), eps, silu, accumulate);
+  {
+    const long long row_bytes = 2LL * channels;
+    int T = static_cast<int>((8 * 1024) / row_bytes) / rpp * rpp;  // ~8 KB of x + ~8 KB of dz per stage
+    if (T < rpp) T = rpp;
+    long long schunks = (2LL * num_sms()) / samples;  // one wave of 2 CTAs per SM
+    const long long most = (rows_per_sample + T - 1) / T;
+    if (schunks > most) schunks = most;
+    if (schunks > chunks) schunks = chunks;  // the workspace is sized for `chunks`
+    if (schunks < 1) schunks = 1;
+    const size_t ring_bytes = static_cast<size_t>(kGnStages) * 2 * T * row_bytes;
+    const size_t scratch = (static_cast<size_t>(rpp) + 1) * 2 * channels * sizeof(float);
+    if (threads <= 320 && ring_bytes + scratch <= 225 * 1024 && samples <= 8192) {
+      static bool attr = false;
+      if (!attr) {
+        LVD_CHECK_CUDA(cudaFuncSetAttribute(gn_stream_bwd_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            225 * 1024));
+        LVD_CHECK_CUDA(cudaFuncSetAttribute(gn_stream_bwd_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            225 * 1024));
+        attr = true;
+      }
+      dim3 sgrid(static_cast<unsigned>(schunks), static_cast<unsigned>(samples));
+      gn_stream_bwd_stats_kernel<<<sgrid, threads, ring_bytes + scratch, ST(stream)>>>(
+          HC(x), ld_x, HC(dz), ld_dz, rows_per_sample, channels, groups, static_cast<int>(schunks), T, stats,
+          HC(gamma), HC(beta), silu, bwd, n, bstats);
+      gn_stream_bwd_apply_kernel<<<sgrid, threads, ring_bytes, ST(stream)>>>(
+          HC(x), ld_x, HC(dz), ld_dz, HM(dx), ld_dx, rows_per_sample, channels, groups, static_cast<int>(schunks), T,
+          stats, bstats, HC(gamma), HC(beta), silu, accumulate);
+    } else {
+    gn_bwd_stats_kernel<<<grid, threads,
+                          (static_cast<size_t>(threads / (channels / 8)) * 2 * channels + 2 * groups) * sizeof(float),
+                          ST(stream)>>>(
+        HC(x), ld_x, HC(dz), ld_dz, rows_per_sample, channels, groups, static_cast<int>(chunks), stats, HC(gamma),
+        HC(beta), eps, silu, bwd);
+    gn_finalize_kernel<<<samples, fin_threads, 0, ST(stream)>>>(bwd, static_cast<int>(chunks), groups, n, eps, bstats, 1);
+    gn_bwd_apply_kernel<<<grid, threads, 0, ST(stream)>>>(HC(x), ld_x, HC(dz), ld_dz, HM(dx), ld_dx, rows_per_sample,
+                                                          channels, groups, static_cast<int>(chunks), stats, bstats,
+                                                          HC(gamma), HC(beta), eps, silu, accumulate);
+    }
+  }
   g_launches.fetch_add(5, std::memory_order_relaxed);
   LVD_CHECK_CUDA(cudaGetLastError());
   return LVD_OK;
@@ -537,22 +876,35 @@ extern "C" int lvd_layernorm_bwd(const void* x, int64_t ld_x, const void* dy, in
   LVD_REQUIRE(ld_x % 8 == 0 && ld_dy % 8 == 0 && ld_dx % 8 == 0, "lvd_layernorm_bwd: ld must be a multiple of 8");
   if (rows <= 0) return LVD_OK;
   const int warps = 8;
-  long long blocks = (rows + warps - 1) / warps;
+  const int vpr = channels / 8;
+  const int lanes = vpr <= 8 * kLnbMaxVec ? 8 : (vpr <= 16 * kLnbMaxVec ? 16 : 32);  // lanes per row
+  const int nv = (vpr + lanes - 1) / lanes;
+  int rsets = nv <= 5 ? 2 : 1;
+  if (rows / ((32 / lanes) * rsets) < 16LL * num_sms()) rsets = 1;
+  const int rows_per_warp = (32 / lanes) * rsets;
+  long long blocks = (rows + warps * rows_per_warp - 1) / (warps * rows_per_warp);
   const long long cap = 16LL * num_sms();
   if (blocks > cap) blocks = cap;
-  const int nv = (channels / 8 + 31) / 32;
-#define LVD_LNB_LAUNCH(NV)                                                                          \
-  layernorm_bwd_kernel<NV><<<static_cast<unsigned>(blocks), warps * 32, 0, ST(stream)>>>(           \
+#define LVD_LNB_LAUNCH(NV, L, R)                                                                              \
+  layernorm_bwd_kernel<NV, L, R><<<static_cast<unsigned>(blocks), warps * 32, channels * sizeof(__half),     \
+                                   ST(stream)>>>(                                                             \
       HC(x), ld_x, HC(dy), ld_dy, HM(dx), ld_dx, rows, channels, HC(gamma), eps, accumulate)
-  if (nv <= 2) {
-    LVD_LNB_LAUNCH(2);
-  } else if (nv <= 3) {
-    LVD_LNB_LAUNCH(3);
-  } else if (nv <= 5) {
-    LVD_LNB_LAUNCH(5);
-  } else {
-    LVD_LNB_LAUNCH(8);
+#define LVD_LNB_LANES(L)                                                   \
+  if (nv <= 2) {                                                           \
+    if (rsets == 1) LVD_LNB_LAUNCH(2, L, 1); else LVD_LNB_LAUNCH(2, L, 2); \
+  } else if (nv <= 5) {                                                    \
+    if (rsets == 1) LVD_LNB_LAUNCH(5, L, 1); else LVD_LNB_LAUNCH(5, L, 2); \
+  } else {                                                                 \
+    LVD_LNB_LAUNCH(8, L, 1);                                               \
   }
+  if (lanes == 8) {
+    LVD_LNB_LANES(8)
+  } else if (lanes == 16) {
+    LVD_LNB_LANES(16)
+  } else {
+    LVD_LNB_LANES(32)
+  }
+#undef LVD_LNB_LANES
 #undef LVD_LNB_LAUNCH
   g_launches.fetch_add(1, std::memory_order_relaxed);
   LVD_CHECK_CUDA(cudaGetLastError());

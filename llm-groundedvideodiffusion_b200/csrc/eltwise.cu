@@ -136,6 +136,24 @@ __global__ void conv_out_kernel(const __half* __restrict__ x, long long ld_x, co
   }
 }
 
+// ---------------------------------------------------------------------------------------------- rows -> NCFHW
+// The wide path of conv_out: the 3x3 conv runs on the tensor-core kernel with the 4 output channels zero-padded to one
+// 64-wide tile (gemm.cu), and this kernel gathers columns [0, Cout) of the [pixels, ld] result into (B, Cout, F, H, W).
+__global__ void rows_to_ncfhw_kernel(const __half* __restrict__ rows, long long ld, __half* __restrict__ out, int B,
+                                     int Cout, int F, long long hw) {
+  const long long total = static_cast<long long>(B) * Cout * F * hw;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long p = idx % hw;
+    long long t = idx / hw;
+    const int f = static_cast<int>(t % F);
+    t /= F;
+    const int co = static_cast<int>(t % Cout);
+    const long long b = t / Cout;
+    out[idx] = rows[((b * F + f) * hw + p) * ld + co];
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- upsample 2x nearest
 __global__ void upsample2x_kernel(const __half* __restrict__ x, long long ld_x, __half* __restrict__ y, long long ld_y,
                                   int n_img, int H, int W, int C) {
@@ -238,6 +256,18 @@ extern "C" int lvd_conv_out(const void* x, int64_t ld_x, const void* weight_krsc
   conv_out_kernel<<<grid_for(npix * 32, 256), 256, smem, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __half*>(x), ld_x, static_cast<const __half*>(weight_krsc), static_cast<const __half*>(bias),
       static_cast<__half*>(out), batch, cin, frames, height, width, cout);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  LVD_CHECK_CUDA(cudaGetLastError());
+  return LVD_OK;
+}
+
+extern "C" int lvd_rows_to_ncfhw(const void* rows, int64_t ld, void* out, int32_t batch, int32_t cout, int32_t frames,
+                                 int64_t hw, void* stream) {
+  LVD_REQUIRE(rows && out && batch >= 1 && cout >= 1 && cout <= ld && frames >= 1 && hw >= 1,
+              "lvd_rows_to_ncfhw: bad arguments");
+  const long long total = static_cast<long long>(batch) * cout * frames * hw;
+  rows_to_ncfhw_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __half*>(rows), ld, static_cast<__half*>(out), batch, cout, frames, hw);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   LVD_CHECK_CUDA(cudaGetLastError());
   return LVD_OK;

@@ -6,6 +6,7 @@
 #include "../../include/lvd_b200.h"
 #include "host_util.h"
 #include "ptx.cuh"
+#include "norm_stream.cuh"
 
 namespace lvd {
 extern std::atomic<long long> g_launches;
@@ -246,31 +247,7 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x, long long ld_x, __
 // shared-memory stages filled by 1-D bulk copies (cp.async.bulk, one per row, or one per stage when rows are dense):
 // the bytes in flight (~75 KB per CTA) no longer depend on registers or occupancy, which is what held the
 // register-staged kernels at half of the HBM rate.  Pass 1 = statistics (+ ticketed finalize), pass 2 = normalise.
-constexpr int kGnStages = 5;
-
-struct GnStream {
-  uint64_t* full;      // [kGnStages]
-  uint4* ring;         // [kGnStages][T][vpr]
-  const __half* src;   // first row of this CTA's range
-  long long ld;
-  int n, T, vpr, nit;
-  bool dense;
-  __device__ __forceinline__ void issue(int it) const {  // whole warp 0
-    const int stage = it % kGnStages;
-    const int rows = n - it * T < T ? n - it * T : T;
-    const uint32_t row_bytes = static_cast<uint32_t>(vpr) * 16u;
-    const int lane = threadIdx.x & 31;
-    if (lane == 0) mbar_arrive_expect_tx(&full[stage], static_cast<uint32_t>(rows) * row_bytes);
-    __syncwarp();
-    uint4* dst = ring + static_cast<long long>(stage) * T * vpr;
-    const __half* from = src + static_cast<long long>(it) * T * ld;
-    if (dense) {
-      if (lane == 0) bulk_load_1d(dst, from, static_cast<uint32_t>(rows) * row_bytes, &full[stage]);
-    } else {
-      for (int r = lane; r < rows; r += 32) bulk_load_1d(dst + static_cast<long long>(r) * vpr, from + r * ld, row_bytes, &full[stage]);
-    }
-  }
-};
+// (kGnStages, GnStream: norm_stream.cuh)
 
 __global__ void __launch_bounds__(320, 2) gn_stream_stats_kernel(const __half* __restrict__ x, long long ld,
                                                                   long long rows_per_sample, int C, int G, int chunks,

@@ -151,7 +151,9 @@ class UNetEngine:
                                              null_pos=g("position_net.null_positive_feature"),
                                              null_xyxy=g("position_net.null_position_feature"))
         w["norm_out"] = norm("conv_norm_out")
-        w["conv_out"] = LayerWeights(w=repack.conv_weight_krsc(g("conv_out.weight")), b=g("conv_out.bias"))
+        wko = repack.conv_weight_krsc(g("conv_out.weight"))
+        wpad, bpad = repack.pad_out_channels(wko, g("conv_out.bias"))  # conv_out runs as one 64-wide GEMM tile
+        w["conv_out"] = LayerWeights(w=wko, b=g("conv_out.bias"), w_pad=wpad, b_pad=bpad, cout=wko.shape[0])
         # all 22 time_emb_proj Linear layers fused into one GEMM per forward (ResnetBlock2D)
         tw = torch.cat(temb_w, 0)
         pad = (-tw.shape[0]) % 64
@@ -338,4 +340,5 @@ class UNetEngine:
         except _Stop:
             return None
         x = ops.groupnorm(x, n_img, w["norm_out"].w, w["norm_out"].b, cfg["norm_eps"], silu=True)
-        return ops.conv_out(x, w["conv_out"].w, w["conv_out"].b, b, frames, h, w_)
+        co = w["conv_out"]
+        return ops.conv_out_tc(x, co.w_pad, co.b_pad, co.cout, b, frames, h, w_)

@@ -363,6 +363,16 @@ def conv_out(x, wk, bias, batch, frames, h, w_):
     return out
 
 
+def conv_out_tc(x, wk_pad, bias_pad, cout, batch, frames, h, w_):
+    """conv_out on the tensor-core kernel: wk_pad [64, 9*Cin] / bias_pad [64] are the conv_out weight / bias with the
+    output channels zero-padded to one 64-wide tile (repack.pad_out_channels); returns (B, cout, F, H, W)."""
+    rows = conv2d_3x3(x, batch * frames, h, w_, wk_pad, bias_pad)
+    out = torch.empty((batch, cout, frames, h, w_), dtype=torch.float16, device=x.device)
+    _lib.check(_lib.lib().lvd_rows_to_ncfhw(rows.data_ptr(), rows.stride(0), out.data_ptr(), batch, cout, frames,
+                                            h * w_, _stream()), "rows_to_ncfhw")
+    return out
+
+
 def upsample2x(x, n_img, h, w_, out=None):
     _check_act(x, "x")
     c = x.shape[1]

@@ -47,3 +47,13 @@ def s2_dgrad_weights(wk, cin):
                     shifts.append((sx, sy))
             out[(a, b)] = (torch.cat(cols, dim=1).contiguous(), shifts)
     return out
+
+
+def pad_out_channels(wk, bias, n=64):
+    """[Cout, K] weight and [Cout] bias -> zero-padded to n output channels (one GEMM tile wide)."""
+    co, k = wk.shape
+    wp = torch.zeros((n, k), dtype=wk.dtype, device=wk.device)
+    wp[:co] = wk
+    bp = torch.zeros((n,), dtype=bias.dtype, device=bias.device)
+    bp[:co] = bias
+    return wp, bp

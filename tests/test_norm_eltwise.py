@@ -88,3 +88,24 @@ def test_upsample_timestep_silu(cuda):
     assert (e.float() - ref).abs().max().item() < 2e-3
     v = _rand((1000,), cuda, seed=16, scale=3.0)
     assert rel_err(ops.silu(v), F.silu(v.float())) < TOL
+
+
+@pytest.mark.gpu
+def test_conv_out_tensor_core_path_matches_small_kernel(cuda):
+    """conv_out through lvd_gemm (output channels zero-padded to a 64-wide tile) + lvd_rows_to_ncfhw against the
+    one-warp-per-pixel kernel and a torch fp32 conv."""
+    from lvd_b200 import ops, repack
+    g = torch.Generator().manual_seed(9)
+    b, f, h, w, cin, cout = 2, 3, 10, 18, 320, 4
+    x = torch.randn((b * f * h * w, cin), generator=g).half().to(cuda)
+    wo = (torch.randn((cout, cin, 3, 3), generator=g) * 0.02).half().to(cuda)
+    bo = (torch.randn((cout,), generator=g) * 0.1).half().to(cuda)
+    wk = repack.conv_weight_krsc(wo)
+    y_small = ops.conv_out(x, wk, bo, b, f, h, w)
+    wp, bp = repack.pad_out_channels(wk, bo)
+    y_tc = ops.conv_out_tc(x, wp, bp, cout, b, f, h, w)
+    xi = x.float().reshape(b * f, h, w, cin).permute(0, 3, 1, 2)
+    ref = torch.nn.functional.conv2d(xi, wo.float(), bo.float(), padding=1)
+    ref = ref.reshape(b, f, cout, h, w).permute(0, 2, 1, 3, 4)
+    assert y_tc.shape == (b, cout, f, h, w)
+    assert rel_err(y_tc, ref) < 3e-3 and rel_err(y_small, ref) < 3e-3
