@@ -37,6 +37,8 @@ class GuidanceGraph:
         self.cfg = engine.cfg
         self.dev = engine.dev
         self._s2 = {}
+        self.use_cuda_graph = True  # replay the pass from a CUDA graph from the second call of a structure on
+        self._graphs = {}
 
     # ------------------------------------------------------------------------------------------ module pairs
     def _resnet_fwd(self, L, x, n_img, h, w_, temb_all):
@@ -189,7 +191,60 @@ class GuidanceGraph:
     def run(self, latents, timestep, cond_embeddings, bboxes, object_positions, guidance_attn_keys, *, loss_scale=1.0,
             base_attn_dim=(40, 72), fg_top_p=0.2, bg_top_p=0.2, fg_weight=1.0, bg_weight=1.0, com_loss_scale=0.0):
         """latents (1, 4, F, h, w) fp16; cond_embeddings (1, 77, D).  Returns (loss [0-d fp32 cuda, scaled by
-        loss_scale], grad (1, 4, F, h, w) fp32 = GRAD_SCALE * d loss / d latents)."""
+        loss_scale], grad (1, 4, F, h, w) fp32 = GRAD_SCALE * d loss / d latents).
+
+        Launch sequencing: the ~2100 launches of one pass are replayed from a CUDA graph from the second call with the
+        same structure (shapes, guided keys, token columns, slot counts, hyper-parameters) on; latents, timestep,
+        embeddings and the rasterised box tables are copied into the graph's static buffers before each replay."""
+        hp = dict(loss_scale=loss_scale, base_attn_dim=tuple(base_attn_dim), fg_top_p=fg_top_p, bg_top_p=bg_top_p,
+                  fg_weight=fg_weight, bg_weight=bg_weight, com_loss_scale=com_loss_scale)
+        tok_cols = tuple(int(t) for obj in object_positions for t in obj)
+        if (not self.use_cuda_graph or ops.PROF is not None or torch.cuda.is_current_stream_capturing() or
+                len(bboxes) == 0 or len(tok_cols) == 0):
+            return self._run_impl(latents, timestep, cond_embeddings, bboxes, object_positions, guidance_attn_keys, **hp)
+        key = (tuple(latents.shape), tuple(cond_embeddings.shape), tuple(tuple(k) for k in guidance_attn_keys),
+               tuple(tuple(int(t) for t in obj) for obj in object_positions), tuple(sorted(hp.items())))
+        ent = self._graphs.get(key)
+        if ent is None:  # first sighting: eager (also warms the allocator, kernel attributes and transposed weights)
+            self._graphs[key] = "seen"
+            return self._run_impl(latents, timestep, cond_embeddings, bboxes, object_positions, guidance_attn_keys, **hp)
+        dev = self.dev
+        frames = latents.shape[2]
+        if ent == "seen":
+            while len([v for v in self._graphs.values() if v != "seen"]) >= 2:  # each graph pins its activations
+                old = next(k for k, v in self._graphs.items() if v != "seen")
+                del self._graphs[old]
+            st = dict(x=torch.empty(tuple(latents.shape), dtype=torch.float16, device=dev),
+                      t=torch.empty((frames,), dtype=torch.float32, device=dev),
+                      ehs=torch.empty(tuple(cond_embeddings.shape), dtype=torch.float16, device=dev), slots={})
+            self._fill_static(st, latents, timestep, cond_embeddings, bboxes, object_positions)
+            # dry run outside capture: allocates the static slot tables for every guided resolution
+            self._run_impl(st["x"], st["t"], st["ehs"], bboxes, object_positions, guidance_attn_keys, slots=st["slots"],
+                           **hp)
+            torch.cuda.synchronize(dev)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                st["loss"], st["grad"] = self._run_impl(st["x"], st["t"], st["ehs"], bboxes, object_positions,
+                                                        guidance_attn_keys, slots=st["slots"], **hp)
+            st["graph"] = g
+            self._graphs[key] = ent = st
+        self._fill_static(ent, latents, timestep, cond_embeddings, bboxes, object_positions)
+        ent["graph"].replay()
+        return ent["loss"].clone(), ent["grad"].clone()
+
+    def _fill_static(self, st, latents, timestep, cond_embeddings, bboxes, object_positions):
+        st["x"].copy_(latents, non_blocking=True)
+        st["ehs"].copy_(cond_embeddings, non_blocking=True)
+        st["t"].fill_(float(timestep))
+        frames = latents.shape[2]
+        for (H, W), (cols, boxes, wts) in st["slots"].items():  # refresh the rasterised boxes of every resolution
+            _, nb_, nw_ = build_slots(bboxes, object_positions, frames, H, W, torch.device("cpu"))
+            boxes.copy_(nb_, non_blocking=True)
+            wts.copy_(nw_, non_blocking=True)
+
+    def _run_impl(self, latents, timestep, cond_embeddings, bboxes, object_positions, guidance_attn_keys, *,
+                  loss_scale=1.0, base_attn_dim=(40, 72), fg_top_p=0.2, bg_top_p=0.2, fg_weight=1.0, bg_weight=1.0,
+                  com_loss_scale=0.0, slots=None):
         cfg, w, dev = self.cfg, self.w, self.dev
         boc = list(cfg["block_out_channels"])
         nb = len(boc)
@@ -208,8 +263,12 @@ class GuidanceGraph:
         if n_obj == 0 or len(tok_cols) == 0:
             return loss, torch.zeros(latents.shape, dtype=torch.float32, device=dev)
         assert len(tok_cols) <= 16, "at most 16 (object, token) pairs per guidance call"
-        t = torch.as_tensor(timestep, device=dev).reshape(-1).to(torch.float32).expand(1).repeat_interleave(frames)
-        t = t.contiguous()
+        if torch.is_tensor(timestep) and timestep.is_cuda and timestep.dtype == torch.float32 and \
+                timestep.numel() == frames:
+            t = timestep  # pre-expanded device tensor (graph replay: the value is read at run time)
+        else:
+            t = torch.as_tensor(timestep, device=dev).reshape(-1).to(torch.float32).expand(1).repeat_interleave(frames)
+            t = t.contiguous()
         temb = ops.timestep_embed(t, boc[0])
         temb = ops.linear(temb, w["time1"].w, w["time1"].b, act=ops.ACT_SILU)
         temb = ops.linear(temb, w["time2"].w, w["time2"].b)
@@ -308,7 +367,13 @@ class GuidanceGraph:
             if kind == "attn" and key is not None:
                 bc = c.block
                 H, W = get_hw_from_attn_dim(attn_dim=bc.hw, base_attn_dim=base_attn_dim)
-                _, boxes, wts_slot = build_slots(bboxes, object_positions, frames, H, W, dev)
+                if slots is not None and (H, W) in slots:  # static tables of a captured graph
+                    _, boxes, wts_slot = slots[(H, W)]
+                else:
+                    tabs = build_slots(bboxes, object_positions, frames, H, W, dev)
+                    if slots is not None:
+                        slots[(H, W)] = tabs
+                    _, boxes, wts_slot = tabs
                 dp = torch.empty_like(bc.p_tok)
                 ops.box_energy(bc.p_tok, loss, boxes, wts_slot, frames=frames, heads=bc.heads, H=H, W=W,
                                fg_top_p=fg_top_p, bg_top_p=bg_top_p, fg_weight=fg_weight, bg_weight=bg_weight,

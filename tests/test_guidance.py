@@ -96,3 +96,38 @@ def test_guidance_gradient_other_key_sets(cuda, keys):
     print(f"\n[guidance keys={keys}] loss {loss.item():.4f} / {ref_loss.item():.4f}  grad cos {cos:.5f} rel {rel:.4f}")
     assert abs(loss.item() - ref_loss.item()) <= 3e-3 * abs(ref_loss.item())
     assert cos >= 0.995 and rel <= 0.08
+
+
+def test_guidance_pass_graph_replay_matches_eager(cuda):
+    """The pass is replayed from a CUDA graph from the second call of a structure on: eager, capture and replay calls
+    must agree (same kernels; the loss is an atomic float reduction, hence the tiny tolerance), and a replay with
+    DIFFERENT boxes / latents / timestep must track the eager result for those inputs (static tables are refreshed)."""
+    from lvd_b200.engine import UNetEngine
+    from lvd_b200.guidance_engine import GuidanceGraph
+    from oracle import unet3d_ref as R
+    from oracle import weights
+    cfg = weights.make_cfg("tiny")
+    eng = UNetEngine(cfg, weights.random_state_dict(cfg, seed=41), device=cuda)
+    gen = torch.Generator().manual_seed(42)
+    F, h, w = 8, 16, 16
+    keys = R.GUIDANCE_KEYS_DEFAULT
+    hp = dict(loss_scale=2.5, base_attn_dim=(h, w), fg_top_p=0.25, bg_top_p=0.25, fg_weight=1.0, bg_weight=2.0)
+    positions = [[2], [4, 5]]
+
+    def inputs(i):
+        x = torch.randn((1, 4, F, h, w), generator=gen).half().to(cuda)
+        ehs = torch.randn((1, 77, 128), generator=gen).half().to(cuda)
+        bboxes = [[(0.05 * i + 0.02 * f, 0.2, 0.5 + 0.02 * f, 0.8) for f in range(F)],
+                  [(0.4, 0.1 * i, 0.9, 0.5 + 0.1 * i) if f % 2 else (0, 0, 0, 0) for f in range(F)]]
+        return x, 900 - 100 * i, ehs, bboxes
+
+    cases = [inputs(i) for i in range(4)]
+    eager = GuidanceGraph(eng)
+    eager.use_cuda_graph = False
+    graphed = GuidanceGraph(eng)
+    for i, (x, t, ehs, bboxes) in enumerate(cases):  # call 0 eager, call 1 captures, calls 2-3 replay
+        l0, g0 = eager.run(x, t, ehs, bboxes, positions, keys, **hp)
+        l1, g1 = graphed.run(x, t, ehs, bboxes, positions, keys, **hp)
+        assert abs(l0.item() - l1.item()) <= 1e-5 * abs(l0.item()) + 1e-7, (i, l0.item(), l1.item())
+        assert torch.equal(g0, g1), i
+    assert sum(1 for v in graphed._graphs.values() if v != "seen") == 1
