@@ -162,6 +162,19 @@ int lvd_upsample2x(const void* x, int64_t ld_x, void* y, int64_t ld_y, int32_t n
                    int32_t channels, void* stream);
 int lvd_timestep_embed(const void* timesteps_f32, void* out, int32_t batch, int32_t dim, void* stream);
 int lvd_silu(const void* x, void* y, int64_t n, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * VAE decode (TextToVideoSDPipeline.decode_latents,
+ * controllable_pipeline_text_to_video_synth.py:374-400, over diffusers 0.27.2 AutoencoderKL -- not vendored by the
+ * reference).  The decoder's convolutions / GroupNorms / up-sampling run on the entry points above; two small
+ * pieces are specific to it:
+ * lvd_softmax_rows   : in-place fp32 row softmax of scale * x (fp16 storage) -- the single-head, 512-wide attention
+ *                      of the decoder's mid block runs its two products as lvd_gemm launches.
+ * lvd_pointwise_small: 1x1 convolution between <= 8 channels on planar (N, C, HW) fp16 (post_quant_conv).
+ * ---------------------------------------------------------------------------------------------------------- */
+int lvd_softmax_rows(void* x, int64_t ld, int64_t rows, int32_t cols, float scale, void* stream);
+int lvd_pointwise_small(const void* x, const void* weight, const void* bias, void* out, int32_t n, int32_t cin,
+                        int32_t cout, int64_t hw, void* stream);
 int lvd_copy_rows(const void* x, int64_t ld_x, void* y, int64_t ld_y, int64_t rows, int32_t channels, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------

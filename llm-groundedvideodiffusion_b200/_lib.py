@@ -131,6 +131,8 @@ def _declare(l):
     l.lvd_upsample2x.argtypes = [vp, i64, vp, i64, i32, i32, i32, i32, vp]
     l.lvd_timestep_embed.argtypes = [vp, vp, i32, i32, vp]
     l.lvd_silu.argtypes = [vp, vp, i64, vp]
+    l.lvd_softmax_rows.argtypes = [vp, i64, i64, i32, ctypes.c_float, vp]
+    l.lvd_pointwise_small.argtypes = [vp, vp, vp, vp, i32, i32, i32, i64, vp]
     l.lvd_copy_rows.argtypes = [vp, i64, vp, i64, i64, i32, vp]
     l.lvd_rows_to_ncfhw.argtypes = [vp, i64, vp, i32, i32, i32, i64, vp]
     l.lvd_cfg_dpm_step.argtypes = [vp, vp, vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, f32, f32, i32, vp]
@@ -173,6 +175,8 @@ EXPORTS = [
     "lvd_upsample2x",
     "lvd_timestep_embed",
     "lvd_silu",
+    "lvd_softmax_rows",
+    "lvd_pointwise_small",
     "lvd_copy_rows",
     "lvd_rows_to_ncfhw",
     "lvd_cfg_dpm_step",

@@ -154,6 +154,92 @@ __global__ void rows_to_ncfhw_kernel(const __half* __restrict__ rows, long long 
   }
 }
 
+// ---------------------------------------------------------------------------------------------- VAE helpers
+// Row softmax (fp32 math, in place) for the single-head 512-wide attention of the VAE mid block, whose two products run
+// as plain GEMMs (diffusers Attention with upcast_softmax: softmax(scale * Q K^T) in fp32, cast to fp16).  One CTA per
+// row, the row lives in registers (cols <= 8192).
+constexpr int kSmxThreads = 256;
+constexpr int kSmxVec = 4;  // 16-byte vectors per thread -> 8 * 4 * 256 = 8192 columns
+__global__ void __launch_bounds__(kSmxThreads) softmax_rows_kernel(__half* __restrict__ x, long long ld, int cols,
+                                                                   float scale_log2) {
+  __shared__ float s_red[kSmxThreads / 32];
+  __half* row = x + static_cast<long long>(blockIdx.x) * ld;
+  const int nvec = cols >> 3;
+  float v[kSmxVec][8];
+  float mx = -3.0e38f;
+#pragma unroll
+  for (int k = 0; k < kSmxVec; ++k) {
+    const int i = threadIdx.x + k * kSmxThreads;
+    if (i < nvec) {
+      const uint4 u = *reinterpret_cast<const uint4*>(row + i * 8);
+      const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __half22float2(h[j]);
+        v[k][2 * j] = f.x;
+        v[k][2 * j + 1] = f.y;
+        mx = fmaxf(mx, fmaxf(f.x, f.y));
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  mx = s_red[0];
+#pragma unroll
+  for (int w = 1; w < kSmxThreads / 32; ++w) mx = fmaxf(mx, s_red[w]);
+  __syncthreads();
+  float sum = 0.f;
+#pragma unroll
+  for (int k = 0; k < kSmxVec; ++k) {
+    if (threadIdx.x + k * kSmxThreads < nvec) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        v[k][j] = exp2f((v[k][j] - mx) * scale_log2);
+        sum += v[k][j];
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = sum;
+  __syncthreads();
+  sum = 0.f;  // fixed order: deterministic
+#pragma unroll
+  for (int w = 0; w < kSmxThreads / 32; ++w) sum += s_red[w];
+  const float inv = 1.0f / sum;
+#pragma unroll
+  for (int k = 0; k < kSmxVec; ++k) {
+    const int i = threadIdx.x + k * kSmxThreads;
+    if (i < nvec) {
+      uint4 u;
+      __half2* h = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) h[j] = __floats2half2_rn(v[k][2 * j] * inv, v[k][2 * j + 1] * inv);
+      *reinterpret_cast<uint4*>(row + i * 8) = u;
+    }
+  }
+}
+
+// 1x1 convolution between <= 8 channels on planar (N, C, HW) fp16 (AutoencoderKL.post_quant_conv): thread per pixel.
+__global__ void pointwise_small_kernel(const __half* __restrict__ x, const __half* __restrict__ w,
+                                       const __half* __restrict__ bias, __half* __restrict__ out, int N, int Cin,
+                                       int Cout, long long hw) {
+  const long long total = static_cast<long long>(N) * hw;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long n = idx / hw, p = idx % hw;
+    float in[8];
+    for (int ci = 0; ci < Cin; ++ci) in[ci] = __half2float(x[(n * Cin + ci) * hw + p]);
+    for (int co = 0; co < Cout; ++co) {
+      float a = bias ? __half2float(bias[co]) : 0.f;
+      for (int ci = 0; ci < Cin; ++ci) a = fmaf(__half2float(w[co * Cin + ci]), in[ci], a);
+      out[(n * Cout + co) * hw + p] = __float2half_rn(a);
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- upsample 2x nearest
 __global__ void upsample2x_kernel(const __half* __restrict__ x, long long ld_x, __half* __restrict__ y, long long ld_y,
                                   int n_img, int H, int W, int C) {
@@ -268,6 +354,29 @@ extern "C" int lvd_rows_to_ncfhw(const void* rows, int64_t ld, void* out, int32_
   const long long total = static_cast<long long>(batch) * cout * frames * hw;
   rows_to_ncfhw_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __half*>(rows), ld, static_cast<__half*>(out), batch, cout, frames, hw);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  LVD_CHECK_CUDA(cudaGetLastError());
+  return LVD_OK;
+}
+
+extern "C" int lvd_softmax_rows(void* x, int64_t ld, int64_t rows, int32_t cols, float scale, void* stream) {
+  LVD_REQUIRE(x && rows >= 1 && cols >= 8 && cols % 8 == 0 && cols <= 8 * kSmxVec * kSmxThreads && ld % 8 == 0 &&
+                  rows < (1ll << 31),
+              "lvd_softmax_rows: bad arguments (cols=%d)", cols);
+  softmax_rows_kernel<<<static_cast<unsigned>(rows), kSmxThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<__half*>(x), ld, cols, scale * 1.4426950408889634f);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  LVD_CHECK_CUDA(cudaGetLastError());
+  return LVD_OK;
+}
+
+extern "C" int lvd_pointwise_small(const void* x, const void* weight, const void* bias, void* out, int32_t n,
+                                   int32_t cin, int32_t cout, int64_t hw, void* stream) {
+  LVD_REQUIRE(x && weight && out && n >= 1 && cin >= 1 && cin <= 8 && cout >= 1 && cout <= 8 && hw >= 1,
+              "lvd_pointwise_small: bad arguments");
+  pointwise_small_kernel<<<grid_for(static_cast<long long>(n) * hw, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __half*>(x), static_cast<const __half*>(weight), static_cast<const __half*>(bias),
+      static_cast<__half*>(out), n, cin, cout, hw);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   LVD_CHECK_CUDA(cudaGetLastError());
   return LVD_OK;

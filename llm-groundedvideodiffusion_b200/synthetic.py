@@ -205,3 +205,65 @@ def random_state_dict(cfg, seed=0, dtype=torch.float32, gain=1.0):
             t = torch.randn(shape, generator=g) * (gain / fan_in ** 0.5)
         sd[name] = t.to(dtype)
     return sd
+
+
+# ---------------------------------------------------------------------------------------------- VAE decoder
+# diffusers 0.27.2 AutoencoderKL (SD-1.x VAE config used by Zeroscope / ModelScope: SURVEY.md Appendix B.8), decoder
+# half only: `post_quant_conv` + `decoder.*` state_dict names and shapes.
+VAE_SD = dict(latent_channels=4, out_channels=3, block_out_channels=(128, 256, 512, 512), layers_per_block=2,
+              norm_num_groups=32, scaling_factor=0.18215)
+VAE_TINY = dict(VAE_SD, block_out_channels=(64, 64, 128, 128))
+
+
+def vae_param_spec(cfg):
+    spec = OrderedDict()
+    boc = list(cfg["block_out_channels"])
+    lc = cfg["latent_channels"]
+    top = boc[-1]
+    _conv2d(spec, "post_quant_conv", lc, lc, 1)
+    _conv2d(spec, "decoder.conv_in", top, lc, 3)
+
+    def resnet(p, cin, cout):
+        _norm(spec, p + ".norm1", cin)
+        _conv2d(spec, p + ".conv1", cout, cin, 3)
+        _norm(spec, p + ".norm2", cout)
+        _conv2d(spec, p + ".conv2", cout, cout, 3)
+        if cin != cout:
+            _conv2d(spec, p + ".conv_shortcut", cout, cin, 1)
+
+    resnet("decoder.mid_block.resnets.0", top, top)
+    a = "decoder.mid_block.attentions.0"
+    _norm(spec, a + ".group_norm", top)
+    for n in ("to_q", "to_k", "to_v", "to_out.0"):
+        _lin(spec, a + "." + n, top, top)
+    resnet("decoder.mid_block.resnets.1", top, top)
+    rev = boc[::-1]
+    prev = rev[0]
+    for i, c in enumerate(rev):
+        for j in range(cfg["layers_per_block"] + 1):
+            resnet(f"decoder.up_blocks.{i}.resnets.{j}", prev if j == 0 else c, c)
+        if i != len(rev) - 1:
+            _conv2d(spec, f"decoder.up_blocks.{i}.upsamplers.0.conv", c, c, 3)
+        prev = c
+    _norm(spec, "decoder.conv_norm_out", boc[0])
+    _conv2d(spec, "decoder.conv_out", cfg["out_channels"], boc[0], 3)
+    return spec
+
+
+def random_vae_state_dict(cfg, seed=0, dtype=torch.float32):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    sd = OrderedDict()
+    for name, shape in vae_param_spec(cfg).items():
+        leaf = name.rsplit(".", 1)[-1]
+        is_norm = "norm" in name.rsplit(".", 2)[-2]
+        if is_norm and leaf == "weight":
+            t = 1.0 + 0.1 * torch.randn(shape, generator=g)
+        elif leaf == "bias":
+            t = 0.05 * torch.randn(shape, generator=g)
+        else:
+            fan_in = 1
+            for s in shape[1:]:
+                fan_in *= s
+            t = torch.randn(shape, generator=g) * fan_in ** -0.5
+        sd[name] = t.to(dtype)
+    return sd
