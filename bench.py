@@ -69,6 +69,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-frames", type=int, default=2)
     ap.add_argument("--profile-json", default=None, help="write the per-kernel-family breakdown here")
+    ap.add_argument("--no-video", action="store_true",
+                    help="skip the secondary end-to-end measurement (one full 50-step video + VAE decode)")
     return ap.parse_args()
 
 
@@ -395,6 +397,44 @@ def run_gpu(args):
     ms_fused = time_steps([1, 6]) if wl["gated"] else None   # fusers on, no guidance
     ms_guided = time_steps([0, 5]) if guided_every else None  # guidance (+ fusers when gated)
 
+    # ---------------- secondary metric: one whole video through TextToVideoSDPipeline.__call__ --
+    # 50 steps (10 guided when the workload is guided, GLIGEN beta 0.4 when gated) + VAE decode to np frames.  Prompt
+    # embeddings are given (the CLIP text encoder is outside this repo's scope), weights are synthetic.
+    video = None
+    if not args.no_video:
+        from lvd_b200.models.controllable_pipeline_text_to_video_synth import TextToVideoSDPipeline
+        from lvd_b200.vae import AutoencoderKL
+        vae = AutoencoderKL().to(dev)
+        vae.load_state_dict(synthetic.random_vae_state_dict(synthetic.VAE_SD, seed=0, dtype=torch.float16))
+        vae.enable_slicing(8)
+        pipe = TextToVideoSDPipeline(unet=unet, vae=vae, scheduler=DPMSolverMultistepScheduler()).to(dev)
+        call = dict(prompt_embeds=ehs_host[1:2], negative_prompt_embeds=ehs_host[0:1], height=lat_h * 8,
+                    width=lat_w * 8, num_frames=frames, num_inference_steps=50, guidance_scale=GUIDANCE_SCALE,
+                    output_type="np", gligen_scheduled_sampling_beta=0.4)
+        if guided_every:
+            call["backward_guidance_kwargs"] = dict(guidance_kw)
+        if wl["gated"]:
+            call["gligen_inputs"] = gl_in
+        pipe(**dict(call, num_inference_steps=6, latents=lat_host.clone()))  # warm-up: VAE allocations, all graph variants
+        barrier()
+        t0 = time.perf_counter()
+        out = pipe(**dict(call, latents=lat_host.clone()))
+        torch.cuda.synchronize()
+        sec = time.perf_counter() - t0
+        tv = torch.tensor([sec], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tv, op=dist.ReduceOp.MAX)
+        sec = float(tv[0])
+        fr = out.frames
+        video = {"seconds_per_video": sec, "videos_per_s": world / sec, "frames_per_s": world * frames / sec,
+                 "frames_shape": list(fr.shape), "finite": bool((fr == fr).all()),
+                 "includes": "TextToVideoSDPipeline.__call__: 50 denoising steps"
+                             + (" (10 guided, 1 iteration each)" if guided_every else "")
+                             + (", GLIGEN fusers on the first 20" if wl["gated"] else "")
+                             + ", VAE decode (native AutoencoderKL, SD-1.x decoder) and tensor2vid to host np.float32; "
+                               "prompt embeddings given (text encoder out of scope); wall clock incl. H2D / D2H"}
+        del pipe, vae, out
+
     # ---------------- instrumented passes: per-kernel-family durations (CUDA events around every launch), eager
     lib = _lib.lib()
     set_fusers(False)
@@ -511,6 +551,7 @@ def run_gpu(args):
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": lat_host.numel() * 2 + ehs_host.numel() * 2,
                     "d2h_bytes_per_step": out_host.numel() * 2 + (4 if guided_every else 0)},
             "gpu_launches": int(launches),
+            "video": video,
             "clocks": clocks,
             "roofline": roofline,
             "step_tflops": tflop_step / (ms_step * 1e-3),

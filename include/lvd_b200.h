@@ -171,8 +171,11 @@ int lvd_silu(const void* x, void* y, int64_t n, void* stream);
  * lvd_softmax_rows   : in-place fp32 row softmax of scale * x (fp16 storage) -- the single-head, 512-wide attention
  *                      of the decoder's mid block runs its two products as lvd_gemm launches.
  * lvd_pointwise_small: 1x1 convolution between <= 8 channels on planar (N, C, HW) fp16 (post_quant_conv).
+ * lvd_frames_postprocess: decoded frames (N, C, HW) fp16 in [-1, 1] -> (N, HW, C) fp32 in [0, 1] -- tensor2vid /
+ *                      VaeImageProcessor.postprocess("np") (controllable_pipeline_text_to_video_synth.py:66-88).
  * ---------------------------------------------------------------------------------------------------------- */
 int lvd_softmax_rows(void* x, int64_t ld, int64_t rows, int32_t cols, float scale, void* stream);
+int lvd_frames_postprocess(const void* x, void* out, int64_t n, int32_t channels, int64_t hw, void* stream);
 int lvd_pointwise_small(const void* x, const void* weight, const void* bias, void* out, int32_t n, int32_t cin,
                         int32_t cout, int64_t hw, void* stream);
 int lvd_copy_rows(const void* x, int64_t ld_x, void* y, int64_t ld_y, int64_t rows, int32_t channels, void* stream);

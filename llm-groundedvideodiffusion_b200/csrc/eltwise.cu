@@ -240,6 +240,23 @@ __global__ void pointwise_small_kernel(const __half* __restrict__ x, const __hal
   }
 }
 
+// (N, C, HW) fp16 in [-1, 1]  ->  (N, HW, C) fp32 in [0, 1]: VaeImageProcessor.postprocess(output_type="np") =
+// denormalize (x / 2 + 0.5).clamp(0, 1) + channels-last, as tensor2vid applies it per video
+// (controllable_pipeline_text_to_video_synth.py:66-88).
+__global__ void frames_postprocess_kernel(const __half* __restrict__ x, float* __restrict__ out, long long n, int C,
+                                          long long hw) {
+  const long long total = n * hw;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long i = idx / hw, p = idx % hw;
+    for (int c = 0; c < C; ++c) {
+      float v = __half2float(x[(i * C + c) * hw + p]) * 0.5f + 0.5f;
+      v = fminf(fmaxf(v, 0.f), 1.f);
+      out[idx * C + c] = v;
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- upsample 2x nearest
 __global__ void upsample2x_kernel(const __half* __restrict__ x, long long ld_x, __half* __restrict__ y, long long ld_y,
                                   int n_img, int H, int W, int C) {
@@ -365,6 +382,15 @@ extern "C" int lvd_softmax_rows(void* x, int64_t ld, int64_t rows, int32_t cols,
               "lvd_softmax_rows: bad arguments (cols=%d)", cols);
   softmax_rows_kernel<<<static_cast<unsigned>(rows), kSmxThreads, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<__half*>(x), ld, cols, scale * 1.4426950408889634f);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  LVD_CHECK_CUDA(cudaGetLastError());
+  return LVD_OK;
+}
+
+extern "C" int lvd_frames_postprocess(const void* x, void* out, int64_t n, int32_t channels, int64_t hw, void* stream) {
+  LVD_REQUIRE(x && out && n >= 1 && channels >= 1 && channels <= 8 && hw >= 1, "lvd_frames_postprocess: bad arguments");
+  frames_postprocess_kernel<<<grid_for(n * hw, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __half*>(x), static_cast<float*>(out), n, channels, hw);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   LVD_CHECK_CUDA(cudaGetLastError());
   return LVD_OK;

@@ -276,6 +276,10 @@ class TextToVideoSDPipeline:
                 callback(i, t, latents)
         if output_type == "latent":
             out = latents
+        elif output_type == "np" and hasattr(self.vae, "decode_video_np"):
+            # native VAE (lvd_b200.vae.AutoencoderKL): decode + tensor2vid's denormalise / channels-last in one pass.
+            # (The reference decodes twice, :963 and :969, and keeps the second result; once gives the same frames.)
+            out = self.vae.decode_video_np(latents)
         else:
             video = self.decode_latents(latents)
             out = video if output_type == "pt" else video.permute(0, 2, 3, 4, 1).clamp(-1, 1).add(1).div(2).cpu().numpy()

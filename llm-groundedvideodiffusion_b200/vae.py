@@ -198,6 +198,18 @@ class AutoencoderKL:
         self._engine = VAEDecoderEngine(self.config, self._state, self._device)
         self._state = None
 
+    def decode_video_np(self, latents):
+        """(B, 4, F, h, w) scheduler latents -> np.float32 [B, F, 8h, 8w, 3] in [0, 1]: `decode_latents` followed by
+        `tensor2vid(..., "np")` (controllable_pipeline_text_to_video_synth.py:374-400, 66-88)."""
+        b, c, f, h, w = latents.shape
+        lat = (latents / self.config.scaling_factor).permute(0, 2, 1, 3, 4).reshape(b * f, c, h, w)
+        img = self.decode(lat).sample
+        n, co, hh, ww = img.shape
+        out = torch.empty((b, f, hh, ww, co), dtype=torch.float32, device=img.device)
+        _lib.check(_lib.lib().lvd_frames_postprocess(img.data_ptr(), out.data_ptr(), n, co, hh * ww, ops._stream()),
+                   "frames_postprocess")
+        return out.cpu().numpy()
+
     def decode(self, z, return_dict=True):
         if self._engine is None:
             raise RuntimeError("AutoencoderKL has no weights: call load_state_dict() first")
