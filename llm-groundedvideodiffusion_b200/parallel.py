@@ -56,3 +56,61 @@ def max_over_ranks(value, device):
     if dist.is_initialized() and dist.get_world_size() > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t[0])
+
+
+def generate_sharded(generate_fn, layouts, device, *, repeats=1, seed_offset=0):
+    """The batch-of-prompts driver of SURVEY.md section 8(e): rank 0 holds `layouts` (one entry per prompt: a dict with
+    `bboxes` [n_obj][F][4] floats and `object_positions` [n_obj][n_tok] ints); the work table (prompt index, repeat,
+    seed) and the packed box tables are broadcast, every rank generates its contiguous window with
+    `generate_fn(seed, bboxes, object_positions) -> uint8 [F, H, W, 3]` (the pipeline call; no collective inside), and
+    the frames are gathered on rank 0 in item order.  Returns (frames uint8 [n_items, F, H, W, 3] | None, table)."""
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    rank = dist.get_rank() if world > 1 else 0
+    if rank == 0:
+        n_prompts = len(layouts)
+        rows = [(p, r, seed_for(p, r, seed_offset)) for p in range(n_prompts) for r in range(repeats)]
+        table = torch.tensor(rows, dtype=torch.int64).reshape(-1, 3)
+        max_obj = max(len(l["bboxes"]) for l in layouts)
+        max_tok = max(len(t) for l in layouts for t in l["object_positions"])
+        frames = len(layouts[0]["bboxes"][0])
+        boxes = torch.zeros((n_prompts, max_obj, frames, 4), dtype=torch.float64)  # float64: box rounding stays bit-exact
+        toks = torch.full((n_prompts, max_obj, max_tok), -1, dtype=torch.int64)
+        for p, l in enumerate(layouts):
+            for o, (ob, ot) in enumerate(zip(l["bboxes"], l["object_positions"])):
+                boxes[p, o] = torch.tensor(ob, dtype=torch.float64)
+                toks[p, o, :len(ot)] = torch.tensor(ot, dtype=torch.int64)
+        meta = torch.tensor([n_prompts, max_obj, max_tok, frames], dtype=torch.int64)
+    else:
+        table = torch.empty(0, dtype=torch.int64)
+        meta = torch.zeros(4, dtype=torch.int64)
+        boxes = toks = None
+    table = broadcast_work_table(table, device)
+    if world > 1:
+        meta = meta.to(device)
+        dist.broadcast(meta, src=0)
+        n_prompts, max_obj, max_tok, frames = (int(v) for v in meta.tolist())
+        boxes = boxes.to(device) if rank == 0 else torch.empty((n_prompts, max_obj, frames, 4), dtype=torch.float64,
+                                                               device=device)
+        toks = toks.to(device) if rank == 0 else torch.empty((n_prompts, max_obj, max_tok), dtype=torch.int64,
+                                                             device=device)
+        dist.broadcast(boxes, src=0)
+        dist.broadcast(toks, src=0)
+    n_items = table.shape[0]
+    lo, hi = shard_items(n_items, rank, world)
+    outs = []
+    for i in range(lo, hi):
+        p, _, seed = (int(v) for v in table[i].tolist())
+        pos = [[int(t) for t in row.tolist() if t >= 0] for row in toks[p]]
+        keep = [o for o, t in enumerate(pos) if len(t) > 0]
+        bb = [[tuple(float(v) for v in fr) for fr in boxes[p, o].tolist()] for o in keep]
+        outs.append(generate_fn(seed, bb, [pos[o] for o in keep]))
+    if outs:
+        local = torch.stack([torch.as_tensor(o) for o in outs]).to(device)
+    else:  # a rank with an empty window still takes part in the gather (shape from a broadcast of rank 0's)
+        local = None
+    shape = torch.tensor(list(local.shape[1:]) if local is not None else [0, 0, 0, 0], dtype=torch.int64, device=device)
+    if world > 1:
+        dist.all_reduce(shape, op=dist.ReduceOp.MAX)
+    if local is None:
+        local = torch.empty((0,) + tuple(int(v) for v in shape.tolist()), dtype=torch.uint8, device=device)
+    return gather_results(local, n_items), table

@@ -55,3 +55,45 @@ def test_shard_items_covers_everything():
             assert wins[0][0] == 0 and wins[-1][1] == n
             assert all(a[1] == b[0] for a, b in zip(wins, wins[1:]))
             assert max(h - l for l, h in wins) - min(h - l for l, h in wins) <= 1
+
+
+def _gen_worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from lvd_b200 import parallel
+    F = 4
+    layouts = None
+    if rank == 0:
+        layouts = [dict(bboxes=[[(0.1 * p, 0.2, 0.5, 0.6 + 0.01 * f) for f in range(F)]] * (1 + p % 2),
+                        object_positions=[[2], [4, 5]][: 1 + p % 2]) for p in range(5)]
+    seen = []
+
+    def fake_pipe(seed, bboxes, positions):  # stands in for the pipeline call: encodes its inputs into the "frames"
+        seen.append((seed, len(bboxes), [len(t) for t in positions]))
+        img = torch.zeros((F, 2, 2, 3), dtype=torch.uint8)
+        img[..., 0] = seed % 251
+        img[..., 1] = len(bboxes)
+        img[..., 2] = int(round(bboxes[0][0][0] * 100))
+        return img
+
+    frames, table = parallel.generate_sharded(fake_pipe, layouts, "cpu", repeats=2, seed_offset=1)
+    ret[f"seen{rank}"] = seen
+    if rank == 0:
+        ret["frames"] = frames[:, 0, 0, 0, :].tolist()
+        ret["table"] = table.tolist()
+    dist.destroy_process_group()
+
+
+def test_generate_sharded_two_ranks_gloo():
+    """Work table + packed box tables broadcast from rank 0, contiguous windows, frames gathered in item order."""
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_gen_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+    table = ret["table"]
+    assert len(table) == 10 and table[3] == [1, 1, 1 + 6789 + 1]
+    assert len(ret["seen0"]) == 5 and len(ret["seen1"]) == 5
+    for (p, r, seed), px in zip(table, ret["frames"]):
+        assert px == [seed % 251, 1 + p % 2, 10 * p]
+    assert ret["seen1"][0] == (table[5][2], 1 + table[5][0] % 2, [1, 2][: 1 + table[5][0] % 2])
