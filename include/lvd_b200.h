@@ -61,7 +61,7 @@ typedef struct lvd_gemm_desc {
   int32_t block_n;    /* 64 | 128 | 160 | 256; n % block_n == 0 (GEGLU: 128 | 256) */
   int64_t ldb;        /* elements */
   int32_t n;          /* GEMM N (for GEGLU: 2x the output width; every block_n columns = [block_n/2 value | block_n/2 gate]) */
-  int32_t act;        /* 0 none, 1 SiLU, 2 GEGLU */
+  int32_t act;        /* 0 none, 1 SiLU, 2 GEGLU, 3 GELU (erf; CLIP text encoder MLP) */
   /* output geometry: tile axis i (=A dims 1..4) covers out_dims[i] positions in steps of a_box[i+1] */
   int32_t out_dims[4];
   int32_t rv_stride[4];      /* rowvec row = sum coord_i * rv_stride[i] */
@@ -121,7 +121,7 @@ typedef struct lvd_attn_desc {
   int32_t n_tok;
   int32_t tok_cols[16];
   float scale;
-  int32_t reserved;
+  int32_t causal; /* mode 0, s_k <= 128, no map outputs: key j is visible to query i iff j <= i (CLIP text encoder) */
 } lvd_attn_desc;
 
 int lvd_attention(const lvd_attn_desc* d, void* stream);
@@ -176,6 +176,10 @@ int lvd_silu(const void* x, void* y, int64_t n, void* stream);
  * ---------------------------------------------------------------------------------------------------------- */
 int lvd_softmax_rows(void* x, int64_t ld, int64_t rows, int32_t cols, float scale, void* stream);
 int lvd_frames_postprocess(const void* x, void* out, int64_t n, int32_t channels, int64_t hw, void* stream);
+/* lvd_embed_tokens: out[(b*seq + s), :] = token_embedding[ids[b, s], :] + position_embedding[s, :]  (fp16; CLIPTextEmbeddings,
+ * the caller-supplied text encoder of _encode_prompt, controllable_pipeline_text_to_video_synth.py:197-372). */
+int lvd_embed_tokens(const int64_t* ids, const void* token_embedding, const void* position_embedding, void* out,
+                     int64_t n_tokens, int32_t seq, int32_t dim, int32_t vocab, void* stream);
 int lvd_pointwise_small(const void* x, const void* weight, const void* bias, void* out, int32_t n, int32_t cin,
                         int32_t cout, int64_t hw, void* stream);
 int lvd_copy_rows(const void* x, int64_t ld_x, void* y, int64_t ld_y, int64_t rows, int32_t channels, void* stream);

@@ -437,6 +437,7 @@ extern "C" int lvd_attention(const lvd_attn_desc* d, void* stream) {
         if (r != 1) return r;
       }
     }
+    LVD_REQUIRE(!d->causal, "lvd_attention: causal masking needs s_k <= 128 and no probability / lse outputs");
     int64_t qd[4] = {width_q, d->s_q, 1, d->nz};
     int64_t qs[4] = {1, d->ld_q, d->ld_q * d->s_q, d->ld_q * d->s_q};
     int qb[4] = {64, d->s_q < 128 ? (int)d->s_q : 128, 1, 1};
@@ -462,6 +463,7 @@ extern "C" int lvd_attention(const lvd_attn_desc* d, void* stream) {
     g.o_z_stride = d->s_q;
     g.p_rows = d->s_q;
   } else if (d->mode == 2) {
+    LVD_REQUIRE(!d->causal, "lvd_attention: causal masking is a mode-0 option");
     // packed sequences: rows (z*hw + p)*F + f -- every F consecutive rows are one sequence; bp sequences per tile
     const int F = d->frames;
     LVD_REQUIRE(F >= 8 && F <= 32 && F % 8 == 0 && d->hw >= 1,

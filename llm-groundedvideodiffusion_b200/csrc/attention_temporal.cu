@@ -194,7 +194,7 @@ struct CrossArgs {
   long long ld_q, ld_kv, ld_o;
   long long n_warps;  // nz * q_tiles * heads
   int q_col0, k_col0, v_col0, o_col0;
-  int s_q, s_k, heads, q_tiles, kv_z_div;
+  int s_q, s_k, heads, q_tiles, kv_z_div, causal;
   float scale_log2;
 };
 
@@ -244,8 +244,9 @@ __global__ void __launch_bounds__(128) cross_attn_mma_kernel(const CrossArgs a) 
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) {
       const int c = nt * 8 + 2 * t;
-      if (c >= a.s_k) s[nt][2 * half] = -INFINITY;
-      if (c + 1 >= a.s_k) s[nt][2 * half + 1] = -INFINITY;
+      const int lim = a.causal ? min(a.s_k, r0 + half * 8 + g + 1) : a.s_k;  // causal: keys 0..query row
+      if (c >= lim) s[nt][2 * half] = -INFINITY;
+      if (c + 1 >= lim) s[nt][2 * half + 1] = -INFINITY;
       mx = fmaxf(mx, fmaxf(s[nt][2 * half], s[nt][2 * half + 1]));
     }
     mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
@@ -328,6 +329,7 @@ int launch_cross_attn_mma(const lvd_attn_desc* d, cudaStream_t stream) {
   a.heads = d->heads;
   a.q_tiles = (a.s_q + 15) / 16;
   a.kv_z_div = d->kv_z_div;
+  a.causal = d->causal ? 1 : 0;
   a.n_warps = static_cast<long long>(d->nz) * a.q_tiles * d->heads;
   a.scale_log2 = d->scale * 1.4426950408889634f;
   const long long blocks = (a.n_warps + 3) / 4;

@@ -222,6 +222,30 @@ __global__ void __launch_bounds__(kSmxThreads) softmax_rows_kernel(__half* __res
   }
 }
 
+// CLIPTextEmbeddings: token embedding gather + position embedding (fp16 add), one 16-byte vector per thread.
+__global__ void embed_tokens_kernel(const long long* __restrict__ ids, const __half* __restrict__ tok,
+                                    const __half* __restrict__ pos, __half* __restrict__ out, long long n_tokens, int seq,
+                                    int dim, int vocab) {
+  const int vpr = dim >> 3;
+  const long long total = n_tokens * vpr;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long t = idx / vpr;
+    const int v = static_cast<int>(idx % vpr);
+    long long id = ids[t];
+    id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+    const uint4 a = *reinterpret_cast<const uint4*>(tok + id * dim + v * 8);
+    const uint4 b = *reinterpret_cast<const uint4*>(pos + (t % seq) * dim + v * 8);
+    uint4 o;
+    const __half2* ha = reinterpret_cast<const __half2*>(&a);
+    const __half2* hb = reinterpret_cast<const __half2*>(&b);
+    __half2* ho = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) ho[i] = __hadd2(ha[i], hb[i]);
+    *reinterpret_cast<uint4*>(out + t * dim + v * 8) = o;
+  }
+}
+
 // 1x1 convolution between <= 8 channels on planar (N, C, HW) fp16 (AutoencoderKL.post_quant_conv): thread per pixel.
 __global__ void pointwise_small_kernel(const __half* __restrict__ x, const __half* __restrict__ w,
                                        const __half* __restrict__ bias, __half* __restrict__ out, int N, int Cin,
@@ -391,6 +415,19 @@ extern "C" int lvd_frames_postprocess(const void* x, void* out, int64_t n, int32
   LVD_REQUIRE(x && out && n >= 1 && channels >= 1 && channels <= 8 && hw >= 1, "lvd_frames_postprocess: bad arguments");
   frames_postprocess_kernel<<<grid_for(n * hw, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __half*>(x), static_cast<float*>(out), n, channels, hw);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  LVD_CHECK_CUDA(cudaGetLastError());
+  return LVD_OK;
+}
+
+extern "C" int lvd_embed_tokens(const int64_t* ids, const void* token_embedding, const void* position_embedding,
+                                void* out, int64_t n_tokens, int32_t seq, int32_t dim, int32_t vocab, void* stream) {
+  LVD_REQUIRE(ids && token_embedding && position_embedding && out && n_tokens >= 1 && seq >= 1 && dim % 8 == 0 &&
+                  vocab >= 1,
+              "lvd_embed_tokens: bad arguments");
+  embed_tokens_kernel<<<grid_for(n_tokens * (dim / 8), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const long long*>(ids), static_cast<const __half*>(token_embedding),
+      static_cast<const __half*>(position_embedding), static_cast<__half*>(out), n_tokens, seq, dim, vocab);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   LVD_CHECK_CUDA(cudaGetLastError());
   return LVD_OK;

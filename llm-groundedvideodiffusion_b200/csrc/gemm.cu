@@ -323,6 +323,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     const bool has_rowvec = kEpi == kEpiGeneric && g.rowvec != nullptr;
     const bool has_gamma = kEpi == kEpiGeneric && g.gamma != 1.0f;
     const bool has_silu = kEpi == kEpiGeneric && g.act == 1;
+    const bool has_gelu = kEpi == kEpiGeneric && g.act == 3;
     const __half* const bias = g.bias;
     int j[4];
     if (has_rowvec) {
@@ -452,6 +453,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
 #pragma unroll
               for (int i = 0; i < 16; ++i) v[i] = silu_f(round_h(v[i]));
             }
+            if (has_gelu) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = gelu_erf_f(round_h(v[i]));
+            }
           }
           if (has_rowvec && valid) {
             float t[16];
@@ -565,7 +570,7 @@ static int launch_gemm(const lvd_gemm_desc* d, cudaStream_t stream) {
   LVD_REQUIRE(d->k_per_tap > 0 && d->k_per_tap % 64 == 0, "lvd_gemm: k_per_tap=%d not a multiple of 64",
               d->k_per_tap);
   LVD_REQUIRE(d->n_taps >= 1 && d->n_taps <= LVD_MAX_TAPS, "lvd_gemm: n_taps=%d", d->n_taps);
-  LVD_REQUIRE(d->act >= 0 && d->act <= 2, "lvd_gemm: act=%d", d->act);
+  LVD_REQUIRE(d->act >= 0 && d->act <= 3, "lvd_gemm: act=%d", d->act);
   LVD_REQUIRE(d->act != 2 || d->block_n == 128 || d->block_n == 256, "lvd_gemm: GEGLU needs block_n 128 or 256");
   LVD_REQUIRE(!d->b_mn_major || d->block_n % 64 == 0, "lvd_gemm: MN-major B needs block_n %% 64 == 0");
   LVD_REQUIRE(d->a_box[0] == 64, "lvd_gemm: a_box[0] must be 64");

@@ -12,7 +12,7 @@ import torch
 from . import _lib
 from ._lib import GemmDesc
 
-ACT_NONE, ACT_SILU, ACT_GEGLU = 0, 1, 2
+ACT_NONE, ACT_SILU, ACT_GEGLU, ACT_GELU = 0, 1, 2, 3
 _NUM_SMS = 148  # B200
 
 # Optional per-launch instrumentation (bench.py's roofline pass): when PROF is a list, every launch appends
@@ -307,7 +307,8 @@ def layernorm(x, gamma, beta, eps=1e-5, out=None):
 
 # ----------------------------------------------------------------------------------------------- attention
 def attention(q, kv, *, heads, nz, s_q=0, s_k=0, q_col0=0, k_col0=0, v_col0=0, kv_z_div=1, temporal=False, frames=0,
-              hw=0, scale=0.125, out=None, o_col0=0, p_full=None, p_tok=None, tok_cols=(), packed=False, lse=None):
+              hw=0, scale=0.125, out=None, o_col0=0, p_full=None, p_tok=None, tok_cols=(), packed=False, lse=None,
+              causal=False):
     """softmax(Q K^T * scale) V with 64-wide heads.  q / kv are 2-D row buffers; q/k/v live at column offsets."""
     _check_act(q, "q")
     _check_act(kv, "kv")
@@ -329,6 +330,7 @@ def attention(q, kv, *, heads, nz, s_q=0, s_k=0, q_col0=0, k_col0=0, v_col0=0, k
     for i, t in enumerate(tok_cols):
         d.tok_cols[i] = int(t)
     d.scale = float(scale)
+    d.causal = 1 if causal else 0
     if temporal:
         fl, fam = 4.0 * nz * hw * heads * frames * frames * 64, "attention_temporal"
     else:
