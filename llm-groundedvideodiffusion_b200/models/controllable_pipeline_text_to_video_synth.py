@@ -37,6 +37,42 @@ class TextToVideoSDPipeline:
         self.guidance_models = None
         self._device = unet.device
 
+    @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path, unet=None, torch_dtype=None, revision=None,
+                        trust_remote_code=None, **kw):
+        """`TextToVideoSDPipeline.from_pretrained(model_key, unet=unet, torch_dtype=torch.float16)` as the runners call
+        it (generation/lvd.py:39-46) for a LOCAL diffusers-format directory: `vae/` and `text_encoder/` load into the
+        native mirrors, `tokenizer/` through transformers' CLIPTokenizer (host code), `scheduler/scheduler_config.json`
+        is kept as `.scheduler.config` so that `DPMSolverMultistepScheduler.from_config(pipe.scheduler.config)` works.
+        Components whose sub-directory is missing are left as None.  No hub access."""
+        import json
+        import os
+        from ..text_encoder import CLIPTextModel
+        from ..vae import AutoencoderKL
+        from .unet_3d_condition import UNet3DConditionModel
+        root = pretrained_model_name_or_path
+        if not os.path.isdir(root):
+            raise OSError(f"{root} is not a local directory: lvd_b200 loads local checkpoints only (no hub access)")
+        if torch_dtype not in (None, torch.float16):
+            raise NotImplementedError("lvd_b200 computes in fp16 (the dtype the reference runners select)")
+        if unet is None:
+            unet = UNet3DConditionModel.from_pretrained(root, subfolder="unet")
+        vae = AutoencoderKL.from_pretrained(root, subfolder="vae") if os.path.isdir(os.path.join(root, "vae")) else None
+        text_encoder = CLIPTextModel.from_pretrained(root, subfolder="text_encoder") \
+            if os.path.isdir(os.path.join(root, "text_encoder")) else None
+        tokenizer = None
+        if os.path.isdir(os.path.join(root, "tokenizer")):
+            from transformers import CLIPTokenizer
+            tokenizer = CLIPTokenizer.from_pretrained(os.path.join(root, "tokenizer"))
+        pipe = cls(vae=vae, text_encoder=text_encoder, tokenizer=tokenizer, unet=unet)
+        sc = os.path.join(root, "scheduler", "scheduler_config.json")
+        if os.path.isfile(sc):
+            class _CheckpointScheduler:  # what the checkpoint ships (DDIM): only its config is consumed
+                config = json.load(open(sc))
+            pipe.checkpoint_scheduler_config = _CheckpointScheduler.config
+            pipe.scheduler = DPMSolverMultistepScheduler.from_config(_CheckpointScheduler.config)
+        return pipe
+
     # ---- small surface the runners touch (generation/lvd.py:39-53)
     def to(self, device):
         d = torch.device(device)

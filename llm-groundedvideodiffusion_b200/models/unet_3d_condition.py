@@ -157,21 +157,9 @@ class UNet3DConditionModel:
     def from_pretrained(cls, pretrained_model_name_or_path, subfolder=None, revision=None, torch_dtype=None, **kw):
         """Loads a LOCAL diffusers-format directory (config.json + diffusion_pytorch_model.{safetensors,bin}); there is
         no network access, so hub names that are not local paths raise."""
-        root = pretrained_model_name_or_path
-        if subfolder:
-            root = os.path.join(root, subfolder)
-        cfg_path = os.path.join(root, "config.json")
-        if not os.path.isfile(cfg_path):
-            raise OSError(f"{cfg_path} not found: lvd_b200 loads local checkpoints only (no hub access)")
-        cfg = json.load(open(cfg_path))
-        allowed = cls.__init__.__code__.co_varnames[1:cls.__init__.__code__.co_argcount]
-        model = cls(**{k: v for k, v in cfg.items() if k in allowed})
-        st = os.path.join(root, "diffusion_pytorch_model.safetensors")
-        if os.path.isfile(st):
-            from safetensors.torch import load_file
-            sd = load_file(st)
-        else:
-            sd = torch.load(os.path.join(root, "diffusion_pytorch_model.bin"), map_location="cpu", weights_only=True)
+        from ..checkpoint import init_kwargs, load_component
+        cfg, sd = load_component(pretrained_model_name_or_path, subfolder)
+        model = cls(**init_kwargs(cls, cfg))
         model.load_state_dict(sd)
         return model
 

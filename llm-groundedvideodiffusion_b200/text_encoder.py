@@ -124,6 +124,15 @@ class CLIPTextModel:
         self._state = None
         self._device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else None
 
+    @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path, subfolder=None, torch_dtype=None, **kw):
+        """Local transformers-format directory (`<path>/<subfolder>/config.json` + weights); no hub access."""
+        from .checkpoint import init_kwargs, load_component
+        cfg, sd = load_component(pretrained_model_name_or_path, subfolder)
+        model = cls(**init_kwargs(cls, cfg))
+        model.load_state_dict({k: v for k, v in sd.items() if k.startswith("text_model.")})
+        return model
+
     @property
     def dtype(self):
         return torch.float16

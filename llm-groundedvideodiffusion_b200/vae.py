@@ -156,6 +156,15 @@ class AutoencoderKL:
         self._device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else None
         self.slice_images = 0  # 0 = decode all images at once; enable_slicing() bounds the activation memory
 
+    @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path, subfolder=None, torch_dtype=None, **kw):
+        """Local diffusers-format directory (`<path>/<subfolder>/config.json` + weights); no hub access."""
+        from .checkpoint import init_kwargs, load_component
+        cfg, sd = load_component(pretrained_model_name_or_path, subfolder)
+        model = cls(**init_kwargs(cls, cfg))
+        model.load_state_dict(sd)
+        return model
+
     @property
     def dtype(self):
         return torch.float16

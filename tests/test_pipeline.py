@@ -78,3 +78,64 @@ def test_pipeline_guided_loop_matches_oracle_loop(cuda):
     print(f"\n[pipeline {steps} steps, {gsteps} guided] final latents engine-vs-oracle: {e:.3e}")
     assert out.shape == (1, 4, F, h, w) and torch.isfinite(out.float()).all()
     assert e <= 2e-2
+
+
+@pytest.mark.gpu
+def test_from_pretrained_local_checkpoint_runs_like_the_runner(cuda, tmp_path):
+    """generation/lvd.py:39-48 against a local diffusers-format directory: UNet3DConditionModel.from_pretrained(
+    model_key, subfolder="unet").to(fp16); TextToVideoSDPipeline.from_pretrained(model_key, unet=unet, torch_dtype=fp16);
+    scheduler = DPMSolverMultistepScheduler.from_config(pipe.scheduler.config); pipe.to("cuda"); enable_vae_slicing();
+    a call with prompt embeddings returns np frames.  Hub names (non-local paths) raise."""
+    import json
+    import os
+
+    from safetensors.torch import save_file
+    from lvd_b200 import synthetic
+    from lvd_b200.models.controllable_pipeline_text_to_video_synth import TextToVideoSDPipeline
+    from lvd_b200.models.unet_3d_condition import UNet3DConditionModel
+    from lvd_b200.scheduler import DPMSolverMultistepScheduler
+    from lvd_b200.text_encoder import clip_param_spec
+    from oracle import weights
+    root = str(tmp_path / "ckpt")
+    ucfg = weights.make_cfg("tiny")
+    os.makedirs(root + "/unet")
+    json.dump({"_class_name": "UNet3DConditionModel", "sample_size": 16, "block_out_channels": ucfg["block_out_channels"],
+               "cross_attention_dim": ucfg["cross_attention_dim"], "attention_head_dim": 64},
+              open(root + "/unet/config.json", "w"))
+    save_file({k: v.half().contiguous() for k, v in weights.random_state_dict(ucfg, seed=51).items()},
+              root + "/unet/diffusion_pytorch_model.safetensors")
+    vcfg = synthetic.VAE_TINY
+    os.makedirs(root + "/vae")
+    json.dump({"_class_name": "AutoencoderKL", "block_out_channels": vcfg["block_out_channels"],
+               "scaling_factor": 0.18215, "sample_size": 256}, open(root + "/vae/config.json", "w"))
+    save_file({k: v.half().contiguous() for k, v in synthetic.random_vae_state_dict(vcfg, seed=52).items()},
+              root + "/vae/diffusion_pytorch_model.safetensors")
+    tcfg = dict(vocab_size=1000, hidden_size=128, intermediate_size=512, num_hidden_layers=2, num_attention_heads=2,
+                max_position_embeddings=77, hidden_act="gelu", eos_token_id=999)
+    os.makedirs(root + "/text_encoder")
+    json.dump(dict(tcfg, architectures=["CLIPTextModel"]), open(root + "/text_encoder/config.json", "w"))
+    g = torch.Generator().manual_seed(53)
+    save_file({k: (0.05 * torch.randn(s, generator=g)).half() for k, s in clip_param_spec(tcfg).items()},
+              root + "/text_encoder/model.safetensors")
+    os.makedirs(root + "/scheduler")
+    json.dump({"_class_name": "DDIMScheduler", "beta_start": 0.00085, "beta_end": 0.012, "beta_schedule": "scaled_linear",
+               "num_train_timesteps": 1000, "steps_offset": 1, "timestep_spacing": "leading",
+               "prediction_type": "epsilon", "clip_sample": False}, open(root + "/scheduler/scheduler_config.json", "w"))
+
+    unet = UNet3DConditionModel.from_pretrained(root, subfolder="unet").to(torch.float16)
+    pipe = TextToVideoSDPipeline.from_pretrained(root, unet=unet, torch_dtype=torch.float16)
+    pipe.scheduler = DPMSolverMultistepScheduler.from_config(pipe.scheduler.config)
+    pipe.to("cuda")
+    pipe.enable_vae_slicing()
+    pipe.guidance_models = None
+    assert pipe.scheduler.config["timestep_spacing"] == "leading" and pipe.scheduler.config["steps_offset"] == 1
+    assert pipe.vae is not None and pipe.text_encoder is not None and pipe.tokenizer is None
+    emb = pipe.text_encoder(torch.randint(1, 998, (2, 77), generator=g))[0]
+    frames = pipe(prompt_embeds=emb[1:], negative_prompt_embeds=emb[:1], height=64, width=128, num_frames=8,
+                  num_inference_steps=2, output_type="np",
+                  generator=torch.Generator().manual_seed(54)).frames
+    assert frames.shape == (1, 8, 64, 128, 3) and (frames >= 0).all() and (frames <= 1).all()
+    with pytest.raises(OSError, match="local"):
+        TextToVideoSDPipeline.from_pretrained("cerspense/zeroscope_v2_576w", unet=unet)
+    with pytest.raises(OSError, match="local"):
+        UNet3DConditionModel.from_pretrained("cerspense/zeroscope_v2_576w", subfolder="unet")
