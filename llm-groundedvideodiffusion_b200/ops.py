@@ -349,8 +349,9 @@ def conv_in(sample, weight, bias, out=None):
     cout = weight.shape[0]
     if out is None:
         out = torch.empty((b * f * h * w_, cout), dtype=torch.float16, device=sample.device)
-    _lib.check(_lib.lib().lvd_conv_in(sample.data_ptr(), weight.data_ptr(), bias.data_ptr(), out.data_ptr(),
-                                      out.stride(0), b, cin, f, h, w_, cout, _stream()), "conv_in")
+    with _Timed("eltwise", 0.0, 2.0 * (sample.numel() + out.shape[0] * cout), "conv_in"):
+        _lib.check(_lib.lib().lvd_conv_in(sample.data_ptr(), weight.data_ptr(), bias.data_ptr(), out.data_ptr(),
+                                          out.stride(0), b, cin, f, h, w_, cout, _stream()), "conv_in")
     return out
 
 
@@ -370,8 +371,9 @@ def conv_out_tc(x, wk_pad, bias_pad, cout, batch, frames, h, w_):
     output channels zero-padded to one 64-wide tile (repack.pad_out_channels); returns (B, cout, F, H, W)."""
     rows = conv2d_3x3(x, batch * frames, h, w_, wk_pad, bias_pad)
     out = torch.empty((batch, cout, frames, h, w_), dtype=torch.float16, device=x.device)
-    _lib.check(_lib.lib().lvd_rows_to_ncfhw(rows.data_ptr(), rows.stride(0), out.data_ptr(), batch, cout, frames,
-                                            h * w_, _stream()), "rows_to_ncfhw")
+    with _Timed("eltwise", 0.0, 4.0 * out.numel(), "rows_to_ncfhw"):
+        _lib.check(_lib.lib().lvd_rows_to_ncfhw(rows.data_ptr(), rows.stride(0), out.data_ptr(), batch, cout, frames,
+                                                h * w_, _stream()), "rows_to_ncfhw")
     return out
 
 
@@ -380,8 +382,9 @@ def upsample2x(x, n_img, h, w_, out=None):
     c = x.shape[1]
     if out is None:
         out = _alloc_out(n_img * 4 * h * w_, c, x)
-    _lib.check(_lib.lib().lvd_upsample2x(x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), n_img, h, w_, c,
-                                         _stream()), "upsample2x")
+    with _Timed("eltwise", 0.0, 2.0 * 5 * x.shape[0] * c, "upsample2x"):
+        _lib.check(_lib.lib().lvd_upsample2x(x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), n_img, h, w_, c,
+                                             _stream()), "upsample2x")
     return out
 
 
@@ -402,8 +405,9 @@ def silu(x):
 def copy_rows(x, out):
     _check_act(x, "x")
     _check_act(out, "out")
-    _lib.check(_lib.lib().lvd_copy_rows(x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), x.shape[0],
-                                        x.shape[1], _stream()), "copy_rows")
+    with _Timed("eltwise", 0.0, 4.0 * x.shape[0] * x.shape[1], "copy_rows"):
+        _lib.check(_lib.lib().lvd_copy_rows(x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), x.shape[0],
+                                            x.shape[1], _stream()), "copy_rows")
     return out
 
 
@@ -606,8 +610,9 @@ def geglu(pre, out=None):
     rows, n2 = pre.shape
     if out is None:
         out = _alloc_out(rows, n2 // 2, pre)
-    _lib.check(_lib.lib().lvd_geglu(pre.data_ptr(), pre.stride(0), out.data_ptr(), out.stride(0), rows, n2 // 2,
-                                    _stream()), "geglu")
+    with _Timed("eltwise", 0.0, 2.0 * rows * (n2 + n2 // 2), "geglu"):
+        _lib.check(_lib.lib().lvd_geglu(pre.data_ptr(), pre.stride(0), out.data_ptr(), out.stride(0), rows, n2 // 2,
+                                        _stream()), "geglu")
     return out
 
 
@@ -617,8 +622,9 @@ def geglu_bwd(pre, dout, out=None):
     rows, n2 = pre.shape
     if out is None:
         out = _alloc_out(rows, n2, pre)
-    _lib.check(_lib.lib().lvd_geglu_bwd(pre.data_ptr(), pre.stride(0), dout.data_ptr(), dout.stride(0), out.data_ptr(),
-                                        out.stride(0), rows, n2 // 2, _stream()), "geglu_bwd")
+    with _Timed("eltwise", 0.0, 2.0 * rows * (2 * n2 + n2 // 2), "geglu_bwd"):
+        _lib.check(_lib.lib().lvd_geglu_bwd(pre.data_ptr(), pre.stride(0), dout.data_ptr(), dout.stride(0), out.data_ptr(),
+                                            out.stride(0), rows, n2 // 2, _stream()), "geglu_bwd")
     return out
 
 
@@ -627,8 +633,9 @@ def add_rows(a, b, out=None):
     _check_act(b, "b")
     if out is None:
         out = _alloc_out(a.shape[0], a.shape[1], a)
-    _lib.check(_lib.lib().lvd_add_rows(a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), out.data_ptr(),
-                                       out.stride(0), a.shape[0], a.shape[1], _stream()), "add_rows")
+    with _Timed("eltwise", 0.0, 6.0 * a.shape[0] * a.shape[1], "add_rows"):
+        _lib.check(_lib.lib().lvd_add_rows(a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), out.data_ptr(),
+                                           out.stride(0), a.shape[0], a.shape[1], _stream()), "add_rows")
     return out
 
 
@@ -636,8 +643,9 @@ def upsample2x_bwd(dy, n_img, h, w_):
     """dy rows of the (2h x 2w_) image -> dx rows of the (h x w_) image."""
     _check_act(dy, "dy")
     out = _alloc_out(n_img * h * w_, dy.shape[1], dy)
-    _lib.check(_lib.lib().lvd_upsample2x_bwd(dy.data_ptr(), dy.stride(0), out.data_ptr(), out.stride(0), n_img, h, w_,
-                                             dy.shape[1], _stream()), "upsample2x_bwd")
+    with _Timed("eltwise", 0.0, 2.0 * 5 * out.shape[0] * dy.shape[1], "upsample2x_bwd"):
+        _lib.check(_lib.lib().lvd_upsample2x_bwd(dy.data_ptr(), dy.stride(0), out.data_ptr(), out.stride(0), n_img, h, w_,
+                                                 dy.shape[1], _stream()), "upsample2x_bwd")
     return out
 
 
