@@ -212,7 +212,9 @@ class UNet3DConditionModel:
         """Eager on the first call of a shape, then captured once and replayed: inputs are copied into the graph's
         static buffers, the output is cloned out of its static buffer."""
         eng = self._engine
-        use_gligen = gligen is not None and eng.fuser_enabled and self._cfg["gated"]
+        if gligen is not None and not self._cfg["gated"]:
+            raise ValueError("`gligen` inputs given but the model has no GLIGEN weights (attention_type='default')")
+        use_gligen = gligen is not None and eng.fuser_enabled
         key = (tuple(sample.shape), tuple(ehs.shape), use_gligen,
                tuple(tuple(v.shape) for v in (gligen["boxes"], gligen["positive_embeddings"], gligen["masks"]))
                if use_gligen else None)
