@@ -251,11 +251,9 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x, long long ld_x, __
 
 __global__ void __launch_bounds__(320, 2) gn_stream_stats_kernel(const __half* __restrict__ x, long long ld,
                                                                   long long rows_per_sample, int C, int G, int chunks,
-                                                                  int T, float* __restrict__ partial, float n,
-                                                                  float eps, float* __restrict__ stats) {
+                                                                  int T, float* __restrict__ partial) {
   extern __shared__ uint4 s_dyn[];
   __shared__ uint64_t s_full[kGnStages];
-  __shared__ int s_last;
   const int vpr = C >> 3;
   const int rpp = blockDim.x / vpr;
   const int v = threadIdx.x % vpr;
@@ -329,52 +327,19 @@ __global__ void __launch_bounds__(320, 2) gn_stream_stats_kernel(const __half* _
     for (int c = 0; c < cpg; ++c) a += col[c];
     partial[((static_cast<long long>(s) * chunks + chunk) * G + g) * 2 + which] = a;
   }
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) s_last = atomicAdd(&g_gn_tickets[s], 1u) == static_cast<unsigned>(chunks - 1);
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  float* s_a = s_part;
-  float* s_b = s_part + blockDim.x;
-  const int nparts = blockDim.x / G;
-  {
-    const int g = threadIdx.x % G, part = threadIdx.x / G;
-    float a = 0.f, b = 0.f;
-    if (part < nparts)
-      for (int k = part; k < chunks; k += nparts) {
-        const float* p = partial + ((static_cast<long long>(s) * chunks + k) * G + g) * 2;
-        a += __ldcg(p);
-        b += __ldcg(p + 1);
-      }
-    s_a[threadIdx.x] = a;
-    s_b[threadIdx.x] = b;
-  }
-  __syncthreads();
-  if (threadIdx.x < G) {
-    float a = 0.f, b = 0.f;
-    for (int q = 0; q < nparts; ++q) {
-      a += s_a[q * G + threadIdx.x];
-      b += s_b[q * G + threadIdx.x];
-    }
-    const float mean = a / n;
-    float var = b / n - mean * mean;
-    var = var > 0.f ? var : 0.f;
-    stats[(static_cast<long long>(s) * G + threadIdx.x) * 2] = mean;
-    stats[(static_cast<long long>(s) * G + threadIdx.x) * 2 + 1] = rsqrtf(var + eps);
-  }
-  if (threadIdx.x == 0) g_gn_tickets[s] = 0u;
 }
 
 __global__ void __launch_bounds__(320, 2) gn_stream_apply_kernel(const __half* __restrict__ x, long long ld_x,
                                                                   __half* __restrict__ y, long long ld_y,
                                                                   long long rows_per_sample, int C, int G, int chunks,
-                                                                  int T, const float* __restrict__ stats,
+                                                                  int T, const float* __restrict__ partial, float n,
+                                                                  float eps, float* __restrict__ stats,
                                                                   const __half* __restrict__ gamma,
                                                                   const __half* __restrict__ beta, int silu) {
   extern __shared__ uint4 s_dyn[];
   __shared__ uint64_t s_full[kGnStages];
   __shared__ float s_mean[64], s_rstd[64];
+  __shared__ float s_a[320], s_b[320];
   const int vpr = C >> 3;
   const int rpp = blockDim.x / vpr;
   const int v = threadIdx.x % vpr;
@@ -398,13 +363,44 @@ __global__ void __launch_bounds__(320, 2) gn_stream_apply_kernel(const __half* _
     for (int i = 0; i < kGnStages; ++i) mbar_init(&s_full[i], 1);
     fence_barrier_init();
   }
-  for (int g = threadIdx.x; g < G; g += blockDim.x) {
-    s_mean[g] = stats[(static_cast<long long>(s) * G + g) * 2];
-    s_rstd[g] = stats[(static_cast<long long>(s) * G + g) * 2 + 1];
-  }
   __syncthreads();
   if (threadIdx.x < 32)
     for (int it = 0; it < kGnStages && it < st.nit; ++it) st.issue(it);
+  // Every CTA folds the sample's chunk partials itself (fixed order: deterministic, identical in all CTAs) while its
+  // first stages are in flight -- a finalising "last CTA" in the statistics pass left the GPU idle for its whole tail.
+  {
+    const int nparts = blockDim.x / G;
+    const int g = threadIdx.x % G, part = threadIdx.x / G;
+    float a = 0.f, b = 0.f;
+    if (part < nparts)
+      for (int k = part; k < chunks; k += nparts) {
+        const float* p = partial + ((static_cast<long long>(s) * chunks + k) * G + g) * 2;
+        a += __ldcg(p);
+        b += __ldcg(p + 1);
+      }
+    s_a[threadIdx.x] = a;
+    s_b[threadIdx.x] = b;
+    __syncthreads();
+    if (threadIdx.x < G) {
+      a = 0.f;
+      b = 0.f;
+      for (int q = 0; q < nparts; ++q) {
+        a += s_a[q * G + threadIdx.x];
+        b += s_b[q * G + threadIdx.x];
+      }
+      const float mean = a / n;
+      float var = b / n - mean * mean;
+      var = var > 0.f ? var : 0.f;
+      const float rstd = rsqrtf(var + eps);
+      s_mean[threadIdx.x] = mean;
+      s_rstd[threadIdx.x] = rstd;
+      if (chunk == 0) {  // kept for lvd_groupnorm_bwd (stats_out)
+        stats[(static_cast<long long>(s) * G + threadIdx.x) * 2] = mean;
+        stats[(static_cast<long long>(s) * G + threadIdx.x) * 2 + 1] = rstd;
+      }
+    }
+    __syncthreads();
+  }
   const int cpg = C / G;
   float sc[8], sh[8];
   if (rsub < rpp) {
@@ -615,17 +611,19 @@ extern "C" int lvd_groupnorm(const void* x, int64_t ld_x, void* y, int64_t ld_y,
     static bool attr2 = false;
     if (!attr2) {
       LVD_CHECK_CUDA(cudaFuncSetAttribute(gn_stream_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
-      LVD_CHECK_CUDA(cudaFuncSetAttribute(gn_stream_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
+      LVD_CHECK_CUDA(cudaFuncSetAttribute(gn_stream_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
       attr2 = true;
     }
-    if (threads <= 320 && ring_bytes + scratch <= 225 * 1024) {
+    if (threads <= 320 && ring_bytes + scratch <= 220 * 1024) {
     dim3 sgrid(static_cast<unsigned>(schunks), static_cast<unsigned>(samples));
     gn_stream_stats_kernel<<<sgrid, threads, ring_bytes + scratch, st>>>(
         static_cast<const __half*>(x), ld_x, rows_per_sample, channels, groups, static_cast<int>(schunks), T,
-        static_cast<float*>(workspace), static_cast<float>(rows_per_sample) * (channels / groups), eps, stats);
+        static_cast<float*>(workspace));
     gn_stream_apply_kernel<<<sgrid, threads, ring_bytes, st>>>(
         static_cast<const __half*>(x), ld_x, static_cast<__half*>(y), ld_y, rows_per_sample, channels, groups,
-        static_cast<int>(schunks), T, stats, static_cast<const __half*>(gamma), static_cast<const __half*>(beta), silu);
+        static_cast<int>(schunks), T, static_cast<const float*>(workspace),
+        static_cast<float>(rows_per_sample) * (channels / groups), eps, stats, static_cast<const __half*>(gamma),
+        static_cast<const __half*>(beta), silu);
     } else {  // very wide rows: register-staged passes
       dim3 grid(static_cast<unsigned>(chunks), static_cast<unsigned>(samples));
       const size_t smem_stats = (static_cast<size_t>(rpp_) + 1) * 2 * channels * sizeof(float);
