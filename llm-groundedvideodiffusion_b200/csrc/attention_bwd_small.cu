@@ -5,6 +5,7 @@
 //     columns: this is where utils/guidance.py's loss enters the backward pass.
 // Both recompute the probabilities from Q, K (nothing but Q/K/V/O is kept from the forward).  fp32 math.
 #include <atomic>
+#include <cstdlib>
 
 #include "../../include/lvd_b200.h"
 #include "host_util.h"
@@ -12,6 +13,10 @@
 
 namespace lvd {
 extern std::atomic<long long> g_launches;
+int launch_cross_attn_bwd_mma(const void* q, long long ld_q, const void* kv, long long ld_kv, int k_col0, int v_col0,
+                              const void* d_o, long long ld_do, const void* dp_tok, const int* slot_col, int n_slots,
+                              void* dq, long long ld_dq, long long s_q, int s_k, int heads, int nz, int kv_z_div,
+                              float scale, cudaStream_t stream);  // attention_temporal.cu
 
 constexpr int kPad = 66;  // padded row length (halves) of 64-wide tiles in shared memory: conflict-free column reads
 
@@ -320,7 +325,14 @@ extern "C" int lvd_cross_attn_bwd(const void* q, int64_t ld_q, int64_t width_q, 
   LVD_REQUIRE(s_k >= 1 && s_k <= 128 && n_slots >= 0 && n_slots <= 16 && (n_slots == 0 || (dp_tok && slot_col_host)),
               "lvd_cross_attn_bwd: s_k=%d n_slots=%d unsupported", s_k, n_slots);
   if (width_q > 0 && width_kv > 0) {
-    // tensor-core path (attn_bwd_small_kernel, mode 0)
+    static const bool force_tile = getenv("LVD_CROSS_BWD_TILE") != nullptr;  // A/B switch for tools/
+    if (!force_tile) {  // warp-level mma.sync kernel (attention_temporal.cu)
+      const int r = launch_cross_attn_bwd_mma(q, ld_q, kv, ld_kv, k_col0, v_col0, d_o, ld_do, dp_tok, slot_col_host,
+                                              n_slots, dq, ld_dq, s_q, s_k, heads, nz, kv_z_div, scale,
+                                              static_cast<cudaStream_t>(stream));
+      if (r != 1) return r;
+    }
+    // tcgen05 tile path (attn_bwd_small_kernel, mode 0)
     return launch_attn_bwd_small(0, q, ld_q, width_q, static_cast<long long>(nz) * s_q, kv, ld_kv, width_kv,
                                  static_cast<long long>((nz + kv_z_div - 1) / kv_z_div) * s_k, d_o, ld_do,
                                  static_cast<long long>(heads) * 64, dp_tok, slot_col_host, n_slots, dq, ld_dq, 0, k_col0,

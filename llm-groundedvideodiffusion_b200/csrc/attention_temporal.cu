@@ -348,6 +348,222 @@ int launch_cross_attn_mma(const lvd_attn_desc* d, cudaStream_t stream) {
   return LVD_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ cross-attention dQ
+// Adjoint of the map-less cross-attention above w.r.t. Q only (K, V come from the text encoder, no function of the
+// latents), with the box-energy gradient dE/dP added on the object-token columns -- the place where utils/guidance.py's
+// loss enters the backward pass.  One warp per (16 query rows, head), everything from registers:
+//   S = Q K^T and dP = dO V^T share one fragment scheme (V's rows play K's role), P = fp16 softmax as in the forward,
+//   dS = P * (dP - rowsum(P * dP)), dQ = scale * dS K with K in the role V has in P V.
+struct CrossBwdMmaArgs {
+  const __half* q;
+  const __half* kv;
+  const __half* d_o;
+  const __half* dp_tok;  // [n_slots][nz][heads][s_q]
+  __half* dq;
+  long long ld_q, ld_kv, ld_do, ld_dq;
+  long long n_warps;
+  int k_col0, v_col0;
+  int s_q, s_k, heads, nz, q_tiles, kv_z_div, n_slots;
+  int slot_col[16];
+  float scale, scale_log2;
+};
+
+template <int NT, int KS>
+__global__ void __launch_bounds__(128) cross_attn_bwd_mma_kernel(const CrossBwdMmaArgs a) {
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const long long w = static_cast<long long>(blockIdx.x) * 4 + (threadIdx.x >> 5);
+  if (w >= a.n_warps) return;
+  const int h = static_cast<int>(w % a.heads);
+  const long long zq = w / a.heads;
+  const int qt = static_cast<int>(zq % a.q_tiles);
+  const long long z = zq / a.q_tiles;
+  const long long zk = z / a.kv_z_div;
+  const int r0 = qt * 16;
+  const __half* qb = a.q + (z * a.s_q) * a.ld_q + h * 64 + t * 8;
+  const __half* db = a.d_o + (z * a.s_q) * a.ld_do + h * 64 + t * 8;
+  const __half* kb = a.kv + (zk * a.s_k) * a.ld_kv + a.k_col0 + h * 64;
+  const __half* vb = a.kv + (zk * a.s_k) * a.ld_kv + a.v_col0 + h * 64;
+  const uint4 zero = make_uint4(0, 0, 0, 0);
+  uint4 qf[2][2], df[2][2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int r = r0 + i * 8 + g;
+    qf[i][0] = r < a.s_q ? ldg16(qb + r * a.ld_q) : zero;
+    qf[i][1] = r < a.s_q ? ldg16(qb + r * a.ld_q + 32) : zero;
+    df[i][0] = r < a.s_q ? ldg16(db + r * a.ld_do) : zero;
+    df[i][1] = r < a.s_q ? ldg16(db + r * a.ld_do + 32) : zero;
+  }
+  float s[NT][4], dp[NT][4];
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) {
+    const int n = nt * 8 + g;
+    const bool ok = n < a.s_k;
+    const uint4 k0 = ok ? ldg16(kb + n * a.ld_kv + t * 8) : zero, k1 = ok ? ldg16(kb + n * a.ld_kv + t * 8 + 32) : zero;
+    const uint4 v0 = ok ? ldg16(vb + n * a.ld_kv + t * 8) : zero, v1 = ok ? ldg16(vb + n * a.ld_kv + t * 8 + 32) : zero;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) s[nt][i] = dp[nt][i] = 0.f;
+#pragma unroll
+    for (int st = 0; st < 4; ++st) {
+      const int w0 = (st & 1) * 2, pc = st >> 1;
+      const uint4& kq = pc ? k1 : k0;
+      const uint4& vq = pc ? v1 : v0;
+      mma16816(s[nt], word_of(qf[0][pc], w0), word_of(qf[1][pc], w0), word_of(qf[0][pc], w0 + 1),
+               word_of(qf[1][pc], w0 + 1), word_of(kq, w0), word_of(kq, w0 + 1));
+      mma16816(dp[nt], word_of(df[0][pc], w0), word_of(df[1][pc], w0), word_of(df[0][pc], w0 + 1),
+               word_of(df[1][pc], w0 + 1), word_of(vq, w0), word_of(vq, w0 + 1));
+    }
+  }
+  // dE/dP of the guided token columns (this lane owns columns 8 nt + 2t, + 1 of rows g and g + 8); the register
+  // arrays keep static indices: the slot list is searched per owned column
+  if (a.n_slots > 0) {
+    const int ra = r0 + g, rb = r0 + 8 + g;
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int c = nt * 8 + 2 * t + e;
+        float va = 0.f, vb_ = 0.f;
+        for (int sl = 0; sl < a.n_slots; ++sl) {
+          if (a.slot_col[sl] == c) {
+            const __half* src = a.dp_tok + ((static_cast<long long>(sl) * a.nz + z) * a.heads + h) * a.s_q;
+            if (ra < a.s_q) va += __half2float(src[ra]);
+            if (rb < a.s_q) vb_ += __half2float(src[rb]);
+          }
+        }
+        dp[nt][e] += va;
+        dp[nt][2 + e] += vb_;
+      }
+    }
+  }
+  uint32_t ds[NT][2];
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    float mx = -3.0e38f;
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      const int c = nt * 8 + 2 * t;
+      if (c >= a.s_k) s[nt][2 * half] = -INFINITY;
+      if (c + 1 >= a.s_k) s[nt][2 * half + 1] = -INFINITY;
+      mx = fmaxf(mx, fmaxf(s[nt][2 * half], s[nt][2 * half + 1]));
+    }
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+    float sum = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      const float e0 = fast_exp2((s[nt][2 * half] - mx) * a.scale_log2);
+      const float e1 = fast_exp2((s[nt][2 * half + 1] - mx) * a.scale_log2);
+      s[nt][2 * half] = e0;
+      s[nt][2 * half + 1] = e1;
+      sum += e0 + e1;
+    }
+    sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+    sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+    const float inv = 1.0f / sum;
+    float dsum = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {  // the probabilities that multiplied V in the forward are the fp16-rounded ones
+      s[nt][2 * half] = round_h(s[nt][2 * half] * inv);
+      s[nt][2 * half + 1] = round_h(s[nt][2 * half + 1] * inv);
+      dsum += s[nt][2 * half] * dp[nt][2 * half] + s[nt][2 * half + 1] * dp[nt][2 * half + 1];
+    }
+    dsum += __shfl_xor_sync(0xffffffffu, dsum, 1);
+    dsum += __shfl_xor_sync(0xffffffffu, dsum, 2);
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt)
+      ds[nt][half] = pack_h2(s[nt][2 * half] * (dp[nt][2 * half] - dsum),
+                             s[nt][2 * half + 1] * (dp[nt][2 * half + 1] - dsum));
+  }
+  // dQ = scale * dS K  (K rows in the role of V rows in P V)
+  float o[8][4];
+#pragma unroll
+  for (int nv = 0; nv < 8; ++nv)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o[nv][i] = 0.f;
+  const int vchunk = (g >> 1) + 4 * (g & 1);
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks) {
+    uint4 kf[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int j = ks * 16 + 2 * t + (i & 1) + (i >> 1) * 8;
+      kf[i] = j < a.s_k ? ldg16(kb + j * a.ld_kv + vchunk * 8) : zero;
+    }
+    const uint32_t a0 = ds[2 * ks][0], a1 = ds[2 * ks][1];
+    const uint32_t a2 = 2 * ks + 1 < NT ? ds[2 * ks + 1 < NT ? 2 * ks + 1 : 0][0] : 0u;
+    const uint32_t a3 = 2 * ks + 1 < NT ? ds[2 * ks + 1 < NT ? 2 * ks + 1 : 0][1] : 0u;
+#pragma unroll
+    for (int nv = 0; nv < 8; ++nv) {
+      const uint32_t sel = (nv & 1) ? 0x7632u : 0x5410u;
+      const uint32_t b0 = __byte_perm(word_of(kf[0], nv >> 1), word_of(kf[1], nv >> 1), sel);
+      const uint32_t b1 = __byte_perm(word_of(kf[2], nv >> 1), word_of(kf[3], nv >> 1), sel);
+      mma16816(o[nv], a0, a1, a2, a3, b0, b1);
+    }
+  }
+  __half* ob = a.dq + (z * a.s_q) * a.ld_dq + h * 64 + t * 8;
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const int r = r0 + half * 8 + g;
+    if (r < a.s_q) {
+      uint4 u0, u1;
+      u0.x = pack_h2(o[0][2 * half] * a.scale, o[1][2 * half] * a.scale);
+      u0.y = pack_h2(o[2][2 * half] * a.scale, o[3][2 * half] * a.scale);
+      u0.z = pack_h2(o[4][2 * half] * a.scale, o[5][2 * half] * a.scale);
+      u0.w = pack_h2(o[6][2 * half] * a.scale, o[7][2 * half] * a.scale);
+      u1.x = pack_h2(o[0][2 * half + 1] * a.scale, o[1][2 * half + 1] * a.scale);
+      u1.y = pack_h2(o[2][2 * half + 1] * a.scale, o[3][2 * half + 1] * a.scale);
+      u1.z = pack_h2(o[4][2 * half + 1] * a.scale, o[5][2 * half + 1] * a.scale);
+      u1.w = pack_h2(o[6][2 * half + 1] * a.scale, o[7][2 * half + 1] * a.scale);
+      *reinterpret_cast<uint4*>(ob + r * a.ld_dq) = u0;
+      *reinterpret_cast<uint4*>(ob + r * a.ld_dq + 32) = u1;
+    }
+  }
+}
+
+int launch_cross_attn_bwd_mma(const void* q, long long ld_q, const void* kv, long long ld_kv, int k_col0, int v_col0,
+                              const void* d_o, long long ld_do, const void* dp_tok, const int* slot_col, int n_slots,
+                              void* dq, long long ld_dq, long long s_q, int s_k, int heads, int nz, int kv_z_div,
+                              float scale, cudaStream_t stream) {
+  if (s_k < 1 || s_k > 128 || n_slots > 16) return 1;
+  CrossBwdMmaArgs a;
+  a.q = static_cast<const __half*>(q);
+  a.kv = static_cast<const __half*>(kv);
+  a.d_o = static_cast<const __half*>(d_o);
+  a.dp_tok = static_cast<const __half*>(dp_tok);
+  a.dq = static_cast<__half*>(dq);
+  a.ld_q = ld_q;
+  a.ld_kv = ld_kv;
+  a.ld_do = ld_do;
+  a.ld_dq = ld_dq;
+  a.k_col0 = k_col0;
+  a.v_col0 = v_col0;
+  a.s_q = static_cast<int>(s_q);
+  a.s_k = s_k;
+  a.heads = heads;
+  a.nz = nz;
+  a.q_tiles = (a.s_q + 15) / 16;
+  a.kv_z_div = kv_z_div;
+  a.n_slots = dp_tok ? n_slots : 0;
+  for (int i = 0; i < 16; ++i) a.slot_col[i] = i < a.n_slots ? slot_col[i] : -1;
+  a.scale = scale;
+  a.scale_log2 = scale * 1.4426950408889634f;
+  a.n_warps = static_cast<long long>(nz) * a.q_tiles * heads;
+  const long long blocks = (a.n_warps + 3) / 4;
+  LVD_REQUIRE(blocks < (1ll << 31), "lvd_cross_attn_bwd: too many query tiles");
+  const unsigned nb = static_cast<unsigned>(blocks);
+  const int nt = (s_k + 7) / 8;
+  if (nt <= 4) {
+    cross_attn_bwd_mma_kernel<4, 2><<<nb, 128, 0, stream>>>(a);
+  } else if (nt <= 10) {
+    cross_attn_bwd_mma_kernel<10, 5><<<nb, 128, 0, stream>>>(a);
+  } else {
+    cross_attn_bwd_mma_kernel<16, 8><<<nb, 128, 0, stream>>>(a);
+  }
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  LVD_CHECK_CUDA(cudaGetLastError());
+  return LVD_OK;
+}
+
 // Packed-sequence temporal attention for frames in {8, 16, 24, 32}; returns 1 when the shape is not covered (the caller
 // then uses the tcgen05 tile kernel), LVD_OK after a launch.
 int launch_temporal_attn_mma(const lvd_attn_desc* d, cudaStream_t stream) {
