@@ -96,7 +96,11 @@ int lvd_gemm(const lvd_gemm_desc* d, void* stream);
  *   (transformer_temporal.py:142-156 permutes instead).  Q, K, V in one buffer.
  * mode 2 (temporal, packed): rows are ((z*hw + p)*frames + f), i.e. every `frames` consecutive rows are one
  *   sequence (the QKV projection writes this order through lvd_gemm's output row mapping, the output projection
- *   reads it back); frames % 8 == 0.  This is the fast path: contiguous TMA boxes, per-row window softmax.
+ *   reads it back); frames in {8, 16, 24, 32}.  This is the fast path: one warp per (sequence, head), every operand
+ *   straight from registers into mma.sync (attention_temporal.cu).
+ * Kernel selection inside mode 0: s_k <= 128 with no map / lse output (the 77 text tokens, the 45-pixel mid block, the
+ *   CLIP text encoder's causal self-attention) runs the same warp-level scheme; everything else (spatial
+ *   self-attention over thousands of keys, map outputs, lse) runs the tcgen05 tile kernel (attention.cu).
  * lse (optional, fp32 [nz, heads, rows]) receives log2-domain logsumexp of every query row for the backward kernels.
  * Output row order == Q row order; column o_col0 + head*64.
  * Optional (s_k <= 128 only): p_full [nz, heads, s_q, s_k] fp16 = the reference's saved attention map
