@@ -158,6 +158,11 @@ int lvd_layernorm(const void* x, int64_t ld_x, void* y, int64_t ld_y, int64_t ro
  * ---------------------------------------------------------------------------------------------------------- */
 int lvd_conv_in(const void* sample, const void* weight, const void* bias, void* out, int64_t ld_out, int32_t batch,
                 int32_t cin, int32_t frames, int32_t height, int32_t width, int32_t cout, void* stream);
+/* lvd_im2col_small: sample (B, cin <= 7, F, H, W) -> rows [B*F*H*W, 64] = the 3x3 / pad 1 patches, column ci*9 + ky*3 + kx
+ *               (zero padded): the wide path of conv_in, which then is one K = 64 lvd_gemm against the OIHW weight
+ *               flattened and zero-padded to 64 columns. */
+int lvd_im2col_small(const void* sample, void* out, int32_t batch, int32_t cin, int32_t frames, int32_t height,
+                     int32_t width, void* stream);
 int lvd_conv_out(const void* x, int64_t ld_x, const void* weight_krsc, const void* bias, void* out, int32_t batch,
                  int32_t cin, int32_t frames, int32_t height, int32_t width, int32_t cout, void* stream);
 int lvd_rows_to_ncfhw(const void* rows, int64_t ld, void* out, int32_t batch, int32_t cout, int32_t frames, int64_t hw,

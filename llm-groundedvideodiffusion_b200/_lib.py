@@ -133,6 +133,7 @@ def _declare(l):
     l.lvd_silu.argtypes = [vp, vp, i64, vp]
     l.lvd_softmax_rows.argtypes = [vp, i64, i64, i32, ctypes.c_float, vp]
     l.lvd_frames_postprocess.argtypes = [vp, vp, i64, i32, i64, vp]
+    l.lvd_im2col_small.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp]
     l.lvd_embed_tokens.argtypes = [vp, vp, vp, vp, i64, i32, i32, i32, vp]
     l.lvd_pointwise_small.argtypes = [vp, vp, vp, vp, i32, i32, i32, i64, vp]
     l.lvd_copy_rows.argtypes = [vp, i64, vp, i64, i64, i32, vp]
@@ -180,6 +181,7 @@ EXPORTS = [
     "lvd_softmax_rows",
     "lvd_pointwise_small",
     "lvd_embed_tokens",
+    "lvd_im2col_small",
     "lvd_frames_postprocess",
     "lvd_copy_rows",
     "lvd_rows_to_ncfhw",

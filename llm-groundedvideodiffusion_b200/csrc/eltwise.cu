@@ -222,6 +222,36 @@ __global__ void __launch_bounds__(kSmxThreads) softmax_rows_kernel(__half* __res
   }
 }
 
+// im2col for the 4-channel conv_in (3x3, pad 1): sample (B, Cin<=7, F, H, W) -> rows [(b*F+f)*H*W + p][64] with column
+// ci*9 + ky*3 + kx (the OIHW weight flattened), zero beyond Cin*9 and outside the image.  The conv itself then runs on the
+// tensor-core kernel as a K = 64 GEMM; one thread per (pixel, 8-column vector).
+__global__ void im2col_small_kernel(const __half* __restrict__ x, __half* __restrict__ out, int B, int Cin, int F, int H,
+                                    int W) {
+  const long long total = static_cast<long long>(B) * F * H * W * 8;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int v = static_cast<int>(idx & 7);
+    long long p = idx >> 3;
+    const long long row = p;
+    const int xx = static_cast<int>(p % W);
+    p /= W;
+    const int yy = static_cast<int>(p % H);
+    p /= H;
+    const int f = static_cast<int>(p % F);
+    const int b = static_cast<int>(p / F);
+    __align__(16) __half vals[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int col = v * 8 + i;
+      const int ci = col / 9, tap = col % 9;
+      const int iy = yy + tap / 3 - 1, ix = xx + tap % 3 - 1;
+      const bool ok = ci < Cin && iy >= 0 && iy < H && ix >= 0 && ix < W;
+      vals[i] = ok ? x[(((static_cast<long long>(b) * Cin + ci) * F + f) * H + iy) * W + ix] : __float2half(0.f);
+    }
+    *reinterpret_cast<uint4*>(out + row * 64 + v * 8) = *reinterpret_cast<const uint4*>(vals);
+  }
+}
+
 // CLIPTextEmbeddings: token embedding gather + position embedding (fp16 add), one 16-byte vector per thread.
 __global__ void embed_tokens_kernel(const long long* __restrict__ ids, const __half* __restrict__ tok,
                                     const __half* __restrict__ pos, __half* __restrict__ out, long long n_tokens, int seq,
@@ -415,6 +445,18 @@ extern "C" int lvd_frames_postprocess(const void* x, void* out, int64_t n, int32
   LVD_REQUIRE(x && out && n >= 1 && channels >= 1 && channels <= 8 && hw >= 1, "lvd_frames_postprocess: bad arguments");
   frames_postprocess_kernel<<<grid_for(n * hw, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __half*>(x), static_cast<float*>(out), n, channels, hw);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  LVD_CHECK_CUDA(cudaGetLastError());
+  return LVD_OK;
+}
+
+extern "C" int lvd_im2col_small(const void* sample, void* out, int32_t batch, int32_t cin, int32_t frames, int32_t height,
+                                int32_t width, void* stream) {
+  LVD_REQUIRE(sample && out && batch >= 1 && cin >= 1 && cin <= 7 && frames >= 1 && height >= 1 && width >= 1,
+              "lvd_im2col_small: bad arguments (cin * 9 must fit 64 columns)");
+  const long long total = static_cast<long long>(batch) * frames * height * width * 8;
+  im2col_small_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __half*>(sample), static_cast<__half*>(out), batch, cin, frames, height, width);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   LVD_CHECK_CUDA(cudaGetLastError());
   return LVD_OK;

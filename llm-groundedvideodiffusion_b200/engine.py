@@ -108,7 +108,8 @@ class UNetEngine:
 
         boc = list(cfg["block_out_channels"])
         nb = len(boc)
-        w["conv_in"] = LayerWeights(w=g("conv_in.weight"), b=g("conv_in.bias"))
+        w["conv_in"] = LayerWeights(w=g("conv_in.weight"), b=g("conv_in.bias"),
+                                    w_pad=repack.conv_in_weight_padded(g("conv_in.weight")))
         w["time1"] = lin("time_embedding.linear_1")
         w["time2"] = lin("time_embedding.linear_2")
         w["transformer_in"] = transformer("transformer_in", cross=False)
@@ -279,7 +280,7 @@ class UNetEngine:
         temb = ops.linear(temb, w["time2"].w, w["time2"].b)
         temb_all = ops.linear(ops.silu(temb), w["temb_all"].w, w["temb_all"].b)
 
-        x = ops.conv_in(sample, w["conv_in"].w, w["conv_in"].b)
+        x = ops.conv_in_tc(sample, w["conv_in"].w_pad, w["conv_in"].b)
         hw = h * w_
         x = self._transformer(w["transformer_in"], x, spatial=False, n_img=n_img, hw=hw, batch=b, frames=frames)
         objs = None

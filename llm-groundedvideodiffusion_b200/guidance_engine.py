@@ -275,7 +275,7 @@ class GuidanceGraph:
         temb_all = ops.linear(ops.silu(temb), w["temb_all"].w, w["temb_all"].b)
 
         tape = []  # (kind, weights, ctx, extra)
-        x = ops.conv_in(latents, w["conv_in"].w, w["conv_in"].b)
+        x = ops.conv_in_tc(latents, w["conv_in"].w_pad, w["conv_in"].b)
         hw = h * w_
         x, c = self._transformer_fwd(w["transformer_in"], x, spatial=False, n_img=n_img, hw=hw, batch=1,
                                      frames=frames)

@@ -355,6 +355,18 @@ def conv_in(sample, weight, bias, out=None):
     return out
 
 
+def conv_in_tc(sample, w_pad, bias, out=None):
+    """conv_in on the tensor-core kernel: im2col of the <= 7-channel sample into 64 columns, then one K = 64 GEMM against
+    `w_pad` [Cout, 64] (repack.conv_in_weight_padded).  Same result layout as conv_in."""
+    b, cin, f, h, w_ = sample.shape
+    assert sample.is_contiguous() and sample.dtype == torch.float16 and cin * 9 <= 64
+    col = torch.empty((b * f * h * w_, 64), dtype=torch.float16, device=sample.device)
+    with _Timed("eltwise", 0.0, 2.0 * (sample.numel() + col.numel()), "im2col_small"):
+        _lib.check(_lib.lib().lvd_im2col_small(sample.data_ptr(), col.data_ptr(), b, cin, f, h, w_, _stream()),
+                   "im2col_small")
+    return linear(col, w_pad, bias, out=out)
+
+
 def conv_out(x, wk, bias, batch, frames, h, w_):
     """rows [B*F*H*W, Cin] -> (B, Cout, F, H, W); wk [Cout, 9*Cin] (K = ky,kx,ci)."""
     _check_act(x, "x")

@@ -57,3 +57,13 @@ def pad_out_channels(wk, bias, n=64):
     bp = torch.zeros((n,), dtype=bias.dtype, device=bias.device)
     bp[:co] = bias
     return wp, bp
+
+
+def conv_in_weight_padded(w):
+    """conv_in weight (Cout, Cin <= 7, 3, 3) -> [Cout, 64]: OIHW flattened (column ci*9 + ky*3 + kx), zero-padded to the
+    64-deep contraction block of lvd_gemm (ops.conv_in_tc)."""
+    co = w.shape[0]
+    flat = w.reshape(co, -1)
+    wp = torch.zeros((co, 64), dtype=w.dtype, device=w.device)
+    wp[:, :flat.shape[1]] = flat
+    return wp

@@ -55,7 +55,8 @@ class VAEDecoderEngine:
         w = LayerWeights()
         pq = g("post_quant_conv.weight")
         w["post_quant"] = LayerWeights(w=pq.reshape(pq.shape[0], pq.shape[1]).contiguous(), b=g("post_quant_conv.bias"))
-        w["conv_in"] = LayerWeights(w=g("decoder.conv_in.weight"), b=g("decoder.conv_in.bias"))
+        w["conv_in"] = LayerWeights(w_pad=repack.conv_in_weight_padded(g("decoder.conv_in.weight")),
+                                    b=g("decoder.conv_in.bias"))
         w["mid0"] = resnet("decoder.mid_block.resnets.0")
         w["mid1"] = resnet("decoder.mid_block.resnets.1")
         a = "decoder.mid_block.attentions.0"
@@ -116,7 +117,7 @@ class VAEDecoderEngine:
         z1 = torch.empty_like(z)
         _lib.check(_lib.lib().lvd_pointwise_small(z.data_ptr(), w.post_quant.w.data_ptr(), w.post_quant.b.data_ptr(),
                                                   z1.data_ptr(), n, lc, lc, h * w_, ops._stream()), "pointwise_small")
-        x = ops.conv_in(z1.view(n, lc, 1, h, w_), w.conv_in.w, w.conv_in.b)
+        x = ops.conv_in_tc(z1.view(n, lc, 1, h, w_), w.conv_in.w_pad, w.conv_in.b)
         x = self._resnet(w.mid0, x, n, h, w_)
         x = self._attention(w.attn, x, n, h * w_)
         x = self._resnet(w.mid1, x, n, h, w_)

@@ -63,6 +63,8 @@ def test_conv_in_out(cuda):
     x4 = x.permute(0, 2, 1, 3, 4).reshape(b * f, 4, h, w).float()
     ref = F.conv2d(x4, wi.float(), bi.float(), padding=1).permute(0, 2, 3, 1).reshape(b * f * h * w, 320)
     assert rel_err(rows, ref) < TOL
+    rows_tc = ops.conv_in_tc(x, repack.conv_in_weight_padded(wi), bi)  # im2col + K = 64 GEMM path
+    assert rel_err(rows_tc, ref) < TOL
     wo = _rand((4, 320, 3, 3), cuda, (9 * 320) ** -0.5, seed=13)
     bo = _rand((4,), cuda, seed=14)
     y = ops.conv_out(rows, repack.conv_weight_krsc(wo), bo, b, f, h, w)
