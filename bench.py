@@ -268,7 +268,6 @@ def run_gpu(args):
     import __graft_entry__ as ge
     ge.build()
     from lvd_b200 import _lib, ops, synthetic
-    from lvd_b200.models import pipelines
     from lvd_b200.models.pipelines import latent_backward_guidance
     from lvd_b200.models.unet_3d_condition import UNet3DConditionModel
     from lvd_b200.scheduler import DPMSolverMultistepScheduler

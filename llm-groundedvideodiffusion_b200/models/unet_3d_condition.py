@@ -15,8 +15,6 @@ Kept from the reference (file:line are into /root/reference/models/unet_3d_condi
 Not implemented (raise, never fall back): attention_mask, class_labels, timestep_cond, additional residuals,
 attn_process_fn, offload_cross_attn_to_cpu, return_cond_ca_only, return_token_ca_only.
 """
-import json
-import os
 from dataclasses import dataclass
 
 import torch
