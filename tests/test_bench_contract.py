@@ -1,0 +1,51 @@
+"""bench.py host-side contract (no GPU): defaults, workload table, and the keys of the reference-arm JSON line
+(the CPU step itself is stubbed out here; it is exercised for real by `bench.py --impl reference`)."""
+import io
+import json
+import os
+import sys
+from contextlib import redirect_stdout
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def test_defaults_and_workloads(monkeypatch):
+    import bench
+    monkeypatch.setattr(sys, "argv", ["bench.py"])
+    a = bench.parse()
+    assert (a.gpus, a.steps, a.warmup, a.impl, a.workload) == (1, 10, 3, "lvd_b200", "lvd_zeroscope")
+    assert set(bench.WORKLOADS) == {"lvd_zeroscope", "lvd_gligen_zeroscope", "lvd_gligen_zeroscope_guided",
+                                    "lvd_plus_modelscope256"}
+    z = bench.WORKLOADS["lvd_zeroscope"]
+    assert (z["frames"], z["h"], z["w"], z["cfg_tflop"], z["guid_tflop"]) == (24, 40, 72, 42.79, 32.59)
+    m = bench.WORKLOADS["lvd_plus_modelscope256"]
+    assert (m["frames"], m["h"], m["w"], m["gated"], m["guided"]) == (16, 32, 32, True, True)
+    assert "576x320" in bench._workload("lvd_zeroscope") and "i % 5 == 0" in bench._workload("lvd_zeroscope")
+    assert "GLIGEN" in bench._workload("lvd_gligen_zeroscope")
+    assert bench.METRIC.startswith("denoising-step frames/s") and bench.UNIT == "frames/s"
+    boxes, pos = bench.bear_layout(24)
+    assert len(boxes) == 1 and len(boxes[0]) == 24 and pos == [[2]]
+    assert boxes[0][0][0] == 0.0 and abs(boxes[0][-1][2] - (0.83 * 0.8 + 0.17)) < 1e-9
+
+
+def test_reference_arm_json_line(monkeypatch):
+    import bench
+    monkeypatch.setattr(bench, "cpu_reference_step", lambda frames, steps, warmup, ge=5: (0.5, 4.0, 16, 6.0, 3.5))
+    monkeypatch.setattr(sys, "argv", ["bench.py", "--impl", "reference", "--steps", "2", "--warmup", "1"])
+    monkeypatch.setenv("RANK", "0")
+    buf = io.StringIO()
+    with redirect_stdout(buf):
+        bench.main()
+    line = json.loads(buf.getvalue().strip())
+    assert line["impl"] == "reference" and line["metric"] == bench.METRIC and line["unit"] == "frames/s"
+    assert line["value"] == 0.5 and line["higher_is_better"] is True and line["vs_baseline"] is None
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] == 16
+    assert line["e2e"] == {"value": 0.5, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert line["config"]["workload"] == bench._workload("lvd_zeroscope")
+    # ranks other than 0 print nothing
+    monkeypatch.setenv("RANK", "1")
+    buf = io.StringIO()
+    with redirect_stdout(buf):
+        bench.main()
+    assert buf.getvalue() == ""
