@@ -1,8 +1,7 @@
-"""Import alias: the product package lives in `llm-groundedvideodiffusion_b200/` (a directory name Python cannot
-import directly because of the hyphen).  `import lvd_b200` maps onto that directory."""
-import os as _os
+"""lvd_b200 -- B200-native (sm_100a) denoising hot path of LLM-grounded Video Diffusion.
 
-_real = _os.path.join(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))), "llm-groundedvideodiffusion_b200")
-__path__.insert(0, _real)
-with open(_os.path.join(_real, "__init__.py")) as _f:
-    exec(compile(_f.read(), _os.path.join(_real, "__init__.py"), "exec"))
+Only what the hot path needs lives here: `csrc/` (hand-written CUDA kernels + the C-ABI), `_lib` (ctypes
+binding), `ops` (launch helpers) and the host-side mirror of the reference interface (`models/`, `utils/`).
+Import as `lvd_b200`.
+"""
+__version__ = "0.1.0"

@@ -280,6 +280,8 @@ class GuidanceGraph:
         x, c = self._transformer_fwd(w["transformer_in"], x, spatial=False, n_img=n_img, hw=hw, batch=1,
                                      frames=frames)
         tape.append(("tattn", w["transformer_in"], c, None))
+        # skips[0] is transformer_in's output: its gradient joins before transformer_in's adjoint runs
+        tape.append(("skip_out", None, None, 0))
         done = False
 
         def layer(L, x, kind, stage, j, h, w_):
@@ -408,8 +410,6 @@ class GuidanceGraph:
                 g = gskip.pop(extra, None)
                 if g is not None:
                     d = g if d is None else ops.add_rows(d, g)
-        g0 = gskip.pop(0, None)
-        if g0 is not None:
-            d = ops.add_rows(d, g0)
+        assert not gskip, sorted(gskip)
         grad = ops.conv_in_bwd(d, w["conv_in"].w, 1, frames, latents.shape[3], latents.shape[4])
         return loss, grad

@@ -12,8 +12,11 @@ Kept from the reference (file:line are into /root/reference/models/unet_3d_condi
   * `.modules()` yields objects whose class name is `GatedSelfAttentionDense` with a writable `.enabled`
     (the pipeline toggles them, controllable_pipeline_text_to_video_synth.py:535-539);
   * `load_state_dict` takes the reference's parameter names unchanged.
+`return_token_ca_only`, `return_cond_ca_only`, `offload_cross_attn_to_cpu` slice / move the stored maps as the reference
+processor does (models/attention_processor.py:556-577); `cross_attn_save_hidden_states` is accepted and ignored (it only
+parks an activation on the processor object for debugging, :457-458).
 Not implemented (raise, never fall back): attention_mask, class_labels, timestep_cond, additional residuals,
-attn_process_fn, offload_cross_attn_to_cpu, return_cond_ca_only, return_token_ca_only.
+attn_process_fn.
 """
 from dataclasses import dataclass
 
@@ -177,23 +180,29 @@ class UNet3DConditionModel:
             # the reference crashes here too (it writes cross_attention_kwargs["attn_key"], :731)
             raise TypeError("cross_attention_kwargs must be a dict")
         kw = cross_attention_kwargs
-        for k in ("attn_process_fn", "offload_cross_attn_to_cpu", "return_cond_ca_only", "return_token_ca_only",
-                  "cross_attn_save_hidden_states"):
-            if kw.get(k):
-                raise NotImplementedError(f"cross_attention_kwargs[{k!r}] is not supported by lvd_b200")
+        if kw.get("attn_process_fn") is not None:
+            raise NotImplementedError("cross_attention_kwargs['attn_process_fn'] is not supported by lvd_b200")
         kw["attn_key"] = ["up", len(self._cfg["block_out_channels"]) - 1]  # what the reference leaves behind
         save_dict = kw.get("save_attn_to_dict")
         save_keys = kw.get("save_keys")
+        tok_only = kw.get("return_token_ca_only")
+        cond_only = bool(kw.get("return_cond_ca_only", False))
+        offload = bool(kw.get("offload_cross_attn_to_cpu", False))
         capture = None
+        pending = []
+        # models/attention_processor.py:578-586: a map is stored only when BOTH save_attn_to_dict and save_keys are
+        # given and the key is listed (save_keys=None takes the materialising path there but stores nothing)
         if save_dict is not None and save_keys is not None and len(save_keys) > 0:
             wanted = {tuple(k) for k in save_keys}
             dev = self._engine.dev
+            if cond_only:
+                assert sample.shape[0] % 2 == 0, f"Samples are not in pairs: {sample.shape[0]} samples"
 
             def capture(key, n_img, heads, hw):
                 if key in wanted:
                     t = torch.empty((n_img, heads, hw, encoder_hidden_states.shape[1]), dtype=torch.float16,
                                     device=dev)
-                    save_dict[key] = t
+                    pending.append((key, t))
                     return dict(p_full=t)
                 return {}
 
@@ -202,6 +211,14 @@ class UNet3DConditionModel:
             out = self._forward_graphed(sample, timestep, encoder_hidden_states, gligen)
         else:
             out = self._engine.forward(sample, timestep, encoder_hidden_states, capture=capture, gligen=gligen)
+        for key, p in pending:  # the slicing the reference processor applies before storing (:556-577)
+            if tok_only is not None:
+                p = p[:, :, :, tok_only:tok_only + 1] if isinstance(tok_only, int) else p[:, :, :, tok_only]
+            if cond_only:
+                p = p[p.shape[0] // 2:]
+            if offload:
+                p = p.cpu()
+            save_dict[key] = p
         if not return_dict:
             return (out,)
         return UNet3DConditionOutput(sample=out)

@@ -267,13 +267,19 @@ def conv_temporal(x, batch, frames, hw, wk, bias=None, *, residual=None, out=Non
 
 # ----------------------------------------------------------------------------------------------- normalisation
 _gn_ws = {}
+_gn_ws_retired = []  # outgrown workspaces stay alive: captured CUDA graphs hold their raw pointers
 
 
 def _gn_workspace(dev, samples, groups):
+    """Scratch for the GroupNorm partial statistics.  64 MB up front covers 240 samples (a CFG batch of 5 videos x 24
+    frames); a larger request allocates a new buffer and RETIRES the old one without freeing it, because UNet /
+    guidance graphs captured earlier replay with the old address baked in."""
     need = samples * 1040 * groups * 8
     ws = _gn_ws.get(dev)
     if ws is None or ws.numel() < need:
-        ws = torch.empty(max(need, 1 << 22), dtype=torch.uint8, device=dev)
+        if ws is not None:
+            _gn_ws_retired.append(ws)
+        ws = torch.empty(max(need, 1 << 26), dtype=torch.uint8, device=dev)
         _gn_ws[dev] = ws
     return ws
 

@@ -6,6 +6,7 @@ The reference loops in Python over keys x objects x frames x tokens with ~20 tin
 Supported: the default max-based (top-k) loss and the centre-of-mass terms.  The deprecated / CLI-unreachable
 variants (ratio-based, CE, smoothing, renorm, upsample, attn-sync, BoxDiff) raise NotImplementedError.
 """
+import re
 from collections.abc import Iterable
 
 import torch
@@ -73,3 +74,93 @@ def compute_ca_lossv3(saved_attn, bboxes, object_positions, guidance_attn_keys, 
                        com_loss_scale=kwargs.get("com_loss_scale", 0.0),
                        out_scale=1.0 / (object_number * num_attn))
     return loss
+
+
+# ------------------------------------------------------------------------------------------------ host: prompt tokens
+def _plural(word):
+    """`inflect.engine().plural` when inflect is installed (the reference's dependency, utils/guidance.py:12-14);
+    otherwise the regular English rules -- only reached for phrases whose last word is not in the prompt."""
+    try:
+        import inflect
+        return inflect.engine().plural(word)
+    except Exception:
+        if re.search(r"(s|x|z|ch|sh)$", word):
+            return word + "es"
+        if re.search(r"[^aeiou]y$", word):
+            return word[:-1] + "ies"
+        return word + "s"
+
+
+def get_token_map(tokenizer, prompt, verbose=False, padding="do_not_pad"):
+    """Token strings of `prompt` incl. <bos>/<eos> (utils/guidance.py:18-41)."""
+    ids = tokenizer([prompt], padding=padding, max_length=77, return_tensors="np")["input_ids"][0]
+    out = []
+    for i, tok_id in enumerate(ids.tolist()):
+        tok = tokenizer._convert_id_to_token(tok_id)
+        if verbose:
+            print(f"{i}, {tok} ({tok_id})")
+        out.append(tok)
+    return out
+
+
+def refine_phrase(prompt, phrase, verbose=False):
+    """Find a form of `phrase` that occurs in `prompt` as whole words: as is, without its digits, its last word, that
+    word's plural (utils/guidance.py:44-66).  Returns (found, refined_phrase)."""
+    def present(p):
+        return re.search(r"\b" + p + r"\b", prompt) is not None
+
+    cand = phrase
+    if present(cand):
+        return True, cand
+    cand = cand.strip("0123456789 ")
+    if present(cand):
+        return True, cand
+    last = cand.split(" ")[-1]
+    if verbose:
+        print(f'**Phrase "{cand}" is not part of the prompt "{prompt}", using the last word "{last}" only**')
+    cand = last
+    if present(cand):
+        return True, cand
+    cand = _plural(cand)
+    if verbose:
+        print(f'**Phrase is still not part of the prompt "{prompt}", using plural "{cand}" instead**')
+    if present(cand):
+        return True, cand
+    print(f'**Phrase is still not part of the prompt "{prompt}"**')
+    return False, cand
+
+
+def get_phrase_indices(tokenizer, prompt, phrases, verbose=False, words=None, include_eos=False, token_map=None,
+                       return_word_token_indices=False):
+    """Token positions of every phrase inside the tokenised prompt (utils/guidance.py:69-151): the phrase is tokenised
+    on its own and located as a sub-sequence of the prompt's token strings."""
+    if token_map is None:
+        token_map = get_token_map(tokenizer, prompt=prompt, verbose=verbose, padding="do_not_pad")
+    joined = " ".join(token_map)
+    positions, word_indices = [], []
+    for i, phrase in enumerate(phrases):
+        found, refined = refine_phrase(prompt, phrase)
+        assert found, "phrase {obj} not found in the prompt {prompt}"
+        sub = get_token_map(tokenizer, prompt=refined, verbose=verbose, padding="do_not_pad")[1:-1]  # no <bos>/<eos>
+        sub_joined = " ".join(sub)
+        if verbose:
+            print("Full str:", joined, "Substr:", sub_joined, "Phrase:", phrases)
+        first = len(joined[: joined.index(sub_joined) - 1].split(" "))  # tokens before the match
+        pos = list(range(first, first + len(sub)))
+        if include_eos:
+            pos.append(token_map.index(tokenizer.eos_token))
+        positions.append(pos)
+        if return_word_token_indices:
+            if words is None:
+                idx = positions[0][-1]
+                print(f'Picking the last token "{token_map[idx]}" ({idx}) as attention token for extracting attention '
+                      "for SAM, which might not be the right one")
+            else:
+                wt = get_token_map(tokenizer, prompt=words[i], verbose=verbose, padding="do_not_pad")
+                idx = first + sub.index(wt[-2])
+            if verbose:
+                print("so_token_index:", idx)
+            word_indices.append(idx)
+    if return_word_token_indices:
+        return positions, word_indices
+    return positions

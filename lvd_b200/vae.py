@@ -189,8 +189,26 @@ class AutoencoderKL:
     def disable_slicing(self):
         self.slice_images = 0
 
+    # diffusers < 0.17 `AttentionBlock` parameter names, still present in the published SD-1.x / Zeroscope / ModelScope
+    # VAE checkpoints; diffusers 0.27.2 converts them on load (`_convert_deprecated_attention_blocks`)
+    _LEGACY_ATTN = {"query": "to_q", "key": "to_k", "value": "to_v", "proj_attn": "to_out.0"}
+
+    @classmethod
+    def _convert_legacy(cls, state_dict):
+        out = {}
+        for k, v in state_dict.items():
+            parts = k.split(".")
+            if len(parts) >= 3 and "attentions" in parts and parts[-2] in cls._LEGACY_ATTN:
+                k = ".".join(parts[:-2] + [cls._LEGACY_ATTN[parts[-2]], parts[-1]])
+            if ".attentions." in k and k.endswith(".weight") and v.dim() == 4 and v.shape[2:] == (1, 1) and \
+                    ".to_" in k:
+                v = v.reshape(v.shape[0], v.shape[1])  # the oldest checkpoints store the projections as 1x1 convs
+            out[k] = v
+        return out
+
     def load_state_dict(self, state_dict, strict=True):
         spec = synthetic.vae_param_spec(self.config)
+        state_dict = self._convert_legacy(state_dict)
         missing = [k for k in spec if k not in state_dict]
         unexpected = [k for k in state_dict if k not in spec and not k.startswith(("encoder.", "quant_conv."))]
         if strict and (missing or unexpected):

@@ -7,7 +7,7 @@ own files verbatim through a `diffusers` shim (`ref_loader.py`, `shim/`) to pin 
 golden vectors under tests/golden/ (`make_golden.py`).
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this package.
-The product package (llm-groundedvideodiffusion_b200/) never does: its ops fail loudly without the CUDA library.
+The product package (lvd_b200/) never does: its ops fail loudly without the CUDA library.
 
 Parity status: the reference ships NO tests, golden vectors or fixtures, so the pin is
 "reference code executed here": tests/golden/*.npz are outputs of the reference's own modules run in this container

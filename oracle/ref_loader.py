@@ -15,6 +15,34 @@ def available():
 _loaded = None
 
 
+def stub_host_modules():
+    """Empty stand-ins for the plotting / LLM-client imports of utils/parse.py and utils/llm.py (matplotlib, imageio,
+    easydict, pyjson5): none carries arithmetic of the path."""
+    def mod(name, **attrs):
+        if name in sys.modules:
+            return sys.modules[name]
+        m = types.ModuleType(name)
+        for k, v in attrs.items():
+            setattr(m, k, v)
+        sys.modules[name] = m
+        return m
+
+    for name in ("matplotlib", "imageio", "easydict", "pyjson5"):
+        try:
+            __import__(name)
+        except ImportError:
+            pass
+    mp = mod("matplotlib")
+    mp.patches = mod("matplotlib.patches", Polygon=object)
+    mp.collections = mod("matplotlib.collections", PatchCollection=object)
+    mp.pyplot = mod("matplotlib.pyplot")
+    mod("imageio", RETURN_BYTES="<bytes>")
+    mod("easydict", EasyDict=dict)
+    import json as _json
+    mod("pyjson5", loads=_json.loads, Json5Exception=ValueError, Json5EOF=ValueError, Json5DecoderException=ValueError,
+        Json5IllegalCharacter=ValueError)
+
+
 def load():
     """Returns a namespace with the reference classes/functions (UNet3DConditionModel, latent_backward_guidance,
     guidance module, parse helpers)."""

@@ -44,7 +44,7 @@ def test_struct_layout_matches_header_sizes():
 
 
 def test_product_package_does_not_import_oracle():
-    pkg = os.path.join(ROOT, "llm-groundedvideodiffusion_b200")
+    pkg = os.path.join(ROOT, "lvd_b200")
     for dp, _, fs in os.walk(pkg):
         for f in fs:
             if f.endswith((".py", ".cu", ".cuh", ".h")):

@@ -47,6 +47,22 @@ def test_vae_mirror_validates_state_dict():
         vae.load_state_dict(dict(sd, extra=torch.zeros(1)))
     with pytest.raises(RuntimeError, match="size mismatch"):
         vae.load_state_dict(dict(sd, **{"decoder.conv_out.bias": torch.zeros(7)}))
+    # published SD-1.x / Zeroscope VAE checkpoints carry the deprecated AttentionBlock names (query / key / value /
+    # proj_attn, the oldest as 1x1 convs): converted on load like diffusers 0.27.2 does
+    legacy = {}
+    ren = {"to_q": "query", "to_k": "key", "to_v": "value", "to_out.0": "proj_attn"}
+    for k, v in sd.items():
+        for new, old in ren.items():
+            if f".attentions.0.{new}." in k:
+                k = k.replace(f".attentions.0.{new}.", f".attentions.0.{old}.")
+                if k.endswith(".weight"):
+                    v = v[:, :, None, None]
+                break
+        legacy[k] = v
+    assert any(".query." in k for k in legacy) and not any(".to_q." in k for k in legacy)
+    vae.load_state_dict(legacy)
+    for k, v in sd.items():
+        assert torch.equal(vae._state[k], v), k
     with pytest.raises(RuntimeError, match="no weights"):
         AutoencoderKL().decode(torch.zeros(1, 4, 8, 8))
     with pytest.raises(NotImplementedError):

@@ -5,8 +5,6 @@ Tolerance.  north_star asks for 1e-3 relative in fp16 against the reference *run
 ~250-layer graph is itself only reproducible to a few 1e-3 of the output scale (we measure that here by running the
 oracle in fp16 on the same GPU), so the gate is:  err(engine fp16 vs oracle fp32) <= max(2e-3, 1.5 x err(oracle fp16
 vs oracle fp32)), err = max|a-b| / max|b|.  Cross-attention maps (probabilities in [0,1]) are held to 3e-3 absolute."""
-import os
-
 import pytest
 import torch
 
@@ -175,34 +173,3 @@ def test_unet_mirror_graph_replay_is_bit_identical_to_eager(cuda):
                 y = unet(x, 300 + i, ehs, cross_attention_kwargs={"gligen": gl}, return_dict=False)[0]
                 assert torch.equal(y, ref[(on, i)]), (rep, on, i)
     assert not torch.equal(ref[(True, 0)], ref[(False, 0)])
-
-
-@pytest.mark.skipif(not os.environ.get("LVD_FULL_SIZE_TESTS"),
-                    reason="3 minutes (1.4 B random weights + fp32 oracle): set LVD_FULL_SIZE_TESTS=1; last result in "
-                           "profiles/r1d_summary.md")
-def test_unet_forward_zeroscope_full_size(cuda):
-    """BASELINE.json config 2 shape: the 1.41 B-parameter Zeroscope UNet on 24 frames of 40x72 latents (one CFG branch),
-    engine fp16 against the fp32 oracle run on the same GPU (TF32 off).  Same gate as the tiny cases, with the fp16 noise
-    floor measured by running the oracle itself in fp16."""
-    from lvd_b200 import synthetic
-    from lvd_b200.engine import UNetEngine
-    from oracle import unet3d_ref as R
-    torch.backends.cuda.matmul.allow_tf32 = False
-    torch.backends.cudnn.allow_tf32 = False
-    cfg = synthetic.make_cfg("zeroscope")
-    sd16 = synthetic.random_state_dict(cfg, seed=0, dtype=torch.float16)
-    x, ehs = _inputs(cfg, 1, 24, 40, 72, cuda, seed=11)
-    x16, e16 = x.half(), ehs.half()
-    eng = UNetEngine(cfg, sd16, device=cuda)
-    y = eng.forward(x16, 951, e16)
-    torch.cuda.synchronize()
-    sd_dev = {k: v.to(cuda) for k, v in sd16.items()}
-    with torch.no_grad():
-        y16 = R.unet_forward(sd_dev, cfg, x16, 951, e16)
-        sd32 = {k: v.float() for k, v in sd_dev.items()}
-        del sd_dev
-        y32 = R.unet_forward(sd32, cfg, x16.float(), 951, e16.float())
-    e_eng, e_ref16 = rel_err(y, y32), rel_err(y16, y32)
-    print(f"\n[unet zeroscope 24f 40x72] engine-vs-fp32 {e_eng:.3e}   torch-fp16-vs-fp32 {e_ref16:.3e}")
-    assert y.shape == (1, 4, 24, 40, 72) and torch.isfinite(y.float()).all()
-    assert e_eng <= max(2e-3, 1.5 * e_ref16)
