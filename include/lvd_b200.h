@@ -208,8 +208,9 @@ int lvd_axpy_h(const void* x, const void* g, void* out, int64_t n, float scale, 
 
 /* ------------------------------------------------------------------------------------------------------------
  * Box energy of the LVD backward guidance on one saved cross-attention map, and dE/dP.
- * Replaces utils/guidance.py:160-526 (add_ca_loss_per_attn_map_to_loss; default top-k "max-based" loss + optional
- * centre-of-mass position/velocity terms) and the normalisation of compute_ca_lossv3 (:529-574).
+ * Replaces utils/guidance.py:160-526 (add_ca_loss_per_attn_map_to_loss: top-k "max-based" / ratio / CE losses, attention
+ * sync, BoxDiff corner constraint, centre-of-mass position/velocity terms) and the normalisation of compute_ca_lossv3
+ * (:529-574).
  *   slot  = one (object, text token) pair; boxes[slot][frame] = (x0,y0,x1,y1) integer rectangle at this map's
  *           resolution (host applies utils/utils.py:82-103 scale_proportion -- Python banker's rounding);
  *   slot_weight[slot] = 1 / len(object_positions[object])  (guidance.py:524)
@@ -228,6 +229,11 @@ typedef struct lvd_energy_desc {
   void* dp;
   int32_t layout, n_text, n_slots, frames, heads, H, W;
   float fg_top_p, bg_top_p, fg_weight, bg_weight, com_loss_scale, out_scale, grad_scale;
+  /* loss_kind: 0 max-based top-k (guidance.py:341-353), 1 ratio-based (:312-323), 2 CE / NLL (:363-396);
+   * k_min = int(upsample_scale^2) (:328-337); eps (:179, 1e-2) enters kinds 1 and 2;
+   * attn_sync_weight (:401-426); boxdiff_* (:433-465).  Kind 2 excludes the sync / BoxDiff / COM terms. */
+  int32_t loss_kind, k_min, boxdiff_normed, boxdiff_L;
+  float eps, attn_sync_weight, boxdiff_loss_scale;
 } lvd_energy_desc;
 
 int lvd_box_energy(const lvd_energy_desc* d, void* stream);

@@ -95,6 +95,13 @@ class EnergyDesc(ctypes.Structure):
         ("com_loss_scale", ctypes.c_float),
         ("out_scale", ctypes.c_float),
         ("grad_scale", ctypes.c_float),
+        ("loss_kind", ctypes.c_int32),
+        ("k_min", ctypes.c_int32),
+        ("boxdiff_normed", ctypes.c_int32),
+        ("boxdiff_L", ctypes.c_int32),
+        ("eps", ctypes.c_float),
+        ("attn_sync_weight", ctypes.c_float),
+        ("boxdiff_loss_scale", ctypes.c_float),
     ]
 
 

@@ -2,10 +2,12 @@
 (oracle/guidance_ref.py: plain PyTorch forward, reference loss, torch.autograd for dE/dlatents) and against the golden
 vectors that the REFERENCE's latent_backward_guidance produced (oracle/make_golden.py).
 
-Tolerances.  The loss is an fp32 reduction of fp16 probabilities: 2e-3 relative.  The gradient passes through ~150
-fp16 layers twice; the check is the direction and size of the latent update: cosine >= 0.995 and
-||delta - delta_ref|| <= 8% ||delta_ref|| against the fp32 oracle (the fp16 autograd run of the oracle itself is
-reported alongside as the yardstick)."""
+Tolerances.  The loss is an fp32 reduction of fp16 probabilities: 1e-4 relative (measured <= 2e-5).  The gradient
+passes through ~150 fp16 layers twice and the top-k energy is discontinuous in the probabilities, so its error is
+judged against the yardstick measured in the same test -- the oracle itself run in fp16 with torch autograd on this
+GPU: ||delta - delta_ref|| <= 1.1 x the yardstick's (tiny 64-channel config: both ~7 %; at the BASELINE shapes the
+engine is at 0.4-2.7 % against 4-5 %, tests/test_parity_fullsize.py), cosine >= 0.997; key sets with smoother
+energies: <= 3 % (measured <= 1.8 %)."""
 import os
 
 import numpy as np
@@ -52,7 +54,7 @@ def test_guidance_step_matches_golden_reference(cuda):
                                              guidance_attn_keys=keys, base_attn_dim=(h, w), **hp)
         ref_lat = torch.from_numpy(g[f"guid{variant}_latents"]).to(cuda)
         ref_loss = float(g[f"guid{variant}_loss"])
-        assert abs(loss.item() - ref_loss) <= 3e-3 * abs(ref_loss), (loss.item(), ref_loss)
+        assert abs(loss.item() - ref_loss) <= 1e-4 * abs(ref_loss), (loss.item(), ref_loss)
         delta, dref = lat.float() - x.half().float().to(cuda), ref_lat - x.to(cuda)
         cos, rel = _cmp(delta, dref)
         # yardstick: the oracle itself evaluated in fp16 on this GPU (fp16 autograd)
@@ -62,12 +64,13 @@ def test_guidance_step_matches_golden_reference(cuda):
         cos16, rel16 = _cmp(lat16.float() - x.half().float().to(cuda), dref)
         print(f"\n[guidance {variant}] loss {loss.item():.4f} (ref {ref_loss:.4f}); update cos {cos:.5f} rel {rel:.4f}"
               f"   | torch fp16 autograd: cos {cos16:.5f} rel {rel16:.4f}")
-        assert cos >= 0.995 and rel <= 0.08
+        assert cos >= 0.997 and rel <= 1.1 * rel16 + 1e-3
         assert torch.isfinite(lat.float()).all()
 
 
 @pytest.mark.parametrize("keys", [[("down", 1, 0, 0)], [("down", 2, 1, 0), ("mid", 0, 0, 0)],
-                                  [("down", 1, 1, 0), ("up", 1, 2, 0)]])
+                                  [("down", 1, 1, 0), ("up", 1, 2, 0)],
+                                  [("down", 0, 1, 0), ("up", 3, 2, 0)]])  # the last one routes the gradient of skip 0
 def test_guidance_gradient_other_key_sets(cuda, keys):
     """Early-exit points in the down path / mid block / up path and skip-gradient routing."""
     from lvd_b200.engine import UNetEngine
@@ -94,8 +97,8 @@ def test_guidance_gradient_other_key_sets(cuda, keys):
                                                base_attn_dim=(h, w), **hp)
     cos, rel = _cmp(grad / GRAD_SCALE, ref_grad)
     print(f"\n[guidance keys={keys}] loss {loss.item():.4f} / {ref_loss.item():.4f}  grad cos {cos:.5f} rel {rel:.4f}")
-    assert abs(loss.item() - ref_loss.item()) <= 3e-3 * abs(ref_loss.item())
-    assert cos >= 0.995 and rel <= 0.08
+    assert abs(loss.item() - ref_loss.item()) <= 1e-4 * abs(ref_loss.item())
+    assert cos >= 0.9995 and rel <= 0.03
 
 
 def test_guidance_pass_graph_replay_matches_eager(cuda):
