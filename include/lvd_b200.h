@@ -238,6 +238,30 @@ typedef struct lvd_energy_desc {
 
 int lvd_box_energy(const lvd_energy_desc* d, void* stream);
 
+/* Optional pre-processing of a saved map ahead of lvd_box_energy, and the adjoints back to dE/dP
+ * (utils/guidance.py:209-226,281-311; utils/attn.py:91-157 GaussianSmoothing).  Maps are fp16
+ * [planes = frames*heads][hw][n_text]; gradients travel as fp32 between adjoint stages, the stage that produces dE/dP
+ * itself writes fp16 (`*_is_half` = 1).
+ *   lvd_attn_smooth      : depthwise 3x3 blur (weights w9_host[9], row-major (d_pixel, d_token)) of the reflect-padded
+ *                          (hw x n_text) plane -- smooth_attn=True
+ *   lvd_attn_renorm      : out[rows][num_tokens-2] = softmax(p[rows][1:num_tokens-1] * scale) -- attn_renorm=True
+ *   lvd_attn_columns     : cols[n_slots][planes][h_out*w_out] = column slot_col[slot] of the map, bilinearly
+ *                          interpolated (align_corners = False) when (h_out, w_out) != (h_in, w_in) -- upsample_scale
+ * ---------------------------------------------------------------------------------------------------------- */
+int lvd_attn_smooth(const void* p, void* out, int64_t planes, int32_t hw, int32_t n_text, const float* w9_host,
+                    void* stream);
+int lvd_attn_smooth_bwd(const void* d_out_f32, void* d_p, int32_t d_p_is_half, int64_t planes, int32_t hw,
+                        int32_t n_text, const float* w9_host, void* stream);
+int lvd_attn_renorm(const void* p, void* out, int64_t rows, int32_t n_text, int32_t num_tokens, float scale,
+                    void* stream);
+int lvd_attn_renorm_bwd(const void* r_out, const void* d_r_f32, void* d_p, int32_t d_p_is_half, int64_t rows,
+                        int32_t n_text, int32_t num_tokens, float scale, void* stream);
+int lvd_attn_columns(const void* map, const int32_t* slot_col_dev, void* cols, int32_t n_slots, int64_t planes,
+                     int32_t n_cols, int32_t h_in, int32_t w_in, int32_t h_out, int32_t w_out, void* stream);
+int lvd_attn_columns_bwd(const void* d_cols, const int32_t* slot_col_dev, void* d_map, int32_t d_map_is_half,
+                         int32_t n_slots, int64_t planes, int32_t n_cols, int32_t h_in, int32_t w_in, int32_t h_out,
+                         int32_t w_out, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * GLIGEN helpers.
  * lvd_copy_rows_seq: dst[(r/n)*dst_seq + dst_off + r%n] = src[(r/n)*src_seq + src_off + r%n]; builds / splits the
@@ -303,6 +327,8 @@ int lvd_self_attn_bwd(const void* qkv, int64_t ld_qkv, int64_t width_qkv, int32_
 int lvd_temporal_attn_bwd(const void* qkv, int64_t ld_qkv, int64_t width_qkv, int32_t q_col0, int32_t k_col0,
                           int32_t v_col0, const void* d_o, int64_t ld_do, void* d_qkv, int64_t ld_dqkv, int64_t n_seq,
                           int32_t heads, int32_t frames, float scale, void* stream);
+/* dp_tok: n_slots in 1..16 -> dE/dP of the listed token columns [n_slots][nz][heads][s_q]; n_slots == -1 -> the dense
+ * map [nz][heads][s_q][s_k] (map pre-processing variants of the energy, more than 16 slots); 0 -> none. */
 int lvd_cross_attn_bwd(const void* q, int64_t ld_q, int64_t width_q, const void* kv, int64_t ld_kv, int64_t width_kv,
                        int32_t k_col0, int32_t v_col0, const void* d_o, int64_t ld_do, const void* dp_tok,
                        const int32_t* slot_col_host,

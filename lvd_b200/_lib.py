@@ -148,6 +148,13 @@ def _declare(l):
     l.lvd_cfg_dpm_step.argtypes = [vp, vp, vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, f32, f32, i32, vp]
     l.lvd_axpy_h.argtypes = [vp, vp, vp, i64, f32, vp]
     l.lvd_box_energy.argtypes = [ctypes.POINTER(EnergyDesc), vp]
+    f9 = ctypes.POINTER(ctypes.c_float)
+    l.lvd_attn_smooth.argtypes = [vp, vp, i64, i32, i32, f9, vp]
+    l.lvd_attn_smooth_bwd.argtypes = [vp, vp, i32, i64, i32, i32, f9, vp]
+    l.lvd_attn_renorm.argtypes = [vp, vp, i64, i32, i32, f32, vp]
+    l.lvd_attn_renorm_bwd.argtypes = [vp, vp, vp, i32, i64, i32, i32, f32, vp]
+    l.lvd_attn_columns.argtypes = [vp, vp, vp, i32, i64, i32, i32, i32, i32, i32, vp]
+    l.lvd_attn_columns_bwd.argtypes = [vp, vp, vp, i32, i32, i64, i32, i32, i32, i32, i32, vp]
     l.lvd_copy_rows_seq.argtypes = [vp, i64, vp, i64, i64, i32, i32, i32, i32, i32, i32, vp]
     l.lvd_gligen_prep.argtypes = [vp, vp, vp, vp, vp, vp, i64, i32, vp]
     l.lvd_groupnorm_bwd.argtypes = [vp, i64, vp, i64, vp, i64, i32, i64, i32, i32, vp, vp, f32, i32, i32, vp, vp, i64,
@@ -195,6 +202,12 @@ EXPORTS = [
     "lvd_cfg_dpm_step",
     "lvd_axpy_h",
     "lvd_box_energy",
+    "lvd_attn_smooth",
+    "lvd_attn_smooth_bwd",
+    "lvd_attn_renorm",
+    "lvd_attn_renorm_bwd",
+    "lvd_attn_columns",
+    "lvd_attn_columns_bwd",
     "lvd_copy_rows_seq",
     "lvd_gligen_prep",
     "lvd_groupnorm_bwd",

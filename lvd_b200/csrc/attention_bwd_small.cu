@@ -322,8 +322,17 @@ extern "C" int lvd_cross_attn_bwd(const void* q, int64_t ld_q, int64_t width_q, 
                                   const int32_t* slot_col_host, int32_t n_slots, void* dq, int64_t ld_dq, int64_t s_q,
                                   int32_t s_k, int32_t heads, int32_t nz, int32_t kv_z_div, float scale, void* stream) {
   LVD_REQUIRE(q && kv && d_o && dq, "lvd_cross_attn_bwd: null pointer");
-  LVD_REQUIRE(s_k >= 1 && s_k <= 128 && n_slots >= 0 && n_slots <= 16 && (n_slots == 0 || (dp_tok && slot_col_host)),
+  LVD_REQUIRE(s_k >= 1 && s_k <= 128 && n_slots >= -1 && n_slots <= 16 &&
+                  (n_slots == 0 || dp_tok) && (n_slots <= 0 || slot_col_host),
               "lvd_cross_attn_bwd: s_k=%d n_slots=%d unsupported", s_k, n_slots);
+  if (n_slots == -1) {  // dense dE/dP map: warp-level kernel only
+    LVD_REQUIRE(width_q > 0 && width_kv > 0, "lvd_cross_attn_bwd: the dense dE/dP form needs the tensor-core path");
+    const int r = launch_cross_attn_bwd_mma(q, ld_q, kv, ld_kv, k_col0, v_col0, d_o, ld_do, dp_tok, nullptr, -1, dq,
+                                            ld_dq, s_q, s_k, heads, nz, kv_z_div, scale,
+                                            static_cast<cudaStream_t>(stream));
+    LVD_REQUIRE(r != 1, "lvd_cross_attn_bwd: dense dE/dP form: unsupported shape");
+    return r;
+  }
   if (width_q > 0 && width_kv > 0) {
     static const bool force_tile = getenv("LVD_CROSS_BWD_TILE") != nullptr;  // A/B switch for tools/
     if (!force_tile) {  // warp-level mma.sync kernel (attention_temporal.cu)

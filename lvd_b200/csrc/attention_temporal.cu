@@ -415,7 +415,22 @@ __global__ void __launch_bounds__(128) cross_attn_bwd_mma_kernel(const CrossBwdM
   }
   // dE/dP of the guided token columns (this lane owns columns 8 nt + 2t, + 1 of rows g and g + 8); the register
   // arrays keep static indices: the slot list is searched per owned column
-  if (a.n_slots > 0) {
+  if (a.n_slots < 0) {
+    // dense dE/dP [nz][heads][s_q][s_k] (map pre-processing variants of the energy, or more than 16 token slots)
+    const int ra = r0 + g, rb = r0 + 8 + g;
+    const __half* src = a.dp_tok + ((z * a.heads + h) * static_cast<long long>(a.s_q)) * a.s_k;
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int c = nt * 8 + 2 * t + e;
+        if (c < a.s_k) {
+          if (ra < a.s_q) dp[nt][e] += __half2float(src[static_cast<long long>(ra) * a.s_k + c]);
+          if (rb < a.s_q) dp[nt][2 + e] += __half2float(src[static_cast<long long>(rb) * a.s_k + c]);
+        }
+      }
+    }
+  } else if (a.n_slots > 0) {
     const int ra = r0 + g, rb = r0 + 8 + g;
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) {
@@ -524,7 +539,7 @@ int launch_cross_attn_bwd_mma(const void* q, long long ld_q, const void* kv, lon
                               const void* d_o, long long ld_do, const void* dp_tok, const int* slot_col, int n_slots,
                               void* dq, long long ld_dq, long long s_q, int s_k, int heads, int nz, int kv_z_div,
                               float scale, cudaStream_t stream) {
-  if (s_k < 1 || s_k > 128 || n_slots > 16) return 1;
+  if (s_k < 1 || s_k > 128 || n_slots > 16) return 1;  // n_slots == -1: dp_tok is the dense map
   CrossBwdMmaArgs a;
   a.q = static_cast<const __half*>(q);
   a.kv = static_cast<const __half*>(kv);
@@ -544,7 +559,7 @@ int launch_cross_attn_bwd_mma(const void* q, long long ld_q, const void* kv, lon
   a.q_tiles = (a.s_q + 15) / 16;
   a.kv_z_div = kv_z_div;
   a.n_slots = dp_tok ? n_slots : 0;
-  for (int i = 0; i < 16; ++i) a.slot_col[i] = i < a.n_slots ? slot_col[i] : -1;
+  for (int i = 0; i < 16; ++i) a.slot_col[i] = (i < a.n_slots && slot_col) ? slot_col[i] : -1;
   a.scale = scale;
   a.scale_log2 = scale * 1.4426950408889634f;
   a.n_warps = static_cast<long long>(nz) * a.q_tiles * heads;

@@ -219,37 +219,36 @@ __global__ void __launch_bounds__(kEnergyThreads) box_energy_kernel(const Energy
   }
   __syncthreads();
 
-  // ---- attention sync between consecutive frames inside this frame's box (guidance.py:401-426; fp32 here, the
-  // reference evaluates the squared difference in the map dtype).  An empty box makes the reference's mean() NaN.
+  // ---- attention sync between consecutive frames (guidance.py:401-426; fp32 here, the reference evaluates the
+  // squared difference in the map dtype).  The crop is the NEXT frame's rectangle: the reference's x_min..y_max were
+  // last assigned by its loop over frame_boxes_t1 (:268-271).  An empty crop makes the reference's mean() NaN.
   if (g.sync_w != 0.f) {
     if (f + 1 < g.frames) {
+      const int* bn = g.boxes + (static_cast<long long>(slot) * g.frames + (f + 1)) * 4;
+      const int nx0 = bn[0], ny0 = bn[1], nx1 = bn[2], ny1 = bn[3];
+      const int narea = (nx1 > nx0 && ny1 > ny0) ? (nx1 - nx0) * (ny1 - ny0) : 0;
       float acc = 0.f;
-      if (area > 0) {
-        const int bw = x1 - x0;
-        const float c2 = 2.f * g.sync_w / static_cast<float>(area);
-        for (int j = threadIdx.x; j < area; j += blockDim.x) {
-          const int i = (y0 + j / bw) * g.W + x0 + j % bw;
+      if (narea > 0) {
+        const int bw = nx1 - nx0;
+        const float c2 = 2.f * g.sync_w / static_cast<float>(narea);
+        for (int j = threadIdx.x; j < narea; j += blockDim.x) {
+          const int i = (ny0 + j / bw) * g.W + nx0 + j % bw;
           const float d = __half2float(col[i]) - col_at(g, slot, f + 1, h, i, false);
           acc += d * d;
           grad[i] += c2 * d;
         }
       }
       acc = block_sum(acc, red);
-      loss += area > 0 ? g.sync_w * acc / static_cast<float>(area) : __int_as_float(0x7fc00000);
+      loss += narea > 0 ? g.sync_w * acc / static_cast<float>(narea) : __int_as_float(0x7fc00000);
     }
-    if (f >= 1) {  // this frame is "frame 2" of the previous frame's term
-      const int* bp = g.boxes + (static_cast<long long>(slot) * g.frames + (f - 1)) * 4;
-      const int px0 = bp[0], py0 = bp[1], px1 = bp[2], py1 = bp[3];
-      const int parea = (px1 > px0 && py1 > py0) ? (px1 - px0) * (py1 - py0) : 0;
-      if (parea > 0) {
-        const int bw = px1 - px0;
-        const float c2 = 2.f * g.sync_w / static_cast<float>(parea);
-        __syncthreads();
-        for (int j = threadIdx.x; j < parea; j += blockDim.x) {
-          const int i = (py0 + j / bw) * g.W + px0 + j % bw;
-          const float d = col_at(g, slot, f - 1, h, i, ce) - col_at(g, slot, f, h, i, false);
-          grad[i] += -c2 * d;
-        }
+    if (f >= 1 && area > 0) {  // this frame is "frame 2" of the previous frame's term, cropped to THIS frame's box
+      const int bw = x1 - x0;
+      const float c2 = 2.f * g.sync_w / static_cast<float>(area);
+      __syncthreads();
+      for (int j = threadIdx.x; j < area; j += blockDim.x) {
+        const int i = (y0 + j / bw) * g.W + x0 + j % bw;
+        const float d = col_at(g, slot, f - 1, h, i, ce) - col_at(g, slot, f, h, i, false);
+        grad[i] += -c2 * d;
       }
     }
     __syncthreads();

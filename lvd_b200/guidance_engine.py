@@ -16,7 +16,7 @@ Gradients are carried multiplied by GRAD_SCALE in fp16 and un-scaled in the fina
 import torch
 
 from . import ops, repack
-from .utils.guidance import build_slots
+from .utils.guidance import build_slots, energy_options, map_energy
 from .utils.utils import get_hw_from_attn_dim
 
 GRAD_SCALE = 1024.0
@@ -82,7 +82,7 @@ class GuidanceGraph:
             d = ops.groupnorm_bwd(c.ins[i], d, c.batch, L.norm.w, L.norm.b, 1e-5, silu=True, stats=c.sts[i])
         return ops.add_rows(d, dout)
 
-    def _block_fwd(self, B, t, *, heads, spatial, n_img, hw, batch, frames, ctx_kv, tok_cols, want_tok):
+    def _block_fwd(self, B, t, *, heads, spatial, n_img, hw, batch, frames, ctx_kv, tok_cols, want_tok, dense=False):
         c = t.shape[1]
         ctx = Ctx(t0=t, heads=heads, spatial=spatial, n_img=n_img, hw=hw, batch=batch, frames=frames)
         n1 = ops.layernorm(t, B.norm1.w, B.norm1.b)
@@ -103,12 +103,15 @@ class GuidanceGraph:
         if spatial:
             q = ops.linear(n2, B.q2)
             kv = ops.linear(ctx_kv, B.kv2)
-            p_tok = None
-            if want_tok:
+            p_tok = p_full = None
+            s_k = ctx_kv.shape[0] // batch
+            if want_tok and dense:  # the whole map (pre-processing variants, > 16 token slots, return_saved_attn)
+                p_full = torch.empty((n_img, heads, hw, s_k), dtype=torch.float16, device=self.dev)
+            elif want_tok:
                 p_tok = torch.empty((len(tok_cols), n_img, heads, hw), dtype=torch.float16, device=self.dev)
-            a2 = ops.attention(q, kv, heads=heads, nz=n_img, s_q=hw, s_k=ctx_kv.shape[0] // batch, k_col0=0, v_col0=c,
-                               kv_z_div=frames, p_tok=p_tok, tok_cols=tok_cols if want_tok else ())
-            ctx.update(q2=q, kv2=kv, p_tok=p_tok, s_k=ctx_kv.shape[0] // batch)
+            a2 = ops.attention(q, kv, heads=heads, nz=n_img, s_q=hw, s_k=s_k, k_col0=0, v_col0=c,
+                               kv_z_div=frames, p_tok=p_tok, p_full=p_full, tok_cols=tok_cols if p_tok is not None else ())
+            ctx.update(q2=q, kv2=kv, p_tok=p_tok, p_full=p_full, s_k=s_k)
         else:
             qkv2 = ops.linear(n2, B.qkv2, row_map=fm2sm)
             a2 = ops.attention(qkv2, qkv2, heads=heads, nz=batch, temporal=True, packed=True, frames=frames, hw=hw,
@@ -123,7 +126,7 @@ class GuidanceGraph:
         t3 = ops.linear(gg, B.ff2.w, B.ff2.b, residual=t2)
         return t3, ctx
 
-    def _block_bwd(self, B, c, d3, dp_tok=None, tok_cols=()):
+    def _block_bwd(self, B, c, d3, dp_tok=None, tok_cols=(), dp_dense=None):
         """d3: gradient w.r.t. the block output, or None when only the cross-attention energy seeds it."""
         sp = c.spatial
         fm2sm = None if sp else ("fm2sm", c.batch, c.frames, c.hw)
@@ -140,7 +143,7 @@ class GuidanceGraph:
             d_a2 = torch.zeros((c.t0.shape[0], ch), dtype=torch.float16, device=self.dev)
         if sp:
             d_q = ops.cross_attention_bwd(c.q2, c.kv2, d_a2, heads=c.heads, nz=c.n_img, s_q=c.hw, s_k=c.s_k,
-                                          kv_z_div=c.frames, dp_tok=dp_tok, slot_cols=tok_cols)
+                                          kv_z_div=c.frames, dp_tok=dp_tok, slot_cols=tok_cols, dp_dense=dp_dense)
             d_n2 = ops.linear_dgrad(d_q, B.q2)
         else:
             d_qkv2 = ops.temporal_attention_bwd(c.qkv2, d_a2, heads=c.heads, n_seq=c.batch * c.hw, frames=c.frames)
@@ -158,23 +161,23 @@ class GuidanceGraph:
         return ops.layernorm_bwd(c.t0, d_n1, B.norm1.w, out=d_t1, accumulate=True)
 
     def _transformer_fwd(self, T, x, *, spatial, n_img, hw, batch, frames, ctx_kv=None, tok_cols=(), want_tok=False,
-                         last=False):
+                         last=False, dense=False):
         samples = n_img if spatial else batch
         st = ops.gn_stats_buffer(samples, self.dev)
         g = ops.groupnorm(x, samples, T.norm.w, T.norm.b, 1e-6, silu=False, stats_out=st)
         t0 = ops.linear(g, T.proj_in.w, T.proj_in.b)
         heads = t0.shape[1] // self.cfg["attention_head_dim"]
         t1, bctx = self._block_fwd(T.block, t0, heads=heads, spatial=spatial, n_img=n_img, hw=hw, batch=batch,
-                                   frames=frames, ctx_kv=ctx_kv, tok_cols=tok_cols, want_tok=want_tok)
+                                   frames=frames, ctx_kv=ctx_kv, tok_cols=tok_cols, want_tok=want_tok, dense=dense)
         out = None if last else ops.linear(t1, T.proj_out.w, T.proj_out.b, residual=x)
         return out, Ctx(x=x, block=bctx, samples=samples, st=st)
 
-    def _transformer_bwd(self, T, c, dout, dp_tok=None, tok_cols=()):
+    def _transformer_bwd(self, T, c, dout, dp_tok=None, tok_cols=(), dp_dense=None):
         if dout is not None:
             d_t1 = ops.linear_dgrad(dout, T.proj_out.w)
         else:
             d_t1 = None
-        d_t0 = self._block_bwd(T.block, c.block, d_t1, dp_tok=dp_tok, tok_cols=tok_cols)
+        d_t0 = self._block_bwd(T.block, c.block, d_t1, dp_tok=dp_tok, tok_cols=tok_cols, dp_dense=dp_dense)
         d_g = ops.linear_dgrad(d_t0, T.proj_in.w)
         if dout is not None:
             return ops.groupnorm_bwd(c.x, d_g, c.samples, T.norm.w, T.norm.b, 1e-6, silu=False, out=dout,
@@ -189,21 +192,29 @@ class GuidanceGraph:
 
     # ------------------------------------------------------------------------------------------ the pass
     def run(self, latents, timestep, cond_embeddings, bboxes, object_positions, guidance_attn_keys, *, loss_scale=1.0,
-            base_attn_dim=(40, 72), fg_top_p=0.2, bg_top_p=0.2, fg_weight=1.0, bg_weight=1.0, com_loss_scale=0.0):
-        """latents (1, 4, F, h, w) fp16; cond_embeddings (1, 77, D).  Returns (loss [0-d fp32 cuda, scaled by
+            return_saved_attn=False, **loss_kw):
+        """latents (1, 4, F, h, w) fp16; cond_embeddings (1, 77, D); `loss_kw` = the loss keywords of
+        utils/guidance.py::add_ca_loss_per_attn_map_to_loss (validated by utils.guidance.energy_options).  Returns (loss [0-d fp32 cuda, scaled by
         loss_scale], grad (1, 4, F, h, w) fp32 = GRAD_SCALE * d loss / d latents).
 
         Launch sequencing: the ~2100 launches of one pass are replayed from a CUDA graph from the second call with the
         same structure (shapes, guided keys, token columns, slot counts, hyper-parameters) on; latents, timestep,
         embeddings and the rasterised box tables are copied into the graph's static buffers before each replay."""
-        hp = dict(loss_scale=loss_scale, base_attn_dim=tuple(base_attn_dim), fg_top_p=fg_top_p, bg_top_p=bg_top_p,
-                  fg_weight=fg_weight, bg_weight=bg_weight, com_loss_scale=com_loss_scale)
+        opts, pre = energy_options(loss_kw, with_pre=True)
         tok_cols = tuple(int(t) for obj in object_positions for t in obj)
+        # dense form: the guided maps are materialised and dE/dP travels as a dense map -- needed by the map
+        # pre-processing variants, by more than 16 (object, token) slots, and when the caller wants the maps back
+        dense = bool(pre.active or len(tok_cols) > 16 or return_saved_attn)
+        hp = dict(opts=opts, pre=pre, dense=dense, loss_scale=float(loss_scale),
+                  base_attn_dim=tuple(loss_kw.get("base_attn_dim", (40, 72))))
         if (not self.use_cuda_graph or ops.PROF is not None or torch.cuda.is_current_stream_capturing() or
-                len(bboxes) == 0 or len(tok_cols) == 0):
+                len(bboxes) == 0 or len(tok_cols) == 0 or return_saved_attn):
+            self.saved_attn = {} if return_saved_attn else None
             return self._run_impl(latents, timestep, cond_embeddings, bboxes, object_positions, guidance_attn_keys, **hp)
+        self.saved_attn = None
         key = (tuple(latents.shape), tuple(cond_embeddings.shape), tuple(tuple(k) for k in guidance_attn_keys),
-               tuple(tuple(int(t) for t in obj) for obj in object_positions), tuple(sorted(hp.items())))
+               tuple(tuple(int(t) for t in obj) for obj in object_positions), tuple(sorted(opts.items())),
+               repr(sorted(pre.items())), dense, hp["loss_scale"], hp["base_attn_dim"])
         ent = self._graphs.get(key)
         if ent is None:  # first sighting: eager (also warms the allocator, kernel attributes and transposed weights)
             self._graphs[key] = "seen"
@@ -243,8 +254,7 @@ class GuidanceGraph:
             wts.copy_(nw_, non_blocking=True)
 
     def _run_impl(self, latents, timestep, cond_embeddings, bboxes, object_positions, guidance_attn_keys, *,
-                  loss_scale=1.0, base_attn_dim=(40, 72), fg_top_p=0.2, bg_top_p=0.2, fg_weight=1.0, bg_weight=1.0,
-                  com_loss_scale=0.0, slots=None):
+                  opts, pre, dense=False, loss_scale=1.0, base_attn_dim=(40, 72), slots=None):
         cfg, w, dev = self.cfg, self.w, self.dev
         boc = list(cfg["block_out_channels"])
         nb = len(boc)
@@ -262,7 +272,7 @@ class GuidanceGraph:
         tok_cols = tuple(int(t) for obj in object_positions for t in obj)
         if n_obj == 0 or len(tok_cols) == 0:
             return loss, torch.zeros(latents.shape, dtype=torch.float32, device=dev)
-        assert len(tok_cols) <= 16, "at most 16 (object, token) pairs per guidance call"
+        assert dense or len(tok_cols) <= 16
         if torch.is_tensor(timestep) and timestep.is_cuda and timestep.dtype == torch.float32 and \
                 timestep.numel() == frames:
             t = timestep  # pre-expanded device tensor (graph replay: the value is read at run time)
@@ -295,7 +305,8 @@ class GuidanceGraph:
                 key = (kind, stage, j, 0)
                 is_last = key == last_key
                 x, c = self._transformer_fwd(L.attn, x, spatial=True, n_img=n_img, hw=hw, batch=1, frames=frames,
-                                             ctx_kv=ctx_kv, tok_cols=tok_cols, want_tok=key in keys, last=is_last)
+                                             ctx_kv=ctx_kv, tok_cols=tok_cols, want_tok=key in keys, last=is_last,
+                                             dense=dense)
                 tape.append(("attn", L.attn, c, key if key in keys else None))
                 if is_last:
                     done = True
@@ -330,7 +341,8 @@ class GuidanceGraph:
             tape.append(("tconv", M.tconv0, c, None))
             key = ("mid", 0, 0, 0)
             x, c = self._transformer_fwd(M.attn, x, spatial=True, n_img=n_img, hw=hw, batch=1, frames=frames,
-                                         ctx_kv=ctx_kv, tok_cols=tok_cols, want_tok=key in keys, last=key == last_key)
+                                         ctx_kv=ctx_kv, tok_cols=tok_cols, want_tok=key in keys, last=key == last_key,
+                                         dense=dense)
             tape.append(("attn", M.attn, c, key if key in keys else None))
             done = key == last_key
         if not done:
@@ -369,24 +381,32 @@ class GuidanceGraph:
             if kind == "attn" and key is not None:
                 bc = c.block
                 H, W = get_hw_from_attn_dim(attn_dim=bc.hw, base_attn_dim=base_attn_dim)
+                H, W = int(H * pre.upsample_scale), int(W * pre.upsample_scale)
                 if slots is not None and (H, W) in slots:  # static tables of a captured graph
-                    _, boxes, wts_slot = slots[(H, W)]
+                    tabs = slots[(H, W)]
                 else:
                     tabs = build_slots(bboxes, object_positions, frames, H, W, dev)
                     if slots is not None:
                         slots[(H, W)] = tabs
-                    _, boxes, wts_slot = tabs
+                if dense:
+                    seeds[key] = map_energy(bc.p_full, loss, bboxes, object_positions, base_attn_dim, opts, pre,
+                                            out_scale=out_scale, want_grad=True, grad_scale=GRAD_SCALE, tables=tabs)
+                    if getattr(self, "saved_attn", None) is not None:
+                        self.saved_attn[key] = bc.p_full
+                    continue
+                _, boxes, wts_slot = tabs
                 dp = torch.empty_like(bc.p_tok)
                 ops.box_energy(bc.p_tok, loss, boxes, wts_slot, frames=frames, heads=bc.heads, H=H, W=W,
-                               fg_top_p=fg_top_p, bg_top_p=bg_top_p, fg_weight=fg_weight, bg_weight=bg_weight,
-                               com_loss_scale=com_loss_scale, out_scale=out_scale, dp=dp, grad_scale=GRAD_SCALE)
+                               out_scale=out_scale, dp=dp, grad_scale=GRAD_SCALE, **opts)
                 seeds[key] = dp
 
         # ---------------- backward
         gskip = {}
         d = None
         for kind, wts, c, extra in reversed(tape):
-            if kind == "attn":
+            if kind == "attn" and dense:
+                d = self._transformer_bwd(wts, c, d, dp_dense=seeds.get(extra))
+            elif kind == "attn":
                 d = self._transformer_bwd(wts, c, d, dp_tok=seeds.get(extra), tok_cols=tok_cols if extra else ())
             elif kind == "tattn":
                 d = self._transformer_bwd(wts, c, d)

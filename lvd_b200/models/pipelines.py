@@ -12,19 +12,18 @@ import torch
 
 from .. import ops
 from ..guidance_engine import GRAD_SCALE, GuidanceGraph
-from ..utils.guidance import _check_kwargs
-
-_graphs = {}
-
+from ..utils.guidance import energy_options
 
 def _graph_for(unet):
+    """The guidance pass of an engine lives ON the engine object (captured graphs and their activations are released
+    with it)."""
     eng = getattr(unet, "_engine", unet)
     if eng is None:
         raise RuntimeError("UNet3DConditionModel has no weights loaded")
-    g = _graphs.get(id(eng))
+    g = getattr(eng, "_guidance_graph", None)
     if g is None:
         g = GuidanceGraph(eng)
-        _graphs[id(eng)] = g
+        eng._guidance_graph = g
     return g
 
 
@@ -32,14 +31,15 @@ def latent_backward_guidance(scheduler, unet, cond_embeddings, index, bboxes, ob
                              loss_scale=30, loss_threshold=0.2, max_iter=5, max_index_step=10,
                              cross_attention_kwargs=None, guidance_attn_keys=None, verbose=False,
                              return_saved_attn=False, clear_cache=False, **kwargs):
-    """return_saved_attn is not supported by the native path (the maps are never materialised); everything else
-    follows models/pipelines.py:21-150."""
-    if return_saved_attn:
-        raise NotImplementedError("lvd_b200 latent_backward_guidance does not materialise attention maps; call "
-                                  "UNet3DConditionModel.forward with save_attn_to_dict for visualisation")
-    if cross_attention_kwargs:
-        raise NotImplementedError("extra cross_attention_kwargs on the guidance pass are not supported")
-    _check_kwargs(kwargs)
+    """models/pipelines.py:21-150.  `return_saved_attn` ("first" / "last", :86-98) makes the pass materialise the guided
+    maps and returns them on the CPU like the reference; `cross_attention_kwargs` may carry the map-saving keys the
+    runners pass along (they are overridden by the guidance pass's own, :66-72) -- anything that would change the forward
+    (gligen, attn_process_fn) is not part of this path in the reference runners and raises."""
+    for k in (cross_attention_kwargs or {}):
+        if k not in ("save_attn_to_dict", "save_keys", "offload_cross_attn_to_cpu", "enable_flash_attn"):
+            raise NotImplementedError(f"cross_attention_kwargs[{k!r}] on the guidance pass is not supported")
+    saved_to_return = None
+    energy_options(kwargs)  # validates the loss keywords (same errors as the reference's own assertions)
     iteration = 0
     if not torch.is_tensor(loss):
         loss = torch.tensor(float(loss))
@@ -53,11 +53,16 @@ def latent_backward_guidance(scheduler, unet, cond_embeddings, index, bboxes, ob
         t_int = int(t)
         while loss.item() / loss_scale > loss_threshold and iteration < max_iter and index < max_index_step:
             x = scheduler.scale_model_input(latents, t)
+            if return_saved_attn and return_saved_attn not in ("first", "last"):
+                raise ValueError(return_saved_attn)  # :97-98
+            want_maps = (return_saved_attn == "first" and iteration == 0) or \
+                        (return_saved_attn == "last" and iteration == max_iter - 1)
             loss, grad = graph.run(x, t, cond_embeddings, bboxes, object_positions, guidance_attn_keys,
-                                   loss_scale=loss_scale, base_attn_dim=kwargs.get("base_attn_dim", (40, 72)),
-                                   fg_top_p=kwargs.get("fg_top_p", 0.2), bg_top_p=kwargs.get("bg_top_p", 0.2),
-                                   fg_weight=kwargs.get("fg_weight", 1.0), bg_weight=kwargs.get("bg_weight", 1.0),
-                                   com_loss_scale=kwargs.get("com_loss_scale", 0.0))
+                                   loss_scale=loss_scale, return_saved_attn=want_maps, **kwargs)
+            if want_maps:
+                saved_to_return = {k: v.detach().cpu() for k, v in graph.saved_attn.items()}
+            if torch.isnan(loss):
+                print("**Loss is NaN**")
             if hasattr(scheduler, "alphas_cumprod"):
                 warnings.warn("Using guidance scaled with alphas_cumprod")
                 alpha_prod_t = float(scheduler.alphas_cumprod[t_int])
@@ -71,4 +76,9 @@ def latent_backward_guidance(scheduler, unet, cond_embeddings, index, bboxes, ob
             if verbose:
                 print(f"time index {index}, loss: {loss.item()/loss_scale:.3f}, loss threshold: {loss_threshold:.3f}, "
                       f"iteration: {iteration}")
+    if return_saved_attn:
+        if saved_to_return is None:  # the reference's local is unbound when the selected iteration never ran (:148-149)
+            raise UnboundLocalError("cannot access local variable 'saved_attn_to_return' where it is not associated "
+                                    "with a value")
+        return latents, loss, saved_to_return
     return latents, loss

@@ -430,9 +430,13 @@ def copy_rows(x, out):
 
 
 # ----------------------------------------------------------------------------------------------- box energy
+LOSS_MAX, LOSS_RATIO, LOSS_CE = 0, 1, 2
+
+
 def box_energy(p, loss, boxes, slot_weight, *, frames, heads, H, W, slot_col=None, n_text=0, fg_top_p=0.2,
                bg_top_p=0.2, fg_weight=1.0, bg_weight=1.0, com_loss_scale=0.0, out_scale=1.0, dp=None,
-               grad_scale=1.0):
+               grad_scale=1.0, loss_kind=LOSS_MAX, k_min=1, eps=1.0e-2, attn_sync_weight=0.0, boxdiff_loss_scale=0.0,
+               boxdiff_normed=True, boxdiff_L=1):
     """Accumulate the box energy of one attention map into `loss` (0-d fp32 CUDA tensor) and optionally write
     grad_scale * dE/dP into `dp`.  slot_col given -> `p` is the full map [F, heads, hw, n_text]; otherwise `p` holds
     token columns [n_slots, F, heads, hw]."""
@@ -452,9 +456,89 @@ def box_energy(p, loss, boxes, slot_weight, *, frames, heads, H, W, slot_col=Non
     d.fg_top_p, d.bg_top_p = float(fg_top_p), float(bg_top_p)
     d.fg_weight, d.bg_weight = float(fg_weight), float(bg_weight)
     d.com_loss_scale, d.out_scale, d.grad_scale = float(com_loss_scale), float(out_scale), float(grad_scale)
+    d.loss_kind, d.k_min = int(loss_kind), int(k_min)
+    d.boxdiff_normed, d.boxdiff_L = 1 if boxdiff_normed else 0, int(boxdiff_L)
+    d.eps, d.attn_sync_weight, d.boxdiff_loss_scale = float(eps), float(attn_sync_weight), float(boxdiff_loss_scale)
     with _Timed("box_energy", 0.0, 2.0 * p.numel()):
         _lib.check(_lib.lib().lvd_box_energy(ctypes.byref(d), _stream()), "box_energy")
     return loss
+
+
+# ----------------------------------------------------------------------------------------------- energy pre-processing
+def gaussian_weights(kernel_size=3, sigma=0.5):
+    """The 3x3 depthwise kernel of utils/attn.py:112-134 (GaussianSmoothing.__init__; the exponent is
+    -((x - mean) / (2 sigma))^2 there, not the textbook -(x - mean)^2 / (2 sigma^2)), row-major, as Python floats."""
+    import math
+    if kernel_size != 3:
+        # the reference pads by exactly 1 and asserts the shape is unchanged (utils/guidance.py:213-218)
+        raise AssertionError("smooth_attn: only kernel_size=3 keeps the map shape (utils/guidance.py:218)")
+    mean = (kernel_size - 1) / 2
+    g1 = [1 / (sigma * math.sqrt(2 * math.pi)) * math.exp(-(((i - mean) / (2 * sigma)) ** 2))
+          for i in range(kernel_size)]
+    tot = sum(a * b for a in g1 for b in g1)
+    return [a * b / tot for a in g1 for b in g1]
+
+
+def _w9(weights):
+    return (ctypes.c_float * 9)(*[float(v) for v in weights])
+
+
+def attn_smooth(p, weights):
+    """p [F, heads, hw, n_text] fp16 -> blurred map of the same shape."""
+    assert p.is_cuda and p.dtype == torch.float16 and p.is_contiguous() and p.dim() == 4
+    out = torch.empty_like(p)
+    _lib.check(_lib.lib().lvd_attn_smooth(p.data_ptr(), out.data_ptr(), p.shape[0] * p.shape[1], p.shape[2], p.shape[3],
+                                          _w9(weights), _stream()), "attn_smooth")
+    return out
+
+
+def attn_smooth_bwd(d_out, weights, half_out):
+    assert d_out.dtype == torch.float32 and d_out.is_contiguous()
+    dp = torch.empty(d_out.shape, dtype=torch.float16 if half_out else torch.float32, device=d_out.device)
+    _lib.check(_lib.lib().lvd_attn_smooth_bwd(d_out.data_ptr(), dp.data_ptr(), 1 if half_out else 0,
+                                              d_out.shape[0] * d_out.shape[1], d_out.shape[2], d_out.shape[3],
+                                              _w9(weights), _stream()), "attn_smooth_bwd")
+    return dp
+
+
+def attn_renorm(p, num_tokens, scale):
+    assert p.is_cuda and p.dtype == torch.float16 and p.is_contiguous() and p.dim() == 4
+    out = torch.empty(p.shape[:3] + (num_tokens - 2,), dtype=torch.float16, device=p.device)
+    _lib.check(_lib.lib().lvd_attn_renorm(p.data_ptr(), out.data_ptr(), p.shape[0] * p.shape[1] * p.shape[2], p.shape[3],
+                                          int(num_tokens), float(scale), _stream()), "attn_renorm")
+    return out
+
+
+def attn_renorm_bwd(r_out, d_r, n_text, num_tokens, scale, half_out):
+    assert d_r.dtype == torch.float32 and d_r.is_contiguous() and r_out.is_contiguous()
+    dp = torch.empty(r_out.shape[:3] + (n_text,), dtype=torch.float16 if half_out else torch.float32,
+                     device=r_out.device)
+    _lib.check(_lib.lib().lvd_attn_renorm_bwd(r_out.data_ptr(), d_r.data_ptr(), dp.data_ptr(), 1 if half_out else 0,
+                                              r_out.shape[0] * r_out.shape[1] * r_out.shape[2], int(n_text),
+                                              int(num_tokens), float(scale), _stream()), "attn_renorm_bwd")
+    return dp
+
+
+def attn_columns(p, slot_col, h_in, w_in, h_out, w_out):
+    """p [F, heads, h_in*w_in, n_cols] -> [n_slots, F, heads, h_out*w_out] (bilinear when the sizes differ)."""
+    assert p.is_cuda and p.dtype == torch.float16 and p.is_contiguous() and slot_col.dtype == torch.int32
+    assert p.shape[2] == h_in * w_in
+    cols = torch.empty((slot_col.numel(), p.shape[0], p.shape[1], h_out * w_out), dtype=torch.float16, device=p.device)
+    _lib.check(_lib.lib().lvd_attn_columns(p.data_ptr(), slot_col.data_ptr(), cols.data_ptr(), slot_col.numel(),
+                                           p.shape[0] * p.shape[1], p.shape[3], h_in, w_in, h_out, w_out, _stream()),
+               "attn_columns")
+    return cols
+
+
+def attn_columns_bwd(d_cols, slot_col, n_cols, h_in, w_in, h_out, w_out, half_out):
+    assert d_cols.dtype == torch.float16 and d_cols.is_contiguous()
+    n_slots, frames, heads, _ = d_cols.shape
+    dm = torch.empty((frames, heads, h_in * w_in, n_cols), dtype=torch.float16 if half_out else torch.float32,
+                     device=d_cols.device)
+    _lib.check(_lib.lib().lvd_attn_columns_bwd(d_cols.data_ptr(), slot_col.data_ptr(), dm.data_ptr(),
+                                               1 if half_out else 0, n_slots, frames * heads, n_cols, h_in, w_in, h_out,
+                                               w_out, _stream()), "attn_columns_bwd")
+    return dm
 
 
 # ----------------------------------------------------------------------------------------------- GLIGEN helpers
@@ -724,7 +808,9 @@ def temporal_attention_bwd(qkv, d_o, *, heads, n_seq, frames, scale=0.125, out=N
 
 
 def cross_attention_bwd(q, kv, d_o, *, heads, nz, s_q, s_k, kv_z_div, dp_tok=None, slot_cols=(), scale=0.125, out=None,
-                        tensor_core=True):
+                        tensor_core=True, dp_dense=None):
+    """dQ of the cross-attention; dE/dP enters either as token columns (dp_tok [n_slots, nz, heads, s_q] + slot_cols) or
+    as a dense map (dp_dense [nz, heads, s_q, s_k])."""
     _check_act(q, "q")
     _check_act(kv, "kv")
     _check_act(d_o, "d_o")
@@ -732,12 +818,17 @@ def cross_attention_bwd(q, kv, d_o, *, heads, nz, s_q, s_k, kv_z_div, dp_tok=Non
     if out is None:
         out = _alloc_out(q.shape[0], c, q)
     cols = (ctypes.c_int32 * max(1, len(slot_cols)))(*[int(x) for x in slot_cols])
+    n_slots = len(slot_cols) if dp_tok is not None else 0
+    if dp_dense is not None:
+        assert dp_tok is None and dp_dense.dtype == torch.float16 and dp_dense.is_contiguous()
+        assert tuple(dp_dense.shape) == (nz, heads, s_q, s_k) and tensor_core
+        dp_tok, n_slots = dp_dense, -1
     with _Timed("attention_cross_bwd", 6.0 * nz * heads * s_q * s_k * 64, 0.0):
         _lib.check(_lib.lib().lvd_cross_attn_bwd(q.data_ptr(), q.stride(0), q.shape[1] if tensor_core else 0, kv.data_ptr(),
                                                  kv.stride(0), kv.shape[1] if tensor_core else 0, 0, c,
                                                  d_o.data_ptr(), d_o.stride(0),
                                                  dp_tok.data_ptr() if dp_tok is not None else None, cols,
-                                                 len(slot_cols) if dp_tok is not None else 0, out.data_ptr(),
+                                                 n_slots, out.data_ptr(),
                                                  out.stride(0), s_q, s_k, heads, nz, kv_z_div, float(scale), _stream()),
                    "cross_attn_bwd")
     return out

@@ -1,7 +1,8 @@
 """TEST INFRASTRUCTURE: restatement of the reference's cross-attention box-energy guidance.
 
   compute_ca_loss       <- utils/guidance.py:529-574 (compute_ca_lossv3) + :160-526 (add_ca_loss_per_attn_map_to_loss),
-                           default "max-based" top-k energy plus the centre-of-mass terms the benchmark config enables
+                           every branch: max-based / ratio / CE losses, smoothing (utils/attn.py:91-157), renorm,
+                           upsampling, attention sync, BoxDiff corner constraint, centre-of-mass terms
   scale_proportion      <- utils/utils.py:82-103     get_hw_from_attn_dim <- utils/utils.py:253-256
   guidance_step         <- models/pipelines.py:59-137 (one iteration of latent_backward_guidance: forward with
                            grad, energy, autograd.grad w.r.t. the latents, x -= sqrt(1-alpha_bar_t) * grad)
@@ -12,6 +13,7 @@ gradient with hand-written backward kernels and is compared with this.
 import math
 
 import torch
+import torch.nn.functional as F
 
 
 def scale_proportion(obj_box, H, W):
@@ -34,14 +36,42 @@ def _center_of_mass(x, h_range, w_range):
     return com_h, com_w
 
 
+def gaussian_kernel2d(kernel_size=3, sigma=0.5):
+    """utils/attn.py:112-134 (GaussianSmoothing.__init__): note the non-standard exponent -((x - mean) / (2 sigma))^2."""
+    ax = torch.arange(kernel_size, dtype=torch.float32)
+    mean = (kernel_size - 1) / 2
+    g1 = 1 / (sigma * math.sqrt(2 * math.pi)) * torch.exp(-(((ax - mean) / (2 * sigma)) ** 2))
+    k = g1[:, None] * g1[None, :]
+    return k / k.sum()
+
+
+def smooth_map(attn_map, kernel_size=3, sigma=0.5):
+    """guidance.py:209-218: the (hw x n_text) plane of every (frame, head) is reflect-padded by 1 and blurred with a
+    depthwise kernel_size x kernel_size kernel in the map's dtype -- the blur mixes neighbouring FLATTENED pixel indices
+    and neighbouring text tokens (that is what the reference computes)."""
+    n_f, heads, hw, n_text = attn_map.shape
+    w = gaussian_kernel2d(kernel_size, sigma).to(attn_map.dtype).to(attn_map.device)
+    x = F.pad(attn_map, (1, 1, 1, 1), mode="reflect")
+    return F.conv2d(x, w.view(1, 1, kernel_size, kernel_size).repeat(heads, 1, 1, 1), groups=heads)
+
+
 def ca_loss_per_map(attn_map, bboxes, object_positions, *, base_attn_dim, fg_top_p=0.2, bg_top_p=0.2, fg_weight=1.0,
-                    bg_weight=1.0, com_loss_scale=0.0):
-    """attn_map (F, heads, hw, 77).  Returns sum over objects of obj_loss / n_tokens (guidance.py:231-524)."""
+                    bg_weight=1.0, com_loss_scale=0.0, use_ratio_based_loss=False, use_max_based_loss=True,
+                    use_ce_based_loss=False, eps=1.0e-2, smooth_attn=False, kernel_size=3, sigma=0.5, upsample_scale=1,
+                    upsample_mode="bilinear", attn_renorm=False, num_tokens=None, renorm_scale=2.0,
+                    attn_sync_weight=0.0, boxdiff_loss_scale=0.0, boxdiff_normed=True, boxdiff_L=1):
+    """attn_map (F, heads, hw, 77).  Returns sum over objects of obj_loss / n_tokens (guidance.py:160-526)."""
     n_f, heads, hw, _ = attn_map.shape
-    H, W = get_hw_from_attn_dim(hw, base_attn_dim)
+    if smooth_attn:
+        attn_map = smooth_map(attn_map, kernel_size, sigma)
+    if attn_renorm:  # :220-222
+        attn_map = F.softmax(attn_map[..., 1:num_tokens - 1] * renorm_scale, dim=-1)
+    H_attn, W_attn = get_hw_from_attn_dim(hw, base_attn_dim)
+    H, W = int(H_attn * upsample_scale), int(W_attn * upsample_scale)
     dev = attn_map.device
     h_range = torch.arange(H, device=dev, dtype=attn_map.dtype)[None]
     w_range = torch.arange(W, device=dev, dtype=attn_map.dtype)[None]
+    k_min = int(upsample_scale * upsample_scale)
     loss = torch.zeros((), device=dev, dtype=torch.float32)
     for obj_idx, obj_boxes in enumerate(bboxes):
         assert n_f == len(obj_boxes)
@@ -51,18 +81,60 @@ def ca_loss_per_map(attn_map, bboxes, object_positions, *, base_attn_dim, fg_top
             mask = torch.zeros((H, W), device=dev)
             x0, y0, x1, y1 = scale_proportion(box, H, W)
             mask[y0:y1, x0:x1] = 1
+            if boxdiff_loss_scale > 0:  # :251-266
+                cmx = torch.zeros((1, W), device=dev)
+                cmy = torch.zeros((1, H), device=dev)
+                for e in (x0, x1):
+                    cmx[:, max(e - boxdiff_L, 0):min(e + boxdiff_L + 1, W)] = 1.0
+                for e in (y0, y1):
+                    cmy[:, max(e - boxdiff_L, 0):min(e + boxdiff_L + 1, H)] = 1.0
             mask_t1 = torch.zeros((H, W), device=dev)
-            x0, y0, x1, y1 = scale_proportion(obj_boxes[f1], H, W)
-            mask_t1[y0:y1, x0:x1] = 1
+            tx0, ty0, tx1, ty1 = scale_proportion(obj_boxes[f1], H, W)
+            mask_t1[ty0:ty1, tx0:tx1] = 1
             for tok in object_positions[obj_idx]:
-                ca = attn_map[f, :, :, tok]
-                ca_t1 = attn_map[f1, :, :, tok]
-                k_fg = int((mask.sum() * fg_top_p).long().clamp_(min=1))
-                k_bg = int(((1 - mask).sum() * bg_top_p).long().clamp_(min=1))
-                m1 = mask.view(1, -1)
-                obj_loss = obj_loss + (1 - (ca * m1).topk(k=k_fg).values.mean(dim=1)).sum(dim=0) * fg_weight
-                obj_loss = obj_loss + ((ca * (1 - m1)).topk(k=k_bg).values.mean(dim=1)).sum(dim=0) * bg_weight
-                if com_loss_scale > 0 and mask.sum() > 0:
+                col = tok - 1 if attn_renorm else tok  # SOT was dropped by the renormalisation (:281-285)
+                ca = attn_map[f, :, :, col]
+                ca_t1 = attn_map[f1, :, :, col]
+                if upsample_scale != 1:  # :297-311
+                    ca = F.interpolate(ca.view(heads, 1, H_attn, W_attn), size=(H, W), mode=upsample_mode)
+                    ca_t1 = F.interpolate(ca_t1.view(heads, 1, H_attn, W_attn), size=(H, W), mode=upsample_mode)
+                if use_ratio_based_loss:  # :312-323
+                    ca = ca.reshape(heads, H, W)
+                    act = (ca * mask).reshape(heads, -1).sum(dim=-1) / (ca.reshape(heads, -1).sum(dim=-1) + eps)
+                    obj_loss = obj_loss + torch.mean((1 - act) ** 2)
+                else:
+                    k_fg = int((mask.sum() * fg_top_p).long().clamp_(min=k_min))
+                    k_bg = int(((1 - mask).sum() * bg_top_p).long().clamp_(min=k_min))
+                    m1 = mask.view(1, -1)
+                    ca = ca.reshape(heads, -1)
+                    if use_max_based_loss:  # :341-353
+                        obj_loss = obj_loss + (1 - (ca * m1).topk(k=k_fg).values.mean(dim=1)).sum(dim=0) * fg_weight
+                        obj_loss = obj_loss + ((ca * (1 - m1)).topk(k=k_bg).values.mean(dim=1)).sum(dim=0) * bg_weight
+                    elif use_ce_based_loss:  # :363-396
+                        ca = torch.clamp(ca, min=eps, max=1 - eps)
+                        fg = (-torch.log(torch.clamp((m1 * ca).topk(k=k_fg).values, min=eps))).mean(dim=1).sum(dim=0)
+                        bg = -torch.log(1 - ((1 - m1) * ca).topk(k=k_bg).values.mean(dim=1)).sum(dim=0)
+                        obj_loss = obj_loss + fg * fg_weight + bg * bg_weight
+                    else:
+                        raise ValueError("Unknown loss: no loss selected")
+                if attn_sync_weight != 0.0:  # :401-426
+                    assert not attn_renorm, "attn_sync with attn_renorm not implemented together"
+                    if f != len(obj_boxes) - 1:
+                        # the crop is the NEXT frame's rectangle: the reference's x_min..y_max were last assigned in
+                        # its loop over frame_boxes_t1 (:268-271) when the sync term reads them (:414-418)
+                        a1 = ca.view(heads, H_attn, W_attn)[:, ty0:ty1, tx0:tx1]
+                        a2 = attn_map[f + 1, :, :, tok].view(heads, H_attn, W_attn)[:, ty0:ty1, tx0:tx1]
+                        obj_loss = obj_loss + ((a1 - a2) ** 2).mean(dim=(1, 2)).sum(dim=0) * attn_sync_weight
+                if boxdiff_loss_scale > 0:  # :433-465
+                    c3 = ca.view(heads, H, W)
+                    mx_x = c3.max(dim=1).values.to(torch.float32)
+                    mx_y = c3.max(dim=2).values.to(torch.float32)
+                    mm_x = mask[None].max(dim=1).values
+                    mm_y = mask[None].max(dim=2).values
+                    red = (lambda t: t.mean()) if boxdiff_normed else (lambda t: t.sum())
+                    cc = red((mx_x - mm_x).abs() * cmx) + red((mx_y - mm_y).abs() * cmy)
+                    obj_loss = obj_loss + cc * boxdiff_loss_scale
+                if com_loss_scale > 0 and mask.sum() > 0:  # :468-522
                     ca2 = ca.view(heads, H, W).to(torch.float32)
                     ch, cw = _center_of_mass(ca2, h_range, w_range)
                     mh, mw = _center_of_mass(mask[None], h_range, w_range)

@@ -1,0 +1,85 @@
+"""Every loss branch of utils/guidance.py::add_ca_loss_per_attn_map_to_loss against golden vectors that the REFERENCE
+produced (tests/golden/energy_variants.npz; generator oracle/make_golden_energy.py: reference compute_ca_lossv3 +
+torch.autograd for dLoss/dP on seeded maps):
+
+  * CPU (`-m "not gpu"`): the oracle restatement (oracle/guidance_ref.py) reproduces loss and gradient of all 27 cases;
+  * GPU: the product (`lvd_b200.utils.guidance.compute_ca_lossv3` -> lvd_box_energy, and the pre-processing kernels for
+    smoothing / renormalisation / upsampling) reproduces them: loss to 2e-4 relative, dLoss/dP to 2e-3 of its max
+    (the kernel does fp32 math on the same fp16-representable probabilities; fp16 only in the emitted gradient).
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import guidance_ref as R
+from oracle.make_golden_energy import KEYS, POSITIONS, cases, make_maps
+
+GOLD = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "energy_variants.npz"))
+CASES = list(cases())
+
+
+def _oracle_kw(kw):
+    return {k: v for k, v in kw.items()}
+
+
+@pytest.mark.parametrize("idx", range(len(CASES)))
+def test_oracle_matches_reference_goldens(idx):
+    name, kw, bboxes = CASES[idx]
+    maps = {k: v.clone().requires_grad_(True) for k, v in make_maps(100 + idx).items()}
+    loss = R.compute_ca_loss(maps, bboxes, POSITIONS, KEYS, **_oracle_kw(kw))
+    ref = float(GOLD[name + "__loss"])
+    assert abs(loss.item() - ref) <= 1e-5 * abs(ref), (name, loss.item(), ref)
+    grads = torch.autograd.grad(loss, [maps[k] for k in KEYS])
+    for k, g in zip(KEYS, grads):
+        gr = torch.from_numpy(GOLD[name + "__grad_" + "_".join(map(str, k))])
+        assert (g - gr).abs().max().item() <= 1e-5 * gr.abs().max().item() + 1e-9, (name, k)
+
+
+def test_oracle_sync_with_empty_box_is_nan_like_the_reference():
+    from oracle.make_golden_energy import BASE_KW, LAYOUTS
+    assert np.isnan(GOLD["sync__absent__loss"])
+    loss = R.compute_ca_loss(make_maps(999), LAYOUTS["absent"], POSITIONS, KEYS, **dict(BASE_KW, attn_sync_weight=1.0))
+    assert torch.isnan(loss)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("idx", range(len(CASES)))
+def test_kernel_matches_reference_goldens(cuda, idx):
+    from lvd_b200.utils import guidance as G
+    name, kw, bboxes = CASES[idx]
+    maps = {k: v.half().to(cuda) for k, v in make_maps(100 + idx).items()}
+    ref = float(GOLD[name + "__loss"])
+    loss = G.compute_ca_lossv3(maps, bboxes, POSITIONS, KEYS, **kw)
+    assert abs(loss.item() - ref) <= 2e-4 * abs(ref), (name, loss.item(), ref)
+    loss2, grads = G.compute_ca_lossv3_with_grad(maps, bboxes, POSITIONS, KEYS, grad_scale=256.0, **kw)
+    assert abs(loss2.item() - ref) <= 2e-4 * abs(ref)
+    for k in KEYS:
+        gr = torch.from_numpy(GOLD[name + "__grad_" + "_".join(map(str, k))]).to(cuda)
+        g = grads[k].float() / 256.0
+        assert g.shape == gr.shape
+        err = (g - gr).abs().max().item()
+        assert err <= 2e-3 * gr.abs().max().item(), (name, k, err, gr.abs().max().item())
+
+
+@pytest.mark.gpu
+def test_kernel_sync_with_empty_box_is_nan_like_the_reference(cuda):
+    from lvd_b200.utils import guidance as G
+    from oracle.make_golden_energy import BASE_KW, LAYOUTS
+    maps = {k: v.half().to(cuda) for k, v in make_maps(999).items()}
+    loss = G.compute_ca_lossv3(maps, LAYOUTS["absent"], POSITIONS, KEYS, **dict(BASE_KW, attn_sync_weight=1.0))
+    assert torch.isnan(loss)
+
+
+def test_option_validation_matches_reference_errors():
+    from lvd_b200.utils.guidance import energy_options
+    with pytest.raises(AssertionError, match="deprecated"):
+        energy_options(dict(exclude_bg_heads=True))
+    with pytest.raises(ValueError, match="no loss selected"):
+        energy_options(dict(use_max_based_loss=False))
+    with pytest.raises(TypeError):
+        energy_options(dict(not_an_option=1))
+    o = energy_options(dict(use_ratio_based_loss=1, boxdiff_loss_scale=0.5, boxdiff_normed=0, verbose=True,
+                            upsample_mode="bilinear", base_attn_dim=(32, 32)))
+    assert o["loss_kind"] == 1 and o["boxdiff_normed"] is False and o["boxdiff_loss_scale"] == 0.5

@@ -134,3 +134,95 @@ def test_guidance_pass_graph_replay_matches_eager(cuda):
         assert abs(l0.item() - l1.item()) <= 1e-5 * abs(l0.item()) + 1e-7, (i, l0.item(), l1.item())
         assert torch.equal(g0, g1), i
     assert sum(1 for v in graphed._graphs.values() if v != "seen") == 1
+
+
+VARIANT_KW = {
+    "ratio_boxdiff": dict(use_ratio_based_loss=True, boxdiff_loss_scale=0.7, boxdiff_normed=True),
+    "boxdiff_sum": dict(fg_top_p=0.5, bg_top_p=0.5, boxdiff_loss_scale=0.2, boxdiff_normed=False, boxdiff_L=2),
+    "sync_com": dict(fg_top_p=0.5, bg_top_p=0.5, attn_sync_weight=3.0, com_loss_scale=0.02),
+    "ce": dict(use_max_based_loss=False, use_ce_based_loss=True, fg_top_p=0.5, bg_top_p=0.5),
+    "smooth": dict(fg_top_p=0.5, bg_top_p=0.5, smooth_attn=True, com_loss_scale=0.02),
+    "renorm": dict(fg_top_p=0.5, bg_top_p=0.5, attn_renorm=True, num_tokens=12),
+    "upsample2_ratio": dict(use_ratio_based_loss=True, upsample_scale=2, boxdiff_loss_scale=0.3),
+    "many_tokens": dict(fg_top_p=0.5, bg_top_p=0.5),
+}
+
+
+@pytest.mark.parametrize("variant", sorted(VARIANT_KW))
+def test_guidance_loss_variants_end_to_end(cuda, variant):
+    """Every loss branch of utils/guidance.py through the whole native pass (forward prefix, energy incl. the map
+    pre-processing kernels, hand-written backward to the latents) against the oracle's autograd.  The dense dE/dP form is
+    exercised by smooth / renorm / upsample and by a layout with 18 (object, token) slots."""
+    from lvd_b200.engine import UNetEngine
+    from lvd_b200.guidance_engine import GRAD_SCALE, GuidanceGraph
+    from oracle import guidance_ref as G
+    from oracle import weights
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    cfg = weights.make_cfg("tiny")
+    sd = weights.random_state_dict(cfg, seed=51)
+    eng = UNetEngine(cfg, sd, device=cuda)
+    gen = torch.Generator().manual_seed(52)
+    F, h, w = 6, 16, 24
+    x = torch.randn((1, 4, F, h, w), generator=gen).half().to(cuda)
+    ehs = torch.randn((1, 77, 128), generator=gen).half().to(cuda)
+    bboxes = [[(0.1 + 0.05 * f, 0.2, 0.55 + 0.05 * f, 0.7) for f in range(F)],
+              [(0.5, 0.45, 0.95, 0.95 - 0.03 * f) for f in range(F)]]
+    positions = [[3], [5, 6]] if variant != "many_tokens" else [list(range(1, 10)), list(range(10, 19))]
+    keys = [("down", 1, 0, 0), ("down", 2, 1, 0), ("up", 1, 1, 0), ("up", 2, 2, 0)]
+    kw = dict(fg_weight=1.0, bg_weight=2.0, base_attn_dim=(h, w), **VARIANT_KW[variant])
+    gg = GuidanceGraph(eng)
+    loss, grad = gg.run(x, 400, ehs, bboxes, positions, keys, loss_scale=4.0, **kw)
+    sd32 = {k: v.half().float().to(cuda) for k, v in sd.items()}
+    _, ref_loss, ref_grad, _ = G.guidance_step(sd32, cfg, x.float(), 400, ehs.float(), bboxes, positions,
+                                               torch.tensor(0.5), guidance_attn_keys=keys, loss_scale=4.0, **kw)
+    cos, rel = _cmp(grad / GRAD_SCALE, ref_grad)
+    print(f"\n[guidance variant {variant}] loss {loss.item():.4f} / {ref_loss.item():.4f}  grad cos {cos:.5f} rel {rel:.4f}")
+    assert abs(loss.item() - ref_loss.item()) <= 1e-3 * abs(ref_loss.item())
+    assert cos >= 0.995 and rel <= 0.10
+    # graph replay of the same structure gives the same numbers
+    l2, g2 = gg.run(x, 400, ehs, bboxes, positions, keys, loss_scale=4.0, **kw)
+    l3, g3 = gg.run(x, 400, ehs, bboxes, positions, keys, loss_scale=4.0, **kw)
+    assert abs(l3.item() - loss.item()) <= 1e-5 * abs(loss.item()) and torch.equal(g3, grad) and torch.equal(g2, grad)
+
+
+def test_latent_backward_guidance_returns_saved_attn(cuda):
+    """`return_saved_attn="first"` (models/pipelines.py:86-98,148-150): the guided maps come back on the CPU, keyed like
+    the reference's, and match the oracle's saved maps; invalid selectors raise like the reference."""
+    from lvd_b200.engine import UNetEngine
+    from lvd_b200.models.pipelines import latent_backward_guidance
+    from oracle import unet3d_ref as R
+    from oracle import weights
+    from oracle.make_golden import FakeScheduler
+    cfg = weights.make_cfg("tiny")
+    sd = weights.random_state_dict(cfg, seed=61)
+    eng = UNetEngine(cfg, sd, device=cuda)
+    gen = torch.Generator().manual_seed(62)
+    F, h, w = 4, 16, 16
+    x = torch.randn((1, 4, F, h, w), generator=gen).half().to(cuda)
+    ehs = torch.randn((1, 77, 128), generator=gen).half().to(cuda)
+    bboxes, positions = [[(0.1, 0.2, 0.6, 0.7)] * F], [[3]]
+    keys = R.GUIDANCE_KEYS_DEFAULT
+    kw = dict(loss_scale=2.5, loss_threshold=0.0, max_iter=2, max_index_step=10, guidance_attn_keys=keys,
+              base_attn_dim=(h, w), fg_top_p=0.25, bg_top_p=0.25,
+              cross_attention_kwargs={"save_attn_to_dict": {}, "save_keys": []})
+    lat, loss, saved = latent_backward_guidance(FakeScheduler(), eng, ehs, 0, bboxes, positions, 500, x,
+                                                torch.tensor(10000.0), return_saved_attn="first", **kw)
+    lat0, loss0 = latent_backward_guidance(FakeScheduler(), eng, ehs, 0, bboxes, positions, 500, x,
+                                           torch.tensor(10000.0), **kw)
+    assert abs(loss.item() - loss0.item()) <= 1e-4 * abs(loss0.item())
+    assert ((lat.float() - lat0.float()).norm() / (lat0.float() - x.float()).norm()).item() < 0.05
+    ref_saved = {}
+    with torch.no_grad():
+        R.unet_forward({k: v.half().float().to(cuda) for k, v in sd.items()}, cfg, x.float(), 500, ehs.float(),
+                       save_keys=keys, saved=ref_saved)
+    assert sorted(saved) == sorted(tuple(k) for k in keys)
+    for k in keys:
+        assert saved[k].device.type == "cpu" and saved[k].shape == ref_saved[k].shape
+        assert (saved[k].float() - ref_saved[k].cpu()).abs().max().item() < 3e-3
+    with pytest.raises(ValueError):
+        latent_backward_guidance(FakeScheduler(), eng, ehs, 0, bboxes, positions, 500, x, torch.tensor(10000.0),
+                                 return_saved_attn=True, **kw)
+    with pytest.raises(UnboundLocalError):  # selected iteration never runs: the reference's local is unbound
+        latent_backward_guidance(FakeScheduler(), eng, ehs, 0, bboxes, positions, 500, x, torch.tensor(0.0),
+                                 return_saved_attn="first", **kw)
