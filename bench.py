@@ -14,11 +14,18 @@ Contract notes
               the updated latents copied D2H inside the timed region, every step.
   * L2      : the step streams 2.8 GB of weights and >20 GB of activations, far larger than the 126 MB L2, so no
               explicit flush is needed between timed iterations (config.l2 says so).
+  * warm-up : exactly --warmup steps run before the timed region.  CUDA-graph capture of the step variants happens in
+              an untimed SETUP phase ahead of the warm-up (config.setup), it is not counted as warm-up.
   * roofline: dominant kernel family = gemm_tc_kernel (Linear + implicit-GEMM Conv2d/Conv3d); algorithmic FLOPs of
-              every launch / its CUDA-event duration, measured in an instrumented step after the timed region.
-  * cpu_baseline / --impl reference: oracle/ (the CPU restatement of the reference; the reference itself is Python
-              that needs diffusers, not installable offline) on a bounded sample: the same CFG step on 2 of the 24
-              frames with the full 1.41 B-parameter UNet, fp32, all host threads.
+              every launch / its duration measured by CUDA events that are nodes of the replayed graphs themselves
+              (`external` events captured around every kernel node), over a region of --steps instrumented replays
+              of the same step sequence right after the headline region (roofline.region).
+  * cpu_baseline / --impl reference: oracle/ (the CPU restatement of the reference, pinned against the reference
+              executed verbatim; the reference itself needs diffusers, not installable offline), fp32, the host threads
+              a probe finds fastest, ONE code path for both: the same step mix on a bounded sample = the first
+              `sample_frames` of the 24 frames with the full 1.41 B-parameter UNet; sample_frames is the largest of
+              {24, 12, 8, 4, 2} whose --steps + --warmup steps fit the CPU time budget (--cpu-budget-s), so a short run
+              (--steps 2 --warmup 0) times the full 24-frame configuration.
 """
 import argparse
 import json
@@ -67,7 +74,12 @@ def parse():
                     help="BASELINE.json config: lvd_zeroscope is the headline (config 2)")
     ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-sample-frames", type=int, default=2)
+    ap.add_argument("--cpu-sample-frames", type=int, default=0,
+                    help="frames of the CPU arm's bounded sample (0 = largest of 24/12/8/4/2 fitting --cpu-budget-s)")
+    ap.add_argument("--cpu-budget-s", type=float, default=240.0, help="wall-clock budget of the CPU arm")
+    ap.add_argument("--no-prompt-batch", action="store_true",
+                    help="skip the prompt-batch measurement (parallel.generate_sharded: scatter + videos + gather)")
+    ap.add_argument("--batch-prompts-per-gpu", type=int, default=3)
     ap.add_argument("--profile-json", default=None, help="write the per-kernel-family breakdown here")
     ap.add_argument("--no-video", action="store_true",
                     help="skip the secondary end-to-end measurement (one full 50-step video + VAE decode)")
@@ -149,10 +161,13 @@ def pick_cpu_threads():
     return best
 
 
-def cpu_reference_step(sample_frames, steps, warmup, guided_every=GUIDED_EVERY):
-    """The reference algorithm (oracle/ restatement, fp32, all host threads) on a bounded sample of the workload:
-    the same step pattern (guided iff i % 5 == 0) on `sample_frames` of the 24 frames, full-size UNet.
-    Returns (frames/s, mean seconds/step, cores, seconds of a guided step, seconds of an unguided step)."""
+def cpu_reference_step(sample_frames, pattern, warmup, budget_s=240.0):
+    """The reference algorithm (oracle/ restatement, fp32, host threads) on a bounded sample of the workload: the step
+    kinds listed in `pattern` (True = guided step, False = unguided), after `warmup` untimed steps, on the first
+    `sample_frames` of the 24 frames with the full-size UNet.  sample_frames == 0: one untimed 2-frame probe step of each
+    kind in `pattern` sizes the sample to the largest of {24, 12, 8, 4, 2} frames whose steps fit `budget_s` (cost is
+    linear in the frame count: every layer is per-frame work or attention over the frame axis of fixed width).
+    Returns dict(frames_per_s, sec_per_step, cores, sec_guided, sec_unguided, sample_frames, steps, warmup)."""
     import torch
     from oracle import guidance_ref, scheduler_ref
     from oracle import unet3d_ref as R
@@ -162,34 +177,66 @@ def cpu_reference_step(sample_frames, steps, warmup, guided_every=GUIDED_EVERY):
     torch.set_num_threads(cores)
     cfg = weights.make_cfg("zeroscope")
     sd = weights.random_state_dict(cfg, seed=0)
-    g = torch.Generator().manual_seed(1)
-    lat = torch.randn((1, 4, sample_frames, LAT_H, LAT_W), generator=g)
-    ehs = torch.randn((2, 77, 1024), generator=g)
     sched = scheduler_ref.DPMSolverRef()
-    sched.set_timesteps(50)
-    bboxes, positions = bear_layout(sample_frames)
-    t_g, t_u = [], []
-    for it in range(warmup + steps):
-        t0 = time.perf_counter()
-        tt = int(sched.timesteps[min(it, 49)])
-        guided = guided_every and (it % guided_every == 0)
-        if guided:
-            lat, _, _, _ = guidance_ref.guidance_step(sd, cfg, lat, tt, ehs[1:], bboxes, positions,
-                                                      sched.alphas_cumprod[tt], guidance_attn_keys=GUIDANCE_KEYS,
-                                                      loss_scale=GUIDANCE_LOSS_SCALE, base_attn_dim=(LAT_H, LAT_W),
-                                                      **GUIDANCE_HP)
-        with torch.no_grad():
-            x = torch.cat([lat, lat], 0)
-            eps = R.unet_forward(sd, cfg, x, tt, ehs)
-            e = scheduler_ref.cfg_combine(eps[:1], eps[1:], GUIDANCE_SCALE)
-            lat = sched.step(e, lat)
-        dt = time.perf_counter() - t0
-        if it >= warmup:
-            (t_g if guided else t_u).append(dt)
-    sec_g = sum(t_g) / len(t_g) if t_g else None
-    sec_u = sum(t_u) / len(t_u) if t_u else None
-    sec = (sum(t_g) + sum(t_u)) / (len(t_g) + len(t_u))
-    return sample_frames / sec, sec, cores, sec_g, sec_u
+
+    def run(frames, kinds):
+        sched.set_timesteps(50)
+        g = torch.Generator().manual_seed(1)
+        lat = torch.randn((1, 4, frames, LAT_H, LAT_W), generator=g)
+        ehs = torch.randn((2, 77, 1024), generator=g)
+        bboxes, positions = bear_layout(frames)
+        times = []
+        for it, guided in enumerate(kinds):
+            t0 = time.perf_counter()
+            if sched.step_index is not None and sched.step_index >= 49:
+                sched.set_timesteps(50)
+            tt = int(sched.timesteps[it % 50])
+            if guided:
+                lat, _, _, _ = guidance_ref.guidance_step(sd, cfg, lat, tt, ehs[1:], bboxes, positions,
+                                                          sched.alphas_cumprod[tt], guidance_attn_keys=GUIDANCE_KEYS,
+                                                          loss_scale=GUIDANCE_LOSS_SCALE, base_attn_dim=(LAT_H, LAT_W),
+                                                          **GUIDANCE_HP)
+            with torch.no_grad():
+                x = torch.cat([lat, lat], 0)
+                eps = R.unet_forward(sd, cfg, x, tt, ehs)
+                e = scheduler_ref.cfg_combine(eps[:1], eps[1:], GUIDANCE_SCALE)
+                lat = sched.step(e, lat)
+            times.append(time.perf_counter() - t0)
+        return times
+
+    all_kinds = [pattern[i % len(pattern)] for i in range(warmup)] + list(pattern)
+    if sample_frames <= 0:
+        probe_kinds = sorted(set(all_kinds), reverse=True)
+        probe = dict(zip(probe_kinds, run(2, probe_kinds)))  # also the first-touch cost of the weights
+        probe = dict(zip(probe_kinds, run(2, probe_kinds)))
+        per_frame = sum(probe[k] for k in all_kinds) / 2.0
+        sample_frames = 2
+        try:
+            import psutil
+            free_gb = psutil.virtual_memory().available / 2 ** 30
+        except Exception:
+            free_gb = 64.0
+        for f in (24, 12, 8, 4):
+            # a guided step keeps ~2.6 GB of fp32 autograd state per frame
+            if per_frame * f <= budget_s and (not any(all_kinds) or 2.6 * f + 12 <= free_gb):
+                sample_frames = f
+                break
+    times = run(sample_frames, all_kinds)[warmup:]
+    t_g = [t for t, k in zip(times, pattern) if k]
+    t_u = [t for t, k in zip(times, pattern) if not k]
+    sec = sum(times) / len(times)
+    return dict(frames_per_s=sample_frames / sec, sec_per_step=sec, cores=cores,
+                sec_guided=sum(t_g) / len(t_g) if t_g else None, sec_unguided=sum(t_u) / len(t_u) if t_u else None,
+                sample_frames=sample_frames, steps=len(pattern), warmup=warmup)
+
+
+def cpu_sample_text(r):
+    full = "the full 24-frame configuration" if r["sample_frames"] == 24 else \
+        f"the first {r['sample_frames']} of the 24 frames"
+    return (f"same step mix on {full} (72x40 latent, full 1.41B-param UNet), fp32, oracle port of the reference incl. "
+            f"autograd guidance, {r['cores']} threads; guided step {r['sec_guided'] and round(r['sec_guided'], 1)} s, "
+            f"unguided step {r['sec_unguided'] and round(r['sec_unguided'], 1)} s; {r['steps']} timed + {r['warmup']} "
+            f"warm-up steps")
 
 
 # BASELINE.json configs 2-4: algorithmic TFLOP per CFG forward / guidance iteration from section 8(d)
@@ -224,18 +271,18 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    ge = 0 if args.unguided else GUIDED_EVERY
-    fps, sec, cores, sec_g, sec_u = cpu_reference_step(args.cpu_sample_frames, max(1, args.steps),
-                                                       max(0, min(args.warmup, 1)), ge)
-    sample = (f"same step pattern on {args.cpu_sample_frames} of 24 frames (72x40 latent, full 1.41B-param UNet), fp32, "
-              f"oracle port of the reference incl. autograd guidance; guided step {sec_g and round(sec_g, 1)} s, "
-              f"unguided step {sec_u and round(sec_u, 1)} s")
+    steps = max(1, args.steps)
+    pattern = [(not args.unguided) and i % GUIDED_EVERY == 0 for i in range(steps)]
+    r = cpu_reference_step(args.cpu_sample_frames, pattern, max(0, args.warmup), args.cpu_budget_s)
+    sample = cpu_sample_text(r)
+    fps = r["frames_per_s"]
     line = {
-        "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": _workload("lvd_zeroscope", args.unguided), "sample": sample},
-        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": max(0, args.warmup), "ms_per_step": r["sec_per_step"] * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": _workload("lvd_zeroscope", args.unguided), "sample": sample,
+                   "sample_frames": r["sample_frames"]},
+        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": sample},
         "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -339,7 +386,21 @@ def run_gpu(args):
         latents = sched.step_cfg(eps[0:1], eps[1:2], latents, GUIDANCE_SCALE)
 
     unet.use_cuda_graph = not args.no_graph
-    for i in range(max(3, args.warmup) + 5):  # warm-up: every (fuser on/off) variant is seen, captured and replayed once
+    # SETUP (untimed, not warm-up): two passes over the 5-step pattern -- every step variant (guided / unguided, fusers
+    # on / off) runs once eagerly and once under CUDA-graph capture, so that warm-up and timed steps are pure replays
+    SETUP_STEPS = 2 * GUIDED_EVERY
+    lib = _lib.lib()
+    c0 = lib.lvd_launch_count()
+    counts = []
+    for i in range(SETUP_STEPS):
+        denoise_step(i)
+        if i < GUIDED_EVERY:  # the eager pass: launches per step variant, counted by the library itself
+            torch.cuda.synchronize()
+            c1 = lib.lvd_launch_count()
+            counts.append(c1 - c0)
+            c0 = c1
+    torch.cuda.synchronize()
+    for i in range(args.warmup):  # exactly --warmup untimed warm-up steps
         denoise_step(i)
     torch.cuda.synchronize()
 
@@ -434,55 +495,98 @@ def run_gpu(args):
                                "prompt embeddings given (text encoder out of scope); wall clock incl. H2D / D2H"}
         del pipe, vae, out
 
-    # ---------------- instrumented passes: per-kernel-family durations (CUDA events around every launch), eager
-    lib = _lib.lib()
+    # ---------------- instrumented replay region: the same step sequence replayed from graphs that were captured with an
+    # `external` CUDA-event pair around every kernel node (ops._Timed); after each step the pairs of the graphs that
+    # replayed are read.  Kernel durations therefore come from replay conditions (no launch gaps, the clocks / power
+    # state of the steady step loop), K steps long; the event nodes themselves cost ~1.5 us each, which is why this
+    # region is separate from the headline one (its own ms/step is reported next to it).
     set_fusers(False)
-    x2 = torch.cat([latents] * 2)
-    ops.PROF = []
-    l0 = lib.lvd_launch_count()
-    eng.forward(x2, float(sched.timesteps[0]), prompt_embeds)
-    torch.cuda.synchronize()
-    launches_per_forward = lib.lvd_launch_count() - l0
-    n_fwd_records = len(ops.PROF)
-    launches_per_guidance = 0
-    if guided_every:
-        l1 = lib.lvd_launch_count()
-        latent_backward_guidance(sched, unet, prompt_embeds[1:2], index=0, t=sched.timesteps[0], latents=latents,
-                                 loss=torch.tensor(10000.0), **guidance_kw)
-        torch.cuda.synchronize()
-        launches_per_guidance = lib.lvd_launch_count() - l1
-    prof = ops.PROF
-    ops.PROF = None
-    launches_per_fused_forward = launches_per_forward
-    if wl["gated"]:
-        set_fusers(True)
-        l2 = lib.lvd_launch_count()
-        eng.forward(x2, float(sched.timesteps[0]), prompt_embeds, gligen=gl_in)
-        torch.cuda.synchronize()
-        launches_per_fused_forward = lib.lvd_launch_count() - l2
-    fam = {}
-    fam_guid = {}
-    shapes = ({}, {})
-    for k_, (name, fl, nb, s, e, tag) in enumerate(prof):
-        d = (fam if k_ < n_fwd_records else fam_guid).setdefault(name, {"ms": 0.0, "flops": 0.0, "bytes": 0.0,
-                                                                        "launches": 0})
-        if tag is not None:
-            sd = shapes[0 if k_ < n_fwd_records else 1].setdefault(tag, {"ms": 0.0, "flops": 0.0, "bytes": 0.0,
-                                                                         "launches": 0})
-            sd["ms"] += s.elapsed_time(e)
-            sd["flops"] += fl
-            sd["bytes"] += nb
-            sd["launches"] += 1
-        d["ms"] += s.elapsed_time(e)
+    gg = getattr(eng, "_guidance_graph", None)
+    fam, fam_guid, shapes = {}, {}, ({}, {})
+    region = None
+    ms_instr = None
+
+    def acc(dst, name, fl, nb, ms_, tag, shp):
+        d = dst.setdefault(name, {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "launches": 0})
+        d["ms"] += ms_
         d["flops"] += fl
         d["bytes"] += nb
         d["launches"] += 1
-    # kernels of this library launched inside timed region 1 (graph replays re-run the captured launches)
-    launches = 0
-    for i in range(args.steps):
-        launches += (launches_per_fused_forward if fusers_on(i) else launches_per_forward) + 1
-        if guided_every and i % guided_every == 0:
-            launches += launches_per_guidance
+        if tag is not None:
+            sd = shp.setdefault(tag, {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "launches": 0})
+            sd["ms"] += ms_
+            sd["flops"] += fl
+            sd["bytes"] += nb
+            sd["launches"] += 1
+
+    n_unet_steps = n_guid_steps = 0
+    if unet.use_cuda_graph:
+        try:
+            ops.PROF, ops.PROF_SCOPE = [], "bench"
+            unet._graphs.clear()
+            if gg is not None:
+                gg._graphs.clear()
+            for i in range(SETUP_STEPS):
+                denoise_step(i)
+            torch.cuda.synchronize()
+            recs = [r for r in ops.PROF if r[6] is not None]
+            ops.PROF, ops.PROF_SCOPE = None, None
+            by_scope = {}
+            for r in recs:
+                by_scope.setdefault(r[6], []).append(r)
+            for i in range(min(args.warmup, 3)):
+                denoise_step(i)
+            torch.cuda.synchronize()
+            t_instr = 0.0
+            for i in range(args.steps):
+                a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                denoise_step(i)
+                b_.record()
+                torch.cuda.synchronize()
+                t_instr += a.elapsed_time(b_)
+                guided = bool(guided_every and i % guided_every == 0)
+                for r in by_scope.get("unet:fusers" if fusers_on(i) else "unet", []):
+                    acc(fam, r[0], r[1], r[2], r[3].elapsed_time(r[4]), r[5], shapes[0])
+                n_unet_steps += 1
+                if guided:
+                    for r in by_scope.get("guidance", []):
+                        acc(fam_guid, r[0], r[1], r[2], r[3].elapsed_time(r[4]), r[5], shapes[1])
+                    n_guid_steps += 1
+            ms_instr = t_instr / args.steps
+            region = (f"{args.steps} instrumented graph replays of the timed step sequence (external CUDA-event nodes "
+                      f"around every kernel node of the replayed graphs), {ms_instr:.2f} ms/step with the event nodes")
+        except Exception as e:  # external-event timing unavailable: fall back to the eager instrumented pass below
+            sys.stderr.write(f"[bench] graph-internal event timing failed ({type(e).__name__}: {e}); eager pass instead\n")
+            fam, fam_guid, shapes = {}, {}, ({}, {})
+            n_unet_steps = n_guid_steps = 0
+            region = None
+        finally:
+            ops.PROF, ops.PROF_SCOPE = None, None
+    if region is None:
+        x2 = torch.cat([latents] * 2)
+        ops.PROF = []
+        eng.forward(x2, float(sched.timesteps[0]), prompt_embeds)
+        torch.cuda.synchronize()
+        n_fwd_records = len(ops.PROF)
+        if guided_every:
+            latent_backward_guidance(sched, unet, prompt_embeds[1:2], index=0, t=sched.timesteps[0], latents=latents,
+                                     loss=torch.tensor(10000.0), **guidance_kw)
+            torch.cuda.synchronize()
+        prof = ops.PROF
+        ops.PROF = None
+        for k_, r in enumerate(prof):
+            first = k_ < n_fwd_records
+            acc(fam if first else fam_guid, r[0], r[1], r[2], r[3].elapsed_time(r[4]), r[5], shapes[0 if first else 1])
+        n_unet_steps, n_guid_steps = 1, (1 if guided_every else 0)
+        region = "one eager CFG forward + one eager guidance iteration with a CUDA-event pair around every launch"
+    for dst, n in ((fam, n_unet_steps), (fam_guid, n_guid_steps), (shapes[0], n_unet_steps), (shapes[1], n_guid_steps)):
+        for v in dst.values():  # per CFG forward / per guidance iteration
+            for k_ in ("ms", "flops", "bytes", "launches"):
+                v[k_] = v[k_] / max(1, n)
+    # kernels of this library launched inside timed region 1 (graph replays re-run the captured launches): per-variant
+    # launch counts were read from the library's own counter during the eager setup pass
+    launches = sum(counts[i % GUIDED_EVERY] for i in range(args.steps))
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -490,31 +594,34 @@ def run_gpu(args):
         pass
     peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
     peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1.4 PFLOP/s sustained"
-    gm = dict(fam.get("gemm_tc_kernel", {"ms": 1.0, "flops": 0.0, "launches": 1}))
-    gg = fam_guid.get("gemm_tc_kernel")
-    if gg:  # the timed step mix = CFG forward + 1/5 guidance iteration: the dominant kernel's launches of both
+    gm = dict(fam.get("gemm_tc_kernel", {"ms": 1.0, "flops": 0.0, "launches": 1, "bytes": 0.0}))
+    gg_ = fam_guid.get("gemm_tc_kernel")
+    if gg_:  # the timed step mix = CFG forward + 1/5 guidance iteration: the dominant kernel's launches of both
         share = 1.0 / GUIDED_EVERY
-        gm = {"ms": gm["ms"] + share * gg["ms"], "flops": gm["flops"] + share * gg["flops"],
-              "launches": gm["launches"] + share * gg["launches"], "bytes": gm.get("bytes", 0.0) + share * gg["bytes"]}
+        gm = {"ms": gm["ms"] + share * gg_["ms"], "flops": gm["flops"] + share * gg_["flops"],
+              "launches": gm["launches"] + share * gg_["launches"], "bytes": gm.get("bytes", 0.0) + share * gg_["bytes"]}
     achieved = gm["flops"] / (gm["ms"] * 1e-3) / 1e12
     traffic, traffic_src = None, None
-    try:  # DRAM bytes per gemm_tc_kernel launch from the committed ncu capture (profiles/, measured, not live)
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_gemm_traffic.json")))
+    try:  # DRAM bytes per gemm_tc_kernel launch from the committed ncu capture of THIS round's code (profiles/)
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r2_gemm_traffic.json")))
         if args.workload == "lvd_zeroscope":
             traffic = tj["traffic_bytes_per_launch"]
-            traffic_src = "profiles/r1_gemm_traffic.json (ncu dram__bytes_*.sum)"
+            traffic_src = "profiles/r2_gemm_traffic.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum " \
+                          "over the gemm_tc_kernel launches of one CFG forward + one guidance iteration, step-mix " \
+                          "weighted)"
     except Exception:
         pass
+    all_ms = sum(v["ms"] for v in fam.values()) + (sum(v["ms"] for v in fam_guid.values()) / GUIDED_EVERY
+                                                     if fam_guid else 0.0)
     roofline = {"bound": "tensor", "kernel": "gemm_tc_kernel", "achieved": achieved, "peak": peak_tf,
                 "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": traffic, "traffic_unit": "bytes/launch",
-                "traffic_source": traffic_src, "algorithmic_bytes_per_launch": gm.get("bytes", 0.0) / max(1, gm["launches"]),
-                "peak_source": peak_src,
-                "launches_per_step": gm["launches"], "ms_per_step": gm["ms"],
-                "share_of_instrumented_step": gm["ms"] / max(1e-9, sum(v["ms"] for v in fam.values()) + (
-                    sum(v["ms"] for v in fam_guid.values()) / GUIDED_EVERY if fam_guid else 0.0)),
-                "note": "FLOPs and CUDA-event time summed over all gemm_tc_kernel launches of one CFG forward (fusers "
-                        "off) plus 1/5 of one guidance iteration when the workload is guided; instrumented eager pass "
-                        "after the timed region"}
+                "traffic_source": traffic_src,
+                "algorithmic_bytes_per_launch": gm.get("bytes", 0.0) / max(1, gm["launches"]),
+                "peak_source": peak_src, "launches_per_step": gm["launches"], "ms_per_step": gm["ms"],
+                "share_of_step_kernel_time": gm["ms"] / max(1e-9, all_ms), "region": region,
+                "instrumented_ms_per_step": ms_instr,
+                "note": "FLOPs and durations summed over all gemm_tc_kernel launches of one CFG forward (fusers per the "
+                        "step pattern) plus 1/5 of one guidance iteration when the workload is guided"}
     if args.profile_json and rank == 0:
         json.dump({"cfg_forward": fam, "guidance_iteration": fam_guid, "gemm_shapes_cfg_forward": shapes[0],
                    "gemm_shapes_guidance_iteration": shapes[1]}, open(args.profile_json, "w"), indent=1)
@@ -529,7 +636,7 @@ def run_gpu(args):
         fps = lambda m: None if m is None else {"ms": m, "frames_per_s": world * frames / (m * 1e-3)}  # noqa: E731
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(3, args.warmup) + 5, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f16", "data": "synthetic",
             "config": {"workload": _workload(args.workload, args.unguided),
                        "weights": f"seeded random init of the {wl['model']} UNet3D config "
@@ -538,8 +645,10 @@ def run_gpu(args):
                        "l2": "inputs larger than L2 (2.8 GB weights + >20 GB activations per step vs 126 MB)",
                        "api": "lvd_b200.models: latent_backward_guidance + UNet3DConditionModel.forward + "
                               "DPMSolverMultistepScheduler.step_cfg (the reference pipeline's loop body)",
-                       "cuda_graph": "UNet3DConditionModel.forward replays a CUDA graph per input shape; guidance pass "
-                                     "eager" if unet.use_cuda_graph else False,
+                       "cuda_graph": "UNet3DConditionModel.forward and the guidance pass (GuidanceGraph.run) each replay a "
+                                     "CUDA graph per structure" if unet.use_cuda_graph else False,
+                       "setup": f"{SETUP_STEPS} untimed setup steps before the warm-up: every step variant runs once "
+                                "eagerly and once under graph capture (not counted as warm-up)",
                        "algorithmic_tflop_per_step": tflop_step,
                        "guidance": None if not guided_every else {
                            "keys": GUIDANCE_KEYS, "layout": "demo bear, 1 object, token 2", "iterations_per_guided_step": 1,
@@ -559,14 +668,14 @@ def run_gpu(args):
                                                                             key=lambda kv: -kv[1]["ms"])},
         }
         if world == 1 and not args.no_cpu_baseline and args.workload == "lvd_zeroscope":
-            # one guided + one unguided step on the CPU, combined with the schedule weights 1:4
-            _, _, cores, sec_g, sec_u = cpu_reference_step(args.cpu_sample_frames, 2, 0, 2 if guided_every else 0)
-            sec = (sec_g + (GUIDED_EVERY - 1) * sec_u) / GUIDED_EVERY if guided_every else sec_u
-            line["cpu_baseline"] = {
-                "value": args.cpu_sample_frames / sec, "unit": UNIT, "cores": cores, "kind": "port",
-                "sample": f"same step mix on {args.cpu_sample_frames} of 24 frames (72x40 latent, full UNet), fp32, "
-                          f"oracle port of the reference (autograd guidance): guided step "
-                          f"{sec_g and round(sec_g, 1)} s, unguided {sec_u and round(sec_u, 1)} s, weighted 1:4"}
+            # the SAME routine as --impl reference (one code path): one guided + one unguided step, combined with the
+            # schedule weights 1:4 of the timed step mix
+            r = cpu_reference_step(args.cpu_sample_frames, [True, False] if guided_every else [False], 0,
+                                   args.cpu_budget_s / 2)
+            sec = (r["sec_guided"] + (GUIDED_EVERY - 1) * r["sec_unguided"]) / GUIDED_EVERY if guided_every \
+                else r["sec_unguided"]
+            line["cpu_baseline"] = {"value": r["sample_frames"] / sec, "unit": UNIT, "cores": r["cores"], "kind": "port",
+                                    "sample": cpu_sample_text(r) + (", weighted 1:4" if guided_every else "")}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -126,6 +126,8 @@ typedef struct lvd_attn_desc {
   int32_t tok_cols[16];
   float scale;
   int32_t causal; /* mode 0, s_k <= 128, no map outputs: key j is visible to query i iff j <= i (CLIP text encoder) */
+  const int32_t* tok_cols_dev; /* optional device copy of tok_cols[n_tok], read by the kernel at run time (so a captured
+                                  CUDA graph serves layouts with other token positions); NULL = use tok_cols */
 } lvd_attn_desc;
 
 int lvd_attention(const lvd_attn_desc* d, void* stream);
@@ -328,12 +330,13 @@ int lvd_temporal_attn_bwd(const void* qkv, int64_t ld_qkv, int64_t width_qkv, in
                           int32_t v_col0, const void* d_o, int64_t ld_do, void* d_qkv, int64_t ld_dqkv, int64_t n_seq,
                           int32_t heads, int32_t frames, float scale, void* stream);
 /* dp_tok: n_slots in 1..16 -> dE/dP of the listed token columns [n_slots][nz][heads][s_q]; n_slots == -1 -> the dense
- * map [nz][heads][s_q][s_k] (map pre-processing variants of the energy, more than 16 slots); 0 -> none. */
+ * map [nz][heads][s_q][s_k] (map pre-processing variants of the energy, more than 16 slots); 0 -> none.
+ * slot_col_dev (optional): device copy of the column list, read at run time instead of slot_col_host (graph replays). */
 int lvd_cross_attn_bwd(const void* q, int64_t ld_q, int64_t width_q, const void* kv, int64_t ld_kv, int64_t width_kv,
                        int32_t k_col0, int32_t v_col0, const void* d_o, int64_t ld_do, const void* dp_tok,
                        const int32_t* slot_col_host,
                        int32_t n_slots, void* dq, int64_t ld_dq, int64_t s_q, int32_t s_k, int32_t heads, int32_t nz,
-                       int32_t kv_z_div, float scale, void* stream);
+                       int32_t kv_z_div, float scale, const int32_t* slot_col_dev, void* stream);
 
 #ifdef __cplusplus
 }

@@ -70,6 +70,7 @@ class AttnDesc(ctypes.Structure):
         ("tok_cols", ctypes.c_int32 * 16),
         ("scale", ctypes.c_float),
         ("causal", ctypes.c_int32),
+        ("tok_cols_dev", ctypes.c_void_p),
     ]
 
 
@@ -170,7 +171,7 @@ def _declare(l):
     l.lvd_self_attn_bwd.argtypes = [vp, i64, i64, i32, i32, i32, vp, i64, vp, vp, vp, i64, i64, i32, i32, f32, vp]
     l.lvd_temporal_attn_bwd.argtypes = [vp, i64, i64, i32, i32, i32, vp, i64, vp, i64, i64, i32, i32, f32, vp]
     l.lvd_cross_attn_bwd.argtypes = [vp, i64, i64, vp, i64, i64, i32, i32, vp, i64, vp, ctypes.POINTER(ctypes.c_int32),
-                                     i32, vp, i64, i64, i32, i32, i32, i32, f32, vp]
+                                     i32, vp, i64, i64, i32, i32, i32, i32, f32, vp, vp]
     for name in EXPORTS:
         fn = getattr(l, name)
         if name not in ("lvd_last_error", "lvd_launch_count"):

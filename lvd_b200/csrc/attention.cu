@@ -40,6 +40,7 @@ struct AttnArgs {
   int kv_same_tile, n_units, kv_total, diag_mod, kv_z_div, heads, nz;
   int n_tok;
   int tok_cols[16];
+  const int* tok_cols_dev;  // optional: the same list in device memory (read at run time: CUDA-graph replays)
   int last_cols16;
   int seq_len;  // > 0: packed-sequence (temporal) mode
   float* lse;   // optional [nz, heads, p_rows] log2-domain logsumexp (multi-unit mode), for the backward kernels
@@ -353,7 +354,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid
             }
             if (g.p_tok) {
               for (int t = 0; t < g.n_tok; ++t) {
-                const int col = g.tok_cols[t] - ch * 32;
+                const int col = (g.tok_cols_dev ? g.tok_cols_dev[t] : g.tok_cols[t]) - ch * 32;
                 if (col >= 0 && col < 32) {
                   float pv = 0.f;
 #pragma unroll
@@ -550,6 +551,7 @@ extern "C" int lvd_attention(const lvd_attn_desc* d, void* stream) {
   LVD_REQUIRE(!d->lse || g.n_units >= 1, "lvd_attention: lse");
   g.n_tok = d->n_tok;
   for (int i = 0; i < d->n_tok; ++i) g.tok_cols[i] = d->tok_cols[i];
+  g.tok_cols_dev = d->tok_cols_dev;
   g.scale_log2 = d->scale * 1.4426950408889634f;
   g.idesc_qk_full = make_idesc_f16(128, 128, 0, 0);
   g.idesc_qk_last = make_idesc_f16(128, static_cast<uint32_t>(g.last_cols16), 0, 0);

@@ -16,7 +16,7 @@ extern std::atomic<long long> g_launches;
 int launch_cross_attn_bwd_mma(const void* q, long long ld_q, const void* kv, long long ld_kv, int k_col0, int v_col0,
                               const void* d_o, long long ld_do, const void* dp_tok, const int* slot_col, int n_slots,
                               void* dq, long long ld_dq, long long s_q, int s_k, int heads, int nz, int kv_z_div,
-                              float scale, cudaStream_t stream);  // attention_temporal.cu
+                              float scale, cudaStream_t stream, const int* slot_col_dev = nullptr);  // attention_temporal.cu
 
 constexpr int kPad = 66;  // padded row length (halves) of 64-wide tiles in shared memory: conflict-free column reads
 
@@ -320,7 +320,8 @@ extern "C" int lvd_cross_attn_bwd(const void* q, int64_t ld_q, int64_t width_q, 
                                   int64_t width_kv, int32_t k_col0, int32_t v_col0, const void* d_o, int64_t ld_do,
                                   const void* dp_tok,
                                   const int32_t* slot_col_host, int32_t n_slots, void* dq, int64_t ld_dq, int64_t s_q,
-                                  int32_t s_k, int32_t heads, int32_t nz, int32_t kv_z_div, float scale, void* stream) {
+                                  int32_t s_k, int32_t heads, int32_t nz, int32_t kv_z_div, float scale,
+                                  const int32_t* slot_col_dev, void* stream) {
   LVD_REQUIRE(q && kv && d_o && dq, "lvd_cross_attn_bwd: null pointer");
   LVD_REQUIRE(s_k >= 1 && s_k <= 128 && n_slots >= -1 && n_slots <= 16 &&
                   (n_slots == 0 || dp_tok) && (n_slots <= 0 || slot_col_host),
@@ -338,9 +339,10 @@ extern "C" int lvd_cross_attn_bwd(const void* q, int64_t ld_q, int64_t width_q, 
     if (!force_tile) {  // warp-level mma.sync kernel (attention_temporal.cu)
       const int r = launch_cross_attn_bwd_mma(q, ld_q, kv, ld_kv, k_col0, v_col0, d_o, ld_do, dp_tok, slot_col_host,
                                               n_slots, dq, ld_dq, s_q, s_k, heads, nz, kv_z_div, scale,
-                                              static_cast<cudaStream_t>(stream));
+                                              static_cast<cudaStream_t>(stream), slot_col_dev);
       if (r != 1) return r;
     }
+    LVD_REQUIRE(!slot_col_dev, "lvd_cross_attn_bwd: device-side column lists need the warp-level kernel");
     // tcgen05 tile path (attn_bwd_small_kernel, mode 0)
     return launch_attn_bwd_small(0, q, ld_q, width_q, static_cast<long long>(nz) * s_q, kv, ld_kv, width_kv,
                                  static_cast<long long>((nz + kv_z_div - 1) / kv_z_div) * s_k, d_o, ld_do,

@@ -365,6 +365,7 @@ struct CrossBwdMmaArgs {
   int k_col0, v_col0;
   int s_q, s_k, heads, nz, q_tiles, kv_z_div, n_slots;
   int slot_col[16];
+  const int* slot_col_dev;  // optional device copy, read at run time (graph replays with other token positions)
   float scale, scale_log2;
 };
 
@@ -439,7 +440,7 @@ __global__ void __launch_bounds__(128) cross_attn_bwd_mma_kernel(const CrossBwdM
         const int c = nt * 8 + 2 * t + e;
         float va = 0.f, vb_ = 0.f;
         for (int sl = 0; sl < a.n_slots; ++sl) {
-          if (a.slot_col[sl] == c) {
+          if ((a.slot_col_dev ? a.slot_col_dev[sl] : a.slot_col[sl]) == c) {
             const __half* src = a.dp_tok + ((static_cast<long long>(sl) * a.nz + z) * a.heads + h) * a.s_q;
             if (ra < a.s_q) va += __half2float(src[ra]);
             if (rb < a.s_q) vb_ += __half2float(src[rb]);
@@ -538,7 +539,7 @@ __global__ void __launch_bounds__(128) cross_attn_bwd_mma_kernel(const CrossBwdM
 int launch_cross_attn_bwd_mma(const void* q, long long ld_q, const void* kv, long long ld_kv, int k_col0, int v_col0,
                               const void* d_o, long long ld_do, const void* dp_tok, const int* slot_col, int n_slots,
                               void* dq, long long ld_dq, long long s_q, int s_k, int heads, int nz, int kv_z_div,
-                              float scale, cudaStream_t stream) {
+                              float scale, cudaStream_t stream, const int* slot_col_dev) {
   if (s_k < 1 || s_k > 128 || n_slots > 16) return 1;  // n_slots == -1: dp_tok is the dense map
   CrossBwdMmaArgs a;
   a.q = static_cast<const __half*>(q);
@@ -560,6 +561,7 @@ int launch_cross_attn_bwd_mma(const void* q, long long ld_q, const void* kv, lon
   a.kv_z_div = kv_z_div;
   a.n_slots = dp_tok ? n_slots : 0;
   for (int i = 0; i < 16; ++i) a.slot_col[i] = (i < a.n_slots && slot_col) ? slot_col[i] : -1;
+  a.slot_col_dev = slot_col_dev;
   a.scale = scale;
   a.scale_log2 = scale * 1.4426950408889634f;
   a.n_warps = static_cast<long long>(nz) * a.q_tiles * heads;

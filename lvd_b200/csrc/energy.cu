@@ -111,6 +111,11 @@ __global__ void __launch_bounds__(kEnergyThreads) box_energy_kernel(const Energy
   const int slot = blockIdx.y;
   const int f = blockIdx.x / g.heads, h = blockIdx.x % g.heads;
   const int hw = g.H * g.W;
+  if (g.slot_weight[slot] == 0.f) {  // padding slot of a graph-replayed table: no energy, zero gradient
+    if (g.dp && g.layout == 0)
+      for (int i = threadIdx.x; i < hw; i += blockDim.x) g.dp[p_index(g, slot, f, h, i)] = __float2half_rn(0.f);
+    return;
+  }
   const int* bx = g.boxes + (static_cast<long long>(slot) * g.frames + f) * 4;
   const int x0 = bx[0], y0 = bx[1], x1 = bx[2], y1 = bx[3];
   const int area = (x1 > x0 && y1 > y0) ? (x1 - x0) * (y1 - y0) : 0;

@@ -16,7 +16,7 @@ Gradients are carried multiplied by GRAD_SCALE in fp16 and un-scaled in the fina
 import torch
 
 from . import ops, repack
-from .utils.guidance import build_slots, energy_options, map_energy
+from .utils.guidance import build_slots, energy_options, map_energy, padded_slot_count
 from .utils.utils import get_hw_from_attn_dim
 
 GRAD_SCALE = 1024.0
@@ -108,9 +108,10 @@ class GuidanceGraph:
             if want_tok and dense:  # the whole map (pre-processing variants, > 16 token slots, return_saved_attn)
                 p_full = torch.empty((n_img, heads, hw, s_k), dtype=torch.float16, device=self.dev)
             elif want_tok:
-                p_tok = torch.empty((len(tok_cols), n_img, heads, hw), dtype=torch.float16, device=self.dev)
+                p_tok = torch.empty((tok_cols.numel(), n_img, heads, hw), dtype=torch.float16, device=self.dev)
             a2 = ops.attention(q, kv, heads=heads, nz=n_img, s_q=hw, s_k=s_k, k_col0=0, v_col0=c,
-                               kv_z_div=frames, p_tok=p_tok, p_full=p_full, tok_cols=tok_cols if p_tok is not None else ())
+                               kv_z_div=frames, p_tok=p_tok, p_full=p_full,
+                               tok_cols_dev=tok_cols if p_tok is not None else None)
             ctx.update(q2=q, kv2=kv, p_tok=p_tok, p_full=p_full, s_k=s_k)
         else:
             qkv2 = ops.linear(n2, B.qkv2, row_map=fm2sm)
@@ -126,7 +127,7 @@ class GuidanceGraph:
         t3 = ops.linear(gg, B.ff2.w, B.ff2.b, residual=t2)
         return t3, ctx
 
-    def _block_bwd(self, B, c, d3, dp_tok=None, tok_cols=(), dp_dense=None):
+    def _block_bwd(self, B, c, d3, dp_tok=None, tok_cols=None, dp_dense=None):
         """d3: gradient w.r.t. the block output, or None when only the cross-attention energy seeds it."""
         sp = c.spatial
         fm2sm = None if sp else ("fm2sm", c.batch, c.frames, c.hw)
@@ -143,7 +144,8 @@ class GuidanceGraph:
             d_a2 = torch.zeros((c.t0.shape[0], ch), dtype=torch.float16, device=self.dev)
         if sp:
             d_q = ops.cross_attention_bwd(c.q2, c.kv2, d_a2, heads=c.heads, nz=c.n_img, s_q=c.hw, s_k=c.s_k,
-                                          kv_z_div=c.frames, dp_tok=dp_tok, slot_cols=tok_cols, dp_dense=dp_dense)
+                                          kv_z_div=c.frames, dp_tok=dp_tok, dp_dense=dp_dense,
+                                          slot_cols_dev=tok_cols if dp_tok is not None else None)
             d_n2 = ops.linear_dgrad(d_q, B.q2)
         else:
             d_qkv2 = ops.temporal_attention_bwd(c.qkv2, d_a2, heads=c.heads, n_seq=c.batch * c.hw, frames=c.frames)
@@ -160,7 +162,7 @@ class GuidanceGraph:
         d_n1 = ops.linear_dgrad(d_qkv, B.qkv1, row_map=sm2fm)
         return ops.layernorm_bwd(c.t0, d_n1, B.norm1.w, out=d_t1, accumulate=True)
 
-    def _transformer_fwd(self, T, x, *, spatial, n_img, hw, batch, frames, ctx_kv=None, tok_cols=(), want_tok=False,
+    def _transformer_fwd(self, T, x, *, spatial, n_img, hw, batch, frames, ctx_kv=None, tok_cols=None, want_tok=False,
                          last=False, dense=False):
         samples = n_img if spatial else batch
         st = ops.gn_stats_buffer(samples, self.dev)
@@ -172,7 +174,7 @@ class GuidanceGraph:
         out = None if last else ops.linear(t1, T.proj_out.w, T.proj_out.b, residual=x)
         return out, Ctx(x=x, block=bctx, samples=samples, st=st)
 
-    def _transformer_bwd(self, T, c, dout, dp_tok=None, tok_cols=(), dp_dense=None):
+    def _transformer_bwd(self, T, c, dout, dp_tok=None, tok_cols=None, dp_dense=None):
         if dout is not None:
             d_t1 = ops.linear_dgrad(dout, T.proj_out.w)
         else:
@@ -205,16 +207,20 @@ class GuidanceGraph:
         # dense form: the guided maps are materialised and dE/dP travels as a dense map -- needed by the map
         # pre-processing variants, by more than 16 (object, token) slots, and when the caller wants the maps back
         dense = bool(pre.active or len(tok_cols) > 16 or return_saved_attn)
+        n_pad = padded_slot_count(len(tok_cols))
         hp = dict(opts=opts, pre=pre, dense=dense, loss_scale=float(loss_scale),
                   base_attn_dim=tuple(loss_kw.get("base_attn_dim", (40, 72))))
-        if (not self.use_cuda_graph or ops.PROF is not None or torch.cuda.is_current_stream_capturing() or
+        if (not self.use_cuda_graph or (ops.PROF is not None and ops.PROF_SCOPE is None) or
+                torch.cuda.is_current_stream_capturing() or
                 len(bboxes) == 0 or len(tok_cols) == 0 or return_saved_attn):
             self.saved_attn = {} if return_saved_attn else None
             return self._run_impl(latents, timestep, cond_embeddings, bboxes, object_positions, guidance_attn_keys, **hp)
         self.saved_attn = None
+        # token positions, object counts and boxes are INPUTS of the captured graph (device tables refreshed before each
+        # replay), not part of its key: layouts differing in them share one graph per padded slot count
         key = (tuple(latents.shape), tuple(cond_embeddings.shape), tuple(tuple(k) for k in guidance_attn_keys),
-               tuple(tuple(int(t) for t in obj) for obj in object_positions), tuple(sorted(opts.items())),
-               repr(sorted(pre.items())), dense, hp["loss_scale"], hp["base_attn_dim"])
+               n_pad, tuple(sorted(opts.items())), repr(sorted(pre.items())), dense, hp["loss_scale"],
+               hp["base_attn_dim"])
         ent = self._graphs.get(key)
         if ent is None:  # first sighting: eager (also warms the allocator, kernel attributes and transposed weights)
             self._graphs[key] = "seen"
@@ -222,21 +228,29 @@ class GuidanceGraph:
         dev = self.dev
         frames = latents.shape[2]
         if ent == "seen":
-            while len([v for v in self._graphs.values() if v != "seen"]) >= 2:  # each graph pins its activations
+            while len([v for v in self._graphs.values() if v != "seen"]) >= 6:  # each graph pins its activations
                 old = next(k for k, v in self._graphs.items() if v != "seen")
                 del self._graphs[old]
             st = dict(x=torch.empty(tuple(latents.shape), dtype=torch.float16, device=dev),
                       t=torch.empty((frames,), dtype=torch.float32, device=dev),
-                      ehs=torch.empty(tuple(cond_embeddings.shape), dtype=torch.float16, device=dev), slots={})
+                      ehs=torch.empty(tuple(cond_embeddings.shape), dtype=torch.float16, device=dev), slots={},
+                      tok=torch.zeros((n_pad,), dtype=torch.int32, device=dev), n_pad=n_pad)
             self._fill_static(st, latents, timestep, cond_embeddings, bboxes, object_positions)
             # dry run outside capture: allocates the static slot tables for every guided resolution
             self._run_impl(st["x"], st["t"], st["ehs"], bboxes, object_positions, guidance_attn_keys, slots=st["slots"],
-                           **hp)
+                           tok_dev=st["tok"], **hp)
             torch.cuda.synchronize(dev)
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                st["loss"], st["grad"] = self._run_impl(st["x"], st["t"], st["ehs"], bboxes, object_positions,
-                                                        guidance_attn_keys, slots=st["slots"], **hp)
+            scope = ops.PROF_SCOPE
+            if scope is not None:
+                ops.PROF_SCOPE = "guidance"
+            try:
+                with torch.cuda.graph(g):
+                    st["loss"], st["grad"] = self._run_impl(st["x"], st["t"], st["ehs"], bboxes, object_positions,
+                                                            guidance_attn_keys, slots=st["slots"], tok_dev=st["tok"],
+                                                            **hp)
+            finally:
+                ops.PROF_SCOPE = scope
             st["graph"] = g
             self._graphs[key] = ent = st
         self._fill_static(ent, latents, timestep, cond_embeddings, bboxes, object_positions)
@@ -248,13 +262,19 @@ class GuidanceGraph:
         st["ehs"].copy_(cond_embeddings, non_blocking=True)
         st["t"].fill_(float(timestep))
         frames = latents.shape[2]
+        first = True
         for (H, W), (cols, boxes, wts) in st["slots"].items():  # refresh the rasterised boxes of every resolution
-            _, nb_, nw_ = build_slots(bboxes, object_positions, frames, H, W, torch.device("cpu"))
+            nc_, nb_, nw_ = build_slots(bboxes, object_positions, frames, H, W, torch.device("cpu"), pad_to=st["n_pad"],
+                                        fold_objects=True)
+            cols.copy_(nc_, non_blocking=True)
             boxes.copy_(nb_, non_blocking=True)
             wts.copy_(nw_, non_blocking=True)
+            if first:
+                st["tok"].copy_(nc_, non_blocking=True)
+                first = False
 
     def _run_impl(self, latents, timestep, cond_embeddings, bboxes, object_positions, guidance_attn_keys, *,
-                  opts, pre, dense=False, loss_scale=1.0, base_attn_dim=(40, 72), slots=None):
+                  opts, pre, dense=False, loss_scale=1.0, base_attn_dim=(40, 72), slots=None, tok_dev=None):
         cfg, w, dev = self.cfg, self.w, self.dev
         boc = list(cfg["block_out_channels"])
         nb = len(boc)
@@ -264,6 +284,9 @@ class GuidanceGraph:
         latents = latents.to(device=dev, dtype=torch.float16).contiguous()
         b, cin, frames, h, w_ = latents.shape
         assert b == 1, "the guidance pass runs the conditional branch only (models/pipelines.py:78-83)"
+        if frames not in (8, 16, 24, 32):
+            raise NotImplementedError(f"lvd_b200 guidance pass: {frames} frames (the packed frame-axis attention and "
+                                      "its adjoint cover 8 / 16 / 24 / 32 frames; the runners use 16 and 24)")
         n_img = frames
         ehs = cond_embeddings.to(device=dev, dtype=torch.float16).contiguous()
         ctx_kv = ehs.reshape(ehs.shape[1], ehs.shape[2])
@@ -273,6 +296,11 @@ class GuidanceGraph:
         if n_obj == 0 or len(tok_cols) == 0:
             return loss, torch.zeros(latents.shape, dtype=torch.float32, device=dev)
         assert dense or len(tok_cols) <= 16
+        n_pad = padded_slot_count(len(tok_cols))
+        if tok_dev is None:
+            tok_dev = torch.tensor(list(tok_cols) + [tok_cols[0]] * (n_pad - len(tok_cols)), dtype=torch.int32,
+                                   device=dev)
+        tok_cols = tok_dev  # the kernels read the column list from device memory (graph input)
         if torch.is_tensor(timestep) and timestep.is_cuda and timestep.dtype == torch.float32 and \
                 timestep.numel() == frames:
             t = timestep  # pre-expanded device tensor (graph replay: the value is read at run time)
@@ -376,7 +404,7 @@ class GuidanceGraph:
 
         # ---------------- energy on the emitted token columns (one launch per guided key), dE/dP seeds
         seeds = {}
-        out_scale = float(loss_scale) / (n_obj * len(keys))
+        out_scale = float(loss_scale) / len(keys)  # 1 / n_objects is folded into the slot weights
         for kind, wts, c, key in tape:
             if kind == "attn" and key is not None:
                 bc = c.block
@@ -385,7 +413,7 @@ class GuidanceGraph:
                 if slots is not None and (H, W) in slots:  # static tables of a captured graph
                     tabs = slots[(H, W)]
                 else:
-                    tabs = build_slots(bboxes, object_positions, frames, H, W, dev)
+                    tabs = build_slots(bboxes, object_positions, frames, H, W, dev, pad_to=n_pad, fold_objects=True)
                     if slots is not None:
                         slots[(H, W)] = tabs
                 if dense:
@@ -407,7 +435,7 @@ class GuidanceGraph:
             if kind == "attn" and dense:
                 d = self._transformer_bwd(wts, c, d, dp_dense=seeds.get(extra))
             elif kind == "attn":
-                d = self._transformer_bwd(wts, c, d, dp_tok=seeds.get(extra), tok_cols=tok_cols if extra else ())
+                d = self._transformer_bwd(wts, c, d, dp_tok=seeds.get(extra), tok_cols=tok_cols if extra else None)
             elif kind == "tattn":
                 d = self._transformer_bwd(wts, c, d)
             elif kind == "resnet":

@@ -249,9 +249,16 @@ class UNet3DConditionModel:
             self._fill_static(st, sample, timestep, ehs, gligen if use_gligen else None)
             torch.cuda.synchronize(dev)
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                # disabled fusers never read the grounding tokens (models/attention.py:44-46): PositionNet is skipped
-                st["out"] = eng.forward(st["x"], st["t"], st["ehs"], gligen=st["gl"])
+            from .. import ops
+            scope = ops.PROF_SCOPE
+            if scope is not None:  # bench.py's instrumented replay: timing-event nodes are captured with the kernels
+                ops.PROF_SCOPE = "unet:fusers" if use_gligen else "unet"
+            try:
+                with torch.cuda.graph(g):
+                    # disabled fusers never read the grounding tokens (models/attention.py:44-46): PositionNet is skipped
+                    st["out"] = eng.forward(st["x"], st["t"], st["ehs"], gligen=st["gl"])
+            finally:
+                ops.PROF_SCOPE = scope
             st["graph"] = g
             self._graphs[key] = ent = st
         self._fill_static(ent, sample, timestep, ehs, gligen if use_gligen else None)

@@ -15,9 +15,14 @@ from ._lib import GemmDesc
 ACT_NONE, ACT_SILU, ACT_GEGLU, ACT_GELU = 0, 1, 2, 3
 _NUM_SMS = 148  # B200
 
-# Optional per-launch instrumentation (bench.py's roofline pass): when PROF is a list, every launch appends
-# (kernel family, algorithmic flops, algorithmic bytes, start event, end event) recorded on the launching stream.
+# Optional per-launch instrumentation (bench.py's roofline / kernel-family numbers): when PROF is a list, every launch
+# appends [kernel family, algorithmic flops, algorithmic bytes, start event, end event, tag, scope] recorded on the
+# launching stream.  Eager launches get ordinary events; launches issued while the stream is being CAPTURED get
+# `external=True` events, which become event-record nodes of the CUDA graph -- after every replay of that graph the pair
+# reads the duration of that kernel node in replay conditions (bench.py's instrumented-replay region).  PROF_SCOPE names
+# the graph being captured so the reader knows which replays refresh which pairs.
 PROF = None
+PROF_SCOPE = None
 FORCE_BLOCK_N = None  # tools/perf_gemm_sweep.py only: override the tile width of every lvd_gemm launch
 FORCE_CTA_PAIR = 0    # 0 auto / 1 single-CTA tiles / 2 CTA pairs (tests and tools/perf_gemm_sweep.py)
 GEGLU_HALF = 128      # value/gate interleave granularity of GEGLU projections (repack.geglu_interleave)
@@ -27,8 +32,9 @@ class _Timed:
     def __init__(self, family, flops=0.0, nbytes=0.0, tag=None):
         self.rec = None
         if PROF is not None:
-            self.rec = [family, float(flops), float(nbytes), torch.cuda.Event(enable_timing=True),
-                        torch.cuda.Event(enable_timing=True), tag]
+            ext = torch.cuda.is_current_stream_capturing()
+            self.rec = [family, float(flops), float(nbytes), torch.cuda.Event(enable_timing=True, external=ext),
+                        torch.cuda.Event(enable_timing=True, external=ext), tag, PROF_SCOPE if ext else None]
 
     def __enter__(self):
         if self.rec is not None:
@@ -314,7 +320,7 @@ def layernorm(x, gamma, beta, eps=1e-5, out=None):
 # ----------------------------------------------------------------------------------------------- attention
 def attention(q, kv, *, heads, nz, s_q=0, s_k=0, q_col0=0, k_col0=0, v_col0=0, kv_z_div=1, temporal=False, frames=0,
               hw=0, scale=0.125, out=None, o_col0=0, p_full=None, p_tok=None, tok_cols=(), packed=False, lse=None,
-              causal=False):
+              causal=False, tok_cols_dev=None):
     """softmax(Q K^T * scale) V with 64-wide heads.  q / kv are 2-D row buffers; q/k/v live at column offsets."""
     _check_act(q, "q")
     _check_act(kv, "kv")
@@ -335,6 +341,10 @@ def attention(q, kv, *, heads, nz, s_q=0, s_k=0, q_col0=0, k_col0=0, v_col0=0, k
     d.n_tok = len(tok_cols)
     for i, t in enumerate(tok_cols):
         d.tok_cols[i] = int(t)
+    if tok_cols_dev is not None:  # int32 device list read at run time (p_tok's leading extent gives the count)
+        assert tok_cols_dev.dtype == torch.int32 and tok_cols_dev.is_cuda and p_tok is not None
+        d.n_tok = int(tok_cols_dev.numel())
+        d.tok_cols_dev = tok_cols_dev.data_ptr()
     d.scale = float(scale)
     d.causal = 1 if causal else 0
     if temporal:
@@ -808,7 +818,7 @@ def temporal_attention_bwd(qkv, d_o, *, heads, n_seq, frames, scale=0.125, out=N
 
 
 def cross_attention_bwd(q, kv, d_o, *, heads, nz, s_q, s_k, kv_z_div, dp_tok=None, slot_cols=(), scale=0.125, out=None,
-                        tensor_core=True, dp_dense=None):
+                        tensor_core=True, dp_dense=None, slot_cols_dev=None):
     """dQ of the cross-attention; dE/dP enters either as token columns (dp_tok [n_slots, nz, heads, s_q] + slot_cols) or
     as a dense map (dp_dense [nz, heads, s_q, s_k])."""
     _check_act(q, "q")
@@ -819,6 +829,10 @@ def cross_attention_bwd(q, kv, d_o, *, heads, nz, s_q, s_k, kv_z_div, dp_tok=Non
         out = _alloc_out(q.shape[0], c, q)
     cols = (ctypes.c_int32 * max(1, len(slot_cols)))(*[int(x) for x in slot_cols])
     n_slots = len(slot_cols) if dp_tok is not None else 0
+    if slot_cols_dev is not None and dp_tok is not None:
+        assert slot_cols_dev.dtype == torch.int32 and slot_cols_dev.is_cuda
+        n_slots = int(slot_cols_dev.numel())
+        cols = (ctypes.c_int32 * max(1, n_slots))(*([0] * max(1, n_slots)))
     if dp_dense is not None:
         assert dp_tok is None and dp_dense.dtype == torch.float16 and dp_dense.is_contiguous()
         assert tuple(dp_dense.shape) == (nz, heads, s_q, s_k) and tensor_core
@@ -829,6 +843,8 @@ def cross_attention_bwd(q, kv, d_o, *, heads, nz, s_q, s_k, kv_z_div, dp_tok=Non
                                                  d_o.data_ptr(), d_o.stride(0),
                                                  dp_tok.data_ptr() if dp_tok is not None else None, cols,
                                                  n_slots, out.data_ptr(),
-                                                 out.stride(0), s_q, s_k, heads, nz, kv_z_div, float(scale), _stream()),
+                                                 out.stride(0), s_q, s_k, heads, nz, kv_z_div, float(scale),
+                                                 slot_cols_dev.data_ptr() if (slot_cols_dev is not None and
+                                                                              n_slots > 0) else None, _stream()),
                    "cross_attn_bwd")
     return out

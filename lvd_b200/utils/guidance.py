@@ -118,10 +118,23 @@ def map_energy(attn_map, loss, bboxes, object_positions, base_attn_dim, opts, pr
     return d
 
 
-def build_slots(bboxes, object_positions, n_frames, H, W, device):
+def padded_slot_count(n):
+    """Slot tables of the graph-replayed guidance pass are padded to a power of two so that layouts with different
+    object / token counts share a captured graph (padding slots carry weight 0 and are skipped by the kernel)."""
+    p = 1
+    while p < n:
+        p *= 2
+    return p
+
+
+def build_slots(bboxes, object_positions, n_frames, H, W, device, pad_to=None, fold_objects=False):
     """Flatten (object, token) pairs into slots and rasterise every per-frame box at resolution (H, W).
-    Returns (cols [n_slots] int32, boxes [n_slots, F, 4] int32, weights [n_slots] fp32) on `device`."""
+    Returns (cols [n_slots] int32, boxes [n_slots, F, 4] int32, weights [n_slots] fp32) on `device`.
+    weights = 1 / len(tokens of the object) (utils/guidance.py:524), additionally / n_objects when fold_objects (the
+    compute_ca_lossv3 normalisation :569-572 moved into the table, so the kernel's out_scale no longer depends on the
+    layout); pad_to appends weight-0 slots."""
     cols, rects, wts = [], [], []
+    n_obj = len(bboxes)
     for obj_idx, obj_boxes in enumerate(bboxes):
         assert n_frames == len(obj_boxes), (
             f"Number of frames {n_frames} mismatches with number of frames in box condition {len(obj_boxes)}")
@@ -134,7 +147,13 @@ def build_slots(bboxes, object_positions, n_frames, H, W, device):
         for tok in toks:
             cols.append(int(tok))
             rects.append(per_frame)
-            wts.append(1.0 / len(toks))
+            wts.append(1.0 / len(toks) / (n_obj if fold_objects else 1))
+    if pad_to is not None:
+        assert pad_to >= len(cols)
+        while len(cols) < pad_to:
+            cols.append(cols[0] if cols else 0)
+            rects.append([(0, 0, 0, 0)] * n_frames)
+            wts.append(0.0)
     return (torch.tensor(cols, dtype=torch.int32, device=device),
             torch.tensor(rects, dtype=torch.int32, device=device).reshape(len(cols), n_frames, 4).contiguous(),
             torch.tensor(wts, dtype=torch.float32, device=device))

@@ -163,7 +163,7 @@ def test_guidance_loss_variants_end_to_end(cuda, variant):
     sd = weights.random_state_dict(cfg, seed=51)
     eng = UNetEngine(cfg, sd, device=cuda)
     gen = torch.Generator().manual_seed(52)
-    F, h, w = 6, 16, 24
+    F, h, w = 8, 16, 24
     x = torch.randn((1, 4, F, h, w), generator=gen).half().to(cuda)
     ehs = torch.randn((1, 77, 128), generator=gen).half().to(cuda)
     bboxes = [[(0.1 + 0.05 * f, 0.2, 0.55 + 0.05 * f, 0.7) for f in range(F)],
@@ -198,7 +198,7 @@ def test_latent_backward_guidance_returns_saved_attn(cuda):
     sd = weights.random_state_dict(cfg, seed=61)
     eng = UNetEngine(cfg, sd, device=cuda)
     gen = torch.Generator().manual_seed(62)
-    F, h, w = 4, 16, 16
+    F, h, w = 8, 16, 16
     x = torch.randn((1, 4, F, h, w), generator=gen).half().to(cuda)
     ehs = torch.randn((1, 77, 128), generator=gen).half().to(cuda)
     bboxes, positions = [[(0.1, 0.2, 0.6, 0.7)] * F], [[3]]
@@ -226,3 +226,36 @@ def test_latent_backward_guidance_returns_saved_attn(cuda):
     with pytest.raises(UnboundLocalError):  # selected iteration never runs: the reference's local is unbound
         latent_backward_guidance(FakeScheduler(), eng, ehs, 0, bboxes, positions, 500, x, torch.tensor(0.0),
                                  return_saved_attn="first", **kw)
+
+
+def test_guidance_graph_is_shared_across_layouts(cuda):
+    """Token positions, object counts and boxes are inputs of the captured graph (device tables), not part of its key: a
+    sweep over layouts with 3-4 (object, token) slots replays ONE graph (slot tables padded to 4), and every replay
+    matches the eager pass for that layout."""
+    from lvd_b200.engine import UNetEngine
+    from lvd_b200.guidance_engine import GuidanceGraph
+    from oracle import unet3d_ref as R
+    from oracle import weights
+    cfg = weights.make_cfg("tiny")
+    eng = UNetEngine(cfg, weights.random_state_dict(cfg, seed=71), device=cuda)
+    gen = torch.Generator().manual_seed(72)
+    F, h, w = 8, 16, 16
+    keys = R.GUIDANCE_KEYS_DEFAULT
+    hp = dict(loss_scale=5.0, base_attn_dim=(h, w), fg_top_p=0.75, bg_top_p=0.75, fg_weight=1.0, bg_weight=4.0,
+              com_loss_scale=0.03)
+    box = lambda i, f: (0.05 * i + 0.02 * f, 0.1 * i, 0.5 + 0.02 * f, 0.6 + 0.05 * i)  # noqa: E731
+    layouts = [([[2], [4, 5]], 2), ([[1, 2], [6]], 2), ([[3], [7], [9]], 3), ([[2], [3], [4], [5]], 4),
+               ([[8, 9, 10]], 1), ([[2], [4, 5]], 2)]
+    eager = GuidanceGraph(eng)
+    eager.use_cuda_graph = False
+    graphed = GuidanceGraph(eng)
+    for i, (positions, n_obj) in enumerate(layouts):
+        x = torch.randn((1, 4, F, h, w), generator=gen).half().to(cuda)
+        ehs = torch.randn((1, 77, 128), generator=gen).half().to(cuda)
+        bboxes = [[box(o + i, f) if (o + f) % 4 else (0, 0, 0, 0) for f in range(F)] for o in range(n_obj)]
+        l0, g0 = eager.run(x, 800 - 50 * i, ehs, bboxes, positions, keys, **hp)
+        l1, g1 = graphed.run(x, 800 - 50 * i, ehs, bboxes, positions, keys, **hp)
+        assert abs(l0.item() - l1.item()) <= 1e-5 * abs(l0.item()) + 1e-7, (i, l0.item(), l1.item())
+        assert torch.equal(g0, g1), i
+    assert sum(1 for v in graphed._graphs.values() if v != "seen") == 1
+    assert len(graphed._graphs) == 1
