@@ -63,6 +63,33 @@ def bear_layout(frames):
     return [boxes], [[2]]
 
 
+def prompt_batch_layouts(n, frames):
+    """Deterministic stand-ins for the cached GPT-4 layouts of `--prompt-type lvd` (55 % one object, 35 %
+    two, 5 % three, 5 % four; 6 % of the boxes absent): objects sweep across the frame, phrases of 1-2 tokens."""
+    pattern = [1, 2, 1, 1, 2, 1, 3, 2, 1, 2, 1, 4, 1, 2, 1, 1, 2, 1, 2, 1]
+    out = []
+    for p in range(n):
+        n_obj = pattern[p % len(pattern)]
+        objs, pos = [], []
+        tok = 2
+        for o in range(n_obj):
+            x0 = 0.05 + 0.2 * o
+            boxes = []
+            for f in range(frames):
+                if (f + 3 * o + p) % 16 == 15:
+                    boxes.append((0.0, 0.0, 0.0, 0.0))  # absent in this frame
+                else:
+                    dx = 0.4 * f / max(frames - 1, 1) * (1 if o % 2 == 0 else -1)
+                    boxes.append((min(max(x0 + dx, 0.0), 0.7), 0.15 + 0.15 * o, min(max(x0 + dx, 0.0), 0.7) + 0.28,
+                                  0.5 + 0.12 * o))
+            objs.append(boxes)
+            n_tok = 2 if (o + p) % 3 == 0 else 1
+            pos.append(list(range(tok, tok + n_tok)))
+            tok += n_tok + 1
+        out.append(dict(bboxes=objs, object_positions=pos))
+    return out
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -81,8 +108,7 @@ def parse():
                     help="skip the prompt-batch measurement (parallel.generate_sharded: scatter + videos + gather)")
     ap.add_argument("--batch-prompts-per-gpu", type=int, default=3)
     ap.add_argument("--profile-json", default=None, help="write the per-kernel-family breakdown here")
-    ap.add_argument("--no-video", action="store_true",
-                    help="skip the secondary end-to-end measurement (one full 50-step video + VAE decode)")
+    ap.add_argument("--no-video", action="store_true", help="alias of --no-prompt-batch")
     return ap.parse_args()
 
 
@@ -457,11 +483,16 @@ def run_gpu(args):
     ms_fused = time_steps([1, 6]) if wl["gated"] else None   # fusers on, no guidance
     ms_guided = time_steps([0, 5]) if guided_every else None  # guidance (+ fusers when gated)
 
-    # ---------------- secondary metric: one whole video through TextToVideoSDPipeline.__call__ --
-    # 50 steps (10 guided when the workload is guided, GLIGEN beta 0.4 when gated) + VAE decode to np frames.  Prompt
-    # embeddings are given (the CLIP text encoder is outside this repo's scope), weights are synthetic.
+    # ---------------- the prompt batch (north_star / SURVEY.md section 8e, BASELINE configs 4-5): a fixed batch of
+    # `--batch-prompts-per-gpu` x N prompts with layouts of 1-4 objects driven through parallel.generate_sharded -- rank 0
+    # scatters the work table (seeds) and the packed box / token tables (NCCL broadcast), every rank runs its window
+    # through TextToVideoSDPipeline.__call__ (50 steps, 10 guided when the workload is guided, GLIGEN beta 0.4 when
+    # gated, VAE decode), the uint8 frames are gathered on rank 0.  Scatter and gather are INSIDE the timed region;
+    # graph capture is excluded by warm-up items (one per padded slot count of the batch).
     video = None
-    if not args.no_video:
+    prompt_batch = None
+    if not (args.no_prompt_batch or args.no_video):
+        from lvd_b200 import parallel
         from lvd_b200.models.controllable_pipeline_text_to_video_synth import TextToVideoSDPipeline
         from lvd_b200.vae import AutoencoderKL
         vae = AutoencoderKL().to(dev)
@@ -471,29 +502,58 @@ def run_gpu(args):
         call = dict(prompt_embeds=ehs_host[1:2], negative_prompt_embeds=ehs_host[0:1], height=lat_h * 8,
                     width=lat_w * 8, num_frames=frames, num_inference_steps=50, guidance_scale=GUIDANCE_SCALE,
                     output_type="np", gligen_scheduled_sampling_beta=0.4)
-        if guided_every:
-            call["backward_guidance_kwargs"] = dict(guidance_kw)
-        if wl["gated"]:
-            call["gligen_inputs"] = gl_in
-        pipe(**dict(call, num_inference_steps=6, latents=lat_host.clone()))  # warm-up: VAE allocations, all graph variants
+
+        def generate(seed, bboxes_, positions_, steps=50):
+            gen = torch.Generator().manual_seed(int(seed))
+            lat0 = torch.randn((1, 4, frames, lat_h, lat_w), generator=gen).half()
+            kw_ = dict(call, num_inference_steps=steps, latents=lat0)
+            if guided_every:
+                kw_["backward_guidance_kwargs"] = dict(guidance_kw, bboxes=bboxes_, object_positions=positions_)
+            if wl["gated"]:
+                kw_["gligen_inputs"] = gligen_inputs(frames, bboxes_, dev, gen)
+            fr = pipe(**kw_).frames  # np.float32 [1, F, H, W, 3] in [0, 1]
+            return torch.from_numpy((fr[0] * 255.0 + 0.5).clip(0, 255).astype("uint8"))
+
+        n_items = args.batch_prompts_per_gpu * world
+        layouts = prompt_batch_layouts(n_items, frames)
+        from lvd_b200.utils.guidance import padded_slot_count
+        slots_of = lambda l: padded_slot_count(sum(len(t) for t in l["object_positions"]))  # noqa: E731
+        for n_pad in sorted({slots_of(l) for l in layouts}):  # warm-up items: one short run per slot-table size
+            l = next(l for l in layouts if slots_of(l) == n_pad)
+            generate(0, l["bboxes"], l["object_positions"], steps=6)
         barrier()
+        stats = {}
         t0 = time.perf_counter()
-        out = pipe(**dict(call, latents=lat_host.clone()))
+        frames_u8, table = parallel.generate_sharded(generate, layouts if rank == 0 else None, dev, stats=stats)
         torch.cuda.synchronize()
         sec = time.perf_counter() - t0
-        tv = torch.tensor([sec], dtype=torch.float64, device=dev)
+        tv = torch.tensor([sec, stats["generate_s"], stats["gather_s"], stats["scatter_s"]], dtype=torch.float64,
+                          device=dev)
+        tmin = tv.clone()
         if world > 1:
             dist.all_reduce(tv, op=dist.ReduceOp.MAX)
-        sec = float(tv[0])
-        fr = out.frames
-        video = {"seconds_per_video": sec, "videos_per_s": world / sec, "frames_per_s": world * frames / sec,
-                 "frames_shape": list(fr.shape), "finite": bool((fr == fr).all()),
-                 "includes": "TextToVideoSDPipeline.__call__: 50 denoising steps"
-                             + (" (10 guided, 1 iteration each)" if guided_every else "")
-                             + (", GLIGEN fusers on the first 20" if wl["gated"] else "")
-                             + ", VAE decode (native AutoencoderKL, SD-1.x decoder) and tensor2vid to host np.float32; "
-                               "prompt embeddings given (text encoder out of scope); wall clock incl. H2D / D2H"}
-        del pipe, vae, out
+            dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
+        sec, gen_max, gather_max, scatter_max = (float(v) for v in tv)
+        gen_min = float(tmin[1])
+        if rank == 0:
+            ok = frames_u8 is not None and tuple(frames_u8.shape) == (n_items, frames, lat_h * 8, lat_w * 8, 3)
+            prompt_batch = {
+                "items": n_items, "items_per_gpu": args.batch_prompts_per_gpu, "seconds": sec,
+                "videos_per_s": n_items / sec, "frames_per_s": n_items * frames / sec,
+                "generate_s_max_rank": gen_max, "generate_s_min_rank": gen_min,
+                "imbalance": (gen_max - gen_min) / gen_max if gen_max > 0 else 0.0,
+                "scatter_s": scatter_max, "gather_s": gather_max, "gather_share": gather_max / sec,
+                "gathered_bytes": int(frames_u8.numel()) if frames_u8 is not None else 0, "frames_ok": bool(ok),
+                "objects_per_layout": [len(l["bboxes"]) for l in layouts],
+                "path": "parallel.generate_sharded: work table + box/token tables broadcast from rank 0, "
+                        "TextToVideoSDPipeline.__call__ per item (50 steps"
+                        + (", 10 guided x 1 iteration" if guided_every else "")
+                        + (", GLIGEN fusers on the first 20" if wl["gated"] else "")
+                        + ", native VAE decode), uint8 frames gathered on rank 0; wall clock, scatter + gather inside"}
+            video = {"seconds_per_video": gen_max / args.batch_prompts_per_gpu,
+                     "videos_per_s": n_items / sec, "frames_per_s": n_items * frames / sec,
+                     "source": "prompt_batch (generate phase of the slowest rank / its items)"}
+        del pipe, vae, frames_u8
 
     # ---------------- instrumented replay region: the same step sequence replayed from graphs that were captured with an
     # `external` CUDA-event pair around every kernel node (ops._Timed); after each step the pairs of the graphs that
@@ -660,6 +720,7 @@ def run_gpu(args):
                     "d2h_bytes_per_step": out_host.numel() * 2 + (4 if guided_every else 0)},
             "gpu_launches": int(launches),
             "video": video,
+            "prompt_batch": prompt_batch,
             "clocks": clocks,
             "roofline": roofline,
             "step_tflops": tflop_step / (ms_step * 1e-3),

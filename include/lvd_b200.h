@@ -236,6 +236,12 @@ typedef struct lvd_energy_desc {
    * attn_sync_weight (:401-426); boxdiff_* (:433-465).  Kind 2 excludes the sync / BoxDiff / COM terms. */
   int32_t loss_kind, k_min, boxdiff_normed, boxdiff_L;
   float eps, attn_sync_weight, boxdiff_loss_scale;
+  /* several prompts in one map (batched guidance pass; an extension, the reference guides one prompt at a time):
+   * p's frame axis has p_frames (0 = frames) entries, slot s covers frames [slot_frame0[s], slot_frame0[s] + frames)
+   * and adds its energy to loss[slot_loss[s]].  NULL tables = one prompt. */
+  int32_t p_frames;
+  const int32_t* slot_frame0;
+  const int32_t* slot_loss;
 } lvd_energy_desc;
 
 int lvd_box_energy(const lvd_energy_desc* d, void* stream);

@@ -103,6 +103,9 @@ class EnergyDesc(ctypes.Structure):
         ("eps", ctypes.c_float),
         ("attn_sync_weight", ctypes.c_float),
         ("boxdiff_loss_scale", ctypes.c_float),
+        ("p_frames", ctypes.c_int32),
+        ("slot_frame0", ctypes.c_void_p),
+        ("slot_loss", ctypes.c_void_p),
     ]
 
 

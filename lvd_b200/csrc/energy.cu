@@ -32,6 +32,11 @@ struct EnergyArgs {
   float fg_top_p, bg_top_p, fg_weight, bg_weight, com_scale, out_scale, grad_scale;
   int loss_kind, k_min, boxdiff_normed, boxdiff_L;
   float eps, eps16, hi16, sync_w, boxdiff_scale;
+  // several prompts in one map (batched guidance): slot -> first frame of its prompt inside p's frame axis, and the
+  // index of its prompt's loss accumulator; p_frames = extent of p's frame axis (== frames for one prompt)
+  const int* slot_frame0;
+  const int* slot_loss;
+  int p_frames;
 };
 
 // One element of a token column; `clamped`: the CE branch works on clamp(P, eps, 1 - eps) evaluated in fp16 (:368)
@@ -39,8 +44,9 @@ __device__ __forceinline__ float col_at(const EnergyArgs& g, int slot, int f, in
 
 __device__ __forceinline__ long long p_index(const EnergyArgs& g, int slot, int f, int h, int i) {
   const long long hw = static_cast<long long>(g.H) * g.W;
-  if (g.layout == 0) return ((static_cast<long long>(slot) * g.frames + f) * g.heads + h) * hw + i;
-  return ((static_cast<long long>(f) * g.heads + h) * hw + i) * g.n_text + g.slot_col[slot];
+  const int z = f + (g.slot_frame0 ? g.slot_frame0[slot] : 0);
+  if (g.layout == 0) return ((static_cast<long long>(slot) * g.p_frames + z) * g.heads + h) * hw + i;
+  return ((static_cast<long long>(z) * g.heads + h) * hw + i) * g.n_text + g.slot_col[slot];
 }
 
 __device__ __forceinline__ float col_at(const EnergyArgs& g, int slot, int f, int h, int i, bool clamped) {
@@ -331,7 +337,7 @@ __global__ void __launch_bounds__(kEnergyThreads) box_energy_kernel(const Energy
     }
   }
   __syncthreads();
-  if (threadIdx.x == 0) atomicAdd(g.loss, loss * wslot);
+  if (threadIdx.x == 0) atomicAdd(g.loss + (g.slot_loss ? g.slot_loss[slot] : 0), loss * wslot);
   if (g.dp) {
     const float gs = wslot * g.grad_scale;
     for (int i = threadIdx.x; i < hw; i += blockDim.x)
@@ -386,6 +392,10 @@ extern "C" int lvd_box_energy(const lvd_energy_desc* d, void* stream) {
   g.hi16 = __half2float(__float2half_rn(1.f - d->eps));
   g.sync_w = d->attn_sync_weight;
   g.boxdiff_scale = d->boxdiff_loss_scale;
+  g.slot_frame0 = d->slot_frame0;
+  g.slot_loss = d->slot_loss;
+  g.p_frames = d->p_frames > 0 ? d->p_frames : d->frames;
+  LVD_REQUIRE(g.p_frames >= d->frames, "lvd_box_energy: p_frames < frames");
   const size_t smem = static_cast<size_t>(2 * npad + hw) * 4 + static_cast<size_t>(hw) * 2;
   static bool attr = false;
   if (!attr) {

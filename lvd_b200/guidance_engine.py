@@ -16,7 +16,7 @@ Gradients are carried multiplied by GRAD_SCALE in fp16 and un-scaled in the fina
 import torch
 
 from . import ops, repack
-from .utils.guidance import build_slots, energy_options, map_energy, padded_slot_count
+from .utils.guidance import build_slots_batch, energy_options, map_energy, padded_slot_count
 from .utils.utils import get_hw_from_attn_dim
 
 GRAD_SCALE = 1024.0
@@ -203,7 +203,10 @@ class GuidanceGraph:
         same structure (shapes, guided keys, token columns, slot counts, hyper-parameters) on; latents, timestep,
         embeddings and the rasterised box tables are copied into the graph's static buffers before each replay."""
         opts, pre = energy_options(loss_kw, with_pre=True)
-        tok_cols = tuple(int(t) for obj in object_positions for t in obj)
+        if latents.shape[0] == 1:
+            tok_cols = tuple(int(t) for obj in object_positions for t in obj)
+        else:
+            tok_cols = tuple(int(t) for pos in object_positions for obj in pos for t in obj)
         # dense form: the guided maps are materialised and dE/dP travels as a dense map -- needed by the map
         # pre-processing variants, by more than 16 (object, token) slots, and when the caller wants the maps back
         dense = bool(pre.active or len(tok_cols) > 16 or return_saved_attn)
@@ -232,7 +235,7 @@ class GuidanceGraph:
                 old = next(k for k, v in self._graphs.items() if v != "seen")
                 del self._graphs[old]
             st = dict(x=torch.empty(tuple(latents.shape), dtype=torch.float16, device=dev),
-                      t=torch.empty((frames,), dtype=torch.float32, device=dev),
+                      t=torch.empty((latents.shape[0] * frames,), dtype=torch.float32, device=dev),
                       ehs=torch.empty(tuple(cond_embeddings.shape), dtype=torch.float16, device=dev), slots={},
                       tok=torch.zeros((n_pad,), dtype=torch.int32, device=dev), n_pad=n_pad)
             self._fill_static(st, latents, timestep, cond_embeddings, bboxes, object_positions)
@@ -261,16 +264,15 @@ class GuidanceGraph:
         st["x"].copy_(latents, non_blocking=True)
         st["ehs"].copy_(cond_embeddings, non_blocking=True)
         st["t"].fill_(float(timestep))
-        frames = latents.shape[2]
+        b, frames = latents.shape[0], latents.shape[2]
+        layouts = [(bboxes, object_positions)] if b == 1 else list(zip(bboxes, object_positions))
         first = True
-        for (H, W), (cols, boxes, wts) in st["slots"].items():  # refresh the rasterised boxes of every resolution
-            nc_, nb_, nw_ = build_slots(bboxes, object_positions, frames, H, W, torch.device("cpu"), pad_to=st["n_pad"],
-                                        fold_objects=True)
-            cols.copy_(nc_, non_blocking=True)
-            boxes.copy_(nb_, non_blocking=True)
-            wts.copy_(nw_, non_blocking=True)
+        for (H, W), tabs in st["slots"].items():  # refresh the rasterised boxes of every resolution
+            new = build_slots_batch(layouts, frames, H, W, torch.device("cpu"), pad_to=st["n_pad"])
+            for dst, src in zip(tabs, new):
+                dst.copy_(src, non_blocking=True)
             if first:
-                st["tok"].copy_(nc_, non_blocking=True)
+                st["tok"].copy_(new[0], non_blocking=True)
                 first = False
 
     def _run_impl(self, latents, timestep, cond_embeddings, bboxes, object_positions, guidance_attn_keys, *,
@@ -283,18 +285,25 @@ class GuidanceGraph:
         last_key = max(keys, key=KEY_ORDER.index)
         latents = latents.to(device=dev, dtype=torch.float16).contiguous()
         b, cin, frames, h, w_ = latents.shape
-        assert b == 1, "the guidance pass runs the conditional branch only (models/pipelines.py:78-83)"
+        # b == 1 is the reference's guidance pass (conditional branch of one prompt, models/pipelines.py:78-83); b > 1
+        # guides b prompts in one pass (an extension: `bboxes` / `object_positions` are then lists with one layout per
+        # prompt, the loss comes back per prompt)
+        layouts = [(bboxes, object_positions)] if b == 1 else list(zip(bboxes, object_positions))
+        assert len(layouts) == b, f"{len(layouts)} layouts for a batch of {b}"
+        if b > 1 and dense:
+            raise NotImplementedError("lvd_b200 guidance pass: the dense dE/dP form (map pre-processing options, more "
+                                      "than 16 token slots, return_saved_attn) runs one prompt at a time")
         if frames not in (8, 16, 24, 32):
             raise NotImplementedError(f"lvd_b200 guidance pass: {frames} frames (the packed frame-axis attention and "
                                       "its adjoint cover 8 / 16 / 24 / 32 frames; the runners use 16 and 24)")
-        n_img = frames
+        n_img = b * frames
         ehs = cond_embeddings.to(device=dev, dtype=torch.float16).contiguous()
-        ctx_kv = ehs.reshape(ehs.shape[1], ehs.shape[2])
-        n_obj = len(bboxes)
-        loss = torch.zeros((), dtype=torch.float32, device=dev)
-        tok_cols = tuple(int(t) for obj in object_positions for t in obj)
+        ctx_kv = ehs.reshape(b * ehs.shape[1], ehs.shape[2])
+        n_obj = sum(len(bb) for bb, _ in layouts)
+        loss = torch.zeros((b,), dtype=torch.float32, device=dev)
+        tok_cols = tuple(int(t) for _, pos in layouts for obj in pos for t in obj)
         if n_obj == 0 or len(tok_cols) == 0:
-            return loss, torch.zeros(latents.shape, dtype=torch.float32, device=dev)
+            return (loss.reshape(()) if b == 1 else loss), torch.zeros(latents.shape, dtype=torch.float32, device=dev)
         assert dense or len(tok_cols) <= 16
         n_pad = padded_slot_count(len(tok_cols))
         if tok_dev is None:
@@ -302,10 +311,10 @@ class GuidanceGraph:
                                    device=dev)
         tok_cols = tok_dev  # the kernels read the column list from device memory (graph input)
         if torch.is_tensor(timestep) and timestep.is_cuda and timestep.dtype == torch.float32 and \
-                timestep.numel() == frames:
+                timestep.numel() == b * frames:
             t = timestep  # pre-expanded device tensor (graph replay: the value is read at run time)
         else:
-            t = torch.as_tensor(timestep, device=dev).reshape(-1).to(torch.float32).expand(1).repeat_interleave(frames)
+            t = torch.as_tensor(timestep, device=dev).reshape(-1).to(torch.float32).expand(b).repeat_interleave(frames)
             t = t.contiguous()
         temb = ops.timestep_embed(t, boc[0])
         temb = ops.linear(temb, w["time1"].w, w["time1"].b, act=ops.ACT_SILU)
@@ -315,7 +324,7 @@ class GuidanceGraph:
         tape = []  # (kind, weights, ctx, extra)
         x = ops.conv_in_tc(latents, w["conv_in"].w_pad, w["conv_in"].b)
         hw = h * w_
-        x, c = self._transformer_fwd(w["transformer_in"], x, spatial=False, n_img=n_img, hw=hw, batch=1,
+        x, c = self._transformer_fwd(w["transformer_in"], x, spatial=False, n_img=n_img, hw=hw, batch=b,
                                      frames=frames)
         tape.append(("tattn", w["transformer_in"], c, None))
         # skips[0] is transformer_in's output: its gradient joins before transformer_in's adjoint runs
@@ -327,19 +336,19 @@ class GuidanceGraph:
             hw = h * w_
             x, c = self._resnet_fwd(L.resnet, x, n_img, h, w_, temb_all)
             tape.append(("resnet", L.resnet, c, None))
-            x, c = self._tconv_fwd(L.tconv, x, 1, frames, hw)
+            x, c = self._tconv_fwd(L.tconv, x, b, frames, hw)
             tape.append(("tconv", L.tconv, c, None))
             if "attn" in L:
                 key = (kind, stage, j, 0)
                 is_last = key == last_key
-                x, c = self._transformer_fwd(L.attn, x, spatial=True, n_img=n_img, hw=hw, batch=1, frames=frames,
+                x, c = self._transformer_fwd(L.attn, x, spatial=True, n_img=n_img, hw=hw, batch=b, frames=frames,
                                              ctx_kv=ctx_kv, tok_cols=tok_cols, want_tok=key in keys, last=is_last,
                                              dense=dense)
                 tape.append(("attn", L.attn, c, key if key in keys else None))
                 if is_last:
                     done = True
                     return x
-                x, c = self._transformer_fwd(L.tattn, x, spatial=False, n_img=n_img, hw=hw, batch=1, frames=frames)
+                x, c = self._transformer_fwd(L.tattn, x, spatial=False, n_img=n_img, hw=hw, batch=b, frames=frames)
                 tape.append(("tattn", L.tattn, c, None))
             return x
 
@@ -365,21 +374,21 @@ class GuidanceGraph:
             hw = h * w_
             x, c = self._resnet_fwd(M.res0, x, n_img, h, w_, temb_all)
             tape.append(("resnet", M.res0, c, None))
-            x, c = self._tconv_fwd(M.tconv0, x, 1, frames, hw)
+            x, c = self._tconv_fwd(M.tconv0, x, b, frames, hw)
             tape.append(("tconv", M.tconv0, c, None))
             key = ("mid", 0, 0, 0)
-            x, c = self._transformer_fwd(M.attn, x, spatial=True, n_img=n_img, hw=hw, batch=1, frames=frames,
+            x, c = self._transformer_fwd(M.attn, x, spatial=True, n_img=n_img, hw=hw, batch=b, frames=frames,
                                          ctx_kv=ctx_kv, tok_cols=tok_cols, want_tok=key in keys, last=key == last_key,
                                          dense=dense)
             tape.append(("attn", M.attn, c, key if key in keys else None))
             done = key == last_key
         if not done:
             M = w["mid"]
-            x, c = self._transformer_fwd(M.tattn, x, spatial=False, n_img=n_img, hw=hw, batch=1, frames=frames)
+            x, c = self._transformer_fwd(M.tattn, x, spatial=False, n_img=n_img, hw=hw, batch=b, frames=frames)
             tape.append(("tattn", M.tattn, c, None))
             x, c = self._resnet_fwd(M.res1, x, n_img, h, w_, temb_all)
             tape.append(("resnet", M.res1, c, None))
-            x, c = self._tconv_fwd(M.tconv1, x, 1, frames, hw)
+            x, c = self._tconv_fwd(M.tconv1, x, b, frames, hw)
             tape.append(("tconv", M.tconv1, c, None))
             for i in range(nb):
                 blk = w["up"][i]
@@ -413,19 +422,22 @@ class GuidanceGraph:
                 if slots is not None and (H, W) in slots:  # static tables of a captured graph
                     tabs = slots[(H, W)]
                 else:
-                    tabs = build_slots(bboxes, object_positions, frames, H, W, dev, pad_to=n_pad, fold_objects=True)
+                    tabs = build_slots_batch(layouts, frames, H, W, dev, pad_to=n_pad)
                     if slots is not None:
                         slots[(H, W)] = tabs
                 if dense:
                     seeds[key] = map_energy(bc.p_full, loss, bboxes, object_positions, base_attn_dim, opts, pre,
-                                            out_scale=out_scale, want_grad=True, grad_scale=GRAD_SCALE, tables=tabs)
+                                            out_scale=out_scale, want_grad=True, grad_scale=GRAD_SCALE,
+                                            tables=tabs[:3])
                     if getattr(self, "saved_attn", None) is not None:
                         self.saved_attn[key] = bc.p_full
                     continue
-                _, boxes, wts_slot = tabs
-                dp = torch.empty_like(bc.p_tok)
+                _, boxes, wts_slot, fr0, lidx = tabs
+                # b > 1: a slot's CTAs cover its own prompt's frames only -- the other frames' dE/dP must read zero
+                dp = torch.empty_like(bc.p_tok) if b == 1 else torch.zeros_like(bc.p_tok)
                 ops.box_energy(bc.p_tok, loss, boxes, wts_slot, frames=frames, heads=bc.heads, H=H, W=W,
-                               out_scale=out_scale, dp=dp, grad_scale=GRAD_SCALE, **opts)
+                               out_scale=out_scale, dp=dp, grad_scale=GRAD_SCALE, p_frames=n_img,
+                               slot_frame0=fr0 if b > 1 else None, slot_loss=lidx if b > 1 else None, **opts)
                 seeds[key] = dp
 
         # ---------------- backward
@@ -459,5 +471,5 @@ class GuidanceGraph:
                 if g is not None:
                     d = g if d is None else ops.add_rows(d, g)
         assert not gskip, sorted(gskip)
-        grad = ops.conv_in_bwd(d, w["conv_in"].w, 1, frames, latents.shape[3], latents.shape[4])
-        return loss, grad
+        grad = ops.conv_in_bwd(d, w["conv_in"].w, b, frames, latents.shape[3], latents.shape[4])
+        return (loss.reshape(()) if b == 1 else loss), grad

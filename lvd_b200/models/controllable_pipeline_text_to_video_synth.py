@@ -19,7 +19,7 @@ from typing import Any
 import torch
 
 from ..scheduler import DPMSolverMultistepScheduler
-from .pipelines import latent_backward_guidance
+from .pipelines import latent_backward_guidance, latent_backward_guidance_batch
 
 
 @dataclass
@@ -276,6 +276,18 @@ class TextToVideoSDPipeline:
         loss_attn = torch.tensor(10000.0)
         backward_guidance = custom_latent_backward_guidance if custom_latent_backward_guidance \
             else latent_backward_guidance
+        # Extension (the reference guides one prompt per call, its loss asserts n_frames == len(boxes)): with several
+        # prompts in the batch, `bboxes` / `object_positions` of backward_guidance_kwargs hold ONE LAYOUT PER PROMPT and
+        # the prompts are guided in lock-step by one batched pass per iteration (latent_backward_guidance_batch)
+        batched_guidance = backward_guidance_kwargs is not None and latents.shape[0] > 1 and \
+            custom_latent_backward_guidance is None
+        if batched_guidance:
+            if len(backward_guidance_kwargs["bboxes"]) != latents.shape[0]:
+                raise ValueError("batched guidance: backward_guidance_kwargs['bboxes'] / ['object_positions'] must hold "
+                                 f"one layout per prompt ({latents.shape[0]})")
+            if return_guidance_saved_attn:
+                raise NotImplementedError("return_guidance_saved_attn with several prompts per call")
+            loss_attn = torch.full((latents.shape[0],), 10000.0)
         fused_step = isinstance(self.scheduler, DPMSolverMultistepScheduler)
         for i, t in enumerate(timesteps):
             if i == num_grounding_steps:
@@ -284,9 +296,13 @@ class TextToVideoSDPipeline:
             if backward_guidance_kwargs is not None:
                 if guidance_type != "main":
                     raise ValueError(f"Unsupported guidance type: {guidance_type}")
-                ret = backward_guidance(self.scheduler, self.unet, cond_prompt_embeds, latents=latents, index=i, t=t,
-                                        loss=loss_attn, return_saved_attn=return_guidance_saved_attn,
-                                        **backward_guidance_kwargs)
+                if batched_guidance:
+                    ret = latent_backward_guidance_batch(self.scheduler, self.unet, cond_prompt_embeds, latents=latents,
+                                                         index=i, t=t, loss=loss_attn, **backward_guidance_kwargs)
+                else:
+                    ret = backward_guidance(self.scheduler, self.unet, cond_prompt_embeds, latents=latents, index=i,
+                                            t=t, loss=loss_attn, return_saved_attn=return_guidance_saved_attn,
+                                            **backward_guidance_kwargs)
                 latents, loss_attn = ret[0], ret[1]
                 if guidance_callback is not None and i % callback_steps == 0:
                     guidance_callback(i, t, latents, None, ret[2] if return_guidance_saved_attn else None)

@@ -82,3 +82,53 @@ def latent_backward_guidance(scheduler, unet, cond_embeddings, index, bboxes, ob
                                     "with a value")
         return latents, loss, saved_to_return
     return latents, loss
+
+
+def latent_backward_guidance_batch(scheduler, unet, cond_embeddings, index, bboxes, object_positions, t, latents, loss,
+                                   loss_scale=30, loss_threshold=0.2, max_iter=5, max_index_step=10,
+                                   guidance_attn_keys=None, verbose=False, **kwargs):
+    """B prompts guided in lock-step (an extension of this repo: the reference guides one prompt per call).  `latents`
+    (B, 4, F, h, w), `cond_embeddings` (B, 77, D), `bboxes` / `object_positions` = one layout per prompt, `loss` = B
+    carried losses (CPU tensor / list).  Per prompt this evaluates exactly the while-loop of latent_backward_guidance
+    (models/pipelines.py:59-137) -- same threshold test, same iteration cap, same update -- but every iteration is ONE
+    batched guidance pass over all B prompts; a prompt whose loop has ended keeps its latents and its loss while the
+    others continue.  Host syncs: one B-float device-to-host copy per iteration."""
+    energy_options(kwargs)
+    b = latents.shape[0]
+    loss = torch.as_tensor(loss, dtype=torch.float32).reshape(-1).clone().cpu()
+    if loss.numel() == 1 and b > 1:
+        loss = loss.expand(b).clone()
+    assert loss.numel() == b and len(bboxes) == b and len(object_positions) == b
+    if index >= max_index_step:
+        return latents, loss
+    if isinstance(max_iter, list):
+        max_iter = max_iter[index]
+    graph = _graph_for(unet)
+    iteration = [0] * b
+    t_int = int(t)
+    if hasattr(scheduler, "alphas_cumprod"):
+        scale = (1 - float(scheduler.alphas_cumprod[t_int])) ** 0.5
+    else:
+        scale = 1.0
+
+    def active(i):
+        return loss[i].item() / loss_scale > loss_threshold and iteration[i] < max_iter
+
+    while any(active(i) for i in range(b)):
+        act = [active(i) for i in range(b)]
+        x = scheduler.scale_model_input(latents, t)
+        new_loss, grad = graph.run(x, t, cond_embeddings, bboxes, object_positions, guidance_attn_keys,
+                                   loss_scale=loss_scale, **kwargs)
+        cur = latents.to(device=grad.device, dtype=torch.float16).contiguous()
+        new_lat, _ = ops.latent_update(cur, grad, scale, 1.0 / GRAD_SCALE)
+        keep = torch.tensor(act, device=grad.device).reshape(b, 1, 1, 1, 1)
+        latents = torch.where(keep, new_lat, cur)  # selection only: prompts whose loop has ended keep their latents
+        host = new_loss.reshape(-1).cpu()
+        for i in range(b):
+            if act[i]:
+                loss[i] = host[i]
+                iteration[i] += 1
+        if verbose:
+            print(f"time index {index}, losses: {[round(v / loss_scale, 3) for v in loss.tolist()]}, iterations: "
+                  f"{iteration}")
+    return latents, loss

@@ -446,7 +446,7 @@ LOSS_MAX, LOSS_RATIO, LOSS_CE = 0, 1, 2
 def box_energy(p, loss, boxes, slot_weight, *, frames, heads, H, W, slot_col=None, n_text=0, fg_top_p=0.2,
                bg_top_p=0.2, fg_weight=1.0, bg_weight=1.0, com_loss_scale=0.0, out_scale=1.0, dp=None,
                grad_scale=1.0, loss_kind=LOSS_MAX, k_min=1, eps=1.0e-2, attn_sync_weight=0.0, boxdiff_loss_scale=0.0,
-               boxdiff_normed=True, boxdiff_L=1):
+               boxdiff_normed=True, boxdiff_L=1, p_frames=0, slot_frame0=None, slot_loss=None):
     """Accumulate the box energy of one attention map into `loss` (0-d fp32 CUDA tensor) and optionally write
     grad_scale * dE/dP into `dp`.  slot_col given -> `p` is the full map [F, heads, hw, n_text]; otherwise `p` holds
     token columns [n_slots, F, heads, hw]."""
@@ -469,6 +469,9 @@ def box_energy(p, loss, boxes, slot_weight, *, frames, heads, H, W, slot_col=Non
     d.loss_kind, d.k_min = int(loss_kind), int(k_min)
     d.boxdiff_normed, d.boxdiff_L = 1 if boxdiff_normed else 0, int(boxdiff_L)
     d.eps, d.attn_sync_weight, d.boxdiff_loss_scale = float(eps), float(attn_sync_weight), float(boxdiff_loss_scale)
+    d.p_frames = int(p_frames)
+    d.slot_frame0 = slot_frame0.data_ptr() if slot_frame0 is not None else None
+    d.slot_loss = slot_loss.data_ptr() if slot_loss is not None else None
     with _Timed("box_energy", 0.0, 2.0 * p.numel()):
         _lib.check(_lib.lib().lvd_box_energy(ctypes.byref(d), _stream()), "box_energy")
     return loss

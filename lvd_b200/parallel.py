@@ -58,14 +58,26 @@ def max_over_ranks(value, device):
     return float(t[0])
 
 
-def generate_sharded(generate_fn, layouts, device, *, repeats=1, seed_offset=0):
+def generate_sharded(generate_fn, layouts, device, *, repeats=1, seed_offset=0, stats=None, batch=1):
     """The batch-of-prompts driver of SURVEY.md section 8(e): rank 0 holds `layouts` (one entry per prompt: a dict with
     `bboxes` [n_obj][F][4] floats and `object_positions` [n_obj][n_tok] ints); the work table (prompt index, repeat,
     seed) and the packed box tables are broadcast, every rank generates its contiguous window with
     `generate_fn(seed, bboxes, object_positions) -> uint8 [F, H, W, 3]` (the pipeline call; no collective inside), and
-    the frames are gathered on rank 0 in item order.  Returns (frames uint8 [n_items, F, H, W, 3] | None, table)."""
+    the frames are gathered on rank 0 in item order.  Returns (frames uint8 [n_items, F, H, W, 3] | None, table).
+    `stats` (a dict) receives this rank's wall-clock seconds of the three phases: scatter, generate, gather.
+    batch > 1: the rank's window is cut into groups of up to `batch` items that go through the pipeline together --
+    `generate_fn(seeds, bboxes_per_item, positions_per_item) -> uint8 [n, F, H, W, 3]` receives lists (multi-prompt
+    batching: one UNet call per step for the whole group, guidance in lock-step)."""
+    import time
     world = dist.get_world_size() if dist.is_initialized() else 1
     rank = dist.get_rank() if world > 1 else 0
+
+    def _sync():
+        if torch.device(device).type == "cuda":
+            torch.cuda.synchronize(device)
+        return time.perf_counter()
+
+    t_start = _sync()
     if rank == 0:
         n_prompts = len(layouts)
         rows = [(p, r, seed_for(p, r, seed_offset)) for p in range(n_prompts) for r in range(repeats)]
@@ -97,15 +109,26 @@ def generate_sharded(generate_fn, layouts, device, *, repeats=1, seed_offset=0):
         dist.broadcast(toks, src=0)
     n_items = table.shape[0]
     lo, hi = shard_items(n_items, rank, world)
+    t_scattered = _sync()
     outs = []
+    items = []
     for i in range(lo, hi):
         p, _, seed = (int(v) for v in table[i].tolist())
         pos = [[int(t) for t in row.tolist() if t >= 0] for row in toks[p]]
         keep = [o for o, t in enumerate(pos) if len(t) > 0]
         bb = [[tuple(float(v) for v in fr) for fr in boxes[p, o].tolist()] for o in keep]
-        outs.append(generate_fn(seed, bb, [pos[o] for o in keep]))
+        items.append((seed, bb, [pos[o] for o in keep]))
+    if batch <= 1:
+        for seed, bb, pos in items:
+            outs.append(torch.as_tensor(generate_fn(seed, bb, pos)))
+    else:
+        for k in range(0, len(items), batch):
+            grp = items[k:k + batch]
+            res = torch.as_tensor(generate_fn([g[0] for g in grp], [g[1] for g in grp], [g[2] for g in grp]))
+            assert res.shape[0] == len(grp)
+            outs.extend(res[j] for j in range(len(grp)))
     if outs:
-        local = torch.stack([torch.as_tensor(o) for o in outs]).to(device)
+        local = torch.stack(outs).to(device)
     else:  # a rank with an empty window still takes part in the gather (shape from a broadcast of rank 0's)
         local = None
     shape = torch.tensor(list(local.shape[1:]) if local is not None else [0, 0, 0, 0], dtype=torch.int64, device=device)
@@ -113,4 +136,10 @@ def generate_sharded(generate_fn, layouts, device, *, repeats=1, seed_offset=0):
         dist.all_reduce(shape, op=dist.ReduceOp.MAX)
     if local is None:
         local = torch.empty((0,) + tuple(int(v) for v in shape.tolist()), dtype=torch.uint8, device=device)
-    return gather_results(local, n_items), table
+    t_generated = _sync()
+    out = gather_results(local, n_items)
+    t_done = _sync()
+    if stats is not None:
+        stats.update(scatter_s=t_scattered - t_start, generate_s=t_generated - t_scattered, gather_s=t_done - t_generated,
+                     items=hi - lo)
+    return out, table

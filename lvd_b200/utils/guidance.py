@@ -159,6 +159,35 @@ def build_slots(bboxes, object_positions, n_frames, H, W, device, pad_to=None, f
             torch.tensor(wts, dtype=torch.float32, device=device))
 
 
+def build_slots_batch(layouts, n_frames, H, W, device, pad_to=None):
+    """Slot tables of a batch of prompts guided in one pass: `layouts` = [(bboxes, object_positions)] per prompt.
+    Returns (cols, boxes, weights, frame0, loss_index): the tables of `build_slots` (1 / n_objects folded in, per
+    prompt) concatenated over the prompts, plus per slot the first frame of its prompt inside the batched frame axis
+    and the index of its prompt's loss accumulator."""
+    cols, boxes, wts, fr0, lidx = [], [], [], [], []
+    for b, (bb, pos) in enumerate(layouts):
+        if len(bb) == 0:
+            continue
+        c, r, w = build_slots(bb, pos, n_frames, H, W, torch.device("cpu"), fold_objects=True)
+        cols.append(c)
+        boxes.append(r)
+        wts.append(w)
+        fr0 += [b * n_frames] * c.numel()
+        lidx += [b] * c.numel()
+    cols, boxes, wts = torch.cat(cols), torch.cat(boxes), torch.cat(wts)
+    n = cols.numel()
+    if pad_to is not None and pad_to > n:
+        k = pad_to - n
+        cols = torch.cat([cols, cols[:1].expand(k)])
+        boxes = torch.cat([boxes, torch.zeros((k, n_frames, 4), dtype=torch.int32)])
+        wts = torch.cat([wts, torch.zeros(k)])
+        fr0 += [0] * k
+        lidx += [0] * k
+    dev = torch.device(device)
+    return (cols.contiguous().to(dev), boxes.contiguous().to(dev), wts.contiguous().to(dev),
+            torch.tensor(fr0, dtype=torch.int32, device=dev), torch.tensor(lidx, dtype=torch.int32, device=dev))
+
+
 def _lossv3(saved_attn, bboxes, object_positions, guidance_attn_keys, want_grad, grad_scale, kwargs):
     opts, pre = energy_options(kwargs, with_pre=True)
     dev = torch.device("cuda", torch.cuda.current_device())

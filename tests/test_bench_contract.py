@@ -31,7 +31,14 @@ def test_defaults_and_workloads(monkeypatch):
 
 def test_reference_arm_json_line(monkeypatch):
     import bench
-    monkeypatch.setattr(bench, "cpu_reference_step", lambda frames, steps, warmup, ge=5: (0.5, 4.0, 16, 6.0, 3.5))
+    seen = {}
+
+    def fake(sample_frames, pattern, warmup, budget_s=240.0):
+        seen.update(pattern=list(pattern), warmup=warmup)
+        return dict(frames_per_s=0.5, sec_per_step=4.0, cores=16, sec_guided=6.0, sec_unguided=3.5, sample_frames=8,
+                    steps=len(pattern), warmup=warmup)
+
+    monkeypatch.setattr(bench, "cpu_reference_step", fake)
     monkeypatch.setattr(sys, "argv", ["bench.py", "--impl", "reference", "--steps", "2", "--warmup", "1"])
     monkeypatch.setenv("RANK", "0")
     buf = io.StringIO()
@@ -43,6 +50,9 @@ def test_reference_arm_json_line(monkeypatch):
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] == 16
     assert line["e2e"] == {"value": 0.5, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert line["config"]["workload"] == bench._workload("lvd_zeroscope")
+    # --steps / --warmup are honoured exactly and reported as executed; the step mix is guided iff i % 5 == 0
+    assert seen == {"pattern": [True, False], "warmup": 1} and line["steps"] == 2 and line["warmup"] == 1
+    assert line["config"]["sample_frames"] == 8 and "first 8 of the 24 frames" in line["cpu_baseline"]["sample"]
     # ranks other than 0 print nothing
     monkeypatch.setenv("RANK", "1")
     buf = io.StringIO()

@@ -259,3 +259,68 @@ def test_guidance_graph_is_shared_across_layouts(cuda):
         assert torch.equal(g0, g1), i
     assert sum(1 for v in graphed._graphs.values() if v != "seen") == 1
     assert len(graphed._graphs) == 1
+
+
+def test_batched_guidance_matches_per_prompt_passes(cuda):
+    """Multi-prompt batching: B prompts with different layouts guided by ONE pass give, per
+    prompt, the loss and dE/dlatent of B separate passes (GEMM rows are computed independently of the row count; only the
+    GroupNorm partial-sum grouping of the 5-D norms changes with the batch -- fp32 rounding)."""
+    from lvd_b200.engine import UNetEngine
+    from lvd_b200.guidance_engine import GuidanceGraph
+    from oracle import unet3d_ref as R
+    from oracle import weights
+    cfg = weights.make_cfg("tiny")
+    eng = UNetEngine(cfg, weights.random_state_dict(cfg, seed=81), device=cuda)
+    gen = torch.Generator().manual_seed(82)
+    B, F, h, w = 3, 8, 16, 16
+    keys = R.GUIDANCE_KEYS_DEFAULT
+    hp = dict(loss_scale=5.0, base_attn_dim=(h, w), fg_top_p=0.75, bg_top_p=0.75, fg_weight=1.0, bg_weight=4.0,
+              com_loss_scale=0.03)
+    x = torch.randn((B, 4, F, h, w), generator=gen).half().to(cuda)
+    ehs = torch.randn((B, 77, 128), generator=gen).half().to(cuda)
+    bboxes = [[[(0.1 + 0.03 * f, 0.2, 0.6, 0.7) for f in range(F)]],
+              [[(0.5, 0.1, 0.9, 0.5 + 0.02 * f) for f in range(F)], [(0.0, 0.5, 0.4, 1.0)] * F],
+              [[(0.2, 0.2, 0.8, 0.8) if f % 3 else (0, 0, 0, 0) for f in range(F)], [(0.6, 0.6, 1.0, 1.0)] * F,
+               [(0.0, 0.0, 0.3, 0.3)] * F]]
+    positions = [[[2]], [[3], [5, 6]], [[1], [4], [8, 9]]]
+    gg = GuidanceGraph(eng)
+    for rep in range(3):  # eager, capture, replay
+        lb, gb = gg.run(x, 600, ehs, bboxes, positions, keys, **hp)
+        assert lb.shape == (B,) and gb.shape == x.shape
+        single = GuidanceGraph(eng)
+        single.use_cuda_graph = False
+        for i in range(B):
+            li, gi = single.run(x[i:i + 1], 600, ehs[i:i + 1], bboxes[i], positions[i], keys, **hp)
+            assert abs(li.item() - lb[i].item()) <= 2e-4 * abs(li.item()), (rep, i, li.item(), lb[i].item())
+            cos, rel = _cmp(gb[i:i + 1], gi)
+            assert cos >= 0.99999 and rel <= 3e-3, (rep, i, cos, rel)
+
+
+def test_latent_backward_guidance_batch_lockstep(cuda):
+    """Per prompt the batched driver runs the reference's while-loop: a prompt below the threshold is left untouched,
+    the others iterate up to max_iter; results match the one-prompt mirror."""
+    from lvd_b200.engine import UNetEngine
+    from lvd_b200.models.pipelines import latent_backward_guidance, latent_backward_guidance_batch
+    from oracle import unet3d_ref as R
+    from oracle import weights
+    from oracle.make_golden import FakeScheduler
+    cfg = weights.make_cfg("tiny")
+    eng = UNetEngine(cfg, weights.random_state_dict(cfg, seed=83), device=cuda)
+    gen = torch.Generator().manual_seed(84)
+    B, F, h, w = 3, 8, 16, 16
+    x = torch.randn((B, 4, F, h, w), generator=gen).half().to(cuda)
+    ehs = torch.randn((B, 77, 128), generator=gen).half().to(cuda)
+    bboxes = [[[(0.1, 0.2, 0.6, 0.7)] * F], [[(0.5, 0.1, 0.9, 0.6)] * F, [(0.0, 0.5, 0.4, 1.0)] * F],
+              [[(0.2, 0.2, 0.8, 0.8)] * F]]
+    positions = [[[2]], [[3], [5, 6]], [[4]]]
+    kw = dict(loss_scale=2.5, loss_threshold=0.5, max_iter=2, max_index_step=10,
+              guidance_attn_keys=R.GUIDANCE_KEYS_DEFAULT, base_attn_dim=(h, w), fg_top_p=0.25, bg_top_p=0.25)
+    start = torch.tensor([10000.0, 1.0, 10000.0])  # prompt 1 starts below the threshold (1.0 / 2.5 < 0.5)
+    lat, loss = latent_backward_guidance_batch(FakeScheduler(), eng, ehs, 0, bboxes, positions, 500, x, start, **kw)
+    assert torch.equal(lat[1], x[1]) and loss[1].item() == 1.0
+    for i in (0, 2):
+        li, ls = latent_backward_guidance(FakeScheduler(), eng, ehs[i:i + 1], 0, bboxes[i], positions[i], 500,
+                                          x[i:i + 1], start[i], **kw)
+        assert abs(ls.item() - loss[i].item()) <= 1e-3 * abs(ls.item())
+        d, dr = lat[i].float() - x[i].float(), li[0].float() - x[i].float()
+        assert ((d - dr).norm() / dr.norm()).item() <= 0.02

@@ -7,7 +7,7 @@ against the oracle restatement run on the same GPU in fp32 (TF32 off) AND in fp1
 GPU: the comparison SURVEY.md section 8(c) names).  Every comparison prints max-normalised, RMS-relative and
 median / p99.9 / max element-wise errors (conftest.err_stats), so the north_star "1e-3 relative fp16" can be judged.
 
-What the numbers say (B200, profiles/r2_parity_fullsize.txt).  fp16 evaluation of this ~250-layer graph is itself only
+What the numbers say (B200, profiles/r2b_parity_fullsize.txt).  fp16 evaluation of this ~250-layer graph is itself only
 reproducible to ~2e-3: the reference's own graph in fp16 (torch) differs from its fp32 evaluation by ||d||/||ref|| =
 2.2-2.4e-3, the engine by 1.9-2.1e-3, and the two fp16 runs differ from each other by 2.8-3.1e-3 (independent rounding
 noise adds in quadrature).  north_star's "1e-3 relative fp16" is therefore below the noise floor of ANY fp16 run of the

@@ -4,9 +4,9 @@
 #   2. the bench line + per-kernel-family profile of the headline workload,
 #   3. (FULL=1) the other BASELINE workloads and the kernel micro-benchmarks.
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_parity_fullsize.py -m gpu -q --no-header -p no:cacheprovider -s > gpurun_out/parity.log 2>&1
+timeout 600 python -m pytest tests/test_parity_fullsize.py -m gpu --timeout 300 -q --no-header -p no:cacheprovider -s > gpurun_out/parity.log 2>&1
 grep -v "^$" gpurun_out/parity.log | tail -60
-timeout 900 python -m pytest tests -m gpu -q --no-header -p no:cacheprovider -x --deselect tests/test_parity_fullsize.py -s > gpurun_out/tests.log 2>&1
+timeout 900 python -m pytest tests -m gpu --timeout 180 -q --no-header -p no:cacheprovider -x --deselect tests/test_parity_fullsize.py -s > gpurun_out/tests.log 2>&1
 tail -4 gpurun_out/tests.log
 grep "^\[" gpurun_out/tests.log | head -40
 timeout 500 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --profile-json gpurun_out/prof.json \
