@@ -107,6 +107,9 @@ def parse():
     ap.add_argument("--no-prompt-batch", action="store_true",
                     help="skip the prompt-batch measurement (parallel.generate_sharded: scatter + videos + gather)")
     ap.add_argument("--batch-prompts-per-gpu", type=int, default=3)
+    ap.add_argument("--prompts-per-call", type=int, default=1,
+                    help="multi-prompt batching of the prompt batch: prompts per pipeline call (one CFG UNet call of "
+                         "2 x this many videos per step, guidance in lock-step)")
     ap.add_argument("--profile-json", default=None, help="write the per-kernel-family breakdown here")
     ap.add_argument("--no-video", action="store_true", help="alias of --no-prompt-batch")
     return ap.parse_args()
@@ -504,27 +507,48 @@ def run_gpu(args):
                     output_type="np", gligen_scheduled_sampling_beta=0.4)
 
         def generate(seed, bboxes_, positions_, steps=50):
-            gen = torch.Generator().manual_seed(int(seed))
-            lat0 = torch.randn((1, 4, frames, lat_h, lat_w), generator=gen).half()
-            kw_ = dict(call, num_inference_steps=steps, latents=lat0)
+            """One pipeline call: a single prompt (scalars) or a group of prompts (lists, multi-prompt batching)."""
+            many = isinstance(seed, (list, tuple))
+            seeds = list(seed) if many else [seed]
+            lays = list(zip(bboxes_, positions_)) if many else [(bboxes_, positions_)]
+            nb = len(seeds)
+            lat0 = torch.cat([torch.randn((1, 4, frames, lat_h, lat_w),
+                                          generator=torch.Generator().manual_seed(int(sd_))).half() for sd_ in seeds])
+            kw_ = dict(call, num_inference_steps=steps, latents=lat0,
+                       prompt_embeds=ehs_host[1:2].expand(nb, -1, -1).contiguous(),
+                       negative_prompt_embeds=ehs_host[0:1].expand(nb, -1, -1).contiguous())
             if guided_every:
-                kw_["backward_guidance_kwargs"] = dict(guidance_kw, bboxes=bboxes_, object_positions=positions_)
+                kw_["backward_guidance_kwargs"] = dict(
+                    guidance_kw, bboxes=[l[0] for l in lays] if many else lays[0][0],
+                    object_positions=[l[1] for l in lays] if many else lays[0][1])
             if wl["gated"]:
-                kw_["gligen_inputs"] = gligen_inputs(frames, bboxes_, dev, gen)
-            fr = pipe(**kw_).frames  # np.float32 [1, F, H, W, 3] in [0, 1]
-            return torch.from_numpy((fr[0] * 255.0 + 0.5).clip(0, 255).astype("uint8"))
+                gen = torch.Generator().manual_seed(int(seeds[0]))
+                per = [gligen_inputs(frames, l[0], dev, gen) for l in lays]  # each: rows [uncond F | cond F]
+                kw_["gligen_inputs"] = {k: torch.cat([p_[k][:frames] for p_ in per] + [p_[k][frames:] for p_ in per])
+                                        for k in per[0]}
+            fr = pipe(**kw_).frames  # np.float32 [nb, F, H, W, 3] in [0, 1]
+            u8 = torch.from_numpy((fr * 255.0 + 0.5).clip(0, 255).astype("uint8"))
+            return u8 if many else u8[0]
 
         n_items = args.batch_prompts_per_gpu * world
         layouts = prompt_batch_layouts(n_items, frames)
         from lvd_b200.utils.guidance import padded_slot_count
         slots_of = lambda l: padded_slot_count(sum(len(t) for t in l["object_positions"]))  # noqa: E731
-        for n_pad in sorted({slots_of(l) for l in layouts}):  # warm-up items: one short run per slot-table size
-            l = next(l for l in layouts if slots_of(l) == n_pad)
-            generate(0, l["bboxes"], l["object_positions"], steps=6)
+        ppc = max(1, args.prompts_per_call)
+        if ppc == 1:
+            for n_pad in sorted({slots_of(l) for l in layouts}):  # warm-up items: one short run per slot-table size
+                l = next(l for l in layouts if slots_of(l) == n_pad)
+                generate(0, l["bboxes"], l["object_positions"], steps=6)
+        else:  # warm-up: this rank's own groups, shortened (same group sizes / padded slot counts as the timed run)
+            lo_, hi_ = parallel.shard_items(n_items, rank, world)
+            for k in range(lo_, hi_, ppc):
+                grp = layouts[k:min(k + ppc, hi_)]
+                generate([0] * len(grp), [l["bboxes"] for l in grp], [l["object_positions"] for l in grp], steps=6)
         barrier()
         stats = {}
         t0 = time.perf_counter()
-        frames_u8, table = parallel.generate_sharded(generate, layouts if rank == 0 else None, dev, stats=stats)
+        frames_u8, table = parallel.generate_sharded(generate, layouts if rank == 0 else None, dev, stats=stats,
+                                                     batch=ppc)
         torch.cuda.synchronize()
         sec = time.perf_counter() - t0
         tv = torch.tensor([sec, stats["generate_s"], stats["gather_s"], stats["scatter_s"]], dtype=torch.float64,
@@ -538,7 +562,7 @@ def run_gpu(args):
         if rank == 0:
             ok = frames_u8 is not None and tuple(frames_u8.shape) == (n_items, frames, lat_h * 8, lat_w * 8, 3)
             prompt_batch = {
-                "items": n_items, "items_per_gpu": args.batch_prompts_per_gpu, "seconds": sec,
+                "items": n_items, "items_per_gpu": args.batch_prompts_per_gpu, "prompts_per_call": ppc, "seconds": sec,
                 "videos_per_s": n_items / sec, "frames_per_s": n_items * frames / sec,
                 "generate_s_max_rank": gen_max, "generate_s_min_rank": gen_min,
                 "imbalance": (gen_max - gen_min) / gen_max if gen_max > 0 else 0.0,

@@ -408,6 +408,265 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid
   }
 }
 
+// ------------------------------------------------------------------------------------------------ spatial self-attention
+// Multi-unit (s_k > 128) softmax(Q K^T) V, the UNet's spatial self-attention (hw = 2880 / 720 / 180 keys).  Same
+// TMA producer / single-thread MMA issuer as attention_kernel, but the softmax side is restructured around what bounded
+// that kernel (4 softmax warps per CTA, a serial S -> softmax -> P V -> read O chain per 128-key unit, O accumulated
+// in registers: tensor pipe 17 % busy):
+//   * EIGHT softmax warps: two threads per score row, each owning one 64-key half of the unit (TMEM lanes are tied to
+//     warp_id % 4, columns are free) -> 4 softmax warps per SM sub-partition with two resident CTAs;
+//   * each half runs its OWN online softmax (m, l) and its own accumulator O_a / O_b in TMEM (keys 0-63 / 64-127 of every
+//     unit: a split over the key axis, combined exactly at the end), so the two threads of a row never exchange
+//     anything inside the loop;
+//   * O stays in TMEM: the P V product ACCUMULATES into it across units.  The reference point m of the exponentials is
+//     only moved when the running maximum grows by more than 2^8 (probabilities then stay <= 256, exact in fp16 to the
+//     same 11 bits); only then is the accumulator rescaled in place (tcgen05.ld / st).  After the first unit this is
+//     rare, so the per-unit chain is S -> two TMEM passes (max, exp2 -> fp16 -> smem) -> P V, with no accumulator
+//     read-back and no register-resident O.
+// Ordering notes: the tensor pipe executes in issue order and tcgen05.commit covers everything issued before it, so
+// s_full(u) also tells the softmax warps that P V of unit u-1 has finished reading the P tile and updating O.
+constexpr int kSelfThreads = 320;
+constexpr float kRescaleLog2 = 8.0f;
+
+__global__ void __launch_bounds__(kSelfThreads, 2) attention_self_kernel(const __grid_constant__ AttnArgs g) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t* sQ = smem;
+  uint8_t* sK = smem + kTile;      // 2 stages
+  uint8_t* sV = smem + 3 * kTile;  // 2 stages
+  uint8_t* sP = smem + 5 * kTile;  // 2 column blocks of 64
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 7 * kTile);
+  uint64_t* q_full = bars + 0;
+  uint64_t* kv_full = bars + 1;   // [2]
+  uint64_t* kv_empty = bars + 3;  // [2]
+  uint64_t* s_full = bars + 5;
+  uint64_t* p_full = bars + 6;
+  uint64_t* o_full = bars + 7;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 8);
+  const int h = blockIdx.x, qt = blockIdx.y, z = blockIdx.z;
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  if (g.q_bytes < kTile || g.kv_bytes < kTile) {
+    uint4 zero = make_uint4(0, 0, 0, 0);
+    for (int i = threadIdx.x; i < 5 * kTile / 16; i += kSelfThreads) reinterpret_cast<uint4*>(smem)[i] = zero;
+    fence_proxy_async_smem();
+  }
+  if (threadIdx.x == 0) {
+    mbar_init(q_full, 1);
+    mbar_init(&kv_full[0], 1);
+    mbar_init(&kv_full[1], 1);
+    mbar_init(&kv_empty[0], 1);
+    mbar_init(&kv_empty[1], 1);
+    mbar_init(s_full, 1);
+    mbar_init(p_full, 256);
+    mbar_init(o_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&g.map_q);
+    tma_prefetch_desc(&g.map_kv);
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_holder, 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+  const uint32_t tmem_s = tmem_base, tmem_o = tmem_base + 128;  // O_a at +128, O_b at +192
+  const int zk = z / g.kv_z_div;
+  const int n_units = g.n_units;
+
+  if (warp == 0) {
+    if (elect_one_sync()) {
+      mbar_arrive_expect_tx(q_full, static_cast<uint32_t>(g.q_bytes));
+      tma_load_4d(sQ, &g.map_q, q_full, g.q_col0 + h * 64, qt * g.qb1, 0, z);
+    }
+    __syncwarp();
+    for (int u = 0; u < n_units; ++u) {
+      const int st = u & 1;
+      mbar_wait(&kv_empty[st], ((u >> 1) & 1) ^ 1u);
+      if (elect_one_sync()) {
+        mbar_arrive_expect_tx(&kv_full[st], static_cast<uint32_t>(2 * g.kv_bytes));
+        tma_load_4d(sK + st * kTile, &g.map_kv, &kv_full[st], g.k_col0 + h * 64, u * 128, 0, zk);
+        tma_load_4d(sV + st * kTile, &g.map_kv, &kv_full[st], g.v_col0 + h * 64, u * 128, 0, zk);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    mbar_wait(q_full, 0);
+    const uint32_t desc_hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+    const uint32_t q_lo = ((smem_u32(sQ) & 0x3FFFFu) >> 4) | (1u << 16);
+    const uint32_t p_lo = ((smem_u32(sP) & 0x3FFFFu) >> 4) | (1u << 16);
+    const uint32_t k_lo0 = ((smem_u32(sK) & 0x3FFFFu) >> 4) | (1u << 16);
+    const uint32_t v_lo0 = ((smem_u32(sV) & 0x3FFFFu) >> 4) | ((8192u >> 4) << 16);  // V is MN-major: [kv][d]
+    const uint32_t idesc_pv = g.idesc_pv;
+    for (int u = 0; u < n_units; ++u) {
+      const int st = u & 1;
+      const bool last = (u == n_units - 1);
+      const int ksteps = (last ? g.last_cols16 : 128) / 16;
+      const uint32_t idesc_qk = last ? g.idesc_qk_last : g.idesc_qk_full;
+      mbar_wait(&kv_full[st], (u >> 1) & 1);
+      tc_fence_after();
+      if (elect_one_sync()) {
+        const uint32_t k_lo = k_lo0 + static_cast<uint32_t>(st) * (kTile >> 4);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_f16(tmem_s, (static_cast<uint64_t>(desc_hi) << 32) | (q_lo + 2u * k),
+                   (static_cast<uint64_t>(desc_hi) << 32) | (k_lo + 2u * k), idesc_qk, k != 0 ? 1u : 0u);
+        umma_commit(s_full);
+      }
+      __syncwarp();
+      mbar_wait(p_full, u & 1);
+      tc_fence_after();
+      if (elect_one_sync()) {
+        const uint32_t v_lo = v_lo0 + static_cast<uint32_t>(st) * (kTile >> 4);
+        for (int ks = 0; ks < ksteps; ++ks) {
+          const uint64_t da = (static_cast<uint64_t>(desc_hi) << 32) |
+                              (p_lo + static_cast<uint32_t>((ks >> 2) * (kTile >> 4) + (ks & 3) * 2));
+          const uint64_t db = (static_cast<uint64_t>(desc_hi) << 32) | (v_lo + static_cast<uint32_t>(ks) * (2048u >> 4));
+          // keys 0-63 of the unit accumulate into O_a, keys 64-127 into O_b; the first product of each overwrites
+          umma_f16(tmem_o + static_cast<uint32_t>(ks >> 2) * 64u, da, db, idesc_pv,
+                   (u != 0 || (ks & 3) != 0) ? 1u : 0u);
+        }
+        umma_commit(&kv_empty[st]);
+        if (last) umma_commit(o_full);
+      }
+      __syncwarp();
+    }
+  } else {
+    const int q = warp & 3;            // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;  // key half of every unit / accumulator owned by this thread
+    const int r = q * 32 + lane;
+    const int c1 = qt * g.qb1 + r;
+    const bool row_valid = (r < g.qb1) && (c1 < g.q_dim1);
+    const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+    const uint32_t my_s = tmem_s + lane_off + static_cast<uint32_t>(half) * 64u;
+    const uint32_t my_o = tmem_o + lane_off + static_cast<uint32_t>(half) * 64u;
+    const float sc = g.scale_log2;
+    uint8_t* p_blk = sP + half * kTile + r * 128;
+    float m_used = -INFINITY, l_run = 0.f;
+
+    for (int u = 0; u < n_units; ++u) {
+      int nvalid = g.kv_total - u * 128 - half * 64;  // valid keys among this thread's 64
+      nvalid = nvalid > 64 ? 64 : (nvalid < 0 ? 0 : nvalid);
+      mbar_wait(s_full, u & 1);
+      tc_fence_after();
+      // ---- pass 1: maximum of this thread's 64 scores
+      float mx = -INFINITY;
+#pragma unroll
+      for (int ch = 0; ch < 2; ++ch) {
+        uint32_t rr[32];
+        tmem_ld32(my_s + ch * 32, rr);
+        tmem_ld_wait();
+        if (nvalid == 64) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(rr[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, (ch * 32 + i < nvalid) ? __uint_as_float(rr[i]) : -INFINITY);
+        }
+      }
+      const float m_cand = fmaxf(m_used, mx * sc);  // sc > 0
+      const bool move = (m_cand - m_used) > kRescaleLog2;  // first unit: m_used = -inf
+      if (u > 0 && __any_sync(0xffffffffu, move)) {
+        // rare: move the reference point of the rows that need it and rescale their accumulator rows in TMEM
+        // (s_full(u) implies P V of unit u-1 is complete, see the header)
+        const float f = move ? fast_exp2(m_used - m_cand) : 1.f;
+#pragma unroll
+        for (int hl = 0; hl < 2; ++hl) {
+          uint32_t rr[32];
+          tmem_ld32(my_o + hl * 32, rr);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) rr[i] = __float_as_uint(__uint_as_float(rr[i]) * f);
+          tmem_st32(my_o + hl * 32, rr);
+        }
+        tmem_st_wait();
+        l_run *= f;
+      }
+      if (move) m_used = m_cand;
+      // ---- pass 2: probabilities relative to m_used -> fp16 -> swizzled smem (A operand of P V)
+      float psum = 0.f;
+#pragma unroll
+      for (int ch = 0; ch < 2; ++ch) {
+        uint32_t rr[32];
+        tmem_ld32(my_s + ch * 32, rr);
+        tmem_ld_wait();
+        float p[32];
+        if (nvalid == 64) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            p[i] = fast_exp2(fmaf(__uint_as_float(rr[i]), sc, -m_used));
+            psum += p[i];
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            p[i] = (ch * 32 + i < nvalid) ? fast_exp2(fmaf(__uint_as_float(rr[i]), sc, -m_used)) : 0.f;
+            psum += p[i];
+          }
+        }
+#pragma unroll
+        for (int s8 = 0; s8 < 4; ++s8) {
+          uint4 v;
+          __half2* hh = reinterpret_cast<__half2*>(&v);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) hh[i] = __floats2half2_rn(p[s8 * 8 + 2 * i], p[s8 * 8 + 2 * i + 1]);
+          const int chunk16 = (ch * 4 + s8) ^ (r & 7);
+          *reinterpret_cast<uint4*>(p_blk + chunk16 * 16) = v;
+        }
+      }
+      l_run += psum;
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(p_full);
+    }
+    // ---- combine the two key halves: O = (O_a 2^(m_a - m) + O_b 2^(m_b - m)) / (l_a 2^(m_a - m) + l_b 2^(m_b - m))
+    mbar_wait(o_full, 0);
+    tc_fence_after();
+    float2* xch = reinterpret_cast<float2*>(sQ);  // Q / K / V / P tiles are dead: every MMA has completed
+    xch[half * 128 + r] = make_float2(m_used, l_run);
+    named_bar_sync(1 + q, 64);
+    const float2 other = xch[(half ^ 1) * 128 + r];
+    const float m_a = half ? other.x : m_used, l_a = half ? other.y : l_run;
+    const float m_b = half ? m_used : other.x, l_b = half ? l_run : other.y;
+    const float m_all = fmaxf(m_a, m_b);
+    const float fa = fast_exp2(m_a - m_all), fb = fast_exp2(m_b - m_all);
+    const float l_all = l_a * fa + l_b * fb;
+    const float inv = 1.f / l_all;
+    uint32_t ra[32], rb[32];
+    tmem_ld32(tmem_o + lane_off + half * 32, ra);       // O_a, output columns [32 half, 32 half + 32)
+    tmem_ld32(tmem_o + lane_off + 64 + half * 32, rb);  // O_b, same columns
+    tmem_ld_wait();
+    if (row_valid) {
+      __half* dst = g.out + (static_cast<long long>(z) * g.o_z_stride + static_cast<long long>(c1) * g.o_d1_stride) * g.ld_o +
+                    g.o_col0 + h * 64 + half * 32;
+      const float wa = fa * inv, wb = fb * inv;
+#pragma unroll
+      for (int s8 = 0; s8 < 4; ++s8) {
+        uint4 v;
+        __half2* hh = reinterpret_cast<__half2*>(&v);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int c = s8 * 8 + 2 * i;
+          hh[i] = __floats2half2_rn(fmaf(__uint_as_float(ra[c]), wa, __uint_as_float(rb[c]) * wb),
+                                    fmaf(__uint_as_float(ra[c + 1]), wa, __uint_as_float(rb[c + 1]) * wb));
+        }
+        *reinterpret_cast<uint4*>(dst + s8 * 8) = v;
+      }
+      if (g.lse && half == 0) g.lse[(static_cast<long long>(z) * g.heads + h) * g.p_rows + c1] = m_all + log2f(l_all);
+    }
+    tc_fence_before();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
 int launch_temporal_attn_mma(const lvd_attn_desc* d, cudaStream_t stream);  // attention_temporal.cu
 int launch_cross_attn_mma(const lvd_attn_desc* d, cudaStream_t stream);     // attention_temporal.cu
 
@@ -564,6 +823,18 @@ extern "C" int lvd_attention(const lvd_attn_desc* d, void* stream) {
   const int q_tiles = (g.q_dim1 + g.qb1 - 1) / g.qb1;
   dim3 grid(d->heads, q_tiles, d->nz);
   LVD_REQUIRE(q_tiles <= 65535 && d->nz <= 65535, "lvd_attention: grid too large");
+  static const bool old_self = getenv("LVD_ATTN_SELF_OLD") != nullptr;  // A/B switch for tools/ and tests
+  if (d->mode == 0 && g.n_units >= 2 && !d->p_full && !d->p_tok && !old_self) {
+    static bool attr2 = false;
+    if (!attr2) {
+      LVD_CHECK_CUDA(cudaFuncSetAttribute(attention_self_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
+      attr2 = true;
+    }
+    attention_self_kernel<<<grid, kSelfThreads, kAttnSmem, static_cast<cudaStream_t>(stream)>>>(g);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    LVD_CHECK_CUDA(cudaGetLastError());
+    return LVD_OK;
+  }
   attention_kernel<<<grid, kAttnThreads, kAttnSmem, static_cast<cudaStream_t>(stream)>>>(g);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   LVD_CHECK_CUDA(cudaGetLastError());

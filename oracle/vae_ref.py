@@ -4,10 +4,14 @@
 `models/attention_processor.py::Attention`), the VAE behind the reference's `decode_latents`
 (models/controllable_pipeline_text_to_video_synth.py:374-400).
 
-PARITY UNPINNED: diffusers is not vendored by the reference and not installable offline, and the reference has no
-fixture for this path, so this restates the published architecture (SD-1.x VAE: block_out_channels (128, 256, 512, 512),
-layers_per_block 2, 32 groups, eps 1e-6, one attention head of width 512 in the mid block with residual connection,
-nearest-2x up-sampling + 3x3 conv after the first three up blocks, scaling_factor 0.18215).  Only tests/ and bench.py's
+PINNED against an independent public implementation that IS installed offline: transformers' `JanusVQVAEDecoder`, a port
+of the CompVis / taming-transformers `Decoder` -- the code the SD-1.x VAE was trained with, of which diffusers'
+AutoencoderKL decoder is a renaming (tests/test_vae.py::test_vae_oracle_pinned_against_transformers_compvis_decoder:
+same weights under the other naming, strict load, images equal to 2e-5 at the tiny and the published SD-1.x width:
+block_out_channels (128, 256, 512, 512), layers_per_block 2, 32 groups, eps 1e-6, one attention head of width 512 in
+the mid block with residual connection, nearest-2x up-sampling + 3x3 conv after the first three up blocks).  What stays
+unverifiable offline: diffusers' own file (not vendored by the reference, not installable) and the scaling_factor
+0.18215 / key names of the published checkpoints (restated from the published config).  Only tests/ and bench.py's
 checker legs may import this module."""
 import torch
 import torch.nn.functional as F

@@ -26,6 +26,79 @@ def test_vae_oracle_shapes_cpu():
     assert y.shape == (2, 3, 64, 64) and torch.isfinite(y).all()
 
 
+def _janus_decoder(cfg, sd):
+    """The CompVis / taming-transformers VAE decoder as shipped in the installed `transformers` (JanusVQVAEDecoder:
+    conv_in -> mid (block_1, attn_1, block_2) -> up levels of num_res_blocks + 1 ResnetBlocks with nearest-2x + conv
+    up-sampling -> norm_out -> swish -> conv_out) -- the architecture the SD-1.x VAE checkpoints were trained with and
+    that diffusers' AutoencoderKL re-implements under other parameter names.  Janus adds attention blocks to the
+    lowest-resolution up level; the SD VAE has none there (attn_resolutions = []), so they are removed.  Weights are the
+    diffusers-named tensors of `sd`, renamed."""
+    from torch import nn
+    from transformers.models.janus.configuration_janus import JanusVQVAEConfig
+    from transformers.models.janus.modeling_janus import JanusVQVAEDecoder
+    boc = list(cfg["block_out_channels"])
+    base = boc[0]
+    jc = JanusVQVAEConfig(base_channels=base, channel_multiplier=[c // base for c in boc],
+                          num_res_blocks=cfg["layers_per_block"], latent_channels=cfg["latent_channels"],
+                          out_channels=cfg["out_channels"], dropout=0.0)
+    dec = JanusVQVAEDecoder(jc).eval()
+    for lvl in dec.up:
+        lvl.attn = nn.ModuleList()
+    ren = {}
+
+    def res(src, dst):
+        for a in ("norm1", "conv1", "norm2", "conv2"):
+            for t in ("weight", "bias"):
+                ren[f"{dst}.{a}.{t}"] = sd[f"{src}.{a}.{t}"]
+        if f"{src}.conv_shortcut.weight" in sd:
+            ren[f"{dst}.nin_shortcut.weight"] = sd[f"{src}.conv_shortcut.weight"]
+            ren[f"{dst}.nin_shortcut.bias"] = sd[f"{src}.conv_shortcut.bias"]
+
+    for t in ("weight", "bias"):
+        ren[f"conv_in.{t}"] = sd[f"decoder.conv_in.{t}"]
+        ren[f"norm_out.{t}"] = sd[f"decoder.conv_norm_out.{t}"]
+        ren[f"conv_out.{t}"] = sd[f"decoder.conv_out.{t}"]
+        ren[f"mid.attn_1.norm.{t}"] = sd[f"decoder.mid_block.attentions.0.group_norm.{t}"]
+    for a, b in (("q", "to_q"), ("k", "to_k"), ("v", "to_v"), ("proj_out", "to_out.0")):
+        ren[f"mid.attn_1.{a}.weight"] = sd[f"decoder.mid_block.attentions.0.{b}.weight"][:, :, None, None]
+        ren[f"mid.attn_1.{a}.bias"] = sd[f"decoder.mid_block.attentions.0.{b}.bias"]
+    res("decoder.mid_block.resnets.0", "mid.block_1")
+    res("decoder.mid_block.resnets.1", "mid.block_2")
+    for i in range(len(boc)):
+        for j in range(cfg["layers_per_block"] + 1):
+            res(f"decoder.up_blocks.{i}.resnets.{j}", f"up.{i}.block.{j}")
+        if i != len(boc) - 1:
+            for t in ("weight", "bias"):
+                ren[f"up.{i}.upsample.conv.{t}"] = sd[f"decoder.up_blocks.{i}.upsamplers.0.conv.{t}"]
+    missing, unexpected = dec.load_state_dict(ren, strict=True), None
+    return dec
+
+
+def test_vae_oracle_pinned_against_transformers_compvis_decoder():
+    """Pins oracle/vae_ref.py (the restatement of diffusers' AutoencoderKL.decode the CUDA decoder is checked against)
+    to an INDEPENDENT public implementation of the same decoder that is installed offline: transformers'
+    JanusVQVAEDecoder, a port of the CompVis / taming-transformers `Decoder` (the code the SD-1.x VAE was trained with;
+    diffusers' AutoencoderKL is a renaming of it).  Same weights (every tensor of the decoder is consumed: strict load),
+    same latents -> same images to fp32 rounding, at the tiny and at the published SD-1.x width."""
+    from lvd_b200 import synthetic
+    from oracle import vae_ref
+    for cfg, hw in ((synthetic.VAE_TINY, (8, 12)), (synthetic.VAE_SD, (4, 6))):
+        sd = synthetic.random_vae_state_dict(cfg, seed=3)
+        dec = _janus_decoder(cfg, sd)
+        z = torch.randn((2, 4) + hw, generator=torch.Generator().manual_seed(4))
+        with torch.no_grad():
+            want = dec(torch.nn.functional.conv2d(z, sd["post_quant_conv.weight"], sd["post_quant_conv.bias"]))
+            got = vae_ref.decode(sd, cfg, z)
+        assert got.shape == want.shape == (2, 3, 8 * hw[0], 8 * hw[1])
+        err = ((got - want).abs().max() / want.abs().max()).item()
+        assert err < 2e-5, err
+    # the decoder's tensor inventory equals the published SD-1.x VAE decoder's (diffusers names): 138 decoder tensors
+    # + post_quant_conv, 49 490 199 parameters
+    spec = synthetic.vae_param_spec(synthetic.VAE_SD)
+    n = sum(int(torch.tensor(s).prod()) if len(s) else 1 for s in spec.values())
+    assert len(spec) == 140 and n == 49_490_199
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("n,h,w,slice_images", [(3, 8, 16, 0), (2, 16, 16, 1), (5, 8, 8, 2)])
 def test_vae_decode_matches_oracle(cuda, n, h, w, slice_images):
