@@ -19,6 +19,41 @@ def seed_for(prompt_index, repeat, seed_offset=0):
     return prompt_index + repeat * 6789 + seed_offset
 
 
+def plan_work_items(n_prompts, save_dir=None, *, repeats=1, seed_offset=0, skip_first_prompts=0, num_prompts=None,
+                    regenerate=1, seed_overrides=None):
+    """The work list of one `generate.py` run (generate.py:225-356), as rows (ind, prompt index, repeat, seed):
+      * `ind` numbers the output directory `<save_dir>/<ind>` and runs over regenerate x prompts, also counting the
+        prompts skipped by `skip_first_prompts` / `num_prompts` (:254-262) -- so windows of a sharded run keep the
+        directory and seed numbering of a single-process run;
+      * seed = ind + repeat * 6789 + seed_offset, or seed_override + regenerate_ind * 56789 + ... when the prompt carries
+        its own seed (:241-243,320-335);
+      * RESUME: a directory that already holds `repeats` files `video*.joblib` is complete and skipped (:289-299); inside
+        an incomplete directory the repeats whose `video_<repeat>.gif` exists are skipped (generation/lvd.py:150-153)."""
+    import os
+    rows = []
+    ind = 0
+    if regenerate > 1:
+        assert skip_first_prompts == 0  # generate.py:246-248
+    for regen in range(regenerate):
+        for p in range(n_prompts):
+            this = ind
+            ind += 1
+            if p < skip_first_prompts or (num_prompts is not None and p >= skip_first_prompts + num_prompts):
+                continue
+            d = os.path.join(save_dir, str(this)) if save_dir is not None else None
+            if d is not None and os.path.isdir(d):
+                done = [f for f in os.listdir(d) if f.startswith("video") and f.endswith("joblib")]
+                if len(done) >= repeats:
+                    continue
+            override = seed_overrides.get(p) if seed_overrides else None
+            base = override + regen * 56789 if override is not None else this
+            for r in range(repeats):
+                if d is not None and os.path.exists(os.path.join(d, f"video_{r}.gif")):
+                    continue
+                rows.append((this, p, r, base + r * 6789 + seed_offset))
+    return rows
+
+
 def broadcast_work_table(table, device):
     """Rank 0 holds `table` (int64 [n_items, k]: prompt index, repeat, seed, ...); every rank receives a copy."""
     world = dist.get_world_size() if dist.is_initialized() else 1

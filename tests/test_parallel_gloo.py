@@ -140,3 +140,26 @@ def test_generate_sharded_multi_prompt_groups_gloo():
     for r in (0, 1):
         st = ret[f"stats{r}"]
         assert set(st) == {"scatter_s", "generate_s", "gather_s", "items"} and st["items"] == (4 if r == 0 else 3)
+
+
+def test_plan_work_items_seed_schedule_and_resume(tmp_path):
+    """generate.py:225-356: directory / seed numbering survives windows, completed directories are skipped, repeats whose
+    gif exists are skipped, per-prompt seed overrides follow the regenerate schedule."""
+    from lvd_b200 import parallel
+    rows = parallel.plan_work_items(5, None, repeats=2, seed_offset=3)
+    assert rows[:3] == [(0, 0, 0, 3), (0, 0, 1, 6789 + 3), (1, 1, 0, 1 + 3)] and len(rows) == 10
+    # a window keeps the global numbering
+    win = parallel.plan_work_items(5, None, repeats=1, skip_first_prompts=2, num_prompts=2)
+    assert win == [(2, 2, 0, 2), (3, 3, 0, 3)]
+    # resume
+    (tmp_path / "1").mkdir()
+    (tmp_path / "1" / "video_0.joblib").write_bytes(b"x")
+    (tmp_path / "1" / "video_1.joblib").write_bytes(b"x")
+    (tmp_path / "3").mkdir()
+    (tmp_path / "3" / "video_0.joblib").write_bytes(b"x")
+    (tmp_path / "3" / "video_0.gif").write_bytes(b"x")
+    rows = parallel.plan_work_items(5, str(tmp_path), repeats=2)
+    assert [r[:3] for r in rows] == [(0, 0, 0), (0, 0, 1), (2, 2, 0), (2, 2, 1), (3, 3, 1), (4, 4, 0), (4, 4, 1)]
+    # regenerate with a per-prompt seed override (prompt 1 carries seed 100)
+    rows = parallel.plan_work_items(2, None, repeats=1, regenerate=2, seed_overrides={1: 100})
+    assert rows == [(0, 0, 0, 0), (1, 1, 0, 100), (2, 0, 0, 2), (3, 1, 0, 100 + 56789)]

@@ -26,3 +26,11 @@ import json; d=json.load(open('gpurun_out/bench_$W.json')); print('$W', round(d[
   timeout 200 python tools/perf_attn.py > gpurun_out/perf_attn.log 2>&1; tail -12 gpurun_out/perf_attn.log
   timeout 200 python tools/perf_gemm_shapes.py > gpurun_out/perf_gemm_shapes.log 2>&1; tail -20 gpurun_out/perf_gemm_shapes.log
 fi
+if [ -n "$FULL" ]; then
+  # multi-prompt batching on BASELINE config 4 (lvd-plus ModelScope-256): 4 prompts per GPU, 1 vs 4 prompts per pipeline call
+  for P in 1 4; do
+    timeout 400 python bench.py --workload lvd_plus_modelscope256 --steps 5 --warmup 3 --no-cpu-baseline --batch-prompts-per-gpu 4 --prompts-per-call $P > gpurun_out/bench_cfg4_ppc$P.json 2> gpurun_out/bench_cfg4_ppc$P.err
+    python -c "
+import json; d=json.load(open('gpurun_out/bench_cfg4_ppc$P.json')); print('cfg4 prompts-per-call $P', d['prompt_batch'])"
+  done
+fi
