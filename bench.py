@@ -311,7 +311,9 @@ def run_reference(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": _workload("lvd_zeroscope", args.unguided), "sample": sample,
                    "sample_frames": r["sample_frames"]},
-        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": sample,
+                         "sample_frames": r["sample_frames"], "sec_guided": r["sec_guided"],
+                         "sec_unguided": r["sec_unguided"]},
         "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -690,9 +692,9 @@ def run_gpu(args):
         tj = json.load(open(os.path.join(ROOT, "profiles", "r2_gemm_traffic.json")))
         if args.workload == "lvd_zeroscope":
             traffic = tj["traffic_bytes_per_launch"]
-            traffic_src = "profiles/r2_gemm_traffic.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum " \
-                          "over the gemm_tc_kernel launches of one CFG forward + one guidance iteration, step-mix " \
-                          "weighted)"
+            traffic_src = "profiles/r2_gemm_traffic.json (ncu launch list with dram__bytes_read.sum + " \
+                          "dram__bytes_write.sum of every gemm_tc_kernel launch of one CFG forward + one guidance " \
+                          "iteration, step-mix weighted; tools/gpu_ncu.sh)"
     except Exception:
         pass
     all_ms = sum(v["ms"] for v in fam.values()) + (sum(v["ms"] for v in fam_guid.values()) / GUIDED_EVERY
@@ -753,14 +755,24 @@ def run_gpu(args):
                                                                             key=lambda kv: -kv[1]["ms"])},
         }
         if world == 1 and not args.no_cpu_baseline and args.workload == "lvd_zeroscope":
-            # the SAME routine as --impl reference (one code path): one guided + one unguided step, combined with the
-            # schedule weights 1:4 of the timed step mix
-            r = cpu_reference_step(args.cpu_sample_frames, [True, False] if guided_every else [False], 0,
-                                   args.cpu_budget_s / 2)
-            sec = (r["sec_guided"] + (GUIDED_EVERY - 1) * r["sec_unguided"]) / GUIDED_EVERY if guided_every \
-                else r["sec_unguided"]
-            line["cpu_baseline"] = {"value": r["sample_frames"] / sec, "unit": UNIT, "cores": r["cores"], "kind": "port",
-                                    "sample": cpu_sample_text(r) + (", weighted 1:4" if guided_every else "")}
+            # the SAME routine as --impl reference (one code path), run as a child process so that a host-memory problem
+            # of the fp32 autograd step can never take the GPU line down with it: one guided + one unguided step,
+            # combined with the schedule weights 1:4 of the timed step mix
+            cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "2" if guided_every else "1",
+                   "--warmup", "0", "--cpu-budget-s", str(args.cpu_budget_s / 2),
+                   "--cpu-sample-frames", str(args.cpu_sample_frames)] + (["--unguided"] if not guided_every else [])
+            try:
+                env = {k: v for k, v in os.environ.items() if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE")}
+                out = subprocess.run(cmd, capture_output=True, text=True, timeout=args.cpu_budget_s * 2 + 300, env=env)
+                cb = json.loads(out.stdout.strip().splitlines()[-1])["cpu_baseline"]
+                sec = (cb["sec_guided"] + (GUIDED_EVERY - 1) * cb["sec_unguided"]) / GUIDED_EVERY if guided_every \
+                    else cb["sec_unguided"]
+                line["cpu_baseline"] = {"value": cb["sample_frames"] / sec, "unit": UNIT, "cores": cb["cores"],
+                                        "kind": "port",
+                                        "sample": cb["sample"] + (", weighted 1:4" if guided_every else "")}
+            except Exception as e:
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": None, "kind": "port",
+                                        "sample": f"CPU leg failed: {type(e).__name__}: {e}"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -552,67 +552,58 @@ __global__ void __launch_bounds__(kSelfThreads, 2) attention_self_kernel(const _
       nvalid = nvalid > 64 ? 64 : (nvalid < 0 ? 0 : nvalid);
       mbar_wait(s_full, u & 1);
       tc_fence_after();
-      // ---- pass 1: maximum of this thread's 64 scores
+      // ---- the thread's 64 scores: both TMEM loads in flight at once, kept in registers for the exponentials (one
+      // TMEM read per score; the accumulator no longer lives in registers, so there is room)
+      uint32_t ra[32], rb[32];
+      tmem_ld32(my_s, ra);
+      tmem_ld32(my_s + 32, rb);
+      tmem_ld_wait();
       float mx = -INFINITY;
+      if (nvalid == 64) {
 #pragma unroll
-      for (int ch = 0; ch < 2; ++ch) {
-        uint32_t rr[32];
-        tmem_ld32(my_s + ch * 32, rr);
-        tmem_ld_wait();
-        if (nvalid == 64) {
+        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fmaxf(__uint_as_float(ra[i]), __uint_as_float(rb[i])));
+      } else {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(rr[i]));
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, (ch * 32 + i < nvalid) ? __uint_as_float(rr[i]) : -INFINITY);
+        for (int i = 0; i < 32; ++i) {
+          if (i >= nvalid) ra[i] = __float_as_uint(-INFINITY);
+          if (32 + i >= nvalid) rb[i] = __float_as_uint(-INFINITY);
+          mx = fmaxf(mx, fmaxf(__uint_as_float(ra[i]), __uint_as_float(rb[i])));
         }
       }
       const float m_cand = fmaxf(m_used, mx * sc);  // sc > 0
       const bool move = (m_cand - m_used) > kRescaleLog2;  // first unit: m_used = -inf
       if (u > 0 && __any_sync(0xffffffffu, move)) {
         // rare: move the reference point of the rows that need it and rescale their accumulator rows in TMEM
-        // (s_full(u) implies P V of unit u-1 is complete, see the header)
+        // (s_full(u) implies P V of unit u-1 is complete, see the header); 8 columns at a time: few live registers
         const float f = move ? fast_exp2(m_used - m_cand) : 1.f;
-#pragma unroll
-        for (int hl = 0; hl < 2; ++hl) {
-          uint32_t rr[32];
-          tmem_ld32(my_o + hl * 32, rr);
+        for (int c8 = 0; c8 < 8; ++c8) {
+          uint32_t rr[8];
+          tmem_ld8(my_o + c8 * 8, rr);
           tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) rr[i] = __float_as_uint(__uint_as_float(rr[i]) * f);
-          tmem_st32(my_o + hl * 32, rr);
+          for (int i = 0; i < 8; ++i) rr[i] = __float_as_uint(__uint_as_float(rr[i]) * f);
+          tmem_st8(my_o + c8 * 8, rr);
         }
         tmem_st_wait();
         l_run *= f;
       }
       if (move) m_used = m_cand;
-      // ---- pass 2: probabilities relative to m_used -> fp16 -> swizzled smem (A operand of P V)
+      // ---- probabilities relative to m_used -> fp16 -> swizzled smem (A operand of P V); masked scores are -inf -> 0
       float psum = 0.f;
 #pragma unroll
       for (int ch = 0; ch < 2; ++ch) {
-        uint32_t rr[32];
-        tmem_ld32(my_s + ch * 32, rr);
-        tmem_ld_wait();
-        float p[32];
-        if (nvalid == 64) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            p[i] = fast_exp2(fmaf(__uint_as_float(rr[i]), sc, -m_used));
-            psum += p[i];
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            p[i] = (ch * 32 + i < nvalid) ? fast_exp2(fmaf(__uint_as_float(rr[i]), sc, -m_used)) : 0.f;
-            psum += p[i];
-          }
-        }
 #pragma unroll
         for (int s8 = 0; s8 < 4; ++s8) {
           uint4 v;
           __half2* hh = reinterpret_cast<__half2*>(&v);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) hh[i] = __floats2half2_rn(p[s8 * 8 + 2 * i], p[s8 * 8 + 2 * i + 1]);
+          for (int i = 0; i < 4; ++i) {
+            const int c = s8 * 8 + 2 * i;
+            const float p0 = fast_exp2(fmaf(__uint_as_float(ch ? rb[c] : ra[c]), sc, -m_used));
+            const float p1 = fast_exp2(fmaf(__uint_as_float(ch ? rb[c + 1] : ra[c + 1]), sc, -m_used));
+            psum += p0 + p1;
+            hh[i] = __floats2half2_rn(p0, p1);
+          }
           const int chunk16 = (ch * 4 + s8) ^ (r & 7);
           *reinterpret_cast<uint4*>(p_blk + chunk16 * 16) = v;
         }
