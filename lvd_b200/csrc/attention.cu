@@ -658,6 +658,247 @@ __global__ void __launch_bounds__(kSelfThreads, 2) attention_self_kernel(const _
   }
 }
 
+// ------------------------------------------------------------------------------------------------ ... with two S buffers
+// attention_self_kernel leaves the softmax warps idle while the tensor pipe computes P V and the next S (one S buffer: the
+// per-CTA chain S -> softmax -> P V -> S is serial; ncu: 5.5 long-scoreboard stall cycles per issue, MUFU pipe 57 %).
+// Here a unit is 64 keys, so that TWO score buffers fit next to the two accumulators in the CTA's 256 TMEM columns
+// (S0 | S1 | O_a | O_b, 64 columns each): the MMA warp issues S(u+1) before it waits for the probabilities of unit u, the
+// softmax warps go from unit to unit without ever waiting for a P V product, and P is double-buffered in shared memory.
+// Two threads per row as before, now 32 keys each.  Hazards, all covered by issue order + tcgen05.commit semantics:
+//   * S(u+1) overwrites the buffer softmax(u-1) read: it is issued after the MMA warp saw p_full(u-1);
+//   * softmax(u+1) overwrites the P buffer P V(u-1) read: it starts after s_full(u+1), and S(u+1) was issued after
+//     P V(u-1);
+//   * the (rare) accumulator rescale in softmax(u+1) must not overlap P V(u): it first waits for pv_done(u), which the
+//     MMA warp commits after every P V; P V(u+1) cannot start before the rescaling thread arrives at p_full(u+1).
+constexpr int kKvStages = 4;   // 64-key K and V tiles (8 KB each)
+constexpr int kTile64 = 64 * 128;
+
+__global__ void __launch_bounds__(kSelfThreads, 2) attention_self2_kernel(const __grid_constant__ AttnArgs g,
+                                                                           const __grid_constant__ CUtensorMap map_kv64) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t* sQ = smem;                              // 128 x 64 halves
+  uint8_t* sK = smem + kTile;                      // kKvStages x (64 keys x 64 halves)
+  uint8_t* sV = smem + kTile + kKvStages * kTile64;
+  uint8_t* sP = smem + kTile + 2 * kKvStages * kTile64;  // 2 buffers x (128 rows x 64 keys)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 7 * kTile);
+  uint64_t* q_full = bars + 0;
+  uint64_t* kv_full = bars + 1;    // [4]
+  uint64_t* kv_empty = bars + 5;   // [4]
+  uint64_t* s_full = bars + 9;     // [2]
+  uint64_t* p_full = bars + 11;    // [2]
+  uint64_t* pv_done = bars + 13;   // [2]
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 15);
+  const int h = blockIdx.x, qt = blockIdx.y, z = blockIdx.z;
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  if (threadIdx.x == 0) {
+    mbar_init(q_full, 1);
+    for (int i = 0; i < kKvStages; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 256);
+      mbar_init(&pv_done[i], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&g.map_q);
+    tma_prefetch_desc(&map_kv64);
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_holder, 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+  const uint32_t tmem_s = tmem_base, tmem_o = tmem_base + 128;  // S0 +0, S1 +64, O_a +128, O_b +192
+  const int zk = z / g.kv_z_div;
+  const int n_units = (g.kv_total + 63) / 64;
+
+  if (warp == 0) {
+    if (elect_one_sync()) {
+      mbar_arrive_expect_tx(q_full, static_cast<uint32_t>(kTile));
+      tma_load_4d(sQ, &g.map_q, q_full, g.q_col0 + h * 64, qt * 128, 0, z);
+    }
+    __syncwarp();
+    for (int u = 0; u < n_units; ++u) {
+      const int st = u & (kKvStages - 1);
+      mbar_wait(&kv_empty[st], ((u / kKvStages) & 1) ^ 1u);
+      if (elect_one_sync()) {
+        mbar_arrive_expect_tx(&kv_full[st], static_cast<uint32_t>(2 * kTile64));
+        tma_load_4d(sK + st * kTile64, &map_kv64, &kv_full[st], g.k_col0 + h * 64, u * 64, 0, zk);
+        tma_load_4d(sV + st * kTile64, &map_kv64, &kv_full[st], g.v_col0 + h * 64, u * 64, 0, zk);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    mbar_wait(q_full, 0);
+    const uint32_t desc_hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+    const uint32_t q_lo = ((smem_u32(sQ) & 0x3FFFFu) >> 4) | (1u << 16);
+    const uint32_t p_lo0 = ((smem_u32(sP) & 0x3FFFFu) >> 4) | (1u << 16);
+    const uint32_t k_lo0 = ((smem_u32(sK) & 0x3FFFFu) >> 4) | (1u << 16);
+    const uint32_t v_lo0 = ((smem_u32(sV) & 0x3FFFFu) >> 4) | ((8192u >> 4) << 16);  // V is MN-major: [kv][d]
+    const uint32_t idesc_qk = make_idesc_f16(128, 64, 0, 0);
+    const uint32_t idesc_pv = g.idesc_pv;
+    auto issue_s = [&](int u) {  // S(u) = Q K(u)^T into score buffer u & 1
+      const int st = u & (kKvStages - 1);
+      mbar_wait(&kv_full[st], (u / kKvStages) & 1);
+      tc_fence_after();
+      if (elect_one_sync()) {
+        const uint32_t k_lo = k_lo0 + static_cast<uint32_t>(st) * (kTile64 >> 4);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_f16(tmem_s + static_cast<uint32_t>(u & 1) * 64u, (static_cast<uint64_t>(desc_hi) << 32) | (q_lo + 2u * k),
+                   (static_cast<uint64_t>(desc_hi) << 32) | (k_lo + 2u * k), idesc_qk, k != 0 ? 1u : 0u);
+        umma_commit(&s_full[u & 1]);
+      }
+      __syncwarp();
+    };
+    issue_s(0);
+    for (int u = 0; u < n_units; ++u) {
+      if (u + 1 < n_units) issue_s(u + 1);
+      const int st = u & (kKvStages - 1);
+      int nkeys = g.kv_total - u * 64;
+      nkeys = nkeys > 64 ? 64 : nkeys;
+      const int ksteps = (nkeys + 15) / 16;
+      mbar_wait(&p_full[u & 1], (u >> 1) & 1);
+      tc_fence_after();
+      if (elect_one_sync()) {
+        const uint32_t v_lo = v_lo0 + static_cast<uint32_t>(st) * (kTile64 >> 4);
+        const uint32_t p_lo = p_lo0 + static_cast<uint32_t>(u & 1) * (kTile >> 4);
+        for (int ks = 0; ks < ksteps; ++ks) {
+          const uint64_t da = (static_cast<uint64_t>(desc_hi) << 32) | (p_lo + static_cast<uint32_t>(ks) * 2u);
+          const uint64_t db = (static_cast<uint64_t>(desc_hi) << 32) | (v_lo + static_cast<uint32_t>(ks) * (2048u >> 4));
+          // keys 0-31 of the unit accumulate into O_a, keys 32-63 into O_b; the first product of each overwrites
+          umma_f16(tmem_o + static_cast<uint32_t>(ks >> 1) * 64u, da, db, idesc_pv,
+                   (u != 0 || (ks & 1) != 0) ? 1u : 0u);
+        }
+        umma_commit(&kv_empty[st]);
+        umma_commit(&pv_done[u & 1]);
+      }
+      __syncwarp();
+    }
+  } else {
+    const int q = warp & 3;            // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;  // 32-key half of every unit / accumulator owned by this thread
+    const int r = q * 32 + lane;
+    const int c1 = qt * 128 + r;
+    const bool row_valid = c1 < g.q_dim1;
+    const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+    const uint32_t my_o = tmem_o + lane_off + static_cast<uint32_t>(half) * 64u;
+    const float sc = g.scale_log2;
+    float m_used = -INFINITY, l_run = 0.f;
+
+    for (int u = 0; u < n_units; ++u) {
+      int nvalid = g.kv_total - u * 64 - half * 32;  // valid keys among this thread's 32
+      nvalid = nvalid > 32 ? 32 : (nvalid < 0 ? 0 : nvalid);
+      mbar_wait(&s_full[u & 1], (u >> 1) & 1);
+      tc_fence_after();
+      uint32_t rr[32];
+      tmem_ld32(tmem_s + lane_off + static_cast<uint32_t>(u & 1) * 64u + static_cast<uint32_t>(half) * 32u, rr);
+      tmem_ld_wait();
+      float mx = -INFINITY;
+      if (nvalid == 32) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(rr[i]));
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          if (i >= nvalid) rr[i] = __float_as_uint(-INFINITY);
+          mx = fmaxf(mx, __uint_as_float(rr[i]));
+        }
+      }
+      const float m_cand = fmaxf(m_used, mx * sc);  // sc > 0
+      const bool move = (m_cand - m_used) > kRescaleLog2;  // first unit: m_used = -inf
+      if (u > 0 && __any_sync(0xffffffffu, move)) {
+        // rare: P V(u-1) may still be running (or not yet issued) -- wait for its commit before touching the accumulator
+        mbar_wait(&pv_done[(u - 1) & 1], ((u - 1) >> 1) & 1);
+        tc_fence_after();
+        const float f = move ? fast_exp2(m_used - m_cand) : 1.f;
+        for (int c8 = 0; c8 < 8; ++c8) {
+          uint32_t t8[8];
+          tmem_ld8(my_o + c8 * 8, t8);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 8; ++i) t8[i] = __float_as_uint(__uint_as_float(t8[i]) * f);
+          tmem_st8(my_o + c8 * 8, t8);
+        }
+        tmem_st_wait();
+        l_run *= f;
+      }
+      if (move) m_used = m_cand;
+      float psum = 0.f;
+      uint8_t* p_row = sP + (u & 1) * kTile + r * 128;
+#pragma unroll
+      for (int s8 = 0; s8 < 4; ++s8) {
+        uint4 v;
+        __half2* hh = reinterpret_cast<__half2*>(&v);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int c = s8 * 8 + 2 * i;
+          const float p0 = fast_exp2(fmaf(__uint_as_float(rr[c]), sc, -m_used));
+          const float p1 = fast_exp2(fmaf(__uint_as_float(rr[c + 1]), sc, -m_used));
+          psum += p0 + p1;
+          hh[i] = __floats2half2_rn(p0, p1);
+        }
+        const int chunk16 = (half * 4 + s8) ^ (r & 7);
+        *reinterpret_cast<uint4*>(p_row + chunk16 * 16) = v;
+      }
+      l_run += psum;
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(&p_full[u & 1]);
+    }
+    // ---- combine the two key halves: O = (O_a 2^(m_a - m) + O_b 2^(m_b - m)) / (l_a 2^(m_a - m) + l_b 2^(m_b - m))
+    mbar_wait(&pv_done[(n_units - 1) & 1], ((n_units - 1) >> 1) & 1);
+    tc_fence_after();
+    float2* xch = reinterpret_cast<float2*>(sQ);  // Q / K / V / P tiles are dead: every MMA has completed
+    xch[half * 128 + r] = make_float2(m_used, l_run);
+    named_bar_sync(1 + q, 64);
+    const float2 other = xch[(half ^ 1) * 128 + r];
+    const float m_a = half ? other.x : m_used, l_a = half ? other.y : l_run;
+    const float m_b = half ? m_used : other.x, l_b = half ? l_run : other.y;
+    const float m_all = fmaxf(m_a, m_b);
+    const float fa = fast_exp2(m_a - m_all), fb = fast_exp2(m_b - m_all);
+    const float l_all = l_a * fa + l_b * fb;
+    const float inv = 1.f / l_all;
+    uint32_t ra[32], rb[32];
+    tmem_ld32(tmem_o + lane_off + half * 32, ra);       // O_a, output columns [32 half, 32 half + 32)
+    tmem_ld32(tmem_o + lane_off + 64 + half * 32, rb);  // O_b, same columns
+    tmem_ld_wait();
+    if (row_valid) {
+      __half* dst = g.out + (static_cast<long long>(z) * g.o_z_stride + static_cast<long long>(c1) * g.o_d1_stride) * g.ld_o +
+                    g.o_col0 + h * 64 + half * 32;
+      const float wa = fa * inv, wb = fb * inv;
+#pragma unroll
+      for (int s8 = 0; s8 < 4; ++s8) {
+        uint4 v;
+        __half2* hh = reinterpret_cast<__half2*>(&v);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int c = s8 * 8 + 2 * i;
+          hh[i] = __floats2half2_rn(fmaf(__uint_as_float(ra[c]), wa, __uint_as_float(rb[c]) * wb),
+                                    fmaf(__uint_as_float(ra[c + 1]), wa, __uint_as_float(rb[c + 1]) * wb));
+        }
+        *reinterpret_cast<uint4*>(dst + s8 * 8) = v;
+      }
+      if (g.lse && half == 0) g.lse[(static_cast<long long>(z) * g.heads + h) * g.p_rows + c1] = m_all + log2f(l_all);
+    }
+    tc_fence_before();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
 int launch_temporal_attn_mma(const lvd_attn_desc* d, cudaStream_t stream);  // attention_temporal.cu
 int launch_cross_attn_mma(const lvd_attn_desc* d, cudaStream_t stream);     // attention_temporal.cu
 
@@ -814,7 +1055,27 @@ extern "C" int lvd_attention(const lvd_attn_desc* d, void* stream) {
   const int q_tiles = (g.q_dim1 + g.qb1 - 1) / g.qb1;
   dim3 grid(d->heads, q_tiles, d->nz);
   LVD_REQUIRE(q_tiles <= 65535 && d->nz <= 65535, "lvd_attention: grid too large");
-  static const bool old_self = getenv("LVD_ATTN_SELF_OLD") != nullptr;  // A/B switch for tools/ and tests
+  static const bool old_self = getenv("LVD_ATTN_SELF_OLD") != nullptr;  // A/B switches for tools/ and tests
+  static const bool one_buf = getenv("LVD_ATTN_SELF_1BUF") != nullptr;
+  if (d->mode == 0 && g.n_units >= 2 && !d->p_full && !d->p_tok && !old_self && !one_buf && d->s_q >= 128) {
+    // two score buffers, 64-key units (attention_self2_kernel): needs its own K/V tensor map with 64-row boxes
+    CUtensorMap map64;
+    const int64_t nzk = (d->nz + d->kv_z_div - 1) / d->kv_z_div;
+    int64_t kd[4] = {width_kv, d->s_k, 1, nzk};
+    int64_t ks[4] = {1, d->ld_kv, d->ld_kv * d->s_k, d->ld_kv * d->s_k};
+    int kb[4] = {64, 64, 1, 1};
+    rc = encode_tmap_f16_sw128(&map64, d->kv, 4, kd, ks, kb);
+    if (rc) return rc;
+    static bool attr3 = false;
+    if (!attr3) {
+      LVD_CHECK_CUDA(cudaFuncSetAttribute(attention_self2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
+      attr3 = true;
+    }
+    attention_self2_kernel<<<grid, kSelfThreads, kAttnSmem, static_cast<cudaStream_t>(stream)>>>(g, map64);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    LVD_CHECK_CUDA(cudaGetLastError());
+    return LVD_OK;
+  }
   if (d->mode == 0 && g.n_units >= 2 && !d->p_full && !d->p_tok && !old_self) {
     static bool attr2 = false;
     if (!attr2) {
