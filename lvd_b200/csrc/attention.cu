@@ -559,17 +559,15 @@ __global__ void __launch_bounds__(kSelfThreads, 2) attention_self_kernel(const _
       tmem_ld32(my_s + 32, rb);
       tmem_ld_wait();
       float mx = -INFINITY;
-      if (nvalid == 64) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fmaxf(__uint_as_float(ra[i]), __uint_as_float(rb[i])));
-      } else {
+      if (nvalid != 64) {
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
           if (i >= nvalid) ra[i] = __float_as_uint(-INFINITY);
           if (32 + i >= nvalid) rb[i] = __float_as_uint(-INFINITY);
-          mx = fmaxf(mx, fmaxf(__uint_as_float(ra[i]), __uint_as_float(rb[i])));
         }
       }
+#pragma unroll
+      for (int i = 0; i < 32; ++i) mx = fmax3(mx, __uint_as_float(ra[i]), __uint_as_float(rb[i]));
       const float m_cand = fmaxf(m_used, mx * sc);  // sc > 0
       const bool move = (m_cand - m_used) > kRescaleLog2;  // first unit: m_used = -inf
       if (u > 0 && __any_sync(0xffffffffu, move)) {
@@ -803,16 +801,13 @@ __global__ void __launch_bounds__(kSelfThreads, 2) attention_self2_kernel(const 
       tmem_ld32(tmem_s + lane_off + static_cast<uint32_t>(u & 1) * 64u + static_cast<uint32_t>(half) * 32u, rr);
       tmem_ld_wait();
       float mx = -INFINITY;
-      if (nvalid == 32) {
+      if (nvalid != 32) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(rr[i]));
-      } else {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
+        for (int i = 0; i < 32; ++i)
           if (i >= nvalid) rr[i] = __float_as_uint(-INFINITY);
-          mx = fmaxf(mx, __uint_as_float(rr[i]));
-        }
       }
+#pragma unroll
+      for (int i = 0; i < 32; i += 2) mx = fmax3(mx, __uint_as_float(rr[i]), __uint_as_float(rr[i + 1]));
       const float m_cand = fmaxf(m_used, mx * sc);  // sc > 0
       const bool move = (m_cand - m_used) > kRescaleLog2;  // first unit: m_used = -inf
       if (u > 0 && __any_sync(0xffffffffu, move)) {

@@ -3,8 +3,9 @@
 //
 //   dP = dO V^T ;  dS = P o (dP - D),  D = rowsum(dO o O) ;  dQ = scale dS K ;  dK = scale dS^T Q ;  dV = P^T dO
 //
-// Two kernels, both one CTA per (128-row tile, head, image) with the forward kernel's warp roles
-// (warp 0 TMA, warp 1 MMA issue, warps 2..5 one score row per thread):
+// Two kernels, both one CTA per (128-row tile, head, image): warp 0 TMA, warp 1 MMA issue, warps 2..9 compute -- two
+// threads per score row, each owning 64 of the unit's 128 key columns (TMEM lanes are tied to warp_id % 4, columns are
+// free; the log-sum-exp is known, so the halves are independent):
 //   attn_bwd_dq_kernel   : fixed query tile, loops over key units;   dQ accumulates in TMEM across units.
 //   attn_bwd_dkdv_kernel : fixed key tile,   loops over query units; dK, dV accumulate in TMEM across units.  The
 //                          P / dS tiles are written once in shared memory as [query][key] and consumed by the
@@ -20,7 +21,7 @@ namespace lvd {
 extern std::atomic<long long> g_launches;
 
 constexpr int kT = 128 * 128;  // bytes of a 128 x 64 fp16 tile
-constexpr int kBwdThreads = 192;
+constexpr int kBwdThreads = 320;  // 2 control warps + 8 compute warps: two threads per score row, 64 key columns each
 
 struct AttnBwdArgs {
   CUtensorMap map_qkv;  // [rows, width] of the q|k|v buffer, box 64 x 128
@@ -72,7 +73,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_dq_kernel(const __gri
     mbar_init(&kv_empty[0], 1);
     mbar_init(&kv_empty[1], 1);
     mbar_init(sdp_full, 1);
-    mbar_init(ds_full, 128);
+    mbar_init(ds_full, 256);
     mbar_init(dq_done, 1);
     fence_barrier_init();
   }
@@ -147,7 +148,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_dq_kernel(const __gri
       __syncwarp();
     }
   } else {
-    const int q = warp & 3;
+    const int q = warp & 3;            // TMEM lane quarter of this warp
+    const int half = (warp - 2) >> 2;  // which 64 of the unit's 128 key columns (and which 32 dQ columns) this thread owns
     const int r = q * 32 + lane;
     const int qi = qt * 128 + r;
     const bool row_valid = qi < g.S;
@@ -163,7 +165,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_dq_kernel(const __gri
       mbar_wait(sdp_full, u & 1);
       tc_fence_after();
       if (u > 0) mbar_wait(dq_done, (u - 1) & 1);  // the previous dQ MMA has finished reading sDS
-      for (int ch = 0; ch < (ncols + 31) / 32; ++ch) {
+      for (int ch = half * 2; ch < half * 2 + 2 && ch * 32 < ncols; ++ch) {
         uint32_t rs[32], rp[32];
         tmem_ld32(tm_s + lane_off + ch * 32, rs);
         tmem_ld32(tm_dp + lane_off + ch * 32, rp);
@@ -188,8 +190,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_dq_kernel(const __gri
     mbar_wait(dq_done, (g.n_units - 1) & 1);
     tc_fence_after();
     __half* dst = g.d_qkv + (static_cast<long long>(row0) + qi) * g.ld_dqkv + g.q_col0 + h * 64;
-#pragma unroll
-    for (int hlf = 0; hlf < 2; ++hlf) {
+    {
+      const int hlf = half;
       uint32_t rr[32];
       tmem_ld32(tm_dq + lane_off + hlf * 32, rr);
       tmem_ld_wait();
@@ -243,7 +245,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_dkdv_kernel(const __g
     mbar_init(&q_empty[0], 1);
     mbar_init(&q_empty[1], 1);
     mbar_init(sdp_full, 1);
-    mbar_init(pds_full, 128);
+    mbar_init(pds_full, 256);
     mbar_init(acc_done, 1);
     fence_barrier_init();
   }
@@ -326,6 +328,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_dkdv_kernel(const __g
     }
   } else {
     const int q = warp & 3;
+    const int half = (warp - 2) >> 2;  // key columns [64 half, 64 half + 64) of every unit; dV / dK columns [32 half, +32)
     const int r = q * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
     uint8_t* p_row = sP + r * 128;
@@ -338,7 +341,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_dkdv_kernel(const __g
       mbar_wait(sdp_full, u & 1);
       tc_fence_after();
       if (u > 0) mbar_wait(acc_done, (u - 1) & 1);  // previous dV/dK MMAs have finished reading sP / sDS
-      for (int ch = 0; ch < 4; ++ch) {
+      for (int ch = half * 2; ch < half * 2 + 2; ++ch) {
         float pv[32], dv_[32];
         if (ch * 32 < kcols16) {
           uint32_t rs[32], rp[32];
@@ -378,7 +381,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_dkdv_kernel(const __g
     const bool key_valid = r < kvalid;
     __half* dst = g.d_qkv + (static_cast<long long>(row0) + ki) * g.ld_dqkv + h * 64;
 #pragma unroll
-    for (int part = 0; part < 4; ++part) {  // 0,1: dV halves; 2,3: dK halves
+    for (int part = half; part < 4; part += 2) {  // 0,1: dV halves; 2,3: dK halves -- this thread's column half of both
       uint32_t rr[32];
       tmem_ld32((part < 2 ? tm_dv : tm_dk) + lane_off + (part & 1) * 32, rr);
       tmem_ld_wait();
@@ -431,7 +434,9 @@ struct AttnBwdSmallArgs {
   uint32_t idesc_s, idesc_dq, idesc_dkv;
 };
 
-__global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_small_kernel(const __grid_constant__ AttnBwdSmallArgs g) {
+constexpr int kBwdSmallThreads = 192;  // 2 control warps + 4 compute warps (one score row per thread)
+
+__global__ void __launch_bounds__(kBwdSmallThreads, 1) attn_bwd_small_kernel(const __grid_constant__ AttnBwdSmallArgs g) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint8_t* sQ = smem;
@@ -450,13 +455,13 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_small_kernel(const __
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   {
     uint4 zero = make_uint4(0, 0, 0, 0);  // P / dS must be zero outside the columns the threads write
-    for (int i = threadIdx.x; i < 4 * kT / 16; i += kBwdThreads) reinterpret_cast<uint4*>(sP)[i] = zero;
+    for (int i = threadIdx.x; i < 4 * kT / 16; i += kBwdSmallThreads) reinterpret_cast<uint4*>(sP)[i] = zero;
     fence_proxy_async_smem();
   }
   if (threadIdx.x == 0) {
     mbar_init(in_full, 1);
     mbar_init(sdp_full, 1);
-    mbar_init(pds_full, 128);
+    mbar_init(pds_full, 256);
     mbar_init(acc_done, 1);
     fence_barrier_init();
   }
@@ -769,7 +774,7 @@ int launch_attn_bwd_small(int mode, const void* q, long long ld_q, long long q_w
     LVD_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_b));
     attr = true;
   }
-  attn_bwd_small_kernel<<<grid, kBwdThreads, smem_b, st>>>(g);
+  attn_bwd_small_kernel<<<grid, kBwdSmallThreads, smem_b, st>>>(g);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   LVD_CHECK_CUDA(cudaGetLastError());
   return LVD_OK;

