@@ -461,7 +461,7 @@ __global__ void __launch_bounds__(kBwdSmallThreads, 1) attn_bwd_small_kernel(con
   if (threadIdx.x == 0) {
     mbar_init(in_full, 1);
     mbar_init(sdp_full, 1);
-    mbar_init(pds_full, 256);
+    mbar_init(pds_full, 128);
     mbar_init(acc_done, 1);
     fence_barrier_init();
   }
