@@ -546,6 +546,11 @@ def run_gpu(args):
             for k in range(lo_, hi_, ppc):
                 grp = layouts[k:min(k + ppc, hi_)]
                 generate([0] * len(grp), [l["bboxes"] for l in grp], [l["object_positions"] for l in grp], steps=6)
+        if world > 1:
+            # one-time NCCL connection setup of the collectives the timed region uses (broadcast + point-to-point gather)
+            # is excluded like graph capture: a tiny gather / broadcast first
+            parallel.gather_results(torch.zeros((1, 16), dtype=torch.uint8, device=dev), world)
+            parallel.broadcast_work_table(torch.zeros((1, 3), dtype=torch.int64), dev)
         barrier()
         stats = {}
         t0 = time.perf_counter()
