@@ -350,6 +350,11 @@ def run_gpu(args):
     from lvd_b200.models.unet_3d_condition import UNet3DConditionModel
     from lvd_b200.scheduler import DPMSolverMultistepScheduler
 
+    # stdout carries exactly ONE line (the JSON): anything else written to fd 1 by libraries (NCCL's version banner
+    # ignores NCCL_DEBUG_FILE on some builds) is sent to stderr
+    sys.stdout.flush()
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     wl = WORKLOADS[args.workload]
     frames, lat_h, lat_w = wl["frames"], wl["h"], wl["w"]
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -778,7 +783,7 @@ def run_gpu(args):
             except Exception as e:
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": None, "kind": "port",
                                         "sample": f"CPU leg failed: {type(e).__name__}: {e}"}
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=json_out, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
