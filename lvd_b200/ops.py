@@ -64,13 +64,32 @@ def _check_act(t, name="tensor"):
         raise ValueError(f"{name}: row stride must be a multiple of 8 and base 16-byte aligned")
 
 
-def pick_block_n(n, act=ACT_NONE, mn_major=False):
+def pick_block_n(n, act=ACT_NONE, mn_major=False, m_tiles=None, k_contract=None):
+    """Tile width of an lvd_gemm launch.  Wide tiles move fewer operand bytes per FLOP, but the kernel is
+    persistent -- one CTA (or CTA pair) per SM walks the tile list -- so what counts is the number of tile ROUNDS the
+    slowest SM runs: at M = 4320 / 2160 / 1080 rows (the 10x18 and 5x9 levels, and every level of the B = 1 guidance
+    pass) 256-wide tiles leave the last round half empty and 160-wide tiles are 13-16 % faster
+    (tools/perf_gemm_blockn.py).  Cost model: rounds x (block_n + 180), the per-tile time fitted to the measured
+    160- vs 256-wide rates."""
     if act == ACT_GEGLU:
         return 2 * GEGLU_HALF
-    for bn in ((256, 128, 64) if mn_major else (256, 160, 128, 64)):
-        if n % bn == 0:
-            return bn
-    raise ValueError(f"N={n} is not a multiple of 64")
+    cands = [bn for bn in ((256, 128, 64) if mn_major else (256, 160, 128, 64)) if n % bn == 0]
+    if not cands:
+        raise ValueError(f"N={n} is not a multiple of 64")
+    if m_tiles is None or len(cands) == 1:
+        return cands[0]
+    pair = m_tiles >= 2 and (k_contract or 0) >= 640  # mirrors the CTA-pair choice of lvd_gemm (gemm.cu)
+    units = _NUM_SMS // 2 if pair else _NUM_SMS
+    rows = (m_tiles + 1) // 2 if pair else m_tiles
+    best = None
+    for bn in cands:
+        if bn == 64 and len(cands) > 1 and n > 64:
+            continue  # 64-wide tiles never win on these shapes (operand traffic)
+        rounds = -(-(rows * (n // bn)) // units)
+        cost = rounds * (bn + 180)
+        if best is None or cost < best[0]:
+            best = (cost, bn)
+    return best[1]
 
 
 @functools.lru_cache(maxsize=None)
@@ -121,7 +140,10 @@ def gemm_raw(*, a, a_dims, a_strides, a_box, taps, k_per_tap, w, n, out, out_dim
     d.b = w.data_ptr()
     d.b_mn_major = 1 if b_mn_major else 0
     if block_n is None:
-        block_n = FORCE_BLOCK_N or pick_block_n(n, act, b_mn_major)
+        m_tiles = 1
+        for i in range(4):
+            m_tiles *= -(-int(out_dims[i]) // max(1, int(a_box[i + 1])))
+        block_n = FORCE_BLOCK_N or pick_block_n(n, act, b_mn_major, m_tiles, len(taps) * int(k_per_tap))
     d.block_n = int(block_n)
     d.ldb = int(ldb if ldb is not None else w.stride(0))
     d.n = int(n)
