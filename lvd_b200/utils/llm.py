@@ -30,6 +30,7 @@ def get_parsed_layout_text_resp(prompt, llm_kwargs=None, max_partial_response_re
             rebuilt += parts[0] + head
         text = parts[1]
     layout = {}
+    prev_cut = 0
     for i, line in enumerate(REQUIRED_LINES):
         nxt = REQUIRED_LINES[i + 1] if i + 1 < len(REQUIRED_LINES) else ""
         if nxt not in text:
@@ -47,13 +48,12 @@ def get_parsed_layout_text_resp(prompt, llm_kwargs=None, max_partial_response_re
                 print(f"Encountered SyntaxError with content {content}: {e}")
                 raise
         layout[line.rstrip(":")] = content
-        if nxt:
-            rebuilt += text[:cut + len(nxt)]
-            text = text[cut + len(nxt):]
-        else:  # the reference re-uses the previous cut position for the last line (utils/llm.py:248-251)
-            rebuilt += text[:_last_cut + len(nxt)]
-            text = text[_last_cut + len(nxt):]
-        _last_cut = cut
+        # reconstructed response: for the last line the reference slices with the STALE position of the previous line
+        # (`required_line_idx` is not updated when there is no next marker, utils/llm.py:228-251); reproduced as is
+        keep = cut if nxt else prev_cut
+        rebuilt += text[:keep + len(nxt)]
+        text = text[keep + len(nxt):]
+        prev_cut = cut
     layout["Prompt"] = prompt
     return layout, rebuilt
 

@@ -179,7 +179,13 @@ def test_guidance_loss_variants_end_to_end(cuda, variant):
     keys = [("down", 1, 0, 0), ("down", 2, 1, 0), ("up", 1, 1, 0), ("up", 2, 2, 0)]
     kw = dict(fg_weight=1.0, bg_weight=2.0, base_attn_dim=(h, w), **VARIANT_KW[variant])
     gg = GuidanceGraph(eng)
-    loss, grad = gg.run(x, 400, ehs, bboxes, positions, keys, loss_scale=4.0, **kw)
+    # the engine additionally gets the pass-through keywords every reference runner sends along
+    # (generation/lvd.py:119-142: exclude_bg_heads, upsample_scale / upsample_mode, verbose)
+    runner_extras = dict(exclude_bg_heads=False, verbose=True)
+    if "upsample_scale" not in kw:
+        runner_extras.update(upsample_scale=1, upsample_mode="bilinear")
+    ekw = dict(kw, **runner_extras)
+    loss, grad = gg.run(x, 400, ehs, bboxes, positions, keys, loss_scale=4.0, **ekw)
     sd32 = {k: v.half().float().to(cuda) for k, v in sd.items()}
     _, ref_loss, ref_grad, _ = G.guidance_step(sd32, cfg, x.float(), 400, ehs.float(), bboxes, positions,
                                                torch.tensor(0.5), guidance_attn_keys=keys, loss_scale=4.0, **kw)
@@ -188,8 +194,8 @@ def test_guidance_loss_variants_end_to_end(cuda, variant):
     assert abs(loss.item() - ref_loss.item()) <= 1e-3 * abs(ref_loss.item())
     assert cos >= 0.995 and rel <= 0.10
     # graph replay of the same structure gives the same numbers
-    l2, g2 = gg.run(x, 400, ehs, bboxes, positions, keys, loss_scale=4.0, **kw)
-    l3, g3 = gg.run(x, 400, ehs, bboxes, positions, keys, loss_scale=4.0, **kw)
+    l2, g2 = gg.run(x, 400, ehs, bboxes, positions, keys, loss_scale=4.0, **ekw)
+    l3, g3 = gg.run(x, 400, ehs, bboxes, positions, keys, loss_scale=4.0, **ekw)
     assert abs(l3.item() - loss.item()) <= 1e-5 * abs(loss.item()) and torch.equal(g3, grad) and torch.equal(g2, grad)
 
 
