@@ -79,6 +79,16 @@ typedef struct lvd_gemm_desc {
   /* 0: automatic; 1: one CTA per 128-row tile; 2: CTA pairs (2-CTA clusters, tcgen05 cta_group::2, 256-row tiles --
    * each SM stages half of every B tile; needs >= 2 row tiles, MN-major B: block_n % 128 == 0) */
   int32_t cta_pair;
+  /* GroupNorm statistics of the output, produced by the epilogue for the GroupNorm that consumes it (diffusers
+   * ResnetBlock2D.norm2 after conv1, TemporalConvLayer's norms after the resnet / the temporal convs:
+   * unet_3d_blocks.py:330-349) -- the normalisation then needs no statistics pass over the tensor.  NULL = off.
+   * gn_partial: fp32 [samples][gn_tiles_per_sample][4][gn_subslots][gn_groups][2], ZERO on entry; every epilogue warp
+   * adds {sum, sum of squares} of its 32 rows per channel group (one writer per float: bit-reproducible).  A row tile
+   * must lie inside one sample (row tiles of a sample are consecutive in tile order); gn_group_width = n / gn_groups;
+   * gn_subslots >= (gn_group_width + 30) / 32 + 1.  lvd_gn_finalize turns the partials into {mean, rstd} and clears
+   * them; lvd_groupnorm_apply normalises with given statistics. */
+  void* gn_partial;
+  int32_t gn_group_width, gn_groups, gn_tiles_per_sample, gn_subslots;
 } lvd_gemm_desc;
 
 int lvd_gemm(const lvd_gemm_desc* d, void* stream);
@@ -145,6 +155,14 @@ int lvd_groupnorm(const void* x, int64_t ld_x, void* y, int64_t ld_y, int32_t sa
                   int32_t channels, int32_t groups, const void* gamma, const void* beta, float eps, int32_t silu,
                   void* stats_out /* optional fp32 [samples, groups, 2] = {mean, rstd}, kept for lvd_groupnorm_bwd */,
                   void* workspace, int64_t workspace_bytes, void* stream);
+/* Statistics from the producing lvd_gemm's epilogue (gn_partial): fold `slots` = tiles_per_sample * 4 * subslots partial
+ * pairs per (sample, group) in a fixed order into stats[sample][group] = {mean, rstd} (count = elements per group) and
+ * reset the partials to zero; then normalise with them (the second pass of lvd_groupnorm only). */
+int lvd_gn_finalize(void* partial, int32_t samples, int32_t slots, int32_t groups, float count, float eps,
+                    void* stats_f32, void* stream);
+int lvd_groupnorm_apply(const void* x, int64_t ld_x, void* y, int64_t ld_y, int32_t samples, int64_t rows_per_sample,
+                        int32_t channels, int32_t groups, const void* gamma, const void* beta, int32_t silu,
+                        const void* stats_f32, void* stream);
 int lvd_layernorm(const void* x, int64_t ld_x, void* y, int64_t ld_y, int64_t rows, int32_t channels,
                   const void* gamma, const void* beta, float eps, void* stream);
 

@@ -38,6 +38,11 @@ class GemmDesc(ctypes.Structure):
         ("b_k_tap_stride", ctypes.c_int32),
         ("b_n_tap_stride", ctypes.c_int32),
         ("cta_pair", ctypes.c_int32),
+        ("gn_partial", ctypes.c_void_p),
+        ("gn_group_width", ctypes.c_int32),
+        ("gn_groups", ctypes.c_int32),
+        ("gn_tiles_per_sample", ctypes.c_int32),
+        ("gn_subslots", ctypes.c_int32),
     ]
 
 
@@ -136,6 +141,8 @@ def _declare(l):
     l.lvd_gemm.argtypes = [ctypes.POINTER(GemmDesc), vp]
     l.lvd_attention.argtypes = [ctypes.POINTER(AttnDesc), vp]
     l.lvd_groupnorm.argtypes = [vp, i64, vp, i64, i32, i64, i32, i32, vp, vp, f32, i32, vp, vp, i64, vp]
+    l.lvd_gn_finalize.argtypes = [vp, i32, i32, i32, f32, f32, vp, vp]
+    l.lvd_groupnorm_apply.argtypes = [vp, i64, vp, i64, i32, i64, i32, i32, vp, vp, i32, vp, vp]
     l.lvd_layernorm.argtypes = [vp, i64, vp, i64, i64, i32, vp, vp, f32, vp]
     l.lvd_conv_in.argtypes = [vp, vp, vp, vp, i64, i32, i32, i32, i32, i32, i32, vp]
     l.lvd_conv_out.argtypes = [vp, i64, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]
@@ -190,6 +197,8 @@ EXPORTS = [
     "lvd_gemm",
     "lvd_attention",
     "lvd_groupnorm",
+    "lvd_gn_finalize",
+    "lvd_groupnorm_apply",
     "lvd_layernorm",
     "lvd_conv_in",
     "lvd_conv_out",

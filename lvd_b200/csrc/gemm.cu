@@ -55,6 +55,11 @@ struct GemmArgs {
               // stores, bit 3 = skip the residual loads (results are garbage)
   float gamma;
   uint32_t idesc;
+  // GroupNorm statistics of the OUTPUT for the GroupNorm that consumes it (NULL = off): every epilogue warp adds the
+  // column sums {sum, sum of squares} of its 32 staged rows, folded per channel group, into
+  // gn_part[sample][row tile of the sample][row quarter][slab residue][group][2]
+  float* gn_part;
+  int gn_gw, gn_groups, gn_tiles_per_sample, gn_sub;
 };
 
 // Timeline tracing for tools/trace_gemm.py (LVD_GEMM_DEBUG bit 6): CTA 0 appends (event << 48 | globaltimer ns).
@@ -325,8 +330,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     const bool has_silu = kEpi == kEpiGeneric && g.act == 1;
     const bool has_gelu = kEpi == kEpiGeneric && g.act == 3;
     const __half* const bias = g.bias;
+    const bool has_gn = g.gn_part != nullptr;
     int j[4];
-    if (has_rowvec) {
+    if (has_rowvec || has_gn) {
       int t = r;
       j[0] = t % g.box[0];
       t /= g.box[0];
@@ -383,7 +389,13 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     for (; it.tile < num_tiles; tile_advance(g, it), first = (first - nslabs) & 3) {
       bool valid = false;
       long long rvrow = 0;
-      if (has_rowvec) {
+      long long gn_slot0 = 0;  // first float of this warp's partial-sum block of the current tile
+      if (has_gn) {
+        const int rt = it.t0 + g.ntile[0] * (it.t1 + g.ntile[1] * (it.t2 + g.ntile[2] * it.t3));
+        const int smp = rt / g.gn_tiles_per_sample, til = rt - smp * g.gn_tiles_per_sample;
+        gn_slot0 = ((static_cast<long long>(smp) * g.gn_tiles_per_sample + til) * 4 + q) * g.gn_sub * g.gn_groups * 2;
+      }
+      if (has_rowvec || has_gn) {
         const int x0 = it.t0 * g.box[0] + j[0], x1 = it.t1 * g.box[1] + j[1];
         const int x2 = it.t2 * g.box[2] + j[2], x3 = it.t3 * g.box[3] + j[3];
         valid = j[3] < g.box[3] && x0 < g.out_dims[0] && x1 < g.out_dims[1] && x2 < g.out_dims[2] &&
@@ -491,6 +503,43 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
 #pragma unroll
         for (int cidx = 0; cidx < 4; ++cidx)
           *reinterpret_cast<uint4*>(obuf + row_off + ((static_cast<uint32_t>(cidx) ^ sw) << 4)) = packed[cidx];
+        if (has_gn) {
+          // GroupNorm statistics of the values just staged (the fp16 the consumer will read): lane c sums column c of the
+          // slab over this warp's 32 rows, a segmented shuffle reduction folds the columns of one channel group, and the
+          // head lane of each group adds the pair into the warp's own partial slot.  A group spans at most gn_sub
+          // consecutive slabs and slabs go to slots by (slab index mod gn_sub), so every float has exactly one writer
+          // per launch: the result does not depend on scheduling (bit-reproducible), the adds only serve zero-init.
+          __syncwarp();
+          const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+          const uint32_t chunk = static_cast<uint32_t>(lane) >> 3, within = (static_cast<uint32_t>(lane) & 7u) * 2u;
+          float s1 = 0.f, s2 = 0.f;
+#pragma unroll 8
+          for (int rr = 0; rr < 32; ++rr) {
+            if ((vmask >> rr) & 1u) {
+              const uint32_t row = static_cast<uint32_t>(q * 32 + rr);
+              const float f = __half2float(*reinterpret_cast<const __half*>(
+                  obuf + row * 64u + ((chunk ^ ((row >> 1) & 3u)) << 4) + within));
+              s1 += f;
+              s2 = fmaf(f, f, s2);
+            }
+          }
+          const int gid = (gcol + lane) / g.gn_gw;
+#pragma unroll
+          for (int off = 1; off < 32; off <<= 1) {
+            const float t1 = __shfl_down_sync(0xffffffffu, s1, off), t2 = __shfl_down_sync(0xffffffffu, s2, off);
+            const int g2 = __shfl_down_sync(0xffffffffu, gid, off);
+            if (lane + off < 32 && g2 == gid) {
+              s1 += t1;
+              s2 += t2;
+            }
+          }
+          const int gprev = __shfl_up_sync(0xffffffffu, gid, 1);
+          if (lane == 0 || gprev != gid) {
+            float* dst = g.gn_part + gn_slot0 + (static_cast<long long>((gcol >> 5) % g.gn_sub) * g.gn_groups + gid) * 2;
+            atomicAdd(dst, s1);
+            atomicAdd(dst + 1, s2);
+          }
+        }
         fence_proxy_async_smem();
         LVD_PH(3);
         // the group's other buffer must have been drained (store seq-1) before anyone writes it in the next slab
@@ -690,6 +739,19 @@ static int launch_gemm(const lvd_gemm_desc* d, cudaStream_t stream) {
   g.residual = static_cast<const __half*>(d->residual);
   g.ld_rowvec = d->ld_rowvec;
   g.gamma = d->gamma;
+  g.gn_part = static_cast<float*>(d->gn_partial);
+  g.gn_gw = d->gn_group_width;
+  g.gn_groups = d->gn_groups;
+  g.gn_tiles_per_sample = d->gn_tiles_per_sample;
+  g.gn_sub = d->gn_subslots;
+  if (g.gn_part) {
+    LVD_REQUIRE(d->act != 2 && g.gn_gw >= 1 && g.gn_groups >= 1 && d->n == g.gn_gw * g.gn_groups,
+                "lvd_gemm: gn statistics need n == groups * group_width and no GEGLU");
+    LVD_REQUIRE(g.gn_tiles_per_sample >= 1 && m_tiles % g.gn_tiles_per_sample == 0,
+                "lvd_gemm: gn_tiles_per_sample=%d does not divide the %lld row tiles", g.gn_tiles_per_sample, m_tiles);
+    LVD_REQUIRE(g.gn_sub >= (g.gn_gw + 30) / 32 + 1, "lvd_gemm: gn_subslots=%d too small for groups of %d channels",
+                g.gn_sub, g.gn_gw);
+  }
   g.idesc = make_idesc_f16(128u * ctas, static_cast<uint32_t>(d->block_n), 0, d->b_mn_major ? 1u : 0u);
 
   const int smem_bytes = 1024 + stages * stage_bytes + n_slabs_smem * kSlabBytes + kBarrierBytes;

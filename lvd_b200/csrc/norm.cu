@@ -368,7 +368,14 @@ __global__ void __launch_bounds__(320, 2) gn_stream_apply_kernel(const __half* _
     for (int it = 0; it < kGnStages && it < st.nit; ++it) st.issue(it);
   // Every CTA folds the sample's chunk partials itself (fixed order: deterministic, identical in all CTAs) while its
   // first stages are in flight -- a finalising "last CTA" in the statistics pass left the GPU idle for its whole tail.
-  {
+  if (partial == nullptr) {
+    // statistics given (produced by the epilogue of the GEMM that wrote x: lvd_gn_finalize)
+    if (threadIdx.x < G) {
+      s_mean[threadIdx.x] = __ldcg(stats + (static_cast<long long>(s) * G + threadIdx.x) * 2);
+      s_rstd[threadIdx.x] = __ldcg(stats + (static_cast<long long>(s) * G + threadIdx.x) * 2 + 1);
+    }
+    __syncthreads();
+  } else {
     const int nparts = blockDim.x / G;
     const int g = threadIdx.x % G, part = threadIdx.x / G;
     float a = 0.f, b = 0.f;
@@ -637,6 +644,89 @@ extern "C" int lvd_groupnorm(const void* x, int64_t ld_x, void* y, int64_t ld_y,
     }
   }
   g_launches.fetch_add(2, std::memory_order_relaxed);
+  LVD_CHECK_CUDA(cudaGetLastError());
+  return LVD_OK;
+}
+
+namespace lvd {
+// Folds the per-warp partial sums written by gemm_tc_kernel's epilogue (gn_part) into {mean, rstd} per (sample, group),
+// in a fixed order (deterministic), and clears them for the next producer.  One CTA per sample; thread = (group, part).
+__global__ void gn_tiles_finalize_kernel(float* __restrict__ part, int slots, int G, float n, float eps,
+                                         float* __restrict__ stats) {
+  __shared__ float s_a[1024], s_b[1024];
+  const int s = blockIdx.x;
+  const int g = threadIdx.x % G, p = threadIdx.x / G, nparts = blockDim.x / G;
+  float a = 0.f, b = 0.f;
+  if (p < nparts)
+    for (int k = p; k < slots; k += nparts) {
+      float* q = part + ((static_cast<long long>(s) * slots + k) * G + g) * 2;
+      a += q[0];
+      b += q[1];
+      q[0] = 0.f;
+      q[1] = 0.f;
+    }
+  s_a[threadIdx.x] = a;
+  s_b[threadIdx.x] = b;
+  __syncthreads();
+  if (threadIdx.x < G) {
+    a = 0.f;
+    b = 0.f;
+    for (int i = 0; i < nparts; ++i) {
+      a += s_a[i * G + threadIdx.x];
+      b += s_b[i * G + threadIdx.x];
+    }
+    const float mean = a / n;
+    float var = b / n - mean * mean;
+    var = var > 0.f ? var : 0.f;
+    stats[(static_cast<long long>(s) * G + threadIdx.x) * 2] = mean;
+    stats[(static_cast<long long>(s) * G + threadIdx.x) * 2 + 1] = rsqrtf(var + eps);
+  }
+}
+}  // namespace lvd
+
+extern "C" int lvd_gn_finalize(void* partial, int32_t samples, int32_t slots, int32_t groups, float count, float eps,
+                               void* stats_f32, void* stream) {
+  LVD_REQUIRE(partial && stats_f32 && samples >= 1 && slots >= 1 && groups >= 1 && groups <= 64 && count > 0.f,
+              "lvd_gn_finalize: bad arguments");
+  const int threads = 1024 / groups * groups;
+  gn_tiles_finalize_kernel<<<samples, threads, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<float*>(partial), slots, groups, count, eps, static_cast<float*>(stats_f32));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  LVD_CHECK_CUDA(cudaGetLastError());
+  return LVD_OK;
+}
+
+extern "C" int lvd_groupnorm_apply(const void* x, int64_t ld_x, void* y, int64_t ld_y, int32_t samples,
+                                   int64_t rows_per_sample, int32_t channels, int32_t groups, const void* gamma,
+                                   const void* beta, int32_t silu, const void* stats_f32, void* stream) {
+  LVD_REQUIRE(x && y && gamma && beta && stats_f32, "lvd_groupnorm_apply: null pointer");
+  LVD_REQUIRE(channels % 8 == 0 && channels % groups == 0 && groups <= 64, "lvd_groupnorm_apply: C=%d G=%d unsupported",
+              channels, groups);
+  LVD_REQUIRE(ld_x % 8 == 0 && ld_y % 8 == 0 && samples >= 1 && rows_per_sample >= 1, "lvd_groupnorm_apply: bad shape");
+  const int threads = gn_threads(channels);
+  const long long row_bytes = 2LL * channels;
+  const int rpp_ = threads / (channels / 8);
+  int T = static_cast<int>((15 * 1024) / row_bytes) / rpp_ * rpp_;
+  if (T < rpp_) T = rpp_;
+  long long schunks = (2LL * num_sms()) / samples;
+  const long long most = (rows_per_sample + T - 1) / T;
+  if (schunks > most) schunks = most;
+  if (schunks < 1) schunks = 1;
+  const size_t ring_bytes = static_cast<size_t>(kGnStages) * T * row_bytes;
+  LVD_REQUIRE(threads <= 320 && ring_bytes <= 220 * 1024, "lvd_groupnorm_apply: C=%d too wide for the streaming pass",
+              channels);
+  static bool attr = false;
+  if (!attr) {
+    LVD_CHECK_CUDA(cudaFuncSetAttribute(gn_stream_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    attr = true;
+  }
+  dim3 sgrid(static_cast<unsigned>(schunks), static_cast<unsigned>(samples));
+  gn_stream_apply_kernel<<<sgrid, threads, ring_bytes, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __half*>(x), ld_x, static_cast<__half*>(y), ld_y, rows_per_sample, channels, groups,
+      static_cast<int>(schunks), T, nullptr, static_cast<float>(rows_per_sample) * (channels / groups), 0.f,
+      const_cast<float*>(static_cast<const float*>(stats_f32)), static_cast<const __half*>(gamma),
+      static_cast<const __half*>(beta), silu);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
   LVD_CHECK_CUDA(cudaGetLastError());
   return LVD_OK;
 }

@@ -164,22 +164,26 @@ class UNetEngine:
         w["temb_all"] = LayerWeights(w=tw.contiguous(), b=tb.contiguous())
 
     # ------------------------------------------------------------------------------------------------ blocks
-    def _resnet(self, L, x, n_img, h, w_, temb_all, out=None):
+    def _resnet(self, L, x, n_img, h, w_, temb_all, out=None, gn_next=None):
+        """`gn_next` = samples of the GroupNorm that reads this block's output NEXT (the 5-D norm of the temporal conv
+        layer): conv2's epilogue then produces its statistics; conv1's epilogue produces norm2's."""
         eps = self.cfg["norm_eps"]
         t = ops.groupnorm(x, n_img, L.norm1.w, L.norm1.b, eps, silu=True)
         lo, hi = L.temb
-        t = ops.conv2d_3x3(t, n_img, h, w_, L.conv1.w, L.conv1.b, rowvec=temb_all[:, lo:hi])
+        t = ops.conv2d_3x3(t, n_img, h, w_, L.conv1.w, L.conv1.b, rowvec=temb_all[:, lo:hi], gn=(n_img, 32))
         t = ops.groupnorm(t, n_img, L.norm2.w, L.norm2.b, eps, silu=True)
         sc = x
         if "shortcut" in L:
             sc = ops.linear(x, L.shortcut.w, L.shortcut.b)
-        return ops.conv2d_3x3(t, n_img, h, w_, L.conv2.w, L.conv2.b, residual=sc, out=out)
+        return ops.conv2d_3x3(t, n_img, h, w_, L.conv2.w, L.conv2.b, residual=sc, out=out,
+                              gn=(gn_next, 32) if gn_next else None)
 
     def _tconv(self, layers, x, batch, frames, hw):
         t = x
         for i, L in enumerate(layers):
             t = ops.groupnorm(t, batch, L.norm.w, L.norm.b, 1e-5, silu=True)
-            t = ops.conv_temporal(t, batch, frames, hw, L.w, L.b, residual=x if i == 3 else None)
+            t = ops.conv_temporal(t, batch, frames, hw, L.w, L.b, residual=x if i == 3 else None,
+                                  gn=(batch, 32) if i < 3 else None)  # the next norm of the chain reads this output
         return t
 
     def _fuser(self, Fz, x, objs, *, heads, n_img, hw):
@@ -262,6 +266,7 @@ class UNetEngine:
         cfg = self.cfg
         w = self.w
         dev = self.dev
+        ops.gn_reset(dev)
         boc = list(cfg["block_out_channels"])
         nb = len(boc)
         sample = sample.to(device=dev, dtype=torch.float16).contiguous()
@@ -294,7 +299,7 @@ class UNetEngine:
 
         def layer(L, x, kind, stage, j, h, w_):
             hw = h * w_
-            x = self._resnet(L.resnet, x, n_img, h, w_, temb_all)
+            x = self._resnet(L.resnet, x, n_img, h, w_, temb_all, gn_next=b)
             x = self._tconv(L.tconv, x, b, frames, hw)
             if "attn" in L:
                 key = (kind, stage, j, 0)
@@ -318,12 +323,12 @@ class UNetEngine:
                     skips.append((x, h, w_))
             M = w["mid"]
             hw = h * w_
-            x = self._resnet(M.res0, x, n_img, h, w_, temb_all)
+            x = self._resnet(M.res0, x, n_img, h, w_, temb_all, gn_next=b)
             x = self._tconv(M.tconv0, x, b, frames, hw)
             x = self._transformer(M.attn, x, spatial=True, n_img=n_img, hw=hw, batch=b, frames=frames, ctx_kv=ctx,
                                   key=("mid", 0, 0, 0), capture=capture, objs=objs)
             x = self._transformer(M.tattn, x, spatial=False, n_img=n_img, hw=hw, batch=b, frames=frames)
-            x = self._resnet(M.res1, x, n_img, h, w_, temb_all)
+            x = self._resnet(M.res1, x, n_img, h, w_, temb_all, gn_next=b)
             x = self._tconv(M.tconv1, x, b, frames, hw)
             for i in range(nb):
                 blk = w["up"][i]

@@ -41,15 +41,16 @@ class GuidanceGraph:
         self._graphs = {}
 
     # ------------------------------------------------------------------------------------------ module pairs
-    def _resnet_fwd(self, L, x, n_img, h, w_, temb_all):
+    def _resnet_fwd(self, L, x, n_img, h, w_, temb_all, gn_next=None):
         eps = self.cfg["norm_eps"]
         s1, s2 = ops.gn_stats_buffer(n_img, self.dev), ops.gn_stats_buffer(n_img, self.dev)
         t1 = ops.groupnorm(x, n_img, L.norm1.w, L.norm1.b, eps, silu=True, stats_out=s1)
         lo, hi = L.temb
-        t2 = ops.conv2d_3x3(t1, n_img, h, w_, L.conv1.w, L.conv1.b, rowvec=temb_all[:, lo:hi])
+        t2 = ops.conv2d_3x3(t1, n_img, h, w_, L.conv1.w, L.conv1.b, rowvec=temb_all[:, lo:hi], gn=(n_img, 32))
         t3 = ops.groupnorm(t2, n_img, L.norm2.w, L.norm2.b, eps, silu=True, stats_out=s2)
         sc = ops.linear(x, L.shortcut.w, L.shortcut.b) if "shortcut" in L else x
-        out = ops.conv2d_3x3(t3, n_img, h, w_, L.conv2.w, L.conv2.b, residual=sc)
+        out = ops.conv2d_3x3(t3, n_img, h, w_, L.conv2.w, L.conv2.b, residual=sc,
+                             gn=(gn_next, 32) if gn_next else None)  # statistics for the temporal conv layer's norm
         return out, Ctx(x=x, t2=t2, n_img=n_img, h=h, w=w_, s1=s1, s2=s2)
 
     def _resnet_bwd(self, L, c, dout):
@@ -71,7 +72,8 @@ class GuidanceGraph:
             ins.append(t)
             sts.append(ops.gn_stats_buffer(batch, self.dev))
             g = ops.groupnorm(t, batch, L.norm.w, L.norm.b, 1e-5, silu=True, stats_out=sts[-1])
-            t = ops.conv_temporal(g, batch, frames, hw, L.w, L.b, residual=x if i == 3 else None)
+            t = ops.conv_temporal(g, batch, frames, hw, L.w, L.b, residual=x if i == 3 else None,
+                                  gn=(batch, 32) if i < 3 else None)
         return t, Ctx(ins=ins, sts=sts, batch=batch, frames=frames, hw=hw)
 
     def _tconv_bwd(self, layers, c, dout):
@@ -278,6 +280,7 @@ class GuidanceGraph:
     def _run_impl(self, latents, timestep, cond_embeddings, bboxes, object_positions, guidance_attn_keys, *,
                   opts, pre, dense=False, loss_scale=1.0, base_attn_dim=(40, 72), slots=None, tok_dev=None):
         cfg, w, dev = self.cfg, self.w, self.dev
+        ops.gn_reset(dev)
         boc = list(cfg["block_out_channels"])
         nb = len(boc)
         keys = [tuple(k) for k in guidance_attn_keys]
@@ -334,7 +337,7 @@ class GuidanceGraph:
         def layer(L, x, kind, stage, j, h, w_):
             nonlocal done
             hw = h * w_
-            x, c = self._resnet_fwd(L.resnet, x, n_img, h, w_, temb_all)
+            x, c = self._resnet_fwd(L.resnet, x, n_img, h, w_, temb_all, gn_next=b)
             tape.append(("resnet", L.resnet, c, None))
             x, c = self._tconv_fwd(L.tconv, x, b, frames, hw)
             tape.append(("tconv", L.tconv, c, None))
@@ -372,7 +375,7 @@ class GuidanceGraph:
         if not done:
             M = w["mid"]
             hw = h * w_
-            x, c = self._resnet_fwd(M.res0, x, n_img, h, w_, temb_all)
+            x, c = self._resnet_fwd(M.res0, x, n_img, h, w_, temb_all, gn_next=b)
             tape.append(("resnet", M.res0, c, None))
             x, c = self._tconv_fwd(M.tconv0, x, b, frames, hw)
             tape.append(("tconv", M.tconv0, c, None))
@@ -386,7 +389,7 @@ class GuidanceGraph:
             M = w["mid"]
             x, c = self._transformer_fwd(M.tattn, x, spatial=False, n_img=n_img, hw=hw, batch=b, frames=frames)
             tape.append(("tattn", M.tattn, c, None))
-            x, c = self._resnet_fwd(M.res1, x, n_img, h, w_, temb_all)
+            x, c = self._resnet_fwd(M.res1, x, n_img, h, w_, temb_all, gn_next=b)
             tape.append(("resnet", M.res1, c, None))
             x, c = self._tconv_fwd(M.tconv1, x, b, frames, hw)
             tape.append(("tconv", M.tconv1, c, None))

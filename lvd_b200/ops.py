@@ -93,9 +93,10 @@ def pick_block_n(n, act=ACT_NONE, mn_major=False, m_tiles=None, k_contract=None)
 
 
 @functools.lru_cache(maxsize=None)
-def choose_box(dims, max_rows=128):
+def choose_box(dims, max_rows=128, div=None):
     """Pick per-axis box extents (product <= 128) for output extents `dims` (fastest axis first) that maximise
-    the fraction of useful rows over all tiles."""
+    the fraction of useful rows over all tiles.  `div[i]` (optional) constrains the box extent of axis i to divisors of
+    div[i] -- used to keep a tile inside one GroupNorm sample (ops.gemm_raw gn=...)."""
     dims = tuple(int(d) for d in dims)
     best = None
 
@@ -115,6 +116,8 @@ def choose_box(dims, max_rows=128):
             return
         d = dims[i]
         for b in range(1, min(d, max_rows // rows, 256) + 1):
+            if div is not None and div[i] is not None and div[i] % b:
+                continue
             # only divisors, or the full extent, or power-of-two chunks: keeps the search small
             if d % b == 0 or b == d or (b & (b - 1)) == 0:
                 rec(i + 1, cur + [b], rows * b)
@@ -123,9 +126,100 @@ def choose_box(dims, max_rows=128):
     return best[1]
 
 
+def _box_efficiency(dims, box):
+    tiles, total = 1, 1
+    for d, b in zip(dims, box):
+        tiles *= -(-int(d) // int(b))
+        total *= int(d)
+    return total / (tiles * 128.0)
+
+
+def _box_for_gn(dims, gn, sample_axis, per_sample):
+    """Box for a conv whose output feeds a GroupNorm with `gn = (samples, groups)`: the unconstrained choice, unless a box
+    whose extent along `sample_axis` divides `per_sample` (so that tiles stay inside one sample) is equally efficient."""
+    free = choose_box(tuple(dims))
+    if gn is None or not GN_EPILOGUE:
+        return free, None
+    div = tuple(per_sample if i == sample_axis else None for i in range(len(dims)))
+    tied = choose_box(tuple(dims), 128, div)
+    if _box_efficiency(dims, tied) + 1e-9 >= _box_efficiency(dims, free):
+        return tied, gn
+    return free, None
+
+
+# ---- GroupNorm statistics from the producing GEMM's epilogue (lvd_gemm gn_partial -> lvd_gn_finalize ->
+# lvd_groupnorm_apply): a conv whose output feeds a GroupNorm is launched with `gn=(samples, groups)`; its epilogue
+# leaves per-warp partial sums in a zero-state buffer and the output tensor carries a handle; `groupnorm` on that
+# tensor then skips its statistics pass.  LVD_GN_EPILOGUE=0 switches the path off (A/B).
+import os as _os
+
+GN_EPILOGUE = _os.environ.get("LVD_GN_EPILOGUE", "1") != "0"
+_gn_part = {}
+_gn_part_retired = []   # outgrown buffers stay alive: captured CUDA graphs hold their addresses
+_gn_pending = {}        # device -> handle whose partials have not been consumed yet
+
+
+class _GnHandle:
+    __slots__ = ("ptr", "shape", "samples", "groups", "slots", "rows_per_sample", "buf")
+
+
+def _gn_part_buffer(dev, nfloats):
+    buf = _gn_part.get(dev)
+    if buf is None or buf.numel() < nfloats:
+        if buf is not None:
+            _gn_part_retired.append(buf)
+        buf = torch.zeros(max(nfloats, 1 << 21), dtype=torch.float32, device=dev)  # zero is the buffer's rest state
+        _gn_part[dev] = buf
+    return buf
+
+
+def gn_reset(dev):
+    """Called at the start of a forward / guidance pass: if an earlier pass died between a producing GEMM and its
+    GroupNorm, bring the partial-statistics buffer back to its zero rest state."""
+    dev = torch.device(dev)
+    if _gn_pending.get(dev) is not None:
+        _gn_pending[dev] = None
+        if dev in _gn_part:
+            _gn_part[dev].zero_()
+
+
+def _gn_plan(out_dims, a_box, out_row_stride, samples, groups, n):
+    """(tiles_per_sample, subslots, rows_per_sample) when every row tile of the launch lies inside one GroupNorm sample
+    and the tiles of a sample are consecutive in tile order; None otherwise (the consumer then runs its own statistics
+    pass)."""
+    dims = [int(v) for v in out_dims]
+    box = [int(a_box[i + 1]) for i in range(4)]
+    rows = dims[0] * dims[1] * dims[2] * dims[3]
+    if rows % samples or n % groups:
+        return None
+    rps = rows // samples
+    prod = 1
+    for i in range(4):  # output rows must be numbered in tile-axis order
+        if dims[i] > 1 and int(out_row_stride[i]) != prod:
+            return None
+        prod *= dims[i]
+    prod, tps, i = 1, 1, 0
+    while i < 4 and prod * dims[i] <= rps:  # axes that lie wholly inside a sample
+        prod *= dims[i]
+        tps *= -(-dims[i] // box[i])
+        i += 1
+    if prod != rps:  # the sample ends inside axis i: it must cover whole boxes of that axis
+        if i >= 4 or rps % prod:
+            return None
+        cnt = rps // prod
+        if dims[i] % cnt or cnt % box[i]:
+            return None
+        tps *= cnt // box[i]
+        i += 1
+    if any(box[k] != 1 for k in range(i, 4) if dims[k] > 1):  # axes that index samples: one sample per tile
+        return None
+    gw = n // groups
+    return tps, (gw + 30) // 32 + 1, rps
+
+
 def gemm_raw(*, a, a_dims, a_strides, a_box, taps, k_per_tap, w, n, out, out_dims, out_row_stride,
              rv_stride=(0, 0, 0, 0), bias=None, act=ACT_NONE, rowvec=None, gamma=1.0, residual=None,
-             b_mn_major=False, block_n=None, ldb=None, b_k_tap_stride=0, b_n_tap_stride=0):
+             b_mn_major=False, block_n=None, ldb=None, b_k_tap_stride=0, b_n_tap_stride=0, gn=None):
     d = GemmDesc()
     d.a = a.data_ptr()
     for i in range(5):
@@ -163,6 +257,26 @@ def gemm_raw(*, a, a_dims, a_strides, a_box, taps, k_per_tap, w, n, out, out_dim
     d.b_k_tap_stride = int(b_k_tap_stride)
     d.b_n_tap_stride = int(b_n_tap_stride)
     d.cta_pair = int(FORCE_CTA_PAIR)
+    if gn is not None and GN_EPILOGUE and act != ACT_GEGLU and len(taps) * int(k_per_tap) >= 960:
+        # (the 5-k-block linears are bound by their epilogue: the extra column-sum pass would cost them more than the
+        # statistics pass it saves)
+        samples, groups = gn
+        plan = _gn_plan(out_dims, a_box, out_row_stride, samples, groups, n)
+        if plan is not None:
+            tps, sub, rps = plan
+            slots = tps * 4 * sub
+            dev = out.device
+            if _gn_pending.get(dev) is not None:
+                raise RuntimeError("lvd_b200: GroupNorm partial statistics of a previous producer were never consumed")
+            buf = _gn_part_buffer(dev, samples * slots * groups * 2)
+            d.gn_partial = buf.data_ptr()
+            d.gn_group_width, d.gn_groups = n // groups, int(groups)
+            d.gn_tiles_per_sample, d.gn_subslots = int(tps), int(sub)
+            h = _GnHandle()
+            h.ptr, h.shape, h.samples, h.groups = out.data_ptr(), tuple(out.shape), int(samples), int(groups)
+            h.slots, h.rows_per_sample, h.buf = slots, rps, buf
+            out._lvd_gn = h
+            _gn_pending[dev] = h
     if PROF is not None:
         m = 1
         for v in out_dims:
@@ -234,7 +348,7 @@ def linear(x, w, bias=None, *, act=ACT_NONE, residual=None, gamma=1.0, out=None,
 TAPS_3X3 = [(0, dx, dy, 0, 0) for dy in (-1, 0, 1) for dx in (-1, 0, 1)]
 
 
-def conv2d_3x3(x, n_img, h, w_, wk, bias=None, *, rowvec=None, residual=None, out=None):
+def conv2d_3x3(x, n_img, h, w_, wk, bias=None, *, rowvec=None, residual=None, out=None, gn=None):
     """3x3 / stride 1 / pad 1 convolution as 9 shifted TMA boxes.  x [n_img*h*w_, Cin]; wk [Cout, 9*Cin] with K
     ordered (ky, kx, ci).  rowvec [n_img, Cout] is added per image (time-embedding projection)."""
     _check_act(x, "x")
@@ -244,11 +358,12 @@ def conv2d_3x3(x, n_img, h, w_, wk, bias=None, *, rowvec=None, residual=None, ou
     if out is None:
         out = _alloc_out(x.shape[0], cout, x)
     ld = x.stride(0)
-    bw, bh, bn = choose_box((w_, h, n_img))
+    # gn = (samples, groups): images per GroupNorm sample = n_img / samples (1: per-frame norm, F: the 5-D norms)
+    (bw, bh, bn), gn = _box_for_gn((w_, h, n_img), gn, 2, n_img // gn[0] if gn else 1)
     return gemm_raw(a=x, a_dims=(cin, w_, h, n_img, 1), a_strides=(1, ld, ld * w_, ld * w_ * h, ld * w_ * h * n_img),
                     a_box=(64, bw, bh, bn, 1), taps=TAPS_3X3, k_per_tap=cin, w=wk, n=cout, out=out,
                     out_dims=(w_, h, n_img, 1), out_row_stride=(1, w_, w_ * h, 0), rv_stride=(0, 0, 1, 0), bias=bias,
-                    rowvec=rowvec, residual=residual)
+                    rowvec=rowvec, residual=residual, gn=gn)
 
 
 def conv2d_3x3_s2(x, n_img, h, w_, wk, bias=None, *, out=None):
@@ -277,7 +392,7 @@ def conv2d_3x3_s2(x, n_img, h, w_, wk, bias=None, *, out=None):
 TAPS_T = [(0, 0, df, 0, 0) for df in (-1, 0, 1)]
 
 
-def conv_temporal(x, batch, frames, hw, wk, bias=None, *, residual=None, out=None):
+def conv_temporal(x, batch, frames, hw, wk, bias=None, *, residual=None, out=None, gn=None):
     """Conv3d (3,1,1) pad (1,0,0) over the frame axis.  x [(batch*frames)*hw, C]; wk [Cout, 3*Cin], K = (kt, ci)."""
     _check_act(x, "x")
     cin = x.shape[1]
@@ -286,11 +401,11 @@ def conv_temporal(x, batch, frames, hw, wk, bias=None, *, residual=None, out=Non
     if out is None:
         out = _alloc_out(x.shape[0], cout, x)
     ld = x.stride(0)
-    bp, bf, bb = choose_box((hw, frames, batch))
+    (bp, bf, bb), gn = _box_for_gn((hw, frames, batch), gn, 2, batch // gn[0] if gn else 1)
     return gemm_raw(a=x, a_dims=(cin, hw, frames, batch, 1),
                     a_strides=(1, ld, ld * hw, ld * hw * frames, ld * hw * frames * batch), a_box=(64, bp, bf, bb, 1),
                     taps=TAPS_T, k_per_tap=cin, w=wk, n=cout, out=out, out_dims=(hw, frames, batch, 1),
-                    out_row_stride=(1, hw, hw * frames, 0), bias=bias, residual=residual)
+                    out_row_stride=(1, hw, hw * frames, 0), bias=bias, residual=residual, gn=gn)
 
 
 # ----------------------------------------------------------------------------------------------- normalisation
@@ -313,12 +428,31 @@ def _gn_workspace(dev, samples, groups):
 
 
 def groupnorm(x, samples, gamma, beta, eps, *, groups=32, silu=False, out=None, stats_out=None):
-    """GroupNorm (+ optional SiLU) with statistics per (sample, group); x [samples*rows_per_sample, C]."""
+    """GroupNorm (+ optional SiLU) with statistics per (sample, group); x [samples*rows_per_sample, C].  When x was
+    written by a GEMM launched with `gn=(samples, groups)` its statistics come from that GEMM's epilogue and only the
+    normalisation pass runs."""
     _check_act(x, "x")
     rows, c = x.shape
     assert rows % samples == 0
     if out is None:
         out = _alloc_out(rows, c, x)
+    h = getattr(x, "_lvd_gn", None)
+    pend = _gn_pending.get(x.device)
+    if pend is not None:
+        if h is not pend or h.ptr != x.data_ptr() or h.shape != tuple(x.shape) or h.samples != samples or \
+                h.groups != groups:
+            raise RuntimeError("lvd_b200: a GEMM left GroupNorm partial statistics for another tensor / another "
+                               "GroupNorm geometry than the one being normalised")
+        _gn_pending[x.device] = None
+        stats = stats_out if stats_out is not None else gn_stats_buffer(samples, x.device, groups)
+        with _Timed("groupnorm", 0.0, 2.0 * rows * c * 2, "gn(epilogue stats) s%d r%d c%d" % (samples, rows // samples, c)):
+            _lib.check(_lib.lib().lvd_gn_finalize(h.buf.data_ptr(), samples, h.slots, groups,
+                                                  float(h.rows_per_sample * (c // groups)), float(eps),
+                                                  stats.data_ptr(), _stream()), "gn_finalize")
+            _lib.check(_lib.lib().lvd_groupnorm_apply(x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), samples,
+                                                      rows // samples, c, groups, gamma.data_ptr(), beta.data_ptr(),
+                                                      1 if silu else 0, stats.data_ptr(), _stream()), "groupnorm_apply")
+        return out
     ws = _gn_workspace(x.device, samples, groups)
     with _Timed("groupnorm", 0.0, 2.0 * rows * c * 2, "gn s%d r%d c%d" % (samples, rows // samples, c)):
         _lib.check(_lib.lib().lvd_groupnorm(x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), samples,

@@ -111,3 +111,51 @@ def test_conv_out_tensor_core_path_matches_small_kernel(cuda):
     ref = ref.reshape(b, f, cout, h, w).permute(0, 2, 1, 3, 4)
     assert y_tc.shape == (b, cout, f, h, w)
     assert rel_err(y_tc, ref) < 3e-3 and rel_err(y_small, ref) < 3e-3
+
+
+@pytest.mark.parametrize("kind,shape,samples", [
+    ("conv2d", (48, 20, 36, 640), 2),     # resnet conv2 -> the temporal conv layer's 5-D norm (sample = 24 frames)
+    ("conv2d", (16, 16, 24, 320), 1),     # guidance pass, one prompt
+    ("tconv", (2, 24, 720, 640), 2),      # temporal conv -> next norm of the chain
+    ("tconv", (1, 16, 1024, 320), 1),
+    ("conv2d_res", (48, 10, 18, 1280), 2),
+])
+def test_groupnorm_statistics_from_the_gemm_epilogue(cuda, kind, shape, samples):
+    """GroupNorm whose statistics come from the producing conv's epilogue (lvd_gemm gn_partial -> lvd_gn_finalize ->
+    lvd_groupnorm_apply) against the two-pass GroupNorm of the same tensor: same statistics up to fp32 summation order,
+    bit-reproducible from run to run, and the partial buffer is back at zero afterwards."""
+    from lvd_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    if kind.startswith("conv2d"):
+        n_img, h, w, c = shape
+        rows = n_img * h * w
+        x = torch.randn((rows, c), generator=g).half().to(cuda)
+        wk = (torch.randn((c, 9 * c), generator=g) * 0.02).half().to(cuda)
+        res = torch.randn((rows, c), generator=g).half().to(cuda) if kind.endswith("res") else None
+        run = lambda gn: ops.conv2d_3x3(x, n_img, h, w, wk, residual=res, gn=gn)  # noqa: E731
+    else:
+        b, f, hw, c = shape
+        rows = b * f * hw
+        x = torch.randn((rows, c), generator=g).half().to(cuda)
+        wk = (torch.randn((c, 3 * c), generator=g) * 0.03).half().to(cuda)
+        run = lambda gn: ops.conv_temporal(x, b, f, hw, wk, gn=gn)  # noqa: E731
+    gamma = (1 + 0.1 * torch.randn(c, generator=g)).half().to(cuda)
+    beta = (0.1 * torch.randn(c, generator=g)).half().to(cuda)
+    assert ops.GN_EPILOGUE
+    y_plain = run(None)
+    ref_stats = ops.gn_stats_buffer(samples, cuda)
+    z_ref = ops.groupnorm(y_plain, samples, gamma, beta, 1e-5, silu=True, stats_out=ref_stats)
+    outs = []
+    for rep in range(3):
+        y = run((samples, 32))
+        assert getattr(y, "_lvd_gn", None) is not None, "the epilogue path was not taken"
+        assert torch.equal(y, y_plain)
+        st = ops.gn_stats_buffer(samples, cuda)
+        z = ops.groupnorm(y, samples, gamma, beta, 1e-5, silu=True, stats_out=st)
+        outs.append((z, st))
+        assert ops._gn_pending[cuda] is None
+        assert float(ops._gn_part[cuda].abs().max()) == 0.0  # self-cleaning
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[2][1])  # bit-reproducible
+    z, st = outs[0]
+    assert ((st - ref_stats).abs() / ref_stats.abs().clamp_min(1e-3)).max().item() < 1e-4
+    assert rel_err(z, z_ref) <= 1e-3
