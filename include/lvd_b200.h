@@ -85,10 +85,27 @@ typedef struct lvd_gemm_desc {
    * gn_partial: fp32 [samples][gn_tiles_per_sample][4][gn_subslots][gn_groups][2], ZERO on entry; every epilogue warp
    * adds {sum, sum of squares} of its 32 rows per channel group (one writer per float: bit-reproducible).  A row tile
    * must lie inside one sample (row tiles of a sample are consecutive in tile order); gn_group_width = n / gn_groups;
-   * gn_subslots >= (gn_group_width + 30) / 32 + 1.  lvd_gn_finalize turns the partials into {mean, rstd} and clears
-   * them; lvd_groupnorm_apply normalises with given statistics. */
+   * gn_subslots >= (gn_group_width + 30) / 32 + 1.  lvd_groupnorm_apply folds the partials into the statistics, clears
+   * them and normalises. */
   void* gn_partial;
   int32_t gn_group_width, gn_groups, gn_tiles_per_sample, gn_subslots;
+  /* LayerNorm folded into the linear that consumes it (models/attention.py:126-170: norm1 -> attn1.to_q/k/v,
+   * norm2 -> attn2.to_q, norm3 -> ff.net.0): A is the RAW LayerNorm input, B the weight with the LayerNorm scale
+   * folded in (B'[n][k] = gamma_k W[n][k], fp16), and the epilogue finishes
+   *     out[r][n] = rstd_r * (acc[r][n] - mean_r * ln_colsum[n]) + ln_bias[n]
+   * ln_colsum[n] = sum_k B'[n][k] (fp32, of the rounded B'), ln_bias[n] = sum_k beta_k W[n][k] + bias[n] (fp32);
+   * ln_stats = fp32 {mean, rstd} per row, row = sum coord_i * ln_row_stride[i] (lvd_ln_rowstats).  Needs act none or
+   * GEGLU, no bias / residual / rowvec / gamma.  NULL = off. */
+  const void* ln_stats;
+  const void* ln_colsum;
+  const void* ln_bias;
+  int32_t ln_row_stride[4];
+  /* Row statistics of the OUTPUT for the LayerNorm that consumes it: lnstat_partial = fp32 {sum, sum of squares}
+   * [n / 32][lnstat_rows] of the 32 fp16 outputs of a row in each 32-column slab (every element written: no initial
+   * state); row = sum coord_i * lnstat_row_stride[i].  NULL = off. */
+  void* lnstat_partial;
+  int64_t lnstat_rows;
+  int32_t lnstat_row_stride[4];
 } lvd_gemm_desc;
 
 int lvd_gemm(const lvd_gemm_desc* d, void* stream);
@@ -155,16 +172,19 @@ int lvd_groupnorm(const void* x, int64_t ld_x, void* y, int64_t ld_y, int32_t sa
                   int32_t channels, int32_t groups, const void* gamma, const void* beta, float eps, int32_t silu,
                   void* stats_out /* optional fp32 [samples, groups, 2] = {mean, rstd}, kept for lvd_groupnorm_bwd */,
                   void* workspace, int64_t workspace_bytes, void* stream);
-/* Statistics from the producing lvd_gemm's epilogue (gn_partial): fold `slots` = tiles_per_sample * 4 * subslots partial
- * pairs per (sample, group) in a fixed order into stats[sample][group] = {mean, rstd} (count = elements per group) and
- * reset the partials to zero; then normalise with them (the second pass of lvd_groupnorm only). */
-int lvd_gn_finalize(void* partial, int32_t samples, int32_t slots, int32_t groups, float count, float eps,
-                    void* stats_f32, void* stream);
+/* GroupNorm of a tensor written by an lvd_gemm with gn_partial set: the statistics pass is replaced by a fold of the
+ * `slots` = tiles_per_sample * 4 * subslots partial pairs per (sample, group) that GEMM's epilogue left in gn_partial
+ * (fixed order; the partials are reset to zero for the next producer), then the normalisation pass of lvd_groupnorm
+ * runs.  workspace as for lvd_groupnorm; stats_out (required) receives {mean, rstd}. */
 int lvd_groupnorm_apply(const void* x, int64_t ld_x, void* y, int64_t ld_y, int32_t samples, int64_t rows_per_sample,
-                        int32_t channels, int32_t groups, const void* gamma, const void* beta, int32_t silu,
-                        const void* stats_f32, void* stream);
+                        int32_t channels, int32_t groups, const void* gamma, const void* beta, float eps, int32_t silu,
+                        void* gn_partial, int32_t slots, void* workspace, void* stats_out, void* stream);
 int lvd_layernorm(const void* x, int64_t ld_x, void* y, int64_t ld_y, int64_t rows, int32_t channels,
                   const void* gamma, const void* beta, float eps, void* stream);
+/* Folds lvd_gemm's lnstat_partial ([slabs][rows] {sum, sum of squares}, slabs = channels / 32) into stats[row] =
+ * {mean, rstd} for a LayerNorm folded into the next lvd_gemm (ln_stats). */
+int lvd_ln_rowstats(const void* lnstat_partial, int32_t slabs, int64_t rows, int32_t channels, float eps,
+                    void* stats_f32, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Thin ends of the UNet and small element-wise pieces.

@@ -43,6 +43,13 @@ class GemmDesc(ctypes.Structure):
         ("gn_groups", ctypes.c_int32),
         ("gn_tiles_per_sample", ctypes.c_int32),
         ("gn_subslots", ctypes.c_int32),
+        ("ln_stats", ctypes.c_void_p),
+        ("ln_colsum", ctypes.c_void_p),
+        ("ln_bias", ctypes.c_void_p),
+        ("ln_row_stride", ctypes.c_int32 * 4),
+        ("lnstat_partial", ctypes.c_void_p),
+        ("lnstat_rows", ctypes.c_int64),
+        ("lnstat_row_stride", ctypes.c_int32 * 4),
     ]
 
 
@@ -141,8 +148,8 @@ def _declare(l):
     l.lvd_gemm.argtypes = [ctypes.POINTER(GemmDesc), vp]
     l.lvd_attention.argtypes = [ctypes.POINTER(AttnDesc), vp]
     l.lvd_groupnorm.argtypes = [vp, i64, vp, i64, i32, i64, i32, i32, vp, vp, f32, i32, vp, vp, i64, vp]
-    l.lvd_gn_finalize.argtypes = [vp, i32, i32, i32, f32, f32, vp, vp]
-    l.lvd_groupnorm_apply.argtypes = [vp, i64, vp, i64, i32, i64, i32, i32, vp, vp, i32, vp, vp]
+    l.lvd_ln_rowstats.argtypes = [vp, i32, i64, i32, f32, vp, vp]
+    l.lvd_groupnorm_apply.argtypes = [vp, i64, vp, i64, i32, i64, i32, i32, vp, vp, f32, i32, vp, i32, vp, vp, vp]
     l.lvd_layernorm.argtypes = [vp, i64, vp, i64, i64, i32, vp, vp, f32, vp]
     l.lvd_conv_in.argtypes = [vp, vp, vp, vp, i64, i32, i32, i32, i32, i32, i32, vp]
     l.lvd_conv_out.argtypes = [vp, i64, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]
@@ -197,8 +204,8 @@ EXPORTS = [
     "lvd_gemm",
     "lvd_attention",
     "lvd_groupnorm",
-    "lvd_gn_finalize",
     "lvd_groupnorm_apply",
+    "lvd_ln_rowstats",
     "lvd_layernorm",
     "lvd_conv_in",
     "lvd_conv_out",

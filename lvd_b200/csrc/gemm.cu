@@ -26,7 +26,7 @@ constexpr int kSlabBufs = 8;             // 4 epilogue groups x 2 buffers
 constexpr int kBarrierBytes = 512;       // mbarriers (8+8 ring, 4+4 accumulator, 8 residual) + the TMEM address
 
 // epilogue specialisations (template parameter): the common cases carry no feature branches in the slab loop
-enum { kEpiGeneric = 0, kEpiBias = 1, kEpiResidual = 2, kEpiGeglu = 3 };
+enum { kEpiGeneric = 0, kEpiBias = 1, kEpiResidual = 2, kEpiGeglu = 3, kEpiLnBias = 4, kEpiLnGeglu = 5 };
 
 struct GemmArgs {
   CUtensorMap map_a;
@@ -60,6 +60,19 @@ struct GemmArgs {
   // gn_part[sample][row tile of the sample][row quarter][slab residue][group][2]
   float* gn_part;
   int gn_gw, gn_groups, gn_tiles_per_sample, gn_sub;
+  // LayerNorm folded into this linear (kEpiLn*): A is the raw LayerNorm input, B carries the LayerNorm weight
+  // (B' = gamma o W), and the epilogue finishes  out[r][n] = rstd_r * (acc[r][n] - mean_r * ln_cs[n]) + ln_bias[n]
+  // with ln_cs[n] = sum_k B'[n][k], ln_bias[n] = sum_k beta_k W[n][k] + bias[n]; ln_stats[row] = {mean, rstd}, row =
+  // sum coord_i * ln_stride[i] (the A row).
+  const float2* ln_stats;
+  const float* ln_cs;
+  const float* ln_bias;
+  int ln_stride[4];
+  // Row statistics of the OUTPUT for the LayerNorm that consumes it (NULL = off): every epilogue thread stores
+  // {sum, sum of squares} of the 32 fp16 values of its row in the slab to lnstat_part[slab][row] (one writer each).
+  float2* lnstat_part;
+  long long lnstat_rows;
+  int lnstat_stride[4];
 };
 
 // Timeline tracing for tools/trace_gemm.py (LVD_GEMM_DEBUG bit 6): CTA 0 appends (event << 48 | globaltimer ns).
@@ -323,7 +336,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     const int grp = (warp - 2) >> 2;
     const bool leader_warp = ((warp - 2) & 3) == 0;  // one elected lane of this warp issues the group's TMA traffic
     const int r = q * 32 + lane;
-    const bool geglu = kEpi == kEpiGeglu || (kEpi == kEpiGeneric && g.act == 2);
+    const bool geglu = kEpi == kEpiGeglu || kEpi == kEpiLnGeglu || (kEpi == kEpiGeneric && g.act == 2);
+    const bool has_ln = kEpi == kEpiLnBias || kEpi == kEpiLnGeglu;
+    const bool has_lnstat = g.lnstat_part != nullptr;
     const bool has_res = kEpi == kEpiResidual || (kEpi == kEpiGeneric && g.residual != nullptr);
     const bool has_rowvec = kEpi == kEpiGeneric && g.rowvec != nullptr;
     const bool has_gamma = kEpi == kEpiGeneric && g.gamma != 1.0f;
@@ -332,7 +347,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     const __half* const bias = g.bias;
     const bool has_gn = g.gn_part != nullptr;
     int j[4];
-    if (has_rowvec || has_gn) {
+    if (has_rowvec || has_gn || has_ln || has_lnstat) {
       int t = r;
       j[0] = t % g.box[0];
       t /= g.box[0];
@@ -395,13 +410,26 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         const int smp = rt / g.gn_tiles_per_sample, til = rt - smp * g.gn_tiles_per_sample;
         gn_slot0 = ((static_cast<long long>(smp) * g.gn_tiles_per_sample + til) * 4 + q) * g.gn_sub * g.gn_groups * 2;
       }
-      if (has_rowvec || has_gn) {
+      float ln_mean = 0.f, ln_rstd = 1.f;
+      long long lnstat_row = 0;
+      if (has_rowvec || has_gn || has_ln || has_lnstat) {
         const int x0 = it.t0 * g.box[0] + j[0], x1 = it.t1 * g.box[1] + j[1];
         const int x2 = it.t2 * g.box[2] + j[2], x3 = it.t3 * g.box[3] + j[3];
         valid = j[3] < g.box[3] && x0 < g.out_dims[0] && x1 < g.out_dims[1] && x2 < g.out_dims[2] &&
                 x3 < g.out_dims[3];
         rvrow = static_cast<long long>(x0) * g.rv_stride[0] + static_cast<long long>(x1) * g.rv_stride[1] +
                 static_cast<long long>(x2) * g.rv_stride[2] + static_cast<long long>(x3) * g.rv_stride[3];
+        if (has_ln && valid) {
+          const float2 st = __ldg(g.ln_stats + static_cast<long long>(x0) * g.ln_stride[0] +
+                                  static_cast<long long>(x1) * g.ln_stride[1] +
+                                  static_cast<long long>(x2) * g.ln_stride[2] +
+                                  static_cast<long long>(x3) * g.ln_stride[3]);
+          ln_mean = st.x;
+          ln_rstd = st.y;
+        }
+        if (has_lnstat)
+          lnstat_row = static_cast<long long>(x0) * g.lnstat_stride[0] + static_cast<long long>(x1) * g.lnstat_stride[1] +
+                       static_cast<long long>(x2) * g.lnstat_stride[2] + static_cast<long long>(x3) * g.lnstat_stride[3];
       }
       if (leader_warp && lane == 0) trace_event(g, 16 + grp * 16 + 0);  // epilogue group: waiting for the tile
       LVD_PH(7);
@@ -421,6 +449,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         res_issued = false;
         LVD_PH(1);
         uint4 packed[4];
+        float ls1 = 0.f, ls2 = 0.f;  // has_lnstat: sum / sum of squares of this row's 32 staged values
 #pragma unroll
         for (int h = 0; h < 2; ++h) {  // two 16-column halves: bounds the live registers
           const int ucol = sl * 32 + h * 16;  // tile-relative accumulator column
@@ -428,7 +457,28 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
           uint32_t rv[16];
           float v[16];
           tmem_ld16(taddr + ucol, rv);
-          if (geglu) {
+          if (geglu && has_ln) {
+            uint32_t rg[16];
+            tmem_ld16(taddr + n_half + ucol, rg);
+            const int tcol = it.nt * block_n + ucol;  // value at tcol, gate at tcol + n_half of the interleaved weight
+            tmem_ld_wait();
+#pragma unroll
+            for (int i4 = 0; i4 < 4; ++i4) {
+              const float4 cv = __ldg(reinterpret_cast<const float4*>(g.ln_cs + tcol) + i4);
+              const float4 bv = __ldg(reinterpret_cast<const float4*>(g.ln_bias + tcol) + i4);
+              const float4 cg = __ldg(reinterpret_cast<const float4*>(g.ln_cs + tcol + n_half) + i4);
+              const float4 bg = __ldg(reinterpret_cast<const float4*>(g.ln_bias + tcol + n_half) + i4);
+              const float cva[4] = {cv.x, cv.y, cv.z, cv.w}, bva[4] = {bv.x, bv.y, bv.z, bv.w};
+              const float cga[4] = {cg.x, cg.y, cg.z, cg.w}, bga[4] = {bg.x, bg.y, bg.z, bg.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int i = 4 * i4 + e;
+                const float val = fmaf(ln_rstd, fmaf(-ln_mean, cva[e], __uint_as_float(rv[i])), bva[e]);
+                const float gate = fmaf(ln_rstd, fmaf(-ln_mean, cga[e], __uint_as_float(rg[i])), bga[e]);
+                v[i] = val * gelu_erf_f(gate);
+              }
+            }
+          } else if (geglu) {
             uint32_t rg[16];
             tmem_ld16(taddr + n_half + ucol, rg);
             // value * gelu(gate); biases of the interleaved weight: value at tcol, gate at tcol + n_half
@@ -448,6 +498,17 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
 #pragma unroll
             for (int i = 0; i < 16; ++i)
               v[i] = (__uint_as_float(rv[i]) + bv[i]) * gelu_erf_f(__uint_as_float(rg[i]) + bg[i]);
+          } else if (has_ln) {
+            tmem_ld_wait();
+#pragma unroll
+            for (int i4 = 0; i4 < 4; ++i4) {
+              const float4 c = __ldg(reinterpret_cast<const float4*>(g.ln_cs + ocol) + i4);
+              const float4 b = __ldg(reinterpret_cast<const float4*>(g.ln_bias + ocol) + i4);
+              v[4 * i4] = fmaf(ln_rstd, fmaf(-ln_mean, c.x, __uint_as_float(rv[4 * i4])), b.x);
+              v[4 * i4 + 1] = fmaf(ln_rstd, fmaf(-ln_mean, c.y, __uint_as_float(rv[4 * i4 + 1])), b.y);
+              v[4 * i4 + 2] = fmaf(ln_rstd, fmaf(-ln_mean, c.z, __uint_as_float(rv[4 * i4 + 2])), b.z);
+              v[4 * i4 + 3] = fmaf(ln_rstd, fmaf(-ln_mean, c.w, __uint_as_float(rv[4 * i4 + 3])), b.w);
+            }
           } else {
             if (bias) {
               float b[16];
@@ -496,7 +557,18 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
           }
           packed[2 * h] = pack8(&v[0]);
           packed[2 * h + 1] = pack8(&v[8]);
+          if (has_lnstat) {  // statistics of the fp16 values the LayerNorm will read
+            unpack8(packed[2 * h], *reinterpret_cast<float(*)[8]>(&v[0]));
+            unpack8(packed[2 * h + 1], *reinterpret_cast<float(*)[8]>(&v[8]));
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              ls1 += v[i];
+              ls2 = fmaf(v[i], v[i], ls2);
+            }
+          }
         }
+        if (has_lnstat && valid)
+          g.lnstat_part[static_cast<long long>(gcol >> 5) * g.lnstat_rows + lnstat_row] = make_float2(ls1, ls2);
         LVD_PH(2);
         if (sl + 4 >= nslabs) release_acc();  // this warp's last TMEM reads of the tile have completed
         if (leader_warp && lane == 0) trace_event(g, 16 + grp * 16 + 2);  // slab math done
@@ -752,6 +824,23 @@ static int launch_gemm(const lvd_gemm_desc* d, cudaStream_t stream) {
     LVD_REQUIRE(g.gn_sub >= (g.gn_gw + 30) / 32 + 1, "lvd_gemm: gn_subslots=%d too small for groups of %d channels",
                 g.gn_sub, g.gn_gw);
   }
+  g.ln_stats = static_cast<const float2*>(d->ln_stats);
+  g.ln_cs = static_cast<const float*>(d->ln_colsum);
+  g.ln_bias = static_cast<const float*>(d->ln_bias);
+  g.lnstat_part = static_cast<float2*>(d->lnstat_partial);
+  g.lnstat_rows = d->lnstat_rows;
+  for (int i = 0; i < 4; ++i) {
+    g.ln_stride[i] = d->ln_row_stride[i];
+    g.lnstat_stride[i] = d->lnstat_row_stride[i];
+  }
+  if (g.ln_stats) {
+    LVD_REQUIRE(g.ln_cs && g.ln_bias, "lvd_gemm: ln_stats needs ln_colsum and ln_bias");
+    LVD_REQUIRE(d->rowvec == nullptr && d->gamma == 1.0f && !d->residual && !d->bias && (d->act == 0 || d->act == 2) &&
+                    d->n_taps == 1 && !g.gn_part,
+                "lvd_gemm: a folded LayerNorm needs a plain linear (act none / GEGLU; bias inside ln_bias)");
+  }
+  if (g.lnstat_part)
+    LVD_REQUIRE(d->act != 2 && g.lnstat_rows >= 1, "lvd_gemm: lnstat_partial needs lnstat_rows and no GEGLU");
   g.idesc = make_idesc_f16(128u * ctas, static_cast<uint32_t>(d->block_n), 0, d->b_mn_major ? 1u : 0u);
 
   const int smem_bytes = 1024 + stages * stage_bytes + n_slabs_smem * kSlabBytes + kBarrierBytes;
@@ -759,14 +848,17 @@ static int launch_gemm(const lvd_gemm_desc* d, cudaStream_t stream) {
   int epi = kEpiGeneric;
   if (plain && d->act == 2 && !d->residual) epi = kEpiGeglu;
   if (plain && d->act == 0) epi = d->residual ? kEpiResidual : kEpiBias;
+  if (g.ln_stats) epi = d->act == 2 ? kEpiLnGeglu : kEpiLnBias;
   typedef void (*KernelFn)(const GemmArgs);
-  static const KernelFn kernels[2][4] = {
-      {gemm_tc_kernel<1, 0>, gemm_tc_kernel<1, 1>, gemm_tc_kernel<1, 2>, gemm_tc_kernel<1, 3>},
-      {gemm_tc_kernel<2, 0>, gemm_tc_kernel<2, 1>, gemm_tc_kernel<2, 2>, gemm_tc_kernel<2, 3>}};
+  static const KernelFn kernels[2][6] = {
+      {gemm_tc_kernel<1, 0>, gemm_tc_kernel<1, 1>, gemm_tc_kernel<1, 2>, gemm_tc_kernel<1, 3>, gemm_tc_kernel<1, 4>,
+       gemm_tc_kernel<1, 5>},
+      {gemm_tc_kernel<2, 0>, gemm_tc_kernel<2, 1>, gemm_tc_kernel<2, 2>, gemm_tc_kernel<2, 3>, gemm_tc_kernel<2, 4>,
+       gemm_tc_kernel<2, 5>}};
   static bool attr_set = false;
   if (!attr_set) {
     for (int i = 0; i < 2; ++i)
-      for (int j = 0; j < 4; ++j)
+      for (int j = 0; j < 6; ++j)
         LVD_CHECK_CUDA(cudaFuncSetAttribute(kernels[i][j], cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
     attr_set = true;
   }

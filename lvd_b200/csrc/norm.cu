@@ -41,6 +41,27 @@ __device__ __forceinline__ void st8(__half* p, const float (&v)[8]) {
 // ------------------------------------------------------------------------------------------------ GroupNorm
 // x is viewed as [samples][rows_per_sample][C] (row stride ld).  4-D GroupNorm: sample = one frame image;
 // 5-D GroupNorm (TemporalConvLayer / TransformerTemporalModel): sample = one video, rows span all frames.
+// Sum of the `count` partial {sum, sumsq} pairs of (sample s, group g) that thread `part` of `nparts` owns: four
+// independent loads in flight, fixed order (deterministic).
+__device__ __forceinline__ void fold_partials(const float* __restrict__ partial, int s, int count, int G, int g,
+                                              int part, int nparts, float& a, float& b) {
+  const float2* p = reinterpret_cast<const float2*>(partial) + static_cast<long long>(s) * count * G + g;
+  int k = part;
+  for (; k + 3 * nparts < count; k += 4 * nparts) {
+    const float2 v0 = __ldcg(p + static_cast<long long>(k) * G);
+    const float2 v1 = __ldcg(p + static_cast<long long>(k + nparts) * G);
+    const float2 v2 = __ldcg(p + static_cast<long long>(k + 2 * nparts) * G);
+    const float2 v3 = __ldcg(p + static_cast<long long>(k + 3 * nparts) * G);
+    a += (v0.x + v1.x) + (v2.x + v3.x);
+    b += (v0.y + v1.y) + (v2.y + v3.y);
+  }
+  for (; k < count; k += nparts) {
+    const float2 v0 = __ldcg(p + static_cast<long long>(k) * G);
+    a += v0.x;
+    b += v0.y;
+  }
+}
+
 // Pass 1 writes per-(sample, chunk, group) partial {sum, sumsq}; pass 2 folds the chunks (deterministic order),
 // normalises, applies the affine and optional SiLU.  Thread -> 8-channel vector mapping is fixed so the
 // per-channel accumulators / affine live in registers.
@@ -125,12 +146,7 @@ __global__ void gn_stats_kernel(const __half* __restrict__ x, long long ld, long
   {
     const int g = threadIdx.x % G, part = threadIdx.x / G;
     float a = 0.f, b = 0.f;
-    if (part < nparts)
-      for (int k = part; k < chunks; k += nparts) {
-        const float* p = partial + ((static_cast<long long>(s) * chunks + k) * G + g) * 2;
-        a += __ldcg(p);
-        b += __ldcg(p + 1);
-      }
+    if (part < nparts) fold_partials(partial, s, chunks, G, g, part, nparts, a, b);
     s_a[threadIdx.x] = a;
     s_b[threadIdx.x] = b;
   }
@@ -332,7 +348,8 @@ __global__ void __launch_bounds__(320, 2) gn_stream_stats_kernel(const __half* _
 __global__ void __launch_bounds__(320, 2) gn_stream_apply_kernel(const __half* __restrict__ x, long long ld_x,
                                                                   __half* __restrict__ y, long long ld_y,
                                                                   long long rows_per_sample, int C, int G, int chunks,
-                                                                  int T, const float* __restrict__ partial, float n,
+                                                                  int pchunks, int T, const float* __restrict__ partial,
+                                                                  float n,
                                                                   float eps, float* __restrict__ stats,
                                                                   const __half* __restrict__ gamma,
                                                                   const __half* __restrict__ beta, int silu) {
@@ -368,23 +385,11 @@ __global__ void __launch_bounds__(320, 2) gn_stream_apply_kernel(const __half* _
     for (int it = 0; it < kGnStages && it < st.nit; ++it) st.issue(it);
   // Every CTA folds the sample's chunk partials itself (fixed order: deterministic, identical in all CTAs) while its
   // first stages are in flight -- a finalising "last CTA" in the statistics pass left the GPU idle for its whole tail.
-  if (partial == nullptr) {
-    // statistics given (produced by the epilogue of the GEMM that wrote x: lvd_gn_finalize)
-    if (threadIdx.x < G) {
-      s_mean[threadIdx.x] = __ldcg(stats + (static_cast<long long>(s) * G + threadIdx.x) * 2);
-      s_rstd[threadIdx.x] = __ldcg(stats + (static_cast<long long>(s) * G + threadIdx.x) * 2 + 1);
-    }
-    __syncthreads();
-  } else {
+  {
     const int nparts = blockDim.x / G;
     const int g = threadIdx.x % G, part = threadIdx.x / G;
     float a = 0.f, b = 0.f;
-    if (part < nparts)
-      for (int k = part; k < chunks; k += nparts) {
-        const float* p = partial + ((static_cast<long long>(s) * chunks + k) * G + g) * 2;
-        a += __ldcg(p);
-        b += __ldcg(p + 1);
-      }
+    if (part < nparts) fold_partials(partial, s, pchunks, G, g, part, nparts, a, b);
     s_a[threadIdx.x] = a;
     s_b[threadIdx.x] = b;
     __syncthreads();
@@ -628,7 +633,7 @@ extern "C" int lvd_groupnorm(const void* x, int64_t ld_x, void* y, int64_t ld_y,
         static_cast<float*>(workspace));
     gn_stream_apply_kernel<<<sgrid, threads, ring_bytes, st>>>(
         static_cast<const __half*>(x), ld_x, static_cast<__half*>(y), ld_y, rows_per_sample, channels, groups,
-        static_cast<int>(schunks), T, static_cast<const float*>(workspace),
+        static_cast<int>(schunks), static_cast<int>(schunks), T, static_cast<const float*>(workspace),
         static_cast<float>(rows_per_sample) * (channels / groups), eps, stats, static_cast<const __half*>(gamma),
         static_cast<const __half*>(beta), silu);
     } else {  // very wide rows: register-staged passes
@@ -649,22 +654,42 @@ extern "C" int lvd_groupnorm(const void* x, int64_t ld_x, void* y, int64_t ld_y,
 }
 
 namespace lvd {
-// Folds the per-warp partial sums written by gemm_tc_kernel's epilogue (gn_part) into {mean, rstd} per (sample, group),
-// in a fixed order (deterministic), and clears them for the next producer.  One CTA per sample; thread = (group, part).
-__global__ void gn_tiles_finalize_kernel(float* __restrict__ part, int slots, int G, float n, float eps,
-                                         float* __restrict__ stats) {
+// Folds the per-warp partial sums written by gemm_tc_kernel's epilogue (gn_part, `slots` per sample) into kGnFoldParts
+// partial pairs per (sample, group) that gn_stream_apply_kernel finishes, and clears them for the next producer.  CTA
+// (c, sample) owns a contiguous range of slots; thread = (group, part) walks it with four loads in flight; every order
+// is fixed (deterministic).
+constexpr int kGnFoldParts = 16;
+__global__ void __launch_bounds__(1024) gn_tiles_fold_kernel(float* __restrict__ part, int slots, int G,
+                                                             float* __restrict__ partial) {
   __shared__ float s_a[1024], s_b[1024];
-  const int s = blockIdx.x;
+  const int c = blockIdx.x, s = blockIdx.y;
   const int g = threadIdx.x % G, p = threadIdx.x / G, nparts = blockDim.x / G;
+  const int per = (slots + kGnFoldParts - 1) / kGnFoldParts;
+  const int k0 = c * per, k1 = k0 + per < slots ? k0 + per : slots;
+  float2* base = reinterpret_cast<float2*>(part) + static_cast<long long>(s) * slots * G + g;
+  const float2 zero = make_float2(0.f, 0.f);
   float a = 0.f, b = 0.f;
-  if (p < nparts)
-    for (int k = p; k < slots; k += nparts) {
-      float* q = part + ((static_cast<long long>(s) * slots + k) * G + g) * 2;
-      a += q[0];
-      b += q[1];
-      q[0] = 0.f;
-      q[1] = 0.f;
-    }
+  int k = k0 + p;
+  for (; k + 3 * nparts < k1; k += 4 * nparts) {
+    float2* q0 = base + static_cast<long long>(k) * G;
+    float2* q1 = base + static_cast<long long>(k + nparts) * G;
+    float2* q2 = base + static_cast<long long>(k + 2 * nparts) * G;
+    float2* q3 = base + static_cast<long long>(k + 3 * nparts) * G;
+    const float2 v0 = __ldcg(q0), v1 = __ldcg(q1), v2 = __ldcg(q2), v3 = __ldcg(q3);
+    *q0 = zero;
+    *q1 = zero;
+    *q2 = zero;
+    *q3 = zero;
+    a += (v0.x + v1.x) + (v2.x + v3.x);
+    b += (v0.y + v1.y) + (v2.y + v3.y);
+  }
+  for (; k < k1; k += nparts) {
+    float2* q0 = base + static_cast<long long>(k) * G;
+    const float2 v0 = __ldcg(q0);
+    *q0 = zero;
+    a += v0.x;
+    b += v0.y;
+  }
   s_a[threadIdx.x] = a;
   s_b[threadIdx.x] = b;
   __syncthreads();
@@ -675,34 +700,22 @@ __global__ void gn_tiles_finalize_kernel(float* __restrict__ part, int slots, in
       a += s_a[i * G + threadIdx.x];
       b += s_b[i * G + threadIdx.x];
     }
-    const float mean = a / n;
-    float var = b / n - mean * mean;
-    var = var > 0.f ? var : 0.f;
-    stats[(static_cast<long long>(s) * G + threadIdx.x) * 2] = mean;
-    stats[(static_cast<long long>(s) * G + threadIdx.x) * 2 + 1] = rsqrtf(var + eps);
+    float* o = partial + ((static_cast<long long>(s) * kGnFoldParts + c) * G + threadIdx.x) * 2;
+    o[0] = a;
+    o[1] = b;
   }
 }
 }  // namespace lvd
 
-extern "C" int lvd_gn_finalize(void* partial, int32_t samples, int32_t slots, int32_t groups, float count, float eps,
-                               void* stats_f32, void* stream) {
-  LVD_REQUIRE(partial && stats_f32 && samples >= 1 && slots >= 1 && groups >= 1 && groups <= 64 && count > 0.f,
-              "lvd_gn_finalize: bad arguments");
-  const int threads = 1024 / groups * groups;
-  gn_tiles_finalize_kernel<<<samples, threads, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<float*>(partial), slots, groups, count, eps, static_cast<float*>(stats_f32));
-  g_launches.fetch_add(1, std::memory_order_relaxed);
-  LVD_CHECK_CUDA(cudaGetLastError());
-  return LVD_OK;
-}
-
 extern "C" int lvd_groupnorm_apply(const void* x, int64_t ld_x, void* y, int64_t ld_y, int32_t samples,
                                    int64_t rows_per_sample, int32_t channels, int32_t groups, const void* gamma,
-                                   const void* beta, int32_t silu, const void* stats_f32, void* stream) {
-  LVD_REQUIRE(x && y && gamma && beta && stats_f32, "lvd_groupnorm_apply: null pointer");
+                                   const void* beta, float eps, int32_t silu, void* gn_partial, int32_t slots,
+                                   void* workspace, void* stats_out, void* stream) {
+  LVD_REQUIRE(x && y && gamma && beta && gn_partial && workspace && stats_out, "lvd_groupnorm_apply: null pointer");
   LVD_REQUIRE(channels % 8 == 0 && channels % groups == 0 && groups <= 64, "lvd_groupnorm_apply: C=%d G=%d unsupported",
               channels, groups);
-  LVD_REQUIRE(ld_x % 8 == 0 && ld_y % 8 == 0 && samples >= 1 && rows_per_sample >= 1, "lvd_groupnorm_apply: bad shape");
+  LVD_REQUIRE(ld_x % 8 == 0 && ld_y % 8 == 0 && samples >= 1 && rows_per_sample >= 1 && slots >= 1,
+              "lvd_groupnorm_apply: bad shape");
   const int threads = gn_threads(channels);
   const long long row_bytes = 2LL * channels;
   const int rpp_ = threads / (channels / 8);
@@ -720,12 +733,52 @@ extern "C" int lvd_groupnorm_apply(const void* x, int64_t ld_x, void* y, int64_t
     LVD_CHECK_CUDA(cudaFuncSetAttribute(gn_stream_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     attr = true;
   }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
   dim3 sgrid(static_cast<unsigned>(schunks), static_cast<unsigned>(samples));
-  gn_stream_apply_kernel<<<sgrid, threads, ring_bytes, static_cast<cudaStream_t>(stream)>>>(
+  gn_tiles_fold_kernel<<<dim3(kGnFoldParts, static_cast<unsigned>(samples)), 1024 / groups * groups, 0, st>>>(
+      static_cast<float*>(gn_partial), slots, groups, static_cast<float*>(workspace));
+  gn_stream_apply_kernel<<<sgrid, threads, ring_bytes, st>>>(
       static_cast<const __half*>(x), ld_x, static_cast<__half*>(y), ld_y, rows_per_sample, channels, groups,
-      static_cast<int>(schunks), T, nullptr, static_cast<float>(rows_per_sample) * (channels / groups), 0.f,
-      const_cast<float*>(static_cast<const float*>(stats_f32)), static_cast<const __half*>(gamma),
-      static_cast<const __half*>(beta), silu);
+      static_cast<int>(schunks), kGnFoldParts, T, static_cast<const float*>(workspace),
+      static_cast<float>(rows_per_sample) * (channels / groups), eps, static_cast<float*>(stats_out),
+      static_cast<const __half*>(gamma), static_cast<const __half*>(beta), silu);
+  g_launches.fetch_add(2, std::memory_order_relaxed);
+  LVD_CHECK_CUDA(cudaGetLastError());
+  return LVD_OK;
+}
+
+namespace lvd {
+// {sum, sum of squares} per (slab, row) left by gemm_tc_kernel's epilogue -> {mean, rstd} per row (fixed order).
+__global__ void __launch_bounds__(256) ln_rowstats_kernel(const float2* __restrict__ part, int slabs, long long rows,
+                                                          float inv_c, float eps, float2* __restrict__ stats) {
+  const long long r = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  float a = 0.f, b = 0.f;
+  int k = 0;
+  for (; k + 3 < slabs; k += 4) {
+    const float2 v0 = __ldcg(part + k * rows + r), v1 = __ldcg(part + (k + 1) * rows + r);
+    const float2 v2 = __ldcg(part + (k + 2) * rows + r), v3 = __ldcg(part + (k + 3) * rows + r);
+    a += (v0.x + v1.x) + (v2.x + v3.x);
+    b += (v0.y + v1.y) + (v2.y + v3.y);
+  }
+  for (; k < slabs; ++k) {
+    const float2 v0 = __ldcg(part + k * rows + r);
+    a += v0.x;
+    b += v0.y;
+  }
+  const float mean = a * inv_c;
+  float var = b * inv_c - mean * mean;
+  var = var > 0.f ? var : 0.f;
+  stats[r] = make_float2(mean, rsqrtf(var + eps));
+}
+}  // namespace lvd
+
+extern "C" int lvd_ln_rowstats(const void* lnstat_partial, int32_t slabs, int64_t rows, int32_t channels, float eps,
+                               void* stats_f32, void* stream) {
+  LVD_REQUIRE(lnstat_partial && stats_f32 && slabs >= 1 && channels == slabs * 32, "lvd_ln_rowstats: bad arguments");
+  if (rows <= 0) return LVD_OK;
+  ln_rowstats_kernel<<<static_cast<unsigned>((rows + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const float2*>(lnstat_partial), slabs, rows, 1.0f / channels, eps, static_cast<float2*>(stats_f32));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   LVD_CHECK_CUDA(cudaGetLastError());
   return LVD_OK;

@@ -64,6 +64,11 @@ class UNetEngine:
             wi, bi = repack.geglu_interleave(g(p + ".ff.net.0.proj.weight"), g(p + ".ff.net.0.proj.bias"))
             d["ff1"] = LayerWeights(w=wi, b=bi)
             d["ff2"] = lin(p + ".ff.net.2")
+            # LayerNorm folded into the linear that consumes it (ops.ln_fold; models/attention.py:126-170)
+            d["qkv1_ln"] = ops.ln_fold(d["qkv1"], None, d["norm1"].w, d["norm1"].b)
+            k2 = "q2" if cross else "qkv2"
+            d[k2 + "_ln"] = ops.ln_fold(d[k2], None, d["norm2"].w, d["norm2"].b)
+            d["ff1_ln"] = ops.ln_fold(wi, bi, d["norm3"].w, d["norm3"].b)
             f = p + ".fuser"
             if (f + ".linear.weight") in sd:  # GatedSelfAttentionDense (models/attention.py:26-60)
                 fwi, fbi = repack.geglu_interleave(g(f + ".ff.net.0.proj.weight"), g(f + ".ff.net.0.proj.bias"))
@@ -214,25 +219,33 @@ class UNetEngine:
         h = ops.linear(h, P.l2.w, P.l2.b, act=ops.ACT_SILU)
         return ops.linear(h, P.l4.w, P.l4.b)
 
+    @staticmethod
+    def _ln_linear(t, norm, w, b, folded, **kw):
+        """linear(LayerNorm(t)): on the raw t with the LayerNorm folded into the weight when t's producer left its row
+        statistics, through the LayerNorm kernel otherwise."""
+        st = ops.ln_rowstats(t)
+        if st is not None:
+            return ops.linear(t, folded.w, ln=(st, folded), **kw)
+        return ops.linear(ops.layernorm(t, norm.w, norm.b), w, b, **kw)
+
     def _block(self, B, t, *, heads, spatial, n_img, hw, batch, frames, ctx_kv=None, key=None, capture=None,
                objs=None):
         c = t.shape[1]
-        n1 = ops.layernorm(t, B.norm1.w, B.norm1.b)
         packed = (not spatial) and frames % 8 == 0 and frames <= 32
         fm2sm = ("fm2sm", batch, frames, hw) if packed else None
         sm2fm = ("sm2fm", batch, frames, hw) if packed else None
-        qkv = ops.linear(n1, B.qkv1, row_map=fm2sm)
+        qkv = self._ln_linear(t, B.norm1, B.qkv1, None, B.qkv1_ln, row_map=fm2sm)
         if spatial:
             a = ops.attention(qkv, qkv, heads=heads, nz=n_img, s_q=hw, s_k=hw, k_col0=c, v_col0=2 * c)
         else:
             a = ops.attention(qkv, qkv, heads=heads, nz=batch, temporal=True, frames=frames, hw=hw, k_col0=c,
                               v_col0=2 * c, packed=packed)
-        t = ops.linear(a, B.out1.w, B.out1.b, residual=t, row_map=sm2fm)
-        if spatial and objs is not None and "fuser" in B and self.fuser_enabled:
+        fused = spatial and objs is not None and "fuser" in B and self.fuser_enabled
+        t = ops.linear(a, B.out1.w, B.out1.b, residual=t, row_map=sm2fm, ln_emit=not fused)
+        if fused:
             t = self._fuser(B.fuser, t, objs, heads=heads, n_img=n_img, hw=hw)
-        n2 = ops.layernorm(t, B.norm2.w, B.norm2.b)
         if spatial:
-            q = ops.linear(n2, B.q2)
+            q = self._ln_linear(t, B.norm2, B.q2, None, B.q2_ln)
             kv = ops.linear(ctx_kv, B.kv2)
             extra = {}
             if capture is not None:
@@ -240,19 +253,18 @@ class UNetEngine:
             a = ops.attention(q, kv, heads=heads, nz=n_img, s_q=hw, s_k=ctx_kv.shape[0] // batch, k_col0=0, v_col0=c,
                               kv_z_div=frames, **extra)
         else:
-            qkv = ops.linear(n2, B.qkv2, row_map=fm2sm)
+            qkv = self._ln_linear(t, B.norm2, B.qkv2, None, B.qkv2_ln, row_map=fm2sm)
             a = ops.attention(qkv, qkv, heads=heads, nz=batch, temporal=True, frames=frames, hw=hw, k_col0=c,
                               v_col0=2 * c, packed=packed)
-        t = ops.linear(a, B.out2.w, B.out2.b, residual=t, row_map=sm2fm if not spatial else None)
-        n3 = ops.layernorm(t, B.norm3.w, B.norm3.b)
-        gg = ops.linear(n3, B.ff1.w, B.ff1.b, act=ops.ACT_GEGLU)
+        t = ops.linear(a, B.out2.w, B.out2.b, residual=t, row_map=sm2fm if not spatial else None, ln_emit=True)
+        gg = self._ln_linear(t, B.norm3, B.ff1.w, B.ff1.b, B.ff1_ln, act=ops.ACT_GEGLU)
         return ops.linear(gg, B.ff2.w, B.ff2.b, residual=t)
 
     def _transformer(self, T, x, *, spatial, n_img, hw, batch, frames, ctx_kv=None, key=None, capture=None,
                      out=None, objs=None):
         samples = n_img if spatial else batch
         t = ops.groupnorm(x, samples, T.norm.w, T.norm.b, 1e-6, silu=False)
-        t = ops.linear(t, T.proj_in.w, T.proj_in.b)
+        t = ops.linear(t, T.proj_in.w, T.proj_in.b, ln_emit=True)
         heads = t.shape[1] // self.cfg["attention_head_dim"]
         t = self._block(T.block, t, heads=heads, spatial=spatial, n_img=n_img, hw=hw, batch=batch, frames=frames,
                         ctx_kv=ctx_kv, key=key, capture=capture, objs=objs)

@@ -147,7 +147,7 @@ def _box_for_gn(dims, gn, sample_axis, per_sample):
     return free, None
 
 
-# ---- GroupNorm statistics from the producing GEMM's epilogue (lvd_gemm gn_partial -> lvd_gn_finalize ->
+# ---- GroupNorm statistics from the producing GEMM's epilogue (lvd_gemm gn_partial ->
 # lvd_groupnorm_apply): a conv whose output feeds a GroupNorm is launched with `gn=(samples, groups)`; its epilogue
 # leaves per-warp partial sums in a zero-state buffer and the output tensor carries a handle; `groupnorm` on that
 # tensor then skips its statistics pass.  LVD_GN_EPILOGUE=0 switches the path off (A/B).
@@ -181,6 +181,63 @@ def gn_reset(dev):
         _gn_pending[dev] = None
         if dev in _gn_part:
             _gn_part[dev].zero_()
+
+
+# ---- LayerNorm folded into the linear that consumes it (lvd_gemm ln_stats / lnstat_partial, lvd_ln_rowstats):
+#   LN(x) @ W.T + b  =  rstd * (x @ (gamma o W).T - mean * colsum) + (W @ beta + b)
+# the producer of x (a linear with ln_emit=True) leaves per-row {sum, sum of squares} per 32-column slab, ln_rowstats
+# folds them into {mean, rstd}, and the consumer runs on the raw x: the LayerNorm pass over the tensor disappears.
+# LVD_LN_FOLD=0 switches the path off (A/B).
+LN_FOLD = _os.environ.get("LVD_LN_FOLD", "1") != "0"
+_ln_part = {}
+_ln_stats = {}
+_ln_gen = {}  # per (device, buffer): emissions so far -- a handle is valid only until the next producer reuses the buffer
+
+
+class LnFolded:
+    """w [N, K] fp16 = gamma o W;  cs [N] fp32 = row sums of the ROUNDED w;  lb [N] fp32 = W @ beta + bias."""
+    __slots__ = ("w", "cs", "lb")
+
+
+def ln_fold(w, bias, gamma, beta):
+    f = LnFolded()
+    wf = w.float()
+    f.w = (wf * gamma.float()[None, :]).half().contiguous()
+    f.cs = f.w.float().sum(1).contiguous()
+    f.lb = (wf @ beta.float()).contiguous()
+    if bias is not None:
+        f.lb = (f.lb + bias.float()).contiguous()
+    return f
+
+
+def _ln_part_buffer(dev, floats2):
+    dev = torch.device(dev)
+    key = (dev, int(floats2))
+    buf = _ln_part.get(key)
+    if buf is None:
+        buf = torch.empty((int(floats2), 2), dtype=torch.float32, device=dev)
+        _ln_part[key] = buf
+    return buf
+
+
+def ln_rowstats(x, eps=1e-5):
+    """{mean, rstd} per row of x [rows, C] from the partial statistics its producer left (linear(..., ln_emit=True));
+    None when x carries none (the caller then runs the LayerNorm kernel)."""
+    h = getattr(x, "_lvd_ln", None)
+    if h is None or not LN_FOLD:
+        return None
+    part, slabs, rows, ptr, gen = h
+    if ptr != x.data_ptr() or x.shape[0] != rows or x.shape[1] != slabs * 32 or _ln_gen.get(part.data_ptr()) != gen:
+        return None
+    key = (x.device, rows)
+    stats = _ln_stats.get(key)
+    if stats is None:
+        stats = torch.empty((rows, 2), dtype=torch.float32, device=x.device)
+        _ln_stats[key] = stats
+    with _Timed("layernorm", 0.0, 8.0 * rows * (slabs + 1), "ln_rowstats r%d c%d" % (rows, slabs * 32)):
+        _lib.check(_lib.lib().lvd_ln_rowstats(part.data_ptr(), slabs, rows, slabs * 32, float(eps), stats.data_ptr(),
+                                              _stream()), "ln_rowstats")
+    return stats
 
 
 def _gn_plan(out_dims, a_box, out_row_stride, samples, groups, n):
@@ -219,7 +276,8 @@ def _gn_plan(out_dims, a_box, out_row_stride, samples, groups, n):
 
 def gemm_raw(*, a, a_dims, a_strides, a_box, taps, k_per_tap, w, n, out, out_dims, out_row_stride,
              rv_stride=(0, 0, 0, 0), bias=None, act=ACT_NONE, rowvec=None, gamma=1.0, residual=None,
-             b_mn_major=False, block_n=None, ldb=None, b_k_tap_stride=0, b_n_tap_stride=0, gn=None):
+             b_mn_major=False, block_n=None, ldb=None, b_k_tap_stride=0, b_n_tap_stride=0, gn=None, ln=None,
+             ln_emit=False):
     d = GemmDesc()
     d.a = a.data_ptr()
     for i in range(5):
@@ -277,6 +335,24 @@ def gemm_raw(*, a, a_dims, a_strides, a_box, taps, k_per_tap, w, n, out, out_dim
             h.slots, h.rows_per_sample, h.buf = slots, rps, buf
             out._lvd_gn = h
             _gn_pending[dev] = h
+    if ln is not None:  # LayerNorm folded into this linear: (stats [rows] {mean, rstd}, colsum, bias, A-row strides)
+        stats, cs, lb, strides = ln
+        assert bias is None and residual is None and rowvec is None and gamma == 1.0 and len(taps) == 1
+        assert cs.dtype == torch.float32 and lb.dtype == torch.float32 and cs.numel() == n and lb.numel() == n
+        d.ln_stats, d.ln_colsum, d.ln_bias = stats.data_ptr(), cs.data_ptr(), lb.data_ptr()
+        for i in range(4):
+            d.ln_row_stride[i] = int(strides[i])
+    if ln_emit and LN_FOLD and act != ACT_GEGLU:
+        rows_total = 1
+        for v in out_dims:
+            rows_total *= int(v)
+        part = _ln_part_buffer(out.device, (n // 32) * rows_total)
+        d.lnstat_partial, d.lnstat_rows = part.data_ptr(), rows_total
+        for i in range(4):
+            d.lnstat_row_stride[i] = int(out_row_stride[i])
+        gen = _ln_gen.get(part.data_ptr(), 0) + 1
+        _ln_gen[part.data_ptr()] = gen
+        out._lvd_ln = (part, n // 32, rows_total, out.data_ptr(), gen)
     if PROF is not None:
         m = 1
         for v in out_dims:
@@ -298,9 +374,11 @@ def _alloc_out(rows, n, like):
 
 
 def linear(x, w, bias=None, *, act=ACT_NONE, residual=None, gamma=1.0, out=None, rowvec=None, rows_per_vec=0,
-           b_mn_major=False, n=None, row_map=None):
+           b_mn_major=False, n=None, row_map=None, ln=None, ln_emit=False):
     """out = epilogue(x @ w.T).  x [rows, K]; w [N, K] (or [K, N] when b_mn_major).  GEGLU expects the
-    value/gate-interleaved weight produced by `repack.geglu_interleave` and returns N/2 columns."""
+    value/gate-interleaved weight produced by `repack.geglu_interleave` and returns N/2 columns.
+    ln_emit: the epilogue also leaves the row statistics of `out` for a LayerNorm folded into the next linear
+    (`ln_rowstats(out)`); ln = (stats, LnFolded): x is the RAW LayerNorm input, w the folded weight (`ln_fold`)."""
     _check_act(x, "x")
     rows, k = x.shape
     if n is None:
@@ -340,9 +418,13 @@ def linear(x, w, bias=None, *, act=ACT_NONE, residual=None, gamma=1.0, out=None,
         a_strides = (1, ld, ld * rows_per_vec, big, big)
         a_box = (64, bx[0], bx[1], 1, 1)
         out_dims, ors, rv = (rows_per_vec, rows // rows_per_vec, 1, 1), (1, rows_per_vec, 0, 0), (0, 1, 0, 0)
+    if ln is not None:
+        stats, folded = ln
+        assert w is folded.w and stats.numel() == 2 * rows
+        ln = (stats, folded.cs, folded.lb, [a_strides[i + 1] // ld if a_dims[i + 1] > 1 else 0 for i in range(4)])
     return gemm_raw(a=x, a_dims=a_dims, a_strides=a_strides, a_box=a_box, taps=[(0, 0, 0, 0, 0)], k_per_tap=k, w=w,
                     n=n, out=out, out_dims=out_dims, out_row_stride=ors, rv_stride=rv, bias=bias, act=act,
-                    rowvec=rowvec, gamma=gamma, residual=residual, b_mn_major=b_mn_major)
+                    rowvec=rowvec, gamma=gamma, residual=residual, b_mn_major=b_mn_major, ln=ln, ln_emit=ln_emit)
 
 
 TAPS_3X3 = [(0, dx, dy, 0, 0) for dy in (-1, 0, 1) for dx in (-1, 0, 1)]
@@ -446,12 +528,11 @@ def groupnorm(x, samples, gamma, beta, eps, *, groups=32, silu=False, out=None, 
         _gn_pending[x.device] = None
         stats = stats_out if stats_out is not None else gn_stats_buffer(samples, x.device, groups)
         with _Timed("groupnorm", 0.0, 2.0 * rows * c * 2, "gn(epilogue stats) s%d r%d c%d" % (samples, rows // samples, c)):
-            _lib.check(_lib.lib().lvd_gn_finalize(h.buf.data_ptr(), samples, h.slots, groups,
-                                                  float(h.rows_per_sample * (c // groups)), float(eps),
-                                                  stats.data_ptr(), _stream()), "gn_finalize")
+            ws = _gn_workspace(x.device, samples, groups)
             _lib.check(_lib.lib().lvd_groupnorm_apply(x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), samples,
                                                       rows // samples, c, groups, gamma.data_ptr(), beta.data_ptr(),
-                                                      1 if silu else 0, stats.data_ptr(), _stream()), "groupnorm_apply")
+                                                      float(eps), 1 if silu else 0, h.buf.data_ptr(), h.slots,
+                                                      ws.data_ptr(), stats.data_ptr(), _stream()), "groupnorm_apply")
         return out
     ws = _gn_workspace(x.device, samples, groups)
     with _Timed("groupnorm", 0.0, 2.0 * rows * c * 2, "gn s%d r%d c%d" % (samples, rows // samples, c)):

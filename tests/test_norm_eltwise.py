@@ -121,7 +121,7 @@ def test_conv_out_tensor_core_path_matches_small_kernel(cuda):
     ("conv2d_res", (48, 10, 18, 1280), 2),
 ])
 def test_groupnorm_statistics_from_the_gemm_epilogue(cuda, kind, shape, samples):
-    """GroupNorm whose statistics come from the producing conv's epilogue (lvd_gemm gn_partial -> lvd_gn_finalize ->
+    """GroupNorm whose statistics come from the producing conv's epilogue (lvd_gemm gn_partial ->
     lvd_groupnorm_apply) against the two-pass GroupNorm of the same tensor: same statistics up to fp32 summation order,
     bit-reproducible from run to run, and the partial buffer is back at zero afterwards."""
     from lvd_b200 import ops
@@ -159,3 +159,67 @@ def test_groupnorm_statistics_from_the_gemm_epilogue(cuda, kind, shape, samples)
     z, st = outs[0]
     assert ((st - ref_stats).abs() / ref_stats.abs().clamp_min(1e-3)).max().item() < 1e-4
     assert rel_err(z, z_ref) <= 1e-3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("rows,c,n,kind", [
+    (2880, 320, 960, "plain"),        # norm1 -> fused QKV (no bias)
+    (1000, 640, 640, "plain"),        # ragged last row tile
+    (2 * 8 * 160, 320, 960, "fm2sm"),  # temporal transformer: the consumer permutes rows, the producer un-permutes
+    (2304, 320, 2560, "geglu"),       # norm3 -> ff.net.0 (GEGLU)
+    (720, 1280, 10240, "geglu"),
+])
+def test_layernorm_folded_into_the_consuming_linear(cuda, rows, c, n, kind):
+    """LN(x) @ W.T + b computed on the raw x (weight = gamma o W, epilogue rstd * (acc - mean * colsum) + bias') with the
+    row statistics taken from the epilogue of the linear that produced x, against LayerNorm kernel + plain linear and
+    against fp32 torch."""
+    from lvd_b200 import ops, repack
+    assert ops.LN_FOLD
+    g = torch.Generator().manual_seed(11)
+    a = torch.randn((rows, c), generator=g).half().to(cuda)
+    res = (torch.randn((rows, c), generator=g) * 2 + 0.7).half().to(cuda)  # rows with a mean well away from 0
+    wp = (torch.randn((c, c), generator=g) * 0.05).half().to(cuda)
+    bp = (torch.randn(c, generator=g) * 0.1).half().to(cuda)
+    gamma = (1 + 0.2 * torch.randn(c, generator=g)).half().to(cuda)
+    beta = (0.2 * torch.randn(c, generator=g)).half().to(cuda)
+    w = (torch.randn((n, c), generator=g) * 0.05).half().to(cuda)
+    b = (torch.randn(n, generator=g) * 0.1).half().to(cuda) if kind == "geglu" else None
+    act = ops.ACT_NONE
+    if kind == "geglu":
+        w, b = repack.geglu_interleave(w, b)
+        act = ops.ACT_GEGLU
+    batch, frames, hw = 2, 8, 160
+    sm2fm = ("sm2fm", batch, frames, hw) if kind == "fm2sm" else None
+    fm2sm = ("fm2sm", batch, frames, hw) if kind == "fm2sm" else None
+    # producer: x = a @ wp.T + bp + res, emitting the row statistics of x
+    x_plain = ops.linear(a, wp, bp, residual=res, row_map=sm2fm)
+    x = ops.linear(a, wp, bp, residual=res, row_map=sm2fm, ln_emit=True)
+    assert torch.equal(x, x_plain)
+    stats = ops.ln_rowstats(x)
+    assert stats is not None
+    xf = x.float()
+    mean_ref = xf.mean(1)
+    rstd_ref = 1.0 / torch.sqrt(xf.var(1, unbiased=False) + 1e-5)
+    assert (stats[:, 0] - mean_ref).abs().max().item() < 2e-5 * (1 + mean_ref.abs().max().item())
+    assert ((stats[:, 1] - rstd_ref).abs() / rstd_ref).max().item() < 1e-4
+    folded = ops.ln_fold(w, b, gamma, beta)
+    y = ops.linear(x, folded.w, act=act, row_map=fm2sm, ln=(stats, folded))
+    y_two = ops.linear(ops.layernorm(x, gamma, beta), w, b, act=act, row_map=fm2sm)
+    # fp32 reference of the reference's own op order (LayerNorm, then the linear) on the same fp16 x
+    ln = F.layer_norm(xf, (c,), gamma.float(), beta.float(), 1e-5)
+    ref_rows = ln
+    if kind == "fm2sm":
+        ref_rows = ln.reshape(batch, frames, hw, c).permute(0, 2, 1, 3).reshape(rows, c)
+    if kind == "geglu":
+        # fp32 GEGLU on the interleaved weight: every block of 256 columns = [128 value | 128 gate]
+        z = ref_rows @ w.float().t() + b.float()
+        zz = z.reshape(rows, n // 256, 2, 128)
+        ref = (zz[:, :, 0] * F.gelu(zz[:, :, 1])).reshape(rows, n // 2)
+    else:
+        ref = ref_rows @ w.float().t()
+    e_fold, e_two = rel_err(y, ref), rel_err(y_two, ref)
+    print("[ln fold %s rows=%d c=%d n=%d] folded-vs-fp32 %.3e   LN-kernel+linear-vs-fp32 %.3e" % (kind, rows, c, n, e_fold, e_two))
+    assert e_fold <= max(1.2 * e_two, 6e-4)
+    # a second producer into the same statistics buffer invalidates the first tensor's handle (no stale statistics)
+    x2 = ops.linear(a, wp, bp, residual=res, row_map=sm2fm, ln_emit=True)
+    assert ops.ln_rowstats(x) is None and ops.ln_rowstats(x2) is not None
