@@ -16,6 +16,7 @@ Gradients are carried multiplied by GRAD_SCALE in fp16 and un-scaled in the fina
 import torch
 
 from . import ops, repack
+from .engine import UNetEngine
 from .utils.guidance import build_slots_batch, energy_options, map_energy, padded_slot_count
 from .utils.utils import get_hw_from_attn_dim
 
@@ -87,10 +88,10 @@ class GuidanceGraph:
     def _block_fwd(self, B, t, *, heads, spatial, n_img, hw, batch, frames, ctx_kv, tok_cols, want_tok, dense=False):
         c = t.shape[1]
         ctx = Ctx(t0=t, heads=heads, spatial=spatial, n_img=n_img, hw=hw, batch=batch, frames=frames)
-        n1 = ops.layernorm(t, B.norm1.w, B.norm1.b)
+        ln_linear = UNetEngine._ln_linear  # LayerNorm folded into the consuming linear (engine.py)
         fm2sm = None if spatial else ("fm2sm", batch, frames, hw)
         sm2fm = None if spatial else ("sm2fm", batch, frames, hw)
-        qkv = ops.linear(n1, B.qkv1, row_map=fm2sm)
+        qkv = ln_linear(t, B.norm1, B.qkv1, None, B.qkv1_ln, row_map=fm2sm)
         if spatial:
             lse = torch.empty((n_img, heads, hw), dtype=torch.float32, device=self.dev)
             a = ops.attention(qkv, qkv, heads=heads, nz=n_img, s_q=hw, s_k=hw, k_col0=c, v_col0=2 * c, lse=lse)
@@ -99,11 +100,10 @@ class GuidanceGraph:
             a = ops.attention(qkv, qkv, heads=heads, nz=batch, temporal=True, packed=True, frames=frames, hw=hw,
                               k_col0=c, v_col0=2 * c)
         ctx["qkv1"] = qkv
-        t1 = ops.linear(a, B.out1.w, B.out1.b, residual=t, row_map=sm2fm)
+        t1 = ops.linear(a, B.out1.w, B.out1.b, residual=t, row_map=sm2fm, ln_emit=True)
         ctx["t1"] = t1
-        n2 = ops.layernorm(t1, B.norm2.w, B.norm2.b)
         if spatial:
-            q = ops.linear(n2, B.q2)
+            q = ln_linear(t1, B.norm2, B.q2, None, B.q2_ln)
             kv = ops.linear(ctx_kv, B.kv2)
             p_tok = p_full = None
             s_k = ctx_kv.shape[0] // batch
@@ -116,14 +116,13 @@ class GuidanceGraph:
                                tok_cols_dev=tok_cols if p_tok is not None else None)
             ctx.update(q2=q, kv2=kv, p_tok=p_tok, p_full=p_full, s_k=s_k)
         else:
-            qkv2 = ops.linear(n2, B.qkv2, row_map=fm2sm)
+            qkv2 = ln_linear(t1, B.norm2, B.qkv2, None, B.qkv2_ln, row_map=fm2sm)
             a2 = ops.attention(qkv2, qkv2, heads=heads, nz=batch, temporal=True, packed=True, frames=frames, hw=hw,
                                k_col0=c, v_col0=2 * c)
             ctx["qkv2"] = qkv2
-        t2 = ops.linear(a2, B.out2.w, B.out2.b, residual=t1, row_map=sm2fm)
+        t2 = ops.linear(a2, B.out2.w, B.out2.b, residual=t1, row_map=sm2fm, ln_emit=True)
         ctx["t2"] = t2
-        n3 = ops.layernorm(t2, B.norm3.w, B.norm3.b)
-        pre = ops.linear(n3, B.ff1.w, B.ff1.b)  # un-fused GEGLU: the adjoint needs the pre-activation
+        pre = ln_linear(t2, B.norm3, B.ff1.w, B.ff1.b, B.ff1_ln)  # un-fused GEGLU: the adjoint needs the pre-activation
         gg = ops.geglu(pre)
         ctx["pre"] = pre
         t3 = ops.linear(gg, B.ff2.w, B.ff2.b, residual=t2)
@@ -169,7 +168,7 @@ class GuidanceGraph:
         samples = n_img if spatial else batch
         st = ops.gn_stats_buffer(samples, self.dev)
         g = ops.groupnorm(x, samples, T.norm.w, T.norm.b, 1e-6, silu=False, stats_out=st)
-        t0 = ops.linear(g, T.proj_in.w, T.proj_in.b)
+        t0 = ops.linear(g, T.proj_in.w, T.proj_in.b, ln_emit=True)
         heads = t0.shape[1] // self.cfg["attention_head_dim"]
         t1, bctx = self._block_fwd(T.block, t0, heads=heads, spatial=spatial, n_img=n_img, hw=hw, batch=batch,
                                    frames=frames, ctx_kv=ctx_kv, tok_cols=tok_cols, want_tok=want_tok, dense=dense)
