@@ -106,6 +106,10 @@ typedef struct lvd_gemm_desc {
   void* lnstat_partial;
   int64_t lnstat_rows;
   int32_t lnstat_row_stride[4];
+  /* Optional fp32 copy of `bias` (the same n values, exactly converted): the specialised epilogues then add it without
+   * converting 32 halves per row and slab -- these epilogues bound the short-K linears (K = 320 / 640).  NULL = read
+   * the fp16 bias. */
+  const void* bias_f32;
 } lvd_gemm_desc;
 
 int lvd_gemm(const lvd_gemm_desc* d, void* stream);

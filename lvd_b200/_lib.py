@@ -50,6 +50,7 @@ class GemmDesc(ctypes.Structure):
         ("lnstat_partial", ctypes.c_void_p),
         ("lnstat_rows", ctypes.c_int64),
         ("lnstat_row_stride", ctypes.c_int32 * 4),
+        ("bias_f32", ctypes.c_void_p),
     ]
 
 

@@ -35,6 +35,7 @@ struct GemmArgs {
   CUtensorMap map_res;  // same geometry over the residual
   long long ld_rowvec;
   const __half* bias;
+  const float* bias32;  // optional fp32 copy of bias (same values): the lean epilogues skip the conversions
   const __half* rowvec;
   const __half* residual;
   int box[4];
@@ -75,15 +76,23 @@ struct GemmArgs {
   int lnstat_stride[4];
 };
 
-// Timeline tracing for tools/trace_gemm.py (LVD_GEMM_DEBUG bit 6): CTA 0 appends (event << 48 | globaltimer ns).
+// Tuning aids (tools/diag_gemm_k320.py, perf_gemm_sweep.py, trace_gemm.py) exist only in builds with
+// LVD_EXTRA_NVCC_FLAGS=-DLVD_GEMM_DEBUG_BITS: the LVD_GEMM_DEBUG environment bits switch parts of the kernel off, bit 6
+// makes CTA 0 append (event << 48 | globaltimer ns) to g_trace.  Release builds carry none of these branches.
 __device__ unsigned long long g_trace[8192];
 __device__ unsigned int g_trace_n;
+#ifdef LVD_GEMM_DEBUG_BITS
+#define LVD_DBG(g, bit) (((g).debug & (bit)) != 0)
 __device__ __forceinline__ void trace_event(const GemmArgs& g, unsigned ev) {
   if ((g.debug & 64) && blockIdx.x == 0) {
     const unsigned i = atomicAdd(&g_trace_n, 1u);
     if (i < 8192) g_trace[i] = (static_cast<unsigned long long>(ev) << 48) | (globaltimer_ns() & 0xFFFFFFFFFFFFull);
   }
 }
+#else
+#define LVD_DBG(g, bit) false
+__device__ __forceinline__ void trace_event(const GemmArgs&, unsigned) {}
+#endif
 
 // Per-warp phase profile of the epilogue (build with LVD_EXTRA_NVCC_FLAGS=-DLVD_GEMM_PHASE_PROF; tools/phase_gemm.py):
 // clock64 deltas accumulated in registers, dumped into g_trace[warp * 16 + phase] by CTA 0 at kernel end.
@@ -149,10 +158,33 @@ __device__ __forceinline__ uint4 pack8(const float* v) {
   return u;
 }
 
+__device__ __forceinline__ uint32_t pack2h(float a, float b) {
+  const __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+__device__ __forceinline__ uint32_t hadd2_u32(uint32_t a, uint32_t b) {
+  const __half2 r = __hadd2(*reinterpret_cast<const __half2*>(&a), *reinterpret_cast<const __half2*>(&b));
+  return *reinterpret_cast<const uint32_t*>(&r);
+}
+// erf-GELU as in gelu_erf_f (Abramowitz-Stegun 7.1.26 tail h(|v|)), finished as max(v, 0) - |v| h: two instructions
+// instead of select + subtract + multiply
+__device__ __forceinline__ float gelu_erf_lean(float v) {
+  const float a = fabsf(v);
+  const float t = fast_rcp(fmaf(0.23164189f, a, 1.0f));
+  float p = fmaf(0.5307027145f, t, -0.7265760135f);
+  p = fmaf(p, t, 0.7107068705f);
+  p = fmaf(p, t, -0.142248368f);
+  p = fmaf(p, t, 0.127414796f);
+  const float h = (p * t) * fast_exp2((a * a) * -0.72134752f);
+  return fmaf(-a, h, fmaxf(v, 0.f));
+}
+
 // kCtas == 2: the CTA pair of a 2-CTA cluster works on one 256-row tile (tcgen05 cta_group::2).  Each CTA stages its
 // own 128-row A tile and HALF of the B tile, the leader's MMA warp issues M=256 instructions that read both CTAs'
 // shared memory, and each CTA's TMEM receives (and its epilogue warps drain) its own 128 accumulator rows.
-template <int kCtas, int kEpi>
+// kFeat: which output statistics the epilogue emits -- a compile-time choice for the specialised epilogues (bit 0 =
+// LayerNorm row statistics, bit 1 = GroupNorm partial sums), -1 = decided at run time (kEpiGeneric).
+template <int kCtas, int kEpi, int kFeat>
 __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_constant__ GemmArgs g) {
   extern __shared__ uint8_t smem_raw[];
   // 128-byte swizzle atoms need 1024-byte aligned stage bases
@@ -214,7 +246,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     const int k_tap_stride = g.b_k_tap_stride, n_tap_stride = g.b_n_tap_stride;
     const bool mn_major = g.b_mn_major != 0;
     const uint32_t tx_bytes = static_cast<uint32_t>(kCtas) * static_cast<uint32_t>(g.a_bytes + g.b_bytes);
-    const bool skip_loads = (g.debug & 1) != 0;
+    const bool skip_loads = LVD_DBG(g, 1);
     TileIter it;
     tile_init<kCtas>(g, it, tile0, static_cast<int>(cta_rank));
     for (; it.tile < num_tiles; tile_advance(g, it)) {
@@ -279,7 +311,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       const uint32_t b_lo0 = ((smem_u32(sB) & 0x3FFFFu) >> 4) | ((mn_major ? (8192u >> 4) : 1u) << 16);
       const uint32_t b_kstep = mn_major ? (2048u >> 4) : (32u >> 4);  // 16 k: 16 rows of 128 B / 32 B along the row
       const uint32_t b_stage16 = b_stage_bytes >> 4;
-      const bool skip_mma = (g.debug & 2) != 0;
+      const bool skip_mma = LVD_DBG(g, 2);
       const int kblocks = g.n_taps * g.kb_per_tap;
       for (int tile = tile0; tile < num_tiles; tile += g.tile_step) {
         if (lane == 0) trace_event(g, 2);  // MMA: waiting for the accumulator
@@ -338,14 +370,15 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     const int r = q * 32 + lane;
     const bool geglu = kEpi == kEpiGeglu || kEpi == kEpiLnGeglu || (kEpi == kEpiGeneric && g.act == 2);
     const bool has_ln = kEpi == kEpiLnBias || kEpi == kEpiLnGeglu;
-    const bool has_lnstat = g.lnstat_part != nullptr;
+    const bool has_lnstat = kFeat < 0 ? g.lnstat_part != nullptr : (kFeat & 1) != 0;
     const bool has_res = kEpi == kEpiResidual || (kEpi == kEpiGeneric && g.residual != nullptr);
     const bool has_rowvec = kEpi == kEpiGeneric && g.rowvec != nullptr;
     const bool has_gamma = kEpi == kEpiGeneric && g.gamma != 1.0f;
     const bool has_silu = kEpi == kEpiGeneric && g.act == 1;
     const bool has_gelu = kEpi == kEpiGeneric && g.act == 3;
     const __half* const bias = g.bias;
-    const bool has_gn = g.gn_part != nullptr;
+    const bool has_gn = kFeat < 0 ? g.gn_part != nullptr : (kFeat & 2) != 0;
+    constexpr bool kLean = kEpi != kEpiGeneric;  // no run-time feature switches inside the slab loop
     int j[4];
     if (has_rowvec || has_gn || has_ln || has_lnstat) {
       int t = r;
@@ -382,7 +415,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     long long ph_last = clock64();
 #endif
     auto issue_res = [&](const TileIter& ti, int sl_, uint32_t seq_) {  // elected lane: TMA-load a residual slab
-      if (g.debug & 8) {  // tuning aid: no residual traffic
+      if (LVD_DBG(g, 8)) {  // tuning aid: no residual traffic
         mbar_arrive(&my_res_full[seq_ & 1]);
         return;
       }
@@ -450,6 +483,176 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         LVD_PH(1);
         uint4 packed[4];
         float ls1 = 0.f, ls2 = 0.f;  // has_lnstat: sum / sum of squares of this row's 32 staged values
+        if constexpr (kLean) {
+          // ---- specialised epilogues: straight-line code, no feature switches.  The accumulator goes back to the MMA
+          // warp right after this warp's last TMEM read of the tile has landed in registers.
+          uint32_t pk[16];  // the row's 32 outputs as packed fp16 pairs
+          [[maybe_unused]] float fv[32];  // ... and in fp32 (LayerNorm row statistics of a residual-free output)
+          if constexpr (kEpi == kEpiGeglu || kEpi == kEpiLnGeglu) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {  // two 16-column halves: value and gate columns are both live
+              const int ucol = sl * 32 + h * 16;          // tile-relative value column; its gate is n_half further
+              const int tcol = it.nt * block_n + ucol;    // the same column of the interleaved weight / bias
+              uint32_t ra[16], rg[16];
+              tmem_ld16(taddr + ucol, ra);
+              tmem_ld16(taddr + n_half + ucol, rg);
+              float val[16], gate[16];
+              if constexpr (kEpi == kEpiLnGeglu) {
+                const float4* cv4 = reinterpret_cast<const float4*>(g.ln_cs + tcol);
+                const float4* bv4 = reinterpret_cast<const float4*>(g.ln_bias + tcol);
+                const float4* cg4 = reinterpret_cast<const float4*>(g.ln_cs + tcol + n_half);
+                const float4* bg4 = reinterpret_cast<const float4*>(g.ln_bias + tcol + n_half);
+                // the first four columns' constants travel under the TMEM read
+                const float4 cv0 = __ldg(cv4), bv0 = __ldg(bv4), cg0 = __ldg(cg4), bg0 = __ldg(bg4);
+                tmem_ld_wait();
+                if (h == 1 && sl + 4 >= nslabs) release_acc();
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const float4 c1 = i == 0 ? cv0 : __ldg(cv4 + i), b1 = i == 0 ? bv0 : __ldg(bv4 + i);
+                  const float4 c2 = i == 0 ? cg0 : __ldg(cg4 + i), b2 = i == 0 ? bg0 : __ldg(bg4 + i);
+                  const float c1a[4] = {c1.x, c1.y, c1.z, c1.w}, b1a[4] = {b1.x, b1.y, b1.z, b1.w};
+                  const float c2a[4] = {c2.x, c2.y, c2.z, c2.w}, b2a[4] = {b2.x, b2.y, b2.z, b2.w};
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    val[4 * i + e] = fmaf(ln_rstd, fmaf(-ln_mean, c1a[e], __uint_as_float(ra[4 * i + e])), b1a[e]);
+                    gate[4 * i + e] = fmaf(ln_rstd, fmaf(-ln_mean, c2a[e], __uint_as_float(rg[4 * i + e])), b2a[e]);
+                  }
+                }
+              } else if (g.bias32) {
+                const float4* bv4 = reinterpret_cast<const float4*>(g.bias32 + tcol);
+                const float4* bg4 = reinterpret_cast<const float4*>(g.bias32 + tcol + n_half);
+                float4 bv[4], bg[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  bv[i] = __ldg(bv4 + i);
+                  bg[i] = __ldg(bg4 + i);
+                }
+                tmem_ld_wait();
+                if (h == 1 && sl + 4 >= nslabs) release_acc();
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  val[4 * i] = __uint_as_float(ra[4 * i]) + bv[i].x;
+                  val[4 * i + 1] = __uint_as_float(ra[4 * i + 1]) + bv[i].y;
+                  val[4 * i + 2] = __uint_as_float(ra[4 * i + 2]) + bv[i].z;
+                  val[4 * i + 3] = __uint_as_float(ra[4 * i + 3]) + bv[i].w;
+                  gate[4 * i] = __uint_as_float(rg[4 * i]) + bg[i].x;
+                  gate[4 * i + 1] = __uint_as_float(rg[4 * i + 1]) + bg[i].y;
+                  gate[4 * i + 2] = __uint_as_float(rg[4 * i + 2]) + bg[i].z;
+                  gate[4 * i + 3] = __uint_as_float(rg[4 * i + 3]) + bg[i].w;
+                }
+              } else {
+                float bv[16], bg[16];
+                if (bias) {
+                  unpack8(*reinterpret_cast<const uint4*>(bias + tcol), *reinterpret_cast<float(*)[8]>(&bv[0]));
+                  unpack8(*reinterpret_cast<const uint4*>(bias + tcol + 8), *reinterpret_cast<float(*)[8]>(&bv[8]));
+                  unpack8(*reinterpret_cast<const uint4*>(bias + tcol + n_half), *reinterpret_cast<float(*)[8]>(&bg[0]));
+                  unpack8(*reinterpret_cast<const uint4*>(bias + tcol + n_half + 8),
+                          *reinterpret_cast<float(*)[8]>(&bg[8]));
+                } else {
+#pragma unroll
+                  for (int i = 0; i < 16; ++i) bv[i] = bg[i] = 0.f;
+                }
+                tmem_ld_wait();
+                if (h == 1 && sl + 4 >= nslabs) release_acc();
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                  val[i] = __uint_as_float(ra[i]) + bv[i];
+                  gate[i] = __uint_as_float(rg[i]) + bg[i];
+                }
+              }
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                pk[8 * h + i] = pack2h(val[2 * i] * gelu_erf_lean(gate[2 * i]), val[2 * i + 1] * gelu_erf_lean(gate[2 * i + 1]));
+            }
+          } else {
+            uint32_t rv[32];
+            tmem_ld32(taddr + sl * 32, rv);
+            if constexpr (kEpi == kEpiLnBias) {
+              const float4* cs4 = reinterpret_cast<const float4*>(g.ln_cs + gcol);
+              const float4* lb4 = reinterpret_cast<const float4*>(g.ln_bias + gcol);
+              float4 c0[2], b0[2];  // the first eight columns' constants travel under the TMEM read
+#pragma unroll
+              for (int i = 0; i < 2; ++i) {
+                c0[i] = __ldg(cs4 + i);
+                b0[i] = __ldg(lb4 + i);
+              }
+              tmem_ld_wait();
+              if (sl + 4 >= nslabs) release_acc();
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float4 c = i < 2 ? c0[i & 1] : __ldg(cs4 + i), b = i < 2 ? b0[i & 1] : __ldg(lb4 + i);
+                fv[4 * i] = fmaf(ln_rstd, fmaf(-ln_mean, c.x, __uint_as_float(rv[4 * i])), b.x);
+                fv[4 * i + 1] = fmaf(ln_rstd, fmaf(-ln_mean, c.y, __uint_as_float(rv[4 * i + 1])), b.y);
+                fv[4 * i + 2] = fmaf(ln_rstd, fmaf(-ln_mean, c.z, __uint_as_float(rv[4 * i + 2])), b.z);
+                fv[4 * i + 3] = fmaf(ln_rstd, fmaf(-ln_mean, c.w, __uint_as_float(rv[4 * i + 3])), b.w);
+              }
+            } else if (g.bias32) {
+              const float4* b4 = reinterpret_cast<const float4*>(g.bias32 + gcol);
+              float4 b[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) b[i] = __ldg(b4 + i);
+              tmem_ld_wait();
+              if (sl + 4 >= nslabs) release_acc();
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                fv[4 * i] = __uint_as_float(rv[4 * i]) + b[i].x;
+                fv[4 * i + 1] = __uint_as_float(rv[4 * i + 1]) + b[i].y;
+                fv[4 * i + 2] = __uint_as_float(rv[4 * i + 2]) + b[i].z;
+                fv[4 * i + 3] = __uint_as_float(rv[4 * i + 3]) + b[i].w;
+              }
+            } else if (bias) {
+              uint4 bh[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) bh[i] = *reinterpret_cast<const uint4*>(bias + gcol + 8 * i);
+              tmem_ld_wait();
+              if (sl + 4 >= nslabs) release_acc();
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                float t[8];
+                unpack8(bh[i], t);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) fv[8 * i + e] = __uint_as_float(rv[8 * i + e]) + t[e];
+              }
+            } else {
+              tmem_ld_wait();
+              if (sl + 4 >= nslabs) release_acc();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) fv[i] = __uint_as_float(rv[i]);
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) pk[i] = pack2h(fv[2 * i], fv[2 * i + 1]);
+            if constexpr (kEpi == kEpiResidual) {
+              // out = fp16(linear) + residual, one fp16 addition like the reference's `hidden_states + residual`; the
+              // residual slab was TMA-loaded into this slab's own staging buffer
+              mbar_wait(&my_res_full[seq & 1], (seq >> 1) & 1u);
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                const uint4 t = *reinterpret_cast<const uint4*>(obuf + row_off + ((static_cast<uint32_t>(c) ^ sw) << 4));
+                pk[4 * c] = hadd2_u32(pk[4 * c], t.x);
+                pk[4 * c + 1] = hadd2_u32(pk[4 * c + 1], t.y);
+                pk[4 * c + 2] = hadd2_u32(pk[4 * c + 2], t.z);
+                pk[4 * c + 3] = hadd2_u32(pk[4 * c + 3], t.w);
+              }
+              if (has_lnstat) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                  const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&pk[i]));
+                  fv[2 * i] = f.x;
+                  fv[2 * i + 1] = f.y;
+                }
+              }
+            }
+            if (has_lnstat) {  // (of the unrounded values when there is no residual: a 1e-5 relative change of rstd)
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                ls1 += fv[i];
+                ls2 = fmaf(fv[i], fv[i], ls2);
+              }
+            }
+          }
+#pragma unroll
+          for (int c = 0; c < 4; ++c) packed[c] = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+        } else {
 #pragma unroll
         for (int h = 0; h < 2; ++h) {  // two 16-column halves: bounds the live registers
           const int ucol = sl * 32 + h * 16;  // tile-relative accumulator column
@@ -567,10 +770,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
             }
           }
         }
+        }
         if (has_lnstat && valid)
           g.lnstat_part[static_cast<long long>(gcol >> 5) * g.lnstat_rows + lnstat_row] = make_float2(ls1, ls2);
         LVD_PH(2);
-        if (sl + 4 >= nslabs) release_acc();  // this warp's last TMEM reads of the tile have completed
+        if (!kLean && sl + 4 >= nslabs) release_acc();  // this warp's last TMEM reads of the tile have completed
         if (leader_warp && lane == 0) trace_event(g, 16 + grp * 16 + 2);  // slab math done
 #pragma unroll
         for (int cidx = 0; cidx < 4; ++cidx)
@@ -626,7 +830,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         if (leader_warp && lane == 0) trace_event(g, 16 + grp * 16 + 4);  // group barrier passed
         if (leader_warp) {
           if (elect_one_sync()) {  // elect.sync is deterministic: the same lane owns the bulk async-groups throughout
-            if (!(g.debug & 4))  // tuning aid: bit 2 drops the output stores
+            if (!LVD_DBG(g, 4))  // tuning aid: bit 2 drops the output stores
               tma_store_5d(&g.map_out, obuf, gcol, it.t0 * g.box[0], it.t1 * g.box[1], it.t2 * g.box[2],
                            it.t3 * g.box[3]);
             bulk_commit_group();
@@ -807,6 +1011,7 @@ static int launch_gemm(const lvd_gemm_desc* d, cudaStream_t stream) {
     g.debug = env ? atoi(env) : 0;
   }
   g.bias = static_cast<const __half*>(d->bias);
+  g.bias32 = static_cast<const float*>(d->bias_f32);
   g.rowvec = static_cast<const __half*>(d->rowvec);
   g.residual = static_cast<const __half*>(d->residual);
   g.ld_rowvec = d->ld_rowvec;
@@ -849,16 +1054,40 @@ static int launch_gemm(const lvd_gemm_desc* d, cudaStream_t stream) {
   if (plain && d->act == 2 && !d->residual) epi = kEpiGeglu;
   if (plain && d->act == 0) epi = d->residual ? kEpiResidual : kEpiBias;
   if (g.ln_stats) epi = d->act == 2 ? kEpiLnGeglu : kEpiLnBias;
+  // statistics emitted by the epilogue: compile-time for the specialised epilogues (only Bias / Residual carry them)
+  int feat = 0;
+  if (g.lnstat_part) feat = 1;
+  if (g.gn_part) feat = 2;
+  LVD_REQUIRE(!(g.lnstat_part && g.gn_part), "lvd_gemm: lnstat_partial and gn_partial are mutually exclusive");
+  if (feat != 0 && epi != kEpiBias && epi != kEpiResidual) {
+    LVD_REQUIRE(!g.ln_stats, "lvd_gemm: a folded LayerNorm cannot emit output statistics");
+    epi = kEpiGeneric;
+  }
+#ifdef LVD_GEMM_DEBUG_BITS
+  if (g.debug & 64) epi = kEpiGeneric;  // the event trace lives in the generic kernel's control flow too
+#endif
   typedef void (*KernelFn)(const GemmArgs);
-  static const KernelFn kernels[2][6] = {
-      {gemm_tc_kernel<1, 0>, gemm_tc_kernel<1, 1>, gemm_tc_kernel<1, 2>, gemm_tc_kernel<1, 3>, gemm_tc_kernel<1, 4>,
-       gemm_tc_kernel<1, 5>},
-      {gemm_tc_kernel<2, 0>, gemm_tc_kernel<2, 1>, gemm_tc_kernel<2, 2>, gemm_tc_kernel<2, 3>, gemm_tc_kernel<2, 4>,
-       gemm_tc_kernel<2, 5>}};
+  // [ctas - 1][slot]: 0 generic | 1..3 bias (none, lnstat, gn) | 4..6 residual (none, lnstat, gn) | 7 geglu |
+  // 8 ln+bias | 9 ln+geglu
+  static const KernelFn kernels[2][10] = {
+      {gemm_tc_kernel<1, kEpiGeneric, -1>, gemm_tc_kernel<1, kEpiBias, 0>, gemm_tc_kernel<1, kEpiBias, 1>,
+       gemm_tc_kernel<1, kEpiBias, 2>, gemm_tc_kernel<1, kEpiResidual, 0>, gemm_tc_kernel<1, kEpiResidual, 1>,
+       gemm_tc_kernel<1, kEpiResidual, 2>, gemm_tc_kernel<1, kEpiGeglu, 0>, gemm_tc_kernel<1, kEpiLnBias, 0>,
+       gemm_tc_kernel<1, kEpiLnGeglu, 0>},
+      {gemm_tc_kernel<2, kEpiGeneric, -1>, gemm_tc_kernel<2, kEpiBias, 0>, gemm_tc_kernel<2, kEpiBias, 1>,
+       gemm_tc_kernel<2, kEpiBias, 2>, gemm_tc_kernel<2, kEpiResidual, 0>, gemm_tc_kernel<2, kEpiResidual, 1>,
+       gemm_tc_kernel<2, kEpiResidual, 2>, gemm_tc_kernel<2, kEpiGeglu, 0>, gemm_tc_kernel<2, kEpiLnBias, 0>,
+       gemm_tc_kernel<2, kEpiLnGeglu, 0>}};
+  int slot = 0;
+  if (epi == kEpiBias) slot = 1 + feat;
+  if (epi == kEpiResidual) slot = 4 + feat;
+  if (epi == kEpiGeglu) slot = 7;
+  if (epi == kEpiLnBias) slot = 8;
+  if (epi == kEpiLnGeglu) slot = 9;
   static bool attr_set = false;
   if (!attr_set) {
     for (int i = 0; i < 2; ++i)
-      for (int j = 0; j < 6; ++j)
+      for (int j = 0; j < 10; ++j)
         LVD_CHECK_CUDA(cudaFuncSetAttribute(kernels[i][j], cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
     attr_set = true;
   }
@@ -875,7 +1104,7 @@ static int launch_gemm(const lvd_gemm_desc* d, cudaStream_t stream) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  LVD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kernels[ctas - 1][epi], g));
+  LVD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kernels[ctas - 1][slot], g));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   LVD_CHECK_CUDA(cudaGetLastError());
   return LVD_OK;

@@ -274,6 +274,22 @@ def _gn_plan(out_dims, a_box, out_row_stride, samples, groups, n):
     return tps, (gw + 30) // 32 + 1, rps
 
 
+_bias32 = {}
+
+
+def _bias_f32(bias):
+    """fp32 copy of a bias vector for the specialised epilogues of lvd_gemm (weights are persistent: converted once and
+    kept, keyed by the storage address; the fp16 tensor is held so that the address cannot be recycled)."""
+    key = (bias.data_ptr(), bias.numel(), bias.device)
+    hit = _bias32.get(key)
+    if hit is None or hit[0]._version != hit[2]:
+        if len(_bias32) > 4096:
+            _bias32.clear()
+        hit = (bias, bias.float().contiguous(), bias._version)
+        _bias32[key] = hit
+    return hit[1].data_ptr()
+
+
 def gemm_raw(*, a, a_dims, a_strides, a_box, taps, k_per_tap, w, n, out, out_dims, out_row_stride,
              rv_stride=(0, 0, 0, 0), bias=None, act=ACT_NONE, rowvec=None, gamma=1.0, residual=None,
              b_mn_major=False, block_n=None, ldb=None, b_k_tap_stride=0, b_n_tap_stride=0, gn=None, ln=None,
@@ -305,6 +321,8 @@ def gemm_raw(*, a, a_dims, a_strides, a_box, taps, k_per_tap, w, n, out, out_dim
         d.rv_stride[i] = int(rv_stride[i])
         d.out_row_stride[i] = int(out_row_stride[i])
     d.bias = bias.data_ptr() if bias is not None else None
+    d.bias_f32 = _bias_f32(bias) if bias is not None and rowvec is None and gamma == 1.0 and act in (ACT_NONE, ACT_GEGLU) \
+        else None
     d.rowvec = rowvec.data_ptr() if rowvec is not None else None
     d.residual = residual.data_ptr() if residual is not None else None
     d.out = out.data_ptr()
