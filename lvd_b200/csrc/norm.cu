@@ -345,6 +345,7 @@ __global__ void __launch_bounds__(320, 2) gn_stream_stats_kernel(const __half* _
   }
 }
 
+template <bool kSilu>
 __global__ void __launch_bounds__(320, 2) gn_stream_apply_kernel(const __half* __restrict__ x, long long ld_x,
                                                                   __half* __restrict__ y, long long ld_y,
                                                                   long long rows_per_sample, int C, int G, int chunks,
@@ -352,7 +353,7 @@ __global__ void __launch_bounds__(320, 2) gn_stream_apply_kernel(const __half* _
                                                                   float n,
                                                                   float eps, float* __restrict__ stats,
                                                                   const __half* __restrict__ gamma,
-                                                                  const __half* __restrict__ beta, int silu) {
+                                                                  const __half* __restrict__ beta) {
   extern __shared__ uint4 s_dyn[];
   __shared__ uint64_t s_full[kGnStages];
   __shared__ float s_mean[64], s_rstd[64];
@@ -434,15 +435,25 @@ __global__ void __launch_bounds__(320, 2) gn_stream_apply_kernel(const __half* _
     const uint4* buf = s_dyn + static_cast<long long>(stage) * T * vpr;
     if (rsub < rpp) {
       for (int r = rsub; r < rows; r += rpp) {
-        float t[8];
-        unpack8v(buf[static_cast<long long>(r) * vpr + v], t);
+        // The normalised value is rounded to fp16 (the reference's GroupNorm output tensor) with the PACKED conversion
+        // and SiLU then works on that value: two MUFU operations per element (ex2, rcp) and no scalar F2F -- the
+        // single-value conversions share the MUFU pipe, which bounds this pass.
+        const uint4 u = buf[static_cast<long long>(r) * vpr + v];
+        const __half2* h = reinterpret_cast<const __half2*>(&u);
+        uint4 o4;
+        __half2* oh = reinterpret_cast<__half2*>(&o4);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          float o = round_h(fmaf(t[i], sc[i], sh[i]));
-          if (silu) o = __fdividef(o, 1.0f + __expf(-o));
-          t[i] = o;
+        for (int i = 0; i < 4; ++i) {
+          const float2 f = __half22float2(h[i]);
+          __half2 yh = __floats2half2_rn(fmaf(f.x, sc[2 * i], sh[2 * i]), fmaf(f.y, sc[2 * i + 1], sh[2 * i + 1]));
+          if (kSilu) {
+            const float2 o = __half22float2(yh);
+            yh = __floats2half2_rn(o.x * fast_rcp(1.0f + fast_exp2(o.x * -1.4426950408889634f)),
+                                   o.y * fast_rcp(1.0f + fast_exp2(o.y * -1.4426950408889634f)));
+          }
+          oh[i] = yh;
         }
-        st8(yb + (static_cast<long long>(it) * T + r) * ld_y, t);
+        *reinterpret_cast<uint4*>(yb + (static_cast<long long>(it) * T + r) * ld_y) = o4;
       }
     }
     __syncthreads();
@@ -623,7 +634,8 @@ extern "C" int lvd_groupnorm(const void* x, int64_t ld_x, void* y, int64_t ld_y,
     static bool attr2 = false;
     if (!attr2) {
       LVD_CHECK_CUDA(cudaFuncSetAttribute(gn_stream_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
-      LVD_CHECK_CUDA(cudaFuncSetAttribute(gn_stream_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+      LVD_CHECK_CUDA(cudaFuncSetAttribute(gn_stream_apply_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+      LVD_CHECK_CUDA(cudaFuncSetAttribute(gn_stream_apply_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
       attr2 = true;
     }
     if (threads <= 320 && ring_bytes + scratch <= 220 * 1024) {
@@ -631,11 +643,11 @@ extern "C" int lvd_groupnorm(const void* x, int64_t ld_x, void* y, int64_t ld_y,
     gn_stream_stats_kernel<<<sgrid, threads, ring_bytes + scratch, st>>>(
         static_cast<const __half*>(x), ld_x, rows_per_sample, channels, groups, static_cast<int>(schunks), T,
         static_cast<float*>(workspace));
-    gn_stream_apply_kernel<<<sgrid, threads, ring_bytes, st>>>(
+    (silu ? gn_stream_apply_kernel<true> : gn_stream_apply_kernel<false>)<<<sgrid, threads, ring_bytes, st>>>(
         static_cast<const __half*>(x), ld_x, static_cast<__half*>(y), ld_y, rows_per_sample, channels, groups,
         static_cast<int>(schunks), static_cast<int>(schunks), T, static_cast<const float*>(workspace),
         static_cast<float>(rows_per_sample) * (channels / groups), eps, stats, static_cast<const __half*>(gamma),
-        static_cast<const __half*>(beta), silu);
+        static_cast<const __half*>(beta));
     } else {  // very wide rows: register-staged passes
       dim3 grid(static_cast<unsigned>(chunks), static_cast<unsigned>(samples));
       const size_t smem_stats = (static_cast<size_t>(rpp_) + 1) * 2 * channels * sizeof(float);
@@ -730,18 +742,19 @@ extern "C" int lvd_groupnorm_apply(const void* x, int64_t ld_x, void* y, int64_t
               channels);
   static bool attr = false;
   if (!attr) {
-    LVD_CHECK_CUDA(cudaFuncSetAttribute(gn_stream_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    LVD_CHECK_CUDA(cudaFuncSetAttribute(gn_stream_apply_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+      LVD_CHECK_CUDA(cudaFuncSetAttribute(gn_stream_apply_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     attr = true;
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   dim3 sgrid(static_cast<unsigned>(schunks), static_cast<unsigned>(samples));
   gn_tiles_fold_kernel<<<dim3(kGnFoldParts, static_cast<unsigned>(samples)), 1024 / groups * groups, 0, st>>>(
       static_cast<float*>(gn_partial), slots, groups, static_cast<float*>(workspace));
-  gn_stream_apply_kernel<<<sgrid, threads, ring_bytes, st>>>(
+  (silu ? gn_stream_apply_kernel<true> : gn_stream_apply_kernel<false>)<<<sgrid, threads, ring_bytes, st>>>(
       static_cast<const __half*>(x), ld_x, static_cast<__half*>(y), ld_y, rows_per_sample, channels, groups,
       static_cast<int>(schunks), kGnFoldParts, T, static_cast<const float*>(workspace),
       static_cast<float>(rows_per_sample) * (channels / groups), eps, static_cast<float*>(stats_out),
-      static_cast<const __half*>(gamma), static_cast<const __half*>(beta), silu);
+      static_cast<const __half*>(gamma), static_cast<const __half*>(beta));
   g_launches.fetch_add(2, std::memory_order_relaxed);
   LVD_CHECK_CUDA(cudaGetLastError());
   return LVD_OK;
