@@ -110,6 +110,11 @@ typedef struct lvd_gemm_desc {
    * converting 32 halves per row and slab -- these epilogues bound the short-K linears (K = 320 / 640).  NULL = read
    * the fp16 bias. */
   const void* bias_f32;
+  /* 1: weight-resident walk (one tap, K-major B whose block_n x K tile fits next to >= 3 A stages; silently the
+   * streaming walk otherwise): the persistent walk keeps every CTA (pair) on one n-tile, whose B tile is staged once
+   * for the whole launch, and only A streams -- for the short-K linears, which are bound by operand delivery from L2.
+   * 0: both operands stream through the ring. */
+  int32_t weight_resident;
 } lvd_gemm_desc;
 
 int lvd_gemm(const lvd_gemm_desc* d, void* stream);

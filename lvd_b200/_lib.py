@@ -51,6 +51,7 @@ class GemmDesc(ctypes.Structure):
         ("lnstat_rows", ctypes.c_int64),
         ("lnstat_row_stride", ctypes.c_int32 * 4),
         ("bias_f32", ctypes.c_void_p),
+        ("weight_resident", ctypes.c_int32),
     ]
 
 

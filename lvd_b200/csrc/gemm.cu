@@ -52,6 +52,9 @@ struct GemmArgs {
   // persistent tile walk: tile += tile_step; its n-tile / row-tile digits advance by precomputed mixed-radix steps
   int tile_step, step_nt;
   int step_lo[4], step_hi[4];
+  // weight-resident mode: the persistent walk advances by a multiple of n_tiles_n, so a CTA (pair) keeps ONE n-tile; its B
+  // tile (all k-blocks) is loaded once into b_slots = kblocks slots and only A streams through the ring
+  int b_resident, b_slots;
   int debug;  // tools/perf_gemm_sweep.py: bit 0 = skip the TMA loads, bit 1 = skip the MMAs, bit 2 = skip the output
               // stores, bit 3 = skip the residual loads (results are garbage)
   float gamma;
@@ -189,7 +192,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   extern __shared__ uint8_t smem_raw[];
   // 128-byte swizzle atoms need 1024-byte aligned stage bases
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  const int warp = threadIdx.x >> 5;
+  // warp index as a value ptxas knows to be warp-uniform: the role loops then live in uniform registers
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   const int stages = g.stages;
   const uint32_t cta_rank = kCtas == 2 ? cluster_ctarank() : 0u;
@@ -197,13 +201,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   const uint32_t b_stage_bytes = static_cast<uint32_t>(b_rows) * 128u;
   uint8_t* sA = smem;
   uint8_t* sB = smem + stages * kAStageBytes;
-  uint8_t* sOut = sB + stages * b_stage_bytes;  // output slabs [128 rows][32 cols] fp16: 2 per epilogue group
+  uint8_t* sOut = sB + g.b_slots * b_stage_bytes;  // output slabs [128 rows][32 cols] fp16: 2 per epilogue group
   uint64_t* full = reinterpret_cast<uint64_t*>(sOut + kSlabBufs * kSlabBytes);
   uint64_t* empty = full + stages;
   uint64_t* tfull = empty + stages;
   uint64_t* tempty = tfull + 4;
   uint64_t* res_full = tempty + 4;  // [group][buffer]
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(res_full + kSlabBufs);
+  uint64_t* bres_full = res_full + kSlabBufs;  // weight-resident mode: the CTA's whole B tile has landed
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bres_full + 1);
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < stages; ++i) {
@@ -215,6 +220,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       mbar_init(&tempty[i], 16 * kCtas);  // one arrival per epilogue warp of every CTA of the pair
     }
     for (int i = 0; i < kSlabBufs; ++i) mbar_init(&res_full[i], 1);
+    mbar_init(bres_full, 1);
     fence_barrier_init();
   }
   if (warp == 0 && lane == 0) {
@@ -245,10 +251,29 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     const int n_taps = g.n_taps, kb_per_tap = g.kb_per_tap, block_n = g.block_n;
     const int k_tap_stride = g.b_k_tap_stride, n_tap_stride = g.b_n_tap_stride;
     const bool mn_major = g.b_mn_major != 0;
-    const uint32_t tx_bytes = static_cast<uint32_t>(kCtas) * static_cast<uint32_t>(g.a_bytes + g.b_bytes);
+    const bool resident = g.b_resident != 0;
+    const uint32_t tx_bytes =
+        static_cast<uint32_t>(kCtas) * static_cast<uint32_t>(g.a_bytes + (resident ? 0 : g.b_bytes));
     const bool skip_loads = LVD_DBG(g, 1);
     TileIter it;
     tile_init<kCtas>(g, it, tile0, static_cast<int>(cta_rank));
+    if (resident && it.tile < num_tiles) {
+      // this CTA's n-tile never changes: stage its B tile once (K-major B, one tap)
+      if (elect_one_sync()) {
+        const int ncoord = it.nt * block_n + static_cast<int>(cta_rank) * b_rows;
+        const uint32_t total = static_cast<uint32_t>(kCtas) * static_cast<uint32_t>(g.b_bytes) *
+                               static_cast<uint32_t>(kb_per_tap);
+        if (kCtas == 2) {
+          if (cta_rank == 0) mbar_arrive_expect_tx(bres_full, total);
+          const uint32_t fbar = mapa_shared(smem_u32(bres_full), 0);
+          for (int kb = 0; kb < kb_per_tap; ++kb) tma_load_2d_pair(sB + kb * b_stage_bytes, &g.map_b, fbar, kb * 64, ncoord);
+        } else {
+          mbar_arrive_expect_tx(bres_full, total);
+          for (int kb = 0; kb < kb_per_tap; ++kb) tma_load_2d(sB + kb * b_stage_bytes, &g.map_b, bres_full, kb * 64, ncoord);
+        }
+      }
+      __syncwarp();
+    }
     for (; it.tile < num_tiles; tile_advance(g, it)) {
       if (lane == 0) trace_event(g, 1);  // producer: tile start
       const int c0 = it.t0 * g.box[0], c1_ = it.t1 * g.box[1], c2_ = it.t2 * g.box[2], c3_ = it.t3 * g.box[3];
@@ -271,7 +296,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
               if (cta_rank == 0) mbar_arrive_expect_tx(&full[stage], tx_bytes);
               const uint32_t fbar = mapa_shared(smem_u32(&full[stage]), 0);
               tma_load_5d_pair(adst, &g.map_a, fbar, o0 + kb * 64, c1, c2, c3, c4);
-              if (!mn_major) {
+              if (resident) {
+              } else if (!mn_major) {
                 tma_load_2d_pair(bdst, &g.map_b, fbar, kcoord, ncoord);
               } else {
                 for (int ch = 0; ch < b_rows / 64; ++ch)
@@ -280,7 +306,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
             } else {
               mbar_arrive_expect_tx(&full[stage], tx_bytes);
               tma_load_5d(adst, &g.map_a, &full[stage], o0 + kb * 64, c1, c2, c3, c4);
-              if (!mn_major) {
+              if (resident) {
+              } else if (!mn_major) {
                 tma_load_2d(bdst, &g.map_b, &full[stage], kcoord, ncoord);
               } else {
                 for (int ch = 0; ch < b_rows / 64; ++ch)
@@ -313,6 +340,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       const uint32_t b_stage16 = b_stage_bytes >> 4;
       const bool skip_mma = LVD_DBG(g, 2);
       const int kblocks = g.n_taps * g.kb_per_tap;
+      const bool resident = g.b_resident != 0;
+      if (resident && tile0 < num_tiles) {
+        mbar_wait(bres_full, 0);
+        tc_fence_after();
+      }
       for (int tile = tile0; tile < num_tiles; tile += g.tile_step) {
         if (lane == 0) trace_event(g, 2);  // MMA: waiting for the accumulator
         mbar_wait(&tempty[acc], acc_phase ^ 1u);
@@ -324,7 +356,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
           tc_fence_after();
           if (elect_one_sync()) {
             const uint32_t a_lo = a_lo0 + static_cast<uint32_t>(stage) * (kAStageBytes >> 4);
-            const uint32_t b_lo = b_lo0 + static_cast<uint32_t>(stage) * b_stage16;
+            const uint32_t b_lo = b_lo0 + static_cast<uint32_t>(resident ? kb : stage) * b_stage16;
             if (!skip_mma) {
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
@@ -964,7 +996,18 @@ static int launch_gemm(const lvd_gemm_desc* d, cudaStream_t stream) {
   g.n_acc = 512 / d->block_n > 4 ? 4 : 512 / d->block_n;
   // grid and the mixed-radix step of the persistent tile walk
   const int max_units = pair ? num_sms() / 2 : num_sms();
-  const int units = g.num_tiles < max_units ? g.num_tiles : max_units;  // CTAs, or CTA pairs
+  int units = g.num_tiles < max_units ? g.num_tiles : max_units;  // CTAs, or CTA pairs
+  // Weight-resident mode (linears with a short K): with a walk step that is a multiple of n_tiles_n every CTA (pair) stays
+  // on one n-tile, keeps that B tile in shared memory for the whole launch and streams only A -- the operand traffic from
+  // L2 (the bound of the K = 320 / 640 linears: ~10.7 TB/s chip-wide) drops from (A + B) to A per tile.
+  const int kblocks_total = d->n_taps * (d->k_per_tap / 64);
+  const int b_res_bytes = kblocks_total * b_rows * 128;
+  int stages_res = (kSmemLimit - 1024 - kBarrierBytes - kSlabBufs * kSlabBytes - b_res_bytes) / kAStageBytes;
+  if (stages_res > 8) stages_res = 8;
+  const bool resident = d->weight_resident == 1 && d->n_taps == 1 && !d->b_mn_major && stages_res >= 3 &&
+                        g.n_tiles_n <= units;
+  if (resident) units = units / g.n_tiles_n * g.n_tiles_n;
+  g.b_resident = resident ? 1 : 0;
   g.tile_step = units;
   g.step_nt = units % g.n_tiles_n;
   for (int hi = 0; hi < 2; ++hi) {
@@ -1001,11 +1044,13 @@ static int launch_gemm(const lvd_gemm_desc* d, cudaStream_t stream) {
   const int n_slabs_smem = kSlabBufs;
   int stages = (kSmemLimit - 1024 - kBarrierBytes - n_slabs_smem * kSlabBytes) / stage_bytes;
   if (stages > 8) stages = 8;
+  if (resident) stages = stages_res;
   {  // tuning aid (tools/perf_gemm_sweep.py): cap the ring depth
     static const char* env = getenv("LVD_GEMM_STAGES");
     if (env && atoi(env) >= 2 && atoi(env) < stages) stages = atoi(env);
   }
   g.stages = stages;
+  g.b_slots = resident ? kblocks_total : stages;
   {
     static const char* env = getenv("LVD_GEMM_DEBUG");
     g.debug = env ? atoi(env) : 0;
@@ -1048,7 +1093,7 @@ static int launch_gemm(const lvd_gemm_desc* d, cudaStream_t stream) {
     LVD_REQUIRE(d->act != 2 && g.lnstat_rows >= 1, "lvd_gemm: lnstat_partial needs lnstat_rows and no GEGLU");
   g.idesc = make_idesc_f16(128u * ctas, static_cast<uint32_t>(d->block_n), 0, d->b_mn_major ? 1u : 0u);
 
-  const int smem_bytes = 1024 + stages * stage_bytes + n_slabs_smem * kSlabBytes + kBarrierBytes;
+  const int smem_bytes = 1024 + stages * kAStageBytes + g.b_slots * g.b_bytes + n_slabs_smem * kSlabBytes + kBarrierBytes;
   const bool plain = d->rowvec == nullptr && d->gamma == 1.0f;
   int epi = kEpiGeneric;
   if (plain && d->act == 2 && !d->residual) epi = kEpiGeglu;

@@ -64,6 +64,19 @@ def _check_act(t, name="tensor"):
         raise ValueError(f"{name}: row stride must be a multiple of 8 and base 16-byte aligned")
 
 
+FORCE_WEIGHT_RESIDENT = None  # tools: 0 / 1 overrides weight_resident_policy
+import os as _os0
+
+WEIGHT_RESIDENT_ON = _os0.environ.get("LVD_WEIGHT_RESIDENT", "0") != "0"
+WEIGHT_RESIDENT_MAX_K = int(_os0.environ.get("LVD_WEIGHT_RESIDENT_MAX_K", "640"))
+
+
+def weight_resident_policy(n_taps, k, n, mn_major):
+    """Whether an lvd_gemm launch asks for the weight-resident walk (include/lvd_b200.h): the short-K linears, whose
+    operand delivery from L2 is the bound.  LVD_WEIGHT_RESIDENT=0 switches it off (A/B)."""
+    return WEIGHT_RESIDENT_ON and n_taps == 1 and not mn_major and k <= WEIGHT_RESIDENT_MAX_K
+
+
 def pick_block_n(n, act=ACT_NONE, mn_major=False, m_tiles=None, k_contract=None):
     """Tile width of an lvd_gemm launch.  Wide tiles move fewer operand bytes per FLOP, but the kernel is
     persistent -- one CTA (or CTA pair) per SM walks the tile list -- so what counts is the number of tile ROUNDS the
@@ -333,6 +346,10 @@ def gemm_raw(*, a, a_dims, a_strides, a_box, taps, k_per_tap, w, n, out, out_dim
     d.b_k_tap_stride = int(b_k_tap_stride)
     d.b_n_tap_stride = int(b_n_tap_stride)
     d.cta_pair = int(FORCE_CTA_PAIR)
+    if FORCE_WEIGHT_RESIDENT is not None:
+        d.weight_resident = int(FORCE_WEIGHT_RESIDENT)
+    else:
+        d.weight_resident = 1 if weight_resident_policy(len(taps), int(k_per_tap), int(n), b_mn_major) else 0
     if gn is not None and GN_EPILOGUE and act != ACT_GEGLU and len(taps) * int(k_per_tap) >= 960:
         # (the 5-k-block linears are bound by their epilogue: the extra column-sum pass would cost them more than the
         # statistics pass it saves)

@@ -39,7 +39,7 @@ def test_struct_layout_matches_header_sizes():
     from lvd_b200 import _lib
     # sizes implied by the header's field lists (LP64): guards against silent ABI drift
     assert ctypes.sizeof(_lib.GemmDesc) == 8 + 40 + 40 + 20 + 4 + 4 + 27 * 20 + 8 + 4 + 4 + 8 + 4 + 4 + 16 + 16 + 32 \
-        + 8 * 4 + 8 * 3 + 4 + 4 + 4 + 4 + 8 + 4 * 4 + 8 * 3 + 4 * 4 + 8 + 8 + 4 * 4 + 8
+        + 8 * 4 + 8 * 3 + 4 + 4 + 4 + 4 + 8 + 4 * 4 + 8 * 3 + 4 * 4 + 8 + 8 + 4 * 4 + 8 + 8
     assert ctypes.sizeof(_lib.AttnDesc) == 8 * 6 + 8 * 3 + 8 * 2 + 8 * 2 + 8 + 4 * 2 + 4 * 4 + 4 * 3 + 4 + 64 + 4 + 4 + 8
     assert ctypes.sizeof(_lib.EnergyDesc) == 8 * 6 + 4 * 7 + 4 * 7 + 4 * 4 + 4 * 3 + 4 + 8 * 2  # p_frames fills the pad
 
