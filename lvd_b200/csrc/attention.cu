@@ -50,7 +50,8 @@ struct AttnArgs {
 
 __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid_constant__ AttnArgs g) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // (warp index through a shuffle: ptxas then knows it is warp-uniform and keeps the role loops in uniform registers)
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   uint8_t* sQ = smem;
   uint8_t* sK = smem + kTile;      // 2 stages
   uint8_t* sV = smem + 3 * kTile;  // 2 stages
@@ -430,7 +431,8 @@ constexpr float kRescaleLog2 = 8.0f;
 
 __global__ void __launch_bounds__(kSelfThreads, 2) attention_self_kernel(const __grid_constant__ AttnArgs g) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // (warp index through a shuffle: ptxas then knows it is warp-uniform and keeps the role loops in uniform registers)
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   uint8_t* sQ = smem;
   uint8_t* sK = smem + kTile;      // 2 stages
   uint8_t* sV = smem + 3 * kTile;  // 2 stages
@@ -674,7 +676,8 @@ constexpr int kTile64 = 64 * 128;
 __global__ void __launch_bounds__(kSelfThreads, 2) attention_self2_kernel(const __grid_constant__ AttnArgs g,
                                                                            const __grid_constant__ CUtensorMap map_kv64) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // (warp index through a shuffle: ptxas then knows it is warp-uniform and keeps the role loops in uniform registers)
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   uint8_t* sQ = smem;                              // 128 x 64 halves
   uint8_t* sK = smem + kTile;                      // kKvStages x (64 keys x 64 halves)
   uint8_t* sV = smem + kTile + kKvStages * kTile64;

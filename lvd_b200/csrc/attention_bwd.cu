@@ -50,7 +50,8 @@ __device__ __forceinline__ void store_chunk16(uint8_t* tile_row, int r, int col,
 // ------------------------------------------------------------------------------------------------ dQ
 __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_dq_kernel(const __grid_constant__ AttnBwdArgs g) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // (warp index through a shuffle: ptxas then knows it is warp-uniform and keeps the role loops in uniform registers)
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   uint8_t* sQ = smem;
   uint8_t* sDO = smem + kT;
   uint8_t* sK = smem + 2 * kT;   // 2 stages
@@ -221,7 +222,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_dq_kernel(const __gri
 // ------------------------------------------------------------------------------------------------ dK, dV
 __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_dkdv_kernel(const __grid_constant__ AttnBwdArgs g) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // (warp index through a shuffle: ptxas then knows it is warp-uniform and keeps the role loops in uniform registers)
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   uint8_t* sK = smem;
   uint8_t* sV = smem + kT;
   uint8_t* sQ = smem + 2 * kT;   // 2 stages
@@ -438,7 +440,8 @@ constexpr int kBwdSmallThreads = 192;  // 2 control warps + 4 compute warps (one
 
 __global__ void __launch_bounds__(kBwdSmallThreads, 1) attn_bwd_small_kernel(const __grid_constant__ AttnBwdSmallArgs g) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // (warp index through a shuffle: ptxas then knows it is warp-uniform and keeps the role loops in uniform registers)
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   uint8_t* sQ = smem;
   uint8_t* sDO = smem + kT;
   uint8_t* sK = smem + 2 * kT;

@@ -69,7 +69,8 @@ __global__ void __launch_bounds__(kTbWarps * 32) temporal_attn_bwd_kernel(
     const __half* __restrict__ qkv, long long ld_qkv, int q_col0, int k_col0, int v_col0, const __half* __restrict__ d_o,
     long long ld_do, __half* __restrict__ d_qkv, long long ld_dqkv, long long n_seq, int heads, int F, float scale) {
   extern __shared__ __half sm_h[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // (warp index through a shuffle: ptxas then knows it is warp-uniform and keeps the role loops in uniform registers)
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int tile = 32 * kPad;
   __half* sQ = sm_h + warp * 4 * tile;
   __half* sK = sQ + tile;
@@ -173,7 +174,8 @@ __global__ void __launch_bounds__(kCbWarps * 32) cross_attn_bwd_kernel(const Cro
   __half* sK = sm_c;
   __half* sV = sK + sk_pad * kPad;
   float* wbuf = reinterpret_cast<float*>(sV + sk_pad * kPad);  // per warp: q[64], do[64], ds[sk_pad]
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // (warp index through a shuffle: ptxas then knows it is warp-uniform and keeps the role loops in uniform registers)
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int h = blockIdx.x, z = blockIdx.z;
   const int zk = z / g.kv_z_div;
   for (int r = threadIdx.x >> 3; r < sk_pad; r += (kCbWarps * 32) >> 3) {

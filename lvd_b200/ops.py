@@ -80,10 +80,10 @@ def weight_resident_policy(n_taps, k, n, mn_major):
 def pick_block_n(n, act=ACT_NONE, mn_major=False, m_tiles=None, k_contract=None):
     """Tile width of an lvd_gemm launch.  Wide tiles move fewer operand bytes per FLOP, but the kernel is
     persistent -- one CTA (or CTA pair) per SM walks the tile list -- so what counts is the number of tile ROUNDS the
-    slowest SM runs: at M = 4320 / 2160 / 1080 rows (the 10x18 and 5x9 levels, and every level of the B = 1 guidance
-    pass) 256-wide tiles leave the last round half empty and 160-wide tiles are 13-16 % faster
-    (tools/perf_gemm_blockn.py).  Cost model: rounds x (block_n + 180), the per-tile time fitted to the measured
-    160- vs 256-wide rates."""
+    slowest SM runs.  Cost model: rounds x (block_n + 78), the per-tile time fitted to the measured 128- / 160- /
+    256-wide rates of the current kernel (tools/perf_gemm_blockn.py: M = 8640, N = 1280 conv3x3 190 / 175 / 184 us,
+    model 1.08 : 1 : 1.05; the constant was 180 before the role loops moved to uniform registers, which made the
+    narrower tiles relatively cheaper)."""
     if act == ACT_GEGLU:
         return 2 * GEGLU_HALF
     cands = [bn for bn in ((256, 128, 64) if mn_major else (256, 160, 128, 64)) if n % bn == 0]
@@ -99,7 +99,7 @@ def pick_block_n(n, act=ACT_NONE, mn_major=False, m_tiles=None, k_contract=None)
         if bn == 64 and len(cands) > 1 and n > 64:
             continue  # 64-wide tiles never win on these shapes (operand traffic)
         rounds = -(-(rows * (n // bn)) // units)
-        cost = rounds * (bn + 180)
+        cost = rounds * (bn + 78)
         if best is None or cost < best[0]:
             best = (cost, bn)
     return best[1]
