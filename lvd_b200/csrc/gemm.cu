@@ -1108,9 +1108,6 @@ static int launch_gemm(const lvd_gemm_desc* d, cudaStream_t stream) {
     LVD_REQUIRE(!g.ln_stats, "lvd_gemm: a folded LayerNorm cannot emit output statistics");
     epi = kEpiGeneric;
   }
-#ifdef LVD_GEMM_DEBUG_BITS
-  if (g.debug & 64) epi = kEpiGeneric;  // the event trace lives in the generic kernel's control flow too
-#endif
   typedef void (*KernelFn)(const GemmArgs);
   // [ctas - 1][slot]: 0 generic | 1..3 bias (none, lnstat, gn) | 4..6 residual (none, lnstat, gn) | 7 geglu |
   // 8 ln+bias | 9 ln+geglu

@@ -10,6 +10,7 @@
 
 namespace lvd {
 extern std::atomic<long long> g_launches;
+constexpr int kGnApplyCtasPerSm = 3;
 
 __device__ __forceinline__ void ld8(const __half* p, float (&v)[8]) {
   uint4 u = *reinterpret_cast<const uint4*>(p);
@@ -346,7 +347,7 @@ __global__ void __launch_bounds__(320, 2) gn_stream_stats_kernel(const __half* _
 }
 
 template <bool kSilu>
-__global__ void __launch_bounds__(320, 2) gn_stream_apply_kernel(const __half* __restrict__ x, long long ld_x,
+__global__ void __launch_bounds__(320, kGnApplyCtasPerSm) gn_stream_apply_kernel(const __half* __restrict__ x, long long ld_x,
                                                                   __half* __restrict__ y, long long ld_y,
                                                                   long long rows_per_sample, int C, int G, int chunks,
                                                                   int pchunks, int T, const float* __restrict__ partial,
@@ -459,6 +460,27 @@ __global__ void __launch_bounds__(320, 2) gn_stream_apply_kernel(const __half* _
     __syncthreads();
     if (threadIdx.x < 32 && it + kGnStages < st.nit) st.issue(it + kGnStages);
   }
+}
+
+// Geometry of the normalisation pass: kGnApplyCtasPerSm co-resident CTAs per SM (the pass is bound by instruction issue
+// and the MUFU pipe, not by bytes in flight: a third CTA per SM buys more than deeper rings), stages of ~12 KB.
+struct GnApplyPlan {
+  int T;
+  long long chunks;
+  size_t ring_bytes;
+};
+static GnApplyPlan gn_apply_plan(int channels, int threads, int samples, long long rows_per_sample) {
+  const long long row_bytes = 2LL * channels;
+  const int rpp_ = threads / (channels / 8);
+  GnApplyPlan p;
+  p.T = static_cast<int>((12 * 1024) / row_bytes) / rpp_ * rpp_;
+  if (p.T < rpp_) p.T = rpp_;
+  p.chunks = (static_cast<long long>(kGnApplyCtasPerSm) * num_sms()) / samples;  // one wave of co-resident CTAs
+  const long long most = (rows_per_sample + p.T - 1) / p.T;
+  if (p.chunks > most) p.chunks = most;
+  if (p.chunks < 1) p.chunks = 1;
+  p.ring_bytes = static_cast<size_t>(kGnStages) * p.T * row_bytes;
+  return p;
 }
 
 static int gn_threads(int C) {
@@ -643,9 +665,11 @@ extern "C" int lvd_groupnorm(const void* x, int64_t ld_x, void* y, int64_t ld_y,
     gn_stream_stats_kernel<<<sgrid, threads, ring_bytes + scratch, st>>>(
         static_cast<const __half*>(x), ld_x, rows_per_sample, channels, groups, static_cast<int>(schunks), T,
         static_cast<float*>(workspace));
-    (silu ? gn_stream_apply_kernel<true> : gn_stream_apply_kernel<false>)<<<sgrid, threads, ring_bytes, st>>>(
+    const GnApplyPlan ap = gn_apply_plan(channels, threads, samples, rows_per_sample);
+    dim3 agrid(static_cast<unsigned>(ap.chunks), static_cast<unsigned>(samples));
+    (silu ? gn_stream_apply_kernel<true> : gn_stream_apply_kernel<false>)<<<agrid, threads, ap.ring_bytes, st>>>(
         static_cast<const __half*>(x), ld_x, static_cast<__half*>(y), ld_y, rows_per_sample, channels, groups,
-        static_cast<int>(schunks), static_cast<int>(schunks), T, static_cast<const float*>(workspace),
+        static_cast<int>(ap.chunks), static_cast<int>(schunks), ap.T, static_cast<const float*>(workspace),
         static_cast<float>(rows_per_sample) * (channels / groups), eps, stats, static_cast<const __half*>(gamma),
         static_cast<const __half*>(beta));
     } else {  // very wide rows: register-staged passes
@@ -729,15 +753,10 @@ extern "C" int lvd_groupnorm_apply(const void* x, int64_t ld_x, void* y, int64_t
   LVD_REQUIRE(ld_x % 8 == 0 && ld_y % 8 == 0 && samples >= 1 && rows_per_sample >= 1 && slots >= 1,
               "lvd_groupnorm_apply: bad shape");
   const int threads = gn_threads(channels);
-  const long long row_bytes = 2LL * channels;
-  const int rpp_ = threads / (channels / 8);
-  int T = static_cast<int>((15 * 1024) / row_bytes) / rpp_ * rpp_;
-  if (T < rpp_) T = rpp_;
-  long long schunks = (2LL * num_sms()) / samples;
-  const long long most = (rows_per_sample + T - 1) / T;
-  if (schunks > most) schunks = most;
-  if (schunks < 1) schunks = 1;
-  const size_t ring_bytes = static_cast<size_t>(kGnStages) * T * row_bytes;
+  const GnApplyPlan ap = gn_apply_plan(channels, threads, samples, rows_per_sample);
+  const int T = ap.T;
+  const long long schunks = ap.chunks;
+  const size_t ring_bytes = ap.ring_bytes;
   LVD_REQUIRE(threads <= 320 && ring_bytes <= 220 * 1024, "lvd_groupnorm_apply: C=%d too wide for the streaming pass",
               channels);
   static bool attr = false;
