@@ -63,12 +63,14 @@ def test_reference_arm_json_line(monkeypatch):
 
 def test_tile_width_chooser_follows_tile_rounds():
     """ops.pick_block_n (host logic): 256-wide tiles where they fill the persistent grid, 160-wide ones where 256 would
-    leave the last round half empty (M = 4320 / 2160: measured 13-16 % faster, tools/perf_gemm_blockn.py); fixed widths
-    where the epilogue dictates them."""
+    leave the last round half empty (M = 4320 / 2160: measured 13-16 % faster, tools/perf_gemm_blockn.py; since the
+    role loops moved to uniform registers also M = 8640: conv3x3 175 vs 184 us); fixed widths where the epilogue dictates
+    them."""
     from lvd_b200 import ops
     t = lambda m: -(-m // 128)  # noqa: E731
     assert ops.pick_block_n(1280, m_tiles=t(138240), k_contract=1280) == 256
-    assert ops.pick_block_n(1280, m_tiles=t(8640), k_contract=11520) == 256
+    assert ops.pick_block_n(1280, m_tiles=t(34560), k_contract=11520) == 256
+    assert ops.pick_block_n(1280, m_tiles=t(8640), k_contract=11520) == 160
     assert ops.pick_block_n(1280, m_tiles=t(4320), k_contract=11520) == 160
     assert ops.pick_block_n(1280, m_tiles=t(2160), k_contract=3840) == 160
     assert ops.pick_block_n(1280, m_tiles=t(1080), k_contract=1280) in (128, 160)
