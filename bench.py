@@ -460,6 +460,11 @@ def run_gpu(args):
     # ---------------- timed region 2: end to end with host buffers (same public calls; H2D in, D2H out, every step)
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    host_prof = None
+    if os.environ.get("LVD_BENCH_HOST_PROFILE"):  # tuning aid: where the host time of an end-to-end step goes
+        import cProfile
+        host_prof = cProfile.Profile()
+        host_prof.enable()
     f0.record()
     for i in range(args.steps):
         latents = lat_host.to(dev, non_blocking=True)
@@ -468,6 +473,10 @@ def run_gpu(args):
         out_host.copy_(latents, non_blocking=True)
         torch.cuda.current_stream().synchronize()
     f1.record()
+    if host_prof is not None:
+        import pstats
+        host_prof.disable()
+        pstats.Stats(host_prof, stream=sys.stderr).sort_stats("cumulative").print_stats(45)
     barrier()
     ms_e2e = f0.elapsed_time(f1)
     sampler.stop()

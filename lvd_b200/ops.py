@@ -6,6 +6,7 @@ current stream only; all arithmetic happens in liblvd_b200.so.
 """
 import ctypes
 import functools
+import os
 
 import torch
 
@@ -64,11 +65,11 @@ def _check_act(t, name="tensor"):
         raise ValueError(f"{name}: row stride must be a multiple of 8 and base 16-byte aligned")
 
 
-FORCE_WEIGHT_RESIDENT = None  # tools: 0 / 1 overrides weight_resident_policy
-import os as _os0
-
-WEIGHT_RESIDENT_ON = _os0.environ.get("LVD_WEIGHT_RESIDENT", "0") != "0"
-WEIGHT_RESIDENT_MAX_K = int(_os0.environ.get("LVD_WEIGHT_RESIDENT_MAX_K", "640"))
+FORCE_WEIGHT_RESIDENT = None  # tests / tools: 0 / 1 overrides weight_resident_policy
+# measured: no gain on any shape of the step, hence off unless LVD_WEIGHT_RESIDENT=1
+WEIGHT_RESIDENT_ON = os.environ.get("LVD_WEIGHT_RESIDENT", "0") != "0"
+WEIGHT_RESIDENT_MAX_K = int(os.environ.get("LVD_WEIGHT_RESIDENT_MAX_K", "640"))
+BIAS_F32 = True  # hand lvd_gemm an fp32 copy of the bias (tests switch it off to compare with the fp16 read)
 
 
 def weight_resident_policy(n_taps, k, n, mn_major):
@@ -334,8 +335,8 @@ def gemm_raw(*, a, a_dims, a_strides, a_box, taps, k_per_tap, w, n, out, out_dim
         d.rv_stride[i] = int(rv_stride[i])
         d.out_row_stride[i] = int(out_row_stride[i])
     d.bias = bias.data_ptr() if bias is not None else None
-    d.bias_f32 = _bias_f32(bias) if bias is not None and rowvec is None and gamma == 1.0 and act in (ACT_NONE, ACT_GEGLU) \
-        else None
+    d.bias_f32 = _bias_f32(bias) if BIAS_F32 and bias is not None and rowvec is None and gamma == 1.0 and \
+        act in (ACT_NONE, ACT_GEGLU) else None
     d.rowvec = rowvec.data_ptr() if rowvec is not None else None
     d.residual = residual.data_ptr() if residual is not None else None
     d.out = out.data_ptr()

@@ -156,3 +156,52 @@ def test_linear_row_maps(cuda, batch, frames, hw):
     out2 = ops.linear(x, w, residual=res, row_map=("sm2fm", batch, frames, hw))
     ref2 = y.half().float().reshape(batch, hw, frames, n).permute(0, 2, 1, 3).reshape(rows, n) + res.float()
     assert rel_err(out2, ref2) < TOL
+
+
+@pytest.mark.parametrize("rows,n,k,res,geglu", [(1000, 960, 320, False, False), (777, 320, 320, True, False),
+                                                (600, 640, 640, True, False), (515, 2560, 320, False, True)])
+def test_linear_fp32_bias_copy_is_bit_identical(cuda, rows, n, k, res, geglu):
+    """The specialised epilogues read an fp32 copy of the bias (lvd_gemm_desc.bias_f32) instead of converting the fp16
+    vector per row and slab: the same numbers, so the outputs must be bit-identical."""
+    from lvd_b200 import ops, repack
+    x = _rand((rows, k), cuda, seed=41)
+    w = _rand((n, k), cuda, k ** -0.5, seed=42)
+    b = _rand((n,), cuda, seed=43)
+    r_ = _rand((rows, n), cuda, seed=44) if res else None
+    act = ops.ACT_NONE
+    if geglu:
+        w, b = repack.geglu_interleave(w, b)
+        act = ops.ACT_GEGLU
+    try:
+        ops.BIAS_F32 = False
+        a = ops.linear(x, w, b, residual=r_, act=act)
+    finally:
+        ops.BIAS_F32 = True
+    c = ops.linear(x, w, b, residual=r_, act=act)
+    assert torch.equal(a, c)
+    if not geglu:
+        ref = (x.float() @ w.float().t() + b.float()).half().float() + (r_.float() if res else 0.0)
+        assert rel_err(c, ref) < TOL
+
+
+@pytest.mark.parametrize("rows,n,k,res,pair", [(20000, 960, 320, False, 1), (20000, 320, 320, True, 2),
+                                               (9000, 640, 640, True, 2), (9000, 640, 640, False, 1)])
+def test_linear_weight_resident_walk_is_bit_identical(cuda, rows, n, k, res, pair):
+    """lvd_gemm_desc.weight_resident: every CTA (pair) keeps one B tile in shared memory for the whole launch and only
+    A streams; a different tile-to-CTA assignment of the same arithmetic."""
+    from lvd_b200 import ops
+    x = _rand((rows, k), cuda, seed=51)
+    w = _rand((n, k), cuda, k ** -0.5, seed=52)
+    b = _rand((n,), cuda, seed=53)
+    r_ = _rand((rows, n), cuda, seed=54) if res else None
+    try:
+        ops.FORCE_CTA_PAIR = pair
+        ops.FORCE_WEIGHT_RESIDENT = 0
+        a = ops.linear(x, w, b, residual=r_)
+        ops.FORCE_WEIGHT_RESIDENT = 1
+        c = ops.linear(x, w, b, residual=r_)
+    finally:
+        ops.FORCE_CTA_PAIR, ops.FORCE_WEIGHT_RESIDENT = 0, None
+    assert torch.equal(a, c)
+    ref = (x.float() @ w.float().t() + b.float()).half().float() + (r_.float() if res else 0.0)
+    assert rel_err(c, ref) < TOL
