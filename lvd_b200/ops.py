@@ -288,20 +288,16 @@ def _gn_plan(out_dims, a_box, out_row_stride, samples, groups, n):
     return tps, (gw + 30) // 32 + 1, rps
 
 
-_bias32 = {}
-
-
 def _bias_f32(bias):
-    """fp32 copy of a bias vector for the specialised epilogues of lvd_gemm (weights are persistent: converted once and
-    kept, keyed by the storage address; the fp16 tensor is held so that the address cannot be recycled)."""
-    key = (bias.data_ptr(), bias.numel(), bias.device)
-    hit = _bias32.get(key)
-    if hit is None or hit[0]._version != hit[2]:
-        if len(_bias32) > 4096:
-            _bias32.clear()
-        hit = (bias, bias.float().contiguous(), bias._version)
-        _bias32[key] = hit
-    return hit[1].data_ptr()
+    """fp32 copy of a bias vector for the specialised epilogues of lvd_gemm.  The copy hangs on the bias tensor OBJECT
+    (weights are persistent objects: converted once), so it lives exactly as long as the bias does -- a captured CUDA
+    graph that has the copy's address baked in belongs to the same engine as the weight and dies with it.  (A global
+    cache with eviction would free copies that captured graphs still read.)"""
+    hit = getattr(bias, "_lvd_f32", None)
+    if hit is None or hit[1] != bias._version or hit[2] != bias.data_ptr():
+        hit = (bias.float().contiguous(), bias._version, bias.data_ptr())
+        bias._lvd_f32 = hit
+    return hit[0].data_ptr()
 
 
 def gemm_raw(*, a, a_dims, a_strides, a_box, taps, k_per_tap, w, n, out, out_dims, out_row_stride,
