@@ -79,3 +79,21 @@ def test_tile_width_chooser_follows_tile_rounds():
     assert ops.pick_block_n(2560, act=ops.ACT_GEGLU, m_tiles=t(138240), k_contract=320) == 256  # value | gate halves
     assert ops.pick_block_n(1280, mn_major=True, m_tiles=t(138240), k_contract=1280) == 256
     assert ops.pick_block_n(1280) == 256 and ops.pick_block_n(320) == 160        # no shape information: widest divisor
+
+
+def test_fp32_bias_copy_follows_the_bias_tensor():
+    """ops._bias_f32 (host logic): the fp32 copy handed to lvd_gemm's specialised epilogues is converted once per bias
+    tensor object, follows in-place updates (load_state_dict into existing weights) and is not shared between
+    objects -- it must live as long as the bias, because captured CUDA graphs hold its address."""
+    import torch
+    from lvd_b200 import ops
+    b = (torch.arange(16, dtype=torch.float32) / 7).half()
+    p1 = ops._bias_f32(b)
+    assert ops._bias_f32(b) == p1
+    copy = b._lvd_f32[0]
+    assert copy.dtype == torch.float32 and torch.equal(copy, b.float())
+    b.mul_(2)  # in-place update of the weight: a fresh copy
+    ops._bias_f32(b)
+    assert torch.equal(b._lvd_f32[0], b.float())
+    c = b.clone()
+    assert ops._bias_f32(c) != ops._bias_f32(b)
