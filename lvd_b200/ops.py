@@ -293,9 +293,13 @@ def _bias_f32(bias):
     (weights are persistent objects: converted once), so it lives exactly as long as the bias does -- a captured CUDA
     graph that has the copy's address baked in belongs to the same engine as the weight and dies with it.  (A global
     cache with eviction would free copies that captured graphs still read.)"""
+    try:
+        version = bias._version
+    except RuntimeError:  # inference tensors carry no version counter (and cannot be updated in place outside inference mode)
+        version = -1
     hit = getattr(bias, "_lvd_f32", None)
-    if hit is None or hit[1] != bias._version or hit[2] != bias.data_ptr():
-        hit = (bias.float().contiguous(), bias._version, bias.data_ptr())
+    if hit is None or hit[1] != version or hit[2] != bias.data_ptr():
+        hit = (bias.float().contiguous(), version, bias.data_ptr())
         bias._lvd_f32 = hit
     return hit[0].data_ptr()
 
