@@ -23,7 +23,7 @@ constexpr int kThreads = 576;            // 2 control warps + 16 epilogue warps
 constexpr int kSmemLimit = 232448;       // 227 KB
 constexpr int kSlabBytes = 128 * 64;     // epilogue staging slab: 128 rows x 32 halves
 constexpr int kSlabBufs = 8;             // 4 epilogue groups x 2 buffers
-constexpr int kBarrierBytes = 512;       // mbarriers (8+8 ring, 4+4 accumulator, 8 residual) + the TMEM address
+constexpr int kBarrierBytes = 512;       // mbarriers (8+8 ring, 4+4 accumulator, 8 residual, 1 resident B) + the TMEM address
 
 // epilogue specialisations (template parameter): the common cases carry no feature branches in the slab loop
 enum { kEpiGeneric = 0, kEpiBias = 1, kEpiResidual = 2, kEpiGeglu = 3, kEpiLnBias = 4, kEpiLnGeglu = 5 };
